@@ -1,0 +1,188 @@
+// deepfluids_b200 -- extern "C" entry points declared in include/deepfluids_b200.h
+#include <stdarg.h>
+#include <string.h>
+
+#include "dfl_common.cuh"
+
+namespace dfl {
+
+static thread_local char g_err[512] = "";
+static int g_num_sms = 148;
+static bool g_inited = false;
+
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static PFN_encodeTiled g_encode = nullptr;
+
+void set_last_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+int check_cuda(cudaError_t e, const char* what) {
+  if (e == cudaSuccess) return DFL_OK;
+  set_last_error("CUDA error in %s: %s (%s)", what, cudaGetErrorName(e), cudaGetErrorString(e));
+  return DFL_ERR_CUDA;
+}
+
+int num_sms() { return g_num_sms; }
+
+int encode_tensor_map(CUtensorMap* out, CUtensorMapDataType dt, int rank, const void* gaddr, const uint64_t* dims,
+                      const uint64_t* strides_bytes, const uint32_t* box, CUtensorMapSwizzle sw) {
+  if (!g_encode) {
+    set_last_error("dfl_init() was not called (TMA driver entry point unresolved)");
+    return DFL_ERR_INIT;
+  }
+  cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  cuuint64_t gd[5], gs[4];
+  cuuint32_t bx[5];
+  for (int i = 0; i < rank; ++i) { gd[i] = dims[i]; bx[i] = box[i]; }
+  for (int i = 0; i + 1 < rank; ++i) gs[i] = strides_bytes[i];
+  CUresult r = g_encode(out, dt, static_cast<cuuint32_t>(rank), const_cast<void*>(gaddr), gd, gs, bx, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_last_error("cuTensorMapEncodeTiled failed (CUresult %d; rank %d, dims %llu %llu %llu..., box %u %u %u...)",
+                   static_cast<int>(r), rank, (unsigned long long)gd[0], (unsigned long long)gd[1],
+                   (unsigned long long)(rank > 2 ? gd[2] : 0), bx[0], bx[1], rank > 2 ? bx[2] : 0);
+    return DFL_ERR_CUDA;
+  }
+  return DFL_OK;
+}
+
+// implemented in the other translation units
+size_t stencil_loss_workspace_bytes(int nd, const int64_t* dims);
+int stencil_loss_fwdbwd(int nd, const int64_t* dims, const void* pot, int pot_channels, const void* x, void* dpot,
+                        void* vel, float* loss3, void* workspace, float w1, float w2, float grad_scale, int dt_pot,
+                        int dt_x, cudaStream_t st);
+int fwd_stencils(int op, int nd, const int64_t* dims, const void* in, int in_cs, void* out0, void* out1, int dtype,
+                 cudaStream_t st);
+int conv_tc_launch(const void* x, const void* w_packed, const float* bias, void* out, void* out2,
+                   const void* residual, const void* mask_src, const int64_t* dims, int nd, int cin, int cout,
+                   int flags, cudaStream_t st);
+int wgrad_tc_launch(const void* x, const void* dpre, float* dw, const int64_t* dims, int nd, int cin, int cout,
+                    cudaStream_t st);
+int fc_fwd(const float* z, const float* W, const float* bias, void* out, int B, int K, int N, int out_dtype,
+           cudaStream_t st);
+int fc_bwd(const float* z, const void* dout, float* dW, float* db, int B, int K, int N, int dout_dtype,
+           cudaStream_t st);
+int lastconv(int op, const void* a, const void* b, const void* c, void* o0, void* o1, const int64_t* dims, int nd,
+             int cout, cudaStream_t st);
+int pool_mask(const void* g, const void* mask_src, void* ds, void* dmasked, const int64_t* cdims, int nd,
+              cudaStream_t st);
+int bias_grad(const void* d, float* db, size_t npos, cudaStream_t st);
+int pack_conv_weights(const float* W, void* wf, void* wd, int taps, int cin, int cout, cudaStream_t st);
+int adam_step(float* p, const float* g, float* m, float* v, size_t n, float lr_t, float b1, float b2, float eps,
+              float grad_scale, cudaStream_t st);
+int cast_f32_bf16(const float* a, void* o, size_t n, cudaStream_t st);
+
+}  // namespace dfl
+
+using namespace dfl;
+#define ST(s) static_cast<cudaStream_t>(s)
+
+#pragma GCC visibility push(default)
+extern "C" {
+
+int dfl_version(void) { return 100; }
+const char* dfl_last_error(void) { return g_err; }
+
+int dfl_init(int device) {
+  int ndev = 0;
+  DFL_CUDA_OK(cudaGetDeviceCount(&ndev));
+  DFL_REQUIRE(device >= 0 && device < ndev, "dfl_init: device %d out of range (have %d)", device, ndev);
+  DFL_CUDA_OK(cudaSetDevice(device));
+  DFL_CUDA_OK(cudaFree(0));
+  cudaDeviceProp prop;
+  DFL_CUDA_OK(cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10) {
+    set_last_error("dfl_init: device %d is sm_%d%d; this library is built for sm_100a (B200) only", device, prop.major,
+                   prop.minor);
+    return DFL_ERR_UNSUPPORTED;
+  }
+  g_num_sms = prop.multiProcessorCount;
+  void* fn = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  DFL_CUDA_OK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+  if (qres != cudaDriverEntryPointSuccess || !fn) {
+    set_last_error("dfl_init: cuTensorMapEncodeTiled not available from the driver");
+    return DFL_ERR_INIT;
+  }
+  g_encode = reinterpret_cast<PFN_encodeTiled>(fn);
+  g_inited = true;
+  return DFL_OK;
+}
+
+int dfl_curl_fwd(const void* pot, void* vel, const int64_t* dims, int ndim, int pot_channels, int dtype, void* stream) {
+  return fwd_stencils(0, ndim, dims, pot, pot_channels, vel, nullptr, dtype, ST(stream));
+}
+int dfl_jacobian_fwd(const void* vel, void* jac, void* vort_or_curl, const int64_t* dims, int ndim, int dtype,
+                     void* stream) {
+  return fwd_stencils(1, ndim, dims, vel, ndim, jac, vort_or_curl, dtype, ST(stream));
+}
+int dfl_divergence(const void* vel, void* div, const int64_t* dims, int ndim, int dtype, void* stream) {
+  return fwd_stencils(2, ndim, dims, vel, ndim, div, nullptr, dtype, ST(stream));
+}
+size_t dfl_stencil_loss_workspace_bytes(const int64_t* dims, int ndim) {
+  return stencil_loss_workspace_bytes(ndim, dims);
+}
+int dfl_stencil_loss_fwdbwd(const void* pot, const void* x, void* dpot, void* vel, float* loss3, void* workspace,
+                            const int64_t* dims, int ndim, int pot_channels, float w1, float w2, float grad_scale,
+                            int dtype_pot, int dtype_x, void* stream) {
+  return stencil_loss_fwdbwd(ndim, dims, pot, pot_channels, x, dpot, vel, loss3, workspace, w1, w2, grad_scale,
+                             dtype_pot, dtype_x, ST(stream));
+}
+int dfl_fc_fwd(const float* z, const float* W, const float* bias, void* out, int B, int K, int N, int out_dtype,
+               void* stream) {
+  return fc_fwd(z, W, bias, out, B, K, N, out_dtype, ST(stream));
+}
+int dfl_fc_bwd(const float* z, const void* dout, float* dW, float* db, int B, int K, int N, int dout_dtype,
+               void* stream) {
+  return fc_bwd(z, dout, dW, db, B, K, N, dout_dtype, ST(stream));
+}
+int dfl_pack_conv_weights(const float* w, void* w_fwd, void* w_dgrad, int taps, int cin, int cout, void* stream) {
+  return pack_conv_weights(w, w_fwd, w_dgrad, taps, cin, cout, ST(stream));
+}
+int dfl_conv3x3_fwd(const void* x, const void* w_packed, const float* bias, void* out, void* out2,
+                    const void* residual, const void* mask_src, const int64_t* dims, int ndim, int cin, int cout,
+                    int flags, void* stream) {
+  return conv_tc_launch(x, w_packed, bias, out, out2, residual, mask_src, dims, ndim, cin, cout, flags, ST(stream));
+}
+int dfl_conv3x3_wgrad(const void* x, const void* dpre, float* dw, const int64_t* dims, int ndim, int cin, int cout,
+                      void* stream) {
+  return wgrad_tc_launch(x, dpre, dw, dims, ndim, cin, cout, ST(stream));
+}
+int dfl_bias_grad(const void* dpre, float* db, size_t npos, void* stream) {
+  return bias_grad(dpre, db, npos, ST(stream));
+}
+int dfl_lastconv_fwd(const void* x, const float* w, const float* bias, float* out, const int64_t* dims, int ndim,
+                     int cout, void* stream) {
+  return lastconv(0, x, w, bias, out, nullptr, dims, ndim, cout, ST(stream));
+}
+int dfl_lastconv_dgrad(const float* dout, const float* w, const void* mask_src, void* dx, void* dx_masked,
+                       const int64_t* dims, int ndim, int cout, void* stream) {
+  DFL_REQUIRE(!(dx_masked && !mask_src), "lastconv_dgrad: dx_masked requested without mask_src");
+  return lastconv(1, dout, w, mask_src, dx, dx_masked, dims, ndim, cout, ST(stream));
+}
+int dfl_lastconv_wgrad(const void* x, const float* dout, float* dw, float* db, const int64_t* dims, int ndim,
+                       int cout, void* stream) {
+  return lastconv(2, x, dout, nullptr, dw, db, dims, ndim, cout, ST(stream));
+}
+int dfl_pool_mask(const void* g, const void* mask_src, void* ds, void* dmasked, const int64_t* cdims, int ndim,
+                  void* stream) {
+  DFL_REQUIRE(!(dmasked && !mask_src), "pool_mask: dmasked requested without mask_src");
+  return pool_mask(g, mask_src, ds, dmasked, cdims, ndim, ST(stream));
+}
+int dfl_adam_step(float* param, const float* grad, float* m, float* v, size_t n, float lr_t, float beta1, float beta2,
+                  float eps, float grad_scale, void* stream) {
+  return adam_step(param, grad, m, v, n, lr_t, beta1, beta2, eps, grad_scale, ST(stream));
+}
+int dfl_cast_f32_bf16(const float* in, void* out, size_t n, void* stream) {
+  return cast_f32_bf16(in, out, n, ST(stream));
+}
+
+}  // extern "C"
+#pragma GCC visibility pop

@@ -1,0 +1,335 @@
+// deepfluids_b200 -- 3x3(x3) convolution, Cin = multiple of 64, Cout = 128, as an implicit GEMM on the
+// 5th-gen tensor cores (tcgen05.mma, fp32 accumulators in TMEM, operands staged by TMA).
+//
+// Replaces slim.conv2d/conv3d (+ bias-add + leaky-ReLU + residual add + nearest x2 upsample, which TF1 runs
+// as separate full passes) on the generator/AE path: reference ops.py:12-16 called from model.py:26,68 and
+// the residual/upsample glue model.py:34-36,76-79.  The same kernel is the data-gradient pass (dgrad): a
+// convolution of dL/dy with the tap-flipped, channel-transposed weights, whose epilogue applies the
+// leaky-ReLU derivative of the producing layer and/or adds the residual-branch gradient.
+//
+//   GEMM view:  D[M = 128 output voxels (a 3D brick), N = 128 out-channels] += A[M, K] * B[N, K]^T
+//               K = taps x Cin, walked tap by tap in 64-channel slices (one 128-byte swizzle row each).
+//   A operand:  for tap (dz,dy,dx) the TMA loads the brick shifted by (dz-1,dy-1,dx-1) straight out of the
+//               NDHWC activation tensor (5-D tiled tensor map, box = [64 ch, bw, bh, bd, 1]); out-of-bounds
+//               voxels are zero-filled by the TMA unit, which *is* TF's SAME padding -- no im2col buffer, no
+//               padded copy.  The box lands in shared memory as 128 rows x 128 B, 128B-swizzled = the canonical
+//               K-major UMMA layout.
+//   B operand:  pre-packed bf16 weights [Cout][tap*Cin + ci] (K-major), 2-D tensor map, box [64, 128].
+//   Roles:      warp 0 = TMA producer, warp 1 = TMEM allocator + single-thread MMA issuer,
+//               warps 2..5 = epilogue (TMEM -> registers -> bias/lrelu/mask/residual -> bf16 -> global,
+//               optionally replicated 2x2(x2) = fused nearest-neighbour upsample).
+//   Pipelines:  6-stage smem ring (full/empty mbarriers), 2 TMEM accumulators (full/empty mbarriers) so the
+//               epilogue of tile i overlaps the MMAs of tile i+1; persistent CTAs, static tile schedule.
+#include "dfl_common.cuh"
+
+namespace dfl {
+
+constexpr int CT_BLOCK_M = 128;
+constexpr int CT_BLOCK_N = 128;
+constexpr int CT_BLOCK_K = 64;                    // bf16 elements = 128 bytes = one swizzle row
+constexpr int CT_STAGES = 6;
+constexpr int CT_A_BYTES = CT_BLOCK_M * CT_BLOCK_K * 2;   // 16 KB
+constexpr int CT_B_BYTES = CT_BLOCK_N * CT_BLOCK_K * 2;   // 16 KB
+constexpr int CT_STAGE_BYTES = CT_A_BYTES + CT_B_BYTES;
+constexpr int CT_THREADS = 192;
+constexpr int CT_SMEM_BYTES = CT_STAGES * CT_STAGE_BYTES + 1024 /*align slack*/ + 1024 /*barriers, bias*/;
+
+enum : int { CF_LRELU = 1, CF_OUT2_UPSAMPLE = 2 };
+
+struct ConvTcParams {
+  int B, D, H, W;
+  int bd, bh, bw;             // brick, bd*bh*bw == 128
+  int tz, ty, tx, ntiles;     // tiles per axis / total (over batch too)
+  int kd, kh, kw;             // 3,3,3 (3D) or 1,3,3 (2D)
+  int cin_chunks;             // Cin / 64
+  int flags;
+  const float* bias;          // [128] or nullptr
+  const __nv_bfloat16* mask_src;  // multiply by lrelu'(mask_src) (dgrad) or nullptr
+  const __nv_bfloat16* residual;  // added into out2 or nullptr
+  __nv_bfloat16* out;         // [B,D,H,W,128] or nullptr
+  __nv_bfloat16* out2;        // [B,D,H,W,128] or upsampled [B,(2D),2H,2W,128] or nullptr
+};
+
+__device__ __forceinline__ void unpack_bf16x8(const uint4& q, float (&f)[8]) {
+  const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    f[2 * k] = __uint_as_float(w[k] << 16);
+    f[2 * k + 1] = __uint_as_float(w[k] & 0xFFFF0000u);
+  }
+}
+__device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
+  __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+
+__global__ void __launch_bounds__(CT_THREADS, 1)
+conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, ConvTcParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  // 1024-byte alignment required by the 128B swizzle atoms
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* ctrl = smem + CT_STAGES * CT_STAGE_BYTES;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(ctrl);            // [CT_STAGES]
+  uint64_t* empty_bar = full_bar + CT_STAGES;                        // [CT_STAGES]
+  uint64_t* tfull_bar = empty_bar + CT_STAGES;                       // [2]
+  uint64_t* tempty_bar = tfull_bar + 2;                              // [2]
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tempty_bar + 2);  // [1]
+  float* s_bias = reinterpret_cast<float*>(ctrl + 256);              // [128]
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int ntaps = p.kd * p.kh * p.kw;
+  const int kblocks = ntaps * p.cin_chunks;
+
+  if (threadIdx.x < CT_BLOCK_N) s_bias[threadIdx.x] = p.bias ? p.bias[threadIdx.x] : 0.f;
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    for (int s = 0; s < CT_STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&tfull_bar[a], 1);
+      mbar_init(&tempty_bar[a], 128);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_ptr, 256);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp == 0) {
+    // ================================ TMA producer ================================
+    if (lane == 0) {
+      uint32_t it = 0;
+      for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
+        int r = tile;
+        const int x0 = (r % p.tx) * p.bw; r /= p.tx;
+        const int y0 = (r % p.ty) * p.bh; r /= p.ty;
+        const int z0 = (r % p.tz) * p.bd; r /= p.tz;
+        const int b = r;
+        int kb = 0;
+        for (int dz = 0; dz < p.kd; ++dz)
+          for (int dy = 0; dy < p.kh; ++dy)
+            for (int dx = 0; dx < p.kw; ++dx)
+              for (int c = 0; c < p.cin_chunks; ++c, ++kb, ++it) {
+                const uint32_t s = it % CT_STAGES, ph = (it / CT_STAGES) & 1;
+                mbar_wait(&empty_bar[s], ph ^ 1);
+                mbar_expect_tx(&full_bar[s], CT_STAGE_BYTES);
+                uint8_t* sa = smem + s * CT_STAGE_BYTES;
+                tma_load_5d(sa, &tmA, &full_bar[s], c * CT_BLOCK_K, x0 + dx - (p.kw >> 1), y0 + dy - (p.kh >> 1),
+                            z0 + dz - (p.kd >> 1), b);
+                tma_load_2d(sa + CT_A_BYTES, &tmB, &full_bar[s], kb * CT_BLOCK_K, 0);
+              }
+      }
+    }
+  } else if (warp == 1) {
+    // ================================ MMA issuer ================================
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(CT_BLOCK_M, CT_BLOCK_N, 0, 0);
+      uint32_t it = 0, tcount = 0;
+      for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++tcount) {
+        const uint32_t acc = tcount & 1, aph = (tcount >> 1) & 1;
+        mbar_wait(&tempty_bar[acc], aph ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * CT_BLOCK_N;
+        for (int kb = 0; kb < kblocks; ++kb, ++it) {
+          const uint32_t s = it % CT_STAGES, ph = (it / CT_STAGES) & 1;
+          mbar_wait(&full_bar[s], ph);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + s * CT_STAGE_BYTES);
+          const uint32_t sb = sa + CT_A_BYTES;
+#pragma unroll
+          for (int k = 0; k < CT_BLOCK_K / 16; ++k) {
+            const uint64_t da = umma_desc_sw128(sa + k * 32, 16, 1024);
+            const uint64_t db = umma_desc_sw128(sb + k * 32, 16, 1024);
+            umma_bf16(d_tmem, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[s]);   // frees the smem slot once these MMAs have read it
+        }
+        umma_commit(&tfull_bar[acc]);   // accumulator complete -> epilogue
+      }
+    }
+  } else {
+    // ================================ epilogue (warps 2..5) ================================
+    const int quarter = warp & 3;                 // TMEM lane quarter this warp may access
+    const int row = quarter * 32 + lane;          // GEMM row = voxel index inside the brick
+    const int lw = row % p.bw, lh = (row / p.bw) % p.bh, ld = row / (p.bw * p.bh);
+    const bool ups = (p.flags & CF_OUT2_UPSAMPLE) != 0;
+    const bool act = (p.flags & CF_LRELU) != 0;
+    uint32_t tcount = 0;
+    for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++tcount) {
+      const uint32_t acc = tcount & 1, aph = (tcount >> 1) & 1;
+      int r = tile;
+      const int x = (r % p.tx) * p.bw + lw; r /= p.tx;
+      const int y = (r % p.ty) * p.bh + lh; r /= p.ty;
+      const int z = (r % p.tz) * p.bd + ld; r /= p.tz;
+      const int b = r;
+      const bool valid = (x < p.W) && (y < p.H) && (z < p.D);
+      const size_t pos = ((static_cast<size_t>(b) * p.D + z) * p.H + y) * p.W + x;
+
+      mbar_wait(&tfull_bar[acc], aph);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * CT_BLOCK_N;
+#pragma unroll 1
+      for (int c0 = 0; c0 < CT_BLOCK_N; c0 += 32) {
+        uint32_t rr[32];
+        tmem_ld_32x32(taddr + c0, rr);
+        tmem_ld_wait();
+        if (valid) {
+          float v[32];
+#pragma unroll
+          for (int k = 0; k < 32; ++k) {
+            float t = __uint_as_float(rr[k]) + s_bias[c0 + k];
+            v[k] = act ? lrelu_f(t) : t;
+          }
+          if (p.mask_src) {
+            const uint4* m = reinterpret_cast<const uint4*>(p.mask_src + pos * CT_BLOCK_N + c0);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              float f[8];
+              unpack_bf16x8(__ldg(m + q), f);
+#pragma unroll
+              for (int k = 0; k < 8; ++k) v[q * 8 + k] *= lrelu_grad_from_out(f[k]);
+            }
+          }
+          if (p.out) {
+            uint4* o = reinterpret_cast<uint4*>(p.out + pos * CT_BLOCK_N + c0);
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+              o[q] = make_uint4(pack_bf16x2(v[q * 8], v[q * 8 + 1]), pack_bf16x2(v[q * 8 + 2], v[q * 8 + 3]),
+                                pack_bf16x2(v[q * 8 + 4], v[q * 8 + 5]), pack_bf16x2(v[q * 8 + 6], v[q * 8 + 7]));
+          }
+          if (p.out2) {
+            if (p.residual) {
+              const uint4* m = reinterpret_cast<const uint4*>(p.residual + pos * CT_BLOCK_N + c0);
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                float f[8];
+                unpack_bf16x8(__ldg(m + q), f);
+#pragma unroll
+                for (int k = 0; k < 8; ++k) v[q * 8 + k] += f[k];
+              }
+            }
+            uint4 pk[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+              pk[q] = make_uint4(pack_bf16x2(v[q * 8], v[q * 8 + 1]), pack_bf16x2(v[q * 8 + 2], v[q * 8 + 3]),
+                                 pack_bf16x2(v[q * 8 + 4], v[q * 8 + 5]), pack_bf16x2(v[q * 8 + 6], v[q * 8 + 7]));
+            if (!ups) {
+              uint4* o = reinterpret_cast<uint4*>(p.out2 + pos * CT_BLOCK_N + c0);
+#pragma unroll
+              for (int q = 0; q < 4; ++q) o[q] = pk[q];
+            } else {
+              // nearest-neighbour x2 (ops.py:75-91): out[2i+a] = in[i]; the z axis only when the conv is 3D
+              const int zr = (p.kd > 1) ? 2 : 1;
+              const int D2 = p.D * zr, H2 = p.H * 2, W2 = p.W * 2;
+              for (int a = 0; a < zr; ++a)
+                for (int e = 0; e < 2; ++e)
+                  for (int f = 0; f < 2; ++f) {
+                    const size_t pos2 =
+                        ((static_cast<size_t>(b) * D2 + (z * zr + a)) * H2 + (2 * y + e)) * W2 + (2 * x + f);
+                    uint4* o = reinterpret_cast<uint4*>(p.out2 + pos2 * CT_BLOCK_N + c0);
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) o[q] = pk[q];
+                  }
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(&tempty_bar[acc]);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    __syncwarp();
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 256);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// host launcher
+// ---------------------------------------------------------------------------------------------
+static void pick_brick(int D, int H, int W, int& bd, int& bh, int& bw) {
+  // 128 voxels; prefer wide-x bricks (contiguous rows), never larger than the (power-of-two-rounded) extent
+  auto p2 = [](int v) { int r = 1; while (r < v) r <<= 1; return r; };
+  bw = std::min(p2(W), 16);
+  bh = std::min(p2(H), 128 / bw);
+  bd = 128 / (bw * bh);
+  if (D == 1) {           // 2D: spend the remaining factor on x, then y
+    while (bd > 1) { if (bw < 128) bw <<= 1; else bh <<= 1; bd >>= 1; }
+  } else if (bd > p2(D)) {
+    while (bd > p2(D)) { bw <<= 1; bd >>= 1; }
+  }
+}
+
+int conv_tc_launch(const void* x, const void* w_packed, const float* bias, void* out, void* out2,
+                   const void* residual, const void* mask_src, const int64_t* dims /*B,D,H,W*/, int nd, int cin,
+                   int cout, int flags, cudaStream_t st) {
+  DFL_REQUIRE(cout == 128, "conv_tc: Cout must be 128 (got %d)", cout);
+  DFL_REQUIRE(cin % 64 == 0 && cin >= 64, "conv_tc: Cin must be a multiple of 64 (got %d)", cin);
+  DFL_REQUIRE(nd == 2 || nd == 3, "conv_tc: ndim must be 2 or 3");
+  ConvTcParams p{};
+  p.B = static_cast<int>(dims[0]);
+  p.D = nd == 3 ? static_cast<int>(dims[1]) : 1;
+  p.H = static_cast<int>(dims[nd - 1]);
+  p.W = static_cast<int>(dims[nd]);
+  p.kd = nd == 3 ? 3 : 1;
+  p.kh = 3;
+  p.kw = 3;
+  pick_brick(p.D, p.H, p.W, p.bd, p.bh, p.bw);
+  p.tx = (p.W + p.bw - 1) / p.bw;
+  p.ty = (p.H + p.bh - 1) / p.bh;
+  p.tz = (p.D + p.bd - 1) / p.bd;
+  p.ntiles = p.B * p.tz * p.ty * p.tx;
+  p.cin_chunks = cin / 64;
+  p.flags = flags;
+  p.bias = bias;
+  p.mask_src = static_cast<const __nv_bfloat16*>(mask_src);
+  p.residual = static_cast<const __nv_bfloat16*>(residual);
+  p.out = static_cast<__nv_bfloat16*>(out);
+  p.out2 = static_cast<__nv_bfloat16*>(out2);
+  DFL_REQUIRE(p.out || p.out2, "conv_tc: no output buffer given");
+
+  CUtensorMap tmA, tmB;
+  {
+    const uint64_t gd[5] = {static_cast<uint64_t>(cin), static_cast<uint64_t>(p.W), static_cast<uint64_t>(p.H),
+                            static_cast<uint64_t>(p.D), static_cast<uint64_t>(p.B)};
+    const uint64_t gs[4] = {static_cast<uint64_t>(cin) * 2, static_cast<uint64_t>(cin) * 2 * p.W,
+                            static_cast<uint64_t>(cin) * 2 * p.W * p.H,
+                            static_cast<uint64_t>(cin) * 2 * p.W * p.H * p.D};
+    const uint32_t box[5] = {64, static_cast<uint32_t>(p.bw), static_cast<uint32_t>(p.bh),
+                             static_cast<uint32_t>(p.bd), 1};
+    int rc = encode_tensor_map(&tmA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, x, gd, gs, box, CU_TENSOR_MAP_SWIZZLE_128B);
+    if (rc) return rc;
+  }
+  {
+    const int ntaps = p.kd * p.kh * p.kw;
+    const uint64_t gd[2] = {static_cast<uint64_t>(ntaps) * cin, 128};
+    const uint64_t gs[1] = {static_cast<uint64_t>(ntaps) * cin * 2};
+    const uint32_t box[2] = {64, 128};
+    int rc = encode_tensor_map(&tmB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, w_packed, gd, gs, box,
+                               CU_TENSOR_MAP_SWIZZLE_128B);
+    if (rc) return rc;
+  }
+  static bool attr_set = false;
+  if (!attr_set) {
+    DFL_CUDA_OK(cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, CT_SMEM_BYTES));
+    attr_set = true;
+  }
+  const int grid = std::min(p.ntiles, num_sms());
+  conv_tc_kernel<<<grid, CT_THREADS, CT_SMEM_BYTES, st>>>(tmA, tmB, p);
+  DFL_LAUNCH_OK("conv_tc_kernel");
+  return DFL_OK;
+}
+
+}  // namespace dfl

@@ -1,0 +1,216 @@
+// deepfluids_b200 -- weight gradient of the 3x3(x3) 128->128 convolution on tcgen05 tensor cores.
+//
+// Replaces TF autodiff's Conv2DBackpropFilter / Conv3DBackpropFilterV2 for the layers built by reference
+// model.py:26,68 (slim.conv2d / slim.conv3d, ops.py:12-16):
+//     dW[tap][ci][co] = sum_p  X[p + tap - 1][ci] * dP[p][co]          (X zero outside the domain = SAME padding)
+//
+//   GEMM view per tap:  D_tap[M = ci (128), N = co (128)] += A_tap[M, K] * B[N, K]^T,  K = voxels.
+//   Both operands are "MN-major": the TMA box of a channels-last tensor lands in smem as K rows (voxels) of
+//   128 bytes (64 channels), 128B-swizzled -- exactly the canonical MN-major UMMA layout, so the activation
+//   and gradient bricks feed the tensor core with no transpose.  A_tap is the brick of X shifted by the tap
+//   offset (TMA zero-fills out-of-bounds = padding); B is the un-shifted brick of dP, shared by the taps.
+//   Each CTA owns a group of <= 4 taps (4 x 128 fp32 TMEM columns = all 512) and a slab of voxel bricks
+//   (split-K); it accumulates in TMEM across its whole slab and adds its partial dW into the fp32 gradient
+//   with red.global.add at the end.
+//   Roles: warp 0 = TMA producer, warp 1 = TMEM alloc + MMA issuer, warps 2..5 = epilogue.
+#include "dfl_common.cuh"
+
+namespace dfl {
+
+constexpr int WG_TILE_K = 128;                        // voxels per brick
+constexpr int WG_OP_BYTES = WG_TILE_K * 128 * 2;      // 32 KB: 128 voxels x 128 channels bf16 (two 64-ch boxes)
+constexpr int WG_A_SLOTS = 4, WG_B_SLOTS = 2;
+constexpr int WG_THREADS = 192;
+constexpr int WG_MAX_TAPS = 4;
+constexpr int WG_SMEM_BYTES = (WG_A_SLOTS + WG_B_SLOTS) * WG_OP_BYTES + 1024 + 256;
+
+struct WgradParams {
+  int B, D, H, W;
+  int bd, bh, bw;
+  int tz, ty, tx, ntiles;
+  int kd, kh, kw;
+  int taps_per_group, ngroups, nslabs;
+  float* dw;          // [taps][128][128] fp32 (TF layout: ..., Cin, Cout), accumulated into
+};
+
+__global__ void __launch_bounds__(WG_THREADS, 1)
+wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmP, WgradParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + WG_A_SLOTS * WG_OP_BYTES;
+  uint8_t* ctrl = sB + WG_B_SLOTS * WG_OP_BYTES;
+  uint64_t* a_full = reinterpret_cast<uint64_t*>(ctrl);
+  uint64_t* a_empty = a_full + WG_A_SLOTS;
+  uint64_t* b_full = a_empty + WG_A_SLOTS;
+  uint64_t* b_empty = b_full + WG_B_SLOTS;
+  uint64_t* acc_full = b_empty + WG_B_SLOTS;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(acc_full + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int group = blockIdx.x % p.ngroups, slab = blockIdx.x / p.ngroups;
+  const int ntaps = p.kd * p.kh * p.kw;
+  const int tap0 = group * p.taps_per_group;
+  const int gtaps = min(p.taps_per_group, ntaps - tap0);
+  // this CTA's slab of bricks: [t_begin, t_end)
+  const int per = (p.ntiles + p.nslabs - 1) / p.nslabs;
+  const int t_begin = slab * per, t_end = min(p.ntiles, t_begin + per);
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmX);
+    tma_prefetch_desc(&tmP);
+    for (int s = 0; s < WG_A_SLOTS; ++s) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], 1); }
+    for (int s = 0; s < WG_B_SLOTS; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 1); }
+    mbar_init(acc_full, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_ptr, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (t_begin < t_end) {
+    if (warp == 0) {
+      if (lane == 0) {
+        uint32_t ia = 0, ib = 0;
+        for (int tile = t_begin; tile < t_end; ++tile, ++ib) {
+          int r = tile;
+          const int x0 = (r % p.tx) * p.bw; r /= p.tx;
+          const int y0 = (r % p.ty) * p.bh; r /= p.ty;
+          const int z0 = (r % p.tz) * p.bd; r /= p.tz;
+          const int b = r;
+          {  // B = dP brick (two 64-channel boxes)
+            const uint32_t s = ib % WG_B_SLOTS, ph = (ib / WG_B_SLOTS) & 1;
+            mbar_wait(&b_empty[s], ph ^ 1);
+            mbar_expect_tx(&b_full[s], WG_OP_BYTES);
+            tma_load_5d(sB + s * WG_OP_BYTES, &tmP, &b_full[s], 0, x0, y0, z0, b);
+            tma_load_5d(sB + s * WG_OP_BYTES + WG_OP_BYTES / 2, &tmP, &b_full[s], 64, x0, y0, z0, b);
+          }
+          for (int t = 0; t < gtaps; ++t, ++ia) {
+            const int tap = tap0 + t;
+            const int dx = tap % p.kw, dy = (tap / p.kw) % p.kh, dz = tap / (p.kw * p.kh);
+            const uint32_t s = ia % WG_A_SLOTS, ph = (ia / WG_A_SLOTS) & 1;
+            mbar_wait(&a_empty[s], ph ^ 1);
+            mbar_expect_tx(&a_full[s], WG_OP_BYTES);
+            const int xs = x0 + dx - (p.kw >> 1), ys = y0 + dy - (p.kh >> 1), zs = z0 + dz - (p.kd >> 1);
+            tma_load_5d(sA + s * WG_OP_BYTES, &tmX, &a_full[s], 0, xs, ys, zs, b);
+            tma_load_5d(sA + s * WG_OP_BYTES + WG_OP_BYTES / 2, &tmX, &a_full[s], 64, xs, ys, zs, b);
+          }
+        }
+      }
+    } else if (warp == 1) {
+      if (lane == 0) {
+        constexpr uint32_t idesc = umma_idesc_bf16(128, 128, 1, 1);   // both operands MN-major
+        uint32_t ia = 0, ib = 0;
+        for (int tile = t_begin; tile < t_end; ++tile, ++ib) {
+          const uint32_t sbs = ib % WG_B_SLOTS, bph = (ib / WG_B_SLOTS) & 1;
+          mbar_wait(&b_full[sbs], bph);
+          tc_fence_after();
+          const uint32_t sb = smem_u32(sB + sbs * WG_OP_BYTES);
+          for (int t = 0; t < gtaps; ++t, ++ia) {
+            const uint32_t s = ia % WG_A_SLOTS, ph = (ia / WG_A_SLOTS) & 1;
+            mbar_wait(&a_full[s], ph);
+            tc_fence_after();
+            const uint32_t sa = smem_u32(sA + s * WG_OP_BYTES);
+            const uint32_t d_tmem = tmem_base + t * 128;
+#pragma unroll
+            for (int k = 0; k < WG_TILE_K / 16; ++k) {
+              // 16 voxels (K) = 2 groups of 8 rows x 128 B; the two 64-channel halves are WG_OP_BYTES/2 apart
+              const uint64_t da = umma_desc_sw128(sa + k * 2048, WG_OP_BYTES / 2, 1024);
+              const uint64_t db = umma_desc_sw128(sb + k * 2048, WG_OP_BYTES / 2, 1024);
+              umma_bf16(d_tmem, da, db, idesc, (tile != t_begin || k != 0) ? 1u : 0u);
+            }
+            umma_commit(&a_empty[s]);
+          }
+          umma_commit(&b_empty[sbs]);
+        }
+        umma_commit(acc_full);
+      }
+    } else {
+      const int quarter = warp & 3;
+      const int ci = quarter * 32 + lane;
+      mbar_wait(acc_full, 0);
+      tc_fence_after();
+      for (int t = 0; t < gtaps; ++t) {
+        float* dst = p.dw + (static_cast<size_t>(tap0 + t) * 128 + ci) * 128;
+#pragma unroll 1
+        for (int c0 = 0; c0 < 128; c0 += 32) {
+          uint32_t rr[32];
+          tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + t * 128 + c0, rr);
+          tmem_ld_wait();
+#pragma unroll
+          for (int k = 0; k < 32; ++k) atomicAdd(dst + c0 + k, __uint_as_float(rr[k]));
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    __syncwarp();
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+static void pick_brick_w(int D, int H, int W, int& bd, int& bh, int& bw) {
+  auto p2 = [](int v) { int r = 1; while (r < v) r <<= 1; return r; };
+  bw = std::min(p2(W), 16);
+  bh = std::min(p2(H), 128 / bw);
+  bd = 128 / (bw * bh);
+  if (D == 1) {
+    while (bd > 1) { if (bw < 128) bw <<= 1; else bh <<= 1; bd >>= 1; }
+  } else if (bd > p2(D)) {
+    while (bd > p2(D)) { bw <<= 1; bd >>= 1; }
+  }
+}
+
+int wgrad_tc_launch(const void* x, const void* dpre, float* dw, const int64_t* dims, int nd, int cin, int cout,
+                    cudaStream_t st) {
+  DFL_REQUIRE(cin == 128 && cout == 128, "wgrad_tc: only Cin = Cout = 128 (got %d, %d)", cin, cout);
+  DFL_REQUIRE(nd == 2 || nd == 3, "wgrad_tc: ndim must be 2 or 3");
+  WgradParams p{};
+  p.B = static_cast<int>(dims[0]);
+  p.D = nd == 3 ? static_cast<int>(dims[1]) : 1;
+  p.H = static_cast<int>(dims[nd - 1]);
+  p.W = static_cast<int>(dims[nd]);
+  p.kd = nd == 3 ? 3 : 1;
+  p.kh = 3;
+  p.kw = 3;
+  pick_brick_w(p.D, p.H, p.W, p.bd, p.bh, p.bw);
+  p.tx = (p.W + p.bw - 1) / p.bw;
+  p.ty = (p.H + p.bh - 1) / p.bh;
+  p.tz = (p.D + p.bd - 1) / p.bd;
+  p.ntiles = p.B * p.tz * p.ty * p.tx;
+  const int ntaps = p.kd * p.kh * p.kw;
+  p.taps_per_group = (nd == 3) ? 4 : 3;
+  p.ngroups = (ntaps + p.taps_per_group - 1) / p.taps_per_group;
+  p.nslabs = std::max(1, std::min(p.ntiles, num_sms() / p.ngroups));
+  p.dw = dw;
+
+  CUtensorMap tmX, tmP;
+  const uint64_t gd[5] = {128, static_cast<uint64_t>(p.W), static_cast<uint64_t>(p.H), static_cast<uint64_t>(p.D),
+                          static_cast<uint64_t>(p.B)};
+  const uint64_t gs[4] = {256, 256ull * p.W, 256ull * p.W * p.H, 256ull * p.W * p.H * p.D};
+  const uint32_t box[5] = {64, static_cast<uint32_t>(p.bw), static_cast<uint32_t>(p.bh), static_cast<uint32_t>(p.bd),
+                           1};
+  int rc = encode_tensor_map(&tmX, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, x, gd, gs, box, CU_TENSOR_MAP_SWIZZLE_128B);
+  if (rc) return rc;
+  rc = encode_tensor_map(&tmP, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, dpre, gd, gs, box, CU_TENSOR_MAP_SWIZZLE_128B);
+  if (rc) return rc;
+  static bool attr_set = false;
+  if (!attr_set) {
+    DFL_CUDA_OK(cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, WG_SMEM_BYTES));
+    attr_set = true;
+  }
+  wgrad_tc_kernel<<<p.ngroups * p.nslabs, WG_THREADS, WG_SMEM_BYTES, st>>>(tmX, tmP, p);
+  DFL_LAUNCH_OK("wgrad_tc_kernel");
+  return DFL_OK;
+}
+
+}  // namespace dfl

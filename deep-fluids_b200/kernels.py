@@ -1,0 +1,165 @@
+"""Thin torch-tensor front end of the C-ABI (one function per entry point of include/deepfluids_b200.h).
+
+torch is plumbing here: it owns the device memory and the stream; every call passes raw pointers through
+ctypes to hand-written sm_100a kernels.  Nothing in this module computes on the CPU or through torch ops.
+"""
+import ctypes as C
+
+import torch
+
+from . import cabi
+from .cabi import F32, BF16, CONV_LRELU, CONV_OUT2_UPSAMPLE, check, dims_array
+
+_DT = {torch.float32: F32, torch.bfloat16: BF16}
+
+
+def _p(t):
+    if t is None:
+        return None
+    assert t.is_cuda and t.is_contiguous(), "deepfluids_b200 kernels need contiguous CUDA tensors"
+    return C.c_void_p(t.data_ptr())
+
+
+def _st():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _dt(t):
+    try:
+        return _DT[t.dtype]
+    except KeyError:
+        raise TypeError("unsupported dtype %s (float32 / bfloat16 only)" % t.dtype)
+
+
+def _spatial(t):
+    """channels-last tensor [B,(D,)H,W,C] -> (dims array, ndim)"""
+    nd = t.dim() - 2
+    assert nd in (2, 3), "expected NHWC or NDHWC tensor"
+    return dims_array(t.shape[:-1]), nd
+
+
+# ------------------------------------------------------------------ stencils
+def curl_fwd(pot):
+    d, nd = _spatial(pot)
+    vel = torch.empty(pot.shape[:-1] + (nd,), dtype=pot.dtype, device=pot.device)
+    check(cabi.lib().dfl_curl_fwd(_p(pot), _p(vel), d, nd, pot.shape[-1], _dt(pot), _st()))
+    return vel
+
+
+def jacobian_fwd(vel, want_jac=True, want_aux=True):
+    d, nd = _spatial(vel)
+    assert vel.shape[-1] == nd
+    jac = torch.empty(vel.shape[:-1] + (nd * nd,), dtype=vel.dtype, device=vel.device) if want_jac else None
+    aux = torch.empty(vel.shape[:-1] + (1 if nd == 2 else 3,), dtype=vel.dtype, device=vel.device) if want_aux else None
+    check(cabi.lib().dfl_jacobian_fwd(_p(vel), _p(jac), _p(aux), d, nd, _dt(vel), _st()))
+    return jac, aux
+
+
+def divergence(vel):
+    d, nd = _spatial(vel)
+    out = torch.empty((vel.shape[0],) + tuple(s - 1 for s in vel.shape[1:-1]) + (1,), dtype=vel.dtype, device=vel.device)
+    check(cabi.lib().dfl_divergence(_p(vel), _p(out), d, nd, _dt(vel), _st()))
+    return out
+
+
+def stencil_loss_fwdbwd(pot, x, w1=1.0, w2=1.0, grad_scale=1.0, want_vel=False, dpot=None, loss3=None, workspace=None):
+    """-> (loss3 [total,l1,jl1] float32 device tensor, dpot, vel|None)"""
+    d, nd = _spatial(x)
+    l = cabi.lib()
+    nb = l.dfl_stencil_loss_workspace_bytes(d, nd)
+    if workspace is None or workspace.numel() < nb:
+        workspace = torch.empty(nb, dtype=torch.uint8, device=x.device)
+    if dpot is None:
+        dpot = torch.empty(x.shape[:-1] + (1 if nd == 2 else 3,), dtype=pot.dtype, device=x.device)
+    if loss3 is None:
+        loss3 = torch.empty(3, dtype=torch.float32, device=x.device)
+    vel = torch.empty(x.shape, dtype=pot.dtype, device=x.device) if want_vel else None
+    check(l.dfl_stencil_loss_fwdbwd(_p(pot), _p(x), _p(dpot), _p(vel), _p(loss3), _p(workspace), d, nd,
+                                    pot.shape[-1], w1, w2, grad_scale, _dt(pot), _dt(x), _st()))
+    return loss3, dpot, vel
+
+
+# ------------------------------------------------------------------ FC
+def fc_fwd(z, W, bias, out_dtype=torch.bfloat16, out=None):
+    B, K = z.shape
+    N = W.shape[1]
+    if out is None:
+        out = torch.empty(B, N, dtype=out_dtype, device=z.device)
+    check(cabi.lib().dfl_fc_fwd(_p(z), _p(W), _p(bias), _p(out), B, K, N, _dt(out), _st()))
+    return out
+
+
+def fc_bwd(z, dout, dW, db):
+    B, K = z.shape
+    N = dW.shape[1]
+    check(cabi.lib().dfl_fc_bwd(_p(z), _p(dout), _p(dW), _p(db), B, K, N, _dt(dout), _st()))
+
+
+# ------------------------------------------------------------------ conv
+def pack_conv_weights(w, w_fwd=None, w_dgrad=None):
+    """w fp32 TF layout [k,(k,)k,Cin,Cout] -> (bf16 [Cout, taps*Cin], bf16 [Cin, taps*Cout])"""
+    cin, cout = w.shape[-2], w.shape[-1]
+    taps = w.numel() // (cin * cout)
+    if w_fwd is None:
+        w_fwd = torch.empty(cout, taps * cin, dtype=torch.bfloat16, device=w.device)
+    if w_dgrad is None:
+        w_dgrad = torch.empty(cin, taps * cout, dtype=torch.bfloat16, device=w.device)
+    check(cabi.lib().dfl_pack_conv_weights(_p(w), _p(w_fwd), _p(w_dgrad), taps, cin, cout, _st()))
+    return w_fwd, w_dgrad
+
+
+def conv3x3(x, w_packed, bias=None, out=None, out2=None, residual=None, mask_src=None, flags=0):
+    """tcgen05 implicit-GEMM conv; see dfl_conv3x3_fwd in include/deepfluids_b200.h."""
+    d, nd = _spatial(x)
+    cin, cout = x.shape[-1], w_packed.shape[0]
+    assert x.dtype == torch.bfloat16 and w_packed.dtype == torch.bfloat16
+    check(cabi.lib().dfl_conv3x3_fwd(_p(x), _p(w_packed), _p(bias), _p(out), _p(out2), _p(residual), _p(mask_src),
+                                     d, nd, cin, cout, flags, _st()))
+
+
+def conv3x3_wgrad(x, dpre, dw):
+    d, nd = _spatial(x)
+    check(cabi.lib().dfl_conv3x3_wgrad(_p(x), _p(dpre), _p(dw), d, nd, x.shape[-1], dpre.shape[-1], _st()))
+
+
+def bias_grad(dpre, db):
+    check(cabi.lib().dfl_bias_grad(_p(dpre), _p(db), dpre.numel() // dpre.shape[-1], _st()))
+
+
+def lastconv_fwd(x, w, bias, out=None):
+    d, nd = _spatial(x)
+    cout = w.shape[-1]
+    if out is None:
+        out = torch.empty(x.shape[:-1] + (cout,), dtype=torch.float32, device=x.device)
+    check(cabi.lib().dfl_lastconv_fwd(_p(x), _p(w), _p(bias), _p(out), d, nd, cout, _st()))
+    return out
+
+
+def lastconv_dgrad(dout, w, mask_src=None, dx=None, dx_masked=None):
+    d, nd = _spatial(dout)
+    check(cabi.lib().dfl_lastconv_dgrad(_p(dout), _p(w), _p(mask_src), _p(dx), _p(dx_masked), d, nd, w.shape[-1], _st()))
+
+
+def lastconv_wgrad(x, dout, dw, db):
+    d, nd = _spatial(x)
+    check(cabi.lib().dfl_lastconv_wgrad(_p(x), _p(dout), _p(dw), _p(db), d, nd, dout.shape[-1], _st()))
+
+
+def pool_mask(g, mask_src, ds, dmasked):
+    """g: fine-grid gradient [B,(2D,)2H,2W,128]; ds / dmasked: coarse [B,(D,)H,W,128]"""
+    ref = ds if ds is not None else dmasked
+    d, nd = _spatial(ref)
+    check(cabi.lib().dfl_pool_mask(_p(g), _p(mask_src), _p(ds), _p(dmasked), d, nd, _st()))
+
+
+# ------------------------------------------------------------------ optimizer / misc
+def adam_step(param, grad, m, v, lr_t, beta1, beta2, eps=1e-8, grad_scale=1.0):
+    check(cabi.lib().dfl_adam_step(_p(param), _p(grad), _p(m), _p(v), param.numel(), lr_t, beta1, beta2, eps,
+                                   grad_scale, _st()))
+
+
+def cast_f32_bf16(a, out=None):
+    if out is None:
+        out = torch.empty(a.shape, dtype=torch.bfloat16, device=a.device)
+    check(cabi.lib().dfl_cast_f32_bf16(_p(a), _p(out), a.numel(), _st()))
+    return out

@@ -1,0 +1,123 @@
+/* deepfluids_b200 -- C ABI of the B200 (sm_100a) hot-path library  (libdeepfluids_b200.so)
+ *
+ * The reference (byungsook/deep-fluids) has no plugin/FFI layer: its hot path is Python graph code whose
+ * arithmetic runs inside TensorFlow 1.15.  This header is the boundary a maintainer would bind instead of
+ * those TF ops (see INTEGRATION.md for the ctypes stub); each entry point names the reference interface it
+ * replaces.  Conventions:
+ *   - plain pointers and sizes only; every pointer is a DEVICE pointer owned by the caller (PyTorch allocates);
+ *   - channels-last tensors: NHWC [B,H,W,C] / NDHWC [B,D,H,W,C]  (reference ops.py:228 "bzyxd");
+ *   - `dims` = {B,H,W} (ndim = 2) or {B,D,H,W} (ndim = 3);  `stream` is a cudaStream_t passed as void*;
+ *   - dtype codes: DFL_F32 = 0, DFL_BF16 = 1;
+ *   - asynchronous on `stream`, never allocates, never synchronises;
+ *   - returns 0 on success, a negative DFL_ERR_* code otherwise; message via dfl_last_error() (thread-local).
+ * There is NO CPU fallback: without a CUDA device / sm_100a the calls fail with DFL_ERR_CUDA.
+ */
+#ifndef DEEPFLUIDS_B200_H_
+#define DEEPFLUIDS_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DFL_F32 0
+#define DFL_BF16 1
+
+#define DFL_OK 0
+#define DFL_ERR_ARG (-1)
+#define DFL_ERR_CUDA (-2)
+#define DFL_ERR_UNSUPPORTED (-3)
+#define DFL_ERR_INIT (-4)
+
+/* conv epilogue flags */
+#define DFL_CONV_LRELU 1          /* y = max(v, 0.2 v)                      (ops.py:9-10)            */
+#define DFL_CONV_OUT2_UPSAMPLE 2  /* out2 is written nearest-x2 upsampled   (ops.py:75-91)          */
+
+/* ---- lifecycle ------------------------------------------------------------------------------------- */
+int dfl_version(void);
+const char* dfl_last_error(void);
+/* bind the calling thread to CUDA device `device`, resolve the TMA driver entry point, query the SM count.
+ * Replaces config.py:76-77 (CUDA_VISIBLE_DEVICES selection) for the library. */
+int dfl_init(int device);
+
+/* ---- finite-difference stencils (reference ops.py:205-290) ------------------------------------------- */
+/* ops.curl (ops.py:264-274; 2D, reads channel 0 of a `pot_channels`-channel tensor) and the 3D curl =
+ * second return of ops.jacobian3 (ops.py:255-260, trainer3.py:18).  vel: 2 (2D) / 3 (3D) channels. */
+int dfl_curl_fwd(const void* pot, void* vel, const int64_t* dims, int ndim, int pot_channels, int dtype, void* stream);
+/* ops.jacobian (ops.py:205-225): jac 4 ch, vort 1 ch;  ops.jacobian3 (ops.py:227-262): jac 9 ch, curl 3 ch.
+ * `jac` or `vort_or_curl` may be NULL. */
+int dfl_jacobian_fwd(const void* vel, void* jac, void* vort_or_curl, const int64_t* dims, int ndim, int dtype,
+                     void* stream);
+/* ops.divergence / ops.divergence3 (ops.py:276-290): out [B,(D-1,)H-1,W-1,1]. */
+int dfl_divergence(const void* vel, void* div, const int64_t* dims, int ndim, int dtype, void* stream);
+
+/* Fused loss + gradient (SURVEY.md 8a "S").  Replaces, in one pass: curl (trainer.py:140 / trainer3.py:18),
+ * jacobian of prediction and target (trainer.py:32,146 / trainer3.py:24), both L1 means (trainer.py:170-172 /
+ * trainer3.py:49-51) and the TF autodiff of all of it w.r.t. the network output.
+ *   pot   [..,pot_channels] network output (stream function, channel 0 / 3-ch vector potential)
+ *   x     [..,2|3]          target velocity
+ *   dpot  [..,1|3]          OUT  grad_scale * dL/dpot                    (dtype = dtype_pot)
+ *   vel   [..,2|3] or NULL  OUT  G_ = curl(pot)                          (dtype = dtype_pot)
+ *   loss3 float[3]          OUT  {w1*l1 + w2*jl1, l1, jl1}  (means; deterministic reduction)
+ *   workspace               dfl_stencil_loss_workspace_bytes(dims, ndim) bytes */
+size_t dfl_stencil_loss_workspace_bytes(const int64_t* dims, int ndim);
+int dfl_stencil_loss_fwdbwd(const void* pot, const void* x, void* dpot, void* vel, float* loss3, void* workspace,
+                            const int64_t* dims, int ndim, int pot_channels, float w1, float w2, float grad_scale,
+                            int dtype_pot, int dtype_x, void* stream);
+
+/* ---- fully connected (slim.fully_connected, activation None: ops.py:23-24, model.py:19,61) ------------ */
+/* out[b,n] = sum_k z[b,k] W[k,n] + bias[n];  z,W,bias fp32 (W in TF [in,out] layout), K <= 16, B <= 64. */
+int dfl_fc_fwd(const float* z, const float* W, const float* bias, void* out, int B, int K, int N, int out_dtype,
+               void* stream);
+/* dW[k,n] = sum_b z[b,k] dout[b,n];  db[n] = sum_b dout[b,n]   (overwritten) */
+int dfl_fc_bwd(const float* z, const void* dout, float* dW, float* db, int B, int K, int N, int dout_dtype,
+               void* stream);
+
+/* ---- 3x3 / 3x3x3 convolution, stride 1, SAME (slim.conv2d / slim.conv3d: ops.py:12-16) ----------------- */
+/* fp32 TF-layout weights [taps][Cin][Cout] (HWIO / DHWIO) -> bf16 GEMM operands for forward and dgrad. */
+int dfl_pack_conv_weights(const float* w, void* w_fwd, void* w_dgrad, int taps, int cin, int cout, void* stream);
+/* Implicit-GEMM conv on tcgen05 tensor cores, bf16 in / fp32 accumulate, Cin % 64 == 0, Cout == 128.
+ *   v    = conv(x, w_packed) + bias;   if (flags & DFL_CONV_LRELU) v = lrelu(v);
+ *   if (mask_src) v *= lrelu'(mask_src)                       (dgrad: derivative of the layer below)
+ *   if (out)  out  = v
+ *   if (out2) out2 = v + residual (residual may be NULL), nearest-x2 upsampled if DFL_CONV_OUT2_UPSAMPLE
+ * Forward use: model.py:26-36 / :68-79 (conv + lrelu [+ residual add + upscale]).  Backward use (dgrad): pass
+ * w_dgrad from dfl_pack_conv_weights, bias = NULL. */
+int dfl_conv3x3_fwd(const void* x, const void* w_packed, const float* bias, void* out, void* out2,
+                    const void* residual, const void* mask_src, const int64_t* dims, int ndim, int cin, int cout,
+                    int flags, void* stream);
+/* dW[tap][ci][co] += sum_p x[p+tap-1][ci] * dpre[p][co]   (fp32, TF layout, accumulated: zero it first). */
+int dfl_conv3x3_wgrad(const void* x, const void* dpre, float* dw, const int64_t* dims, int ndim, int cin, int cout,
+                      void* stream);
+/* db[c] += sum_p dpre[p][c]   (dpre bf16 [npos][128]) */
+int dfl_bias_grad(const void* dpre, float* db, size_t npos, void* stream);
+
+/* last conv 128 -> cout (1..3), no activation (model.py:42,84): x bf16, w fp32 [taps][128][cout], out fp32 */
+int dfl_lastconv_fwd(const void* x, const float* w, const float* bias, float* out, const int64_t* dims, int ndim,
+                     int cout, void* stream);
+/* dx = conv^T(dout, w) (bf16, may be NULL);  dx_masked = dx * lrelu'(mask_src) (bf16, may be NULL) */
+int dfl_lastconv_dgrad(const float* dout, const float* w, const void* mask_src, void* dx, void* dx_masked,
+                       const int64_t* dims, int ndim, int cout, void* stream);
+/* dw += x^T dout, db += sum dout  (fp32, accumulated) */
+int dfl_lastconv_wgrad(const void* x, const float* dout, float* dw, float* db, const int64_t* dims, int ndim,
+                       int cout, void* stream);
+
+/* adjoint of nearest-x2 upsampling fused with the lrelu derivative (model.py:35-36 / :77-78 backward):
+ *   ds = sum of the 2x2(x2) children of g;  dmasked = ds * lrelu'(mask_src).  cdims = COARSE dims. */
+int dfl_pool_mask(const void* g, const void* mask_src, void* ds, void* dmasked, const int64_t* cdims, int ndim,
+                  void* stream);
+
+/* ---- optimizer (tf.train.AdamOptimizer / GradientDescentOptimizer: trainer.py:160-165) ----------------- */
+/* flat fp32 buffers; lr_t = lr*sqrt(1-b2^t)/(1-b1^t) computed by the caller; m = v = NULL selects plain GD. */
+int dfl_adam_step(float* param, const float* grad, float* m, float* v, size_t n, float lr_t, float beta1, float beta2,
+                  float eps, float grad_scale, void* stream);
+
+/* ---- misc ------------------------------------------------------------------------------------------- */
+int dfl_cast_f32_bf16(const float* in, void* out, size_t n, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DEEPFLUIDS_B200_H_ */

@@ -1,0 +1,108 @@
+"""TEST INFRASTRUCTURE ONLY -- CPU oracle for the deep-fluids train step (loss, Adam, LR schedule).
+
+Restates trainer.py:136-184 / trainer3.py:14-63 (generator `build_model`: G_s -> curl -> jacobian ->
+L1 + Jacobian-L1 loss -> Adam.minimize), trainer.py:357-396 / trainer3.py:240-279 (AE variant),
+trainer.py:69-80,284-288 (LR schedule).  Backward = torch autograd over the fp32/fp64 restatement.
+Parity status: stencils/loss pinned via the tf shim (oracle/make_golden.py); conv/FC/Adam unpinned
+(TensorFlow 1.15 not available) -- see oracle/ref_ops.py.
+"""
+import math
+from collections import OrderedDict
+
+import torch
+
+from . import ref_ops as R
+from . import ref_model as M
+
+
+def stencil_loss(pot_or_vel, x, w1=1.0, w2=1.0, use_curl=True):
+    """Loss of the de/ae path given the network output and the target velocity x.
+
+    2D: pot [B,H,W,>=1] -> G_=curl(pot) (trainer.py:140);  3D: pot [B,D,H,W,3] -> G_=jacobian3(pot)[1]
+    (trainer3.py:18).  loss = w1*mean|G_-x| + w2*mean|J(G_)-J(x)| (trainer.py:170-172, trainer3.py:49-51).
+    Returns (loss, l1, j_l1, G_)."""
+    is3d = x.dim() == 5
+    if use_curl:
+        g = R.curl3(pot_or_vel) if is3d else R.curl(pot_or_vel)
+    else:
+        g = pot_or_vel
+    jac = R.jacobian3 if is3d else R.jacobian
+    l1 = (g - x).abs().mean()
+    jl1 = (jac(g)[0] - jac(x)[0]).abs().mean()
+    return w1 * l1 + w2 * jl1, l1, jl1, g
+
+
+class TFAdam(object):
+    """tf.train.AdamOptimizer(lr, beta1, beta2, epsilon=1e-8) semantics (trainer.py:160-162):
+        lr_t = lr*sqrt(1-b2^t)/(1-b1^t);  m = b1 m + (1-b1) g;  v = b2 v + (1-b2) g^2
+        theta -= lr_t * m / (sqrt(v) + eps)          (epsilon NOT bias-corrected: differs from torch.optim.Adam)
+    """
+
+    def __init__(self, var, beta1=0.5, beta2=0.999, eps=1e-8):
+        self.b1, self.b2, self.eps = beta1, beta2, eps
+        self.t = 0
+        self.m = OrderedDict((k, torch.zeros_like(v)) for k, v in var.items())
+        self.v = OrderedDict((k, torch.zeros_like(v)) for k, v in var.items())
+
+    def step(self, var, grads, lr):
+        self.t += 1
+        lr_t = lr * math.sqrt(1.0 - self.b2 ** self.t) / (1.0 - self.b1 ** self.t)
+        for k in var:
+            g = grads[k]
+            self.m[k].mul_(self.b1).add_(g, alpha=1 - self.b1)
+            self.v[k].mul_(self.b2).addcmul_(g, g, value=1 - self.b2)
+            var[k].sub_(lr_t * self.m[k] / (self.v[k].sqrt() + self.eps))
+
+
+def lr_decay(step, max_step, lr_max=1e-4, lr_min=2.5e-6):
+    """g_lr_update of trainer.py:74-75, evaluated with the already-incremented global step
+    (it runs after the optimizer op, trainer.py:284-288; the first step uses lr_max)."""
+    return lr_min + 0.5 * (lr_max - lr_min) * (math.cos(step * math.pi / max_step) + 1)
+
+
+def lr_step(lr, lr_min=2.5e-6):
+    """'step' schedule, trainer.py:77-78."""
+    return max(lr * 0.5, lr_min)
+
+
+def generator_loss_and_grads(z, x, var, filters=128, num_conv=4, repeat=0, w1=1.0, w2=1.0,
+                             use_curl=True, name="G"):
+    """One forward+backward of `build_model` (arch=de). Returns (loss, l1, jl1, G_, grads dict)."""
+    is3d = x.dim() == 5
+    cout = (3 if is3d else 1) if use_curl else x.shape[-1]
+    output_shape = list(x.shape[1:-1]) + [cout]
+    leaves = OrderedDict((k, v.detach().clone().requires_grad_(True)) for k, v in var.items())
+    pot = M.generator_forward(z, leaves, output_shape, filters, num_conv, repeat, name)
+    loss, l1, jl1, g = stencil_loss(pot, x, w1, w2, use_curl)
+    gs = torch.autograd.grad(loss, list(leaves.values()))
+    grads = OrderedDict((k, gi) for k, gi in zip(leaves.keys(), gs))
+    return loss.detach(), l1.detach(), jl1.detach(), g.detach(), pot.detach(), grads
+
+
+def ae_loss_and_grads(x, y_last, var, p_num, filters=128, z_num=16, num_conv=4, repeat=0,
+                      w1=1.0, w2=1.0, w4=1.0, use_curl=True, name="AE"):
+    """One forward+backward of `build_model_ae` (trainer.py:357-396 / trainer3.py:240-279).
+    y_last = y[:,:,-1] [B,p_num]; loss_p = mean((y_last - z[:,-p_num:])^2)."""
+    leaves = OrderedDict((k, v.detach().clone().requires_grad_(True)) for k, v in var.items())
+    s, z = M.ae_forward(x, leaves, filters, z_num, num_conv, repeat, name)
+    loss, l1, jl1, g = stencil_loss(s, x, w1, w2, use_curl)
+    loss_p = ((y_last - z[:, -p_num:]) ** 2).mean()
+    total = loss + w4 * loss_p
+    gs = torch.autograd.grad(total, list(leaves.values()))
+    grads = OrderedDict((k, gi) for k, gi in zip(leaves.keys(), gs))
+    return total.detach(), l1.detach(), jl1.detach(), loss_p.detach(), g.detach(), z.detach(), grads
+
+
+def synthetic_batch(batch, spatial, seed=123, z_dim=3, dtype=torch.float32, smooth=2):
+    """params y~U[-1,1] [B,z_dim]; target velocity = reference-curl of a smoothed
+    N(0,1) potential scaled to max|x|=1 (mirrors x/=x_range, data.py:329)."""
+    g = torch.Generator().manual_seed(seed)
+    y = torch.rand(batch, z_dim, generator=g, dtype=torch.float64) * 2 - 1
+    nd = len(spatial)
+    pot = torch.randn([batch] + list(spatial) + [1 if nd == 2 else 3], generator=g, dtype=torch.float64)
+    for _ in range(smooth):  # cheap separable box smoothing, band-limits the field
+        for ax in range(1, nd + 1):
+            pot = (pot + torch.roll(pot, 1, ax) + torch.roll(pot, -1, ax)) / 3.0
+    x = R.curl(pot) if nd == 2 else R.curl3(pot)
+    x = x / x.abs().max()
+    return x.to(dtype), y.to(dtype)
