@@ -1,0 +1,228 @@
+"""Generator train-step engine: plans buffers once, then drives the C-ABI kernels in a fixed order.
+
+This is the B200 replacement for what `sess.run(g_optim)` executes in the reference (trainer.py:269 /
+trainer3.py:156): GeneratorBE/GeneratorBE3 forward (model.py:5-87), curl + Jacobian-L1 loss
+(trainer.py:138-172 / trainer3.py:16-51), TF autodiff backward and AdamOptimizer.minimize (trainer.py:160-184).
+
+Data layout in HBM (all channels-last, ops.py:228):
+  * activations  bf16 [B,(D,)H,W,128]; every conv output y (post leaky-ReLU) is kept for the backward pass
+    (it is the next layer's wgrad operand and its sign gives the leaky-ReLU derivative);
+  * `x0` of block i+1 is written directly by the last conv of block i (fused residual add + nearest x2 upsample);
+  * parameters   one flat fp32 buffer with TF-named, TF-laid-out views (`G/<n>_conv/weights` = [k,(k,)k,Cin,Cout]),
+    matching flat fp32 gradient / Adam-m / Adam-v buffers (one fused Adam launch, one all-reduce);
+  * GEMM operands bf16 re-packs of the conv weights (forward: [Cout, taps*Cin]; dgrad: [Cin, taps'*Cout]).
+"""
+import math
+from collections import OrderedDict
+
+import numpy as np
+import torch
+
+from . import kernels as K
+
+
+def _repeat_num(spatial, repeat):
+    rep = int(np.log2(np.max(spatial))) - 2 if repeat == 0 else repeat   # model.py:9-12 / :51-54
+    assert rep > 0 and sum(int(i) % (2 ** (rep - 1)) for i in spatial) == 0
+    return rep
+
+
+def xavier_uniform(shape, generator, device):
+    """slim default initializer (xavier_initializer, uniform): U(-l,l), l = sqrt(6/(fan_in+fan_out))."""
+    rf = 1
+    for s in shape[:-2]:
+        rf *= s
+    lim = math.sqrt(6.0 / (rf * shape[-2] + rf * shape[-1]))
+    return (torch.rand(shape, generator=generator, dtype=torch.float64) * 2 - 1).mul_(lim).float().to(device)
+
+
+class FlatParams(object):
+    """One flat fp32 buffer + named TF-layout views; companion grad / m / v buffers."""
+
+    def __init__(self, table, device):
+        self.table = OrderedDict(table)
+        self.offsets = OrderedDict()
+        off = 0
+        for k, shp in self.table.items():
+            self.offsets[k] = off
+            off += (int(np.prod(shp)) + 63) // 64 * 64      # keep every view 256-byte aligned
+        self.total = off
+        self.data = torch.zeros(off, dtype=torch.float32, device=device)
+        self.grad = torch.zeros(off, dtype=torch.float32, device=device)
+        self.m = torch.zeros(off, dtype=torch.float32, device=device)
+        self.v = torch.zeros(off, dtype=torch.float32, device=device)
+
+    def _view(self, buf, k):
+        n = int(np.prod(self.table[k]))
+        return buf[self.offsets[k]:self.offsets[k] + n].view(*self.table[k])
+
+    def p(self, k):
+        return self._view(self.data, k)
+
+    def g(self, k):
+        return self._view(self.grad, k)
+
+    def num_params(self):
+        return int(sum(int(np.prod(s)) for s in self.table.values()))
+
+    def state_dict(self):
+        return OrderedDict((k, self.p(k).detach().cpu().clone()) for k in self.table)
+
+    def load_state_dict(self, sd):
+        for k in self.table:
+            self.p(k).copy_(torch.as_tensor(sd[k]).to(self.data.device).view(*self.table[k]))
+
+
+class GeneratorEngine(object):
+    """GeneratorBE / GeneratorBE3 (skip_concat=False) forward + backward on hand-written sm_100a kernels."""
+
+    def __init__(self, batch, output_shape, z_dim=3, filters=128, num_conv=4, repeat=0, name="G", device=None,
+                 seed=123, init=None):
+        assert filters == 128, "the tensor-core conv kernels are specialised for filters=128 (config.py:21 default)"
+        self.device = device or torch.device("cuda", torch.cuda.current_device())
+        self.B, self.name, self.filters, self.num_conv = int(batch), name, filters, int(num_conv)
+        self.spatial = [int(s) for s in output_shape[:-1]]
+        self.cout = int(output_shape[-1])
+        self.nd = len(self.spatial)
+        self.z_dim = int(z_dim)
+        self.rep = _repeat_num(self.spatial, repeat)
+        self.level_shape = [[int(s // 2 ** (self.rep - 1 - i)) for s in self.spatial] for i in range(self.rep)]
+        self.taps = 3 ** self.nd
+        # ---- variables, TF names & layouts (model.py:19,26,42 / :61,68,84)
+        tab = OrderedDict()
+        n_fc = int(np.prod(self.level_shape[0])) * filters
+        tab["%s/0_fc/weights" % name] = (self.z_dim, n_fc)
+        tab["%s/0_fc/biases" % name] = (n_fc,)
+        self.conv_names = []
+        n = 1
+        for i in range(self.rep):
+            row = []
+            for _ in range(self.num_conv):
+                tab["%s/%d_conv/weights" % (name, n)] = (3,) * self.nd + (filters, filters)
+                tab["%s/%d_conv/biases" % (name, n)] = (filters,)
+                row.append("%s/%d_conv" % (name, n))
+                n += 1
+            self.conv_names.append(row)
+        self.last_name = "%s/%d_conv" % (name, n)
+        tab[self.last_name + "/weights"] = (3,) * self.nd + (filters, self.cout)
+        tab[self.last_name + "/biases"] = (self.cout,)
+        self.params = FlatParams(tab, self.device)
+        if init is not None:
+            self.params.load_state_dict(init)
+        else:
+            g = torch.Generator().manual_seed(seed)
+            for k, shp in tab.items():
+                if k.endswith("weights"):
+                    self.params.p(k).copy_(xavier_uniform(tuple(shp), g, self.device))
+        self.variables = list(tab.keys())
+        # ---- bf16 GEMM operands
+        self.wf, self.wd = {}, {}
+        for row in self.conv_names:
+            for cn in row:
+                self.wf[cn] = torch.empty(filters, self.taps * filters, dtype=torch.bfloat16, device=self.device)
+                self.wd[cn] = torch.empty(filters, self.taps * filters, dtype=torch.bfloat16, device=self.device)
+        self.repack()
+        # ---- activations (bf16) and gradient scratch
+        bf = dict(dtype=torch.bfloat16, device=self.device)
+        self.x0, self.y = [], []
+        for i in range(self.rep):
+            shp = [self.B] + self.level_shape[i] + [filters]
+            self.x0.append(torch.empty(shp, **bf))
+            self.y.append([torch.empty(shp, **bf) for _ in range(self.num_conv)])
+        top = [self.B] + self.level_shape[-1] + [filters]
+        self.s = torch.empty(top, **bf)
+        self.pot = torch.empty([self.B] + self.spatial + [self.cout], dtype=torch.float32, device=self.device)
+        # gradient scratch is sized for the finest level and re-viewed per level
+        self._gbuf = [torch.empty(top, **bf) for _ in range(4)]
+        self.z = None
+        self.adam_t = 0
+
+    # ------------------------------------------------------------------ helpers
+    def _gview(self, k, level):
+        shp = [self.B] + self.level_shape[level] + [self.filters]
+        n = int(np.prod(shp))
+        return self._gbuf[k].view(-1)[:n].view(shp)
+
+    def repack(self):
+        """fp32 master weights -> bf16 tensor-core operands (after every optimizer step)."""
+        for row in self.conv_names:
+            for cn in row:
+                K.pack_conv_weights(self.params.p(cn + "/weights"), self.wf[cn], self.wd[cn])
+
+    # ------------------------------------------------------------------ forward (model.py:5-46 / :48-87)
+    def forward(self, z):
+        P = self.params
+        self.z = z.contiguous().float()
+        assert self.z.shape == (self.B, self.z_dim)
+        K.fc_fwd(self.z, P.p(self.name + "/0_fc/weights"), P.p(self.name + "/0_fc/biases"),
+                 out=self.x0[0].view(self.B, -1))
+        for i in range(self.rep):
+            cur = self.x0[i]
+            for c in range(self.num_conv):
+                cn = self.conv_names[i][c]
+                bias = P.p(cn + "/biases")
+                if c < self.num_conv - 1:
+                    K.conv3x3(cur, self.wf[cn], bias, out=self.y[i][c], flags=K.CONV_LRELU)
+                elif i < self.rep - 1:   # x += x0; x = upscale(x, 2); x0 = x   (model.py:34-37 / :76-79)
+                    K.conv3x3(cur, self.wf[cn], bias, out=self.y[i][c], out2=self.x0[i + 1], residual=self.x0[i],
+                              flags=K.CONV_LRELU | K.CONV_OUT2_UPSAMPLE)
+                else:                    # x += x0                                 (model.py:39 / :82)
+                    K.conv3x3(cur, self.wf[cn], bias, out=self.y[i][c], out2=self.s, residual=self.x0[i],
+                              flags=K.CONV_LRELU)
+                cur = self.y[i][c]
+        K.lastconv_fwd(self.s, P.p(self.last_name + "/weights"), P.p(self.last_name + "/biases"), out=self.pot)
+        return self.pot
+
+    # ------------------------------------------------------------------ backward (TF autodiff of the above)
+    def backward(self, dpot):
+        """dpot: fp32 gradient w.r.t. the generator output.  Accumulates into params.grad (call zero_grad first)."""
+        P = self.params
+        nc = self.num_conv
+        top = self.rep - 1
+        K.lastconv_wgrad(self.s, dpot, P.g(self.last_name + "/weights"), P.g(self.last_name + "/biases"))
+        ds = self._gview(0, top)
+        dpre = self._gview(1, top)
+        K.lastconv_dgrad(dpot, P.p(self.last_name + "/weights"), self.y[top][nc - 1], ds, dpre)
+        for i in range(top, -1, -1):
+            other = self._gview(2, i)
+            gx0 = self._gview(3, i)
+            for c in range(nc - 1, -1, -1):
+                cn = self.conv_names[i][c]
+                xin = self.y[i][c - 1] if c > 0 else self.x0[i]
+                K.conv3x3_wgrad(xin, dpre, P.g(cn + "/weights"))
+                K.bias_grad(dpre, P.g(cn + "/biases"))
+                if c > 0:     # dL/d(pre-activation of layer c-1) = dgrad * lrelu'(y[c-1])
+                    K.conv3x3(dpre, self.wd[cn], None, out=other, mask_src=self.y[i][c - 1])
+                    dpre, other = other, dpre
+                else:         # dL/dx0 = dgrad + residual-branch gradient ds
+                    K.conv3x3(dpre, self.wd[cn], None, out2=gx0, residual=ds)
+            if i > 0:         # x0[i] = upscale(y4[i-1] + x0[i-1]): pool the children, then the lrelu derivative
+                ds = self._gview(0, i - 1)
+                dpre = self._gview(1, i - 1)
+                K.pool_mask(gx0, self.y[i - 1][nc - 1], ds, dpre)
+            else:
+                K.fc_bwd(self.z, gx0.view(self.B, -1), P.g(self.name + "/0_fc/weights"), P.g(self.name + "/0_fc/biases"))
+
+    def zero_grad(self):
+        self.params.grad.zero_()
+
+    # ------------------------------------------------------------------ optimizer (trainer.py:160-165,184)
+    def adam_step(self, lr, beta1=0.5, beta2=0.999, eps=1e-8, grad_scale=1.0):
+        self.adam_t += 1
+        t = self.adam_t
+        lr_t = lr * math.sqrt(1.0 - beta2 ** t) / (1.0 - beta1 ** t)
+        P = self.params
+        K.adam_step(P.data, P.grad, P.m, P.v, lr_t, beta1, beta2, eps, grad_scale)
+        self.repack()
+
+    def sgd_step(self, lr, grad_scale=1.0):
+        P = self.params
+        K.adam_step(P.data, P.grad, None, None, lr, 0.0, 0.0, 0.0, grad_scale)
+        self.repack()
+
+    # kernel launches of one forward+backward+update (for bench.py's gpu_launches claim)
+    def launches_per_step(self):
+        n_conv = self.rep * self.num_conv
+        fwd = 1 + n_conv + 1
+        bwd = 2 + n_conv * 3 + (self.rep - 1) + 1
+        return fwd + 2 + bwd + 1 + 1 + n_conv   # + stencil(2) + memset + adam + repack

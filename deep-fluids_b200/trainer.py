@@ -1,0 +1,193 @@
+"""Trainer with the reference's constructor / method / attribute names (trainer.py:12-293), eager and B200-native.
+
+Where the reference builds a TF graph and runs `sess.run(self.g_optim)` (trainer.py:269), `train_step()` here issues
+the same computation as a fixed sequence of sm_100a kernels through the C-ABI:
+    x, y = batch()                                    (trainer.py:17; dequeue)
+    G_s  = GeneratorBE(y)                             (trainer.py:138)   engine.forward
+    G_   = curl(G_s); jacobians; g_loss               (trainer.py:140-172) one fused stencil kernel (loss + dL/dG_s)
+    grads, Adam                                       (trainer.py:160-184) engine.backward + fused Adam
+    g_lr update                                       (trainer.py:284-288)
+Data parallelism (new; the reference is single-GPU): when torch.distributed is initialised the flat fp32 gradient
+buffer is summed with ONE NCCL all-reduce per step and the 1/world factor is folded into the Adam kernel.
+Out of scope here: arch 'dg'/'nn', summaries/images, test()/generate() dumps.
+"""
+import math
+import os
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from . import kernels as K
+from .engine import GeneratorEngine
+
+
+class Trainer(object):
+    def __init__(self, config, batch_manager):
+        self.config = config
+        self.batch_manager = batch_manager
+        self.x, self.y = batch_manager.batch()     # normalized input (trainer.py:17)
+        self.device = self.x.device
+
+        self.is_3d = config.is_3d
+        self.dataset = config.dataset
+        self.data_type = config.data_type
+        self.arch = config.arch
+        if 'nn' in self.arch or 'dg' in self.arch:
+            raise NotImplementedError("arch '%s' is outside the B200 hot path (SURVEY.md 2: de/ae only)" % self.arch)
+
+        self.res_x, self.res_y, self.res_z = config.res_x, config.res_y, config.res_z
+        self.c_num = batch_manager.c_num
+        self.b_num = config.batch_size
+        self.test_b_num = config.test_batch_size
+        self.repeat = config.repeat
+        self.filters = config.filters
+        self.num_conv = config.num_conv
+        self.w1, self.w2 = config.w1, config.w2
+
+        self.use_c = config.use_curl
+        spatial = list(self.x.shape[1:-1])
+        if self.use_c:                              # trainer.py:48-55
+            self.output_shape = spatial + [3 if self.is_3d else 1]
+        else:
+            self.output_shape = spatial + [self.x.shape[-1]]
+
+        self.optimizer = config.optimizer
+        self.beta1, self.beta2 = config.beta1, config.beta2
+        self.model_dir = getattr(config, "model_dir", "")
+        self.load_path = config.load_path
+
+        self.start_step = config.start_step
+        self.step = self.start_step                 # tf.Variable 'step' (trainer.py:65)
+        self.max_step = int(config.max_epoch // batch_manager.epochs_per_step)   # trainer.py:67
+        if getattr(config, "max_step", 0):
+            self.max_step = int(config.max_step)
+
+        self.lr_update = config.lr_update
+        self.lr_min, self.lr_max = config.lr_min, config.lr_max
+        if self.lr_update not in ('decay', 'step'):
+            raise Exception("[!] Invalid lr update method")     # trainer.py:80
+        self.g_lr = config.lr_max                   # trainer.py:72 / :77
+
+        self.lr_update_step = config.lr_update_step
+        self.log_step = config.log_step
+        self.test_step = config.test_step
+        self.save_sec = config.save_sec
+        self.is_train = config.is_train
+
+        self.world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+        self.rank = dist.get_rank() if self.world > 1 else 0
+
+        if 'ae' in self.arch:
+            raise NotImplementedError("arch 'ae' (BASELINE config 5) is the next SURVEY 8 row; not built in round 1")
+        self.build_model()
+
+        if self.load_path and os.path.exists(os.path.join(self.load_path, "model.pt")):
+            self.load(os.path.join(self.load_path, "model.pt"))
+
+    # ------------------------------------------------------------------ build (trainer.py:136-184)
+    def build_model(self):
+        if not self.use_c:
+            raise NotImplementedError("use_curl=False output path is not built yet (BASELINE configs all use curl)")
+        if self.optimizer not in ('adam', 'gd'):
+            raise Exception("[!] Invalid opimizer")              # sic, trainer.py:167
+        self.engine = GeneratorEngine(self.b_num, self.output_shape, z_dim=self.c_num, filters=self.filters,
+                                      num_conv=self.num_conv, repeat=self.repeat, name="G", device=self.device,
+                                      seed=self.config.random_seed)
+        self.G_var = self.engine.variables
+        self.G_s = self.engine.pot
+        self._loss3 = torch.zeros(3, dtype=torch.float32, device=self.device)
+        self._dpot = torch.empty_like(self.engine.pot)
+        nb = K.cabi.lib().dfl_stencil_loss_workspace_bytes(K.dims_array(self.x.shape[:-1]), self.x.dim() - 2)
+        self._ws = torch.empty(nb, dtype=torch.uint8, device=self.device)
+        self.G_ = None
+        self.g_loss = self.g_loss_l1 = self.g_loss_j_l1 = None
+
+    # ------------------------------------------------------------------ one `sess.run(self.g_optim)`
+    def train_step(self, x=None, y=None, want_vel=False):
+        if x is None:
+            x, y = self.batch_manager.batch()
+        self.x, self.y = x, y
+        eng = self.engine
+        eng.zero_grad()
+        pot = eng.forward(y)
+        _, _, vel = K.stencil_loss_fwdbwd(pot, x, self.w1, self.w2, 1.0, want_vel=want_vel, dpot=self._dpot,
+                                          loss3=self._loss3, workspace=self._ws)
+        if want_vel:
+            self.G_ = vel
+        eng.backward(self._dpot)
+        scale = 1.0
+        if self.world > 1:
+            dist.all_reduce(eng.params.grad)        # ONE NCCL all-reduce over the flat gradient buffer
+            scale = 1.0 / self.world
+        if self.optimizer == 'adam':
+            eng.adam_step(self.g_lr, self.beta1, self.beta2, 1e-8, scale)
+        else:
+            eng.sgd_step(self.g_lr, scale)
+        self.step += 1
+        return self._loss3
+
+    def update_lr(self, step_in_loop):
+        """`sess.run(self.g_lr_update)` (trainer.py:284-288): evaluated with the already-incremented global step."""
+        if self.lr_update == 'step':
+            if step_in_loop % self.lr_update_step == self.lr_update_step - 1:
+                self.g_lr = max(self.g_lr * 0.5, self.lr_min)
+        else:
+            self.g_lr = self.lr_min + 0.5 * (self.lr_max - self.lr_min) * (math.cos(self.step * math.pi / self.max_step) + 1)
+
+    def losses(self):
+        """(g_loss, g_loss_l1, g_loss_j_l1) of the last step as Python floats (one D2H read)."""
+        l = self._loss3.tolist()
+        self.g_loss, self.g_loss_l1, self.g_loss_j_l1 = l
+        return l
+
+    # ------------------------------------------------------------------ loops (trainer.py:224-293)
+    def train(self):
+        if 'ae' in self.arch:
+            self.train_ae()
+        else:
+            self.train_()
+
+    def train_(self):
+        for step in range(self.start_step, self.max_step):
+            self.train_step()
+            if step % self.log_step == 0 or step == self.max_step - 1:
+                ep = step * self.batch_manager.epochs_per_step
+                loss = self.losses()[0]
+                assert not np.isnan(loss), 'Model diverged with loss = NaN'      # trainer.py:275
+                if self.rank == 0:
+                    print("\n[{}/{}/ep{:.2f}] Loss: {:.6f}".format(step, self.max_step, ep, loss))
+            self.update_lr(step)
+        if self.model_dir and self.rank == 0:
+            self.save(os.path.join(self.model_dir, 'model.pt'))
+        self.batch_manager.stop_thread()
+
+    def train_ae(self):
+        raise NotImplementedError("arch 'ae' is the next SURVEY 8 row")
+
+    # ------------------------------------------------------------------ generator-only use (trainer.py:295-304)
+    def build_test_model(self):
+        self.z = None
+
+    def generate_velocity(self, z):
+        """G_ = curl(G_s(z)) for a batch of parameters z [b_num, c_num] (the inference half of trainer.py:138-140)."""
+        pot = self.engine.forward(z)
+        return K.curl_fwd(pot)
+
+    def test(self):
+        raise NotImplementedError("test()/generate() dumps are SURVEY 8(f) row N1")
+
+    # ------------------------------------------------------------------ checkpoint (state_dict with TF variable names)
+    def save(self, path):
+        sd = {"variables": self.engine.params.state_dict(), "step": self.step, "g_lr": self.g_lr,
+              "adam_t": self.engine.adam_t, "adam_m": self.engine.params.m.cpu(), "adam_v": self.engine.params.v.cpu()}
+        torch.save(sd, path)
+
+    def load(self, path):
+        sd = torch.load(path, map_location="cpu")
+        self.engine.params.load_state_dict(sd["variables"])
+        self.engine.params.m.copy_(sd["adam_m"])
+        self.engine.params.v.copy_(sd["adam_v"])
+        self.engine.adam_t = sd["adam_t"]
+        self.step, self.g_lr = sd["step"], sd["g_lr"]
+        self.engine.repack()

@@ -102,23 +102,21 @@ def test_curl_divergence_free_full_size():
     assert float(K.divergence(K.curl_fwd(psi)).abs().max()) <= 1e-5
 
 
-def test_stencil_loss_linearity_full_size():
-    """Full-size property: dL/dA of the fused kernel is the adjoint of the (linear) curl+jacobian chain, so
-    <dA, A'> summed over a random direction equals the directional derivative of the loss (finite difference)."""
+def test_stencil_loss_directional_derivative_full_size():
+    """Full-size (64^3) size-independent property: along the direction sign(dL/dA) the finite-difference slope of
+    the fused kernel's loss equals sum|dL/dA| (L1 kinks flip ~eps of the signs -> 2% tolerance)."""
     from deepfluids_b200 import kernels as K
     g = torch.Generator(device="cuda").manual_seed(4)
     A = torch.randn(1, 64, 64, 64, 3, device=dev(), generator=g)
     x = torch.randn(1, 64, 64, 64, 3, device=dev(), generator=g)
-    dirn = torch.randn(1, 64, 64, 64, 3, device=dev(), generator=g)
-    l0, dA, _ = K.stencil_loss_fwdbwd(A, x)
-    dA = dA.clone()
+    _, dA, _ = K.stencil_loss_fwdbwd(A, x)
+    dirn = torch.sign(dA)
     eps = 1e-3
-    lp, _, _ = K.stencil_loss_fwdbwd(A + eps * dirn, x)
-    lp = lp.clone()
-    lm, _, _ = K.stencil_loss_fwdbwd(A - eps * dirn, x)
-    fd = (lp[0].item() - lm[0].item()) / (2 * eps)
-    an = float((dA.double() * dirn.double()).sum())
-    assert abs(fd - an) <= 2e-2 * max(abs(an), 1e-3)
+    lp = K.stencil_loss_fwdbwd(A + eps * dirn, x)[0][0].item()
+    lm = K.stencil_loss_fwdbwd(A - eps * dirn, x)[0][0].item()
+    fd = (lp - lm) / (2 * eps)
+    an = float(dA.double().abs().sum())
+    assert an > 0.1 and abs(fd - an) <= 2e-2 * an
 
 
 # ------------------------------------------------------------------------------------------ convolution

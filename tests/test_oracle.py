@@ -1,0 +1,146 @@
+"""CPU tests (run with -m "not gpu"): the oracle against the committed golden vectors produced by the reference's
+own ops.py (oracle/make_golden.py), plus known-answer tests for the parts the reference never tested."""
+import math
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import ref_model as M
+from oracle import ref_ops as R
+from oracle import ref_train as T
+
+
+def test_golden_2d(golden_dir):
+    g = np.load(golden_dir + "/stencil2d.npz")
+    psi, vel, x = (torch.from_numpy(g[k]) for k in ("psi", "vel", "x"))
+    assert np.array_equal(R.curl(psi).numpy(), g["curl"])
+    j, w = R.jacobian(vel)
+    assert np.array_equal(j.numpy(), g["jac"]) and np.array_equal(w.numpy(), g["vort"])
+    assert np.array_equal(R.divergence(torch.from_numpy(g["curl"])).numpy(), g["div_of_curl"])
+    assert np.array_equal(R.lrelu(vel).numpy(), g["lrelu"])
+    assert np.array_equal(R.upscale(vel, 2).numpy(), g["upscale"])
+    p = psi.clone().requires_grad_(True)
+    loss, l1, jl1, _ = T.stencil_loss(p, x)
+    (dp,) = torch.autograd.grad(loss, p)
+    assert loss.item() == g["loss"].item() and l1.item() == g["loss_l1"].item() and jl1.item() == g["loss_j_l1"].item()
+    assert np.array_equal(dp.numpy(), g["dpsi"])
+
+
+def test_golden_3d(golden_dir):
+    g = np.load(golden_dir + "/stencil3d.npz")
+    A, vel, x = (torch.from_numpy(g[k]) for k in ("A", "vel", "x"))
+    j, c = R.jacobian3(vel)
+    assert np.array_equal(j.numpy(), g["jac"]) and np.array_equal(c.numpy(), g["curl_of_vel"])
+    assert np.array_equal(R.curl3(A).numpy(), g["curl_of_A"])
+    assert np.array_equal(R.divergence3(torch.from_numpy(g["curl_of_A"])).numpy(), g["div_of_curl"])
+    assert np.array_equal(R.upscale3(vel, 2).numpy(), g["upscale3"])
+    a = A.clone().requires_grad_(True)
+    loss, l1, jl1, _ = T.stencil_loss(a, x)
+    (dA,) = torch.autograd.grad(loss, a)
+    assert loss.item() == g["loss"].item()
+    assert np.array_equal(dA.numpy(), g["dA"])
+
+
+def test_curl_is_divergence_free():
+    g = torch.Generator().manual_seed(0)
+    assert float(R.divergence(R.curl(torch.randn(2, 33, 17, 1, generator=g))).abs().max()) <= 1e-5
+    assert float(R.divergence3(R.curl3(torch.randn(2, 9, 12, 15, 3, generator=g))).abs().max()) <= 1e-5
+
+
+def test_fdiff_adjoint_identity():
+    """<D f, g> == <f, D^T g> with the folded-backward-difference adjoint used by the CUDA kernel."""
+    g = torch.Generator().manual_seed(1)
+    for n in (2, 3, 4, 9):
+        f = torch.randn(n, generator=g, dtype=torch.float64)
+        gg = torch.randn(n, generator=g, dtype=torch.float64)
+        gh = gg.clone()
+        gh[n - 2] = gg[n - 2] + gg[n - 1]
+        gh[n - 1] = 0
+        dt = torch.zeros(n, dtype=torch.float64)
+        for k in range(n):
+            dt[k] = (gh[k - 1] if k >= 1 else 0.0) - gh[k]
+        assert abs(float((R.fdiff(f, 0) * gg).sum() - (f * dt).sum())) < 1e-12
+
+
+def test_jacobian_linearity():
+    g = torch.Generator().manual_seed(2)
+    a, b = torch.randn(1, 5, 6, 7, 3, generator=g, dtype=torch.float64), torch.randn(1, 5, 6, 7, 3, generator=g, dtype=torch.float64)
+    assert torch.allclose(R.jacobian3(a)[0] - R.jacobian3(b)[0], R.jacobian3(a - b)[0], atol=1e-12)
+
+
+def test_param_counts_and_shapes():
+    # 2 977 409 / 7 352 451 / 9 122 435 / 41 252 752 / 51 227 155
+    assert M.count_params(M.generator_layout([128, 96, 1])[0]) == 2977409
+    assert M.count_params(M.generator_layout([64, 64, 64, 3])[0]) == 7352451
+    assert M.count_params(M.generator_layout([128, 128, 128, 3])[0]) == 9122435
+    assert M.count_params(M.encoder_layout([128, 128, 128, 3])[0]) == 41252752
+    assert M.count_params(M.ae_layout([128, 128, 128, 3])) == 51227155
+    tab, rep, x0 = M.generator_layout([128, 96, 1])
+    assert rep == 5 and x0 == [8, 6] and list(tab)[0] == "G/0_fc/weights" and list(tab)[-1] == "G/21_conv/biases"
+
+
+def test_conv_same_padding_and_direct_witness():
+    g = torch.Generator().manual_seed(3)
+    x = torch.randn(2, 5, 6, 4, generator=g)
+    w = torch.randn(3, 3, 4, 5, generator=g)
+    b = torch.randn(5, generator=g)
+    assert torch.allclose(R.conv_nd(x, w, b), R.conv_nd_direct(x, w, b), atol=1e-5)
+    x3 = torch.randn(1, 4, 5, 6, 3, generator=g)
+    w3 = torch.randn(3, 3, 3, 3, 2, generator=g)
+    assert torch.allclose(R.conv_nd(x3, w3, torch.zeros(2)), R.conv_nd_direct(x3, w3, torch.zeros(2)), atol=1e-5)
+    # TF SAME at stride 2, k=3, even size: pad (0,1): out[0] reads in[0..2]
+    xi = torch.arange(8.0).reshape(1, 1, 8, 1).repeat(1, 2, 1, 1)
+    wi = torch.zeros(3, 3, 1, 1)
+    wi[0, 0] = 1.0      # picks the top-left tap => input at (2y+0-0, 2x+0-0) with pad_before = 0
+    y = R.conv_nd(xi, wi, torch.zeros(1), stride=2)
+    assert y.shape == (1, 1, 4, 1) and y[0, 0, :, 0].tolist() == [0.0, 2.0, 4.0, 6.0]
+
+
+def test_generator_forward_shapes_small():
+    tab, rep, x0 = M.generator_layout([16, 8, 1], filters=8, num_conv=2)
+    var = M.init_variables(tab, 1)
+    out = M.generator_forward(torch.zeros(3, 3), var, [16, 8, 1], filters=8, num_conv=2)
+    assert out.shape == (3, 16, 8, 1)
+    tab3, _, _ = M.generator_layout([8, 8, 16, 3], filters=4, num_conv=1)
+    out3 = M.generator_forward(torch.zeros(2, 3), M.init_variables(tab3, 1), [8, 8, 16, 3], filters=4, num_conv=1)
+    assert out3.shape == (2, 8, 8, 16, 3)
+    taba = M.ae_layout([16, 16, 2], filters=4, z_num=5, num_conv=2)
+    o, z = M.ae_forward(torch.zeros(2, 16, 16, 2), M.init_variables(taba, 1), filters=4, z_num=5, num_conv=2)
+    assert o.shape == (2, 16, 16, 2) and z.shape == (2, 5)
+
+
+def test_tf_adam_two_step_hand_calc():
+    var = {"p": torch.tensor([1.0], dtype=torch.float64)}
+    opt = T.TFAdam(var, beta1=0.5, beta2=0.999, eps=1e-8)
+    g1, g2, lr = 0.5, -0.25, 0.1
+    opt.step(var, {"p": torch.tensor([g1], dtype=torch.float64)}, lr)
+    m1, v1 = 0.5 * g1, 0.001 * g1 * g1
+    p1 = 1.0 - lr * math.sqrt(1 - 0.999) / (1 - 0.5) * m1 / (math.sqrt(v1) + 1e-8)
+    assert abs(var["p"].item() - p1) < 1e-12
+    opt.step(var, {"p": torch.tensor([g2], dtype=torch.float64)}, lr)
+    m2, v2 = 0.5 * m1 + 0.5 * g2, 0.999 * v1 + 0.001 * g2 * g2
+    p2 = p1 - lr * math.sqrt(1 - 0.999 ** 2) / (1 - 0.25) * m2 / (math.sqrt(v2) + 1e-8)
+    assert abs(var["p"].item() - p2) < 1e-12
+
+
+def test_cosine_lr_endpoints():
+    assert T.lr_decay(0, 1000) == pytest.approx(1e-4)
+    assert T.lr_decay(1000, 1000) == pytest.approx(2.5e-6)
+    assert T.lr_step(1e-4) == 5e-5 and T.lr_step(3e-6) == 2.5e-6
+
+
+def test_upsample_then_conv_equals_phase_convs():
+    """nearest-x2 followed by conv3 == phase-specific 2-tap convs with pre-summed weights (checked along W)."""
+    g = torch.Generator().manual_seed(4)
+    x = torch.randn(1, 1, 6, 2, generator=g, dtype=torch.float64)
+    w = torch.zeros(3, 3, 2, 3, dtype=torch.float64)
+    w[1] = torch.randn(3, 2, 3, generator=g, dtype=torch.float64)    # only the middle kernel row: a 1D conv along W
+    xu = R.upscale(x, 2)[:, :1]                                       # [1,1,12,2]
+    ref = R.conv_nd(xu, w, torch.zeros(3, dtype=torch.float64))[0, 0]
+    xw = torch.nn.functional.pad(x[0, 0], (0, 0, 1, 1))               # [W+2, C]
+    out = torch.zeros(12, 3, dtype=torch.float64)
+    for i in range(6):
+        out[2 * i] = xw[i] @ w[1, 0] + xw[i + 1] @ (w[1, 1] + w[1, 2])
+        out[2 * i + 1] = xw[i + 1] @ (w[1, 0] + w[1, 1]) + xw[i + 2] @ w[1, 2]
+    assert torch.allclose(ref, out, atol=1e-12)
