@@ -1,0 +1,315 @@
+#!/usr/bin/env python
+"""bench.py -- deep-fluids generator train step (fwd + curl/Jacobian loss + bwd + Adam) on N B200s of one node.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c2|c3|c4|tiny] [--impl reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N --steps K --warmup W
+
+A "step" = one pass of the hot path over one batch of synthetic input = one `sess.run(g_optim)` of the reference
+(trainer.py:269 / trainer3.py:156).  Prints ONE JSON line (rank 0).  Fields beyond the base contract:
+  roofline      dominant kernel (tcgen05 conv, fwd+dgrad launches) achieved TFLOP/s vs the measured bf16 peak
+  cpu_baseline  the CPU oracle (torch-CPU restatement of the reference path; TF1 cannot run here) on the host cores
+  e2e           same metric through Trainer.train_step() with HOST (pinned) inputs, H2D + D2H inside the timed region
+`--impl reference` times the oracle on the host cores (the reference's own CPU path is TensorFlow 1.15: not runnable).
+"""
+import argparse
+import json
+import math
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "velocity_fields_per_sec_fwd_bwd"
+UNIT = "fields/s"
+
+# BASELINE.json configs (per-GPU batch; multi-GPU = weak scaling, batch sharded by replication of the per-GPU work)
+WORKLOADS = {
+    # name: (is_3d, res_z, res_y, res_x, per_gpu_batch, description)
+    "c2": (False, 1, 128, 96, 64, "2D smoke_pos_size 128x96 generator+curl, batch 64/GPU (BASELINE configs[1])"),
+    "c3": (True, 64, 64, 64, 16, "3D smoke3_vel_buo 64^3 generator+curl, batch 16/GPU (BASELINE configs[2])"),
+    "c4": (True, 128, 128, 128, 4, "3D smoke3_vel_buo 128^3 generator+curl+grad-loss, batch 4/GPU (BASELINE configs[3])"),
+    "tiny": (False, 1, 32, 24, 4, "2D 32x24 plumbing check"),
+}
+# algorithmic conv FLOPs per field, fwd+bwd
+FLOPS_PER_FIELD = {"c2": 58.0e9, "c3": 3196.0e9, "c4": 25575.0e9, "tiny": None}
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return {"hbm_gbs": d["hbm_gbs"], "tf_burst": d["bf16_tflops"], "tf_sustained": d["bf16_tflops_sustained"],
+                "src": "measured"}
+    return {"hbm_gbs": 6650.0, "tf_burst": 1590.0, "tf_sustained": 1400.0, "src": "fallback"}
+
+
+class ClockSampler(object):
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md clocks line)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.idx, self.rows, self.proc = gpu_index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], None, set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1]))
+                mx = float(r[2])
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                pass
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def make_config(workload, extra=()):
+    from deepfluids_b200 import config as C
+    is3d, rz, ry, rx, b, _ = WORKLOADS[workload]
+    argv = ["--synthetic=true", "--is_3d=%s" % ("true" if is3d else "false"), "--res_x=%d" % rx, "--res_y=%d" % ry,
+            "--res_z=%d" % rz, "--batch_size=%d" % b, "--max_step=1000000"] + list(extra)
+    cfg, _ = C.get_config(argv)
+    return cfg
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# CPU arm: the oracle (faithful torch-CPU restatement; kind = "port") on the host cores
+# ------------------------------------------------------------------------------------------------------------------
+def cpu_oracle_fields_per_sec(workload, steps, warmup, budget_s=25.0):
+    import torch
+    from oracle import ref_model as M          # allowed importer: bench.py cpu_baseline / --impl reference
+    from oracle import ref_train as T
+    is3d, rz, ry, rx, _, _ = WORKLOADS[workload]
+    spatial = [rz, ry, rx] if is3d else [ry, rx]
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    flops = FLOPS_PER_FIELD[workload] or 1e9
+    # bounded sample: batch sized for ~2 s per step at ~0.5 TFLOP/s, at least 1 field
+    b = max(1, min(8, int(2.0 * 0.5e12 / flops)))
+    cout = 3 if is3d else 1
+    tab, _, _ = M.generator_layout(spatial + [cout])
+    var = M.init_variables(tab, 123)
+    opt = T.TFAdam(var, 0.5, 0.999)
+    x, y = T.synthetic_batch(b, spatial, seed=123)
+    times = []
+    t_begin = time.time()
+    for i in range(warmup + steps):
+        t0 = time.time()
+        loss, _, _, _, _, grads = T.generator_loss_and_grads(y, x, var)
+        opt.step(var, grads, 1e-4)
+        dt = time.time() - t0
+        if i >= warmup:
+            times.append(dt)
+        if time.time() - t_begin > budget_s and len(times) >= 1:
+            break
+    per_step = sum(times) / len(times)
+    return {"value": b / per_step, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": "%d timed step(s) of batch %d (fwd+bwd+TF-Adam) of workload %s, fp32 torch-CPU/oneDNN oracle"
+                      % (len(times), b, workload), "ms_per_step": per_step * 1e3, "batch": b}
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    r = cpu_oracle_fields_per_sec(args.workload, max(1, args.steps), min(args.warmup, 1), budget_s=150.0)
+    out = {"impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": args.gpus,
+           "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True,
+           "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+           "config": {"workload": WORKLOADS[args.workload][5], "batch_per_step": r["batch"],
+                      "note": "reference CPU path = TensorFlow 1.15 (not installable); timed = oracle/ torch-CPU port"},
+           "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
+           "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+           "gpu_launches": 0}
+    print(json.dumps(out))
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# GPU arm
+# ------------------------------------------------------------------------------------------------------------------
+def run_gpu_arm(args):
+    import torch
+    import torch.distributed as dist
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    assert world == args.gpus, "--gpus %d but WORLD_SIZE=%d (launch with torch.distributed.run)" % (args.gpus, world)
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    from deepfluids_b200 import kernels as K
+    from deepfluids_b200.data import BatchManager
+    from deepfluids_b200.trainer import Trainer
+    from deepfluids_b200.trainer3 import Trainer3
+
+    cfg = make_config(args.workload)
+    bm = BatchManager(cfg, device=dev, pool=2, rank=rank)
+    tr = (Trainer3 if cfg.is_3d else Trainer)(cfg, bm)
+    B = cfg.batch_size
+    peaks = load_peaks()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed_region(step_fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            step_fn()
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item())
+
+    # ---------------- device-resident arm (`value`) ----------------
+    def step_resident():
+        tr.train_step()
+        tr.update_lr(tr.step)
+
+    for _ in range(args.warmup):
+        step_resident()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    l0 = K.PROF.launches
+    ms = timed_region(step_resident, args.steps)
+    launches = K.PROF.launches - l0
+    clocks = sampler.stop() if rank == 0 else None
+    ms_per_step = ms / args.steps
+    value = B * world / (ms_per_step * 1e-3)
+
+    # ---------------- end-to-end arm (`e2e`): host pinned inputs -> H2D -> train_step -> D2H loss ----------------
+    xh = [x.cpu().pin_memory() for x, _ in bm._pool]
+    yh = [y.cpu().pin_memory() for _, y in bm._pool]
+    xd, yd = torch.empty_like(bm._pool[0][0]), torch.empty_like(bm._pool[0][1])
+    loss_h = torch.empty(3, dtype=torch.float32).pin_memory()
+    cnt = [0]
+
+    def step_e2e():
+        i = cnt[0] % len(xh)
+        cnt[0] += 1
+        xd.copy_(xh[i], non_blocking=True)
+        yd.copy_(yh[i], non_blocking=True)
+        l3 = tr.train_step(xd, yd)
+        tr.update_lr(tr.step)
+        loss_h.copy_(l3, non_blocking=True)
+        torch.cuda.current_stream().synchronize()       # the user reads the loss every step
+        assert loss_h[0] == loss_h[0], "NaN loss"
+
+    for _ in range(max(1, args.warmup // 2)):
+        step_e2e()
+    ms_e = timed_region(step_e2e, args.steps)
+    e2e_value = B * world / (ms_e / args.steps * 1e-3)
+    h2d = xd.numel() * xd.element_size() + yd.numel() * yd.element_size()
+
+    # ---------------- per-kernel timing with CUDA events (2 extra instrumented steps, same stream) ----------------
+    K.PROF.events = []
+    for _ in range(2):
+        tr.train_step()
+    torch.cuda.synchronize()
+    agg = {}
+    for name, s, e, work in K.PROF.events:
+        a = agg.setdefault(name, [0.0, 0.0, 0])
+        a[0] += s.elapsed_time(e) * 1e-3
+        a[1] += work
+        a[2] += 1
+    K.PROF.events = None
+    conv_t, conv_f, conv_n = agg.get("conv_tc", [1e-9, 0.0, 1])
+    wg_t, wg_f, wg_n = agg.get("wgrad_tc", [1e-9, 0.0, 1])
+    st_t, st_b, st_n = agg.get("stencil_fused", [1e-9, 0.0, 1])
+    achieved = conv_f / conv_t / 1e12
+    roofline = {"kernel": "conv_tc_kernel (tcgen05 implicit-GEMM conv, fwd + dgrad launches)", "bound": "tensor",
+                "achieved": achieved, "peak": peaks["tf_sustained"], "unit": "TFLOP/s",
+                "frac": achieved / peaks["tf_sustained"], "peak_source": "%s (sustained bf16, kernel timed inside a long step)" % peaks["src"],
+                "launches_timed": conv_n, "avg_launch_ms": conv_t / conv_n * 1e3, "traffic": load_traffic("conv_tc_kernel"),
+                "share_of_step": conv_t / 2 / (ms_per_step * 1e-3),
+                "others": {
+                    "wgrad_tc_kernel": {"bound": "tensor", "achieved": wg_f / wg_t / 1e12, "unit": "TFLOP/s",
+                                        "frac": wg_f / wg_t / 1e12 / peaks["tf_sustained"],
+                                        "share_of_step": wg_t / 2 / (ms_per_step * 1e-3)},
+                    "stencil_fused_kernel": {"bound": "hbm", "achieved": st_b / st_t / 1e9, "unit": "GB/s",
+                                             "frac": st_b / st_t / 1e9 / peaks["hbm_gbs"],
+                                             "share_of_step": st_t / 2 / (ms_per_step * 1e-3)}}}
+    fl = FLOPS_PER_FIELD[args.workload]
+    if fl:
+        roofline["step_conv_tflops_per_gpu"] = value / world * fl / 1e12
+        roofline["step_frac_of_peak"] = value / world * fl / 1e12 / peaks["tf_sustained"]
+
+    if rank == 0:
+        cpu = cpu_oracle_fields_per_sec(args.workload, 3, 1) if world == 1 and not args.no_cpu else None
+        out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+               "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+               "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+               "config": {"workload": WORKLOADS[args.workload][5], "global_batch": B * world, "per_gpu_batch": B,
+                          "parallelism": "dp%d" % world, "filters": 128, "num_conv": 4,
+                          "l2": "per-step working set (>= %.0f MB of activations) exceeds the 126 MB L2; no flush needed"
+                                % (tr.engine.x0[-1].numel() * 2 * 6 / 1e6),
+                          "precision": "bf16 operands/activations, fp32 accumulate (TMEM), fp32 master weights + Adam"},
+               "clocks": clocks, "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d,
+                                         "d2h_bytes_per_step": 12, "ms_per_step": ms_e / args.steps},
+               "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu}
+        print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def load_traffic(kernel):
+    """dram bytes per launch from the committed ncu summary (profiles/ncu_summary.json), else null."""
+    p = os.path.join(ROOT, "profiles", "ncu_summary.json")
+    try:
+        return json.load(open(p))[kernel]["dram_bytes_per_launch"]
+    except Exception:
+        return None
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", type=str, default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", type=str, default="c2", choices=sorted(WORKLOADS))
+    ap.add_argument("--no-cpu", dest="no_cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+    if args.impl == "reference":
+        run_reference_arm(args)
+    else:
+        run_gpu_arm(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -13,6 +13,26 @@ from .cabi import F32, BF16, CONV_LRELU, CONV_OUT2_UPSAMPLE, check, dims_array
 _DT = {torch.float32: F32, torch.bfloat16: BF16}
 
 
+class _Prof(object):
+    """Launch counter (bench.py's `gpu_launches` claim) and optional per-kernel CUDA-event timing."""
+    launches = 0
+    events = None        # when a list: (kernel name, start event, end event, algorithmic work) tuples are appended
+
+    @classmethod
+    def timed(cls, name, work, fn):
+        cls.launches += 1
+        if cls.events is None:
+            return fn()
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        fn()
+        e.record()
+        cls.events.append((name, s, e, work))
+
+
+PROF = _Prof
+
+
 def _p(t):
     if t is None:
         return None
@@ -42,6 +62,7 @@ def _spatial(t):
 def curl_fwd(pot):
     d, nd = _spatial(pot)
     vel = torch.empty(pot.shape[:-1] + (nd,), dtype=pot.dtype, device=pot.device)
+    PROF.launches += 1
     check(cabi.lib().dfl_curl_fwd(_p(pot), _p(vel), d, nd, pot.shape[-1], _dt(pot), _st()))
     return vel
 
@@ -51,6 +72,7 @@ def jacobian_fwd(vel, want_jac=True, want_aux=True):
     assert vel.shape[-1] == nd
     jac = torch.empty(vel.shape[:-1] + (nd * nd,), dtype=vel.dtype, device=vel.device) if want_jac else None
     aux = torch.empty(vel.shape[:-1] + (1 if nd == 2 else 3,), dtype=vel.dtype, device=vel.device) if want_aux else None
+    PROF.launches += 1
     check(cabi.lib().dfl_jacobian_fwd(_p(vel), _p(jac), _p(aux), d, nd, _dt(vel), _st()))
     return jac, aux
 
@@ -58,6 +80,7 @@ def jacobian_fwd(vel, want_jac=True, want_aux=True):
 def divergence(vel):
     d, nd = _spatial(vel)
     out = torch.empty((vel.shape[0],) + tuple(s - 1 for s in vel.shape[1:-1]) + (1,), dtype=vel.dtype, device=vel.device)
+    PROF.launches += 1
     check(cabi.lib().dfl_divergence(_p(vel), _p(out), d, nd, _dt(vel), _st()))
     return out
 
@@ -74,8 +97,13 @@ def stencil_loss_fwdbwd(pot, x, w1=1.0, w2=1.0, grad_scale=1.0, want_vel=False, 
     if loss3 is None:
         loss3 = torch.empty(3, dtype=torch.float32, device=x.device)
     vel = torch.empty(x.shape, dtype=pot.dtype, device=x.device) if want_vel else None
-    check(l.dfl_stencil_loss_fwdbwd(_p(pot), _p(x), _p(dpot), _p(vel), _p(loss3), _p(workspace), d, nd,
-                                    pot.shape[-1], w1, w2, grad_scale, _dt(pot), _dt(x), _st()))
+    nvox = x.numel() // x.shape[-1]
+    work = nvox * (pot.shape[-1] * pot.element_size() + x.shape[-1] * x.element_size()
+                   + dpot.shape[-1] * dpot.element_size())          # algorithmic bytes: read pot + x, write dpot
+    PROF.launches += 1                                              # + the tiny finalize kernel
+    PROF.timed("stencil_fused", work, lambda: check(l.dfl_stencil_loss_fwdbwd(
+        _p(pot), _p(x), _p(dpot), _p(vel), _p(loss3), _p(workspace), d, nd, pot.shape[-1], w1, w2, grad_scale,
+        _dt(pot), _dt(x), _st())))
     return loss3, dpot, vel
 
 
@@ -85,6 +113,7 @@ def fc_fwd(z, W, bias, out_dtype=torch.bfloat16, out=None):
     N = W.shape[1]
     if out is None:
         out = torch.empty(B, N, dtype=out_dtype, device=z.device)
+    PROF.launches += 1
     check(cabi.lib().dfl_fc_fwd(_p(z), _p(W), _p(bias), _p(out), B, K, N, _dt(out), _st()))
     return out
 
@@ -92,6 +121,7 @@ def fc_fwd(z, W, bias, out_dtype=torch.bfloat16, out=None):
 def fc_bwd(z, dout, dW, db):
     B, K = z.shape
     N = dW.shape[1]
+    PROF.launches += 1
     check(cabi.lib().dfl_fc_bwd(_p(z), _p(dout), _p(dW), _p(db), B, K, N, _dt(dout), _st()))
 
 
@@ -104,6 +134,7 @@ def pack_conv_weights(w, w_fwd=None, w_dgrad=None):
         w_fwd = torch.empty(cout, taps * cin, dtype=torch.bfloat16, device=w.device)
     if w_dgrad is None:
         w_dgrad = torch.empty(cin, taps * cout, dtype=torch.bfloat16, device=w.device)
+    PROF.launches += 1
     check(cabi.lib().dfl_pack_conv_weights(_p(w), _p(w_fwd), _p(w_dgrad), taps, cin, cout, _st()))
     return w_fwd, w_dgrad
 
@@ -113,16 +144,20 @@ def conv3x3(x, w_packed, bias=None, out=None, out2=None, residual=None, mask_src
     d, nd = _spatial(x)
     cin, cout = x.shape[-1], w_packed.shape[0]
     assert x.dtype == torch.bfloat16 and w_packed.dtype == torch.bfloat16
-    check(cabi.lib().dfl_conv3x3_fwd(_p(x), _p(w_packed), _p(bias), _p(out), _p(out2), _p(residual), _p(mask_src),
-                                     d, nd, cin, cout, flags, _st()))
+    flops = 2.0 * (x.numel() // cin) * cin * cout * (3 ** nd)     # algorithmic MACs x 2 (dense taps)
+    PROF.timed("conv_tc", flops, lambda: check(cabi.lib().dfl_conv3x3_fwd(
+        _p(x), _p(w_packed), _p(bias), _p(out), _p(out2), _p(residual), _p(mask_src), d, nd, cin, cout, flags, _st())))
 
 
 def conv3x3_wgrad(x, dpre, dw):
     d, nd = _spatial(x)
-    check(cabi.lib().dfl_conv3x3_wgrad(_p(x), _p(dpre), _p(dw), d, nd, x.shape[-1], dpre.shape[-1], _st()))
+    flops = 2.0 * (x.numel() // x.shape[-1]) * x.shape[-1] * dpre.shape[-1] * (3 ** nd)
+    PROF.timed("wgrad_tc", flops, lambda: check(cabi.lib().dfl_conv3x3_wgrad(
+        _p(x), _p(dpre), _p(dw), d, nd, x.shape[-1], dpre.shape[-1], _st())))
 
 
 def bias_grad(dpre, db):
+    PROF.launches += 1
     check(cabi.lib().dfl_bias_grad(_p(dpre), _p(db), dpre.numel() // dpre.shape[-1], _st()))
 
 
@@ -131,17 +166,20 @@ def lastconv_fwd(x, w, bias, out=None):
     cout = w.shape[-1]
     if out is None:
         out = torch.empty(x.shape[:-1] + (cout,), dtype=torch.float32, device=x.device)
+    PROF.launches += 1
     check(cabi.lib().dfl_lastconv_fwd(_p(x), _p(w), _p(bias), _p(out), d, nd, cout, _st()))
     return out
 
 
 def lastconv_dgrad(dout, w, mask_src=None, dx=None, dx_masked=None):
     d, nd = _spatial(dout)
+    PROF.launches += 1
     check(cabi.lib().dfl_lastconv_dgrad(_p(dout), _p(w), _p(mask_src), _p(dx), _p(dx_masked), d, nd, w.shape[-1], _st()))
 
 
 def lastconv_wgrad(x, dout, dw, db):
     d, nd = _spatial(x)
+    PROF.launches += 1
     check(cabi.lib().dfl_lastconv_wgrad(_p(x), _p(dout), _p(dw), _p(db), d, nd, dout.shape[-1], _st()))
 
 
@@ -149,11 +187,13 @@ def pool_mask(g, mask_src, ds, dmasked):
     """g: fine-grid gradient [B,(2D,)2H,2W,128]; ds / dmasked: coarse [B,(D,)H,W,128]"""
     ref = ds if ds is not None else dmasked
     d, nd = _spatial(ref)
+    PROF.launches += 1
     check(cabi.lib().dfl_pool_mask(_p(g), _p(mask_src), _p(ds), _p(dmasked), d, nd, _st()))
 
 
 # ------------------------------------------------------------------ optimizer / misc
 def adam_step(param, grad, m, v, lr_t, beta1, beta2, eps=1e-8, grad_scale=1.0):
+    PROF.launches += 1
     check(cabi.lib().dfl_adam_step(_p(param), _p(grad), _p(m), _p(v), param.numel(), lr_t, beta1, beta2, eps,
                                    grad_scale, _st()))
 
@@ -161,5 +201,6 @@ def adam_step(param, grad, m, v, lr_t, beta1, beta2, eps=1e-8, grad_scale=1.0):
 def cast_f32_bf16(a, out=None):
     if out is None:
         out = torch.empty(a.shape, dtype=torch.bfloat16, device=a.device)
+    PROF.launches += 1
     check(cabi.lib().dfl_cast_f32_bf16(_p(a), _p(out), a.numel(), _st()))
     return out
