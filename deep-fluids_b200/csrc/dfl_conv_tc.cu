@@ -20,6 +20,16 @@
 //               optionally replicated 2x2(x2) = fused nearest-neighbour upsample).
 //   Pipelines:  6-stage smem ring (full/empty mbarriers), 2 TMEM accumulators (full/empty mbarriers) so the
 //               epilogue of tile i overlaps the MMAs of tile i+1; persistent CTAs, static tile schedule.
+//
+// v2 ("tap windows", default): measured on B200 (tools/umma_probe.cu, profiles/r01_umma_probe.txt) the tensor core
+// applies the 128B swizzle to ABSOLUTE shared-memory address bits, so a UMMA descriptor may start at any 128-byte row
+// of a TMA-written image and use any row pitch.  The kernel therefore keeps ONE halo'd activation brick resident in
+// smem per 64-channel slice and reads every (dz,dy,dx) tap as a shifted descriptor window over it (no per-tap
+// reload: A traffic / 9..27), processes 256 voxels per tile as two M=128 halves that share each streamed weight
+// tile (B traffic / 2), and spends the freed smem on an 8-deep weight ring (hides the ~2500-cycle TMA latency that
+// bound v1: profiles/r01_ncu_conv_tc_v1_c2_fullres.json).
+#include <stdlib.h>
+
 #include "dfl_common.cuh"
 
 namespace dfl {
@@ -256,6 +266,272 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   }
 }
 
+// =============================================================================================
+// v2 kernel: resident brick slots + tap windows
+//   3D tile = 2(z) x 16(y) x 8(x) voxels; M-half h = z-plane h; brick = 4 plane slots of 18 x 10 rows (128 B each)
+//   2D tile = 16(y) x 16(x) voxels;        M-half h = x-half h;  brick = 18 x 18 rows, 2 slots ping-pong per phase
+//   phase = (tile, 64-channel slice);  warps: 0 = brick producer, 1 = MMA issuer (+TMEM alloc), 2 = weight producer,
+//   3..6 = epilogue.
+// =============================================================================================
+constexpr int C2_BSTAGES = 8;
+constexpr int C2_SLOT_BYTES_3D = 23552;   // 180 rows * 128 B = 23040, padded to a 1024-byte multiple
+constexpr int C2_SLOT_BYTES_2D = 41984;   // 324 rows * 128 B = 41472, padded
+constexpr int C2_BRICK_BYTES = 4 * C2_SLOT_BYTES_3D;   // 94208 >= 2 * C2_SLOT_BYTES_2D (83968)
+constexpr int C2_THREADS = 224;
+constexpr int C2_SMEM_BYTES = C2_BRICK_BYTES + C2_BSTAGES * CT_B_BYTES + 1024 + 1024;
+
+__device__ __forceinline__ void conv_epilogue_row(const ConvTcParams& p, uint32_t taddr, bool valid, int b, int z,
+                                                  int y, int x, const float* s_bias) {
+  const bool ups = (p.flags & CF_OUT2_UPSAMPLE) != 0;
+  const bool act = (p.flags & CF_LRELU) != 0;
+  const size_t pos = ((static_cast<size_t>(b) * p.D + z) * p.H + y) * p.W + x;
+#pragma unroll 1
+  for (int c0 = 0; c0 < CT_BLOCK_N; c0 += 32) {
+    uint32_t rr[32];
+    tmem_ld_32x32(taddr + c0, rr);
+    tmem_ld_wait();
+    if (!valid) continue;
+    float v[32];
+#pragma unroll
+    for (int k = 0; k < 32; ++k) {
+      float t = __uint_as_float(rr[k]) + s_bias[c0 + k];
+      v[k] = act ? lrelu_f(t) : t;
+    }
+    if (p.mask_src) {
+      const uint4* m = reinterpret_cast<const uint4*>(p.mask_src + pos * CT_BLOCK_N + c0);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        float f[8];
+        unpack_bf16x8(__ldg(m + q), f);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) v[q * 8 + k] *= lrelu_grad_from_out(f[k]);
+      }
+    }
+    if (p.out) {
+      uint4* o = reinterpret_cast<uint4*>(p.out + pos * CT_BLOCK_N + c0);
+#pragma unroll
+      for (int q = 0; q < 4; ++q)
+        o[q] = make_uint4(pack_bf16x2(v[q * 8], v[q * 8 + 1]), pack_bf16x2(v[q * 8 + 2], v[q * 8 + 3]),
+                          pack_bf16x2(v[q * 8 + 4], v[q * 8 + 5]), pack_bf16x2(v[q * 8 + 6], v[q * 8 + 7]));
+    }
+    if (p.out2) {
+      if (p.residual) {
+        const uint4* m = reinterpret_cast<const uint4*>(p.residual + pos * CT_BLOCK_N + c0);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          float f[8];
+          unpack_bf16x8(__ldg(m + q), f);
+#pragma unroll
+          for (int k = 0; k < 8; ++k) v[q * 8 + k] += f[k];
+        }
+      }
+      uint4 pk[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q)
+        pk[q] = make_uint4(pack_bf16x2(v[q * 8], v[q * 8 + 1]), pack_bf16x2(v[q * 8 + 2], v[q * 8 + 3]),
+                           pack_bf16x2(v[q * 8 + 4], v[q * 8 + 5]), pack_bf16x2(v[q * 8 + 6], v[q * 8 + 7]));
+      if (!ups) {
+        uint4* o = reinterpret_cast<uint4*>(p.out2 + pos * CT_BLOCK_N + c0);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) o[q] = pk[q];
+      } else {
+        const int zr = (p.kd > 1) ? 2 : 1;
+        const int D2 = p.D * zr, H2 = p.H * 2, W2 = p.W * 2;
+        for (int a = 0; a < zr; ++a)
+          for (int e = 0; e < 2; ++e)
+            for (int f = 0; f < 2; ++f) {
+              const size_t pos2 = ((static_cast<size_t>(b) * D2 + (z * zr + a)) * H2 + (2 * y + e)) * W2 + (2 * x + f);
+              uint4* o = reinterpret_cast<uint4*>(p.out2 + pos2 * CT_BLOCK_N + c0);
+#pragma unroll
+              for (int q = 0; q < 4; ++q) o[q] = pk[q];
+            }
+      }
+    }
+  }
+}
+
+template <bool k3D>
+__global__ void __launch_bounds__(C2_THREADS, 1)
+conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, ConvTcParams p) {
+  constexpr int NSLOT = k3D ? 4 : 2;
+  constexpr int SLOT_BYTES = k3D ? C2_SLOT_BYTES_3D : C2_SLOT_BYTES_2D;
+  constexpr int SLOT_TX = (k3D ? 180 : 324) * 128;    // bytes landed per slot fill
+  constexpr int HX = k3D ? 10 : 18;                   // brick rows per y-line
+  constexpr int TZ = k3D ? 2 : 1, TY = 16, TX = k3D ? 8 : 16;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sB = smem + C2_BRICK_BYTES;
+  uint8_t* ctrl = sB + C2_BSTAGES * CT_B_BYTES;
+  uint64_t* a_full = reinterpret_cast<uint64_t*>(ctrl);   // [4]
+  uint64_t* a_empty = a_full + 4;                         // [4]
+  uint64_t* b_full = a_empty + 4;                         // [C2_BSTAGES]
+  uint64_t* b_empty = b_full + C2_BSTAGES;                // [C2_BSTAGES]
+  uint64_t* tfull_bar = b_empty + C2_BSTAGES;             // [2]
+  uint64_t* tempty_bar = tfull_bar + 2;                   // [2]
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+  float* s_bias = reinterpret_cast<float*>(ctrl + 512);   // [128]
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int ntaps = p.kd * p.kh * p.kw;
+
+  if (threadIdx.x < CT_BLOCK_N) s_bias[threadIdx.x] = p.bias ? p.bias[threadIdx.x] : 0.f;
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    for (int s = 0; s < 4; ++s) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], 1); }
+    for (int s = 0; s < C2_BSTAGES; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(&tfull_bar[a], 1); mbar_init(&tempty_bar[a], 128); }
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_ptr, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp == 0) {
+    // ================================ brick producer ================================
+    if (lane == 0) {
+      uint32_t fills[NSLOT];
+#pragma unroll
+      for (int s = 0; s < NSLOT; ++s) fills[s] = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
+        int r = tile;
+        const int x0 = (r % p.tx) * TX; r /= p.tx;
+        const int y0 = (r % p.ty) * TY; r /= p.ty;
+        const int z0 = (r % p.tz) * TZ; r /= p.tz;
+        const int b = r;
+        for (int c = 0; c < p.cin_chunks; ++c, ++phase) {
+          if (k3D) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              mbar_wait(&a_empty[j], (fills[j] & 1) ^ 1);
+              mbar_expect_tx(&a_full[j], SLOT_TX);
+              tma_load_5d(smem + j * SLOT_BYTES, &tmA, &a_full[j], c * CT_BLOCK_K, x0 - 1, y0 - 1, z0 - 1 + j, b);
+              ++fills[j];
+            }
+          } else {
+            const int j = phase & 1;
+            mbar_wait(&a_empty[j], (fills[j] & 1) ^ 1);
+            mbar_expect_tx(&a_full[j], SLOT_TX);
+            tma_load_5d(smem + j * SLOT_BYTES, &tmA, &a_full[j], c * CT_BLOCK_K, x0 - 1, y0 - 1, 0, b);
+            ++fills[j];
+          }
+        }
+      }
+    }
+  } else if (warp == 2) {
+    // ================================ weight producer ================================
+    if (lane == 0) {
+      uint32_t it = 0;
+      for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x)
+        for (int c = 0; c < p.cin_chunks; ++c)
+          for (int t = 0; t < ntaps; ++t, ++it) {
+            const uint32_t s = it % C2_BSTAGES, ph = (it / C2_BSTAGES) & 1;
+            mbar_wait(&b_empty[s], ph ^ 1);
+            mbar_expect_tx(&b_full[s], CT_B_BYTES);
+            tma_load_2d(sB + s * CT_B_BYTES, &tmB, &b_full[s], (t * p.cin_chunks + c) * CT_BLOCK_K, 0);
+          }
+    }
+  } else if (warp == 1) {
+    // ================================ MMA issuer ================================
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(CT_BLOCK_M, CT_BLOCK_N, 0, 0);
+      const uint32_t brick = smem_u32(smem);
+      uint32_t fills[NSLOT];
+#pragma unroll
+      for (int s = 0; s < NSLOT; ++s) fills[s] = 0;
+      uint32_t it = 0, tcount = 0, phase = 0;
+      for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++tcount) {
+        const uint32_t acc = tcount & 1, aph = (tcount >> 1) & 1;
+        mbar_wait(&tempty_bar[acc], aph ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * 256;
+        for (int c = 0; c < p.cin_chunks; ++c, ++phase) {
+          for (int dz = 0; dz < p.kd; ++dz) {
+            // wait for the brick slots this tap group reads
+            if (k3D) {
+              if (dz == 0) { mbar_wait(&a_full[0], fills[0] & 1); ++fills[0]; mbar_wait(&a_full[1], fills[1] & 1); ++fills[1]; }
+              else if (dz == 1) { mbar_wait(&a_full[2], fills[2] & 1); ++fills[2]; }
+              else { mbar_wait(&a_full[3], fills[3] & 1); ++fills[3]; }
+            } else {
+              const int j = phase & 1;
+              mbar_wait(&a_full[j], fills[j] & 1);
+              ++fills[j];
+            }
+            tc_fence_after();
+            for (int dy = 0; dy < 3; ++dy)
+              for (int dx = 0; dx < 3; ++dx, ++it) {
+                const uint32_t s = it % C2_BSTAGES, ph = (it / C2_BSTAGES) & 1;
+                mbar_wait(&b_full[s], ph);
+                tc_fence_after();
+                const uint32_t sb = smem_u32(sB + s * CT_B_BYTES);
+                const bool first = (c == 0 && dz == 0 && dy == 0 && dx == 0);
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                  const uint32_t a0 = k3D ? brick + (h + dz) * SLOT_BYTES + (dy * HX + dx) * 128
+                                          : brick + (phase & 1) * SLOT_BYTES + (dy * HX + dx + 8 * h) * 128;
+#pragma unroll
+                  for (int k = 0; k < CT_BLOCK_K / 16; ++k) {
+                    const uint64_t da = umma_desc_sw128(a0 + k * 32, 16, HX * 128);
+                    const uint64_t db = umma_desc_sw128(sb + k * 32, 16, 1024);
+                    umma_bf16(d_tmem + h * CT_BLOCK_N, da, db, idesc, (first && k == 0) ? 0u : 1u);
+                  }
+                }
+                umma_commit(&b_empty[s]);
+              }
+            // release the brick slots no later tap group of this phase reads
+            if (k3D) {
+              umma_commit(&a_empty[dz]);
+              if (dz == 2) umma_commit(&a_empty[3]);
+            } else {
+              umma_commit(&a_empty[phase & 1]);
+            }
+          }
+        }
+        umma_commit(&tfull_bar[acc]);
+      }
+    }
+  } else {
+    // ================================ epilogue (warps 3..6) ================================
+    const int quarter = warp & 3;
+    const int row = quarter * 32 + lane;
+    const int line = row >> 3, xi = row & 7;
+    uint32_t tcount = 0;
+    for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++tcount) {
+      const uint32_t acc = tcount & 1, aph = (tcount >> 1) & 1;
+      int r = tile;
+      const int x0 = (r % p.tx) * TX; r /= p.tx;
+      const int y0 = (r % p.ty) * TY; r /= p.ty;
+      const int z0 = (r % p.tz) * TZ; r /= p.tz;
+      const int b = r;
+      mbar_wait(&tfull_bar[acc], aph);
+      tc_fence_after();
+#pragma unroll 1
+      for (int h = 0; h < 2; ++h) {
+        const int z = k3D ? z0 + h : 0, y = y0 + line, x = k3D ? x0 + xi : x0 + 8 * h + xi;
+        const bool valid = (x < p.W) && (y < p.H) && (z < p.D);
+        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * 256 + h * CT_BLOCK_N;
+        conv_epilogue_row(p, taddr, valid, b, z, y, x, s_bias);
+      }
+      tc_fence_before();
+      mbar_arrive(&tempty_bar[acc]);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    __syncwarp();
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
 // ---------------------------------------------------------------------------------------------
 // host launcher
 // ---------------------------------------------------------------------------------------------
@@ -286,7 +562,12 @@ int conv_tc_launch(const void* x, const void* w_packed, const float* bias, void*
   p.kd = nd == 3 ? 3 : 1;
   p.kh = 3;
   p.kw = 3;
-  pick_brick(p.D, p.H, p.W, p.bd, p.bh, p.bw);
+  static const bool use_v1 = (getenv("DFL_CONV_V1") != nullptr);
+  if (use_v1) {
+    pick_brick(p.D, p.H, p.W, p.bd, p.bh, p.bw);
+  } else {  // v2 tiles: 3D 2x16x8, 2D 1x16x16
+    p.bd = nd == 3 ? 2 : 1; p.bh = 16; p.bw = nd == 3 ? 8 : 16;
+  }
   p.tx = (p.W + p.bw - 1) / p.bw;
   p.ty = (p.H + p.bh - 1) / p.bh;
   p.tz = (p.D + p.bd - 1) / p.bd;
@@ -307,8 +588,8 @@ int conv_tc_launch(const void* x, const void* w_packed, const float* bias, void*
     const uint64_t gs[4] = {static_cast<uint64_t>(cin) * 2, static_cast<uint64_t>(cin) * 2 * p.W,
                             static_cast<uint64_t>(cin) * 2 * p.W * p.H,
                             static_cast<uint64_t>(cin) * 2 * p.W * p.H * p.D};
-    const uint32_t box[5] = {64, static_cast<uint32_t>(p.bw), static_cast<uint32_t>(p.bh),
-                             static_cast<uint32_t>(p.bd), 1};
+    uint32_t box[5] = {64, static_cast<uint32_t>(p.bw), static_cast<uint32_t>(p.bh), static_cast<uint32_t>(p.bd), 1};
+    if (!use_v1) { box[1] = p.bw + 2; box[2] = p.bh + 2; box[3] = 1; }   // one halo'd plane per TMA
     int rc = encode_tensor_map(&tmA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, x, gd, gs, box, CU_TENSOR_MAP_SWIZZLE_128B);
     if (rc) return rc;
   }
@@ -321,13 +602,26 @@ int conv_tc_launch(const void* x, const void* w_packed, const float* bias, void*
                                CU_TENSOR_MAP_SWIZZLE_128B);
     if (rc) return rc;
   }
-  static bool attr_set = false;
-  if (!attr_set) {
-    DFL_CUDA_OK(cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, CT_SMEM_BYTES));
-    attr_set = true;
-  }
   const int grid = std::min(p.ntiles, num_sms());
-  conv_tc_kernel<<<grid, CT_THREADS, CT_SMEM_BYTES, st>>>(tmA, tmB, p);
+  if (use_v1) {
+    static bool attr_set = false;
+    if (!attr_set) {
+      DFL_CUDA_OK(cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, CT_SMEM_BYTES));
+      attr_set = true;
+    }
+    conv_tc_kernel<<<grid, CT_THREADS, CT_SMEM_BYTES, st>>>(tmA, tmB, p);
+  } else {
+    static bool attr_set = false;
+    if (!attr_set) {
+      DFL_CUDA_OK(cudaFuncSetAttribute(conv_tc2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, C2_SMEM_BYTES));
+      DFL_CUDA_OK(cudaFuncSetAttribute(conv_tc2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, C2_SMEM_BYTES));
+      attr_set = true;
+    }
+    if (nd == 3)
+      conv_tc2_kernel<true><<<grid, C2_THREADS, C2_SMEM_BYTES, st>>>(tmA, tmB, p);
+    else
+      conv_tc2_kernel<false><<<grid, C2_THREADS, C2_SMEM_BYTES, st>>>(tmA, tmB, p);
+  }
   DFL_LAUNCH_OK("conv_tc_kernel");
   return DFL_OK;
 }
