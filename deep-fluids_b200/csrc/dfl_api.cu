@@ -71,6 +71,8 @@ int fc_bwd(const float* z, const void* dout, float* dW, float* db, int B, int K,
            cudaStream_t st);
 int lastconv(int op, const void* a, const void* b, const void* c, void* o0, void* o1, const int64_t* dims, int nd,
              int cout, cudaStream_t st);
+int lastconv_bwd_tc(const void* s, const float* dout, const float* w, const void* mask_src, void* ds, void* ds_masked,
+                    float* dw, float* db, const int64_t* dims, int nd, int cout, cudaStream_t st);
 int pool_mask(const void* g, const void* mask_src, void* ds, void* dmasked, const int64_t* cdims, int nd,
               cudaStream_t st);
 int bias_grad(const void* d, float* db, size_t npos, cudaStream_t st);
@@ -170,6 +172,10 @@ int dfl_lastconv_dgrad(const float* dout, const float* w, const void* mask_src, 
 int dfl_lastconv_wgrad(const void* x, const float* dout, float* dw, float* db, const int64_t* dims, int ndim,
                        int cout, void* stream) {
   return lastconv(2, x, dout, nullptr, dw, db, dims, ndim, cout, ST(stream));
+}
+int dfl_lastconv_bwd(const void* s, const float* dout, const float* w, const void* mask_src, void* ds, void* ds_masked,
+                     float* dw, float* db, const int64_t* dims, int ndim, int cout, void* stream) {
+  return lastconv_bwd_tc(s, dout, w, mask_src, ds, ds_masked, dw, db, dims, ndim, cout, ST(stream));
 }
 int dfl_pool_mask(const void* g, const void* mask_src, void* ds, void* dmasked, const int64_t* cdims, int ndim,
                   void* stream) {

@@ -58,6 +58,8 @@ struct ConvTcParams {
   const __nv_bfloat16* residual;  // added into out2 or nullptr
   __nv_bfloat16* out;         // [B,D,H,W,128] or nullptr
   __nv_bfloat16* out2;        // [B,D,H,W,128] or upsampled [B,(2D),2H,2W,128] or nullptr
+  float* out_f32;             // kN = 16 variant: fp32 [B,D,H,W,cout_small]
+  int cout_small;
 };
 
 __device__ __forceinline__ void unpack_bf16x8(const uint4& q, float (&f)[8]) {
@@ -350,7 +352,9 @@ __device__ __forceinline__ void conv_epilogue_row(const ConvTcParams& p, uint32_
   }
 }
 
-template <bool k3D>
+// kN = 128: the 128->128 layers.  kN = 16: the 128 -> 1..3 output conv (model.py:42,84), weights zero-padded to 16
+// output channels; its epilogue writes fp32 [voxel][p.cout_small] (+ bias) = the network output (potential).
+template <bool k3D, int kN>
 __global__ void __launch_bounds__(C2_THREADS, 1)
 conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, ConvTcParams p) {
   constexpr int NSLOT = k3D ? 4 : 2;
@@ -361,6 +365,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sB = smem + C2_BRICK_BYTES;
+  constexpr int B_BYTES = kN * CT_BLOCK_K * 2;
   uint8_t* ctrl = sB + C2_BSTAGES * CT_B_BYTES;
   uint64_t* a_full = reinterpret_cast<uint64_t*>(ctrl);   // [4]
   uint64_t* a_empty = a_full + 4;                         // [4]
@@ -374,7 +379,8 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int ntaps = p.kd * p.kh * p.kw;
 
-  if (threadIdx.x < CT_BLOCK_N) s_bias[threadIdx.x] = p.bias ? p.bias[threadIdx.x] : 0.f;
+  if (threadIdx.x < CT_BLOCK_N)
+    s_bias[threadIdx.x] = (p.bias && (kN == CT_BLOCK_N || threadIdx.x < p.cout_small)) ? p.bias[threadIdx.x] : 0.f;
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
@@ -433,14 +439,14 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           for (int t = 0; t < ntaps; ++t, ++it) {
             const uint32_t s = it % C2_BSTAGES, ph = (it / C2_BSTAGES) & 1;
             mbar_wait(&b_empty[s], ph ^ 1);
-            mbar_expect_tx(&b_full[s], CT_B_BYTES);
+            mbar_expect_tx(&b_full[s], B_BYTES);
             tma_load_2d(sB + s * CT_B_BYTES, &tmB, &b_full[s], (t * p.cin_chunks + c) * CT_BLOCK_K, 0);
           }
     }
   } else if (warp == 1) {
     // ================================ MMA issuer ================================
     if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc_bf16(CT_BLOCK_M, CT_BLOCK_N, 0, 0);
+      constexpr uint32_t idesc = umma_idesc_bf16(CT_BLOCK_M, kN, 0, 0);
       const uint32_t brick = smem_u32(smem);
       uint32_t fills[NSLOT];
 #pragma unroll
@@ -516,7 +522,17 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         const int z = k3D ? z0 + h : 0, y = y0 + line, x = k3D ? x0 + xi : x0 + 8 * h + xi;
         const bool valid = (x < p.W) && (y < p.H) && (z < p.D);
         const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * 256 + h * CT_BLOCK_N;
-        conv_epilogue_row(p, taddr, valid, b, z, y, x, s_bias);
+        if (kN == CT_BLOCK_N) {
+          conv_epilogue_row(p, taddr, valid, b, z, y, x, s_bias);
+        } else {
+          uint32_t rr[32];
+          tmem_ld_32x32(taddr, rr);      // columns >= 16 are never written: ignored
+          tmem_ld_wait();
+          if (valid) {
+            float* o = p.out_f32 + (((static_cast<size_t>(b) * p.D + z) * p.H + y) * p.W + x) * p.cout_small;
+            for (int c = 0; c < p.cout_small; ++c) o[c] = __uint_as_float(rr[c]) + s_bias[c];
+          }
+        }
       }
       tc_fence_before();
       mbar_arrive(&tempty_bar[acc]);
@@ -551,7 +567,8 @@ static void pick_brick(int D, int H, int W, int& bd, int& bh, int& bw) {
 int conv_tc_launch(const void* x, const void* w_packed, const float* bias, void* out, void* out2,
                    const void* residual, const void* mask_src, const int64_t* dims /*B,D,H,W*/, int nd, int cin,
                    int cout, int flags, cudaStream_t st) {
-  DFL_REQUIRE(cout == 128, "conv_tc: Cout must be 128 (got %d)", cout);
+  const bool small = cout < 128;   // 128 -> 1..3 output conv: w_packed is [16][taps*cin], out is fp32 [.., cout]
+  DFL_REQUIRE(cout == 128 || (cout >= 1 && cout <= 16), "conv_tc: Cout must be 128 or <= 16 (got %d)", cout);
   DFL_REQUIRE(cin % 64 == 0 && cin >= 64, "conv_tc: Cin must be a multiple of 64 (got %d)", cin);
   DFL_REQUIRE(nd == 2 || nd == 3, "conv_tc: ndim must be 2 or 3");
   ConvTcParams p{};
@@ -577,9 +594,12 @@ int conv_tc_launch(const void* x, const void* w_packed, const float* bias, void*
   p.bias = bias;
   p.mask_src = static_cast<const __nv_bfloat16*>(mask_src);
   p.residual = static_cast<const __nv_bfloat16*>(residual);
-  p.out = static_cast<__nv_bfloat16*>(out);
+  p.out = small ? nullptr : static_cast<__nv_bfloat16*>(out);
   p.out2 = static_cast<__nv_bfloat16*>(out2);
-  DFL_REQUIRE(p.out || p.out2, "conv_tc: no output buffer given");
+  p.out_f32 = small ? static_cast<float*>(out) : nullptr;
+  p.cout_small = small ? cout : 0;
+  DFL_REQUIRE(out || out2, "conv_tc: no output buffer given");
+  DFL_REQUIRE(!(small && use_v1), "conv_tc: the small-Cout variant exists only in the v2 kernel");
 
   CUtensorMap tmA, tmB;
   {
@@ -595,9 +615,9 @@ int conv_tc_launch(const void* x, const void* w_packed, const float* bias, void*
   }
   {
     const int ntaps = p.kd * p.kh * p.kw;
-    const uint64_t gd[2] = {static_cast<uint64_t>(ntaps) * cin, 128};
+    const uint64_t gd[2] = {static_cast<uint64_t>(ntaps) * cin, static_cast<uint64_t>(small ? 16 : 128)};
     const uint64_t gs[1] = {static_cast<uint64_t>(ntaps) * cin * 2};
-    const uint32_t box[2] = {64, 128};
+    const uint32_t box[2] = {64, static_cast<uint32_t>(small ? 16 : 128)};
     int rc = encode_tensor_map(&tmB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, w_packed, gd, gs, box,
                                CU_TENSOR_MAP_SWIZZLE_128B);
     if (rc) return rc;
@@ -613,14 +633,20 @@ int conv_tc_launch(const void* x, const void* w_packed, const float* bias, void*
   } else {
     static bool attr_set = false;
     if (!attr_set) {
-      DFL_CUDA_OK(cudaFuncSetAttribute(conv_tc2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, C2_SMEM_BYTES));
-      DFL_CUDA_OK(cudaFuncSetAttribute(conv_tc2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, C2_SMEM_BYTES));
+      DFL_CUDA_OK(cudaFuncSetAttribute(conv_tc2_kernel<true, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, C2_SMEM_BYTES));
+      DFL_CUDA_OK(cudaFuncSetAttribute(conv_tc2_kernel<false, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, C2_SMEM_BYTES));
+      DFL_CUDA_OK(cudaFuncSetAttribute(conv_tc2_kernel<true, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, C2_SMEM_BYTES));
+      DFL_CUDA_OK(cudaFuncSetAttribute(conv_tc2_kernel<false, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, C2_SMEM_BYTES));
       attr_set = true;
     }
-    if (nd == 3)
-      conv_tc2_kernel<true><<<grid, C2_THREADS, C2_SMEM_BYTES, st>>>(tmA, tmB, p);
+    if (nd == 3 && !small)
+      conv_tc2_kernel<true, 128><<<grid, C2_THREADS, C2_SMEM_BYTES, st>>>(tmA, tmB, p);
+    else if (nd == 3)
+      conv_tc2_kernel<true, 16><<<grid, C2_THREADS, C2_SMEM_BYTES, st>>>(tmA, tmB, p);
+    else if (!small)
+      conv_tc2_kernel<false, 128><<<grid, C2_THREADS, C2_SMEM_BYTES, st>>>(tmA, tmB, p);
     else
-      conv_tc2_kernel<false><<<grid, C2_THREADS, C2_SMEM_BYTES, st>>>(tmA, tmB, p);
+      conv_tc2_kernel<false, 16><<<grid, C2_THREADS, C2_SMEM_BYTES, st>>>(tmA, tmB, p);
   }
   DFL_LAUNCH_OK("conv_tc_kernel");
   return DFL_OK;

@@ -1,0 +1,332 @@
+// deepfluids_b200 -- backward of the 128 -> C (C = 1..3) output convolution (reference model.py:42,84) on tcgen05.
+//
+// TF autodiff runs Conv*BackpropInput + Conv*BackpropFilter + BiasAddGrad here; both contractions are tiny in one
+// GEMM dimension (C*taps <= 81), so instead of a spatial convolution they are expressed over an im2col tile of the
+// C-channel output gradient that 128 builder threads assemble directly in shared memory (rows = voxels, columns =
+// k = tap*C + co, 128B-swizzled exactly like a TMA image):
+//     G[q][k]     = dOut[q - (tap-1)][co]                       (zero outside the domain)
+//     ds[q][ci]   = sum_k G[q][k] * W[tap][ci][co]              dgrad:  D1[M=voxel, N=ci]  = G (K-major A) x W'^T
+//     dW[k][ci]   = sum_q s[q][ci] * G[q][k]                    wgrad:  D2[M=ci,    N=k]  += s^T (MN-major A) x G (MN-major B)
+//     db[co]      = sum_q dOut[q][co]
+// The SAME smem image of G is the K-major A operand of the first GEMM and the MN-major B operand of the second.
+// s tiles arrive by TMA (two 64-channel boxes); W' (bf16 [128 ci][128 k]) is resident in smem; D1 is double-buffered in
+// TMEM and drained by 4 epilogue warps (store ds and ds * lrelu'(y) in bf16); D2 accumulates over the CTA's whole slab
+// and is added to the fp32 gradient with atomics at the end.
+// Warps: 0 = TMA producer, 1 = TMEM alloc + MMA issuer, 2..5 = epilogue, 6..9 = im2col builders.
+#include "dfl_common.cuh"
+
+namespace dfl {
+
+constexpr int LB_THREADS = 320;
+constexpr int LB_OP = 32768;                       // one 128 x 128 bf16 operand image (two 16 KB halves)
+constexpr int LB_SMEM = 5 * LB_OP + 1024 + 1024;   // W' + 2 G + 2 S + ctrl + align slack
+
+struct LastBwdParams {
+  int B, D, H, W;
+  int ty, tx, ntiles;          // tiles of 1 x 8 x 16 voxels
+  const float* dout;           // [B,D,H,W,C] fp32
+  const float* w;              // [taps][128][C] fp32 (TF layout)
+  const __nv_bfloat16* mask_src;   // y of the layer below (lrelu derivative) or nullptr
+  __nv_bfloat16* ds;           // [B,D,H,W,128] or nullptr
+  __nv_bfloat16* ds_masked;    // [B,D,H,W,128] or nullptr
+  float* dw;                   // [taps][128][C] fp32, accumulated
+  float* db;                   // [C] fp32, accumulated
+};
+
+__device__ __forceinline__ uint32_t lb_pack(float a, float b) {
+  __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+
+template <int C, bool k3D>
+__global__ void __launch_bounds__(LB_THREADS, 1)
+lastconv_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmS, LastBwdParams p) {
+  constexpr int NT = k3D ? 27 : 9;
+  constexpr int KREAL = NT * C;                   // <= 81
+  constexpr int KSTEPS1 = (KREAL + 15) / 16;      // K16 steps of the dgrad GEMM
+  constexpr int NCHUNK = (KREAL + 7) / 8;         // 16-byte chunks per im2col row that carry data
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sW = smem;                   // [2 halves][128 rows (ci)][128 B]   K-major, k = tap*C+co
+  uint8_t* sG = smem + LB_OP;           // 2 buffers
+  uint8_t* sS = smem + 3 * LB_OP;       // 2 buffers
+  uint8_t* ctrl = smem + 5 * LB_OP;
+  uint64_t* s_full = reinterpret_cast<uint64_t*>(ctrl);
+  uint64_t* s_empty = s_full + 2;
+  uint64_t* g_full = s_empty + 2;
+  uint64_t* g_empty = g_full + 2;
+  uint64_t* d1_full = g_empty + 2;
+  uint64_t* d1_empty = d1_full + 2;
+  uint64_t* d2_full = d1_empty + 2;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(d2_full + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  // ---- one-time: zero both G buffers, write W' (bf16, swizzled K-major image) ----
+  for (int i = threadIdx.x; i < 3 * LB_OP / 16; i += LB_THREADS) reinterpret_cast<uint4*>(sW)[i] = make_uint4(0, 0, 0, 0);
+  __syncthreads();
+  for (int i = threadIdx.x; i < 128 * KREAL; i += LB_THREADS) {
+    const int ci = i / KREAL, k = i % KREAL;
+    const int t = k / C, co = k % C;
+    const float v = p.w[(static_cast<size_t>(t) * 128 + ci) * C + co];
+    const int half = k >> 6, kk = k & 63;
+    const int chunk = (kk >> 3) ^ (ci & 7);
+    *reinterpret_cast<__nv_bfloat16*>(sW + half * (LB_OP / 2) + ci * 128 + chunk * 16 + (kk & 7) * 2) = __float2bfloat16_rn(v);
+  }
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmS);
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&s_full[s], 1); mbar_init(&s_empty[s], 1);
+      mbar_init(&g_full[s], 128); mbar_init(&g_empty[s], 1);
+      mbar_init(&d1_full[s], 1); mbar_init(&d1_empty[s], 128);
+    }
+    mbar_init(d2_full, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_ptr, 512);
+    tmem_relinquish();
+  }
+  fence_proxy_async();          // generic-proxy smem writes (W', zeros) -> visible to the tensor core (async proxy)
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+  const int my_tiles = (p.ntiles > static_cast<int>(blockIdx.x))
+                           ? (p.ntiles - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x)
+                           : 0;
+
+  if (warp == 0) {
+    // ================================ TMA producer: s tiles ================================
+    if (lane == 0) {
+      uint32_t i = 0;
+      for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++i) {
+        int r = tile;
+        const int x0 = (r % p.tx) * 16; r /= p.tx;
+        const int y0 = (r % p.ty) * 8; r /= p.ty;
+        const int z = r % p.D;
+        const int b = r / p.D;
+        const uint32_t s = i & 1, ph = (i >> 1) & 1;
+        mbar_wait(&s_empty[s], ph ^ 1);
+        mbar_expect_tx(&s_full[s], LB_OP);
+        tma_load_5d(sS + s * LB_OP, &tmS, &s_full[s], 0, x0, y0, z, b);
+        tma_load_5d(sS + s * LB_OP + LB_OP / 2, &tmS, &s_full[s], 64, x0, y0, z, b);
+      }
+    }
+  } else if (warp == 1) {
+    // ================================ MMA issuer ================================
+    if (lane == 0) {
+      constexpr uint32_t idesc1 = umma_idesc_bf16(128, 128, 0, 0);   // G (K-major) x W' (K-major)
+      constexpr uint32_t idesc2 = umma_idesc_bf16(128, 128, 1, 1);   // s^T (MN-major) x G (MN-major)
+      const uint32_t w0 = smem_u32(sW);
+      for (int i = 0; i < my_tiles; ++i) {
+        const uint32_t s = i & 1, ph = (i >> 1) & 1;
+        mbar_wait(&g_full[s], ph);
+        mbar_wait(&s_full[s], ph);
+        mbar_wait(&d1_empty[s], ph ^ 1);
+        tc_fence_after();
+        const uint32_t g0 = smem_u32(sG + s * LB_OP), s0 = smem_u32(sS + s * LB_OP);
+#pragma unroll
+        for (int k = 0; k < KSTEPS1; ++k) {
+          const uint32_t off = (k >> 2) * (LB_OP / 2) + (k & 3) * 32;
+          umma_bf16(tmem_base + s * 128, umma_desc_sw128(g0 + off, 16, 1024), umma_desc_sw128(w0 + off, 16, 1024), idesc1,
+                    k != 0 ? 1u : 0u);
+        }
+        umma_commit(&d1_full[s]);
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+          umma_bf16(tmem_base + 256, umma_desc_sw128(s0 + k * 2048, LB_OP / 2, 1024),
+                    umma_desc_sw128(g0 + k * 2048, LB_OP / 2, 1024), idesc2, (i != 0 || k != 0) ? 1u : 0u);
+        umma_commit(&g_empty[s]);
+        umma_commit(&s_empty[s]);
+      }
+      umma_commit(d2_full);
+    }
+  } else if (warp < 6) {
+    // ================================ epilogue (warps 2..5) ================================
+    const int quarter = warp & 3;
+    const int row = quarter * 32 + lane;
+    const int lx = row & 15, ly = row >> 4;
+    int i = 0;
+    for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++i) {
+      int r = tile;
+      const int x = (r % p.tx) * 16 + lx; r /= p.tx;
+      const int y = (r % p.ty) * 8 + ly; r /= p.ty;
+      const int z = r % p.D;
+      const int b = r / p.D;
+      const bool valid = (x < p.W) && (y < p.H);
+      const size_t pos = ((static_cast<size_t>(b) * p.D + z) * p.H + y) * p.W + x;
+      const uint32_t s = i & 1, ph = (i >> 1) & 1;
+      mbar_wait(&d1_full[s], ph);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + s * 128;
+#pragma unroll 1
+      for (int c0 = 0; c0 < 128; c0 += 32) {
+        uint32_t rr[32];
+        tmem_ld_32x32(taddr + c0, rr);
+        tmem_ld_wait();
+        if (!valid) continue;
+        if (p.ds) {
+          uint4* o = reinterpret_cast<uint4*>(p.ds + pos * 128 + c0);
+#pragma unroll
+          for (int q = 0; q < 4; ++q)
+            o[q] = make_uint4(lb_pack(__uint_as_float(rr[q * 8]), __uint_as_float(rr[q * 8 + 1])),
+                              lb_pack(__uint_as_float(rr[q * 8 + 2]), __uint_as_float(rr[q * 8 + 3])),
+                              lb_pack(__uint_as_float(rr[q * 8 + 4]), __uint_as_float(rr[q * 8 + 5])),
+                              lb_pack(__uint_as_float(rr[q * 8 + 6]), __uint_as_float(rr[q * 8 + 7])));
+        }
+        if (p.ds_masked) {
+          const uint4* m = reinterpret_cast<const uint4*>(p.mask_src + pos * 128 + c0);
+          uint4* o = reinterpret_cast<uint4*>(p.ds_masked + pos * 128 + c0);
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const uint4 mv = __ldg(m + q);
+            const uint32_t mw[4] = {mv.x, mv.y, mv.z, mv.w};
+            uint32_t ow[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const float a = __uint_as_float(rr[q * 8 + 2 * e]) * lrelu_grad_from_out(__uint_as_float(mw[e] << 16));
+              const float c = __uint_as_float(rr[q * 8 + 2 * e + 1]) * lrelu_grad_from_out(__uint_as_float(mw[e] & 0xFFFF0000u));
+              ow[e] = lb_pack(a, c);
+            }
+            o[q] = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(&d1_empty[s]);
+    }
+    // ---- D2 -> dW (fp32 atomics), lane = ci ----
+    if (my_tiles > 0) {
+      mbar_wait(d2_full, 0);
+      tc_fence_after();
+      const int ci = row;
+#pragma unroll 1
+      for (int c0 = 0; c0 < ((KREAL + 31) / 32) * 32; c0 += 32) {
+        uint32_t rr[32];
+        tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + 256 + c0, rr);
+        tmem_ld_wait();
+#pragma unroll
+        for (int e = 0; e < 32; ++e) {
+          const int k = c0 + e;
+          if (k < KREAL) atomicAdd(p.dw + (static_cast<size_t>(k / C) * 128 + ci) * C + (k % C), __uint_as_float(rr[e]));
+        }
+      }
+    }
+  } else {
+    // ================================ im2col builders (warps 6..9) ================================
+    const int row = (warp - 6) * 32 + lane;
+    const int lx = row & 15, ly = row >> 4;
+    float bsum[C];
+#pragma unroll
+    for (int c = 0; c < C; ++c) bsum[c] = 0.f;
+    int i = 0;
+    for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++i) {
+      int r = tile;
+      const int x = (r % p.tx) * 16 + lx; r /= p.tx;
+      const int y = (r % p.ty) * 8 + ly; r /= p.ty;
+      const int z = r % p.D;
+      const int b = r / p.D;
+      const bool valid = (x < p.W) && (y < p.H);
+      const uint32_t s = i & 1, ph = (i >> 1) & 1;
+      mbar_wait(&g_empty[s], ph ^ 1);
+      uint8_t* grow = sG + s * LB_OP + row * 128;
+      const float* base = p.dout + (static_cast<size_t>(b) * p.D * p.H * p.W) * C;
+#pragma unroll
+      for (int j = 0; j < NCHUNK; ++j) {
+        float v[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          const int k = j * 8 + e;
+          v[e] = 0.f;
+          if (k < KREAL) {
+            const int t = k / C, co = k % C;
+            const int dx = t % 3, dy = (t / 3) % 3, dz = k3D ? t / 9 : 1;
+            const int xx = x - (dx - 1), yy = y - (dy - 1), zz = k3D ? z - (dz - 1) : z;
+            if (valid && xx >= 0 && xx < p.W && yy >= 0 && yy < p.H && zz >= 0 && zz < p.D)
+              v[e] = __ldg(base + ((static_cast<size_t>(zz) * p.H + yy) * p.W + xx) * C + co);
+          }
+        }
+        const int half = j >> 3, jj = j & 7;
+        *reinterpret_cast<uint4*>(grow + half * (LB_OP / 2) + ((jj ^ (row & 7)) * 16)) =
+            make_uint4(lb_pack(v[0], v[1]), lb_pack(v[2], v[3]), lb_pack(v[4], v[5]), lb_pack(v[6], v[7]));
+      }
+      if (valid) {
+#pragma unroll
+        for (int c = 0; c < C; ++c)
+          bsum[c] += __ldg(base + ((static_cast<size_t>(z) * p.H + y) * p.W + x) * C + c);
+      }
+      fence_proxy_async();
+      mbar_arrive(&g_full[s]);
+    }
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+      const float t = warp_sum(bsum[c]);
+      if (lane == 0 && my_tiles > 0) atomicAdd(p.db + c, t);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    __syncwarp();
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+template <int C, bool k3D>
+static int lastconv_bwd_launch_t(const CUtensorMap& tmS, const LastBwdParams& p, cudaStream_t st) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    DFL_CUDA_OK(cudaFuncSetAttribute(lastconv_bwd_tc_kernel<C, k3D>, cudaFuncAttributeMaxDynamicSharedMemorySize, LB_SMEM));
+    attr_set = true;
+  }
+  const int grid = std::min(p.ntiles, num_sms());
+  lastconv_bwd_tc_kernel<C, k3D><<<grid, LB_THREADS, LB_SMEM, st>>>(tmS, p);
+  DFL_LAUNCH_OK("lastconv_bwd_tc_kernel");
+  return DFL_OK;
+}
+
+int lastconv_bwd_tc(const void* s, const float* dout, const float* w, const void* mask_src, void* ds, void* ds_masked,
+                    float* dw, float* db, const int64_t* dims, int nd, int cout, cudaStream_t st) {
+  DFL_REQUIRE(nd == 2 || nd == 3, "lastconv_bwd: ndim must be 2 or 3");
+  DFL_REQUIRE(cout >= 1 && cout <= 3, "lastconv_bwd: Cout must be 1..3 (got %d)", cout);
+  DFL_REQUIRE(!(ds_masked && !mask_src), "lastconv_bwd: ds_masked requested without mask_src");
+  LastBwdParams p{};
+  p.B = static_cast<int>(dims[0]);
+  p.D = nd == 3 ? static_cast<int>(dims[1]) : 1;
+  p.H = static_cast<int>(dims[nd - 1]);
+  p.W = static_cast<int>(dims[nd]);
+  p.tx = (p.W + 15) / 16;
+  p.ty = (p.H + 7) / 8;
+  p.ntiles = p.B * p.D * p.ty * p.tx;
+  p.dout = dout;
+  p.w = w;
+  p.mask_src = static_cast<const __nv_bfloat16*>(mask_src);
+  p.ds = static_cast<__nv_bfloat16*>(ds);
+  p.ds_masked = static_cast<__nv_bfloat16*>(ds_masked);
+  p.dw = dw;
+  p.db = db;
+  CUtensorMap tmS;
+  const uint64_t gd[5] = {128, static_cast<uint64_t>(p.W), static_cast<uint64_t>(p.H), static_cast<uint64_t>(p.D),
+                          static_cast<uint64_t>(p.B)};
+  const uint64_t gs[4] = {256, 256ull * p.W, 256ull * p.W * p.H, 256ull * p.W * p.H * p.D};
+  const uint32_t box[5] = {64, 16, 8, 1, 1};
+  int rc = encode_tensor_map(&tmS, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, s, gd, gs, box, CU_TENSOR_MAP_SWIZZLE_128B);
+  if (rc) return rc;
+  if (nd == 3) {
+    switch (cout) {
+      case 1: return lastconv_bwd_launch_t<1, true>(tmS, p, st);
+      case 2: return lastconv_bwd_launch_t<2, true>(tmS, p, st);
+      default: return lastconv_bwd_launch_t<3, true>(tmS, p, st);
+    }
+  }
+  switch (cout) {
+    case 1: return lastconv_bwd_launch_t<1, false>(tmS, p, st);
+    case 2: return lastconv_bwd_launch_t<2, false>(tmS, p, st);
+    default: return lastconv_bwd_launch_t<3, false>(tmS, p, st);
+  }
+}
+
+}  // namespace dfl

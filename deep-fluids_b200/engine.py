@@ -121,6 +121,7 @@ class GeneratorEngine(object):
             for cn in row:
                 self.wf[cn] = torch.empty(filters, self.taps * filters, dtype=torch.bfloat16, device=self.device)
                 self.wd[cn] = torch.empty(filters, self.taps * filters, dtype=torch.bfloat16, device=self.device)
+        self.w_last16 = torch.zeros(16, self.taps * filters, dtype=torch.bfloat16, device=self.device)
         self.repack()
         # ---- activations (bf16) and gradient scratch
         bf = dict(dtype=torch.bfloat16, device=self.device)
@@ -148,6 +149,7 @@ class GeneratorEngine(object):
         for row in self.conv_names:
             for cn in row:
                 K.pack_conv_weights(self.params.p(cn + "/weights"), self.wf[cn], self.wd[cn])
+        K.pack_lastconv_weights(self.params.p(self.last_name + "/weights"), self.w_last16)
 
     # ------------------------------------------------------------------ forward (model.py:5-46 / :48-87)
     def forward(self, z):
@@ -170,7 +172,7 @@ class GeneratorEngine(object):
                     K.conv3x3(cur, self.wf[cn], bias, out=self.y[i][c], out2=self.s, residual=self.x0[i],
                               flags=K.CONV_LRELU)
                 cur = self.y[i][c]
-        K.lastconv_fwd(self.s, P.p(self.last_name + "/weights"), P.p(self.last_name + "/biases"), out=self.pot)
+        K.lastconv_fwd_tc(self.s, self.w_last16, P.p(self.last_name + "/biases"), self.cout, out=self.pot)
         return self.pot
 
     # ------------------------------------------------------------------ backward (TF autodiff of the above)
@@ -179,10 +181,10 @@ class GeneratorEngine(object):
         P = self.params
         nc = self.num_conv
         top = self.rep - 1
-        K.lastconv_wgrad(self.s, dpot, P.g(self.last_name + "/weights"), P.g(self.last_name + "/biases"))
         ds = self._gview(0, top)
         dpre = self._gview(1, top)
-        K.lastconv_dgrad(dpot, P.p(self.last_name + "/weights"), self.y[top][nc - 1], ds, dpre)
+        K.lastconv_bwd(self.s, dpot, P.p(self.last_name + "/weights"), self.y[top][nc - 1], ds, dpre,
+                       P.g(self.last_name + "/weights"), P.g(self.last_name + "/biases"))
         for i in range(top, -1, -1):
             other = self._gview(2, i)
             gx0 = self._gview(3, i)

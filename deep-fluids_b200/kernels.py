@@ -183,6 +183,35 @@ def lastconv_wgrad(x, dout, dw, db):
     check(cabi.lib().dfl_lastconv_wgrad(_p(x), _p(dout), _p(dw), _p(db), d, nd, dout.shape[-1], _st()))
 
 
+def pack_lastconv_weights(w, w16=None):
+    """w fp32 TF layout [k,(k,)k,128,C] -> bf16 [16, taps*128] (rows >= C stay zero): operand of the small-Cout conv."""
+    cin, cout = w.shape[-2], w.shape[-1]
+    taps = w.numel() // (cin * cout)
+    if w16 is None:
+        w16 = torch.zeros(16, taps * cin, dtype=torch.bfloat16, device=w.device)
+    PROF.launches += 1
+    check(cabi.lib().dfl_pack_conv_weights(_p(w), _p(w16), None, taps, cin, cout, _st()))
+    return w16
+
+
+def lastconv_fwd_tc(x, w16, bias, cout, out=None):
+    """128 -> cout (1..3) output conv on the tap-window tensor-core kernel (N = 16 variant); out fp32 [.., cout]."""
+    d, nd = _spatial(x)
+    if out is None:
+        out = torch.empty(x.shape[:-1] + (cout,), dtype=torch.float32, device=x.device)
+    flops = 2.0 * (x.numel() // 128) * 128 * cout * (3 ** nd)
+    PROF.timed("lastconv_fwd_tc", flops, lambda: check(cabi.lib().dfl_conv3x3_fwd(
+        _p(x), _p(w16), _p(bias), _p(out), None, None, None, d, nd, 128, cout, 0, _st())))
+    return out
+
+
+def lastconv_bwd(s, dout, w, mask_src, ds, ds_masked, dw, db):
+    """fused dgrad + wgrad + bias-grad of the output conv (tensor cores)"""
+    d, nd = _spatial(s)
+    PROF.timed("lastconv_bwd_tc", 0.0, lambda: check(cabi.lib().dfl_lastconv_bwd(
+        _p(s), _p(dout), _p(w), _p(mask_src), _p(ds), _p(ds_masked), _p(dw), _p(db), d, nd, w.shape[-1], _st())))
+
+
 def pool_mask(g, mask_src, ds, dmasked):
     """g: fine-grid gradient [B,(2D,)2H,2W,128]; ds / dmasked: coarse [B,(D,)H,W,128]"""
     ref = ds if ds is not None else dmasked

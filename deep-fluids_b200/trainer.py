@@ -18,6 +18,7 @@ import numpy as np
 import torch
 import torch.distributed as dist
 
+from . import dp
 from . import kernels as K
 from .engine import GeneratorEngine
 
@@ -116,10 +117,7 @@ class Trainer(object):
         if want_vel:
             self.G_ = vel
         eng.backward(self._dpot)
-        scale = 1.0
-        if self.world > 1:
-            dist.all_reduce(eng.params.grad)        # ONE NCCL all-reduce over the flat gradient buffer
-            scale = 1.0 / self.world
+        scale = dp.allreduce_grads_(eng.params.grad)   # ONE NCCL all-reduce over the flat gradient buffer
         if self.optimizer == 'adam':
             eng.adam_step(self.g_lr, self.beta1, self.beta2, 1e-8, scale)
         else:

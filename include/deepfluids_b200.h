@@ -84,7 +84,9 @@ int dfl_pack_conv_weights(const float* w, void* w_fwd, void* w_dgrad, int taps, 
  *   if (out)  out  = v
  *   if (out2) out2 = v + residual (residual may be NULL), nearest-x2 upsampled if DFL_CONV_OUT2_UPSAMPLE
  * Forward use: model.py:26-36 / :68-79 (conv + lrelu [+ residual add + upscale]).  Backward use (dgrad): pass
- * w_dgrad from dfl_pack_conv_weights, bias = NULL. */
+ * w_dgrad from dfl_pack_conv_weights, bias = NULL.
+ * Small-Cout variant (the 128 -> 1..3 output conv, model.py:42,84): cout in [1,16], w_packed = bf16 [16][taps*Cin]
+ * (rows >= cout zero), `out` = fp32 [..,cout] = conv + bias; no activation / out2 / residual / mask. */
 int dfl_conv3x3_fwd(const void* x, const void* w_packed, const float* bias, void* out, void* out2,
                     const void* residual, const void* mask_src, const int64_t* dims, int ndim, int cin, int cout,
                     int flags, void* stream);
@@ -103,6 +105,12 @@ int dfl_lastconv_dgrad(const float* dout, const float* w, const void* mask_src, 
 /* dw += x^T dout, db += sum dout  (fp32, accumulated) */
 int dfl_lastconv_wgrad(const void* x, const float* dout, float* dw, float* db, const int64_t* dims, int ndim,
                        int cout, void* stream);
+
+/* Fused tensor-core backward of the output conv: ds = conv^T(dout, w) (bf16, may be NULL), ds_masked = ds *
+ * lrelu'(mask_src) (bf16, may be NULL), dw += s^T (x) dout, db += sum dout (fp32, accumulated).  s = the conv's input
+ * (bf16 [..,128]).  Replaces Conv*BackpropInput + Conv*BackpropFilter + BiasAddGrad of model.py:42,84. */
+int dfl_lastconv_bwd(const void* s, const float* dout, const float* w, const void* mask_src, void* ds, void* ds_masked,
+                     float* dw, float* db, const int64_t* dims, int ndim, int cout, void* stream);
 
 /* adjoint of nearest-x2 upsampling fused with the lrelu derivative (model.py:35-36 / :77-78 backward):
  *   ds = sum of the 2x2(x2) children of g;  dmasked = ds * lrelu'(mask_src).  cdims = COARSE dims. */

@@ -85,28 +85,37 @@ def init_variables(table, seed=123, dtype=torch.float32):
     return out
 
 
+def bf16_round_ste(x):
+    """Round to bf16 with a straight-through gradient: models the B200 path's bf16 *storage* of activations (fp32
+    accumulation inside each layer) so that leaky-ReLU masks agree with the device; used only by parity tests."""
+    return x + (x.detach().bfloat16().to(x.dtype) - x.detach())
+
+
 def generator_forward(z, var, output_shape, filters=128, num_conv=4, repeat=0, name="G",
-                      act=R.lrelu, keep=None):
+                      act=R.lrelu, keep=None, store=None):
     """GeneratorBE / GeneratorBE3 forward (model.py:5-46 / :48-87), skip_concat=False.
 
-    z [B,z_dim]; returns out [B,*spatial,C_out].  `keep`, if a list, receives every intermediate."""
+    z [B,z_dim]; returns out [B,*spatial,C_out].  `keep`, if a list, receives every intermediate.  `store`, if given
+    (e.g. bf16_round_ste), is applied to every tensor the device path materialises (FC output, each conv output,
+    each residual sum) and to the conv weights' operand copy; default None = exact fp32 reference semantics."""
+    st = store if store is not None else (lambda t: t)
     spatial = list(output_shape[:-1])
     nd = len(spatial)
     rep = _repeat_num(spatial, repeat)
     x0s = [int(i // 2 ** (rep - 1)) for i in spatial]
     x = R.linear(z, var["%s/0_fc/weights" % name], var["%s/0_fc/biases" % name])
-    x = x.reshape([-1] + x0s + [filters])
+    x = st(x.reshape([-1] + x0s + [filters]))
     x0 = x
     n = 1
     up = R.upscale if nd == 2 else R.upscale3
     for idx in range(rep):
         for _ in range(num_conv):
-            x = R.conv_nd(x, var["%s/%d_conv/weights" % (name, n)], var["%s/%d_conv/biases" % (name, n)],
-                          1, act)
+            x = st(R.conv_nd(x, st(var["%s/%d_conv/weights" % (name, n)]), var["%s/%d_conv/biases" % (name, n)],
+                             1, act))
             if keep is not None:
                 keep.append(x)
             n += 1
-        x = x + x0                      # model.py:34 / :76 and :39 / :82
+        x = st(x + x0)                  # model.py:34 / :76 and :39 / :82
         if idx < rep - 1:
             x = up(x, 2)                # model.py:35-36 / :77-78
             x0 = x

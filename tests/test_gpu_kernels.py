@@ -286,6 +286,36 @@ def test_lastconv_fwd_dgrad_wgrad(shape, nd, cout):
     assert rel_l2(db, gb) <= 1e-5
 
 
+@pytest.mark.parametrize("shape,nd,cout", [((2, 4, 6, 11), 3, 3), ((1, 8, 8, 8), 3, 3), ((1, 5, 20, 37), 3, 1), ((3, 16, 12), 2, 1),
+                                           ((2, 9, 21), 2, 2), ((2, 40, 33), 2, 3)])
+def test_lastconv_tensorcore_fwd_and_fused_bwd(shape, nd, cout):
+    """tap-window N=16 forward and the fused im2col-GEMM backward vs autograd on the oracle (bf16 operands, fp32 acc)."""
+    from deepfluids_b200 import kernels as K
+    g = torch.Generator().manual_seed(41)
+    x = (torch.randn(*shape, 128, generator=g) * 0.5).bfloat16()
+    w = R.xavier_uniform_((3,) * nd + (128, cout), g).bfloat16().float()     # bf16-representable weights
+    b = torch.randn(cout, generator=g) * 0.1
+    xin = x.float().requires_grad_(True)
+    wt = w.clone().requires_grad_(True)
+    bt = b.clone().requires_grad_(True)
+    y = R.conv_nd(xin, wt, bt, 1, None)
+    dy = (torch.randn(y.shape, generator=g) * 1e-3).bfloat16().float()       # bf16-representable gradient
+    gx, gw, gb = torch.autograd.grad(y, [xin, wt, bt], dy)
+    w16 = K.pack_lastconv_weights(w.to(dev()))
+    out = K.lastconv_fwd_tc(x.to(dev()), w16, b.to(dev()), cout)
+    assert rel_l2(out, y.detach()) <= 1e-5
+    mask_src = torch.randn(*shape, 128, generator=g).bfloat16()
+    ds = torch.empty(x.shape, dtype=torch.bfloat16, device=dev())
+    dsm = torch.empty_like(ds)
+    dw = torch.zeros(w.shape, device=dev())
+    db = torch.zeros(cout, device=dev())
+    K.lastconv_bwd(x.to(dev()), dy.to(dev()), w.to(dev()), mask_src.to(dev()), ds, dsm, dw, db)
+    assert rel_l2(ds.float(), gx) <= 4e-3
+    assert rel_l2(dsm.float(), gx * torch.where(mask_src.float() >= 0, 1.0, 0.2)) <= 4e-3
+    assert rel_l2(dw, gw) <= 1e-4
+    assert rel_l2(db, gb) <= 1e-5
+
+
 @pytest.mark.parametrize("cshape,nd", [((2, 3, 4, 5), 3), ((2, 6, 7), 2)])
 def test_pool_mask(cshape, nd):
     from deepfluids_b200 import kernels as K

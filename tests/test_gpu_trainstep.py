@@ -40,10 +40,13 @@ def test_generator_fwd_bwd_vs_oracle(spatial, num_conv, B):
     assert abs(loss3[0].item() - loss.item()) <= 1e-2 * abs(loss.item())
     # divergence-free output (north_star: <= 1e-5)
     assert float(K.divergence(vel).abs().max()) <= 1e-5
-    # (1) backward kernels alone: oracle autograd driven by the SAME upstream gradient dL/dpot the GPU produced
-    #     (isolates conv dgrad/wgrad/pool/FC-bwd accuracy from L1 sign flips): rel-L2 <= 3e-2 on every tensor
+    # (1) backward kernels alone: oracle autograd driven by the SAME upstream gradient dL/dpot the GPU produced, on
+    #     the oracle run with bf16 *storage* of activations (fp32 math; straight-through rounding) so the
+    #     leaky-ReLU masks agree with the device -- isolates dgrad/wgrad/pool/FC-bwd accuracy from the sign flips of
+    #     the non-smooth ops (L1 loss, lrelu): rel-L2 <= 3e-2 on every gradient tensor
     leaves = OrderedDict((k, v.clone().requires_grad_(True)) for k, v in var.items())
-    pot_o = M.generator_forward(y, leaves, spatial + [cout], num_conv=num_conv)
+    pot_o = M.generator_forward(y, leaves, spatial + [cout], num_conv=num_conv, store=M.bf16_round_ste)
+    assert rel_l2(pot, pot_o.detach()) <= 3e-3
     gs = torch.autograd.grad(pot_o, list(leaves.values()), dpot.cpu())
     worst = 0.0
     for k, gref in zip(leaves, gs):
