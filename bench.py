@@ -214,7 +214,9 @@ def run_gpu_arm(args):
     # ---------------- end-to-end arm (`e2e`): host pinned inputs -> H2D -> train_step -> D2H loss ----------------
     xh = [x.cpu().pin_memory() for x, _ in bm._pool]
     yh = [y.cpu().pin_memory() for _, y in bm._pool]
-    xd, yd = torch.empty_like(bm._pool[0][0]), torch.empty_like(bm._pool[0][1])
+    # H2D straight into the trainer's static (graph-captured) input buffers when they exist
+    xd = tr._xs if tr._xs is not None else torch.empty_like(bm._pool[0][0])
+    yd = tr._ys if tr._ys is not None else torch.empty_like(bm._pool[0][1])
     loss_h = torch.empty(3, dtype=torch.float32).pin_memory()
     cnt = [0]
 
@@ -237,6 +239,7 @@ def run_gpu_arm(args):
 
     # ---------------- per-kernel timing with CUDA events (2 extra instrumented steps, same stream) ----------------
     K.PROF.events = []
+    tr.use_graph = False          # eager launches so every kernel can be bracketed by events
     for _ in range(2):
         tr.train_step()
     torch.cuda.synchronize()

@@ -34,6 +34,7 @@ SIGNATURES = {
     "dfl_lastconv_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _dims, _i, _i, _vp]),
     "dfl_pool_mask": (_i, [_vp, _vp, _vp, _vp, _dims, _i, _vp]),
     "dfl_adam_step": (_i, [_vp, _vp, _vp, _vp, _sz, _f, _f, _f, _f, _f, _vp]),
+    "dfl_adam_step_dev": (_i, [_vp, _vp, _vp, _vp, _sz, _vp, _f, _f, _f, _f, _vp]),
     "dfl_cast_f32_bf16": (_i, [_vp, _vp, _sz, _vp]),
 }
 

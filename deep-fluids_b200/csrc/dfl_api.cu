@@ -77,8 +77,8 @@ int pool_mask(const void* g, const void* mask_src, void* ds, void* dmasked, cons
               cudaStream_t st);
 int bias_grad(const void* d, float* db, size_t npos, cudaStream_t st);
 int pack_conv_weights(const float* W, void* wf, void* wd, int taps, int cin, int cout, cudaStream_t st);
-int adam_step(float* p, const float* g, float* m, float* v, size_t n, float lr_t, float b1, float b2, float eps,
-              float grad_scale, cudaStream_t st);
+int adam_step(float* p, const float* g, float* m, float* v, size_t n, float lr_t, const float* lr_t_dev, float b1,
+              float b2, float eps, float grad_scale, cudaStream_t st);
 int cast_f32_bf16(const float* a, void* o, size_t n, cudaStream_t st);
 
 }  // namespace dfl
@@ -184,7 +184,12 @@ int dfl_pool_mask(const void* g, const void* mask_src, void* ds, void* dmasked, 
 }
 int dfl_adam_step(float* param, const float* grad, float* m, float* v, size_t n, float lr_t, float beta1, float beta2,
                   float eps, float grad_scale, void* stream) {
-  return adam_step(param, grad, m, v, n, lr_t, beta1, beta2, eps, grad_scale, ST(stream));
+  return adam_step(param, grad, m, v, n, lr_t, nullptr, beta1, beta2, eps, grad_scale, ST(stream));
+}
+int dfl_adam_step_dev(float* param, const float* grad, float* m, float* v, size_t n, const float* lr_t_dev, float beta1,
+                      float beta2, float eps, float grad_scale, void* stream) {
+  DFL_REQUIRE(lr_t_dev != nullptr, "adam_step_dev: lr_t_dev is NULL");
+  return adam_step(param, grad, m, v, n, 0.f, lr_t_dev, beta1, beta2, eps, grad_scale, ST(stream));
 }
 int dfl_cast_f32_bf16(const float* in, void* out, size_t n, void* stream) {
   return cast_f32_bf16(in, out, n, ST(stream));

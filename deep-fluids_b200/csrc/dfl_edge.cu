@@ -527,8 +527,9 @@ int pack_conv_weights(const float* W, void* wf, void* wd, int taps, int cin, int
 //   lr_t = lr * sqrt(1 - b2^t) / (1 - b1^t) is computed by the host and passed in.  grad_scale folds 1/world.
 // =============================================================================================
 __global__ void adam_step_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
-                                 float* __restrict__ v, size_t n, float lr_t, float b1, float b2, float eps,
-                                 float grad_scale) {
+                                 float* __restrict__ v, size_t n, float lr_t, const float* __restrict__ lr_t_dev,
+                                 float b1, float b2, float eps, float grad_scale) {
+  if (lr_t_dev) lr_t = *lr_t_dev;      // CUDA-graph friendly: the step size lives in device memory
   for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n;
        i += static_cast<size_t>(gridDim.x) * blockDim.x) {
     const float gi = g[i] * grad_scale;
@@ -540,19 +541,20 @@ __global__ void adam_step_kernel(float* __restrict__ p, const float* __restrict_
   }
 }
 __global__ void sgd_step_kernel(float* __restrict__ p, const float* __restrict__ g, size_t n, float lr,
-                                float grad_scale) {
+                                const float* __restrict__ lr_dev, float grad_scale) {
+  if (lr_dev) lr = *lr_dev;
   for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n;
        i += static_cast<size_t>(gridDim.x) * blockDim.x)
     p[i] -= lr * g[i] * grad_scale;
 }
 
-int adam_step(float* p, const float* g, float* m, float* v, size_t n, float lr_t, float b1, float b2, float eps,
-              float grad_scale, cudaStream_t st) {
+int adam_step(float* p, const float* g, float* m, float* v, size_t n, float lr_t, const float* lr_t_dev, float b1,
+              float b2, float eps, float grad_scale, cudaStream_t st) {
   const int grid = static_cast<int>(std::min<size_t>((n + 255) / 256, static_cast<size_t>(num_sms()) * 16));
   if (m && v)
-    adam_step_kernel<<<grid, 256, 0, st>>>(p, g, m, v, n, lr_t, b1, b2, eps, grad_scale);
+    adam_step_kernel<<<grid, 256, 0, st>>>(p, g, m, v, n, lr_t, lr_t_dev, b1, b2, eps, grad_scale);
   else
-    sgd_step_kernel<<<grid, 256, 0, st>>>(p, g, n, lr_t, grad_scale);
+    sgd_step_kernel<<<grid, 256, 0, st>>>(p, g, n, lr_t, lr_t_dev, grad_scale);
   DFL_LAUNCH_OK("adam_step_kernel");
   return DFL_OK;
 }

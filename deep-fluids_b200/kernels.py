@@ -221,6 +221,13 @@ def pool_mask(g, mask_src, ds, dmasked):
 
 
 # ------------------------------------------------------------------ optimizer / misc
+def adam_step_dev(param, grad, m, v, lr_t_dev, beta1, beta2, eps=1e-8, grad_scale=1.0):
+    """Adam / GD with the step size in device memory (CUDA-graph replayable)."""
+    PROF.launches += 1
+    check(cabi.lib().dfl_adam_step_dev(_p(param), _p(grad), _p(m), _p(v), param.numel(), _p(lr_t_dev), beta1, beta2, eps,
+                                       grad_scale, _st()))
+
+
 def adam_step(param, grad, m, v, lr_t, beta1, beta2, eps=1e-8, grad_scale=1.0):
     PROF.launches += 1
     check(cabi.lib().dfl_adam_step(_p(param), _p(grad), _p(m), _p(v), param.numel(), lr_t, beta1, beta2, eps,

@@ -103,21 +103,85 @@ class Trainer(object):
         self._ws = torch.empty(nb, dtype=torch.uint8, device=self.device)
         self.G_ = None
         self.g_loss = self.g_loss_l1 = self.g_loss_j_l1 = None
+        self.use_graph = bool(int(os.environ.get("DFL_CUDA_GRAPH", "1")))
+        self._captured = False
+        self._xs = self._ys = None
 
     # ------------------------------------------------------------------ one `sess.run(self.g_optim)`
-    def train_step(self, x=None, y=None, want_vel=False):
-        if x is None:
-            x, y = self.batch_manager.batch()
-        self.x, self.y = x, y
+    def _step_body_a(self, x, y, want_vel=False):
+        """zero grads, forward, fused loss + dL/dpot, backward (everything before the gradient exchange)"""
         eng = self.engine
         eng.zero_grad()
         pot = eng.forward(y)
         _, _, vel = K.stencil_loss_fwdbwd(pot, x, self.w1, self.w2, 1.0, want_vel=want_vel, dpot=self._dpot,
                                           loss3=self._loss3, workspace=self._ws)
+        eng.backward(self._dpot)
+        return vel
+
+    def _step_body_b(self, scale):
+        self.engine.optimizer_step_dev(self._lr_dev, self.optimizer == 'adam', self.beta1, self.beta2, 1e-8, scale)
+
+    def _capture(self):
+        """Capture the step as CUDA graph(s): the reference issues ONE sess.run per step; here ~115 kernel launches
+        are replayed with one cudaGraphLaunch (two when a gradient all-reduce sits in between)."""
+        self._xs, self._ys = torch.empty_like(self.x), torch.empty_like(self.y)
+        self._xs.copy_(self.x)
+        self._ys.copy_(self.y)
+        self._lr_dev = torch.zeros(1, dtype=torch.float32, device=self.device)
+        self._lr_host = torch.zeros(1, dtype=torch.float32).pin_memory()
+        scale = 1.0 / self.world
+        # one eager pass on a side stream: sets every kernel's attributes, warms allocator (grad buffers stay zeroed
+        # at the end because lr = 0 leaves the weights untouched)
+        side = torch.cuda.Stream(device=self.device)
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            self._step_body_a(self._xs, self._ys)
+            self._step_body_b(scale)          # lr_dev == 0 -> parameters unchanged; Adam moments are reset below
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        self.engine.params.m.zero_()
+        self.engine.params.v.zero_()
+        l0 = K.PROF.launches
+        self._graph_a = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self._graph_a):
+            self._step_body_a(self._xs, self._ys)
+            if self.world == 1:
+                self._step_body_b(scale)
+        self._graph_b = None
+        if self.world > 1:
+            self._graph_b = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self._graph_b):
+                self._step_body_b(scale)
+        self.launches_per_step = K.PROF.launches - l0
+        self._captured = True
+
+    def train_step(self, x=None, y=None, want_vel=False):
+        if x is None:
+            x, y = self.batch_manager.batch()
+        self.x, self.y = x, y
+        eng = self.engine
+        if self.use_graph and not want_vel:
+            if not self._captured:
+                self._capture()
+            if x.data_ptr() != self._xs.data_ptr():
+                self._xs.copy_(x, non_blocking=True)
+            if y.data_ptr() != self._ys.data_ptr():
+                self._ys.copy_(y, non_blocking=True)
+            lr_t = eng.adam_lr_t(self.g_lr, self.beta1, self.beta2) if self.optimizer == 'adam' else self.g_lr
+            self._lr_host[0] = lr_t
+            self._lr_dev.copy_(self._lr_host, non_blocking=True)
+            self._graph_a.replay()
+            if self._graph_b is not None:
+                dp.allreduce_grads_(eng.params.grad)     # ONE NCCL all-reduce over the flat gradient buffer
+                self._graph_b.replay()
+            K.PROF.launches += self.launches_per_step
+            self.step += 1
+            return self._loss3
+        # ---- eager path (debug / per-kernel timing / want_vel) ----
+        vel = self._step_body_a(x, y, want_vel)
         if want_vel:
             self.G_ = vel
-        eng.backward(self._dpot)
-        scale = dp.allreduce_grads_(eng.params.grad)   # ONE NCCL all-reduce over the flat gradient buffer
+        scale = dp.allreduce_grads_(eng.params.grad)
         if self.optimizer == 'adam':
             eng.adam_step(self.g_lr, self.beta1, self.beta2, 1e-8, scale)
         else:

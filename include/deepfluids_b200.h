@@ -122,6 +122,10 @@ int dfl_pool_mask(const void* g, const void* mask_src, void* ds, void* dmasked, 
 int dfl_adam_step(float* param, const float* grad, float* m, float* v, size_t n, float lr_t, float beta1, float beta2,
                   float eps, float grad_scale, void* stream);
 
+/* same, with the step size read from device memory (`lr_t_dev[0]`) so the launch can live inside a CUDA graph */
+int dfl_adam_step_dev(float* param, const float* grad, float* m, float* v, size_t n, const float* lr_t_dev, float beta1,
+                      float beta2, float eps, float grad_scale, void* stream);
+
 /* ---- misc ------------------------------------------------------------------------------------------- */
 int dfl_cast_f32_bf16(const float* in, void* out, size_t n, void* stream);
 

@@ -119,7 +119,7 @@ def generator_forward(z, var, output_shape, filters=128, num_conv=4, repeat=0, n
         if idx < rep - 1:
             x = up(x, 2)                # model.py:35-36 / :77-78
             x0 = x
-    out = R.conv_nd(x, var["%s/%d_conv/weights" % (name, n)], var["%s/%d_conv/biases" % (name, n)], 1, None)
+    out = R.conv_nd(x, st(var["%s/%d_conv/weights" % (name, n)]), var["%s/%d_conv/biases" % (name, n)], 1, None)
     return out
 
 
