@@ -107,7 +107,10 @@ def cpu_oracle_fields_per_sec(workload, steps, warmup, budget_s=25.0):
     from oracle import ref_train as T
     is3d, rz, ry, rx, _, _ = WORKLOADS[workload]
     spatial = [rz, ry, rx] if is3d else [ry, rx]
-    cores = os.cpu_count() or 1
+    ncpu = os.cpu_count() or 1
+    # measured on the GPU box (profiles/r01_cpu_threads_sweep.txt): oneDNN is fastest at 16 threads; at 128 threads
+    # the same step is 200x slower (oversubscription), so "all the threads it can use" = min(cores, 16)
+    cores = min(ncpu, 16)
     torch.set_num_threads(cores)
     flops = FLOPS_PER_FIELD[workload] or 1e9
     # bounded sample: batch sized for ~2 s per step at ~0.5 TFLOP/s, at least 1 field
@@ -131,7 +134,8 @@ def cpu_oracle_fields_per_sec(workload, steps, warmup, budget_s=25.0):
     per_step = sum(times) / len(times)
     return {"value": b / per_step, "unit": UNIT, "cores": cores, "kind": "port",
             "sample": "%d timed step(s) of batch %d (fwd+bwd+TF-Adam) of workload %s, fp32 torch-CPU/oneDNN oracle"
-                      % (len(times), b, workload), "ms_per_step": per_step * 1e3, "batch": b}
+                      % (len(times), b, workload) + " (%d of %d host cores: fastest thread count measured)" % (cores, ncpu),
+            "ms_per_step": per_step * 1e3, "batch": b}
 
 
 def run_reference_arm(args):
