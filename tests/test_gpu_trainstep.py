@@ -49,9 +49,16 @@ def test_generator_fwd_bwd_vs_oracle(spatial, num_conv, B):
     e_pot = rel_l2(pot, pot_o.detach())
     gs = torch.autograd.grad(pot_o, list(leaves.values()), dpot.cpu())
     errs = OrderedDict((k, rel_l2(eng.params.g(k), gref)) for k, gref in zip(leaves, gs))
+    # the loss is invariant to a constant shift of the potential (curl kills it), so d loss / d (last-layer bias) =
+    # sum(dL/dpot) is exactly 0 in exact arithmetic: both sides are rounding noise -> compare it absolutely instead
+    last_b = list(var.keys())[-1]
+    assert last_b.endswith("biases")
+    scale_b = float(dpot.abs().sum())
+    assert float(eng.params.g(last_b).abs().max()) <= 1e-3 * scale_b and float(grads[last_b].abs().max()) <= 1e-3 * scale_b
+    del errs[last_b]
     # (2) end to end vs the pure-fp32 oracle (includes sign(.) of the L1 losses and lrelu masks, which flip where the
     #     argument is below the bf16 noise): rel-L2 <= 1e-1
-    errs_e2e = OrderedDict((k, rel_l2(eng.params.g(k), grads[k])) for k in var)
+    errs_e2e = OrderedDict((k, rel_l2(eng.params.g(k), grads[k])) for k in var if k != last_b)
     report = "pot(bf16-storage oracle) %.2e | chain max %.2e (%s) | e2e max %.2e (%s)" % (
         e_pot, max(errs.values()), max(errs, key=errs.get), max(errs_e2e.values()), max(errs_e2e, key=errs_e2e.get))
     print(report)
