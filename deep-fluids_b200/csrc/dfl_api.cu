@@ -63,8 +63,8 @@ int fwd_stencils(int op, int nd, const int64_t* dims, const void* in, int in_cs,
 int conv_tc_launch(const void* x, const void* w_packed, const float* bias, void* out, void* out2,
                    const void* residual, const void* mask_src, const int64_t* dims, int nd, int cin, int cout,
                    int flags, cudaStream_t st);
-int wgrad_tc_launch(const void* x, const void* dpre, float* dw, const int64_t* dims, int nd, int cin, int cout,
-                    cudaStream_t st);
+int wgrad_tc_launch(const void* x, const void* dpre, float* dw, float* db, const int64_t* dims, int nd, int cin,
+                    int cout, cudaStream_t st);
 int fc_fwd(const float* z, const float* W, const float* bias, void* out, int B, int K, int N, int out_dtype,
            cudaStream_t st);
 int fc_bwd(const float* z, const void* dout, float* dW, float* db, int B, int K, int N, int dout_dtype,
@@ -153,9 +153,9 @@ int dfl_conv3x3_fwd(const void* x, const void* w_packed, const float* bias, void
                     int flags, void* stream) {
   return conv_tc_launch(x, w_packed, bias, out, out2, residual, mask_src, dims, ndim, cin, cout, flags, ST(stream));
 }
-int dfl_conv3x3_wgrad(const void* x, const void* dpre, float* dw, const int64_t* dims, int ndim, int cin, int cout,
-                      void* stream) {
-  return wgrad_tc_launch(x, dpre, dw, dims, ndim, cin, cout, ST(stream));
+int dfl_conv3x3_wgrad(const void* x, const void* dpre, float* dw, float* db, const int64_t* dims, int ndim, int cin,
+                      int cout, void* stream) {
+  return wgrad_tc_launch(x, dpre, dw, db, dims, ndim, cin, cout, ST(stream));
 }
 int dfl_bias_grad(const void* dpre, float* db, size_t npos, void* stream) {
   return bias_grad(dpre, db, npos, ST(stream));

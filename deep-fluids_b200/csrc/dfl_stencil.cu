@@ -46,7 +46,7 @@ constexpr int S3_TX = 32, S3_TY = 16;          // threads = halo'd tile columns
 constexpr int S3_OX = S3_TX - 5, S3_OY = S3_TY - 5;  // output columns per tile
 
 template <typename TP, typename TX_, typename TO, bool kWriteVel>
-__global__ void __launch_bounds__(S3_TX* S3_TY)
+__global__ void __launch_bounds__(S3_TX* S3_TY, 2)
 stencil3d_fused_kernel(const TP* __restrict__ pot, const TX_* __restrict__ xt, TO* __restrict__ dpot,
                        TO* __restrict__ vel, double* __restrict__ partials, StencilParams p) {
   __shared__ __align__(16) float sA[2][S3_TY][S3_TX][3];
@@ -85,18 +85,40 @@ stencil3d_fused_kernel(const TP* __restrict__ pot, const TX_* __restrict__ xt, T
   float x_prev[3] = {0, 0, 0}, x_cur[3] = {0, 0, 0}, x_new[3];
   float d_prev[3] = {0, 0, 0}, d_cur[3] = {0, 0, 0}, d_new[3];
   float facc_l1 = 0.f, facc_j = 0.f;  // <= zseg*12 terms per thread: fp32 is ample, fp64 only across threads
+  float sz_prev[3] = {0, 0, 0};       // wz0*sgn(dzp) of the previous plane == the backward z term of this plane
+
+  // software prefetch: A[t+1] and x[t] are requested one iteration before they are consumed, so the global-load
+  // latency overlaps the previous iteration's arithmetic and barrier
+  float a_pf[3] = {0, 0, 0}, x_pf[3] = {0, 0, 0};
+  {
+    const int t0 = zs - 2;
+    if (t0 >= 0 && t0 < D && in_xy) {
+      const TP* q = pot + (col + static_cast<size_t>(t0) * plane) * p.pot_cs;
+      a_pf[0] = ldf(q); a_pf[1] = ldf(q + 1); a_pf[2] = ldf(q + 2);
+    }
+    const int q0 = t0 - 1;
+    if (q0 >= 0 && q0 < D && in_xy) {
+      const TX_* xp = xt + (col + static_cast<size_t>(q0) * plane) * 3;
+      x_pf[0] = ldf(xp); x_pf[1] = ldf(xp + 1); x_pf[2] = ldf(xp + 2);
+    }
+  }
 
   for (int t = zs - 2; t <= ze + 2; ++t) {
     const int cur = t & 1, prv = cur ^ 1;
-    // ---- load A[t] (own column) ----
-    const bool zin = (t >= 0 && t < D);
-    if (zin && in_xy) {
-      const TP* q = pot + (col + static_cast<size_t>(t) * plane) * p.pot_cs;
-      a_nxt[0] = ldf(q);
-      a_nxt[1] = ldf(q + 1);
-      a_nxt[2] = ldf(q + 2);
-    } else {
-      a_nxt[0] = a_nxt[1] = a_nxt[2] = 0.f;
+    // ---- A[t], x[t-1] were prefetched; request A[t+1], x[t] now ----
+    a_nxt[0] = a_pf[0]; a_nxt[1] = a_pf[1]; a_nxt[2] = a_pf[2];
+    x_new[0] = x_pf[0]; x_new[1] = x_pf[1]; x_new[2] = x_pf[2];
+    a_pf[0] = a_pf[1] = a_pf[2] = 0.f;
+    x_pf[0] = x_pf[1] = x_pf[2] = 0.f;
+    if (in_xy && t + 1 <= ze + 2) {
+      if (t + 1 >= 0 && t + 1 < D) {
+        const TP* q = pot + (col + static_cast<size_t>(t + 1) * plane) * p.pot_cs;
+        a_pf[0] = ldf(q); a_pf[1] = ldf(q + 1); a_pf[2] = ldf(q + 2);
+      }
+      if (t >= 0 && t < D) {
+        const TX_* xp = xt + (col + static_cast<size_t>(t) * plane) * 3;
+        x_pf[0] = ldf(xp); x_pf[1] = ldf(xp + 1); x_pf[2] = ldf(xp + 2);
+      }
     }
     sA[cur][j][i][0] = a_nxt[0];
     sA[cur][j][i][1] = a_nxt[1];
@@ -107,10 +129,6 @@ stencil3d_fused_kernel(const TP* __restrict__ pot, const TX_* __restrict__ xt, T
       const int q = t - 1;
       const bool qin = (q >= 0 && q < D) && in_xy;
       if (qin) {
-        const TX_* xp = xt + (col + static_cast<size_t>(q) * plane) * 3;
-        x_new[0] = ldf(xp);
-        x_new[1] = ldf(xp + 1);
-        x_new[2] = ldf(xp + 2);
         // z differences (replicate last): q <= D-2 ? A[q+1]-A[q] : A[q]-A[q-1]
         const bool zl = (q <= D - 2);
         const float dudz = zl ? (a_nxt[0] - a_cur[0]) : (a_cur[0] - a_prev[0]);
@@ -145,7 +163,7 @@ stencil3d_fused_kernel(const TP* __restrict__ pot, const TX_* __restrict__ xt, T
       const bool qin = (q >= 0 && q < D) && in_xy;
       const float wxm = wgt(cx - 1, W), wx0 = wgt(cx, W);
       const float wym = wgt(cy - 1, H), wy0 = wgt(cy, H);
-      const float wzm = wgt(q - 1, D), wz0 = wgt(q, D);
+      const float wz0 = wgt(q, D);
       const bool count = out_col && q >= zs && q < ze;
 #pragma unroll
       for (int c = 0; c < 3; ++c) {
@@ -157,10 +175,11 @@ stencil3d_fused_kernel(const TP* __restrict__ pot, const TX_* __restrict__ xt, T
         const float dyp = (sG[prv][jp][i][c] - g0) - (sX[prv][jp][i][c] - x0);
         const float dym = (g0 - sG[prv][jm][i][c]) - (x0 - sX[prv][jm][i][c]);
         const float dzp = (g_new[c] - g0) - (x_new[c] - x0);
-        const float dzm = (g0 - g_prev[c]) - (x0 - x_prev[c]);
+        const float szp = wz0 * sgnf(dzp);      // the forward z term of plane q is the backward term of plane q+1
         float dg = p.c1 * sgnf(e) +
                    p.c2 * ((wxm * sgnf(dxm) - wx0 * sgnf(dxp)) + (wym * sgnf(dym) - wy0 * sgnf(dyp)) +
-                           (wzm * sgnf(dzm) - wz0 * sgnf(dzp)));
+                           (sz_prev[c] - szp));
+        sz_prev[c] = qin ? szp : 0.f;
         d_new[c] = qin ? dg : 0.f;
         if (count) {
           facc_l1 += fabsf(e);
@@ -462,10 +481,10 @@ static void stencil_plan(int nd, const int64_t* dims, StencilParams& p) {
     p.tiles_y = (p.H + S3_OY - 1) / S3_OY;
     // z segments: enough blocks for ~3 waves of 148 SMs x 2 blocks, but >= 16 planes per segment
     int cols = p.B * p.tiles_x * p.tiles_y;
-    int want = (148 * 2 * 3 + cols - 1) / cols;
+    int want = (148 * 2 * 2 + cols - 1) / cols;
     int nseg = want < 1 ? 1 : want;
     int zseg = (p.D + nseg - 1) / nseg;
-    if (zseg < 16) zseg = p.D < 16 ? p.D : 16;
+    if (zseg < 32) zseg = p.D < 32 ? p.D : 32;
     p.zseg = zseg;
     p.nseg = (p.D + zseg - 1) / zseg;
   } else {

@@ -22,7 +22,8 @@ constexpr int WG_OP_BYTES = WG_TILE_K * 128 * 2;      // 32 KB: 128 voxels x 128
 constexpr int WG_A_SLOTS = 4, WG_B_SLOTS = 2;
 constexpr int WG_THREADS = 192;
 constexpr int WG_MAX_TAPS = 4;
-constexpr int WG_SMEM_BYTES = (WG_A_SLOTS + WG_B_SLOTS) * WG_OP_BYTES + 1024 + 256;
+constexpr int WG_ONES_BYTES = 2048;   // 16 K-rows x 128 B of bf16 1.0: A operand of the bias-gradient MMA
+constexpr int WG_SMEM_BYTES = (WG_A_SLOTS + WG_B_SLOTS) * WG_OP_BYTES + WG_ONES_BYTES + 1024 + 256;
 
 struct WgradParams {
   int B, D, H, W;
@@ -31,6 +32,7 @@ struct WgradParams {
   int kd, kh, kw;
   int taps_per_group, ngroups, nslabs;
   float* dw;          // [taps][128][128] fp32 (TF layout: ..., Cin, Cout), accumulated into
+  float* db;          // [128] fp32 bias gradient (sum_p dP[p][co]), accumulated into; may be nullptr
 };
 
 __global__ void __launch_bounds__(WG_THREADS, 1)
@@ -39,7 +41,8 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sA = smem;
   uint8_t* sB = smem + WG_A_SLOTS * WG_OP_BYTES;
-  uint8_t* ctrl = sB + WG_B_SLOTS * WG_OP_BYTES;
+  uint8_t* sOnes = sB + WG_B_SLOTS * WG_OP_BYTES;
+  uint8_t* ctrl = sOnes + WG_ONES_BYTES;
   uint64_t* a_full = reinterpret_cast<uint64_t*>(ctrl);
   uint64_t* a_empty = a_full + WG_A_SLOTS;
   uint64_t* b_full = a_empty + WG_A_SLOTS;
@@ -55,6 +58,10 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
   // this CTA's slab of bricks: [t_begin, t_end)
   const int per = (p.ntiles + p.nslabs - 1) / p.nslabs;
   const int t_begin = slab * per, t_end = min(p.ntiles, t_begin + per);
+  // The last tap group has a free 128-column TMEM slot (27 = 6*4+3, 9 = 3*3): it also accumulates the bias gradient
+  // db[co] = sum_p dP[p][co] as one more GEMM, ones[M x K] (x) dP -- every row of that accumulator equals db.
+  const bool do_bias = (p.db != nullptr) && (group == p.ngroups - 1) && (gtaps < WG_MAX_TAPS);
+  for (int i = threadIdx.x; i < WG_ONES_BYTES / 4; i += WG_THREADS) reinterpret_cast<uint32_t*>(sOnes)[i] = 0x3F803F80u;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmX);
@@ -68,6 +75,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
     tmem_alloc(tmem_ptr, 512);
     tmem_relinquish();
   }
+  fence_proxy_async();     // the ones tile was written through the generic proxy
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -126,6 +134,13 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
             }
             umma_commit(&a_empty[s]);
           }
+          if (do_bias) {
+            const uint32_t so = smem_u32(sOnes);
+#pragma unroll
+            for (int k = 0; k < WG_TILE_K / 16; ++k)
+              umma_bf16(tmem_base + 3 * 128, umma_desc_sw128(so, 0, 1024), umma_desc_sw128(sb + k * 2048, WG_OP_BYTES / 2, 1024),
+                        idesc, (tile != t_begin || k != 0) ? 1u : 0u);
+          }
           umma_commit(&b_empty[sbs]);
         }
         umma_commit(acc_full);
@@ -144,6 +159,18 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
           tmem_ld_wait();
 #pragma unroll
           for (int k = 0; k < 32; ++k) atomicAdd(dst + c0 + k, __uint_as_float(rr[k]));
+        }
+      }
+      if (do_bias && quarter == 0) {      // row 0 of the bias accumulator (all rows are equal)
+#pragma unroll 1
+        for (int c0 = 0; c0 < 128; c0 += 32) {
+          uint32_t rr[32];
+          tmem_ld_32x32(tmem_base + 3 * 128 + c0, rr);
+          tmem_ld_wait();
+          if (lane == 0) {
+#pragma unroll
+            for (int k = 0; k < 32; ++k) atomicAdd(p.db + c0 + k, __uint_as_float(rr[k]));
+          }
         }
       }
     }
@@ -170,8 +197,8 @@ static void pick_brick_w(int D, int H, int W, int& bd, int& bh, int& bw) {
   }
 }
 
-int wgrad_tc_launch(const void* x, const void* dpre, float* dw, const int64_t* dims, int nd, int cin, int cout,
-                    cudaStream_t st) {
+int wgrad_tc_launch(const void* x, const void* dpre, float* dw, float* db, const int64_t* dims, int nd, int cin,
+                    int cout, cudaStream_t st) {
   DFL_REQUIRE(cin == 128 && cout == 128, "wgrad_tc: only Cin = Cout = 128 (got %d, %d)", cin, cout);
   DFL_REQUIRE(nd == 2 || nd == 3, "wgrad_tc: ndim must be 2 or 3");
   WgradParams p{};
@@ -192,6 +219,7 @@ int wgrad_tc_launch(const void* x, const void* dpre, float* dw, const int64_t* d
   p.ngroups = (ntaps + p.taps_per_group - 1) / p.taps_per_group;
   p.nslabs = std::max(1, std::min(p.ntiles, num_sms() / p.ngroups));
   p.dw = dw;
+  p.db = db;
 
   CUtensorMap tmX, tmP;
   const uint64_t gd[5] = {128, static_cast<uint64_t>(p.W), static_cast<uint64_t>(p.H), static_cast<uint64_t>(p.D),

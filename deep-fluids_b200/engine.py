@@ -77,7 +77,7 @@ class GeneratorEngine(object):
     """GeneratorBE / GeneratorBE3 (skip_concat=False) forward + backward on hand-written sm_100a kernels."""
 
     def __init__(self, batch, output_shape, z_dim=3, filters=128, num_conv=4, repeat=0, name="G", device=None,
-                 seed=123, init=None):
+                 seed=123, init=None, inference=False):
         assert filters == 128, "the tensor-core conv kernels are specialised for filters=128 (config.py:21 default)"
         self.device = device or torch.device("cuda", torch.cuda.current_device())
         self.B, self.name, self.filters, self.num_conv = int(batch), name, filters, int(num_conv)
@@ -125,18 +125,24 @@ class GeneratorEngine(object):
         self.repack()
         # ---- activations (bf16) and gradient scratch
         bf = dict(dtype=torch.bfloat16, device=self.device)
+        self.inference = bool(inference)
         self.x0, self.y = [], []
         for i in range(self.rep):
             shp = [self.B] + self.level_shape[i] + [filters]
             self.x0.append(torch.empty(shp, **bf))
-            self.y.append([torch.empty(shp, **bf) for _ in range(self.num_conv)])
+            if self.inference:     # forward only: two ping-pong buffers per level instead of one tensor per layer
+                pp = [torch.empty(shp, **bf) for _ in range(min(2, self.num_conv))]
+                self.y.append([pp[c % len(pp)] for c in range(self.num_conv)])
+            else:
+                self.y.append([torch.empty(shp, **bf) for _ in range(self.num_conv)])
         top = [self.B] + self.level_shape[-1] + [filters]
         self.s = torch.empty(top, **bf)
         self.pot = torch.empty([self.B] + self.spatial + [self.cout], dtype=torch.float32, device=self.device)
         # gradient scratch is sized for the finest level and re-viewed per level
-        self._gbuf = [torch.empty(top, **bf) for _ in range(4)]
+        self._gbuf = [] if self.inference else [torch.empty(top, **bf) for _ in range(4)]
         self.z = None
         self.adam_t = 0
+        self.debug = None
 
     # ------------------------------------------------------------------ helpers
     def _gview(self, k, level):
@@ -156,8 +162,10 @@ class GeneratorEngine(object):
         P = self.params
         self.z = z.contiguous().float()
         assert self.z.shape == (self.B, self.z_dim)
-        K.fc_fwd(self.z, P.p(self.name + "/0_fc/weights"), P.p(self.name + "/0_fc/biases"),
-                 out=self.x0[0].view(self.B, -1))
+        x0v = self.x0[0].view(self.B, -1)
+        for b0 in range(0, self.B, 64):      # the FC kernel keeps <= 64 parameter rows in smem
+            K.fc_fwd(self.z[b0:b0 + 64], P.p(self.name + "/0_fc/weights"), P.p(self.name + "/0_fc/biases"),
+                     out=x0v[b0:b0 + 64])
         for i in range(self.rep):
             cur = self.x0[i]
             for c in range(self.num_conv):
@@ -178,6 +186,8 @@ class GeneratorEngine(object):
     # ------------------------------------------------------------------ backward (TF autodiff of the above)
     def backward(self, dpot):
         """dpot: fp32 gradient w.r.t. the generator output.  Accumulates into params.grad (call zero_grad first)."""
+        assert not self.inference, "inference engine has no backward pass"
+        assert self.B <= 64, "fc_bwd keeps <= 64 parameter rows in smem"
         P = self.params
         nc = self.num_conv
         top = self.rep - 1
@@ -191,8 +201,9 @@ class GeneratorEngine(object):
             for c in range(nc - 1, -1, -1):
                 cn = self.conv_names[i][c]
                 xin = self.y[i][c - 1] if c > 0 else self.x0[i]
-                K.conv3x3_wgrad(xin, dpre, P.g(cn + "/weights"))
-                K.bias_grad(dpre, P.g(cn + "/biases"))
+                if self.debug is not None:        # parity debugging: dL/d(pre-activation) of every layer
+                    self.debug[cn] = dpre.clone()
+                K.conv3x3_wgrad(xin, dpre, P.g(cn + "/weights"), P.g(cn + "/biases"))
                 if c > 0:     # dL/d(pre-activation of layer c-1) = dgrad * lrelu'(y[c-1])
                     K.conv3x3(dpre, self.wd[cn], None, out=other, mask_src=self.y[i][c - 1])
                     dpre, other = other, dpre

@@ -149,11 +149,12 @@ def conv3x3(x, w_packed, bias=None, out=None, out2=None, residual=None, mask_src
         _p(x), _p(w_packed), _p(bias), _p(out), _p(out2), _p(residual), _p(mask_src), d, nd, cin, cout, flags, _st())))
 
 
-def conv3x3_wgrad(x, dpre, dw):
+def conv3x3_wgrad(x, dpre, dw, db=None):
+    """dw += x^T (x) dpre per tap; db += column sums of dpre (optional, free in the kernel)"""
     d, nd = _spatial(x)
     flops = 2.0 * (x.numel() // x.shape[-1]) * x.shape[-1] * dpre.shape[-1] * (3 ** nd)
     PROF.timed("wgrad_tc", flops, lambda: check(cabi.lib().dfl_conv3x3_wgrad(
-        _p(x), _p(dpre), _p(dw), d, nd, x.shape[-1], dpre.shape[-1], _st())))
+        _p(x), _p(dpre), _p(dw), _p(db), d, nd, x.shape[-1], dpre.shape[-1], _st())))
 
 
 def bias_grad(dpre, db):

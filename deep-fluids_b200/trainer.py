@@ -227,17 +227,54 @@ class Trainer(object):
     def train_ae(self):
         raise NotImplementedError("arch 'ae' is the next SURVEY 8 row")
 
-    # ------------------------------------------------------------------ generator-only use (trainer.py:295-304)
+    # ------------------------------------------------------------------ inference (trainer.py:295-354, 750-771)
     def build_test_model(self):
-        self.z = None
+        """`reuse=True` generator on z:[test_b_num, c_num] (trainer.py:295-304): a forward-only engine sharing the
+        trained variables.  The 3D trainer uses the 3D curl here (the reference's trainer3.py:188 applies the 2D curl
+        to the 3-channel potential -- a bug that is not reproduced)."""
+        self.test_engine = GeneratorEngine(self.test_b_num, self.output_shape, z_dim=self.c_num, filters=self.filters,
+                                           num_conv=self.num_conv, repeat=self.repeat, name="G", device=self.device,
+                                           init=self.engine.params.state_dict(), inference=True)
 
     def generate_velocity(self, z):
-        """G_ = curl(G_s(z)) for a batch of parameters z [b_num, c_num] (the inference half of trainer.py:138-140)."""
-        pot = self.engine.forward(z)
-        return K.curl_fwd(pot)
+        """G_ = curl(G_s(z)) for parameters z [n, c_num], n a multiple of test_b_num or <= it (sess.run(self.G_, {z}))."""
+        if not hasattr(self, "test_engine"):
+            self.build_test_model()
+        z = torch.as_tensor(z, dtype=torch.float32, device=self.device)
+        outs = []
+        for b0 in range(0, z.shape[0], self.test_b_num):
+            zb = z[b0:b0 + self.test_b_num]
+            n = zb.shape[0]
+            if n < self.test_b_num:
+                zb = torch.cat([zb, zb.new_zeros(self.test_b_num - n, zb.shape[1])])
+            pot = self.test_engine.forward(zb)
+            outs.append(K.curl_fwd(pot)[:n].clone())
+        return torch.cat(outs)
 
     def test(self):
-        raise NotImplementedError("test()/generate() dumps are SURVEY 8(f) row N1")
+        if 'ae' in self.arch:
+            raise NotImplementedError("test_ae is part of the AE row (next)")
+        self.test_()
+
+    def test_(self):
+        """Sweep the last parameter at fixed p1,p2 = 10,2, de-normalise and dump `<model_dir>/10_2/%d.npz`
+        (trainer.py:314-354)."""
+        self.build_test_model()
+        p1, p2 = 10, 2
+        y1, y2, y3 = (int(v) for v in self.batch_manager.y_num[:3])
+        assert y3 % self.test_b_num == 0
+        c1 = p1 / float(y1 - 1) * 2 - 1
+        c2 = p2 / float(y2 - 1) * 2 - 1
+        z_c = np.zeros((y3, self.c_num), dtype=np.float32)
+        z_c[:, 0], z_c[:, 1], z_c[:, -1] = c1, c2, np.linspace(-1, 1, num=y3)
+        G = self.generate_velocity(z_c)
+        G, _ = self.batch_manager.denorm(x=G)
+        out_dir = os.path.join(self.model_dir, '%d_%d' % (p1, p2))
+        os.makedirs(out_dir, exist_ok=True)
+        G = G.cpu().numpy()
+        for i, G_ in enumerate(G):
+            np.savez_compressed(os.path.join(out_dir, '%d.npz' % i), x=G_)
+        return out_dir
 
     # ------------------------------------------------------------------ checkpoint (state_dict with TF variable names)
     def save(self, path):

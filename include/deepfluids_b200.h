@@ -90,9 +90,10 @@ int dfl_pack_conv_weights(const float* w, void* w_fwd, void* w_dgrad, int taps, 
 int dfl_conv3x3_fwd(const void* x, const void* w_packed, const float* bias, void* out, void* out2,
                     const void* residual, const void* mask_src, const int64_t* dims, int ndim, int cin, int cout,
                     int flags, void* stream);
-/* dW[tap][ci][co] += sum_p x[p+tap-1][ci] * dpre[p][co]   (fp32, TF layout, accumulated: zero it first). */
-int dfl_conv3x3_wgrad(const void* x, const void* dpre, float* dw, const int64_t* dims, int ndim, int cin, int cout,
-                      void* stream);
+/* dW[tap][ci][co] += sum_p x[p+tap-1][ci] * dpre[p][co]   (fp32, TF layout, accumulated: zero it first);
+ * if db != NULL also db[co] += sum_p dpre[p][co] (BiasAddGrad), computed as one more GEMM in a free TMEM slot. */
+int dfl_conv3x3_wgrad(const void* x, const void* dpre, float* dw, float* db, const int64_t* dims, int ndim, int cin,
+                      int cout, void* stream);
 /* db[c] += sum_p dpre[p][c]   (dpre bf16 [npos][128]) */
 int dfl_bias_grad(const void* dpre, float* db, size_t npos, void* stream);
 

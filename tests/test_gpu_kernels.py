@@ -212,10 +212,12 @@ def test_conv_dgrad_and_wgrad_vs_autograd(shape, nd):
     # wgrad (fp32 accumulate in TMEM, fp32 atomics) + bias grad
     dw = torch.zeros(w.shape, dtype=torch.float32, device=dev())
     db = torch.zeros(128, dtype=torch.float32, device=dev())
-    K.conv3x3_wgrad(x.to(dev()), dy.to(dev()), dw)
-    K.bias_grad(dy.to(dev()), db)
+    db2 = torch.zeros(128, dtype=torch.float32, device=dev())
+    K.conv3x3_wgrad(x.to(dev()), dy.to(dev()), dw, db2)       # bias gradient fused into a free TMEM slot
+    K.bias_grad(dy.to(dev()), db)                             # standalone column-sum kernel
     assert rel_l2(dw, gw) <= 1e-4
     assert rel_l2(db, gb) <= 1e-4
+    assert rel_l2(db2, gb) <= 1e-4
 
 
 def test_conv_linearity_full_size():

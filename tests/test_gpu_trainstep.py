@@ -117,3 +117,26 @@ def test_trainer_api_runs_and_loss_decreases():
             first = tr.losses()[0]
     last = tr.losses()[0]
     assert np.isfinite(last) and last < first, (first, last)
+
+
+def test_inference_path_matches_training_forward(tmp_path):
+    """build_test_model / generate_velocity / test_ dumps (trainer.py:295-354) -- the forward-only engine
+    must reproduce the training engine's potential -> curl bit for bit, for a batch larger than the FC kernel's 64 rows."""
+    from deepfluids_b200 import config as C, kernels as K
+    from deepfluids_b200.data import BatchManager
+    from deepfluids_b200.trainer import Trainer
+    cfg, _ = C.get_config(["--synthetic=true", "--res_x=24", "--res_y=32", "--batch_size=4", "--num_conv=3",
+                           "--test_batch_size=100", "--max_step=10"])
+    cfg.model_dir = str(tmp_path)
+    bm = BatchManager(cfg, pool=1)
+    bm.y_num = [21, 5, 200]
+    tr = Trainer(cfg, bm)
+    tr.train_step()
+    x, y = bm.batch()
+    vel_train = K.curl_fwd(tr.engine.forward(y)).clone()
+    vel_test = tr.generate_velocity(y)
+    assert torch.equal(vel_train, vel_test)
+    out_dir = tr.test_()
+    d = np.load(out_dir + "/199.npz")["x"]
+    assert d.shape == (32, 24, 2) and np.isfinite(d).all()
+    assert float(K.divergence(torch.from_numpy(d[None]).cuda()).abs().max()) <= 1e-5
