@@ -106,3 +106,44 @@ def synthetic_batch(batch, spatial, seed=123, z_dim=3, dtype=torch.float32, smoo
     x = R.curl(pot) if nd == 2 else R.curl3(pot)
     x = x / x.abs().max()
     return x.to(dtype), y.to(dtype)
+
+
+def teacher_forced_backward(z, var, acts, dpot, num_conv=4, name="G", operand_round=None):
+    """Backward pass of the generator evaluated layer by layer with torch autograd, where every layer's INPUT is the
+    activation tensor the device path actually stored (`acts` = {"x0": [per level], "y": [[per conv] per level],
+    "s": top-level residual sum}, fp32 CPU copies).  Because the leaky-ReLU masks are then computed from the same
+    forward state as on the device, this isolates the accuracy of the backward kernels (dgrad / wgrad / bias-grad /
+    pooling / FC-backward) from the sign flips that bf16 activation noise causes in a free-running comparison.
+    `operand_round` (e.g. ref_model.bf16_round_ste) models the bf16 operand copy of the conv weights."""
+    rnd = operand_round if operand_round is not None else (lambda t: t)
+    nd = acts["s"].dim() - 2
+    rep = len(acts["x0"])
+    grads = OrderedDict()
+    n_last = rep * num_conv + 1
+
+    def layer_grads(xin, wname, act, gout):
+        xin = xin.detach().clone().requires_grad_(True)
+        w = var[wname + "/weights"].detach().clone().requires_grad_(True)
+        b = var[wname + "/biases"].detach().clone().requires_grad_(True)
+        out = R.conv_nd(xin, rnd(w), b, 1, act)
+        gx, gw, gb = torch.autograd.grad(out, [xin, w, b], gout)
+        grads[wname + "/weights"], grads[wname + "/biases"] = gw, gb
+        return gx
+
+    g = layer_grads(acts["s"], "%s/%d_conv" % (name, n_last), None, dpot)      # ds
+    for i in range(rep - 1, -1, -1):
+        ds = g
+        gy = ds
+        for c in range(num_conv - 1, -1, -1):
+            xin = acts["y"][i][c - 1] if c > 0 else acts["x0"][i]
+            gy = layer_grads(xin, "%s/%d_conv" % (name, i * num_conv + c + 1), R.lrelu, gy)
+        gx0 = gy + ds
+        if i > 0:      # adjoint of nearest x2 upsampling: sum over the children
+            u = torch.zeros_like(acts["x0"][i - 1]).requires_grad_(True)
+            up = R.upscale(u, 2) if nd == 2 else R.upscale3(u, 2)
+            (g,) = torch.autograd.grad(up, u, gx0)
+        else:
+            flat = gx0.reshape(gx0.shape[0], -1)
+            grads["%s/0_fc/weights" % name] = z.t() @ flat
+            grads["%s/0_fc/biases" % name] = flat.sum(0)
+    return grads

@@ -40,15 +40,17 @@ def test_generator_fwd_bwd_vs_oracle(spatial, num_conv, B):
     assert abs(loss3[0].item() - loss.item()) <= 1e-2 * abs(loss.item())
     # divergence-free output (north_star: <= 1e-5)
     assert float(K.divergence(vel).abs().max()) <= 1e-5
-    # (1) backward kernels alone: oracle autograd driven by the SAME upstream gradient dL/dpot the GPU produced, on
-    #     the oracle run with bf16 *storage* of activations / operand weights (fp32 math; straight-through rounding)
-    #     so the leaky-ReLU masks agree with the device -- isolates dgrad/wgrad/pool/FC-bwd accuracy from the sign
-    #     flips of the non-smooth ops (L1 loss, lrelu): rel-L2 <= 3e-2 on every gradient tensor
-    leaves = OrderedDict((k, v.clone().requires_grad_(True)) for k, v in var.items())
-    pot_o = M.generator_forward(y, leaves, spatial + [cout], num_conv=num_conv, store=M.bf16_round_ste)
-    e_pot = rel_l2(pot, pot_o.detach())
-    gs = torch.autograd.grad(pot_o, list(leaves.values()), dpot.cpu())
-    errs = OrderedDict((k, rel_l2(eng.params.g(k), gref)) for k, gref in zip(leaves, gs))
+    # (1) backward kernels alone ("teacher forced"): the oracle back-propagates the SAME upstream gradient dL/dpot layer
+    #     by layer through torch autograd, each layer fed with the activation the device actually stored, so the
+    #     leaky-ReLU masks are identical.  (A free-running comparison cannot be tight: two bf16 pipelines disagree on
+    #     ~1e-3 of the lrelu signs, and every flipped sign changes that element's gradient by 5x -- measured with
+    #     tools/chain_debug.py: 3-7 % rel-L2 per level, with NO kernel error.)   Bound: rel-L2 <= 2e-2.
+    acts = {"x0": [t.float().cpu() for t in eng.x0], "y": [[t.float().cpu() for t in row] for row in eng.y],
+            "s": eng.s.float().cpu()}
+    tf_grads = T.teacher_forced_backward(y, var, acts, dpot.cpu(), num_conv=num_conv, operand_round=M.bf16_round_ste)
+    pot_o = M.generator_forward(y, var, spatial + [cout], num_conv=num_conv, store=M.bf16_round_ste)
+    e_pot = rel_l2(pot, pot_o)
+    errs = OrderedDict((k, rel_l2(eng.params.g(k), tf_grads[k])) for k in var)
     # the loss is invariant to a constant shift of the potential (curl kills it), so d loss / d (last-layer bias) =
     # sum(dL/dpot) is exactly 0 in exact arithmetic: both sides are rounding noise -> compare it absolutely instead
     last_b = list(var.keys())[-1]
@@ -56,8 +58,8 @@ def test_generator_fwd_bwd_vs_oracle(spatial, num_conv, B):
     scale_b = float(dpot.abs().sum())
     assert float(eng.params.g(last_b).abs().max()) <= 1e-3 * scale_b and float(grads[last_b].abs().max()) <= 1e-3 * scale_b
     del errs[last_b]
-    # (2) end to end vs the pure-fp32 oracle (includes sign(.) of the L1 losses and lrelu masks, which flip where the
-    #     argument is below the bf16 noise): rel-L2 <= 1e-1
+    # (2) free-running end to end vs the pure-fp32 oracle (includes the sign flips of the L1 losses and lrelu masks
+    #     under bf16 noise, see above): rel-L2 <= 2e-1 (weights)
     errs_e2e = OrderedDict((k, rel_l2(eng.params.g(k), grads[k])) for k in var if k != last_b)
     # weight gradients are well-conditioned sums; bias gradients are sums over ALL voxels of a field that is a discrete
     # derivative (curl / Jacobian adjoints), i.e. they cancel almost completely, so their *relative* error is dominated
@@ -70,8 +72,8 @@ def test_generator_fwd_bwd_vs_oracle(spatial, num_conv, B):
         (e_pot,) + mx(errs, "weights") + mx(errs, "biases") + mx(errs_e2e, "weights") + mx(errs_e2e, "biases"))
     print(report)
     assert e_pot <= 1e-2, report
-    assert mx(errs, "weights")[0] <= 3e-2 and mx(errs, "biases")[0] <= 1.5e-1, report
-    assert mx(errs_e2e, "weights")[0] <= 1e-1 and mx(errs_e2e, "biases")[0] <= 2e-1, report
+    assert mx(errs, "weights")[0] <= 2e-2 and mx(errs, "biases")[0] <= 5e-2, report
+    assert mx(errs_e2e, "weights")[0] <= 2e-1 and mx(errs_e2e, "biases")[0] <= 3e-1, report
 
 
 def test_train_steps_match_oracle_adam():
