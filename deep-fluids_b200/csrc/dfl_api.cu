@@ -31,7 +31,8 @@ int check_cuda(cudaError_t e, const char* what) {
 int num_sms() { return g_num_sms; }
 
 int encode_tensor_map(CUtensorMap* out, CUtensorMapDataType dt, int rank, const void* gaddr, const uint64_t* dims,
-                      const uint64_t* strides_bytes, const uint32_t* box, CUtensorMapSwizzle sw) {
+                      const uint64_t* strides_bytes, const uint32_t* box, CUtensorMapSwizzle sw,
+                      const uint32_t* elem_strides) {
   if (!g_encode) {
     set_last_error("dfl_init() was not called (TMA driver entry point unresolved)");
     return DFL_ERR_INIT;
@@ -39,7 +40,7 @@ int encode_tensor_map(CUtensorMap* out, CUtensorMapDataType dt, int rank, const 
   cuuint32_t estr[5] = {1, 1, 1, 1, 1};
   cuuint64_t gd[5], gs[4];
   cuuint32_t bx[5];
-  for (int i = 0; i < rank; ++i) { gd[i] = dims[i]; bx[i] = box[i]; }
+  for (int i = 0; i < rank; ++i) { gd[i] = dims[i]; bx[i] = box[i]; if (elem_strides) estr[i] = elem_strides[i]; }
   for (int i = 0; i + 1 < rank; ++i) gs[i] = strides_bytes[i];
   CUresult r = g_encode(out, dt, static_cast<cuuint32_t>(rank), const_cast<void*>(gaddr), gd, gs, bx, estr,
                         CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -63,20 +64,29 @@ int fwd_stencils(int op, int nd, const int64_t* dims, const void* in, int in_cs,
 int conv_tc_launch(const void* x, const void* w_packed, const float* bias, void* out, void* out2,
                    const void* residual, const void* mask_src, const int64_t* dims, int nd, int cin, int cout,
                    int flags, cudaStream_t st);
-int wgrad_tc_launch(const void* x, const void* dpre, float* dw, float* db, const int64_t* dims, int nd, int cin,
-                    int cout, cudaStream_t st);
+int wgrad_tc_launch(const void* x, const void* dpre, float* dw, float* db, const int64_t* x_dims, const int64_t* dims,
+                    int nd, int in_stride, int pad, int dw_tap_stride, int dw_row_stride, cudaStream_t st);
+int conv_tap_launch(const void* x, const void* w_packed, const float* bias, void* out, void* out2,
+                    const void* residual, const void* mask_src, const int64_t* in_dims, const int64_t* tile_dims,
+                    const int64_t* out_dims, int nd, int cin, int in_stride, int ntap, const int32_t* taps,
+                    int out_stride, const int32_t* out_off, int64_t w_ld, int flags, cudaStream_t st);
+int pad_cast(const float* in, void* out, size_t n, int cin, cudaStream_t st);
+int add_mask(const void* a, const void* b, const void* y, void* out, size_t n, cudaStream_t st);
+int enc_fc_fwd(const void* flat, const float* W, const float* bias, float* z, int B, int V, int nblk, int Z, cudaStream_t st);
+int enc_fc_bwd(const void* flat, const float* W, const float* dz, float* dW, float* db, void* dflat, int B, int V,
+               int nblk, int Z, cudaStream_t st);
+int fc_dz(const void* dout, const float* W, float* dz, int B, int K, int N, int dout_dtype, int accumulate, cudaStream_t st);
+int ae_loss_p(const float* z, const float* y, float* dz, float* loss_p, int B, int Z, int P, float scale, cudaStream_t st);
 int fc_fwd(const float* z, const float* W, const float* bias, void* out, int B, int K, int N, int out_dtype,
            cudaStream_t st);
 int fc_bwd(const float* z, const void* dout, float* dW, float* db, int B, int K, int N, int dout_dtype,
            cudaStream_t st);
-int lastconv(int op, const void* a, const void* b, const void* c, void* o0, void* o1, const int64_t* dims, int nd,
-             int cout, cudaStream_t st);
 int lastconv_bwd_tc(const void* s, const float* dout, const float* w, const void* mask_src, void* ds, void* ds_masked,
                     float* dw, float* db, const int64_t* dims, int nd, int cout, cudaStream_t st);
 int pool_mask(const void* g, const void* mask_src, void* ds, void* dmasked, const int64_t* cdims, int nd,
               cudaStream_t st);
 int bias_grad(const void* d, float* db, size_t npos, cudaStream_t st);
-int pack_conv_weights(const float* W, void* wf, void* wd, int taps, int cin, int cout, cudaStream_t st);
+int pack_conv_weights(const float* W, void* wf, void* wd, int taps, int cin, int cout, int cin_ld, cudaStream_t st);
 int adam_step(float* p, const float* g, float* m, float* v, size_t n, float lr_t, const float* lr_t_dev, float b1,
               float b2, float eps, float grad_scale, cudaStream_t st);
 int cast_f32_bf16(const float* a, void* o, size_t n, cudaStream_t st);
@@ -146,7 +156,11 @@ int dfl_fc_bwd(const float* z, const void* dout, float* dW, float* db, int B, in
   return fc_bwd(z, dout, dW, db, B, K, N, dout_dtype, ST(stream));
 }
 int dfl_pack_conv_weights(const float* w, void* w_fwd, void* w_dgrad, int taps, int cin, int cout, void* stream) {
-  return pack_conv_weights(w, w_fwd, w_dgrad, taps, cin, cout, ST(stream));
+  return pack_conv_weights(w, w_fwd, w_dgrad, taps, cin, cout, cin, ST(stream));
+}
+int dfl_pack_conv_weights_ex(const float* w, void* w_fwd, void* w_dgrad, int taps, int cin, int cout, int cin_ld,
+                             void* stream) {
+  return pack_conv_weights(w, w_fwd, w_dgrad, taps, cin, cout, cin_ld, ST(stream));
 }
 int dfl_conv3x3_fwd(const void* x, const void* w_packed, const float* bias, void* out, void* out2,
                     const void* residual, const void* mask_src, const int64_t* dims, int ndim, int cin, int cout,
@@ -155,23 +169,42 @@ int dfl_conv3x3_fwd(const void* x, const void* w_packed, const float* bias, void
 }
 int dfl_conv3x3_wgrad(const void* x, const void* dpre, float* dw, float* db, const int64_t* dims, int ndim, int cin,
                       int cout, void* stream) {
-  return wgrad_tc_launch(x, dpre, dw, db, dims, ndim, cin, cout, ST(stream));
+  DFL_REQUIRE(cin == 128 && cout == 128, "conv3x3_wgrad: Cin = Cout = 128 only (use dfl_conv_wgrad_ex for blocks)");
+  return wgrad_tc_launch(x, dpre, dw, db, dims, dims, ndim, 1, 1, 128 * 128, 128, ST(stream));
+}
+int dfl_conv_wgrad_ex(const void* x, const void* dpre, float* dw, float* db, const int64_t* x_dims, const int64_t* dims,
+                      int ndim, int in_stride, int pad, int dw_tap_stride, int dw_row_stride, void* stream) {
+  return wgrad_tc_launch(x, dpre, dw, db, x_dims, dims, ndim, in_stride, pad, dw_tap_stride, dw_row_stride, ST(stream));
+}
+int dfl_conv_taps(const void* x, const void* w_packed, const float* bias, void* out, void* out2, const void* residual,
+                  const void* mask_src, const int64_t* in_dims, const int64_t* tile_dims, const int64_t* out_dims, int ndim,
+                  int cin, int in_stride, int ntap, const int32_t* taps, int out_stride, const int32_t* out_off,
+                  int64_t w_ld, int flags, void* stream) {
+  return conv_tap_launch(x, w_packed, bias, out, out2, residual, mask_src, in_dims, tile_dims, out_dims, ndim, cin,
+                         in_stride, ntap, taps, out_stride, out_off, w_ld, flags, ST(stream));
+}
+int dfl_pad_cast(const float* in, void* out, size_t n, int cin, void* stream) { return pad_cast(in, out, n, cin, ST(stream)); }
+int dfl_add_mask(const void* a, const void* b, const void* y, void* out, size_t n, void* stream) {
+  return add_mask(a, b, y, out, n, ST(stream));
+}
+int dfl_enc_fc_fwd(const void* flat, const float* W, const float* bias, float* z, int B, int V, int nblk, int Z,
+                   void* stream) {
+  return enc_fc_fwd(flat, W, bias, z, B, V, nblk, Z, ST(stream));
+}
+int dfl_enc_fc_bwd(const void* flat, const float* W, const float* dz, float* dW, float* db, void* dflat, int B, int V,
+                   int nblk, int Z, void* stream) {
+  return enc_fc_bwd(flat, W, dz, dW, db, dflat, B, V, nblk, Z, ST(stream));
+}
+int dfl_fc_dz(const void* dout, const float* W, float* dz, int B, int K, int N, int dout_dtype, int accumulate,
+              void* stream) {
+  return fc_dz(dout, W, dz, B, K, N, dout_dtype, accumulate, ST(stream));
+}
+int dfl_ae_loss_p(const float* z, const float* y, float* dz, float* loss_p, int B, int Z, int P, float scale,
+                  void* stream) {
+  return ae_loss_p(z, y, dz, loss_p, B, Z, P, scale, ST(stream));
 }
 int dfl_bias_grad(const void* dpre, float* db, size_t npos, void* stream) {
   return bias_grad(dpre, db, npos, ST(stream));
-}
-int dfl_lastconv_fwd(const void* x, const float* w, const float* bias, float* out, const int64_t* dims, int ndim,
-                     int cout, void* stream) {
-  return lastconv(0, x, w, bias, out, nullptr, dims, ndim, cout, ST(stream));
-}
-int dfl_lastconv_dgrad(const float* dout, const float* w, const void* mask_src, void* dx, void* dx_masked,
-                       const int64_t* dims, int ndim, int cout, void* stream) {
-  DFL_REQUIRE(!(dx_masked && !mask_src), "lastconv_dgrad: dx_masked requested without mask_src");
-  return lastconv(1, dout, w, mask_src, dx, dx_masked, dims, ndim, cout, ST(stream));
-}
-int dfl_lastconv_wgrad(const void* x, const float* dout, float* dw, float* db, const int64_t* dims, int ndim,
-                       int cout, void* stream) {
-  return lastconv(2, x, dout, nullptr, dw, db, dims, ndim, cout, ST(stream));
 }
 int dfl_lastconv_bwd(const void* s, const float* dout, const float* w, const void* mask_src, void* ds, void* ds_masked,
                      float* dw, float* db, const int64_t* dims, int ndim, int cout, void* stream) {

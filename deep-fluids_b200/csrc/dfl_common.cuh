@@ -197,6 +197,7 @@ __host__ __device__ constexpr uint32_t umma_idesc_bf16(int M, int N, int a_mn_ma
 // host: TMA tensor-map creation through the driver entry point (no libcuda link dependency)
 // ------------------------------------------------------------------------------------------
 int encode_tensor_map(CUtensorMap* out, CUtensorMapDataType dt, int rank, const void* gaddr, const uint64_t* dims,
-                      const uint64_t* strides_bytes /* rank-1 entries */, const uint32_t* box, CUtensorMapSwizzle sw);
+                      const uint64_t* strides_bytes /* rank-1 entries */, const uint32_t* box, CUtensorMapSwizzle sw,
+                      const uint32_t* elem_strides = nullptr /* traversal strides, default 1 */);
 
 }  // namespace dfl

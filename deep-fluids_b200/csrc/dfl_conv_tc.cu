@@ -44,7 +44,8 @@ constexpr int CT_STAGE_BYTES = CT_A_BYTES + CT_B_BYTES;
 constexpr int CT_THREADS = 192;
 constexpr int CT_SMEM_BYTES = CT_STAGES * CT_STAGE_BYTES + 1024 /*align slack*/ + 1024 /*barriers, bias*/;
 
-enum : int { CF_LRELU = 1, CF_OUT2_UPSAMPLE = 2 };
+enum : int { CF_LRELU = 1, CF_OUT2_UPSAMPLE = 2, CF_MASK_AFTER_RESIDUAL = 4 };
+constexpr int CT_MAX_TAPS = 27;
 
 struct ConvTcParams {
   int B, D, H, W;
@@ -60,6 +61,14 @@ struct ConvTcParams {
   __nv_bfloat16* out2;        // [B,D,H,W,128] or upsampled [B,(2D),2H,2W,128] or nullptr
   float* out_f32;             // kN = 16 variant: fp32 [B,D,H,W,cout_small]
   int cout_small;
+  // output tensor geometry (== B,D,H,W of the tile domain unless the generic tap kernel maps positions)
+  int oD, oH, oW;
+  // ---- generic per-tap kernel only (strided / transposed-strided convolutions, explicit tap lists) ----
+  int in_stride;              // A box origin = in_stride * tile origin + tap offset
+  int out_stride, orz, ory, orx;   // output voxel = out_stride * tile voxel + (orz, ory, orx)
+  int ntap;
+  int tap_dz[CT_MAX_TAPS], tap_dy[CT_MAX_TAPS], tap_dx[CT_MAX_TAPS];   // input-coordinate offsets
+  int tap_col[CT_MAX_TAPS];   // weight K-column (elements) of the tap's first 64-channel slice
 };
 
 __device__ __forceinline__ void unpack_bf16x8(const uint4& q, float (&f)[8]) {
@@ -75,10 +84,20 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
   return *reinterpret_cast<uint32_t*>(&h);
 }
 
+// The shared epilogue (defined below) converts one accumulator row to bf16 outputs.
+__device__ __forceinline__ void conv_epilogue_row(const ConvTcParams& p, uint32_t taddr, bool valid, int b, int z,
+                                                  int y, int x, const float* s_bias);
+
+// =============================================================================================
+// Generic per-tap kernel (one TMA box per (tap, 64-channel slice); 6 x 32 KB stages).  Used where the tap-window
+// kernel does not apply: stride-2 convolutions (TMA element strides pick every 2nd voxel), their data gradient
+// (one launch per output parity class with that class's tap subset, outputs written to the strided positions) and
+// any explicit tap list.  Inputs wider than 128 channels are stored as channel blocks [nblk*B, D, H, W, 128]:
+// 64-channel slice c lives in block c>>1, i.e. at batch coordinate b + (c>>1)*B.
+// =============================================================================================
 __global__ void __launch_bounds__(CT_THREADS, 1)
-conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, ConvTcParams p) {
+conv_tap_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, ConvTcParams p) {
   extern __shared__ uint8_t smem_raw[];
-  // 1024-byte alignment required by the 128B swizzle atoms
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* ctrl = smem + CT_STAGES * CT_STAGE_BYTES;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(ctrl);            // [CT_STAGES]
@@ -89,8 +108,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   float* s_bias = reinterpret_cast<float*>(ctrl + 256);              // [128]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int ntaps = p.kd * p.kh * p.kw;
-  const int kblocks = ntaps * p.cin_chunks;
+  const int kblocks = p.ntap * p.cin_chunks;
 
   if (threadIdx.x < CT_BLOCK_N) s_bias[threadIdx.x] = p.bias ? p.bias[threadIdx.x] : 0.f;
   if (warp == 0 && lane == 0) {
@@ -116,7 +134,6 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const uint32_t tmem_base = *tmem_ptr;
 
   if (warp == 0) {
-    // ================================ TMA producer ================================
     if (lane == 0) {
       uint32_t it = 0;
       for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
@@ -125,23 +142,19 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int y0 = (r % p.ty) * p.bh; r /= p.ty;
         const int z0 = (r % p.tz) * p.bd; r /= p.tz;
         const int b = r;
-        int kb = 0;
-        for (int dz = 0; dz < p.kd; ++dz)
-          for (int dy = 0; dy < p.kh; ++dy)
-            for (int dx = 0; dx < p.kw; ++dx)
-              for (int c = 0; c < p.cin_chunks; ++c, ++kb, ++it) {
-                const uint32_t s = it % CT_STAGES, ph = (it / CT_STAGES) & 1;
-                mbar_wait(&empty_bar[s], ph ^ 1);
-                mbar_expect_tx(&full_bar[s], CT_STAGE_BYTES);
-                uint8_t* sa = smem + s * CT_STAGE_BYTES;
-                tma_load_5d(sa, &tmA, &full_bar[s], c * CT_BLOCK_K, x0 + dx - (p.kw >> 1), y0 + dy - (p.kh >> 1),
-                            z0 + dz - (p.kd >> 1), b);
-                tma_load_2d(sa + CT_A_BYTES, &tmB, &full_bar[s], kb * CT_BLOCK_K, 0);
-              }
+        for (int t = 0; t < p.ntap; ++t)
+          for (int c = 0; c < p.cin_chunks; ++c, ++it) {
+            const uint32_t s = it % CT_STAGES, ph = (it / CT_STAGES) & 1;
+            mbar_wait(&empty_bar[s], ph ^ 1);
+            mbar_expect_tx(&full_bar[s], CT_STAGE_BYTES);
+            uint8_t* sa = smem + s * CT_STAGE_BYTES;
+            tma_load_5d(sa, &tmA, &full_bar[s], (c & 1) * CT_BLOCK_K, x0 * p.in_stride + p.tap_dx[t],
+                        y0 * p.in_stride + p.tap_dy[t], z0 * p.in_stride + p.tap_dz[t], b + (c >> 1) * p.B);
+            tma_load_2d(sa + CT_A_BYTES, &tmB, &full_bar[s], p.tap_col[t] + c * CT_BLOCK_K, 0);
+          }
       }
     }
   } else if (warp == 1) {
-    // ================================ MMA issuer ================================
     if (lane == 0) {
       constexpr uint32_t idesc = umma_idesc_bf16(CT_BLOCK_M, CT_BLOCK_N, 0, 0);
       uint32_t it = 0, tcount = 0;
@@ -162,18 +175,15 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             const uint64_t db = umma_desc_sw128(sb + k * 32, 16, 1024);
             umma_bf16(d_tmem, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
           }
-          umma_commit(&empty_bar[s]);   // frees the smem slot once these MMAs have read it
+          umma_commit(&empty_bar[s]);
         }
-        umma_commit(&tfull_bar[acc]);   // accumulator complete -> epilogue
+        umma_commit(&tfull_bar[acc]);
       }
     }
   } else {
-    // ================================ epilogue (warps 2..5) ================================
-    const int quarter = warp & 3;                 // TMEM lane quarter this warp may access
-    const int row = quarter * 32 + lane;          // GEMM row = voxel index inside the brick
+    const int quarter = warp & 3;
+    const int row = quarter * 32 + lane;
     const int lw = row % p.bw, lh = (row / p.bw) % p.bh, ld = row / (p.bw * p.bh);
-    const bool ups = (p.flags & CF_OUT2_UPSAMPLE) != 0;
-    const bool act = (p.flags & CF_LRELU) != 0;
     uint32_t tcount = 0;
     for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++tcount) {
       const uint32_t acc = tcount & 1, aph = (tcount >> 1) & 1;
@@ -182,78 +192,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const int y = (r % p.ty) * p.bh + lh; r /= p.ty;
       const int z = (r % p.tz) * p.bd + ld; r /= p.tz;
       const int b = r;
-      const bool valid = (x < p.W) && (y < p.H) && (z < p.D);
-      const size_t pos = ((static_cast<size_t>(b) * p.D + z) * p.H + y) * p.W + x;
-
+      const int xo = x * p.out_stride + p.orx, yo = y * p.out_stride + p.ory, zo = z * p.out_stride + p.orz;
+      const bool valid = (x < p.W) && (y < p.H) && (z < p.D) && (xo < p.oW) && (yo < p.oH) && (zo < p.oD);
       mbar_wait(&tfull_bar[acc], aph);
       tc_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * CT_BLOCK_N;
-#pragma unroll 1
-      for (int c0 = 0; c0 < CT_BLOCK_N; c0 += 32) {
-        uint32_t rr[32];
-        tmem_ld_32x32(taddr + c0, rr);
-        tmem_ld_wait();
-        if (valid) {
-          float v[32];
-#pragma unroll
-          for (int k = 0; k < 32; ++k) {
-            float t = __uint_as_float(rr[k]) + s_bias[c0 + k];
-            v[k] = act ? lrelu_f(t) : t;
-          }
-          if (p.mask_src) {
-            const uint4* m = reinterpret_cast<const uint4*>(p.mask_src + pos * CT_BLOCK_N + c0);
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              float f[8];
-              unpack_bf16x8(__ldg(m + q), f);
-#pragma unroll
-              for (int k = 0; k < 8; ++k) v[q * 8 + k] *= lrelu_grad_from_out(f[k]);
-            }
-          }
-          if (p.out) {
-            uint4* o = reinterpret_cast<uint4*>(p.out + pos * CT_BLOCK_N + c0);
-#pragma unroll
-            for (int q = 0; q < 4; ++q)
-              o[q] = make_uint4(pack_bf16x2(v[q * 8], v[q * 8 + 1]), pack_bf16x2(v[q * 8 + 2], v[q * 8 + 3]),
-                                pack_bf16x2(v[q * 8 + 4], v[q * 8 + 5]), pack_bf16x2(v[q * 8 + 6], v[q * 8 + 7]));
-          }
-          if (p.out2) {
-            if (p.residual) {
-              const uint4* m = reinterpret_cast<const uint4*>(p.residual + pos * CT_BLOCK_N + c0);
-#pragma unroll
-              for (int q = 0; q < 4; ++q) {
-                float f[8];
-                unpack_bf16x8(__ldg(m + q), f);
-#pragma unroll
-                for (int k = 0; k < 8; ++k) v[q * 8 + k] += f[k];
-              }
-            }
-            uint4 pk[4];
-#pragma unroll
-            for (int q = 0; q < 4; ++q)
-              pk[q] = make_uint4(pack_bf16x2(v[q * 8], v[q * 8 + 1]), pack_bf16x2(v[q * 8 + 2], v[q * 8 + 3]),
-                                 pack_bf16x2(v[q * 8 + 4], v[q * 8 + 5]), pack_bf16x2(v[q * 8 + 6], v[q * 8 + 7]));
-            if (!ups) {
-              uint4* o = reinterpret_cast<uint4*>(p.out2 + pos * CT_BLOCK_N + c0);
-#pragma unroll
-              for (int q = 0; q < 4; ++q) o[q] = pk[q];
-            } else {
-              // nearest-neighbour x2 (ops.py:75-91): out[2i+a] = in[i]; the z axis only when the conv is 3D
-              const int zr = (p.kd > 1) ? 2 : 1;
-              const int D2 = p.D * zr, H2 = p.H * 2, W2 = p.W * 2;
-              for (int a = 0; a < zr; ++a)
-                for (int e = 0; e < 2; ++e)
-                  for (int f = 0; f < 2; ++f) {
-                    const size_t pos2 =
-                        ((static_cast<size_t>(b) * D2 + (z * zr + a)) * H2 + (2 * y + e)) * W2 + (2 * x + f);
-                    uint4* o = reinterpret_cast<uint4*>(p.out2 + pos2 * CT_BLOCK_N + c0);
-#pragma unroll
-                    for (int q = 0; q < 4; ++q) o[q] = pk[q];
-                  }
-            }
-          }
-        }
-      }
+      conv_epilogue_row(p, taddr, valid, b, zo, yo, xo, s_bias);
       tc_fence_before();
       mbar_arrive(&tempty_bar[acc]);
     }
@@ -286,7 +230,8 @@ __device__ __forceinline__ void conv_epilogue_row(const ConvTcParams& p, uint32_
                                                   int y, int x, const float* s_bias) {
   const bool ups = (p.flags & CF_OUT2_UPSAMPLE) != 0;
   const bool act = (p.flags & CF_LRELU) != 0;
-  const size_t pos = ((static_cast<size_t>(b) * p.D + z) * p.H + y) * p.W + x;
+  const bool mask_after = (p.flags & CF_MASK_AFTER_RESIDUAL) != 0;   // out2 = (v + residual) * lrelu'(mask_src)
+  const size_t pos = ((static_cast<size_t>(b) * p.oD + z) * p.oH + y) * p.oW + x;
 #pragma unroll 1
   for (int c0 = 0; c0 < CT_BLOCK_N; c0 += 32) {
     uint32_t rr[32];
@@ -299,7 +244,7 @@ __device__ __forceinline__ void conv_epilogue_row(const ConvTcParams& p, uint32_
       float t = __uint_as_float(rr[k]) + s_bias[c0 + k];
       v[k] = act ? lrelu_f(t) : t;
     }
-    if (p.mask_src) {
+    if (p.mask_src && !mask_after) {
       const uint4* m = reinterpret_cast<const uint4*>(p.mask_src + pos * CT_BLOCK_N + c0);
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
@@ -327,6 +272,16 @@ __device__ __forceinline__ void conv_epilogue_row(const ConvTcParams& p, uint32_
           for (int k = 0; k < 8; ++k) v[q * 8 + k] += f[k];
         }
       }
+      if (p.mask_src && mask_after) {
+        const uint4* m = reinterpret_cast<const uint4*>(p.mask_src + pos * CT_BLOCK_N + c0);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          float f[8];
+          unpack_bf16x8(__ldg(m + q), f);
+#pragma unroll
+          for (int k = 0; k < 8; ++k) v[q * 8 + k] *= lrelu_grad_from_out(f[k]);
+        }
+      }
       uint4 pk[4];
 #pragma unroll
       for (int q = 0; q < 4; ++q)
@@ -338,7 +293,7 @@ __device__ __forceinline__ void conv_epilogue_row(const ConvTcParams& p, uint32_
         for (int q = 0; q < 4; ++q) o[q] = pk[q];
       } else {
         const int zr = (p.kd > 1) ? 2 : 1;
-        const int D2 = p.D * zr, H2 = p.H * 2, W2 = p.W * 2;
+        const int D2 = p.oD * zr, H2 = p.oH * 2, W2 = p.oW * 2;
         for (int a = 0; a < zr; ++a)
           for (int e = 0; e < 2; ++e)
             for (int f = 0; f < 2; ++f) {
@@ -417,14 +372,15 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             for (int j = 0; j < 4; ++j) {
               mbar_wait(&a_empty[j], (fills[j] & 1) ^ 1);
               mbar_expect_tx(&a_full[j], SLOT_TX);
-              tma_load_5d(smem + j * SLOT_BYTES, &tmA, &a_full[j], c * CT_BLOCK_K, x0 - 1, y0 - 1, z0 - 1 + j, b);
+              tma_load_5d(smem + j * SLOT_BYTES, &tmA, &a_full[j], (c & 1) * CT_BLOCK_K, x0 - 1, y0 - 1, z0 - 1 + j,
+                          b + (c >> 1) * p.B);
               ++fills[j];
             }
           } else {
             const int j = phase & 1;
             mbar_wait(&a_empty[j], (fills[j] & 1) ^ 1);
             mbar_expect_tx(&a_full[j], SLOT_TX);
-            tma_load_5d(smem + j * SLOT_BYTES, &tmA, &a_full[j], c * CT_BLOCK_K, x0 - 1, y0 - 1, 0, b);
+            tma_load_5d(smem + j * SLOT_BYTES, &tmA, &a_full[j], (c & 1) * CT_BLOCK_K, x0 - 1, y0 - 1, 0, b + (c >> 1) * p.B);
             ++fills[j];
           }
         }
@@ -549,7 +505,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 }
 
 // ---------------------------------------------------------------------------------------------
-// host launcher
+// host launchers
 // ---------------------------------------------------------------------------------------------
 static void pick_brick(int D, int H, int W, int& bd, int& bh, int& bw) {
   // 128 voxels; prefer wide-x bricks (contiguous rows), never larger than the (power-of-two-rounded) extent
@@ -564,27 +520,36 @@ static void pick_brick(int D, int H, int W, int& bd, int& bh, int& bw) {
   }
 }
 
+// activation tensor map: channels-last blocks [nblk*B, D, H, W, min(cin,128)]
+static int make_act_map(CUtensorMap* tm, const void* x, int cin, int nbatch, int D, int H, int W, const uint32_t* box,
+                        const uint32_t* estride) {
+  const int cb = std::min(cin, 128);
+  const uint64_t gd[5] = {static_cast<uint64_t>(cb), static_cast<uint64_t>(W), static_cast<uint64_t>(H),
+                          static_cast<uint64_t>(D), static_cast<uint64_t>(nbatch)};
+  const uint64_t gs[4] = {static_cast<uint64_t>(cb) * 2, static_cast<uint64_t>(cb) * 2 * W,
+                          static_cast<uint64_t>(cb) * 2 * W * H, static_cast<uint64_t>(cb) * 2 * W * H * D};
+  return encode_tensor_map(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, x, gd, gs, box, CU_TENSOR_MAP_SWIZZLE_128B, estride);
+}
+
+// Tap-window kernel: 3x3(x3), stride 1, SAME.  cin = 64, 128 or a multiple of 128 (channel-blocked input
+// [cin/128 * B, D, H, W, 128]); cout = 128, or 1..16 for the output conv.
 int conv_tc_launch(const void* x, const void* w_packed, const float* bias, void* out, void* out2,
                    const void* residual, const void* mask_src, const int64_t* dims /*B,D,H,W*/, int nd, int cin,
                    int cout, int flags, cudaStream_t st) {
   const bool small = cout < 128;   // 128 -> 1..3 output conv: w_packed is [16][taps*cin], out is fp32 [.., cout]
   DFL_REQUIRE(cout == 128 || (cout >= 1 && cout <= 16), "conv_tc: Cout must be 128 or <= 16 (got %d)", cout);
-  DFL_REQUIRE(cin % 64 == 0 && cin >= 64, "conv_tc: Cin must be a multiple of 64 (got %d)", cin);
+  DFL_REQUIRE(cin == 64 || (cin >= 128 && cin % 128 == 0), "conv_tc: Cin must be 64 or a multiple of 128 (got %d)", cin);
   DFL_REQUIRE(nd == 2 || nd == 3, "conv_tc: ndim must be 2 or 3");
   ConvTcParams p{};
   p.B = static_cast<int>(dims[0]);
   p.D = nd == 3 ? static_cast<int>(dims[1]) : 1;
   p.H = static_cast<int>(dims[nd - 1]);
   p.W = static_cast<int>(dims[nd]);
+  p.oD = p.D; p.oH = p.H; p.oW = p.W;
   p.kd = nd == 3 ? 3 : 1;
   p.kh = 3;
   p.kw = 3;
-  static const bool use_v1 = (getenv("DFL_CONV_V1") != nullptr);
-  if (use_v1) {
-    pick_brick(p.D, p.H, p.W, p.bd, p.bh, p.bw);
-  } else {  // v2 tiles: 3D 2x16x8, 2D 1x16x16
-    p.bd = nd == 3 ? 2 : 1; p.bh = 16; p.bw = nd == 3 ? 8 : 16;
-  }
+  p.bd = nd == 3 ? 2 : 1; p.bh = 16; p.bw = nd == 3 ? 8 : 16;    // tiles: 3D 2x16x8, 2D 1x16x16
   p.tx = (p.W + p.bw - 1) / p.bw;
   p.ty = (p.H + p.bh - 1) / p.bh;
   p.tz = (p.D + p.bd - 1) / p.bd;
@@ -599,18 +564,12 @@ int conv_tc_launch(const void* x, const void* w_packed, const float* bias, void*
   p.out_f32 = small ? static_cast<float*>(out) : nullptr;
   p.cout_small = small ? cout : 0;
   DFL_REQUIRE(out || out2, "conv_tc: no output buffer given");
-  DFL_REQUIRE(!(small && use_v1), "conv_tc: the small-Cout variant exists only in the v2 kernel");
 
   CUtensorMap tmA, tmB;
   {
-    const uint64_t gd[5] = {static_cast<uint64_t>(cin), static_cast<uint64_t>(p.W), static_cast<uint64_t>(p.H),
-                            static_cast<uint64_t>(p.D), static_cast<uint64_t>(p.B)};
-    const uint64_t gs[4] = {static_cast<uint64_t>(cin) * 2, static_cast<uint64_t>(cin) * 2 * p.W,
-                            static_cast<uint64_t>(cin) * 2 * p.W * p.H,
-                            static_cast<uint64_t>(cin) * 2 * p.W * p.H * p.D};
-    uint32_t box[5] = {64, static_cast<uint32_t>(p.bw), static_cast<uint32_t>(p.bh), static_cast<uint32_t>(p.bd), 1};
-    if (!use_v1) { box[1] = p.bw + 2; box[2] = p.bh + 2; box[3] = 1; }   // one halo'd plane per TMA
-    int rc = encode_tensor_map(&tmA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, x, gd, gs, box, CU_TENSOR_MAP_SWIZZLE_128B);
+    const uint32_t box[5] = {64, static_cast<uint32_t>(p.bw + 2), static_cast<uint32_t>(p.bh + 2), 1, 1};
+    const int nblk = std::max(1, cin / 128);
+    int rc = make_act_map(&tmA, x, cin, nblk * p.B, p.D, p.H, p.W, box, nullptr);   // one halo'd plane per TMA
     if (rc) return rc;
   }
   {
@@ -619,36 +578,99 @@ int conv_tc_launch(const void* x, const void* w_packed, const float* bias, void*
     const uint64_t gs[1] = {static_cast<uint64_t>(ntaps) * cin * 2};
     const uint32_t box[2] = {64, static_cast<uint32_t>(small ? 16 : 128)};
     int rc = encode_tensor_map(&tmB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, w_packed, gd, gs, box,
-                               CU_TENSOR_MAP_SWIZZLE_128B);
+                               CU_TENSOR_MAP_SWIZZLE_128B, nullptr);
     if (rc) return rc;
   }
   const int grid = std::min(p.ntiles, num_sms());
-  if (use_v1) {
-    static bool attr_set = false;
-    if (!attr_set) {
-      DFL_CUDA_OK(cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, CT_SMEM_BYTES));
-      attr_set = true;
-    }
-    conv_tc_kernel<<<grid, CT_THREADS, CT_SMEM_BYTES, st>>>(tmA, tmB, p);
-  } else {
-    static bool attr_set = false;
-    if (!attr_set) {
-      DFL_CUDA_OK(cudaFuncSetAttribute(conv_tc2_kernel<true, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, C2_SMEM_BYTES));
-      DFL_CUDA_OK(cudaFuncSetAttribute(conv_tc2_kernel<false, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, C2_SMEM_BYTES));
-      DFL_CUDA_OK(cudaFuncSetAttribute(conv_tc2_kernel<true, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, C2_SMEM_BYTES));
-      DFL_CUDA_OK(cudaFuncSetAttribute(conv_tc2_kernel<false, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, C2_SMEM_BYTES));
-      attr_set = true;
-    }
-    if (nd == 3 && !small)
-      conv_tc2_kernel<true, 128><<<grid, C2_THREADS, C2_SMEM_BYTES, st>>>(tmA, tmB, p);
-    else if (nd == 3)
-      conv_tc2_kernel<true, 16><<<grid, C2_THREADS, C2_SMEM_BYTES, st>>>(tmA, tmB, p);
-    else if (!small)
-      conv_tc2_kernel<false, 128><<<grid, C2_THREADS, C2_SMEM_BYTES, st>>>(tmA, tmB, p);
-    else
-      conv_tc2_kernel<false, 16><<<grid, C2_THREADS, C2_SMEM_BYTES, st>>>(tmA, tmB, p);
+  static bool attr_set = false;
+  if (!attr_set) {
+    DFL_CUDA_OK(cudaFuncSetAttribute(conv_tc2_kernel<true, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, C2_SMEM_BYTES));
+    DFL_CUDA_OK(cudaFuncSetAttribute(conv_tc2_kernel<false, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, C2_SMEM_BYTES));
+    DFL_CUDA_OK(cudaFuncSetAttribute(conv_tc2_kernel<true, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, C2_SMEM_BYTES));
+    DFL_CUDA_OK(cudaFuncSetAttribute(conv_tc2_kernel<false, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, C2_SMEM_BYTES));
+    attr_set = true;
   }
-  DFL_LAUNCH_OK("conv_tc_kernel");
+  if (nd == 3 && !small)
+    conv_tc2_kernel<true, 128><<<grid, C2_THREADS, C2_SMEM_BYTES, st>>>(tmA, tmB, p);
+  else if (nd == 3)
+    conv_tc2_kernel<true, 16><<<grid, C2_THREADS, C2_SMEM_BYTES, st>>>(tmA, tmB, p);
+  else if (!small)
+    conv_tc2_kernel<false, 128><<<grid, C2_THREADS, C2_SMEM_BYTES, st>>>(tmA, tmB, p);
+  else
+    conv_tc2_kernel<false, 16><<<grid, C2_THREADS, C2_SMEM_BYTES, st>>>(tmA, tmB, p);
+  DFL_LAUNCH_OK("conv_tc2_kernel");
+  return DFL_OK;
+}
+
+// Generic per-tap launcher.  in_dims = {nblk*B, D, H, W} of the (channel-blocked) input tensor, tile_dims = {B, D, H, W}
+// of the tile domain, out_dims = {D, H, W} of the output tensor; taps = ntap x {dz, dy, dx, kcol}; w_ld = row length of
+// the packed weight matrix (elements); the weight pointer addresses the first of the 128 output-channel rows.
+int conv_tap_launch(const void* x, const void* w_packed, const float* bias, void* out, void* out2,
+                    const void* residual, const void* mask_src, const int64_t* in_dims, const int64_t* tile_dims,
+                    const int64_t* out_dims, int nd, int cin, int in_stride, int ntap, const int32_t* taps,
+                    int out_stride, const int32_t* out_off, int64_t w_ld, int flags, cudaStream_t st) {
+  DFL_REQUIRE(nd == 2 || nd == 3, "conv_tap: ndim must be 2 or 3");
+  DFL_REQUIRE(cin == 64 || (cin >= 128 && cin % 128 == 0), "conv_tap: Cin must be 64 or a multiple of 128 (got %d)", cin);
+  DFL_REQUIRE(ntap >= 1 && ntap <= CT_MAX_TAPS, "conv_tap: 1..27 taps (got %d)", ntap);
+  DFL_REQUIRE(in_stride == 1 || in_stride == 2, "conv_tap: in_stride must be 1 or 2");
+  DFL_REQUIRE(out || out2, "conv_tap: no output buffer given");
+  ConvTcParams p{};
+  p.B = static_cast<int>(tile_dims[0]);
+  p.D = nd == 3 ? static_cast<int>(tile_dims[1]) : 1;
+  p.H = static_cast<int>(tile_dims[nd - 1]);
+  p.W = static_cast<int>(tile_dims[nd]);
+  p.oD = nd == 3 ? static_cast<int>(out_dims[0]) : 1;
+  p.oH = static_cast<int>(out_dims[nd - 2]);
+  p.oW = static_cast<int>(out_dims[nd - 1]);
+  p.kd = nd == 3 ? 3 : 1; p.kh = 3; p.kw = 3;
+  pick_brick(p.D, p.H, p.W, p.bd, p.bh, p.bw);
+  p.tx = (p.W + p.bw - 1) / p.bw;
+  p.ty = (p.H + p.bh - 1) / p.bh;
+  p.tz = (p.D + p.bd - 1) / p.bd;
+  p.ntiles = p.B * p.tz * p.ty * p.tx;
+  p.cin_chunks = cin / 64;
+  p.flags = flags;
+  p.bias = bias;
+  p.mask_src = static_cast<const __nv_bfloat16*>(mask_src);
+  p.residual = static_cast<const __nv_bfloat16*>(residual);
+  p.out = static_cast<__nv_bfloat16*>(out);
+  p.out2 = static_cast<__nv_bfloat16*>(out2);
+  p.in_stride = in_stride;
+  p.out_stride = out_stride;
+  p.orz = nd == 3 ? out_off[0] : 0;
+  p.ory = out_off[nd - 2];
+  p.orx = out_off[nd - 1];
+  p.ntap = ntap;
+  for (int t = 0; t < ntap; ++t) {
+    p.tap_dz[t] = taps[4 * t]; p.tap_dy[t] = taps[4 * t + 1]; p.tap_dx[t] = taps[4 * t + 2]; p.tap_col[t] = taps[4 * t + 3];
+  }
+  CUtensorMap tmA, tmB;
+  {
+    const int Din = nd == 3 ? static_cast<int>(in_dims[1]) : 1;
+    const uint32_t s = static_cast<uint32_t>(in_stride);
+    // with a traversal stride s the TMA loads ceil(box/s) elements: box = s * voxels wanted
+    const uint32_t box[5] = {64, p.bw * s, p.bh * s, (Din == 1 ? 1u : p.bd * s), 1};
+    const uint32_t es[5] = {1, s, s, (Din == 1 ? 1u : s), 1};
+    int rc = make_act_map(&tmA, x, cin, static_cast<int>(in_dims[0]), Din, static_cast<int>(in_dims[nd - 1]),
+                          static_cast<int>(in_dims[nd]), box, es);
+    if (rc) return rc;
+  }
+  {
+    const uint64_t gd[2] = {static_cast<uint64_t>(w_ld), 128};
+    const uint64_t gs[1] = {static_cast<uint64_t>(w_ld) * 2};
+    const uint32_t box[2] = {64, 128};
+    int rc = encode_tensor_map(&tmB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, w_packed, gd, gs, box,
+                               CU_TENSOR_MAP_SWIZZLE_128B, nullptr);
+    if (rc) return rc;
+  }
+  static bool attr_set = false;
+  if (!attr_set) {
+    DFL_CUDA_OK(cudaFuncSetAttribute(conv_tap_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, CT_SMEM_BYTES));
+    attr_set = true;
+  }
+  const int grid = std::min(p.ntiles, num_sms());
+  conv_tap_kernel<<<grid, CT_THREADS, CT_SMEM_BYTES, st>>>(tmA, tmB, p);
+  DFL_LAUNCH_OK("conv_tap_kernel");
   return DFL_OK;
 }
 

@@ -1,8 +1,6 @@
 // deepfluids_b200 -- HBM-bound edge layers and element-wise glue of the generator train step (SIMT kernels).
 //
 //   fc_fwd / fc_bwd            slim.fully_connected, activation None      (reference ops.py:23-24, model.py:19,61)
-//   lastconv_{fwd,dgrad,wgrad} the 128 -> 1/2/3 channel output conv       (model.py:42,84): reads/writes 128-ch
-//                              activations once per voxel -> memory/FMA-bound, not a tensor-core shape (N <= 3)
 //   pool_mask                  adjoint of nearest x2 upsample (sum over the 2x2(x2) children, ops.py:75-91)
 //                              fused with the leaky-ReLU derivative of the layer below (ops.py:9-10)
 //   bias_grad                  column sums of dL/d(pre-activation)
@@ -88,315 +86,6 @@ int fc_bwd(const float* z, const void* dout, float* dW, float* db, int B, int K,
     fc_bwd_kernel<<<grid, threads, 0, st>>>(z, static_cast<const float*>(dout), dW, db, B, K, N);
   DFL_LAUNCH_OK("fc_bwd_kernel");
   return DFL_OK;
-}
-
-// =============================================================================================
-// last conv 128 -> COUT (1..3), k = 3, SAME, no activation.  x bf16 [B,D,H,W,128]; W fp32 TF layout
-// [taps][128][COUT]; out fp32 [B,D,H,W,COUT].   One warp per run of 8 consecutive x voxels; lane l owns input
-// channels 4l..4l+3; the x-1..x+8 neighbour slices are loaded once per (dz,dy) and reused by the three dx taps.
-// =============================================================================================
-constexpr int LC_RUN = 8;
-
-struct LcParams {
-  int B, D, H, W, kd;   // kd = 3 (3D) or 1 (2D)
-  int runs_per_row, nruns;
-};
-
-__device__ __forceinline__ void ld_bf16x4(const __nv_bfloat16* p, float (&f)[4]) {
-  const uint2 q = __ldg(reinterpret_cast<const uint2*>(p));
-  f[0] = __uint_as_float(q.x << 16);
-  f[1] = __uint_as_float(q.x & 0xFFFF0000u);
-  f[2] = __uint_as_float(q.y << 16);
-  f[3] = __uint_as_float(q.y & 0xFFFF0000u);
-}
-
-template <int COUT>
-__global__ void __launch_bounds__(128)
-lastconv_fwd_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ W, const float* __restrict__ bias,
-                    float* __restrict__ out, LcParams p) {
-  extern __shared__ float sw[];   // [taps][COUT][128]
-  const int ntaps = p.kd * 9;
-  for (int i = threadIdx.x; i < ntaps * 128 * COUT; i += blockDim.x) {
-    const int co = i % COUT, ci = (i / COUT) % 128, t = i / (COUT * 128);
-    sw[(t * COUT + co) * 128 + ci] = W[i];
-  }
-  __syncthreads();
-  const int lane = threadIdx.x & 31;
-  const int wglobal = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
-  for (int run = wglobal; run < p.nruns; run += nw) {
-    int r = run;
-    const int xr = (r % p.runs_per_row) * LC_RUN; r /= p.runs_per_row;
-    const int y = r % p.H; r /= p.H;
-    const int z = r % p.D;
-    const int b = r / p.D;
-    float acc[LC_RUN][COUT];
-#pragma unroll
-    for (int j = 0; j < LC_RUN; ++j)
-#pragma unroll
-      for (int c = 0; c < COUT; ++c) acc[j][c] = 0.f;
-    for (int dz = 0; dz < p.kd; ++dz) {
-      const int zz = z + dz - (p.kd >> 1);
-      if (zz < 0 || zz >= p.D) continue;
-      for (int dy = 0; dy < 3; ++dy) {
-        const int yy = y + dy - 1;
-        if (yy < 0 || yy >= p.H) continue;
-        const __nv_bfloat16* row = x + ((static_cast<size_t>(b) * p.D + zz) * p.H + yy) * p.W * 128 + lane * 4;
-        float xin[LC_RUN + 2][4];
-#pragma unroll
-        for (int j = 0; j < LC_RUN + 2; ++j) {
-          const int xx = xr + j - 1;
-          if (xx >= 0 && xx < p.W) ld_bf16x4(row + static_cast<size_t>(xx) * 128, xin[j]);
-          else xin[j][0] = xin[j][1] = xin[j][2] = xin[j][3] = 0.f;
-        }
-#pragma unroll
-        for (int dx = 0; dx < 3; ++dx) {
-          const int t = (dz * 3 + dy) * 3 + dx;
-          float w[COUT][4];
-#pragma unroll
-          for (int c = 0; c < COUT; ++c) {
-            const float4 q = *reinterpret_cast<const float4*>(&sw[(t * COUT + c) * 128 + lane * 4]);
-            w[c][0] = q.x; w[c][1] = q.y; w[c][2] = q.z; w[c][3] = q.w;
-          }
-#pragma unroll
-          for (int j = 0; j < LC_RUN; ++j)
-#pragma unroll
-            for (int c = 0; c < COUT; ++c)
-#pragma unroll
-              for (int e = 0; e < 4; ++e) acc[j][c] = fmaf(xin[j + dx][e], w[c][e], acc[j][c]);
-        }
-      }
-    }
-#pragma unroll
-    for (int j = 0; j < LC_RUN; ++j)
-#pragma unroll
-      for (int c = 0; c < COUT; ++c) acc[j][c] = warp_sum(acc[j][c]);
-    if (lane < LC_RUN * COUT) {
-      const int j = lane / COUT, c = lane % COUT;
-      float v = 0.f;
-#pragma unroll
-      for (int jj = 0; jj < LC_RUN; ++jj)
-#pragma unroll
-        for (int cc = 0; cc < COUT; ++cc)
-          if (jj == j && cc == c) v = acc[jj][cc];
-      const int xx = xr + j;
-      if (xx < p.W)
-        out[(((static_cast<size_t>(b) * p.D + z) * p.H + y) * p.W + xx) * COUT + c] = v + bias[c];
-    }
-  }
-}
-
-// dX[p, ci] = sum_{t,co} dOut[p - (t-1), co] W[t, ci, co];  optional second output dX * lrelu'(mask_src)
-template <int COUT>
-__global__ void __launch_bounds__(128)
-lastconv_dgrad_kernel(const float* __restrict__ dout, const float* __restrict__ W,
-                      const __nv_bfloat16* __restrict__ mask_src, __nv_bfloat16* __restrict__ dx,
-                      __nv_bfloat16* __restrict__ dx_masked, LcParams p) {
-  extern __shared__ float sw[];   // [taps][COUT][128]
-  const int ntaps = p.kd * 9;
-  for (int i = threadIdx.x; i < ntaps * 128 * COUT; i += blockDim.x) {
-    const int co = i % COUT, ci = (i / COUT) % 128, t = i / (COUT * 128);
-    sw[(t * COUT + co) * 128 + ci] = W[i];
-  }
-  __syncthreads();
-  const int lane = threadIdx.x & 31;
-  const int wglobal = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
-  for (int run = wglobal; run < p.nruns; run += nw) {
-    int r = run;
-    const int xr = (r % p.runs_per_row) * LC_RUN; r /= p.runs_per_row;
-    const int y = r % p.H; r /= p.H;
-    const int z = r % p.D;
-    const int b = r / p.D;
-    float acc[LC_RUN][4];
-#pragma unroll
-    for (int j = 0; j < LC_RUN; ++j) acc[j][0] = acc[j][1] = acc[j][2] = acc[j][3] = 0.f;
-    for (int dz = 0; dz < p.kd; ++dz) {
-      const int zz = z - (dz - (p.kd >> 1));
-      if (zz < 0 || zz >= p.D) continue;
-      for (int dy = 0; dy < 3; ++dy) {
-        const int yy = y - (dy - 1);
-        if (yy < 0 || yy >= p.H) continue;
-        const float* row = dout + ((static_cast<size_t>(b) * p.D + zz) * p.H + yy) * p.W * COUT;
-        // gradient values at x positions xr-1 .. xr+8 (same for all lanes: broadcast loads)
-        float g[LC_RUN + 2][COUT];
-#pragma unroll
-        for (int j = 0; j < LC_RUN + 2; ++j) {
-          const int xx = xr + j - 1;
-#pragma unroll
-          for (int c = 0; c < COUT; ++c) g[j][c] = (xx >= 0 && xx < p.W) ? __ldg(row + static_cast<size_t>(xx) * COUT + c) : 0.f;
-        }
-#pragma unroll
-        for (int dx = 0; dx < 3; ++dx) {
-          const int t = (dz * 3 + dy) * 3 + dx;
-          float w[COUT][4];
-#pragma unroll
-          for (int c = 0; c < COUT; ++c) {
-            const float4 q = *reinterpret_cast<const float4*>(&sw[(t * COUT + c) * 128 + lane * 4]);
-            w[c][0] = q.x; w[c][1] = q.y; w[c][2] = q.z; w[c][3] = q.w;
-          }
-          // output voxel xr+j receives dOut[x - (dx-1)] = g[j + 1 - (dx-1)] = g[j + 2 - dx]
-#pragma unroll
-          for (int j = 0; j < LC_RUN; ++j)
-#pragma unroll
-            for (int c = 0; c < COUT; ++c)
-#pragma unroll
-              for (int e = 0; e < 4; ++e) acc[j][e] = fmaf(g[j + 2 - dx][c], w[c][e], acc[j][e]);
-        }
-      }
-    }
-#pragma unroll
-    for (int j = 0; j < LC_RUN; ++j) {
-      const int xx = xr + j;
-      if (xx >= p.W) continue;
-      const size_t off = ((((static_cast<size_t>(b) * p.D + z) * p.H + y) * p.W + xx) * 128) + lane * 4;
-      if (dx) {
-        uint2 o;
-        __nv_bfloat162 h0 = __floats2bfloat162_rn(acc[j][0], acc[j][1]), h1 = __floats2bfloat162_rn(acc[j][2], acc[j][3]);
-        o.x = *reinterpret_cast<uint32_t*>(&h0);
-        o.y = *reinterpret_cast<uint32_t*>(&h1);
-        *reinterpret_cast<uint2*>(dx + off) = o;
-      }
-      if (dx_masked) {
-        float m[4];
-        ld_bf16x4(mask_src + off, m);
-        uint2 o;
-        __nv_bfloat162 h0 = __floats2bfloat162_rn(acc[j][0] * lrelu_grad_from_out(m[0]), acc[j][1] * lrelu_grad_from_out(m[1]));
-        __nv_bfloat162 h1 = __floats2bfloat162_rn(acc[j][2] * lrelu_grad_from_out(m[2]), acc[j][3] * lrelu_grad_from_out(m[3]));
-        o.x = *reinterpret_cast<uint32_t*>(&h0);
-        o.y = *reinterpret_cast<uint32_t*>(&h1);
-        *reinterpret_cast<uint2*>(dx_masked + off) = o;
-      }
-    }
-  }
-}
-
-// dW[t][ci][co] += sum_p x[p+t-1][ci] dOut[p][co];  db[co] += sum_p dOut[p][co].
-// Block = 4 voxel-lanes x kd warps; warp (s, dz) walks input voxels q of sub-slab s and scatters x[q] into the
-// 9 (dy,dx) taps of plane dz:  dW[t] += x[q] * dOut[q - (t-1)].  Lane l owns ci = 4l..4l+3.
-template <int COUT>
-__global__ void __launch_bounds__(384)
-lastconv_wgrad_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ dout, float* __restrict__ dW,
-                      float* __restrict__ db, LcParams p) {
-  __shared__ float red[3][9][COUT][128];
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int dzi = warp % p.kd, sub = warp / p.kd;
-  const int nsub = (blockDim.x >> 5) / p.kd;
-  for (int i = threadIdx.x; i < 3 * 9 * COUT * 128; i += blockDim.x) (&red[0][0][0][0])[i] = 0.f;
-  __syncthreads();
-  float acc[9][COUT][4];
-#pragma unroll
-  for (int t = 0; t < 9; ++t)
-#pragma unroll
-    for (int c = 0; c < COUT; ++c) acc[t][c][0] = acc[t][c][1] = acc[t][c][2] = acc[t][c][3] = 0.f;
-  float bsum[COUT];
-#pragma unroll
-  for (int c = 0; c < COUT; ++c) bsum[c] = 0.f;
-  const size_t nvox = static_cast<size_t>(p.B) * p.D * p.H * p.W;
-  const int dz = dzi - (p.kd >> 1) + ((p.kd == 1) ? 0 : 0);
-  for (size_t q = static_cast<size_t>(blockIdx.x) * nsub + sub; q < nvox; q += static_cast<size_t>(gridDim.x) * nsub) {
-    const int xq = q % p.W, yq = (q / p.W) % p.H, zq = (q / (static_cast<size_t>(p.W) * p.H)) % p.D;
-    float xv[4];
-    ld_bf16x4(x + q * 128 + lane * 4, xv);
-    // tap (dz,dy,dx) pairs x[q] with dOut at p = q - (tap - 1)
-    const int zp = zq - dz;
-    if (zp >= 0 && zp < p.D) {
-#pragma unroll
-      for (int dy = 0; dy < 3; ++dy) {
-        const int yp = yq - (dy - 1);
-#pragma unroll
-        for (int dx = 0; dx < 3; ++dx) {
-          const int xp = xq - (dx - 1);
-          if (yp >= 0 && yp < p.H && xp >= 0 && xp < p.W) {
-            const float* g = dout + (q + (static_cast<ptrdiff_t>(zp - zq) * p.H + (yp - yq)) * p.W + (xp - xq)) * COUT;
-#pragma unroll
-            for (int c = 0; c < COUT; ++c) {
-              const float gv = __ldg(g + c);
-#pragma unroll
-              for (int e = 0; e < 4; ++e) acc[dy * 3 + dx][c][e] = fmaf(xv[e], gv, acc[dy * 3 + dx][c][e]);
-            }
-          }
-        }
-      }
-    }
-    if (dzi == 0 && lane == 0) {
-#pragma unroll
-      for (int c = 0; c < COUT; ++c) bsum[c] += __ldg(dout + q * COUT + c);
-    }
-  }
-#pragma unroll
-  for (int t = 0; t < 9; ++t)
-#pragma unroll
-    for (int c = 0; c < COUT; ++c)
-#pragma unroll
-      for (int e = 0; e < 4; ++e) atomicAdd(&red[dzi][t][c][lane * 4 + e], acc[t][c][e]);
-  __syncthreads();
-  const int ntaps = p.kd * 9;
-  for (int i = threadIdx.x; i < ntaps * COUT * 128; i += blockDim.x) {
-    const int ci = i % 128, c = (i / 128) % COUT, t = i / (128 * COUT);
-    atomicAdd(&dW[(static_cast<size_t>(t) * 128 + ci) * COUT + c], red[t / 9][t % 9][c][ci]);
-  }
-  if (dzi == 0 && lane == 0) {
-#pragma unroll
-    for (int c = 0; c < COUT; ++c) atomicAdd(&db[c], bsum[c]);
-  }
-}
-
-static void lc_plan(const int64_t* dims, int nd, LcParams& p) {
-  p.B = static_cast<int>(dims[0]);
-  p.D = nd == 3 ? static_cast<int>(dims[1]) : 1;
-  p.H = static_cast<int>(dims[nd - 1]);
-  p.W = static_cast<int>(dims[nd]);
-  p.kd = nd == 3 ? 3 : 1;
-  p.runs_per_row = (p.W + LC_RUN - 1) / LC_RUN;
-  p.nruns = p.B * p.D * p.H * p.runs_per_row;
-}
-
-template <int COUT>
-static int lastconv_dispatch(int op, const void* a, const void* b, const void* c, void* o0, void* o1,
-                             const LcParams& p, cudaStream_t st) {
-  const int ntaps = p.kd * 9;
-  const size_t smem = static_cast<size_t>(ntaps) * COUT * 128 * sizeof(float);
-  const int grid = std::min((p.nruns + 3) / 4, num_sms() * 8);
-  if (op == 0) {
-    static bool set = false;
-    if (!set && smem > 48 * 1024) {
-      DFL_CUDA_OK(cudaFuncSetAttribute(lastconv_fwd_kernel<COUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
-      set = true;
-    }
-    lastconv_fwd_kernel<COUT><<<grid, 128, smem, st>>>(static_cast<const __nv_bfloat16*>(a), static_cast<const float*>(b),
-                                                       static_cast<const float*>(c), static_cast<float*>(o0), p);
-  } else if (op == 1) {
-    static bool set = false;
-    if (!set && smem > 48 * 1024) {
-      DFL_CUDA_OK(cudaFuncSetAttribute(lastconv_dgrad_kernel<COUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
-      set = true;
-    }
-    lastconv_dgrad_kernel<COUT><<<grid, 128, smem, st>>>(static_cast<const float*>(a), static_cast<const float*>(b),
-                                                         static_cast<const __nv_bfloat16*>(c),
-                                                         static_cast<__nv_bfloat16*>(o0),
-                                                         static_cast<__nv_bfloat16*>(o1), p);
-  } else {
-    const int wgrid = num_sms() * 2;
-    lastconv_wgrad_kernel<COUT><<<wgrid, 4 * p.kd * 32, 0, st>>>(static_cast<const __nv_bfloat16*>(a),
-                                                                 static_cast<const float*>(b), static_cast<float*>(o0),
-                                                                 static_cast<float*>(o1), p);
-  }
-  DFL_LAUNCH_OK("lastconv_kernel");
-  return DFL_OK;
-}
-
-// op 0: fwd(a=x, b=W, c=bias -> o0=out f32)   op 1: dgrad(a=dout, b=W, c=mask_src|null -> o0=dx|null, o1=dx_masked|null)
-// op 2: wgrad(a=x, b=dout -> o0=dW (+=), o1=db (+=))
-int lastconv(int op, const void* a, const void* b, const void* c, void* o0, void* o1, const int64_t* dims, int nd,
-             int cout, cudaStream_t st) {
-  DFL_REQUIRE(nd == 2 || nd == 3, "lastconv: ndim must be 2 or 3");
-  DFL_REQUIRE(cout >= 1 && cout <= 3, "lastconv: Cout must be 1..3 (got %d)", cout);
-  LcParams p{};
-  lc_plan(dims, nd, p);
-  switch (cout) {
-    case 1: return lastconv_dispatch<1>(op, a, b, c, o0, o1, p, st);
-    case 2: return lastconv_dispatch<2>(op, a, b, c, o0, o1, p, st);
-    default: return lastconv_dispatch<3>(op, a, b, c, o0, o1, p, st);
-  }
 }
 
 // =============================================================================================
@@ -503,21 +192,26 @@ int bias_grad(const void* d, float* db, size_t npos, cudaStream_t st) {
 //    wf bf16 [Cout][taps*Cin]          (fwd B operand: row n = co, K = tap*Cin + ci)
 //    wd bf16 [Cin][taps*Cout]          (dgrad B operand: row n = ci, K = tap'*Cout + co, tap' = flipped tap)
 // =============================================================================================
+// `cin_ld` >= cin is the padded input-channel count of the forward operand (rows of zeros stay untouched), used by the
+// encoder's first conv whose 2/3 input channels are zero-padded to 128.
 __global__ void pack_conv_weights_kernel(const float* __restrict__ W, __nv_bfloat16* __restrict__ wf,
-                                         __nv_bfloat16* __restrict__ wd, int taps, int cin, int cout) {
-  const int n = taps * cin * cout;
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-    const int co = i % cout, ci = (i / cout) % cin, t = i / (cout * cin);
+                                         __nv_bfloat16* __restrict__ wd, int taps, int cin, int cout, int cin_ld) {
+  const size_t n = static_cast<size_t>(taps) * cin * cout;
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int co = i % cout, ci = (i / cout) % cin, t = i / (static_cast<size_t>(cout) * cin);
     const __nv_bfloat16 v = __float2bfloat16_rn(W[i]);
-    if (wf) wf[static_cast<size_t>(co) * taps * cin + t * cin + ci] = v;
-    if (wd) wd[static_cast<size_t>(ci) * taps * cout + (taps - 1 - t) * cout + co] = v;
+    if (wf) wf[(static_cast<size_t>(co) * taps + t) * cin_ld + ci] = v;
+    if (wd) wd[(static_cast<size_t>(ci) * taps + (taps - 1 - t)) * cout + co] = v;
   }
 }
 
-int pack_conv_weights(const float* W, void* wf, void* wd, int taps, int cin, int cout, cudaStream_t st) {
-  const int n = taps * cin * cout;
-  pack_conv_weights_kernel<<<(n + 255) / 256, 256, 0, st>>>(W, static_cast<__nv_bfloat16*>(wf),
-                                                            static_cast<__nv_bfloat16*>(wd), taps, cin, cout);
+int pack_conv_weights(const float* W, void* wf, void* wd, int taps, int cin, int cout, int cin_ld, cudaStream_t st) {
+  const size_t n = static_cast<size_t>(taps) * cin * cout;
+  const int grid = static_cast<int>(std::min<size_t>((n + 255) / 256, static_cast<size_t>(num_sms()) * 16));
+  if (cin_ld < cin) cin_ld = cin;
+  pack_conv_weights_kernel<<<grid, 256, 0, st>>>(W, static_cast<__nv_bfloat16*>(wf),
+                                                            static_cast<__nv_bfloat16*>(wd), taps, cin, cout, cin_ld);
   DFL_LAUNCH_OK("pack_conv_weights_kernel");
   return DFL_OK;
 }
@@ -569,6 +263,246 @@ int cast_f32_bf16(const float* a, void* o, size_t n, cudaStream_t st) {
   const int grid = static_cast<int>(std::min<size_t>((n + 255) / 256, static_cast<size_t>(num_sms()) * 16));
   cast_f32_bf16_kernel<<<grid, 256, 0, st>>>(a, static_cast<__nv_bfloat16*>(o), n);
   DFL_LAUNCH_OK("cast_kernel");
+  return DFL_OK;
+}
+
+// =============================================================================================
+// AE / encoder glue (reference model.py:118-216, trainer.py:357-396)
+// =============================================================================================
+// pad_cast: fp32 [n][cin] -> bf16 [n][128], channels >= cin zero (input of the encoder's first conv)
+__global__ void pad_cast_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ out, size_t n, int cin) {
+  const size_t total = n * 16;     // 16 threads per voxel, 8 channels each
+  for (size_t idx = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; idx < total;
+       idx += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int q = idx & 15;
+    const size_t v = idx >> 4;
+    uint32_t w[4] = {0, 0, 0, 0};
+    if (q == 0) {
+      float f[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+      for (int c = 0; c < cin && c < 8; ++c) f[c] = in[v * cin + c];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        __nv_bfloat162 h = __floats2bfloat162_rn(f[2 * k], f[2 * k + 1]);
+        w[k] = *reinterpret_cast<uint32_t*>(&h);
+      }
+    }
+    *reinterpret_cast<uint4*>(out + v * 128 + q * 8) = make_uint4(w[0], w[1], w[2], w[3]);
+  }
+}
+int pad_cast(const float* in, void* out, size_t n, int cin, cudaStream_t st) {
+  DFL_REQUIRE(cin >= 1 && cin <= 8, "pad_cast: 1..8 input channels (got %d)", cin);
+  const int grid = static_cast<int>(std::min<size_t>((n * 16 + 255) / 256, static_cast<size_t>(num_sms()) * 16));
+  pad_cast_kernel<<<grid, 256, 0, st>>>(in, static_cast<__nv_bfloat16*>(out), n, cin);
+  DFL_LAUNCH_OK("pad_cast_kernel");
+  return DFL_OK;
+}
+
+// add_mask: out = (a + b) * lrelu'(y)   (b and/or y may be null)      bf16 arrays of n elements (n % 8 == 0)
+__global__ void add_mask_kernel(const __nv_bfloat16* __restrict__ a, const __nv_bfloat16* __restrict__ b,
+                                const __nv_bfloat16* __restrict__ y, __nv_bfloat16* __restrict__ out, size_t n8) {
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n8;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const uint4 av = __ldg(reinterpret_cast<const uint4*>(a) + i);
+    uint4 bv = make_uint4(0, 0, 0, 0), yv = make_uint4(0, 0, 0, 0);
+    if (b) bv = __ldg(reinterpret_cast<const uint4*>(b) + i);
+    if (y) yv = __ldg(reinterpret_cast<const uint4*>(y) + i);
+    const uint32_t aw[4] = {av.x, av.y, av.z, av.w}, bw[4] = {bv.x, bv.y, bv.z, bv.w}, yw[4] = {yv.x, yv.y, yv.z, yv.w};
+    uint32_t ow[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      float lo = __uint_as_float(aw[k] << 16) + __uint_as_float(bw[k] << 16);
+      float hi = __uint_as_float(aw[k] & 0xFFFF0000u) + __uint_as_float(bw[k] & 0xFFFF0000u);
+      if (y) {
+        lo *= lrelu_grad_from_out(__uint_as_float(yw[k] << 16));
+        hi *= lrelu_grad_from_out(__uint_as_float(yw[k] & 0xFFFF0000u));
+      }
+      __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
+      ow[k] = *reinterpret_cast<uint32_t*>(&h);
+    }
+    reinterpret_cast<uint4*>(out)[i] = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+  }
+}
+int add_mask(const void* a, const void* b, const void* y, void* out, size_t n, cudaStream_t st) {
+  DFL_REQUIRE(n % 8 == 0, "add_mask: element count must be a multiple of 8");
+  const size_t n8 = n / 8;
+  const int grid = static_cast<int>(std::min<size_t>((n8 + 255) / 256, static_cast<size_t>(num_sms()) * 16));
+  add_mask_kernel<<<grid, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(a), static_cast<const __nv_bfloat16*>(b),
+                                        static_cast<const __nv_bfloat16*>(y), static_cast<__nv_bfloat16*>(out), n8);
+  DFL_LAUNCH_OK("add_mask_kernel");
+  return DFL_OK;
+}
+
+// Encoder FC (model.py:149,185): z[b][j] = bias[j] + sum_n flat[b][n] W[n][j], Z <= 16 outputs, B <= 8.
+// flat is the channel-blocked concat tensor [nblk][B][V][128] bf16; TF's flatten order is (voxel, channel) with
+// channel = blk*128 + c, so n = v*(nblk*128) + blk*128 + c.  One thread per n; block partial sums -> atomics.
+constexpr int EF_MAXB = 8, EF_Z = 16;
+__global__ void __launch_bounds__(256)
+enc_fc_fwd_kernel(const __nv_bfloat16* __restrict__ flat, const float* __restrict__ W, const float* __restrict__ bias,
+                  float* __restrict__ z, int B, int V, int nblk, int Z) {
+  __shared__ float red[8][EF_MAXB * EF_Z];
+  const size_t F = static_cast<size_t>(V) * nblk * 128;
+  float acc[EF_MAXB][EF_Z];
+#pragma unroll
+  for (int b = 0; b < EF_MAXB; ++b)
+#pragma unroll
+    for (int j = 0; j < EF_Z; ++j) acc[b][j] = 0.f;
+  for (size_t n = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; n < F;
+       n += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int c = n & 127;
+    const int blk = (n >> 7) % nblk;
+    const size_t v = (n >> 7) / nblk;
+    float w[EF_Z];
+#pragma unroll
+    for (int j = 0; j < EF_Z; ++j) w[j] = (j < Z) ? __ldg(W + n * Z + j) : 0.f;
+#pragma unroll
+    for (int b = 0; b < EF_MAXB; ++b) {
+      if (b < B) {
+        const float f = __bfloat162float(flat[((static_cast<size_t>(blk) * B + b) * V + v) * 128 + c]);
+#pragma unroll
+        for (int j = 0; j < EF_Z; ++j) acc[b][j] = fmaf(f, w[j], acc[b][j]);
+      }
+    }
+  }
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int b = 0; b < EF_MAXB; ++b)
+#pragma unroll
+    for (int j = 0; j < EF_Z; ++j) {
+      const float t = warp_sum(acc[b][j]);
+      if (lane == 0) red[warp][b * EF_Z + j] = t;
+    }
+  __syncthreads();
+  if (threadIdx.x < EF_MAXB * EF_Z) {
+    const int b = threadIdx.x / EF_Z, j = threadIdx.x % EF_Z;
+    if (b < B && j < Z) {
+      float t = 0.f;
+      for (int w8 = 0; w8 < 8; ++w8) t += red[w8][threadIdx.x];
+      if (blockIdx.x == 0) t += bias[j];
+      atomicAdd(z + b * Z + j, t);
+    }
+  }
+}
+int enc_fc_fwd(const void* flat, const float* W, const float* bias, float* z, int B, int V, int nblk, int Z,
+               cudaStream_t st) {
+  DFL_REQUIRE(B <= EF_MAXB && Z <= EF_Z, "enc_fc_fwd: B <= %d, Z <= %d (got %d, %d)", EF_MAXB, EF_Z, B, Z);
+  DFL_CUDA_OK(cudaMemsetAsync(z, 0, sizeof(float) * B * Z, st));
+  const size_t F = static_cast<size_t>(V) * nblk * 128;
+  const int grid = static_cast<int>(std::min<size_t>((F + 255) / 256, static_cast<size_t>(num_sms()) * 4));
+  enc_fc_fwd_kernel<<<grid, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(flat), W, bias, z, B, V, nblk, Z);
+  DFL_LAUNCH_OK("enc_fc_fwd_kernel");
+  return DFL_OK;
+}
+
+// backward: dW[n][j] = sum_b flat[b][n] dz[b][j] (written), db[j] = sum_b dz[b][j] (written),
+//           dflat[b][n] = sum_j dz[b][j] W[n][j] (bf16, same channel-blocked layout as flat)
+__global__ void __launch_bounds__(256)
+enc_fc_bwd_kernel(const __nv_bfloat16* __restrict__ flat, const float* __restrict__ W, const float* __restrict__ dz,
+                  float* __restrict__ dW, float* __restrict__ db, __nv_bfloat16* __restrict__ dflat, int B, int V,
+                  int nblk, int Z) {
+  __shared__ float sdz[EF_MAXB * EF_Z];
+  if (threadIdx.x < EF_MAXB * EF_Z) {
+    const int b = threadIdx.x / EF_Z, j = threadIdx.x % EF_Z;
+    sdz[threadIdx.x] = (b < B && j < Z) ? dz[b * Z + j] : 0.f;
+  }
+  __syncthreads();
+  if (blockIdx.x == 0 && threadIdx.x < Z) {
+    float t = 0.f;
+    for (int b = 0; b < B; ++b) t += sdz[b * EF_Z + threadIdx.x];
+    db[threadIdx.x] = t;
+  }
+  const size_t F = static_cast<size_t>(V) * nblk * 128;
+  for (size_t n = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; n < F;
+       n += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int c = n & 127;
+    const int blk = (n >> 7) % nblk;
+    const size_t v = (n >> 7) / nblk;
+    float w[EF_Z], g[EF_Z];
+#pragma unroll
+    for (int j = 0; j < EF_Z; ++j) { w[j] = (j < Z) ? __ldg(W + n * Z + j) : 0.f; g[j] = 0.f; }
+#pragma unroll
+    for (int b = 0; b < EF_MAXB; ++b) {
+      if (b < B) {
+        const size_t off = ((static_cast<size_t>(blk) * B + b) * V + v) * 128 + c;
+        const float f = __bfloat162float(flat[off]);
+        float d = 0.f;
+#pragma unroll
+        for (int j = 0; j < EF_Z; ++j) {
+          g[j] = fmaf(f, sdz[b * EF_Z + j], g[j]);
+          d = fmaf(sdz[b * EF_Z + j], w[j], d);
+        }
+        dflat[off] = __float2bfloat16_rn(d);
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < EF_Z; ++j)
+      if (j < Z) dW[n * Z + j] = g[j];
+  }
+}
+int enc_fc_bwd(const void* flat, const float* W, const float* dz, float* dW, float* db, void* dflat, int B, int V,
+               int nblk, int Z, cudaStream_t st) {
+  DFL_REQUIRE(B <= EF_MAXB && Z <= EF_Z, "enc_fc_bwd: B <= %d, Z <= %d (got %d, %d)", EF_MAXB, EF_Z, B, Z);
+  const size_t F = static_cast<size_t>(V) * nblk * 128;
+  const int grid = static_cast<int>(std::min<size_t>((F + 255) / 256, static_cast<size_t>(num_sms()) * 8));
+  enc_fc_bwd_kernel<<<grid, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(flat), W, dz, dW, db,
+                                          static_cast<__nv_bfloat16*>(dflat), B, V, nblk, Z);
+  DFL_LAUNCH_OK("enc_fc_bwd_kernel");
+  return DFL_OK;
+}
+
+// decoder-FC input gradient: dz[b][k] (+)= sum_n dout[b][n] W[k][n]     one block per (b, k)
+template <typename TI>
+__global__ void __launch_bounds__(256)
+fc_dz_kernel(const TI* __restrict__ dout, const float* __restrict__ W, float* __restrict__ dz, int K, int N, int accumulate) {
+  __shared__ float red[8];
+  const int b = blockIdx.x / K, k = blockIdx.x % K;
+  float t = 0.f;
+  for (int n = threadIdx.x; n < N; n += 256) t = fmaf(ldf(dout + static_cast<size_t>(b) * N + n), __ldg(W + static_cast<size_t>(k) * N + n), t);
+  t = warp_sum(t);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = t;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float r = 0.f;
+    for (int i = 0; i < 8; ++i) r += red[i];
+    dz[b * K + k] = accumulate ? dz[b * K + k] + r : r;
+  }
+}
+int fc_dz(const void* dout, const float* W, float* dz, int B, int K, int N, int dout_dtype, int accumulate, cudaStream_t st) {
+  if (dout_dtype == DT_BF16)
+    fc_dz_kernel<<<B * K, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(dout), W, dz, K, N, accumulate);
+  else
+    fc_dz_kernel<<<B * K, 256, 0, st>>>(static_cast<const float*>(dout), W, dz, K, N, accumulate);
+  DFL_LAUNCH_OK("fc_dz_kernel");
+  return DFL_OK;
+}
+
+// AE parameter loss (trainer.py:385-387): loss_p = mean((y - z[:, Z-P:])^2);  dz[:, Z-P:] = scale * 2 (z - y) / (B P),
+// dz[:, :Z-P] = 0 (dz is then accumulated into by the decoder's fc_dz).   single block
+__global__ void ae_loss_p_kernel(const float* __restrict__ z, const float* __restrict__ y, float* __restrict__ dz,
+                                 float* __restrict__ loss_p, int B, int Z, int P, float scale) {
+  __shared__ float red[256];
+  float acc = 0.f;
+  for (int i = threadIdx.x; i < B * Z; i += blockDim.x) {
+    const int b = i / Z, j = i % Z;
+    float d = 0.f;
+    if (j >= Z - P) {
+      const float e = z[i] - y[b * P + (j - (Z - P))];
+      acc += e * e;
+      d = scale * 2.f * e / static_cast<float>(B * P);
+    }
+    dz[i] = d;
+  }
+  red[threadIdx.x] = acc;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) *loss_p = red[0] / static_cast<float>(B * P);
+}
+int ae_loss_p(const float* z, const float* y, float* dz, float* loss_p, int B, int Z, int P, float scale, cudaStream_t st) {
+  DFL_REQUIRE(P >= 1 && P <= Z, "ae_loss_p: need 1 <= p_num <= z_num");
+  ae_loss_p_kernel<<<1, 256, 0, st>>>(z, y, dz, loss_p, B, Z, P, scale);
+  DFL_LAUNCH_OK("ae_loss_p_kernel");
   return DFL_OK;
 }
 

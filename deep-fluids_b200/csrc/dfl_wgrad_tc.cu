@@ -31,8 +31,11 @@ struct WgradParams {
   int tz, ty, tx, ntiles;
   int kd, kh, kw;
   int taps_per_group, ngroups, nslabs;
-  float* dw;          // [taps][128][128] fp32 (TF layout: ..., Cin, Cout), accumulated into
+  float* dw;          // fp32 gradient block, element (tap, ci, co) at dw[tap*dw_tap_stride + ci*dw_row_stride + co]
   float* db;          // [128] fp32 bias gradient (sum_p dP[p][co]), accumulated into; may be nullptr
+  int in_stride;      // 1, or 2 for the weight gradient of a stride-2 convolution (X sampled at 2p + tap - pad)
+  int pad;            // tap offset = tap index - pad   (1 for SAME stride 1; pad_before of TF SAME for stride 2)
+  int dw_tap_stride, dw_row_stride;   // TF layout [taps][Cin][Cout]: Cin*Cout and Cout
 };
 
 __global__ void __launch_bounds__(WG_THREADS, 1)
@@ -104,7 +107,8 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
             const uint32_t s = ia % WG_A_SLOTS, ph = (ia / WG_A_SLOTS) & 1;
             mbar_wait(&a_empty[s], ph ^ 1);
             mbar_expect_tx(&a_full[s], WG_OP_BYTES);
-            const int xs = x0 + dx - (p.kw >> 1), ys = y0 + dy - (p.kh >> 1), zs = z0 + dz - (p.kd >> 1);
+            const int xs = x0 * p.in_stride + dx - p.pad, ys = y0 * p.in_stride + dy - p.pad,
+                      zs = (p.kd > 1) ? z0 * p.in_stride + dz - p.pad : 0;
             tma_load_5d(sA + s * WG_OP_BYTES, &tmX, &a_full[s], 0, xs, ys, zs, b);
             tma_load_5d(sA + s * WG_OP_BYTES + WG_OP_BYTES / 2, &tmX, &a_full[s], 64, xs, ys, zs, b);
           }
@@ -151,7 +155,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
       mbar_wait(acc_full, 0);
       tc_fence_after();
       for (int t = 0; t < gtaps; ++t) {
-        float* dst = p.dw + (static_cast<size_t>(tap0 + t) * 128 + ci) * 128;
+        float* dst = p.dw + static_cast<size_t>(tap0 + t) * p.dw_tap_stride + static_cast<size_t>(ci) * p.dw_row_stride;
 #pragma unroll 1
         for (int c0 = 0; c0 < 128; c0 += 32) {
           uint32_t rr[32];
@@ -197,10 +201,12 @@ static void pick_brick_w(int D, int H, int W, int& bd, int& bh, int& bw) {
   }
 }
 
-int wgrad_tc_launch(const void* x, const void* dpre, float* dw, float* db, const int64_t* dims, int nd, int cin,
-                    int cout, cudaStream_t st) {
-  DFL_REQUIRE(cin == 128 && cout == 128, "wgrad_tc: only Cin = Cout = 128 (got %d, %d)", cin, cout);
+// x: [B, xD, xH, xW, 128] bf16 (one 128-channel block), dpre: [B, D, H, W, 128] bf16 (tile domain).  For stride 1
+// x dims == dims; for the gradient of a stride-2 conv x is the fine grid and the TMA walks it with element stride 2.
+int wgrad_tc_launch(const void* x, const void* dpre, float* dw, float* db, const int64_t* x_dims, const int64_t* dims,
+                    int nd, int in_stride, int pad, int dw_tap_stride, int dw_row_stride, cudaStream_t st) {
   DFL_REQUIRE(nd == 2 || nd == 3, "wgrad_tc: ndim must be 2 or 3");
+  DFL_REQUIRE(in_stride == 1 || in_stride == 2, "wgrad_tc: in_stride must be 1 or 2");
   WgradParams p{};
   p.B = static_cast<int>(dims[0]);
   p.D = nd == 3 ? static_cast<int>(dims[1]) : 1;
@@ -220,17 +226,32 @@ int wgrad_tc_launch(const void* x, const void* dpre, float* dw, float* db, const
   p.nslabs = std::max(1, std::min(p.ntiles, num_sms() / p.ngroups));
   p.dw = dw;
   p.db = db;
+  p.in_stride = in_stride;
+  p.pad = pad;
+  p.dw_tap_stride = dw_tap_stride;
+  p.dw_row_stride = dw_row_stride;
 
   CUtensorMap tmX, tmP;
-  const uint64_t gd[5] = {128, static_cast<uint64_t>(p.W), static_cast<uint64_t>(p.H), static_cast<uint64_t>(p.D),
-                          static_cast<uint64_t>(p.B)};
-  const uint64_t gs[4] = {256, 256ull * p.W, 256ull * p.W * p.H, 256ull * p.W * p.H * p.D};
-  const uint32_t box[5] = {64, static_cast<uint32_t>(p.bw), static_cast<uint32_t>(p.bh), static_cast<uint32_t>(p.bd),
-                           1};
-  int rc = encode_tensor_map(&tmX, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, x, gd, gs, box, CU_TENSOR_MAP_SWIZZLE_128B);
-  if (rc) return rc;
-  rc = encode_tensor_map(&tmP, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, dpre, gd, gs, box, CU_TENSOR_MAP_SWIZZLE_128B);
-  if (rc) return rc;
+  {
+    const int xD = nd == 3 ? static_cast<int>(x_dims[1]) : 1, xH = static_cast<int>(x_dims[nd - 1]),
+              xW = static_cast<int>(x_dims[nd]);
+    const uint32_t s = static_cast<uint32_t>(in_stride);
+    const uint64_t gd[5] = {128, static_cast<uint64_t>(xW), static_cast<uint64_t>(xH), static_cast<uint64_t>(xD),
+                            static_cast<uint64_t>(x_dims[0])};
+    const uint64_t gs[4] = {256, 256ull * xW, 256ull * xW * xH, 256ull * xW * xH * xD};
+    const uint32_t box[5] = {64, p.bw * s, p.bh * s, (xD == 1 ? 1u : p.bd * s), 1};
+    const uint32_t es[5] = {1, s, s, (xD == 1 ? 1u : s), 1};
+    int rc = encode_tensor_map(&tmX, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, x, gd, gs, box, CU_TENSOR_MAP_SWIZZLE_128B, es);
+    if (rc) return rc;
+  }
+  {
+    const uint64_t gd[5] = {128, static_cast<uint64_t>(p.W), static_cast<uint64_t>(p.H), static_cast<uint64_t>(p.D),
+                            static_cast<uint64_t>(p.B)};
+    const uint64_t gs[4] = {256, 256ull * p.W, 256ull * p.W * p.H, 256ull * p.W * p.H * p.D};
+    const uint32_t box[5] = {64, static_cast<uint32_t>(p.bw), static_cast<uint32_t>(p.bh), static_cast<uint32_t>(p.bd), 1};
+    int rc = encode_tensor_map(&tmP, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, dpre, gd, gs, box, CU_TENSOR_MAP_SWIZZLE_128B);
+    if (rc) return rc;
+  }
   static bool attr_set = false;
   if (!attr_set) {
     DFL_CUDA_OK(cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, WG_SMEM_BYTES));

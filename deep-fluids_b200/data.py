@@ -48,7 +48,12 @@ class BatchManager(object):
 
     def _make(self, sp, g):
         nd = len(sp)
-        y = torch.rand(self.batch_size, self.c_num, device=self.device, generator=g) * 2 - 1
+        if 'ae' in getattr(self.config, "arch", "de"):
+            # AE scenes store the source-position history: y [B, dof, num_frames] (data.py:70-72); only the last
+            # frame supervises the latent code (trainer.py:385)
+            y = torch.rand(self.batch_size, self.dof, 1, device=self.device, generator=g) * 2 - 1
+        else:
+            y = torch.rand(self.batch_size, self.c_num, device=self.device, generator=g) * 2 - 1
         pot = torch.randn([self.batch_size] + sp + [1 if nd == 2 else 3], device=self.device, generator=g)
         for _ in range(2):                       # separable box smoothing: band-limits the field
             for ax in range(1, nd + 1):

@@ -184,8 +184,9 @@ class GeneratorEngine(object):
         return self.pot
 
     # ------------------------------------------------------------------ backward (TF autodiff of the above)
-    def backward(self, dpot):
-        """dpot: fp32 gradient w.r.t. the generator output.  Accumulates into params.grad (call zero_grad first)."""
+    def backward(self, dpot, dz=None):
+        """dpot: fp32 gradient w.r.t. the generator output.  Accumulates into params.grad (call zero_grad first).
+        dz (fp32 [B, z_dim], optional): the gradient w.r.t. the generator input is ADDED to it (AE decoder)."""
         assert not self.inference, "inference engine has no backward pass"
         assert self.B <= 64, "fc_bwd keeps <= 64 parameter rows in smem"
         P = self.params
@@ -215,6 +216,8 @@ class GeneratorEngine(object):
                 K.pool_mask(gx0, self.y[i - 1][nc - 1], ds, dpre)
             else:
                 K.fc_bwd(self.z, gx0.view(self.B, -1), P.g(self.name + "/0_fc/weights"), P.g(self.name + "/0_fc/biases"))
+                if dz is not None:
+                    K.fc_dz(gx0.view(self.B, -1), P.p(self.name + "/0_fc/weights"), dz, accumulate=True)
 
     def zero_grad(self):
         self.params.grad.zero_()

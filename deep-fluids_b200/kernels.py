@@ -8,7 +8,7 @@ import ctypes as C
 import torch
 
 from . import cabi
-from .cabi import F32, BF16, CONV_LRELU, CONV_OUT2_UPSAMPLE, check, dims_array
+from .cabi import F32, BF16, CONV_LRELU, CONV_OUT2_UPSAMPLE, CONV_MASK_AFTER_RESIDUAL, check, dims_array
 
 _DT = {torch.float32: F32, torch.bfloat16: BF16}
 
@@ -139,14 +139,87 @@ def pack_conv_weights(w, w_fwd=None, w_dgrad=None):
     return w_fwd, w_dgrad
 
 
-def conv3x3(x, w_packed, bias=None, out=None, out2=None, residual=None, mask_src=None, flags=0):
-    """tcgen05 implicit-GEMM conv; see dfl_conv3x3_fwd in include/deepfluids_b200.h."""
-    d, nd = _spatial(x)
-    cin, cout = x.shape[-1], w_packed.shape[0]
-    assert x.dtype == torch.bfloat16 and w_packed.dtype == torch.bfloat16
+def conv3x3(x, w_packed, bias=None, out=None, out2=None, residual=None, mask_src=None, flags=0, nblk=1):
+    """tcgen05 implicit-GEMM conv; see dfl_conv3x3_fwd in include/deepfluids_b200.h.  `nblk` > 1: x is a channel-blocked
+    tensor [nblk*B,(D,)H,W,128] holding nblk*128 input channels."""
+    nd = x.dim() - 2
+    d = dims_array((x.shape[0] // nblk,) + tuple(x.shape[1:-1]))
+    cin, cout = x.shape[-1] * nblk, w_packed.shape[0]
+    assert x.dtype == torch.bfloat16 and w_packed.dtype == torch.bfloat16 and x.shape[0] % nblk == 0
     flops = 2.0 * (x.numel() // cin) * cin * cout * (3 ** nd)     # algorithmic MACs x 2 (dense taps)
     PROF.timed("conv_tc", flops, lambda: check(cabi.lib().dfl_conv3x3_fwd(
         _p(x), _p(w_packed), _p(bias), _p(out), _p(out2), _p(residual), _p(mask_src), d, nd, cin, cout, flags, _st())))
+
+
+def pack_conv_weights_ex(w, w_fwd, w_dgrad, cin_ld):
+    """as pack_conv_weights, forward operand laid out for `cin_ld` (>= Cin) input channels"""
+    cin, cout = w.shape[-2], w.shape[-1]
+    taps = w.numel() // (cin * cout)
+    PROF.launches += 1
+    check(cabi.lib().dfl_pack_conv_weights_ex(_p(w), _p(w_fwd), _p(w_dgrad), taps, cin, cout, cin_ld, _st()))
+
+
+def conv_taps(x, w_rows, bias, out, out2, residual, mask_src, tile_dims, out_dims, cin, in_stride, taps, out_stride,
+              out_off, flags=0):
+    """generic per-tap tensor-core conv (dfl_conv_taps).  x: channel-blocked input [nblk*B,(D,)H,W,128]; w_rows: bf16
+    2-D view [128, w_ld] of the packed weight rows of this output block; taps: list of (dz, dy, dx, kcol)."""
+    nd = x.dim() - 2
+    tarr = (C.c_int32 * (4 * len(taps)))(*[int(v) for t in taps for v in t])
+    oarr = (C.c_int32 * 3)(*([int(v) for v in out_off] + [0] * (3 - len(out_off))))
+    assert w_rows.shape[0] == 128 and w_rows.stride(1) == 1
+    flops = 2.0 * float(torch.tensor(tile_dims).prod()) * cin * 128 * len(taps)
+    PROF.timed("conv_tap", flops, lambda: check(cabi.lib().dfl_conv_taps(
+        _p(x), C.c_void_p(w_rows.data_ptr()), _p(bias), _p(out), _p(out2), _p(residual), _p(mask_src),
+        dims_array(x.shape[:-1]), dims_array(tile_dims), dims_array(out_dims), nd, cin, in_stride, len(taps), tarr,
+        out_stride, oarr, w_rows.stride(0), flags, _st())))
+
+
+def conv_wgrad_ex(x, dpre, dw_ptr_tensor, db, in_stride, pad, dw_tap_stride, dw_row_stride):
+    """weight gradient of one (input block, output block) pair; dw_ptr_tensor: fp32 tensor whose data_ptr is the
+    address of element (tap 0, ci 0, co 0) of the destination block."""
+    nd = x.dim() - 2
+    flops = 2.0 * (dpre.numel() // 128) * 128 * 128 * (3 ** nd)
+    PROF.timed("wgrad_tc", flops, lambda: check(cabi.lib().dfl_conv_wgrad_ex(
+        _p(x), _p(dpre), C.c_void_p(dw_ptr_tensor.data_ptr()), _p(db), dims_array(x.shape[:-1]),
+        dims_array(dpre.shape[:-1]), nd, in_stride, pad, dw_tap_stride, dw_row_stride, _st())))
+
+
+def pad_cast(x, out):
+    """fp32 [..., cin] -> bf16 [..., 128] zero padded"""
+    PROF.launches += 1
+    check(cabi.lib().dfl_pad_cast(_p(x), _p(out), x.numel() // x.shape[-1], x.shape[-1], _st()))
+
+
+def add_mask(a, b, y, out):
+    """out = (a + b) * lrelu'(y)   (b, y optional)"""
+    PROF.launches += 1
+    check(cabi.lib().dfl_add_mask(_p(a), _p(b), _p(y), _p(out), a.numel(), _st()))
+
+
+def enc_fc_fwd(flat, W, bias, z, nblk):
+    B = flat.shape[0] // nblk
+    V = flat.numel() // (flat.shape[0] * 128)
+    PROF.launches += 1
+    check(cabi.lib().dfl_enc_fc_fwd(_p(flat), _p(W), _p(bias), _p(z), B, V, nblk, W.shape[1], _st()))
+
+
+def enc_fc_bwd(flat, W, dz, dW, db, dflat, nblk):
+    B = flat.shape[0] // nblk
+    V = flat.numel() // (flat.shape[0] * 128)
+    PROF.launches += 1
+    check(cabi.lib().dfl_enc_fc_bwd(_p(flat), _p(W), _p(dz), _p(dW), _p(db), _p(dflat), B, V, nblk, W.shape[1], _st()))
+
+
+def fc_dz(dout, W, dz, accumulate=False):
+    B, N = dout.shape
+    PROF.launches += 1
+    check(cabi.lib().dfl_fc_dz(_p(dout), _p(W), _p(dz), B, W.shape[0], N, _dt(dout), 1 if accumulate else 0, _st()))
+
+
+def ae_loss_p(z, y_last, dz, loss_p, scale):
+    B, Z = z.shape
+    PROF.launches += 1
+    check(cabi.lib().dfl_ae_loss_p(_p(z), _p(y_last), _p(dz), _p(loss_p), B, Z, y_last.shape[1], scale, _st()))
 
 
 def conv3x3_wgrad(x, dpre, dw, db=None):
@@ -160,28 +233,6 @@ def conv3x3_wgrad(x, dpre, dw, db=None):
 def bias_grad(dpre, db):
     PROF.launches += 1
     check(cabi.lib().dfl_bias_grad(_p(dpre), _p(db), dpre.numel() // dpre.shape[-1], _st()))
-
-
-def lastconv_fwd(x, w, bias, out=None):
-    d, nd = _spatial(x)
-    cout = w.shape[-1]
-    if out is None:
-        out = torch.empty(x.shape[:-1] + (cout,), dtype=torch.float32, device=x.device)
-    PROF.launches += 1
-    check(cabi.lib().dfl_lastconv_fwd(_p(x), _p(w), _p(bias), _p(out), d, nd, cout, _st()))
-    return out
-
-
-def lastconv_dgrad(dout, w, mask_src=None, dx=None, dx_masked=None):
-    d, nd = _spatial(dout)
-    PROF.launches += 1
-    check(cabi.lib().dfl_lastconv_dgrad(_p(dout), _p(w), _p(mask_src), _p(dx), _p(dx_masked), d, nd, w.shape[-1], _st()))
-
-
-def lastconv_wgrad(x, dout, dw, db):
-    d, nd = _spatial(x)
-    PROF.launches += 1
-    check(cabi.lib().dfl_lastconv_wgrad(_p(x), _p(dout), _p(dw), _p(db), d, nd, dout.shape[-1], _st()))
 
 
 def pack_lastconv_weights(w, w16=None):

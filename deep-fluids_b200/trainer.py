@@ -79,9 +79,16 @@ class Trainer(object):
         self.world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
         self.rank = dist.get_rank() if self.world > 1 else 0
 
-        if 'ae' in self.arch:
-            raise NotImplementedError("arch 'ae' (BASELINE config 5) is the next SURVEY 8 row; not built in round 1")
-        self.build_model()
+        if 'ae' in self.arch:                       # trainer.py:88-96
+            self.z_num = config.z_num
+            self.p_num = self.batch_manager.dof
+            self.use_sparse = config.use_sparse
+            if self.use_sparse:
+                raise NotImplementedError("use_sparse (Bernoulli-KL on sigmoid(z), trainer.py:389-394) is off by default and not built")
+            self.w4 = config.w4
+            self.build_model_ae()
+        else:
+            self.build_model()
 
         if self.load_path and os.path.exists(os.path.join(self.load_path, "model.pt")):
             self.load(os.path.join(self.load_path, "model.pt"))
@@ -156,6 +163,8 @@ class Trainer(object):
         self._captured = True
 
     def train_step(self, x=None, y=None, want_vel=False):
+        if 'ae' in self.arch:
+            return self.train_step_ae(x, y)[0]
         if x is None:
             x, y = self.batch_manager.batch()
         self.x, self.y = x, y
@@ -224,8 +233,69 @@ class Trainer(object):
             self.save(os.path.join(self.model_dir, 'model.pt'))
         self.batch_manager.stop_thread()
 
+    # ------------------------------------------------------------------ auto-encoder (trainer.py:357-462, trainer3.py:240-345)
+    def build_model_ae(self):
+        from .encoder import AEEngine
+        if not self.is_3d and self.use_c:
+            raise NotImplementedError("2D AE with use_curl needs a 2-channel dL/d(output) from the stencil kernel; only the "
+                                      "3D AE (BASELINE config 5) is built")
+        if not self.use_c:
+            raise NotImplementedError("use_curl=False is not built")
+        if self.optimizer not in ('adam', 'gd'):
+            raise Exception("[!] Invalid opimizer")
+        x_shape = list(self.x.shape[1:])
+        self.ae = AEEngine(self.b_num, x_shape, self.filters, self.z_num, self.num_conv, self.repeat, "AE", self.device,
+                           self.config.random_seed)
+        self.engine = self.ae                        # checkpoint / DP code paths use `.engine.params`
+        self.var = self.ae.variables
+        self._loss3 = torch.zeros(3, dtype=torch.float32, device=self.device)
+        self._loss_p = torch.zeros(1, dtype=torch.float32, device=self.device)
+        self._dpot = torch.empty_like(self.ae.dec.pot)
+        nb = K.cabi.lib().dfl_stencil_loss_workspace_bytes(K.dims_array(self.x.shape[:-1]), self.x.dim() - 2)
+        self._ws = torch.empty(nb, dtype=torch.uint8, device=self.device)
+        self.use_graph = False
+        self._captured = False
+        self._xs = self._ys = None
+        self.loss = self.loss_l1 = self.loss_j_l1 = self.loss_p = None
+
+    def train_step_ae(self, x=None, y=None):
+        """one `sess.run(self.optim)` of the AE graph (trainer.py:437): s,z = AE(x); x_ = curl(s);
+        loss = w1*L1 + w2*L1(J) + w4*mean((y[:,:,-1] - z[:,-p_num:])^2)   (trainer.py:382-387)"""
+        if x is None:
+            x, y = self.batch_manager.batch()
+        self.x, self.y = x, y
+        ae = self.ae
+        y_last = y[:, :, -1].contiguous() if y.dim() == 3 else y[:, -self.p_num:].contiguous()
+        ae.zero_grad()
+        pot, z = ae.forward(x)
+        K.stencil_loss_fwdbwd(pot, x, self.w1, self.w2, 1.0, dpot=self._dpot, loss3=self._loss3, workspace=self._ws)
+        K.ae_loss_p(z, y_last, ae.dz, self._loss_p, self.w4)
+        ae.backward(self._dpot)
+        scale = dp.allreduce_grads_(ae.params.grad)
+        ae.optimizer_step(self.g_lr, self.optimizer == 'adam', self.beta1, self.beta2, 1e-8, scale)
+        self.step += 1
+        return self._loss3, self._loss_p
+
+    def losses_ae(self):
+        l = self._loss3.tolist()
+        lp = float(self._loss_p.item())
+        self.loss_l1, self.loss_j_l1, self.loss_p = l[1], l[2], lp
+        self.loss = l[0] + self.w4 * lp
+        return self.loss, l[1], l[2], lp
+
     def train_ae(self):
-        raise NotImplementedError("arch 'ae' is the next SURVEY 8 row")
+        for step in range(self.start_step, self.max_step):
+            self.train_step_ae()
+            if step % self.log_step == 0 or step == self.max_step - 1:
+                ep = step * self.batch_manager.epochs_per_step
+                loss = self.losses_ae()[0]
+                assert not np.isnan(loss), 'Model diverged with loss = NaN'      # trainer.py:444
+                if self.rank == 0:
+                    print("\n[{}/{}/ep{:.2f}] Loss: {:.6f}".format(step, self.max_step, ep, loss))
+            self.update_lr(step)
+        if self.model_dir and self.rank == 0:
+            self.save(os.path.join(self.model_dir, 'model.pt'))
+        self.batch_manager.stop_thread()
 
     # ------------------------------------------------------------------ inference (trainer.py:295-354, 750-771)
     def build_test_model(self):

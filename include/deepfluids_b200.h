@@ -34,6 +34,7 @@ extern "C" {
 /* conv epilogue flags */
 #define DFL_CONV_LRELU 1          /* y = max(v, 0.2 v)                      (ops.py:9-10)            */
 #define DFL_CONV_OUT2_UPSAMPLE 2  /* out2 is written nearest-x2 upsampled   (ops.py:75-91)          */
+#define DFL_CONV_MASK_AFTER_RESIDUAL 4 /* out2 = (v + residual) * lrelu'(mask_src) instead of v*lrelu' + residual */
 
 /* ---- lifecycle ------------------------------------------------------------------------------------- */
 int dfl_version(void);
@@ -97,16 +98,6 @@ int dfl_conv3x3_wgrad(const void* x, const void* dpre, float* dw, float* db, con
 /* db[c] += sum_p dpre[p][c]   (dpre bf16 [npos][128]) */
 int dfl_bias_grad(const void* dpre, float* db, size_t npos, void* stream);
 
-/* last conv 128 -> cout (1..3), no activation (model.py:42,84): x bf16, w fp32 [taps][128][cout], out fp32 */
-int dfl_lastconv_fwd(const void* x, const float* w, const float* bias, float* out, const int64_t* dims, int ndim,
-                     int cout, void* stream);
-/* dx = conv^T(dout, w) (bf16, may be NULL);  dx_masked = dx * lrelu'(mask_src) (bf16, may be NULL) */
-int dfl_lastconv_dgrad(const float* dout, const float* w, const void* mask_src, void* dx, void* dx_masked,
-                       const int64_t* dims, int ndim, int cout, void* stream);
-/* dw += x^T dout, db += sum dout  (fp32, accumulated) */
-int dfl_lastconv_wgrad(const void* x, const float* dout, float* dw, float* db, const int64_t* dims, int ndim,
-                       int cout, void* stream);
-
 /* Fused tensor-core backward of the output conv: ds = conv^T(dout, w) (bf16, may be NULL), ds_masked = ds *
  * lrelu'(mask_src) (bf16, may be NULL), dw += s^T (x) dout, db += sum dout (fp32, accumulated).  s = the conv's input
  * (bf16 [..,128]).  Replaces Conv*BackpropInput + Conv*BackpropFilter + BiasAddGrad of model.py:42,84. */
@@ -116,6 +107,43 @@ int dfl_lastconv_bwd(const void* s, const float* dout, const float* w, const voi
 /* adjoint of nearest-x2 upsampling fused with the lrelu derivative (model.py:35-36 / :77-78 backward):
  *   ds = sum of the 2x2(x2) children of g;  dmasked = ds * lrelu'(mask_src).  cdims = COARSE dims. */
 int dfl_pool_mask(const void* g, const void* mask_src, void* ds, void* dmasked, const int64_t* cdims, int ndim,
+                  void* stream);
+
+/* ---- encoder / auto-encoder extensions (EncoderBE/EncoderBE3, AE/AE3: model.py:118-216; trainer.py:357-396) ------
+ * Activations wider than 128 channels are stored as channel blocks [nblk*B,(D,)H,W,128] (block-major), so the concat
+ * of model.py:144,180 is free: producers write straight into their block.  dfl_conv3x3_fwd accepts such inputs
+ * (cin a multiple of 128). */
+/* forward operand with the input-channel count padded to cin_ld (first conv: 2/3 channels zero-padded to 128) */
+int dfl_pack_conv_weights_ex(const float* w, void* w_fwd, void* w_dgrad, int taps, int cin, int cout, int cin_ld,
+                             void* stream);
+/* Generic per-tap tensor-core convolution (one TMA box per tap): stride-2 convolutions (model.py:140,176; TMA element
+ * stride 2, TF SAME padding via the tap offsets), their data gradient (one launch per output parity class: tap subset +
+ * out_stride/out_off place the results on the fine grid) or any explicit tap list.  in_dims = {nblk*B,(D,)H,W} of the
+ * input, tile_dims = {B,(D,)H,W} of the tile domain, out_dims = {(D,)H,W} of the output tensor, taps = ntap x {dz,dy,dx,
+ * kcol}, w_ld = row length of the packed weight matrix whose 128 output rows start at w_packed.  Epilogue as
+ * dfl_conv3x3_fwd. */
+int dfl_conv_taps(const void* x, const void* w_packed, const float* bias, void* out, void* out2, const void* residual,
+                  const void* mask_src, const int64_t* in_dims, const int64_t* tile_dims, const int64_t* out_dims, int ndim,
+                  int cin, int in_stride, int ntap, const int32_t* taps, int out_stride, const int32_t* out_off,
+                  int64_t w_ld, int flags, void* stream);
+/* weight gradient of one (128-channel input block, 128-channel output block) pair; in_stride 2 samples x at
+ * 2p + tap - pad (stride-2 conv); element (tap, ci, co) is added at dw[tap*dw_tap_stride + ci*dw_row_stride + co]. */
+int dfl_conv_wgrad_ex(const void* x, const void* dpre, float* dw, float* db, const int64_t* x_dims, const int64_t* dims,
+                      int ndim, int in_stride, int pad, int dw_tap_stride, int dw_row_stride, void* stream);
+/* fp32 [n][cin] -> bf16 [n][128] with zero padding (encoder input) */
+int dfl_pad_cast(const float* in, void* out, size_t n, int cin, void* stream);
+/* out = (a + b) * lrelu'(y);  b, y may be NULL;  bf16, n % 8 == 0 */
+int dfl_add_mask(const void* a, const void* b, const void* y, void* out, size_t n, void* stream);
+/* encoder FC (model.py:149,185) on the channel-blocked concat tensor [nblk][B][V][128]: z = flat W + bias (Z<=16,B<=8)*/
+int dfl_enc_fc_fwd(const void* flat, const float* W, const float* bias, float* z, int B, int V, int nblk, int Z,
+                   void* stream);
+int dfl_enc_fc_bwd(const void* flat, const float* W, const float* dz, float* dW, float* db, void* dflat, int B, int V,
+                   int nblk, int Z, void* stream);
+/* decoder FC input gradient: dz[b][k] (+)= sum_n dout[b][n] W[k][n] */
+int dfl_fc_dz(const void* dout, const float* W, float* dz, int B, int K, int N, int dout_dtype, int accumulate,
+              void* stream);
+/* AE parameter loss (trainer.py:385-387): loss_p = mean((y - z[:, Z-P:])^2); dz = scale * d loss_p / dz */
+int dfl_ae_loss_p(const float* z, const float* y, float* dz, float* loss_p, int B, int Z, int P, float scale,
                   void* stream);
 
 /* ---- optimizer (tf.train.AdamOptimizer / GradientDescentOptimizer: trainer.py:160-165) ----------------- */

@@ -260,34 +260,6 @@ def test_fc_fwd_bwd(B, K_, N):
     assert rel_l2(db, dout.float().sum(0)) <= 1e-5
 
 
-@pytest.mark.parametrize("shape,nd,cout", [((2, 4, 6, 11), 3, 3), ((1, 8, 8, 8), 3, 3), ((3, 16, 12), 2, 1), ((2, 9, 21), 2, 2)])
-def test_lastconv_fwd_dgrad_wgrad(shape, nd, cout):
-    from deepfluids_b200 import kernels as K
-    g = torch.Generator().manual_seed(40)
-    x = (torch.randn(*shape, 128, generator=g) * 0.5).bfloat16()
-    w = R.xavier_uniform_((3,) * nd + (128, cout), g)
-    b = torch.randn(cout, generator=g) * 0.1
-    xin = x.float().requires_grad_(True)
-    wt = w.clone().requires_grad_(True)
-    bt = b.clone().requires_grad_(True)
-    y = R.conv_nd(xin, wt, bt, 1, None)
-    dy = torch.randn(y.shape, generator=g)
-    gx, gw, gb = torch.autograd.grad(y, [xin, wt, bt], dy)
-    out = K.lastconv_fwd(x.to(dev()), w.to(dev()), b.to(dev()))
-    assert rel_l2(out, y.detach()) <= 1e-5
-    mask_src = torch.randn(*shape, 128, generator=g).bfloat16()
-    dx = torch.empty(x.shape, dtype=torch.bfloat16, device=dev())
-    dxm = torch.empty_like(dx)
-    K.lastconv_dgrad(dy.to(dev()), w.to(dev()), mask_src.to(dev()), dx, dxm)
-    assert rel_l2(dx.float(), gx) <= 4e-3
-    assert rel_l2(dxm.float(), gx * torch.where(mask_src.float() >= 0, 1.0, 0.2)) <= 4e-3
-    dw = torch.zeros(w.shape, device=dev())
-    db = torch.zeros(cout, device=dev())
-    K.lastconv_wgrad(x.to(dev()), dy.to(dev()), dw, db)
-    assert rel_l2(dw, gw) <= 1e-5
-    assert rel_l2(db, gb) <= 1e-5
-
-
 @pytest.mark.parametrize("shape,nd,cout", [((2, 4, 6, 11), 3, 3), ((1, 8, 8, 8), 3, 3), ((1, 5, 20, 37), 3, 1), ((3, 16, 12), 2, 1),
                                            ((2, 9, 21), 2, 2), ((2, 40, 33), 2, 3)])
 def test_lastconv_tensorcore_fwd_and_fused_bwd(shape, nd, cout):
