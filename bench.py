@@ -14,6 +14,7 @@ A "step" = one pass of the hot path over one batch of synthetic input = one `ses
 import argparse
 import json
 import math
+import numpy as np
 import os
 import subprocess
 import sys
@@ -32,10 +33,12 @@ WORKLOADS = {
     "c2": (False, 1, 128, 96, 64, "2D smoke_pos_size 128x96 generator+curl, batch 64/GPU (BASELINE configs[1])"),
     "c3": (True, 64, 64, 64, 16, "3D smoke3_vel_buo 64^3 generator+curl, batch 16/GPU (BASELINE configs[2])"),
     "c4": (True, 128, 128, 128, 4, "3D smoke3_vel_buo 128^3 generator+curl+grad-loss, batch 4/GPU (BASELINE configs[3])"),
+    "c5": (True, 128, 128, 128, 4, "3D AE 128^3 encoder-decoder (arch=ae), batch 4/GPU (BASELINE configs[4])"),
     "tiny": (False, 1, 32, 24, 4, "2D 32x24 plumbing check"),
 }
+ARCH = {"c5": "ae"}
 # algorithmic conv FLOPs per field, fwd+bwd
-FLOPS_PER_FIELD = {"c2": 58.0e9, "c3": 3196.0e9, "c4": 25575.0e9, "tiny": None}
+FLOPS_PER_FIELD = {"c2": 58.0e9, "c3": 3196.0e9, "c4": 25575.0e9, "c5": 49471.0e9, "tiny": None}
 
 
 def load_peaks():
@@ -93,7 +96,7 @@ def make_config(workload, extra=()):
     from deepfluids_b200 import config as C
     is3d, rz, ry, rx, b, _ = WORKLOADS[workload]
     argv = ["--synthetic=true", "--is_3d=%s" % ("true" if is3d else "false"), "--res_x=%d" % rx, "--res_y=%d" % ry,
-            "--res_z=%d" % rz, "--batch_size=%d" % b, "--max_step=1000000"] + list(extra)
+            "--res_z=%d" % rz, "--batch_size=%d" % b, "--max_step=1000000", "--arch=%s" % ARCH.get(workload, "de")] + list(extra)
     cfg, _ = C.get_config(argv)
     return cfg
 
@@ -116,15 +119,24 @@ def cpu_oracle_fields_per_sec(workload, steps, warmup, budget_s=25.0):
     # bounded sample: batch sized for ~2 s per step at ~0.5 TFLOP/s, at least 1 field
     b = max(1, min(8, int(2.0 * 0.5e12 / flops)))
     cout = 3 if is3d else 1
-    tab, _, _ = M.generator_layout(spatial + [cout])
+    is_ae = ARCH.get(workload) == "ae"
+    if is_ae:
+        tab = M.ae_layout(spatial + [cout])
+        warmup = 0                      # one 128^3 AE step is ~50 TFLOP: a single timed step is the bounded sample
+    else:
+        tab, _, _ = M.generator_layout(spatial + [cout])
     var = M.init_variables(tab, 123)
     opt = T.TFAdam(var, 0.5, 0.999)
     x, y = T.synthetic_batch(b, spatial, seed=123)
+    ylast = torch.rand(b, 2) * 2 - 1
     times = []
     t_begin = time.time()
     for i in range(warmup + steps):
         t0 = time.time()
-        loss, _, _, _, _, grads = T.generator_loss_and_grads(y, x, var)
+        if is_ae:
+            grads = T.ae_loss_and_grads(x, ylast, var, 2)[-1]
+        else:
+            loss, _, _, _, _, grads = T.generator_loss_and_grads(y, x, var)
         opt.step(var, grads, 1e-4)
         dt = time.time() - t0
         if i >= warmup:
@@ -254,6 +266,10 @@ def run_gpu_arm(args):
         a[1] += work
         a[2] += 1
     K.PROF.events = None
+    for extra in ("conv_tap",):           # stride-2 / per-tap launches count as conv work too (AE)
+        if extra in agg:
+            a, e = agg.setdefault("conv_tc", [0.0, 0.0, 0]), agg[extra]
+            a[0] += e[0]; a[1] += e[1]; a[2] += e[2]
     conv_t, conv_f, conv_n = agg.get("conv_tc", [1e-9, 0.0, 1])
     wg_t, wg_f, wg_n = agg.get("wgrad_tc", [1e-9, 0.0, 1])
     st_t, st_b, st_n = agg.get("stencil_fused", [1e-9, 0.0, 1])
@@ -283,7 +299,7 @@ def run_gpu_arm(args):
                "config": {"workload": WORKLOADS[args.workload][5], "global_batch": B * world, "per_gpu_batch": B,
                           "parallelism": "dp%d" % world, "filters": 128, "num_conv": 4,
                           "l2": "per-step working set (>= %.0f MB of activations) exceeds the 126 MB L2; no flush needed"
-                                % (tr.engine.x0[-1].numel() * 2 * 6 / 1e6),
+                                % (B * float(np.prod(bm._pool[0][0].shape[1:-1])) * 128 * 2 * 6 / 1e6),
                           "precision": "bf16 operands/activations, fp32 accumulate (TMEM), fp32 master weights + Adam"},
                "clocks": clocks, "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d,
                                          "d2h_bytes_per_step": 12, "ms_per_step": ms_e / args.steps},
