@@ -22,6 +22,7 @@ SIGNATURES = {
     "dfl_divergence": (_i, [_vp, _vp, _dims, _i, _i, _vp]),
     "dfl_stencil_loss_workspace_bytes": (_sz, [_dims, _i]),
     "dfl_stencil_loss_fwdbwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _dims, _i, _i, _f, _f, _f, _i, _i, _vp]),
+    "dfl_stencil_loss_fwdbwd_ex": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _dims, _i, _i, _i, _f, _f, _f, _i, _i, _vp]),
     "dfl_fc_fwd": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
     "dfl_fc_bwd": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
     "dfl_pack_conv_weights": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp]),

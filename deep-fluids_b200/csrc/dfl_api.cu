@@ -58,7 +58,7 @@ int encode_tensor_map(CUtensorMap* out, CUtensorMapDataType dt, int rank, const 
 size_t stencil_loss_workspace_bytes(int nd, const int64_t* dims);
 int stencil_loss_fwdbwd(int nd, const int64_t* dims, const void* pot, int pot_channels, const void* x, void* dpot,
                         void* vel, float* loss3, void* workspace, float w1, float w2, float grad_scale, int dt_pot,
-                        int dt_x, cudaStream_t st);
+                        int dt_x, int dpot_channels, cudaStream_t st);
 int fwd_stencils(int op, int nd, const int64_t* dims, const void* in, int in_cs, void* out0, void* out1, int dtype,
                  cudaStream_t st);
 int conv_tc_launch(const void* x, const void* w_packed, const float* bias, void* out, void* out2,
@@ -145,7 +145,13 @@ int dfl_stencil_loss_fwdbwd(const void* pot, const void* x, void* dpot, void* ve
                             const int64_t* dims, int ndim, int pot_channels, float w1, float w2, float grad_scale,
                             int dtype_pot, int dtype_x, void* stream) {
   return stencil_loss_fwdbwd(ndim, dims, pot, pot_channels, x, dpot, vel, loss3, workspace, w1, w2, grad_scale,
-                             dtype_pot, dtype_x, ST(stream));
+                             dtype_pot, dtype_x, 0, ST(stream));
+}
+int dfl_stencil_loss_fwdbwd_ex(const void* pot, const void* x, void* dpot, void* vel, float* loss3, void* workspace,
+                               const int64_t* dims, int ndim, int pot_channels, int dpot_channels, float w1, float w2,
+                               float grad_scale, int dtype_pot, int dtype_x, void* stream) {
+  return stencil_loss_fwdbwd(ndim, dims, pot, pot_channels, x, dpot, vel, loss3, workspace, w1, w2, grad_scale,
+                             dtype_pot, dtype_x, dpot_channels, ST(stream));
 }
 int dfl_fc_fwd(const float* z, const float* W, const float* bias, void* out, int B, int K, int N, int out_dtype,
                void* stream) {

@@ -34,6 +34,7 @@ __device__ __forceinline__ float foldv(float g0, float g1, int k, int n) {
 struct StencilParams {
   int B, D, H, W;       // D == 1 for 2D
   int pot_cs;           // channel stride (number of channels) of the potential tensor
+  int dpot_cs;          // channel stride of the gradient tensor (2D: 1, or pot_cs when the caller wants a full-shape gradient)
   float c1, c2;         // w1/N1 * grad_scale, w2/N2 * grad_scale
   int zseg;             // z planes per block (3D)
   int tiles_x, tiles_y, nseg;
@@ -324,7 +325,8 @@ stencil2d_fused_kernel(const TP* __restrict__ pot, const TX_* __restrict__ xt, T
     // d psi = D_y^T gU - D_x^T gV'   with v = -(D_x psi)  =>  d psi = D_y^T gU - D_x^T gV
     const float dyT_U = foldv(sD[jm][i][0], sD[j][i][0], cy - 1, H) - foldv(sD[j][i][0], sD[jp][i][0], cy, H);
     const float dxT_V = foldv(sD[j][im][1], sD[j][i][1], cx - 1, W) - foldv(sD[j][i][1], sD[j][ip][1], cx, W);
-    stf(dpot + pix, dyT_U - dxT_V);
+    stf(dpot + pix * p.dpot_cs, dyT_U - dxT_V);
+    for (int c = 1; c < p.dpot_cs; ++c) stf(dpot + pix * p.dpot_cs + c, 0.f);   // unused output channels (2D AE)
   }
   acc_l1 = warp_sum(acc_l1);
   acc_j = warp_sum(acc_j);
@@ -532,13 +534,15 @@ static int stencil_launch_typed(int nd, const void* pot, const void* x, void* dp
 
 int stencil_loss_fwdbwd(int nd, const int64_t* dims, const void* pot, int pot_channels, const void* x, void* dpot,
                         void* vel, float* loss3, void* workspace, float w1, float w2, float grad_scale, int dt_pot,
-                        int dt_x, cudaStream_t st) {
+                        int dt_x, int dpot_channels, cudaStream_t st) {
   DFL_REQUIRE(nd == 2 || nd == 3, "stencil_loss: ndim must be 2 or 3 (got %d)", nd);
   StencilParams p{};
   stencil_plan(nd, dims, p);
   DFL_REQUIRE(p.H >= 2 && p.W >= 2 && (nd == 2 || p.D >= 2), "stencil_loss: every spatial extent must be >= 2");
   DFL_REQUIRE(pot_channels >= (nd == 3 ? 3 : 1), "stencil_loss: potential needs >= %d channels", nd == 3 ? 3 : 1);
   p.pot_cs = pot_channels;
+  p.dpot_cs = (nd == 2) ? (dpot_channels > 0 ? dpot_channels : 1) : 3;
+  DFL_REQUIRE(nd == 2 || pot_channels == 3, "stencil_loss (3D): the potential must have exactly 3 channels");
   const double vox = static_cast<double>(p.B) * p.D * p.H * p.W;
   const double n1 = vox * nd, n2 = vox * nd * nd;
   p.c1 = static_cast<float>(static_cast<double>(w1) * grad_scale / n1);

@@ -86,7 +86,8 @@ def divergence(vel):
 
 
 def stencil_loss_fwdbwd(pot, x, w1=1.0, w2=1.0, grad_scale=1.0, want_vel=False, dpot=None, loss3=None, workspace=None):
-    """-> (loss3 [total,l1,jl1] float32 device tensor, dpot, vel|None)"""
+    """-> (loss3 [total,l1,jl1] float32 device tensor, dpot, vel|None).  If `dpot` is given with more than one channel in
+    2D, the gradient is written full-shape (channel 0 = d/d psi, the rest 0)."""
     d, nd = _spatial(x)
     l = cabi.lib()
     nb = l.dfl_stencil_loss_workspace_bytes(d, nd)
@@ -101,9 +102,9 @@ def stencil_loss_fwdbwd(pot, x, w1=1.0, w2=1.0, grad_scale=1.0, want_vel=False, 
     work = nvox * (pot.shape[-1] * pot.element_size() + x.shape[-1] * x.element_size()
                    + dpot.shape[-1] * dpot.element_size())          # algorithmic bytes: read pot + x, write dpot
     PROF.launches += 1                                              # + the tiny finalize kernel
-    PROF.timed("stencil_fused", work, lambda: check(l.dfl_stencil_loss_fwdbwd(
-        _p(pot), _p(x), _p(dpot), _p(vel), _p(loss3), _p(workspace), d, nd, pot.shape[-1], w1, w2, grad_scale,
-        _dt(pot), _dt(x), _st())))
+    PROF.timed("stencil_fused", work, lambda: check(l.dfl_stencil_loss_fwdbwd_ex(
+        _p(pot), _p(x), _p(dpot), _p(vel), _p(loss3), _p(workspace), d, nd, pot.shape[-1], dpot.shape[-1], w1, w2,
+        grad_scale, _dt(pot), _dt(x), _st())))
     return loss3, dpot, vel
 
 

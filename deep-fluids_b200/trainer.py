@@ -236,9 +236,6 @@ class Trainer(object):
     # ------------------------------------------------------------------ auto-encoder (trainer.py:357-462, trainer3.py:240-345)
     def build_model_ae(self):
         from .encoder import AEEngine
-        if not self.is_3d and self.use_c:
-            raise NotImplementedError("2D AE with use_curl needs a 2-channel dL/d(output) from the stencil kernel; only the "
-                                      "3D AE (BASELINE config 5) is built")
         if not self.use_c:
             raise NotImplementedError("use_curl=False is not built")
         if self.optimizer not in ('adam', 'gd'):

@@ -68,6 +68,12 @@ int dfl_stencil_loss_fwdbwd(const void* pot, const void* x, void* dpot, void* ve
                             const int64_t* dims, int ndim, int pot_channels, float w1, float w2, float grad_scale,
                             int dtype_pot, int dtype_x, void* stream);
 
+/* same; the 2D gradient is written with `dpot_channels` channels (channel 0 = d/d psi, the others 0) so it can feed a
+ * network whose output has more than one channel (2D AE with use_curl: trainer.py:359-361 curls channel 0 only). */
+int dfl_stencil_loss_fwdbwd_ex(const void* pot, const void* x, void* dpot, void* vel, float* loss3, void* workspace,
+                               const int64_t* dims, int ndim, int pot_channels, int dpot_channels, float w1, float w2,
+                               float grad_scale, int dtype_pot, int dtype_x, void* stream);
+
 /* ---- fully connected (slim.fully_connected, activation None: ops.py:23-24, model.py:19,61) ------------ */
 /* out[b,n] = sum_k z[b,k] W[k,n] + bias[n];  z,W,bias fp32 (W in TF [in,out] layout), K <= 16, B <= 64. */
 int dfl_fc_fwd(const float* z, const float* W, const float* bias, void* out, int B, int K, int N, int out_dtype,

@@ -228,6 +228,32 @@ def test_ae_step_vs_oracle():
         assert torch.isfinite(ae.params.g(k)).all(), k
 
 
+def test_ae2d_step_vs_oracle():
+    """2D AE with use_curl (trainer.py:357-396): the decoder emits 2 channels, curl reads channel 0 only"""
+    from deepfluids_b200 import kernels as K
+    from deepfluids_b200.encoder import AEEngine
+    spatial, B, nc = [32, 24], 2, 2
+    ae = AEEngine(B, spatial + [2], z_num=16, num_conv=nc, device=dev(), seed=5)
+    var = ae.params.state_dict()
+    assert list(var.keys()) == list(M.ae_layout(spatial + [2], num_conv=nc).keys())
+    x, _ = T.synthetic_batch(B, spatial, seed=8)
+    ylast = torch.rand(B, 2, generator=torch.Generator().manual_seed(2)) * 2 - 1
+    total, l1, jl1, lp, g, zref, grads = T.ae_loss_and_grads(x, ylast, var, 2, num_conv=nc)
+    ae.zero_grad()
+    pot, z = ae.forward(x.to(dev()))
+    dpot = torch.empty_like(pot)
+    loss3, _, _ = K.stencil_loss_fwdbwd(pot, x.to(dev()), dpot=dpot)
+    assert float(dpot[..., 1].abs().max()) == 0.0
+    lpd = torch.empty(1, device=dev())
+    K.ae_loss_p(z, ylast.to(dev()), ae.dz, lpd, 1.0)
+    ae.backward(dpot)
+    assert rel_l2(z, zref) <= 2e-2
+    assert abs(loss3[0].item() + lpd.item() - total.item()) <= 1e-2 * abs(total.item())
+    errs = {k: rel_l2(ae.params.g(k), grads[k]) for k in var if k.endswith("weights")}
+    worst = max(errs, key=errs.get)
+    assert errs[worst] <= 2.5e-1, (worst, errs[worst])
+
+
 def test_trainer_ae_api_runs_and_loss_decreases():
     from deepfluids_b200 import config as C
     from deepfluids_b200.data import BatchManager
