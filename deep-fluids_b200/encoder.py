@@ -109,7 +109,6 @@ class EncoderEngine(object):
         self.DS = [torch.empty([(self.nblk[i] - 1) * B] + self.res[i] + [128], **bf) for i in range(self.rep)]
         self._dp = [torch.empty([B] + self.res[0] + [128], **bf) for _ in range(2)]
         self._dw_e0 = torch.zeros(self.taps, 128, 128, dtype=torch.float32, device=self.device)
-        self._db_dummy = torch.zeros(128, dtype=torch.float32, device=self.device)
 
     # ------------------------------------------------------------------ helpers
     def _blk(self, t, i, n=1):

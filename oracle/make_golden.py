@@ -100,6 +100,15 @@ def main(reference_root="/root/reference", out_dir=os.path.join(ROOT, "tests", "
                         div_of_curl=_np(d3_ref), upscale3=_np(u3_ref),
                         x=_np(x3), loss=np.float32(loss.item()), loss_l1=np.float32(l1.item()),
                         loss_j_l1=np.float32(jl1.item()), dA=_np(dA))
+    # ---------------- boundary: the reference's flag surface (config.py:16-70), names and defaults ----------------
+    import importlib.util
+    import json
+    spec = importlib.util.spec_from_file_location("_dfl_reference_config", reference_root + "/config.py")
+    cfgmod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(cfgmod)
+    ref_cfg, _ = cfgmod.parser.parse_known_args([])
+    with open(os.path.join(out_dir, "reference_config_defaults.json"), "w") as f:
+        json.dump(dict(sorted(vars(ref_cfg).items())), f, indent=1)
     print("golden fixtures written to", out_dir)
 
 

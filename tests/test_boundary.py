@@ -1,0 +1,37 @@
+"""CPU tests of the drop-in boundary's host logic: the flag surface equals the reference's (golden generated from
+/root/reference/config.py by oracle/make_golden.py), unknown flags are tolerated (config.py:73 parse_known_args), the
+error behaviour of main()/Trainer mirrors main.py:29-30 / trainer.py:80,167."""
+import json
+import os
+
+import pytest
+
+from deepfluids_b200 import config as C
+
+
+def test_flag_names_and_defaults_match_reference(golden_dir):
+    ref = json.load(open(os.path.join(golden_dir, "reference_config_defaults.json")))
+    cfg, unparsed = C.get_config([])
+    mine = vars(cfg)
+    for k, v in ref.items():
+        assert k in mine, "missing reference flag --%s" % k
+        assert mine[k] == v, (k, mine[k], v)
+    extra = set(mine) - set(ref)
+    assert extra == {"synthetic", "synthetic_samples", "max_step"}       # new knobs are optional, defaults inert
+    assert cfg.synthetic is False and cfg.max_step == 0
+
+
+def test_unknown_flags_are_tolerated_like_the_reference():
+    # run.bat:56 passes `--filter=64`; argparse prefix matching + parse_known_args make that legal in the reference
+    cfg, unparsed = C.get_config(["--filter=64", "--not_a_flag=1", "--is_3d=True"])
+    assert cfg.filters == 64 and cfg.is_3d is True and "--not_a_flag=1" in unparsed
+
+
+def test_str2bool():
+    assert C.str2bool("True") and C.str2bool("1") and not C.str2bool("no")
+
+
+def test_main_requires_load_path_for_test_mode(tmp_path, monkeypatch):
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip("main() needs the B200 path; the control-flow check runs on the GPU box")
