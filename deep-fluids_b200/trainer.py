@@ -139,15 +139,17 @@ class Trainer(object):
         scale = 1.0 / self.world
         # one eager pass on a side stream: sets every kernel's attributes, warms allocator (grad buffers stay zeroed
         # at the end because lr = 0 leaves the weights untouched)
+        m0, v0 = self.engine.params.m.clone(), self.engine.params.v.clone()   # (a resumed run has non-zero moments)
         side = torch.cuda.Stream(device=self.device)
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):
             self._step_body_a(self._xs, self._ys)
-            self._step_body_b(scale)          # lr_dev == 0 -> parameters unchanged; Adam moments are reset below
+            self._step_body_b(scale)          # lr_dev == 0 -> parameters unchanged; Adam moments are restored below
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
-        self.engine.params.m.zero_()
-        self.engine.params.v.zero_()
+        self.engine.params.m.copy_(m0)
+        self.engine.params.v.copy_(v0)
+        del m0, v0
         l0 = K.PROF.launches
         self._graph_a = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self._graph_a):

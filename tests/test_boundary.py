@@ -4,8 +4,6 @@ error behaviour of main()/Trainer mirrors main.py:29-30 / trainer.py:80,167."""
 import json
 import os
 
-import pytest
-
 from deepfluids_b200 import config as C
 
 
@@ -29,9 +27,3 @@ def test_unknown_flags_are_tolerated_like_the_reference():
 
 def test_str2bool():
     assert C.str2bool("True") and C.str2bool("1") and not C.str2bool("no")
-
-
-def test_main_requires_load_path_for_test_mode(tmp_path, monkeypatch):
-    import torch
-    if not torch.cuda.is_available():
-        pytest.skip("main() needs the B200 path; the control-flow check runs on the GPU box")

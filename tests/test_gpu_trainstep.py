@@ -3,6 +3,7 @@
 bf16 path tolerances (operands/activations bf16, fp32 accumulate, fp32 master weights): rel-L2 <= 2e-2 on the
 potential and on every gradient tensor, loss within 1e-2 relative (SURVEY 8c proposal); Adam update compared on the
 fp32 parameters after 2 steps."""
+import os
 from collections import OrderedDict
 
 import numpy as np
@@ -142,3 +143,57 @@ def test_inference_path_matches_training_forward(tmp_path):
     d = np.load(out_dir + "/199.npz")["x"]
     assert d.shape == (32, 24, 2) and np.isfinite(d).all()
     assert float(K.divergence(torch.from_numpy(d[None]).cuda()).abs().max()) <= 1e-5
+
+
+@pytest.mark.parametrize("spatial,B", [([128, 96], 2), ([32, 64, 112], 1)])
+def test_reference_recipe_shapes(spatial, B):
+    """The reference's own recipes at full network size (filters 128, num_conv 4): the default 2D 128x96 field
+    (config.py:17-22, run.bat:13) and the 3D smoke recipe 112x64x32 (run.bat:21; W = 112 is not a power of two, first
+    layer 14x8x4).  Potential / loss vs the fp32 oracle; backward kernels vs the teacher-forced oracle."""
+    from deepfluids_b200 import kernels as K
+    from deepfluids_b200.engine import GeneratorEngine
+    dev = torch.device("cuda:0")
+    nd = len(spatial)
+    cout = 3 if nd == 3 else 1
+    eng = GeneratorEngine(B, spatial + [cout], z_dim=3, num_conv=4, device=dev, seed=21)
+    assert eng.level_shape[0] == ([8, 6] if nd == 2 else [4, 8, 14])
+    x, y = T.synthetic_batch(B, spatial, seed=13)
+    pot = eng.forward(y.to(dev))
+    loss3, dpot, vel = K.stencil_loss_fwdbwd(pot, x.to(dev), want_vel=True)
+    eng.zero_grad()
+    eng.backward(dpot)
+    var = eng.params.state_dict()
+    pot_ref = M.generator_forward(y, var, spatial + [cout], num_conv=4)
+    loss_ref = T.stencil_loss(pot_ref, x)[0]
+    assert rel_l2(pot, pot_ref) <= 2e-2
+    assert abs(loss3[0].item() - loss_ref.item()) <= 1e-2 * abs(loss_ref.item())
+    assert float(K.divergence(vel).abs().max()) <= 1e-5
+    acts = {"x0": [t.float().cpu() for t in eng.x0], "y": [[t.float().cpu() for t in row] for row in eng.y],
+            "s": eng.s.float().cpu()}
+    tf_grads = T.teacher_forced_backward(y, var, acts, dpot.cpu(), num_conv=4, operand_round=M.bf16_round_ste)
+    worst = max(rel_l2(eng.params.g(k), tf_grads[k]) for k in var if k.endswith("weights"))
+    assert worst <= 2e-2, worst
+
+
+def test_main_control_flow_and_errors(tmp_path, monkeypatch):
+    """main.py:10-31: train mode builds dirs / params.json and trains; test mode without load_path raises."""
+    from deepfluids_b200 import config as C
+    from deepfluids_b200.main import main
+    monkeypatch.chdir(tmp_path)
+    cfg, _ = C.get_config(["--synthetic=true", "--res_x=24", "--res_y=32", "--batch_size=2", "--num_conv=1",
+                           "--max_step=3", "--log_step=1"])
+    tr = main(cfg)
+    assert tr.step == 3 and os.path.exists(os.path.join(cfg.model_dir, "params.json"))
+    assert os.path.exists(os.path.join(cfg.model_dir, "model.pt"))
+    cfg2, _ = C.get_config(["--synthetic=true", "--res_x=24", "--res_y=32", "--batch_size=2", "--num_conv=1",
+                            "--is_train=false"])
+    with pytest.raises(Exception, match="load_path"):
+        main(cfg2)
+    # resume from the checkpoint (load_path sets model_dir, util.py:37-38)
+    cfg3, _ = C.get_config(["--synthetic=true", "--res_x=24", "--res_y=32", "--batch_size=2", "--num_conv=1",
+                            "--max_step=5", "--load_path=" + cfg.model_dir, "--start_step=3"])
+    tr3 = main(cfg3)
+    assert tr3.step == 5 and tr3.engine.adam_t == 5
+    cfg4, _ = C.get_config(["--synthetic=true", "--optimizer=foo", "--res_x=24", "--res_y=32", "--batch_size=2"])
+    with pytest.raises(Exception, match="Invalid opimizer"):
+        main(cfg4)
