@@ -36,12 +36,13 @@ struct WgradParams {
   int in_stride;      // 1, or 2 for the weight gradient of a stride-2 convolution (X sampled at 2p + tap - pad)
   int pad;            // tap offset = tap index - pad   (1 for SAME stride 1; pad_before of TF SAME for stride 2)
   int dw_tap_stride, dw_row_stride;   // TF layout [taps][Cin][Cout]: Cin*Cout and Cout
-  // brick mode (stride 1, bw >= 8): ONE x-halo'd brick of X per (dz,dy) group and tile; the three dx taps are row-shifted
-  // descriptor windows over it (A traffic / 2.7)
+  // brick mode (stride 1, bw >= 8): ONE y-halo'd brick of X per (dz,dx) group and tile; the three dy taps are descriptor
+  // windows shifted by whole x-lines (bw rows = a multiple of 1024 B, so every window stays swizzle-atom aligned: an
+  // x-halo variant whose windows start on arbitrary rows measured 2x SLOWER MMAs for these MN-major operands)
   int brick;
   int a_half;         // bytes between the two 64-channel halves of a brick (1024-aligned)
 };
-constexpr int WG_BRICK_SLOT = 40960;      // >= 2 * bd*bh*(bw+2)*128 for every tile shape pick_brick_w produces
+constexpr int WG_BRICK_SLOT = 40960;      // >= 2 * bd*(bh+2)*bw*128 for the tile shapes that use brick mode
 constexpr int WG_BRICK_SLOTS = 3;
 
 __global__ void __launch_bounds__(WG_THREADS, 1)
@@ -108,13 +109,13 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
             tma_load_5d(sB + s * WG_OP_BYTES + WG_OP_BYTES / 2, &tmP, &b_full[s], 64, x0, y0, z0, b);
           }
           if (p.brick) {
-            const int dy = (tap0 / p.kw) % p.kh, dz = tap0 / (p.kw * p.kh);
+            const int dx = group % 3, dz = group / 3;
             const uint32_t s = ia % WG_BRICK_SLOTS, ph = (ia / WG_BRICK_SLOTS) & 1;
             mbar_wait(&a_empty[s], ph ^ 1);
-            mbar_expect_tx(&a_full[s], 2 * p.bd * p.bh * (p.bw + 2) * 128);
-            const int ys = y0 + dy - p.pad, zs = (p.kd > 1) ? z0 + dz - p.pad : 0;
-            tma_load_5d(sA + s * WG_BRICK_SLOT, &tmX, &a_full[s], 0, x0 - p.pad, ys, zs, b);
-            tma_load_5d(sA + s * WG_BRICK_SLOT + p.a_half, &tmX, &a_full[s], 64, x0 - p.pad, ys, zs, b);
+            mbar_expect_tx(&a_full[s], 2 * p.bd * (p.bh + 2) * p.bw * 128);
+            const int xs = x0 + dx - p.pad, zs = (p.kd > 1) ? z0 + dz - p.pad : 0;
+            tma_load_5d(sA + s * WG_BRICK_SLOT, &tmX, &a_full[s], 0, xs, y0 - p.pad, zs, b);
+            tma_load_5d(sA + s * WG_BRICK_SLOT + p.a_half, &tmX, &a_full[s], 64, xs, y0 - p.pad, zs, b);
             ++ia;
           } else
           for (int t = 0; t < gtaps; ++t, ++ia) {
@@ -144,14 +145,13 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
             mbar_wait(&a_full[s], ph);
             tc_fence_after();
             const uint32_t sa = smem_u32(sA + s * WG_BRICK_SLOT);
-            const int pitch = p.bw + 2;                                   // brick rows per x-line
-            const uint32_t sbo = (p.bw >= 16) ? 1024u : static_cast<uint32_t>(pitch * 128);
-            for (int t = 0; t < gtaps; ++t) {                             // t = dx
+            for (int t = 0; t < gtaps; ++t) {                             // t = dy
 #pragma unroll
               for (int k = 0; k < WG_TILE_K / 16; ++k) {
                 const int v = k * 16;                                     // first voxel of this K step (x fastest)
-                const uint32_t row0 = static_cast<uint32_t>((v / p.bw) * pitch + (v % p.bw) + t);
-                umma_bf16(tmem_base + t * 128, umma_desc_sw128(sa + row0 * 128, p.a_half, sbo),
+                const int l = v / p.bw, xoff = v % p.bw;                  // tile line (lz*bh + ly) and x offset
+                const uint32_t row0 = static_cast<uint32_t>((((l / p.bh) * (p.bh + 2) + (l % p.bh) + t) * p.bw) + xoff);
+                umma_bf16(tmem_base + t * 128, umma_desc_sw128(sa + row0 * 128, p.a_half, 1024),
                           umma_desc_sw128(sb + k * 2048, WG_OP_BYTES / 2, 1024), idesc, (tile != t_begin || k != 0) ? 1u : 0u);
               }
             }
@@ -190,7 +190,8 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
       mbar_wait(acc_full, 0);
       tc_fence_after();
       for (int t = 0; t < gtaps; ++t) {
-        float* dst = p.dw + static_cast<size_t>(tap0 + t) * p.dw_tap_stride + static_cast<size_t>(ci) * p.dw_row_stride;
+        const int tap = p.brick ? ((group / 3) * 3 + t) * 3 + (group % 3) : tap0 + t;   // brick: group = (dz,dx), t = dy
+        float* dst = p.dw + static_cast<size_t>(tap) * p.dw_tap_stride + static_cast<size_t>(ci) * p.dw_row_stride;
 #pragma unroll 1
         for (int c0 = 0; c0 < 128; c0 += 32) {
           uint32_t rr[32];
@@ -256,9 +257,9 @@ int wgrad_tc_launch(const void* x, const void* dpre, float* dw, float* db, const
   p.tz = (p.D + p.bd - 1) / p.bd;
   p.ntiles = p.B * p.tz * p.ty * p.tx;
   const int ntaps = p.kd * p.kh * p.kw;
-  p.brick = (in_stride == 1 && p.bw >= 8 && (p.bw == 8 || p.bw % 16 == 0) &&
-             2 * ((p.bd * p.bh * (p.bw + 2) * 128 + 1023) / 1024 * 1024) <= WG_BRICK_SLOT) ? 1 : 0;
-  p.a_half = (p.bd * p.bh * (p.bw + 2) * 128 + 1023) / 1024 * 1024;
+  p.brick = (in_stride == 1 && (p.bw == 8 || p.bw % 16 == 0) && (p.bw >= 16 || p.bh % 2 == 0) &&
+             2 * p.bd * (p.bh + 2) * p.bw * 128 <= WG_BRICK_SLOT) ? 1 : 0;
+  p.a_half = p.bd * (p.bh + 2) * p.bw * 128;      // rows * 128 B; bw is a multiple of 8 -> 1024-aligned
   p.taps_per_group = p.brick ? 3 : ((nd == 3) ? 4 : 3);
   p.ngroups = (ntaps + p.taps_per_group - 1) / p.taps_per_group;
   p.nslabs = std::max(1, std::min(p.ntiles, num_sms() / p.ngroups));
@@ -277,7 +278,7 @@ int wgrad_tc_launch(const void* x, const void* dpre, float* dw, float* db, const
     const uint64_t gd[5] = {128, static_cast<uint64_t>(xW), static_cast<uint64_t>(xH), static_cast<uint64_t>(xD),
                             static_cast<uint64_t>(x_dims[0])};
     const uint64_t gs[4] = {256, 256ull * xW, 256ull * xW * xH, 256ull * xW * xH * xD};
-    const uint32_t box[5] = {64, p.brick ? static_cast<uint32_t>(p.bw + 2) : p.bw * s, p.bh * s,
+    const uint32_t box[5] = {64, p.bw * s, p.brick ? static_cast<uint32_t>(p.bh + 2) : p.bh * s,
                              (xD == 1 ? 1u : p.bd * s), 1};
     const uint32_t es[5] = {1, s, s, (xD == 1 ? 1u : s), 1};
     int rc = encode_tensor_map(&tmX, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, x, gd, gs, box, CU_TENSOR_MAP_SWIZZLE_128B, es);
