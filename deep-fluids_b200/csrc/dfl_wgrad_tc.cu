@@ -135,6 +135,15 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
       if (lane == 0) {
         constexpr uint32_t idesc = umma_idesc_bf16(128, 128, 1, 1);   // both operands MN-major
         uint32_t ia = 0, ib = 0;
+        // brick mode: byte offset of K step k inside the brick for dy = 0 (tile-independent; computed ONCE -- this thread
+        // issues every MMA, so per-MMA integer divisions would cap the issue rate below the tensor pipe's)
+        uint32_t koff[WG_TILE_K / 16];
+#pragma unroll
+        for (int k = 0; k < WG_TILE_K / 16; ++k) {
+          const int v = k * 16, l = v / p.bw, xoff = v % p.bw;
+          koff[k] = static_cast<uint32_t>((((l / p.bh) * (p.bh + 2) + (l % p.bh)) * p.bw + xoff) * 128);
+        }
+        const uint32_t line_bytes = static_cast<uint32_t>(p.bw * 128);
         for (int tile = t_begin; tile < t_end; ++tile, ++ib) {
           const uint32_t sbs = ib % WG_B_SLOTS, bph = (ib / WG_B_SLOTS) & 1;
           mbar_wait(&b_full[sbs], bph);
@@ -145,15 +154,13 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
             mbar_wait(&a_full[s], ph);
             tc_fence_after();
             const uint32_t sa = smem_u32(sA + s * WG_BRICK_SLOT);
-            for (int t = 0; t < gtaps; ++t) {                             // t = dy
+            const uint32_t acc = (tile != t_begin) ? 1u : 0u;
 #pragma unroll
-              for (int k = 0; k < WG_TILE_K / 16; ++k) {
-                const int v = k * 16;                                     // first voxel of this K step (x fastest)
-                const int l = v / p.bw, xoff = v % p.bw;                  // tile line (lz*bh + ly) and x offset
-                const uint32_t row0 = static_cast<uint32_t>((((l / p.bh) * (p.bh + 2) + (l % p.bh) + t) * p.bw) + xoff);
-                umma_bf16(tmem_base + t * 128, umma_desc_sw128(sa + row0 * 128, p.a_half, 1024),
-                          umma_desc_sw128(sb + k * 2048, WG_OP_BYTES / 2, 1024), idesc, (tile != t_begin || k != 0) ? 1u : 0u);
-              }
+            for (int t = 0; t < 3; ++t) {                                 // t = dy: window shifted by t x-lines
+#pragma unroll
+              for (int k = 0; k < WG_TILE_K / 16; ++k)
+                umma_bf16(tmem_base + t * 128, umma_desc_sw128(sa + koff[k] + t * line_bytes, p.a_half, 1024),
+                          umma_desc_sw128(sb + k * 2048, WG_OP_BYTES / 2, 1024), idesc, (k != 0) ? 1u : acc);
             }
             umma_commit(&a_empty[s]);
             ++ia;
