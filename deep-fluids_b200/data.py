@@ -18,7 +18,16 @@ class _Queue(object):
         return 0
 
 
-class BatchManager(object):
+def BatchManager(config, device=None, pool=4, rank=0):
+    """Factory with the reference's constructor name (data.py:16): the real-dataset loader when `data/<dataset>/args.txt`
+    exists and --synthetic is not set, else the synthetic on-device source."""
+    root = getattr(config, "data_path", None) or os.path.join(config.data_dir, config.dataset)
+    if not getattr(config, "synthetic", False) and os.path.exists(os.path.join(root, "args.txt")):
+        return DatasetBatchManager(config, device=device, rank=rank)
+    return SyntheticBatchManager(config, device=device, pool=pool, rank=rank)
+
+
+class SyntheticBatchManager(object):
     def __init__(self, config, device=None, pool=4, rank=0):
         self.config = config
         self.root = getattr(config, "data_path", "")
@@ -26,8 +35,6 @@ class BatchManager(object):
         self.is_3d = config.is_3d
         self.batch_size = config.batch_size
         self.res_x, self.res_y, self.res_z = config.res_x, config.res_y, config.res_z
-        if not getattr(config, "synthetic", False) and os.path.isdir(self.root):
-            raise NotImplementedError("real dataset loading (data.py:16-108) is SURVEY 8(f) N2; pass --synthetic=true")
         self.c_num = 3                       # smoke_pos_size / smoke3_vel_buo: [p0, p1, t]  (data.py:52-60)
         self.y_num = [21, 5, 200] if not self.is_3d else [5, 3, 250]
         self.y_range = [[-1.0, 1.0]] * self.c_num
@@ -82,3 +89,144 @@ class BatchManager(object):
     def random_list(self, num):
         x, y = self._pool[0]
         return x[:num], None, y[:num]
+
+
+def preprocess(file_path, data_type, x_range, y_range):
+    """npz {x, y} -> normalised (x, y), as reference data.py:311-333: velocity x /= x_range (density: x*2-1);
+    y[i] -> [-1, 1] by its [min, max]."""
+    import numpy as np
+    with np.load(file_path) as data:
+        x = data['x'].astype(np.float32)
+        y = np.array(data['y'], dtype=np.float32)
+    if data_type[0] == 'd':
+        x = x * 2 - 1
+    else:
+        x = x / x_range
+    for i, ri in enumerate(y_range):
+        y[i] = (y[i] - ri[0]) / (ri[1] - ri[0]) * 2 - 1
+    return x, y
+
+
+class DatasetBatchManager(object):
+    """Real mantaflow dataset (reference data.py:16-171): `args.txt` ("key: value" per line), `v/*.npz` with x (velocity
+    field) and y (parameters, or [dof, num_frames] history for AE scenes), `v_range.txt` (min/max -> x_range).
+    The reference's GIL-bound loader threads + TF FIFOQueue become worker threads that assemble whole batches in pinned
+    host memory; `.batch()` hands out device tensors (async H2D on the caller's stream)."""
+
+    def __init__(self, config, device=None, rank=0, prefetch=4):
+        import glob
+        import numpy as np
+        import queue
+        self.config = config
+        self.root = getattr(config, "data_path", None) or os.path.join(config.data_dir, config.dataset)
+        self.device = device if device is not None else torch.device("cuda", torch.cuda.current_device())
+        self.rng = np.random.RandomState(int(config.random_seed) + int(rank))
+        self.args = {}
+        with open(os.path.join(self.root, 'args.txt'), 'r') as f:          # data.py:22-29
+            for line in f:
+                if ': ' in line:
+                    arg, val = line.rstrip("\n").split(': ', 1)
+                    self.args[arg] = val
+        self.is_3d = config.is_3d
+        self.data_type = config.data_type
+        pat = os.path.join(self.root, self.data_type[0], "*")
+        if 'ae' in config.arch:                                             # data.py:32-38: sort by (scene, frame)
+            nf = int(self.args['num_frames'])
+
+            def sortf(x):
+                n = os.path.basename(x)[:-4].split('_')
+                return int(n[0]) * nf + int(n[1])
+            self.paths = sorted(glob.glob(pat), key=sortf)
+        else:
+            self.paths = sorted(glob.glob(pat))
+        self.num_samples = len(self.paths)
+        assert self.num_samples > 0, "no samples under %s" % pat
+        self.batch_size = config.batch_size
+        self.epochs_per_step = self.batch_size / float(self.num_samples)   # data.py:52
+        self.res_x, self.res_y, self.res_z = config.res_x, config.res_y, config.res_z
+        self.depth = (3 if self.is_3d else 2) if self.data_type == 'velocity' else 1
+        self.c_num = int(self.args['num_param'])
+        self.feature_dim = ([self.res_z] if self.is_3d else []) + [self.res_y, self.res_x, self.depth]
+        if 'ae' in config.arch:
+            self.dof = int(self.args['num_dof'])
+            self.label_dim = [self.dof, int(self.args['num_frames'])]
+        else:
+            self.dof = 0
+            self.label_dim = [self.c_num]
+        r = np.loadtxt(os.path.join(self.root, self.data_type[0] + '_range.txt'))   # data.py:87-88
+        self.x_range = float(max(abs(r[0]), abs(r[1])))
+        self.y_range, self.y_num = [], []
+        for i in range(self.c_num):                                          # data.py:92-108
+            p_name = self.args['p%d' % i]
+            self.y_num.append(int(self.args['num_{}'.format(p_name)]))
+            if 'ae' not in config.arch:
+                self.y_range.append([float(self.args['min_{}'.format(p_name)]), float(self.args['max_{}'.format(p_name)])])
+        if 'ae' in config.arch:
+            self.y_range = [[-1, 1] for _ in range(self.label_dim[0])]
+        self.num_threads = int(max(1, min(config.num_worker, os.cpu_count() or 1, self.batch_size)))
+        self._queue = queue.Queue(maxsize=prefetch)
+        self._threads, self._stop = [], False
+        self.q = self                       # Trainer reads batch_manager.q.size()
+
+    def size(self):
+        return self._queue.qsize()
+
+    # ---- loader threads (data.py:116-159)
+    def _worker(self, seed):
+        import numpy as np
+        rng = np.random.RandomState(seed)
+        pin = torch.cuda.is_available()
+        while not self._stop:
+            xb = torch.empty([self.batch_size] + self.feature_dim, dtype=torch.float32)
+            yb = torch.empty([self.batch_size] + self.label_dim, dtype=torch.float32)
+            for i in range(self.batch_size):
+                x, y = preprocess(self.paths[rng.randint(self.num_samples)], self.data_type, self.x_range, self.y_range)
+                xb[i] = torch.from_numpy(np.ascontiguousarray(x)).reshape(self.feature_dim)
+                yb[i] = torch.from_numpy(np.ascontiguousarray(y)).reshape(self.label_dim)
+            if pin:
+                xb, yb = xb.pin_memory(), yb.pin_memory()
+            while not self._stop:
+                try:
+                    self._queue.put((xb, yb), timeout=0.1)
+                    break
+                except Exception:
+                    continue
+
+    def start_thread(self, sess=None):
+        import threading
+        if self._threads:
+            return
+        self._stop = False
+        for i in range(self.num_threads):
+            t = threading.Thread(target=self._worker, args=(int(self.rng.randint(1 << 30)),), daemon=True)
+            t.start()
+            self._threads.append(t)
+
+    def stop_thread(self):
+        self._stop = True
+        for t in self._threads:
+            t.join(timeout=2.0)
+        self._threads = []
+
+    def batch(self):
+        """(x, y) of one batch on the device: x [B,(D,)H,W,C] in [-1,1], y [B,c_num] (AE: [B,dof,frames])"""
+        self.start_thread()
+        xb, yb = self._queue.get()
+        return xb.to(self.device, non_blocking=True), yb.to(self.device, non_blocking=True)
+
+    def denorm(self, x=None, y=None):
+        if x is not None:
+            x = x * self.x_range if self.data_type[0] != 'd' else (x + 1) * 0.5
+        if y is not None and 'ae' not in self.config.arch:
+            y = y.clone() if hasattr(y, "clone") else y.copy()
+            for i, ri in enumerate(self.y_range):
+                y[..., i] = (y[..., i] + 1) * 0.5 * (ri[1] - ri[0]) + ri[0]
+        return x, y
+
+    def random_list(self, num):
+        xs, ys = [], []
+        for _ in range(num):
+            x, y = preprocess(self.paths[self.rng.randint(self.num_samples)], self.data_type, self.x_range, self.y_range)
+            xs.append(torch.from_numpy(x))
+            ys.append(torch.from_numpy(y))
+        return torch.stack(xs).to(self.device), None, torch.stack(ys).to(self.device)
