@@ -275,6 +275,29 @@ class Trainer(object):
         self.step += 1
         return self._loss3, self._loss_p
 
+    # ---- AE inference pieces of test_ae / autoencode (trainer.py:464-583): encode x -> z, decode z -> velocity
+    def _chunks(self, t):
+        n = t.shape[0]
+        for b0 in range(0, n, self.b_num):
+            c = t[b0:b0 + self.b_num]
+            k = c.shape[0]
+            if k < self.b_num:
+                c = torch.cat([c, c.new_zeros((self.b_num - k,) + tuple(c.shape[1:]))])
+            yield c.contiguous(), k
+
+    def encode(self, x):
+        """latent codes z [n, z_num] of velocity fields x [n,(D,)H,W,C]  (`sess.run(self.z, {self.x: x})`, trainer.py:504)"""
+        x = torch.as_tensor(x, dtype=torch.float32, device=self.device)
+        return torch.cat([self.ae.enc.forward(c)[:k].clone() for c, k in self._chunks(x)])
+
+    def decode(self, z):
+        """velocity fields from latent codes (`sess.run(self.x_, {self.z: z})`, trainer.py:551-552), normalised units"""
+        z = torch.as_tensor(z, dtype=torch.float32, device=self.device)
+        return torch.cat([K.curl_fwd(self.ae.dec.forward(c))[:k].clone() for c, k in self._chunks(z)])
+
+    def autoencode(self, x):
+        return self.decode(self.encode(x))
+
     def losses_ae(self):
         l = self._loss3.tolist()
         lp = float(self._loss_p.item())

@@ -270,3 +270,23 @@ def test_trainer_ae_api_runs_and_loss_decreases():
             first = tr.losses_ae()[0]
     last = tr.losses_ae()[0]
     assert np.isfinite(last) and last < first, (first, last)
+
+
+def test_ae_encode_decode_inference():
+    """decode-from-z entry (trainer.py:551-552) and latent dump (trainer.py:504) reuse the training engines"""
+    from deepfluids_b200 import config as C, kernels as K
+    from deepfluids_b200.data import BatchManager
+    from deepfluids_b200.trainer3 import Trainer3
+    cfg, _ = C.get_config(["--synthetic=true", "--arch=ae", "--is_3d=true", "--res_x=16", "--res_y=16", "--res_z=16",
+                           "--batch_size=2", "--num_conv=2", "--max_step=4"])
+    bm = BatchManager(cfg, pool=2)
+    tr = Trainer3(cfg, bm)
+    x = torch.cat([bm._pool[0][0], bm._pool[1][0][:1]])           # 3 fields: not a multiple of the batch
+    z = tr.encode(x)
+    assert z.shape == (3, cfg.z_num) and torch.isfinite(z).all()
+    pot, z2 = tr.ae.forward(x[:2].contiguous())
+    assert torch.equal(z[:2], z2)
+    v = tr.decode(z)
+    assert v.shape == x.shape and torch.equal(v[:2], K.curl_fwd(pot))
+    assert float(K.divergence(v).abs().max()) <= 1e-5
+    assert torch.equal(tr.autoencode(x), v)
