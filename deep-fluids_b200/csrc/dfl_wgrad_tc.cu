@@ -96,10 +96,13 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
       if (lane == 0) {
         uint32_t ia = 0, ib = 0;
         for (int tile = t_begin; tile < t_end; ++tile, ++ib) {
+          // z-fastest traversal: a CTA's consecutive bricks are z-neighbours, so the planes the dz = 0/1/2 tap groups
+          // share are re-read from L2 within a few bricks instead of one z-plane (4 MB per slab at 128^3) later --
+          // ncu showed 13.0 GB of DRAM reads per launch (3x the algorithmic 4.3 GB) with the x-fastest order
           int r = tile;
+          const int z0 = (r % p.tz) * p.bd; r /= p.tz;
           const int x0 = (r % p.tx) * p.bw; r /= p.tx;
           const int y0 = (r % p.ty) * p.bh; r /= p.ty;
-          const int z0 = (r % p.tz) * p.bd; r /= p.tz;
           const int b = r;
           {  // B = dP brick (two 64-channel boxes)
             const uint32_t s = ib % WG_B_SLOTS, ph = (ib / WG_B_SLOTS) & 1;
