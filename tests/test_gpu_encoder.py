@@ -285,8 +285,9 @@ def test_ae_encode_decode_inference():
     z = tr.encode(x)
     assert z.shape == (3, cfg.z_num) and torch.isfinite(z).all()
     pot, z2 = tr.ae.forward(x[:2].contiguous())
-    assert torch.equal(z[:2], z2)
+    # (the encoder FC reduces over blocks with fp32 atomics: run-to-run differences in the last bits of z)
+    assert rel_l2(z[:2], z2) <= 1e-5
     v = tr.decode(z)
-    assert v.shape == x.shape and torch.equal(v[:2], K.curl_fwd(pot))
+    assert v.shape == x.shape and rel_l2(v[:2], K.curl_fwd(pot)) <= 2e-3
     assert float(K.divergence(v).abs().max()) <= 1e-5
-    assert torch.equal(tr.autoencode(x), v)
+    assert rel_l2(tr.autoencode(x), v) <= 2e-3
