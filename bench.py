@@ -179,6 +179,7 @@ def run_gpu_arm(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
+        os.environ.setdefault("NCCL_DEBUG", "WARN")      # keep NCCL's version banner off stdout: ONE JSON line only
         dist.init_process_group("nccl", device_id=dev)
 
     from deepfluids_b200 import kernels as K
@@ -304,7 +305,8 @@ def run_gpu_arm(args):
                "clocks": clocks, "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d,
                                          "d2h_bytes_per_step": 12, "ms_per_step": ms_e / args.steps},
                "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu}
-        print(json.dumps(out))
+        sys.stdout.flush()
+        print(json.dumps(out), flush=True)
     if world > 1:
         dist.destroy_process_group()
 

@@ -284,10 +284,12 @@ def test_ae_encode_decode_inference():
     x = torch.cat([bm._pool[0][0], bm._pool[1][0][:1]])           # 3 fields: not a multiple of the batch
     z = tr.encode(x)
     assert z.shape == (3, cfg.z_num) and torch.isfinite(z).all()
-    pot, z2 = tr.ae.forward(x[:2].contiguous())
+    _, z2 = tr.ae.forward(x[:2].contiguous())
     # (the encoder FC reduces over blocks with fp32 atomics: run-to-run differences in the last bits of z)
     assert rel_l2(z[:2], z2) <= 1e-5
     v = tr.decode(z)
-    assert v.shape == x.shape and rel_l2(v[:2], K.curl_fwd(pot)) <= 2e-3
-    assert float(K.divergence(v).abs().max()) <= 1e-5
-    assert rel_l2(tr.autoencode(x), v) <= 2e-3
+    assert v.shape == x.shape and float(K.divergence(v).abs().max()) <= 1e-5
+    # decode is a pure function of z: the chunked / padded path equals a direct decoder call on the same codes
+    direct = K.curl_fwd(tr.ae.dec.forward(z[:2].contiguous()))
+    assert torch.equal(v[:2], direct)
+    assert torch.equal(tr.decode(z), v)
