@@ -41,6 +41,24 @@ ARCH = {"c5": "ae"}
 FLOPS_PER_FIELD = {"c2": 58.0e9, "c3": 3196.0e9, "c4": 25575.0e9, "c5": 49471.0e9, "tiny": None}
 
 
+# stdout carries exactly ONE line (the JSON): everything else any library prints to fd 1 (e.g. NCCL's version banner)
+# is routed to stderr for the lifetime of the process
+_REAL_STDOUT = None
+
+
+def _guard_stdout():
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line):
+    sys.stdout.flush()
+    os.write(_REAL_STDOUT if _REAL_STDOUT is not None else 1, (line + "\n").encode())
+
+
 def load_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -163,7 +181,7 @@ def run_reference_arm(args):
            "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
            "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
            "gpu_launches": 0}
-    print(json.dumps(out))
+    emit(json.dumps(out))
 
 
 # ------------------------------------------------------------------------------------------------------------------
@@ -179,7 +197,6 @@ def run_gpu_arm(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        os.environ.setdefault("NCCL_DEBUG", "WARN")      # keep NCCL's version banner off stdout: ONE JSON line only
         dist.init_process_group("nccl", device_id=dev)
 
     from deepfluids_b200 import kernels as K
@@ -305,8 +322,7 @@ def run_gpu_arm(args):
                "clocks": clocks, "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d,
                                          "d2h_bytes_per_step": 12, "ms_per_step": ms_e / args.steps},
                "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu}
-        sys.stdout.flush()
-        print(json.dumps(out), flush=True)
+        emit(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()
 
@@ -329,6 +345,7 @@ def main():
     ap.add_argument("--workload", type=str, default="c4", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu", dest="no_cpu", action="store_true", help="skip the cpu_baseline leg")
     args = ap.parse_args()
+    _guard_stdout()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     if args.impl == "reference":
         run_reference_arm(args)
