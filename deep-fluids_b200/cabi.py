@@ -40,6 +40,8 @@ SIGNATURES = {
     "dfl_enc_fc_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
     "dfl_fc_dz": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
     "dfl_ae_loss_p": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _f, _vp]),
+    "dfl_ae_sigmoid": (_i, [_vp, _vp, _i, _vp]),
+    "dfl_ae_sparse_bwd": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _f, _f, _vp]),
     "dfl_pool_mask": (_i, [_vp, _vp, _vp, _vp, _dims, _i, _vp]),
     "dfl_adam_step": (_i, [_vp, _vp, _vp, _vp, _sz, _f, _f, _f, _f, _f, _vp]),
     "dfl_adam_step_dev": (_i, [_vp, _vp, _vp, _vp, _sz, _vp, _f, _f, _f, _f, _vp]),

@@ -77,6 +77,9 @@ int enc_fc_bwd(const void* flat, const float* W, const float* dz, float* dW, flo
                int nblk, int Z, cudaStream_t st);
 int fc_dz(const void* dout, const float* W, float* dz, int B, int K, int N, int dout_dtype, int accumulate, cudaStream_t st);
 int ae_loss_p(const float* z, const float* y, float* dz, float* loss_p, int B, int Z, int P, float scale, cudaStream_t st);
+int ae_sigmoid(const float* zl, float* z, int n, cudaStream_t st);
+int ae_sparse_bwd(const float* z, float* dz, float* dzl, float* loss_kl, int B, int Z, int P, float rho, float w5,
+                  cudaStream_t st);
 int fc_fwd(const float* z, const float* W, const float* bias, void* out, int B, int K, int N, int out_dtype,
            cudaStream_t st);
 int fc_bwd(const float* z, const void* dout, float* dW, float* db, int B, int K, int N, int dout_dtype,
@@ -232,6 +235,12 @@ int dfl_adam_step_dev(float* param, const float* grad, float* m, float* v, size_
 }
 int dfl_cast_f32_bf16(const float* in, void* out, size_t n, void* stream) {
   return cast_f32_bf16(in, out, n, ST(stream));
+}
+
+int dfl_ae_sigmoid(const float* zl, float* z, int n, void* stream) { return ae_sigmoid(zl, z, n, ST(stream)); }
+int dfl_ae_sparse_bwd(const float* z, float* dz, float* dzl, float* loss_kl, int B, int Z, int P, float rho, float w5,
+                      void* stream) {
+  return ae_sparse_bwd(z, dz, dzl, loss_kl, B, Z, P, rho, w5, ST(stream));
 }
 
 }  // extern "C"

@@ -506,4 +506,46 @@ int ae_loss_p(const float* z, const float* y, float* dz, float* loss_p, int B, i
   return DFL_OK;
 }
 
+// use_sparse (config.py:29-30, model.py:196,210, trainer.py:389-394): z = sigmoid(z_lin); loss_kl = sum_j KL(Bernoulli(rho) ||
+// Bernoulli(mean_b z[b][j])) over the first Z-P latent dims.  Tiny tensors ([B, Z<=16]): single-block kernels.
+__global__ void ae_sigmoid_kernel(const float* __restrict__ zl, float* __restrict__ z, int n) {
+  for (int i = threadIdx.x; i < n; i += blockDim.x) z[i] = 1.f / (1.f + __expf(-zl[i]));
+}
+// dz (gradient w.r.t. the sigmoid OUTPUT, [B,Z]) += w5 * d loss_kl / dz;  then dzl = dz * z (1 - z);  loss_kl written
+__global__ void ae_sparse_bwd_kernel(const float* __restrict__ z, float* __restrict__ dz, float* __restrict__ dzl,
+                                     float* __restrict__ loss_kl, int B, int Z, int P, float rho, float w5) {
+  __shared__ float skl[32];
+  const int j = threadIdx.x;
+  float kl = 0.f;
+  if (j < Z - P) {
+    float m = 0.f;
+    for (int b = 0; b < B; ++b) m += z[b * Z + j];
+    m /= static_cast<float>(B);
+    kl = rho * (logf(rho) - logf(m)) + (1.f - rho) * (logf(1.f - rho) - logf(1.f - m));
+    const float g = w5 * (-rho / m + (1.f - rho) / (1.f - m)) / static_cast<float>(B);
+    for (int b = 0; b < B; ++b) dz[b * Z + j] += g;
+  }
+  if (j < 32) skl[j] = (j < Z - P) ? kl : 0.f;
+  __syncthreads();
+  if (j == 0) {
+    float t = 0.f;
+    for (int k = 0; k < 32; ++k) t += skl[k];
+    *loss_kl = t;
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < B * Z; i += blockDim.x) dzl[i] = dz[i] * z[i] * (1.f - z[i]);
+}
+int ae_sigmoid(const float* zl, float* z, int n, cudaStream_t st) {
+  ae_sigmoid_kernel<<<1, 128, 0, st>>>(zl, z, n);
+  DFL_LAUNCH_OK("ae_sigmoid_kernel");
+  return DFL_OK;
+}
+int ae_sparse_bwd(const float* z, float* dz, float* dzl, float* loss_kl, int B, int Z, int P, float rho, float w5,
+                  cudaStream_t st) {
+  DFL_REQUIRE(Z <= 32 && P >= 0 && P < Z, "ae_sparse_bwd: need z_num <= 32 and 0 <= p_num < z_num");
+  ae_sparse_bwd_kernel<<<1, 64, 0, st>>>(z, dz, dzl, loss_kl, B, Z, P, rho, w5);
+  DFL_LAUNCH_OK("ae_sparse_bwd_kernel");
+  return DFL_OK;
+}
+
 }  // namespace dfl

@@ -32,7 +32,7 @@ def _same_pad_before(n, k=3, s=2):
 class EncoderEngine(object):
     def __init__(self, batch, x_shape, filters=128, z_num=16, num_conv=3, repeat=0, name="enc", device=None, seed=123,
                  params=None):
-        assert filters == 128
+        assert filters == 128 and num_conv >= 1, "encoder needs filters=128 and at least one conv per level"
         self.device = device or torch.device("cuda", torch.cuda.current_device())
         self.B, self.name, self.F, self.nc, self.z_num = int(batch), name, filters, int(num_conv), int(z_num)
         self.spatial = [int(s) for s in x_shape[:-1]]
@@ -233,8 +233,10 @@ class AEEngine(object):
     """AE / AE3 (model.py:190-216): z = Enc(x, num_conv-1);  out = Gen(z, x.shape, num_conv);  one flat parameter buffer
     with the reference's variable names (`AE/enc/...`, `AE/dec/...`)."""
 
-    def __init__(self, batch, x_shape, filters=128, z_num=16, num_conv=4, repeat=0, name="AE", device=None, seed=123):
+    def __init__(self, batch, x_shape, filters=128, z_num=16, num_conv=4, repeat=0, name="AE", device=None, seed=123,
+                 use_sparse=False):
         self.device = device or torch.device("cuda", torch.cuda.current_device())
+        self.use_sparse = bool(use_sparse)
         # build both tables first so they can share ONE flat buffer (one Adam launch / one all-reduce)
         self.enc = EncoderEngine(batch, x_shape, filters, z_num, num_conv - 1, repeat, name + "/enc", self.device, seed)
         self.dec = GeneratorEngine(batch, list(x_shape), z_dim=z_num, filters=filters, num_conv=num_conv, repeat=repeat,
@@ -254,6 +256,9 @@ class AEEngine(object):
         self.variables = list(tab.keys())
         self.z_num = z_num
         self.dz = torch.zeros(batch, z_num, dtype=torch.float32, device=self.device)
+        self.z_sig = torch.zeros_like(self.dz)
+        self.dz_lin = torch.zeros_like(self.dz)
+        self.loss_kl = torch.zeros(1, dtype=torch.float32, device=self.device)
         self.adam_t = 0
 
     def repack(self):
@@ -262,13 +267,21 @@ class AEEngine(object):
 
     def forward(self, x):
         z = self.enc.forward(x)
+        if self.use_sparse:                       # model.py:196 / :210
+            K.ae_sigmoid(z, self.z_sig)
+            z = self.z_sig
         pot = self.dec.forward(z)
         return pot, z
 
-    def backward(self, dpot):
-        """dz must already hold d(loss_p)/dz (ae_loss_p); the decoder adds its FC input gradient, then the encoder runs."""
+    def backward(self, dpot, p_num=0, sparsity=0.01, w5=1.0):
+        """dz must already hold d(loss_p)/dz (ae_loss_p); the decoder adds its FC input gradient, then the encoder runs.
+        With use_sparse the Bernoulli-KL term (trainer.py:389-394) and the sigmoid derivative are applied in between."""
         self.dec.backward(dpot, dz=self.dz)
-        self.enc.backward(self.dz)
+        if self.use_sparse:
+            K.ae_sparse_bwd(self.z_sig, self.dz, self.dz_lin, self.loss_kl, p_num, sparsity, w5)
+            self.enc.backward(self.dz_lin)
+        else:
+            self.enc.backward(self.dz)
 
     def zero_grad(self):
         self.params.grad.zero_()

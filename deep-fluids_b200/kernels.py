@@ -223,6 +223,17 @@ def ae_loss_p(z, y_last, dz, loss_p, scale):
     check(cabi.lib().dfl_ae_loss_p(_p(z), _p(y_last), _p(dz), _p(loss_p), B, Z, y_last.shape[1], scale, _st()))
 
 
+def ae_sigmoid(z_lin, z):
+    PROF.launches += 1
+    check(cabi.lib().dfl_ae_sigmoid(_p(z_lin), _p(z), z_lin.numel(), _st()))
+
+
+def ae_sparse_bwd(z, dz, dz_lin, loss_kl, p_num, rho, w5):
+    B, Z = z.shape
+    PROF.launches += 1
+    check(cabi.lib().dfl_ae_sparse_bwd(_p(z), _p(dz), _p(dz_lin), _p(loss_kl), B, Z, p_num, rho, w5, _st()))
+
+
 def conv3x3_wgrad(x, dpre, dw, db=None):
     """dw += x^T (x) dpre per tap; db += column sums of dpre (optional, free in the kernel)"""
     d, nd = _spatial(x)

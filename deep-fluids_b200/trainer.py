@@ -83,9 +83,9 @@ class Trainer(object):
             self.z_num = config.z_num
             self.p_num = self.batch_manager.dof
             self.use_sparse = config.use_sparse
-            if self.use_sparse:
-                raise NotImplementedError("use_sparse (Bernoulli-KL on sigmoid(z), trainer.py:389-394) is off by default and not built")
+            self.sparsity = config.sparsity
             self.w4 = config.w4
+            self.w5 = config.w5
             self.build_model_ae()
         else:
             self.build_model()
@@ -244,7 +244,7 @@ class Trainer(object):
             raise Exception("[!] Invalid opimizer")
         x_shape = list(self.x.shape[1:])
         self.ae = AEEngine(self.b_num, x_shape, self.filters, self.z_num, self.num_conv, self.repeat, "AE", self.device,
-                           self.config.random_seed)
+                           self.config.random_seed, use_sparse=self.use_sparse)
         self.engine = self.ae                        # checkpoint / DP code paths use `.engine.params`
         self.var = self.ae.variables
         self._loss3 = torch.zeros(3, dtype=torch.float32, device=self.device)
@@ -269,7 +269,7 @@ class Trainer(object):
         pot, z = ae.forward(x)
         K.stencil_loss_fwdbwd(pot, x, self.w1, self.w2, 1.0, dpot=self._dpot, loss3=self._loss3, workspace=self._ws)
         K.ae_loss_p(z, y_last, ae.dz, self._loss_p, self.w4)
-        ae.backward(self._dpot)
+        ae.backward(self._dpot, self.p_num, self.sparsity, self.w5)
         scale = dp.allreduce_grads_(ae.params.grad)
         ae.optimizer_step(self.g_lr, self.optimizer == 'adam', self.beta1, self.beta2, 1e-8, scale)
         self.step += 1
@@ -303,6 +303,9 @@ class Trainer(object):
         lp = float(self._loss_p.item())
         self.loss_l1, self.loss_j_l1, self.loss_p = l[1], l[2], lp
         self.loss = l[0] + self.w4 * lp
+        if self.use_sparse:
+            self.loss_kl = float(self.ae.loss_kl.item())
+            self.loss += self.w5 * self.loss_kl
         return self.loss, l[1], l[2], lp
 
     def train_ae(self):

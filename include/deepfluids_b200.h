@@ -152,6 +152,12 @@ int dfl_fc_dz(const void* dout, const float* W, float* dz, int B, int K, int N, 
 int dfl_ae_loss_p(const float* z, const float* y, float* dz, float* loss_p, int B, int Z, int P, float scale,
                   void* stream);
 
+/* use_sparse (model.py:196,210; trainer.py:389-394): z = sigmoid(z_lin);  backward: dz += w5 * d/dz sum_j KL(Bernoulli(rho)
+ * || Bernoulli(mean_b z[:, j])) over the first Z-P dims, then dz_lin = dz * z (1 - z); loss_kl written. */
+int dfl_ae_sigmoid(const float* z_lin, float* z, int n, void* stream);
+int dfl_ae_sparse_bwd(const float* z, float* dz, float* dz_lin, float* loss_kl, int B, int Z, int P, float rho, float w5,
+                      void* stream);
+
 /* ---- optimizer (tf.train.AdamOptimizer / GradientDescentOptimizer: trainer.py:160-165) ----------------- */
 /* flat fp32 buffers; lr_t = lr*sqrt(1-b2^t)/(1-b1^t) computed by the caller; m = v = NULL selects plain GD. */
 int dfl_adam_step(float* param, const float* grad, float* m, float* v, size_t n, float lr_t, float beta1, float beta2,

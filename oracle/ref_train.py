@@ -80,14 +80,19 @@ def generator_loss_and_grads(z, x, var, filters=128, num_conv=4, repeat=0, w1=1.
 
 
 def ae_loss_and_grads(x, y_last, var, p_num, filters=128, z_num=16, num_conv=4, repeat=0,
-                      w1=1.0, w2=1.0, w4=1.0, use_curl=True, name="AE"):
+                      w1=1.0, w2=1.0, w4=1.0, use_curl=True, name="AE", use_sparse=False, sparsity=0.01, w5=1.0):
     """One forward+backward of `build_model_ae` (trainer.py:357-396 / trainer3.py:240-279).
     y_last = y[:,:,-1] [B,p_num]; loss_p = mean((y_last - z[:,-p_num:])^2)."""
     leaves = OrderedDict((k, v.detach().clone().requires_grad_(True)) for k, v in var.items())
-    s, z = M.ae_forward(x, leaves, filters, z_num, num_conv, repeat, name)
+    s, z = M.ae_forward(x, leaves, filters, z_num, num_conv, repeat, name, use_sparse=use_sparse)
     loss, l1, jl1, g = stencil_loss(s, x, w1, w2, use_curl)
     loss_p = ((y_last - z[:, -p_num:]) ** 2).mean()
     total = loss + w4 * loss_p
+    if use_sparse:   # trainer.py:389-394: sum_j KL(Bernoulli(rho) || Bernoulli(mean_b z[:, j])) over the non-supervised dims
+        m = z[:, :-p_num].mean(0)
+        rho = torch.tensor(sparsity, dtype=z.dtype)
+        kl = rho * (rho.log() - m.log()) + (1 - rho) * ((1 - rho).log() - (1 - m).log())
+        total = total + w5 * kl.sum()
     gs = torch.autograd.grad(total, list(leaves.values()))
     grads = OrderedDict((k, gi) for k, gi in zip(leaves.keys(), gs))
     return total.detach(), l1.detach(), jl1.detach(), loss_p.detach(), g.detach(), z.detach(), grads

@@ -272,6 +272,30 @@ def test_trainer_ae_api_runs_and_loss_decreases():
     assert np.isfinite(last) and last < first, (first, last)
 
 
+def test_ae_use_sparse_vs_oracle():
+    """use_sparse=True (config.py:29): sigmoid on z + Bernoulli-KL sparsity term (trainer.py:389-394)"""
+    from deepfluids_b200 import kernels as K
+    from deepfluids_b200.encoder import AEEngine
+    spatial, B, nc = [16, 16, 16], 2, 2
+    ae = AEEngine(B, spatial + [3], z_num=16, num_conv=nc, device=dev(), seed=4, use_sparse=True)
+    var = ae.params.state_dict()
+    x, _ = T.synthetic_batch(B, spatial, seed=6)
+    ylast = torch.rand(B, 2, generator=torch.Generator().manual_seed(1))
+    total, l1, jl1, lp, g, zref, grads = T.ae_loss_and_grads(x, ylast, var, 2, num_conv=nc, use_sparse=True,
+                                                             sparsity=0.05, w5=0.5)
+    ae.zero_grad()
+    pot, z = ae.forward(x.to(dev()))
+    loss3, dpot, _ = K.stencil_loss_fwdbwd(pot, x.to(dev()))
+    lpd = torch.empty(1, device=dev())
+    K.ae_loss_p(z, ylast.to(dev()), ae.dz, lpd, 1.0)
+    ae.backward(dpot, 2, 0.05, 0.5)
+    assert rel_l2(z, zref) <= 2e-2 and float(z.min()) > 0 and float(z.max()) < 1
+    tot = loss3[0].item() + lpd.item() + 0.5 * ae.loss_kl.item()
+    assert abs(tot - total.item()) <= 1e-2 * abs(total.item())
+    k = "AE/enc/%d_fc/weights" % (len([v for v in var if "/enc/" in v]) // 2 - 1)
+    assert k in var and rel_l2(ae.params.g(k), grads[k]) <= 1e-1
+
+
 def test_ae_encode_decode_inference():
     """decode-from-z entry (trainer.py:551-552) and latent dump (trainer.py:504) reuse the training engines"""
     from deepfluids_b200 import config as C, kernels as K

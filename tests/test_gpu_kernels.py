@@ -325,3 +325,24 @@ def test_adam_matches_tf_semantics():
         lr_t = lr * math.sqrt(1 - 0.999 ** t) / (1 - 0.5 ** t)
         K.adam_step(p, gr.to(dev()), m, v, lr_t, 0.5, 0.999, 1e-8)
     np.testing.assert_allclose(p.cpu().numpy(), var["w"].numpy(), rtol=1e-5, atol=1e-7)
+
+
+def test_cabi_error_paths():
+    """argument errors come back as negative codes with a message (no CPU fallback, no crash, no silent success)"""
+    from deepfluids_b200 import kernels as K
+    from deepfluids_b200.cabi import DflError
+    x = torch.zeros(1, 8, 8, 100, dtype=torch.bfloat16, device=dev())       # Cin = 100: unsupported
+    w = torch.zeros(128, 900, dtype=torch.bfloat16, device=dev())
+    out = torch.zeros(1, 8, 8, 128, dtype=torch.bfloat16, device=dev())
+    with pytest.raises(DflError, match="Cin must be"):
+        K.conv3x3(x, w, None, out=out)
+    with pytest.raises(DflError, match="no output buffer"):
+        K.conv3x3(torch.zeros(1, 8, 8, 128, dtype=torch.bfloat16, device=dev()), torch.zeros(128, 9 * 128, dtype=torch.bfloat16, device=dev()))
+    with pytest.raises(DflError, match="extent must be >= 2"):
+        K.curl_fwd(torch.zeros(1, 1, 8, 1, device=dev()))
+    with pytest.raises(DflError, match="K <= 16"):
+        K.fc_fwd(torch.zeros(2, 17, device=dev()), torch.zeros(17, 64, device=dev()), torch.zeros(64, device=dev()))
+    with pytest.raises(TypeError):
+        K.curl_fwd(torch.zeros(1, 8, 8, 1, dtype=torch.float16, device=dev()))
+    with pytest.raises(AssertionError):
+        K.curl_fwd(torch.zeros(1, 8, 8, 1))                                  # CPU tensor: refused, never computed on the host
