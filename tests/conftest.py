@@ -10,6 +10,13 @@ if ROOT not in sys.path:
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a real B200 (run with -m gpu on the GPU box)")
+    # the CPU oracle (torch/oneDNN) is fastest at <= 16 threads; on the 128-core GPU host the default thread count
+    # oversubscribes and is two orders of magnitude slower (profiles/r01_cpu_threads_sweep.txt)
+    try:
+        import torch
+        torch.set_num_threads(min(16, os.cpu_count() or 1))
+    except Exception:
+        pass
 
 
 @pytest.fixture(scope="session")
