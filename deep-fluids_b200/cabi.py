@@ -7,7 +7,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libdeepfluids_b200.so")
 
 F32, BF16 = 0, 1
-CONV_LRELU, CONV_OUT2_UPSAMPLE, CONV_MASK_AFTER_RESIDUAL = 1, 2, 4
+CONV_LRELU, CONV_OUT2_UPSAMPLE, CONV_MASK_AFTER_RESIDUAL, CONV_SPLIT_IO = 1, 2, 4, 8
 
 _vp, _i, _f, _sz = C.c_void_p, C.c_int, C.c_float, C.c_size_t
 _dims = C.POINTER(C.c_int64)
@@ -42,6 +42,11 @@ SIGNATURES = {
     "dfl_ae_loss_p": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _f, _vp]),
     "dfl_ae_sigmoid": (_i, [_vp, _vp, _i, _vp]),
     "dfl_ae_sparse_bwd": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _f, _f, _vp]),
+    "dfl_conv3x3_fwd_ex": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _dims, _i, _i, _i, _i, C.POINTER(C.c_int32), _i, _vp]),
+    "dfl_pack_conv_weights_split": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp]),
+    "dfl_split_f32": (_i, [_vp, _vp, _sz, _i, _i, _vp]),
+    "dfl_merge_split": (_i, [_vp, _vp, _sz, _vp]),
+    "dfl_pool_mask_split": (_i, [_vp, _vp, _vp, _vp, _dims, _i, _vp]),
     "dfl_pool_mask": (_i, [_vp, _vp, _vp, _vp, _dims, _i, _vp]),
     "dfl_adam_step": (_i, [_vp, _vp, _vp, _vp, _sz, _f, _f, _f, _f, _f, _vp]),
     "dfl_adam_step_dev": (_i, [_vp, _vp, _vp, _vp, _sz, _vp, _f, _f, _f, _f, _vp]),

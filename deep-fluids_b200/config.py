@@ -79,6 +79,9 @@ b200_arg.add_argument('--synthetic', type=str2bool, default=False,
                       help='use the synthetic tensor source instead of data/<dataset> (SURVEY 8d)')
 b200_arg.add_argument('--synthetic_samples', type=int, default=21000)
 b200_arg.add_argument('--max_step', type=int, default=0, help='override max_step (0 = derive from max_epoch)')
+b200_arg.add_argument('--precision', type=str, default='bf16', choices=['bf16', 'fp32x3'],
+                      help="conv arithmetic: 'bf16' operands/activations, or 'fp32x3' = fp32-grade via split bf16 "
+                           "operands (hi/lo pairs, 3 MMA terms, fp32 accumulate) matching the reference's fp32 graphs")
 
 
 def get_config(argv=None):

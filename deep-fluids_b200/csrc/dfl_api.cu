@@ -63,7 +63,7 @@ int fwd_stencils(int op, int nd, const int64_t* dims, const void* in, int in_cs,
                  cudaStream_t st);
 int conv_tc_launch(const void* x, const void* w_packed, const float* bias, void* out, void* out2,
                    const void* residual, const void* mask_src, const int64_t* dims, int nd, int cin, int cout,
-                   int flags, cudaStream_t st);
+                   int flags, const int32_t* blkmap, int nphys, cudaStream_t st);
 int wgrad_tc_launch(const void* x, const void* dpre, float* dw, float* db, const int64_t* x_dims, const int64_t* dims,
                     int nd, int in_stride, int pad, int dw_tap_stride, int dw_row_stride, cudaStream_t st);
 int conv_tap_launch(const void* x, const void* w_packed, const float* bias, void* out, void* out2,
@@ -78,6 +78,11 @@ int enc_fc_bwd(const void* flat, const float* W, const float* dz, float* dW, flo
 int fc_dz(const void* dout, const float* W, float* dz, int B, int K, int N, int dout_dtype, int accumulate, cudaStream_t st);
 int ae_loss_p(const float* z, const float* y, float* dz, float* loss_p, int B, int Z, int P, float scale, cudaStream_t st);
 int ae_sigmoid(const float* zl, float* z, int n, cudaStream_t st);
+int pack_split(const float* W, void* wf, void* wd, int taps, int cin, int cout, cudaStream_t st);
+int split_f32(const float* in, void* out, size_t n, int cin, int cpad, cudaStream_t st);
+int merge_split(const void* in, float* out, size_t n, cudaStream_t st);
+int pool_mask_split(const void* g, const void* mask_src, void* ds, void* dmasked, const int64_t* cdims, int nd,
+                    cudaStream_t st);
 int ae_sparse_bwd(const float* z, float* dz, float* dzl, float* loss_kl, int B, int Z, int P, float rho, float w5,
                   cudaStream_t st);
 int fc_fwd(const float* z, const float* W, const float* bias, void* out, int B, int K, int N, int out_dtype,
@@ -174,7 +179,14 @@ int dfl_pack_conv_weights_ex(const float* w, void* w_fwd, void* w_dgrad, int tap
 int dfl_conv3x3_fwd(const void* x, const void* w_packed, const float* bias, void* out, void* out2,
                     const void* residual, const void* mask_src, const int64_t* dims, int ndim, int cin, int cout,
                     int flags, void* stream) {
-  return conv_tc_launch(x, w_packed, bias, out, out2, residual, mask_src, dims, ndim, cin, cout, flags, ST(stream));
+  return conv_tc_launch(x, w_packed, bias, out, out2, residual, mask_src, dims, ndim, cin, cout, flags, nullptr, 0,
+                        ST(stream));
+}
+int dfl_conv3x3_fwd_ex(const void* x, const void* w_packed, const float* bias, void* out, void* out2,
+                       const void* residual, const void* mask_src, const int64_t* dims, int ndim, int cin, int cout,
+                       int flags, const int32_t* blkmap, int nphys, void* stream) {
+  return conv_tc_launch(x, w_packed, bias, out, out2, residual, mask_src, dims, ndim, cin, cout, flags, blkmap, nphys,
+                        ST(stream));
 }
 int dfl_conv3x3_wgrad(const void* x, const void* dpre, float* dw, float* db, const int64_t* dims, int ndim, int cin,
                       int cout, void* stream) {
@@ -237,6 +249,18 @@ int dfl_cast_f32_bf16(const float* in, void* out, size_t n, void* stream) {
   return cast_f32_bf16(in, out, n, ST(stream));
 }
 
+int dfl_pack_conv_weights_split(const float* w, void* w_fwd, void* w_dgrad, int taps, int cin, int cout, void* stream) {
+  return pack_split(w, w_fwd, w_dgrad, taps, cin, cout, ST(stream));
+}
+int dfl_split_f32(const float* in, void* out, size_t n, int cin, int cpad, void* stream) {
+  return split_f32(in, out, n, cin, cpad, ST(stream));
+}
+int dfl_merge_split(const void* in, float* out, size_t n, void* stream) { return merge_split(in, out, n, ST(stream)); }
+int dfl_pool_mask_split(const void* g, const void* mask_src, void* ds, void* dmasked, const int64_t* cdims, int ndim,
+                        void* stream) {
+  DFL_REQUIRE(!(dmasked && !mask_src), "pool_mask_split: dmasked requested without mask_src");
+  return pool_mask_split(g, mask_src, ds, dmasked, cdims, ndim, ST(stream));
+}
 int dfl_ae_sigmoid(const float* zl, float* z, int n, void* stream) { return ae_sigmoid(zl, z, n, ST(stream)); }
 int dfl_ae_sparse_bwd(const float* z, float* dz, float* dzl, float* loss_kl, int B, int Z, int P, float rho, float w5,
                       void* stream) {

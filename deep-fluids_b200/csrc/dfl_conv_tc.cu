@@ -44,7 +44,7 @@ constexpr int CT_STAGE_BYTES = CT_A_BYTES + CT_B_BYTES;
 constexpr int CT_THREADS = 192;
 constexpr int CT_SMEM_BYTES = CT_STAGES * CT_STAGE_BYTES + 1024 /*align slack*/ + 1024 /*barriers, bias*/;
 
-enum : int { CF_LRELU = 1, CF_OUT2_UPSAMPLE = 2, CF_MASK_AFTER_RESIDUAL = 4 };
+enum : int { CF_LRELU = 1, CF_OUT2_UPSAMPLE = 2, CF_MASK_AFTER_RESIDUAL = 4, CF_SPLIT_IO = 8 };
 constexpr int CT_MAX_TAPS = 27;
 
 struct ConvTcParams {
@@ -63,6 +63,9 @@ struct ConvTcParams {
   int cout_small;
   // output tensor geometry (== B,D,H,W of the tile domain unless the generic tap kernel maps positions)
   int oD, oH, oW;
+  // virtual -> physical channel block of the input (64-channel slice c reads block blkmap[c >> 1]).  Identity except in
+  // the fp32-grade "bf16x3" mode, where the input is a (hi, lo) pair and the virtual blocks are [hi, lo, hi].
+  int blkmap[8];
   // ---- generic per-tap kernel only (strided / transposed-strided convolutions, explicit tap lists) ----
   int in_stride;              // A box origin = in_stride * tile origin + tap offset
   int out_stride, orz, ory, orx;   // output voxel = out_stride * tile voxel + (orz, ory, orx)
@@ -149,7 +152,7 @@ conv_tap_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             mbar_expect_tx(&full_bar[s], CT_STAGE_BYTES);
             uint8_t* sa = smem + s * CT_STAGE_BYTES;
             tma_load_5d(sa, &tmA, &full_bar[s], (c & 1) * CT_BLOCK_K, x0 * p.in_stride + p.tap_dx[t],
-                        y0 * p.in_stride + p.tap_dy[t], z0 * p.in_stride + p.tap_dz[t], b + (c >> 1) * p.B);
+                        y0 * p.in_stride + p.tap_dy[t], z0 * p.in_stride + p.tap_dz[t], b + p.blkmap[c >> 1] * p.B);
             tma_load_2d(sa + CT_A_BYTES, &tmB, &full_bar[s], p.tap_col[t] + c * CT_BLOCK_K, 0);
           }
       }
@@ -226,11 +229,50 @@ constexpr int C2_BRICK_BYTES = 4 * C2_SLOT_BYTES_3D;   // 94208 >= 2 * C2_SLOT_B
 constexpr int C2_THREADS = 224;
 constexpr int C2_SMEM_BYTES = C2_BRICK_BYTES + C2_BSTAGES * CT_B_BYTES + 1024 + 1024;
 
+// ---- epilogue helpers ------------------------------------------------------------------------------------
+__device__ __forceinline__ void epi_load32(const __nv_bfloat16* ptr, float (&f)[32]) {
+  const uint4* m = reinterpret_cast<const uint4*>(ptr);
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    float t[8];
+    unpack_bf16x8(__ldg(m + q), t);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) f[q * 8 + k] = t[k];
+  }
+}
+// store 32 channels as bf16; in split mode also the residual lo = bf16(v - float(bf16(v))) one block further
+__device__ __forceinline__ void epi_store32(__nv_bfloat16* ptr, const float (&v)[32], bool split, size_t blkstride) {
+  uint4* o = reinterpret_cast<uint4*>(ptr);
+  uint32_t w[16];
+#pragma unroll
+  for (int k = 0; k < 16; ++k) w[k] = pack_bf16x2(v[2 * k], v[2 * k + 1]);
+#pragma unroll
+  for (int q = 0; q < 4; ++q) o[q] = make_uint4(w[4 * q], w[4 * q + 1], w[4 * q + 2], w[4 * q + 3]);
+  if (split) {
+    uint4* l = reinterpret_cast<uint4*>(ptr + blkstride);
+    uint32_t wl[16];
+#pragma unroll
+    for (int k = 0; k < 16; ++k)
+      wl[k] = pack_bf16x2(v[2 * k] - __uint_as_float(w[k] << 16), v[2 * k + 1] - __uint_as_float(w[k] & 0xFFFF0000u));
+#pragma unroll
+    for (int q = 0; q < 4; ++q) l[q] = make_uint4(wl[4 * q], wl[4 * q + 1], wl[4 * q + 2], wl[4 * q + 3]);
+  }
+}
+
+// One accumulator row (one output voxel, 128 channels) -> outputs:
+//   v    = acc + bias;  lrelu if CF_LRELU
+//   out  = v * lrelu'(mask_src)                (mask only if given and not CF_MASK_AFTER_RESIDUAL)
+//   out2 = (v + residual) [* lrelu'(mask_src) if CF_MASK_AFTER_RESIDUAL], nearest-x2 replicated if CF_OUT2_UPSAMPLE
+// CF_SPLIT_IO (fp32-grade mode): every bf16 tensor is a (hi, lo) pair one block (B*voxels*128 elements) apart: residual
+// is read as hi + lo, outputs are written as hi = bf16(v), lo = bf16(v - hi); masks use the hi part (same sign).
 __device__ __forceinline__ void conv_epilogue_row(const ConvTcParams& p, uint32_t taddr, bool valid, int b, int z,
                                                   int y, int x, const float* s_bias) {
   const bool ups = (p.flags & CF_OUT2_UPSAMPLE) != 0;
   const bool act = (p.flags & CF_LRELU) != 0;
-  const bool mask_after = (p.flags & CF_MASK_AFTER_RESIDUAL) != 0;   // out2 = (v + residual) * lrelu'(mask_src)
+  const bool mask_after = (p.flags & CF_MASK_AFTER_RESIDUAL) != 0;
+  const bool split = (p.flags & CF_SPLIT_IO) != 0;
+  const size_t vox = static_cast<size_t>(p.oD) * p.oH * p.oW;
+  const size_t blk = static_cast<size_t>(p.B) * vox * CT_BLOCK_N;          // block stride of an output-shaped tensor
   const size_t pos = ((static_cast<size_t>(b) * p.oD + z) * p.oH + y) * p.oW + x;
 #pragma unroll 1
   for (int c0 = 0; c0 < CT_BLOCK_N; c0 += 32) {
@@ -238,69 +280,51 @@ __device__ __forceinline__ void conv_epilogue_row(const ConvTcParams& p, uint32_
     tmem_ld_32x32(taddr + c0, rr);
     tmem_ld_wait();
     if (!valid) continue;
-    float v[32];
+    float v[32], m[32];
 #pragma unroll
     for (int k = 0; k < 32; ++k) {
       float t = __uint_as_float(rr[k]) + s_bias[c0 + k];
       v[k] = act ? lrelu_f(t) : t;
     }
-    if (p.mask_src && !mask_after) {
-      const uint4* m = reinterpret_cast<const uint4*>(p.mask_src + pos * CT_BLOCK_N + c0);
+    if (p.mask_src) {
+      epi_load32(p.mask_src + pos * CT_BLOCK_N + c0, m);
 #pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        float f[8];
-        unpack_bf16x8(__ldg(m + q), f);
-#pragma unroll
-        for (int k = 0; k < 8; ++k) v[q * 8 + k] *= lrelu_grad_from_out(f[k]);
-      }
+      for (int k = 0; k < 32; ++k) m[k] = lrelu_grad_from_out(m[k]);
     }
     if (p.out) {
-      uint4* o = reinterpret_cast<uint4*>(p.out + pos * CT_BLOCK_N + c0);
+      float o[32];
 #pragma unroll
-      for (int q = 0; q < 4; ++q)
-        o[q] = make_uint4(pack_bf16x2(v[q * 8], v[q * 8 + 1]), pack_bf16x2(v[q * 8 + 2], v[q * 8 + 3]),
-                          pack_bf16x2(v[q * 8 + 4], v[q * 8 + 5]), pack_bf16x2(v[q * 8 + 6], v[q * 8 + 7]));
+      for (int k = 0; k < 32; ++k) o[k] = (p.mask_src && !mask_after) ? v[k] * m[k] : v[k];
+      epi_store32(p.out + pos * CT_BLOCK_N + c0, o, split, blk);
     }
     if (p.out2) {
       if (p.residual) {
-        const uint4* m = reinterpret_cast<const uint4*>(p.residual + pos * CT_BLOCK_N + c0);
+        float f[32];
+        epi_load32(p.residual + pos * CT_BLOCK_N + c0, f);
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          float f[8];
-          unpack_bf16x8(__ldg(m + q), f);
+        for (int k = 0; k < 32; ++k) v[k] += f[k];
+        if (split) {
+          epi_load32(p.residual + blk + pos * CT_BLOCK_N + c0, f);
 #pragma unroll
-          for (int k = 0; k < 8; ++k) v[q * 8 + k] += f[k];
+          for (int k = 0; k < 32; ++k) v[k] += f[k];
         }
       }
       if (p.mask_src && mask_after) {
-        const uint4* m = reinterpret_cast<const uint4*>(p.mask_src + pos * CT_BLOCK_N + c0);
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          float f[8];
-          unpack_bf16x8(__ldg(m + q), f);
-#pragma unroll
-          for (int k = 0; k < 8; ++k) v[q * 8 + k] *= lrelu_grad_from_out(f[k]);
-        }
+        for (int k = 0; k < 32; ++k) v[k] *= m[k];
       }
-      uint4 pk[4];
-#pragma unroll
-      for (int q = 0; q < 4; ++q)
-        pk[q] = make_uint4(pack_bf16x2(v[q * 8], v[q * 8 + 1]), pack_bf16x2(v[q * 8 + 2], v[q * 8 + 3]),
-                           pack_bf16x2(v[q * 8 + 4], v[q * 8 + 5]), pack_bf16x2(v[q * 8 + 6], v[q * 8 + 7]));
       if (!ups) {
-        uint4* o = reinterpret_cast<uint4*>(p.out2 + pos * CT_BLOCK_N + c0);
-#pragma unroll
-        for (int q = 0; q < 4; ++q) o[q] = pk[q];
+        epi_store32(p.out2 + pos * CT_BLOCK_N + c0, v, split, blk);
       } else {
+        // nearest-neighbour x2 (ops.py:75-91): out[2i+a] = in[i]; the z axis only when the conv is 3D
         const int zr = (p.kd > 1) ? 2 : 1;
         const int D2 = p.oD * zr, H2 = p.oH * 2, W2 = p.oW * 2;
+        const size_t blk2 = blk * (zr * 4);
         for (int a = 0; a < zr; ++a)
           for (int e = 0; e < 2; ++e)
             for (int f = 0; f < 2; ++f) {
               const size_t pos2 = ((static_cast<size_t>(b) * D2 + (z * zr + a)) * H2 + (2 * y + e)) * W2 + (2 * x + f);
-              uint4* o = reinterpret_cast<uint4*>(p.out2 + pos2 * CT_BLOCK_N + c0);
-#pragma unroll
-              for (int q = 0; q < 4; ++q) o[q] = pk[q];
+              epi_store32(p.out2 + pos2 * CT_BLOCK_N + c0, v, split, blk2);
             }
       }
     }
@@ -373,14 +397,14 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
               mbar_wait(&a_empty[j], (fills[j] & 1) ^ 1);
               mbar_expect_tx(&a_full[j], SLOT_TX);
               tma_load_5d(smem + j * SLOT_BYTES, &tmA, &a_full[j], (c & 1) * CT_BLOCK_K, x0 - 1, y0 - 1, z0 - 1 + j,
-                          b + (c >> 1) * p.B);
+                          b + p.blkmap[c >> 1] * p.B);
               ++fills[j];
             }
           } else {
             const int j = phase & 1;
             mbar_wait(&a_empty[j], (fills[j] & 1) ^ 1);
             mbar_expect_tx(&a_full[j], SLOT_TX);
-            tma_load_5d(smem + j * SLOT_BYTES, &tmA, &a_full[j], (c & 1) * CT_BLOCK_K, x0 - 1, y0 - 1, 0, b + (c >> 1) * p.B);
+            tma_load_5d(smem + j * SLOT_BYTES, &tmA, &a_full[j], (c & 1) * CT_BLOCK_K, x0 - 1, y0 - 1, 0, b + p.blkmap[c >> 1] * p.B);
             ++fills[j];
           }
         }
@@ -535,7 +559,7 @@ static int make_act_map(CUtensorMap* tm, const void* x, int cin, int nbatch, int
 // [cin/128 * B, D, H, W, 128]); cout = 128, or 1..16 for the output conv.
 int conv_tc_launch(const void* x, const void* w_packed, const float* bias, void* out, void* out2,
                    const void* residual, const void* mask_src, const int64_t* dims /*B,D,H,W*/, int nd, int cin,
-                   int cout, int flags, cudaStream_t st) {
+                   int cout, int flags, const int32_t* blkmap /*cin/128 entries or null*/, int nphys, cudaStream_t st) {
   const bool small = cout < 128;   // 128 -> 1..3 output conv: w_packed is [16][taps*cin], out is fp32 [.., cout]
   DFL_REQUIRE(cout == 128 || (cout >= 1 && cout <= 16), "conv_tc: Cout must be 128 or <= 16 (got %d)", cout);
   DFL_REQUIRE(cin == 64 || (cin >= 128 && cin % 128 == 0), "conv_tc: Cin must be 64 or a multiple of 128 (got %d)", cin);
@@ -564,12 +588,15 @@ int conv_tc_launch(const void* x, const void* w_packed, const float* bias, void*
   p.out_f32 = small ? static_cast<float*>(out) : nullptr;
   p.cout_small = small ? cout : 0;
   DFL_REQUIRE(out || out2, "conv_tc: no output buffer given");
+  const int nblk = std::max(1, cin / 128);
+  DFL_REQUIRE(nblk <= 8, "conv_tc: at most 8 channel blocks (Cin <= 1024)");
+  for (int i = 0; i < 8; ++i) p.blkmap[i] = (blkmap && i < nblk) ? blkmap[i] : i;
+  if (nphys <= 0) nphys = nblk;
 
   CUtensorMap tmA, tmB;
   {
     const uint32_t box[5] = {64, static_cast<uint32_t>(p.bw + 2), static_cast<uint32_t>(p.bh + 2), 1, 1};
-    const int nblk = std::max(1, cin / 128);
-    int rc = make_act_map(&tmA, x, cin, nblk * p.B, p.D, p.H, p.W, box, nullptr);   // one halo'd plane per TMA
+    int rc = make_act_map(&tmA, x, cin, nphys * p.B, p.D, p.H, p.W, box, nullptr);   // one halo'd plane per TMA
     if (rc) return rc;
   }
   {
@@ -640,6 +667,7 @@ int conv_tap_launch(const void* x, const void* w_packed, const float* bias, void
   p.orz = nd == 3 ? out_off[0] : 0;
   p.ory = out_off[nd - 2];
   p.orx = out_off[nd - 1];
+  for (int i = 0; i < 8; ++i) p.blkmap[i] = i;
   p.ntap = ntap;
   for (int t = 0; t < ntap; ++t) {
     p.tap_dz[t] = taps[4 * t]; p.tap_dy[t] = taps[4 * t + 1]; p.tap_dx[t] = taps[4 * t + 2]; p.tap_col[t] = taps[4 * t + 3];

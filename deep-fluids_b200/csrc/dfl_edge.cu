@@ -548,4 +548,128 @@ int ae_sparse_bwd(const float* z, float* dz, float* dzl, float* loss_kl, int B, 
   return DFL_OK;
 }
 
+// =============================================================================================
+// fp32-grade mode ("bf16x3", BASELINE config 2): every logical fp32 tensor is a (hi, lo) pair of bf16 tensors,
+// hi = bf16(v), lo = bf16(v - hi), stored as two consecutive channel blocks.  x*w ~ x_hi*w_hi + x_lo*w_hi + x_hi*w_lo
+// (the dropped lo*lo term is 2^-18 relative) is ONE tensor-core GEMM over the virtual input blocks [hi, lo, hi]
+// with the weight operand [w_hi | w_hi | w_lo] and fp32 accumulation.
+// =============================================================================================
+__device__ __forceinline__ void split_bf16(float v, __nv_bfloat16& hi, __nv_bfloat16& lo) {
+  hi = __float2bfloat16_rn(v);
+  lo = __float2bfloat16_rn(v - __bfloat162float(hi));
+}
+
+// W fp32 [taps][cin][cout] -> split operands, K laid out [tap][virtual block 0..2][128 channels] (channels >= cin/cout
+// of a padded operand stay zero: zero the buffers once):
+//   wf [cout_rows][taps*3*128]:  k = (t*3 + vb)*128 + ci,  vb = 0: w_hi, 1: w_hi, 2: w_lo      (forward)
+//   wd [cin_rows ][taps*3*128]:  k = ((taps-1-t)*3 + vb)*128 + co                              (dgrad)
+__global__ void pack_split_kernel(const float* __restrict__ W, __nv_bfloat16* __restrict__ wf,
+                                  __nv_bfloat16* __restrict__ wd, int taps, int cin, int cout) {
+  const size_t n = static_cast<size_t>(taps) * cin * cout;
+  const size_t ld = static_cast<size_t>(taps) * 384;
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int co = i % cout, ci = (i / cout) % cin, t = i / (static_cast<size_t>(cout) * cin);
+    __nv_bfloat16 hi, lo;
+    split_bf16(W[i], hi, lo);
+    if (wf) {
+      __nv_bfloat16* r = wf + co * ld + static_cast<size_t>(t) * 384 + ci;
+      r[0] = hi; r[128] = hi; r[256] = lo;
+    }
+    if (wd) {
+      __nv_bfloat16* r = wd + ci * ld + static_cast<size_t>(taps - 1 - t) * 384 + co;
+      r[0] = hi; r[128] = hi; r[256] = lo;
+    }
+  }
+}
+int pack_split(const float* W, void* wf, void* wd, int taps, int cin, int cout, cudaStream_t st) {
+  DFL_REQUIRE(cin <= 128 && cout <= 128, "pack_split: Cin, Cout <= 128");
+  const size_t n = static_cast<size_t>(taps) * cin * cout;
+  const int grid = static_cast<int>(std::min<size_t>((n + 255) / 256, static_cast<size_t>(num_sms()) * 16));
+  pack_split_kernel<<<grid, 256, 0, st>>>(W, static_cast<__nv_bfloat16*>(wf), static_cast<__nv_bfloat16*>(wd), taps, cin, cout);
+  DFL_LAUNCH_OK("pack_split_kernel");
+  return DFL_OK;
+}
+
+// fp32 [n][cin] -> (hi, lo) bf16 [2][n][cpad]; channels >= cin zero.  cpad = cin (plain split) or 128 (padded).
+__global__ void split_f32_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ out, size_t n, int cin, int cpad) {
+  const size_t total = n * cpad;
+  for (size_t idx = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; idx < total;
+       idx += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int c = idx % cpad;
+    const size_t v = idx / cpad;
+    __nv_bfloat16 hi = __float2bfloat16_rn(0.f), lo = hi;
+    if (c < cin) split_bf16(in[v * cin + c], hi, lo);
+    out[idx] = hi;
+    out[total + idx] = lo;
+  }
+}
+int split_f32(const float* in, void* out, size_t n, int cin, int cpad, cudaStream_t st) {
+  DFL_REQUIRE(cpad >= cin, "split_f32: cpad < cin");
+  const int grid = static_cast<int>(std::min<size_t>((n * cpad + 255) / 256, static_cast<size_t>(num_sms()) * 16));
+  split_f32_kernel<<<grid, 256, 0, st>>>(in, static_cast<__nv_bfloat16*>(out), n, cin, cpad);
+  DFL_LAUNCH_OK("split_f32_kernel");
+  return DFL_OK;
+}
+// (hi, lo) bf16 [2][n] -> fp32 [n]
+__global__ void merge_split_kernel(const __nv_bfloat16* __restrict__ in, float* __restrict__ out, size_t n) {
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x)
+    out[i] = __bfloat162float(in[i]) + __bfloat162float(in[n + i]);
+}
+int merge_split(const void* in, float* out, size_t n, cudaStream_t st) {
+  const int grid = static_cast<int>(std::min<size_t>((n + 255) / 256, static_cast<size_t>(num_sms()) * 16));
+  merge_split_kernel<<<grid, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(in), out, n);
+  DFL_LAUNCH_OK("merge_split_kernel");
+  return DFL_OK;
+}
+
+// pool_mask on (hi, lo) pairs: ds = sum of the children of g_hi + g_lo; dmasked = ds * lrelu'(mask_hi); outputs split
+__global__ void pool_mask_split_kernel(const __nv_bfloat16* __restrict__ g, const __nv_bfloat16* __restrict__ mask_src,
+                                       __nv_bfloat16* __restrict__ ds, __nv_bfloat16* __restrict__ dmasked, int B, int D,
+                                       int H, int W, int zr) {
+  const size_t ncoarse = static_cast<size_t>(B) * D * H * W;
+  const size_t nfine = ncoarse * zr * 4;
+  const size_t n = ncoarse * 128;
+  for (size_t idx = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; idx < n;
+       idx += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int c = idx & 127;
+    size_t v = idx >> 7;
+    const int x = v % W; v /= W;
+    const int y = v % H; v /= H;
+    const int z = v % D;
+    const int b = v / D;
+    const int D2 = D * zr, H2 = 2 * H, W2 = 2 * W;
+    float s = 0.f;
+    for (int a = 0; a < zr; ++a)
+      for (int e = 0; e < 2; ++e)
+        for (int f = 0; f < 2; ++f) {
+          const size_t pos2 = ((static_cast<size_t>(b) * D2 + (z * zr + a)) * H2 + (2 * y + e)) * W2 + (2 * x + f);
+          s += __bfloat162float(g[pos2 * 128 + c]) + __bfloat162float(g[(nfine + pos2) * 128 + c]);
+        }
+    __nv_bfloat16 hi, lo;
+    if (ds) {
+      split_bf16(s, hi, lo);
+      ds[idx] = hi;
+      ds[n + idx] = lo;
+    }
+    if (dmasked) {
+      split_bf16(s * lrelu_grad_from_out(__bfloat162float(mask_src[idx])), hi, lo);
+      dmasked[idx] = hi;
+      dmasked[n + idx] = lo;
+    }
+  }
+}
+int pool_mask_split(const void* g, const void* mask_src, void* ds, void* dmasked, const int64_t* cdims, int nd,
+                    cudaStream_t st) {
+  const int B = cdims[0], D = nd == 3 ? cdims[1] : 1, H = cdims[nd - 1], W = cdims[nd];
+  const size_t n = static_cast<size_t>(B) * D * H * W * 128;
+  const int grid = static_cast<int>(std::min<size_t>((n + 255) / 256, static_cast<size_t>(num_sms()) * 16));
+  pool_mask_split_kernel<<<grid, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(g), static_cast<const __nv_bfloat16*>(mask_src),
+                                               static_cast<__nv_bfloat16*>(ds), static_cast<__nv_bfloat16*>(dmasked), B, D, H, W,
+                                               nd == 3 ? 2 : 1);
+  DFL_LAUNCH_OK("pool_mask_split_kernel");
+  return DFL_OK;
+}
+
 }  // namespace dfl

@@ -115,17 +115,31 @@ class GeneratorEngine(object):
                 if k.endswith("weights"):
                     self.params.p(k).copy_(xavier_uniform(tuple(shp), g, self.device))
         self.variables = list(tab.keys())
-        # ---- bf16 GEMM operands
+        self.inference = bool(inference)
+        self._alloc_operands()
+        self.repack()
+        self._alloc()
+        self.z = None
+        self.adam_t = 0
+        self.debug = None
+
+    # ------------------------------------------------------------------ buffers (overridden by the fp32-grade engine)
+    precision = "bf16"
+
+    def _alloc_operands(self):
+        """bf16 GEMM operands: forward [Cout, taps*Cin], dgrad [Cin, taps'*Cout], output conv [16, taps*Cin]"""
+        filters = self.filters
         self.wf, self.wd = {}, {}
         for row in self.conv_names:
             for cn in row:
                 self.wf[cn] = torch.empty(filters, self.taps * filters, dtype=torch.bfloat16, device=self.device)
                 self.wd[cn] = torch.empty(filters, self.taps * filters, dtype=torch.bfloat16, device=self.device)
         self.w_last16 = torch.zeros(16, self.taps * filters, dtype=torch.bfloat16, device=self.device)
-        self.repack()
-        # ---- activations (bf16) and gradient scratch
+
+    def _alloc(self):
+        """activations (bf16) and gradient scratch"""
+        filters = self.filters
         bf = dict(dtype=torch.bfloat16, device=self.device)
-        self.inference = bool(inference)
         self.x0, self.y = [], []
         for i in range(self.rep):
             shp = [self.B] + self.level_shape[i] + [filters]
@@ -140,9 +154,6 @@ class GeneratorEngine(object):
         self.pot = torch.empty([self.B] + self.spatial + [self.cout], dtype=torch.float32, device=self.device)
         # gradient scratch is sized for the finest level and re-viewed per level
         self._gbuf = [] if self.inference else [torch.empty(top, **bf) for _ in range(4)]
-        self.z = None
-        self.adam_t = 0
-        self.debug = None
 
     # ------------------------------------------------------------------ helpers
     def _gview(self, k, level):

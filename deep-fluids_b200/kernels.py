@@ -8,7 +8,8 @@ import ctypes as C
 import torch
 
 from . import cabi
-from .cabi import F32, BF16, CONV_LRELU, CONV_OUT2_UPSAMPLE, CONV_MASK_AFTER_RESIDUAL, check, dims_array
+from .cabi import (F32, BF16, CONV_LRELU, CONV_OUT2_UPSAMPLE, CONV_MASK_AFTER_RESIDUAL, CONV_SPLIT_IO, check,
+                   dims_array)
 
 _DT = {torch.float32: F32, torch.bfloat16: BF16}
 
@@ -232,6 +233,50 @@ def ae_sparse_bwd(z, dz, dz_lin, loss_kl, p_num, rho, w5):
     B, Z = z.shape
     PROF.launches += 1
     check(cabi.lib().dfl_ae_sparse_bwd(_p(z), _p(dz), _p(dz_lin), _p(loss_kl), B, Z, p_num, rho, w5, _st()))
+
+
+# ------------------------------------------------------------------ fp32-grade mode (bf16x3 split operands)
+_SPLIT_MAP = (C.c_int32 * 3)(0, 1, 0)
+
+
+def pack_conv_weights_split(w, w_fwd, w_dgrad):
+    """fp32 TF-layout weights -> split tensor-core operands [rows][taps*384] (see dfl_pack_conv_weights_split)"""
+    cin, cout = w.shape[-2], w.shape[-1]
+    taps = w.numel() // (cin * cout)
+    PROF.launches += 1
+    check(cabi.lib().dfl_pack_conv_weights_split(_p(w), _p(w_fwd), _p(w_dgrad), taps, cin, cout, _st()))
+
+
+def conv3x3_split(x2, w_split, bias=None, out=None, out2=None, residual=None, mask_src=None, flags=0, cout=128):
+    """fp32-grade conv: x2 = (hi, lo) pair [2*B,(D,)H,W,128]; bf16 outputs / residual are pairs too; cout < 128 selects
+    the output-conv variant (fp32 out)."""
+    nd = x2.dim() - 2
+    d = dims_array((x2.shape[0] // 2,) + tuple(x2.shape[1:-1]))
+    flops = 2.0 * (x2.numel() // 256) * 384 * cout * (3 ** nd)
+    fl = flags | (CONV_SPLIT_IO if cout == 128 else 0)
+    PROF.timed("conv_tc", flops, lambda: check(cabi.lib().dfl_conv3x3_fwd_ex(
+        _p(x2), _p(w_split), _p(bias), _p(out), _p(out2), _p(residual), _p(mask_src), d, nd, 384, cout, fl, _SPLIT_MAP, 2,
+        _st())))
+
+
+def split_f32(x, out, cpad=None):
+    """fp32 [..., c] -> (hi, lo) pair written to out [2, ..., cpad]"""
+    c = x.shape[-1]
+    PROF.launches += 1
+    check(cabi.lib().dfl_split_f32(_p(x), _p(out), x.numel() // c, c, cpad or c, _st()))
+
+
+def merge_split(x2, out):
+    PROF.launches += 1
+    check(cabi.lib().dfl_merge_split(_p(x2), _p(out), out.numel(), _st()))
+
+
+def pool_mask_split(g2, mask_src, ds2, dmasked2):
+    ref = ds2 if ds2 is not None else dmasked2
+    nd = ref.dim() - 2
+    d = dims_array((ref.shape[0] // 2,) + tuple(ref.shape[1:-1]))
+    PROF.launches += 1
+    check(cabi.lib().dfl_pool_mask_split(_p(g2), _p(mask_src), _p(ds2), _p(dmasked2), d, nd, _st()))
 
 
 def conv3x3_wgrad(x, dpre, dw, db=None):

@@ -21,6 +21,7 @@ import torch.distributed as dist
 from . import dp
 from . import kernels as K
 from .engine import GeneratorEngine
+from .engine_fp32 import GeneratorEngineFP32
 
 
 class Trainer(object):
@@ -99,9 +100,11 @@ class Trainer(object):
             raise NotImplementedError("use_curl=False output path is not built yet (BASELINE configs all use curl)")
         if self.optimizer not in ('adam', 'gd'):
             raise Exception("[!] Invalid opimizer")              # sic, trainer.py:167
-        self.engine = GeneratorEngine(self.b_num, self.output_shape, z_dim=self.c_num, filters=self.filters,
-                                      num_conv=self.num_conv, repeat=self.repeat, name="G", device=self.device,
-                                      seed=self.config.random_seed)
+        self.precision = getattr(self.config, "precision", "bf16")
+        self._engine_cls = GeneratorEngineFP32 if self.precision == "fp32x3" else GeneratorEngine
+        self.engine = self._engine_cls(self.b_num, self.output_shape, z_dim=self.c_num, filters=self.filters,
+                                       num_conv=self.num_conv, repeat=self.repeat, name="G", device=self.device,
+                                       seed=self.config.random_seed)
         self.G_var = self.engine.variables
         self.G_s = self.engine.pot
         self._loss3 = torch.zeros(3, dtype=torch.float32, device=self.device)
@@ -327,9 +330,10 @@ class Trainer(object):
         """`reuse=True` generator on z:[test_b_num, c_num] (trainer.py:295-304): a forward-only engine sharing the
         trained variables.  The 3D trainer uses the 3D curl here (the reference's trainer3.py:188 applies the 2D curl
         to the 3-channel potential -- a bug that is not reproduced)."""
-        self.test_engine = GeneratorEngine(self.test_b_num, self.output_shape, z_dim=self.c_num, filters=self.filters,
-                                           num_conv=self.num_conv, repeat=self.repeat, name="G", device=self.device,
-                                           init=self.engine.params.state_dict(), inference=True)
+        cls = getattr(self, "_engine_cls", GeneratorEngine)
+        self.test_engine = cls(self.test_b_num, self.output_shape, z_dim=self.c_num, filters=self.filters,
+                               num_conv=self.num_conv, repeat=self.repeat, name="G", device=self.device,
+                               init=self.engine.params.state_dict(), inference=True)
 
     def generate_velocity(self, z):
         """G_ = curl(G_s(z)) for parameters z [n, c_num], n a multiple of test_b_num or <= it (sess.run(self.G_, {z}))."""

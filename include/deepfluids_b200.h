@@ -35,6 +35,7 @@ extern "C" {
 #define DFL_CONV_LRELU 1          /* y = max(v, 0.2 v)                      (ops.py:9-10)            */
 #define DFL_CONV_OUT2_UPSAMPLE 2  /* out2 is written nearest-x2 upsampled   (ops.py:75-91)          */
 #define DFL_CONV_MASK_AFTER_RESIDUAL 4 /* out2 = (v + residual) * lrelu'(mask_src) instead of v*lrelu' + residual */
+#define DFL_CONV_SPLIT_IO 8       /* fp32-grade mode: bf16 tensors are (hi, lo) pairs one channel block apart      */
 
 /* ---- lifecycle ------------------------------------------------------------------------------------- */
 int dfl_version(void);
@@ -157,6 +158,23 @@ int dfl_ae_loss_p(const float* z, const float* y, float* dz, float* loss_p, int 
 int dfl_ae_sigmoid(const float* z_lin, float* z, int n, void* stream);
 int dfl_ae_sparse_bwd(const float* z, float* dz, float* dz_lin, float* loss_kl, int B, int Z, int P, float rho, float w5,
                       void* stream);
+
+/* ---- fp32-grade mode "bf16x3" (BASELINE config 2: the reference's fp32 arithmetic on bf16 tensor cores) -------------
+ * A logical fp32 tensor is a (hi, lo) pair of bf16 tensors (hi = bf16(v), lo = bf16(v - hi)) stored as two consecutive
+ * channel blocks [2*B,(D,)H,W,128].  conv(x, w) ~ x_hi*w_hi + x_lo*w_hi + x_hi*w_lo is one dfl_conv3x3_fwd_ex launch with
+ * cin = 384 (virtual blocks), blkmap = {0, 1, 0}, nphys = 2, the operand from dfl_pack_conv_weights_split and
+ * DFL_CONV_SPLIT_IO (outputs written as pairs, residual read as hi + lo); fp32 accumulation in TMEM.  Weight gradients
+ * are three dfl_conv3x3_wgrad launches (hi.hi, lo.hi, hi.lo) accumulating into the same fp32 buffer. */
+int dfl_conv3x3_fwd_ex(const void* x, const void* w_packed, const float* bias, void* out, void* out2,
+                       const void* residual, const void* mask_src, const int64_t* dims, int ndim, int cin, int cout,
+                       int flags, const int32_t* blkmap, int nphys, void* stream);
+int dfl_pack_conv_weights_split(const float* w, void* w_fwd, void* w_dgrad, int taps, int cin, int cout, void* stream);
+/* fp32 [n][cin] -> (hi, lo) bf16 [2][n][cpad] (channels >= cin zero);  (hi, lo) bf16 [2][n] -> fp32 [n] */
+int dfl_split_f32(const float* in, void* out, size_t n, int cin, int cpad, void* stream);
+int dfl_merge_split(const void* in, float* out, size_t n, void* stream);
+/* dfl_pool_mask on (hi, lo) pairs (inputs and outputs) */
+int dfl_pool_mask_split(const void* g, const void* mask_src, void* ds, void* dmasked, const int64_t* cdims, int ndim,
+                        void* stream);
 
 /* ---- optimizer (tf.train.AdamOptimizer / GradientDescentOptimizer: trainer.py:160-165) ----------------- */
 /* flat fp32 buffers; lr_t = lr*sqrt(1-b2^t)/(1-b1^t) computed by the caller; m = v = NULL selects plain GD. */

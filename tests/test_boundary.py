@@ -15,7 +15,7 @@ def test_flag_names_and_defaults_match_reference(golden_dir):
         assert k in mine, "missing reference flag --%s" % k
         assert mine[k] == v, (k, mine[k], v)
     extra = set(mine) - set(ref)
-    assert extra == {"synthetic", "synthetic_samples", "max_step"}       # new knobs are optional, defaults inert
+    assert extra == {"synthetic", "synthetic_samples", "max_step", "precision"}   # new knobs are optional, defaults inert
     assert cfg.synthetic is False and cfg.max_step == 0
 
 

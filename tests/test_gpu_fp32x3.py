@@ -1,0 +1,164 @@
+"""GPU parity of the fp32-grade ("bf16x3" split operand) path used for BASELINE config 2 (the reference computes in
+fp32: data.py:81-83 placeholders, slim variables tf.float32) against the fp32 CPU oracle.
+
+Tolerances (written here as the spec asks): a (hi, lo) bf16 pair carries 16 mantissa bits (rel 2^-17 = 7.6e-6) and the
+product drops the lo*lo term (2^-18), accumulation is fp32 in TMEM.
+  * single conv                                  rel-L2 <= 2e-5
+  * generator potential (17 layers)              rel-L2 <= 1e-4,   loss within 1e-4 relative
+  * teacher-forced gradients (same lrelu masks)  rel-L2 <= 5e-4 (weights), 2e-3 (biases: cancelling sums)
+  * free-running gradients vs pure fp32          rel-L2 <= 2e-2   (rare lrelu / |.| sign flips, each a 5x / 2x change)
+"""
+from collections import OrderedDict
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from oracle import ref_model as M
+from oracle import ref_ops as R
+from oracle import ref_train as T
+
+
+def rel_l2(a, b):
+    a, b = a.double().cpu(), b.double().cpu()
+    return float((a - b).norm() / b.norm().clamp_min(1e-30))
+
+
+def _split(x, dev):
+    """host-side (hi, lo) split of an fp32 channels-last tensor -> [2B, ..., C] bf16 on the device"""
+    hi = x.bfloat16()
+    lo = (x - hi.float()).bfloat16()
+    return torch.cat([hi, lo], 0).to(dev).contiguous()
+
+
+def _merge(x2):
+    B = x2.shape[0] // 2
+    return (x2[:B].float() + x2[B:].float()).cpu()
+
+
+def test_split_merge_roundtrip():
+    from deepfluids_b200 import kernels as K
+    dev = torch.device("cuda:0")
+    g = torch.Generator().manual_seed(0)
+    x = torch.randn(5, 7, 9, 3, generator=g) * 3
+    out = torch.empty(2, 5, 7, 9, 128, dtype=torch.bfloat16, device=dev)
+    K.split_f32(x.to(dev), out, cpad=128)
+    torch.cuda.synchronize()
+    assert torch.equal(out[:, ..., 3:].float().cpu(), torch.zeros(2, 5, 7, 9, 125))
+    assert torch.equal(out[0, ..., :3].cpu(), x.bfloat16())
+    back = out[0, ..., :3].float() + out[1, ..., :3].float()
+    assert rel_l2(back, x) <= 8e-6
+    x = torch.randn(6, 8, 128, generator=g)
+    o2 = torch.empty(12, 8, 128, dtype=torch.bfloat16, device=dev)
+    K.split_f32(x.to(dev), o2)
+    m = torch.empty(6, 8, 128, device=dev)
+    K.merge_split(o2, m)
+    torch.cuda.synchronize()
+    assert torch.equal(m.cpu(), _merge(o2))
+    assert rel_l2(m, x) <= 8e-6
+
+
+@pytest.mark.parametrize("spatial,B", [([32, 48], 3), ([8, 16, 16], 2)])
+def test_split_conv_vs_fp32_oracle(spatial, B):
+    """conv + bias + lrelu + residual + x2 upsample on (hi, lo) pairs vs the fp32 oracle conv (ops.py:26-57)"""
+    from deepfluids_b200 import kernels as K
+    dev = torch.device("cuda:0")
+    nd = len(spatial)
+    g = torch.Generator().manual_seed(1)
+    x = torch.randn([B] + spatial + [128], generator=g)
+    res = torch.randn([B] + spatial + [128], generator=g)
+    w = torch.randn([3] * nd + [128, 128], generator=g) * 0.03
+    b = torch.randn(128, generator=g) * 0.1
+    taps = 3 ** nd
+    wf = torch.empty(128, taps * 384, dtype=torch.bfloat16, device=dev)
+    wd = torch.empty(128, taps * 384, dtype=torch.bfloat16, device=dev)
+    K.pack_conv_weights_split(w.to(dev), wf, wd)
+    x2, r2 = _split(x, dev), _split(res, dev)
+    y2 = torch.empty_like(x2)
+    up2 = torch.empty([2 * B] + [2 * s for s in spatial] + [128], dtype=torch.bfloat16, device=dev)
+    K.conv3x3_split(x2, wf, b.to(dev), out=y2, out2=up2, residual=r2, flags=K.CONV_LRELU | K.CONV_OUT2_UPSAMPLE)
+    torch.cuda.synchronize()
+    y_ref = R.conv_nd(x, w, b, 1, R.lrelu)
+    u_ref = (R.upscale if nd == 2 else R.upscale3)(y_ref + res, 2)
+    assert rel_l2(_merge(y2), y_ref) <= 2e-5
+    assert rel_l2(_merge(up2), u_ref) <= 2e-5
+    # dgrad operand + lrelu-derivative mask + un-masked second output (the backward use of the same kernel)
+    gy = torch.randn([B] + spatial + [128], generator=g)
+    g2 = _split(gy, dev)
+    dm2, dr2 = torch.empty_like(x2), torch.empty_like(x2)
+    K.conv3x3_split(g2, wd, None, out=dm2, out2=dr2, residual=r2, mask_src=y2[:B])
+    torch.cuda.synchronize()
+    xin = x.clone().requires_grad_(True)
+    (gx,) = torch.autograd.grad(R.conv_nd(xin, w, b, 1, None), xin, gy)
+    mask = torch.where(_merge(y2) > 0, torch.ones(()), torch.full((), 0.2))
+    assert rel_l2(_merge(dm2), gx * mask) <= 2e-5
+    assert rel_l2(_merge(dr2), gx + res) <= 2e-5
+
+
+def test_split_lastconv_and_pool():
+    from deepfluids_b200 import kernels as K
+    dev = torch.device("cuda:0")
+    g = torch.Generator().manual_seed(2)
+    B, spatial, C = 2, [16, 24], 1
+    x = torch.randn([B] + spatial + [128], generator=g)
+    w = torch.randn(3, 3, 128, C, generator=g) * 0.05
+    b = torch.randn(C, generator=g)
+    w16 = torch.zeros(16, 9 * 384, dtype=torch.bfloat16, device=dev)
+    wdl = torch.zeros(128, 9 * 384, dtype=torch.bfloat16, device=dev)
+    K.pack_conv_weights_split(w.to(dev), w16, wdl)
+    out = torch.empty([B] + spatial + [C], device=dev)
+    K.conv3x3_split(_split(x, dev), w16, b.to(dev), out=out, cout=C)
+    torch.cuda.synchronize()
+    assert rel_l2(out, R.conv_nd(x, w, b, 1, None)) <= 2e-5
+    # pooling of the children + lrelu mask on pairs
+    gx = torch.randn(B, 16, 24, 128, generator=g)
+    ysrc = torch.randn(B, 8, 12, 128, generator=g)
+    ds2 = torch.empty(2 * B, 8, 12, 128, dtype=torch.bfloat16, device=dev)
+    dm2 = torch.empty_like(ds2)
+    K.pool_mask_split(_split(gx, dev), ysrc.bfloat16().to(dev), ds2, dm2)
+    torch.cuda.synchronize()
+    pooled = gx.view(B, 8, 2, 12, 2, 128).sum((2, 4))
+    mask = torch.where(ysrc.bfloat16().float() > 0, torch.ones(()), torch.full((), 0.2))
+    assert rel_l2(_merge(ds2), pooled) <= 2e-5
+    assert rel_l2(_merge(dm2), pooled * mask) <= 2e-5
+
+
+@pytest.mark.parametrize("spatial,num_conv,B", [([32, 24], 2, 3), ([64, 48], 4, 2), ([16, 16, 16], 2, 2)])
+def test_generator_fp32x3_vs_fp32_oracle(spatial, num_conv, B):
+    from deepfluids_b200 import kernels as K
+    from deepfluids_b200.engine_fp32 import GeneratorEngineFP32
+    dev = torch.device("cuda:0")
+    nd = len(spatial)
+    cout = 3 if nd == 3 else 1
+    eng = GeneratorEngineFP32(B, spatial + [cout], z_dim=3, num_conv=num_conv, device=dev, seed=11)
+    x, y = T.synthetic_batch(B, spatial, seed=3)
+    pot = eng.forward(y.to(dev))
+    loss3, dpot, vel = K.stencil_loss_fwdbwd(pot, x.to(dev), want_vel=True)
+    eng.zero_grad()
+    eng.backward(dpot)
+    torch.cuda.synchronize()
+    var = eng.params.state_dict()
+    loss, l1, jl1, g_ref, pot_ref, grads = T.generator_loss_and_grads(y, x, var, num_conv=num_conv)
+    e_pot = rel_l2(pot, pot_ref)
+    assert e_pot <= 1e-4, e_pot
+    assert abs(loss3[0].item() - loss.item()) <= 1e-4 * abs(loss.item())
+    assert float(K.divergence(vel).abs().max()) <= 1e-5
+    acts = {"x0": [_merge(t) for t in eng.x0], "y": [[_merge(t) for t in row] for row in eng.y], "s": _merge(eng.s)}
+    tf_grads = T.teacher_forced_backward(y, var, acts, dpot.cpu(), num_conv=num_conv)
+    last_b = list(var.keys())[-1]
+    errs = OrderedDict((k, rel_l2(eng.params.g(k), tf_grads[k])) for k in var if k != last_b)
+    errs_e2e = OrderedDict((k, rel_l2(eng.params.g(k), grads[k])) for k in var if k != last_b)
+    scale_b = float(dpot.abs().sum())
+    assert float(eng.params.g(last_b).abs().max()) <= 1e-4 * scale_b
+
+    def mx(d, suffix):
+        sel = {k: v for k, v in d.items() if k.endswith(suffix)}
+        k = max(sel, key=sel.get)
+        return sel[k], k
+    report = "pot %.2e | chain: weights %.2e (%s) biases %.2e (%s) | e2e: weights %.2e (%s) biases %.2e (%s)" % (
+        (e_pot,) + mx(errs, "weights") + mx(errs, "biases") + mx(errs_e2e, "weights") + mx(errs_e2e, "biases"))
+    print(report)
+    assert mx(errs, "weights")[0] <= 5e-4 and mx(errs, "biases")[0] <= 2e-3, report
+    assert mx(errs_e2e, "weights")[0] <= 2e-2 and mx(errs_e2e, "biases")[0] <= 5e-2, report
