@@ -37,6 +37,13 @@ WORKLOADS = {
     "tiny": (False, 1, 32, 24, 4, "2D 32x24 plumbing check"),
 }
 ARCH = {"c5": "ae"}
+# BASELINE configs[1] is quoted in fp32 (the reference's TF graphs are fp32): it runs the fp32-grade split-operand path
+DEFAULT_PRECISION = {"c2": "fp32x3"}
+PRECISION_NOTE = {
+    "bf16": "bf16 operands/activations, fp32 accumulate (TMEM), fp32 master weights + Adam",
+    "fp32x3": "fp32-grade: activations/gradients/weights as (hi, lo) bf16 pairs (16-bit mantissa), x*w = 3 tcgen05 MMA "
+              "terms (hi*hi + lo*hi + hi*lo), fp32 accumulate (TMEM), fp32 master weights + Adam",
+}
 # algorithmic conv FLOPs per field, fwd+bwd
 FLOPS_PER_FIELD = {"c2": 58.0e9, "c3": 3196.0e9, "c4": 25575.0e9, "c5": 49471.0e9, "tiny": None}
 
@@ -204,7 +211,9 @@ def run_gpu_arm(args):
     from deepfluids_b200.trainer import Trainer
     from deepfluids_b200.trainer3 import Trainer3
 
-    cfg = make_config(args.workload)
+    precision = args.precision or DEFAULT_PRECISION.get(args.workload, "bf16")
+    cfg = make_config(args.workload, ["--precision=%s" % precision])
+    terms = 3 if precision == "fp32x3" else 1      # MMA terms executed per algorithmic multiply-add
     bm = BatchManager(cfg, device=dev, pool=2, rank=rank)
     tr = (Trainer3 if cfg.is_3d else Trainer)(cfg, bm)
     B = cfg.batch_size
@@ -291,10 +300,13 @@ def run_gpu_arm(args):
     conv_t, conv_f, conv_n = agg.get("conv_tc", [1e-9, 0.0, 1])
     wg_t, wg_f, wg_n = agg.get("wgrad_tc", [1e-9, 0.0, 1])
     st_t, st_b, st_n = agg.get("stencil_fused", [1e-9, 0.0, 1])
+    conv_f /= terms                     # PROF counts executed MMA flops; the roofline numerator is algorithmic flops
+    wg_f /= terms
     achieved = conv_f / conv_t / 1e12
     roofline = {"kernel": "conv_tc_kernel (tcgen05 implicit-GEMM conv, fwd + dgrad launches)", "bound": "tensor",
                 "achieved": achieved, "peak": peaks["tf_sustained"], "unit": "TFLOP/s",
                 "frac": achieved / peaks["tf_sustained"], "peak_source": "%s (sustained bf16, kernel timed inside a long step)" % peaks["src"],
+                "mma_terms_per_flop": terms, "executed_tflops": achieved * terms,
                 "launches_timed": conv_n, "avg_launch_ms": conv_t / conv_n * 1e3, "traffic": load_traffic("conv_tc_kernel"),
                 "share_of_step": conv_t / 2 / (ms_per_step * 1e-3),
                 "others": {
@@ -313,12 +325,12 @@ def run_gpu_arm(args):
         cpu = cpu_oracle_fields_per_sec(args.workload, 3, 1) if world == 1 and not args.no_cpu else None
         out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
-               "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+               "vs_baseline": None, "dtype": "bf16" if terms == 1 else "f32 (bf16x3 split operands)", "data": "synthetic",
                "config": {"workload": WORKLOADS[args.workload][5], "global_batch": B * world, "per_gpu_batch": B,
                           "parallelism": "dp%d" % world, "filters": 128, "num_conv": 4,
                           "l2": "per-step working set (>= %.0f MB of activations) exceeds the 126 MB L2; no flush needed"
                                 % (B * float(np.prod(bm._pool[0][0].shape[1:-1])) * 128 * 2 * 6 / 1e6),
-                          "precision": "bf16 operands/activations, fp32 accumulate (TMEM), fp32 master weights + Adam"},
+                          "precision": PRECISION_NOTE[precision]},
                "clocks": clocks, "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d,
                                          "d2h_bytes_per_step": 12, "ms_per_step": ms_e / args.steps},
                "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu}
@@ -343,6 +355,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", type=str, default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", type=str, default="c4", choices=sorted(WORKLOADS))
+    ap.add_argument("--precision", type=str, default=None, choices=["bf16", "fp32x3"],
+                    help="default: fp32x3 for c2 (BASELINE quotes it in fp32), bf16 otherwise")
     ap.add_argument("--no-cpu", dest="no_cpu", action="store_true", help="skip the cpu_baseline leg")
     args = ap.parse_args()
     _guard_stdout()

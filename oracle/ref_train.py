@@ -113,23 +113,29 @@ def synthetic_batch(batch, spatial, seed=123, z_dim=3, dtype=torch.float32, smoo
     return x.to(dtype), y.to(dtype)
 
 
-def teacher_forced_backward(z, var, acts, dpot, num_conv=4, name="G", operand_round=None):
+def teacher_forced_backward(z, var, acts, dpot, num_conv=4, name="G", operand_round=None, mask_from_acts=False):
     """Backward pass of the generator evaluated layer by layer with torch autograd, where every layer's INPUT is the
     activation tensor the device path actually stored (`acts` = {"x0": [per level], "y": [[per conv] per level],
     "s": top-level residual sum}, fp32 CPU copies).  Because the leaky-ReLU masks are then computed from the same
     forward state as on the device, this isolates the accuracy of the backward kernels (dgrad / wgrad / bias-grad /
     pooling / FC-backward) from the sign flips that bf16 activation noise causes in a free-running comparison.
-    `operand_round` (e.g. ref_model.bf16_round_ste) models the bf16 operand copy of the conv weights."""
+    `operand_round` (e.g. ref_model.bf16_round_ste) models the bf16 operand copy of the conv weights.
+    `mask_from_acts`: take the leaky-ReLU derivative from the sign of the STORED layer output instead of recomputing
+    the pre-activation here (a recomputation that differs by 1e-5 relative still flips ~1e-5 of the signs, each flip a
+    5x change of that element: rel-L2 ~ sqrt(1e-5) = 3e-3, which would hide a 1e-4-grade kernel error)."""
     rnd = operand_round if operand_round is not None else (lambda t: t)
     nd = acts["s"].dim() - 2
     rep = len(acts["x0"])
     grads = OrderedDict()
     n_last = rep * num_conv + 1
 
-    def layer_grads(xin, wname, act, gout):
+    def layer_grads(xin, wname, act, gout, yact=None):
         xin = xin.detach().clone().requires_grad_(True)
         w = var[wname + "/weights"].detach().clone().requires_grad_(True)
         b = var[wname + "/biases"].detach().clone().requires_grad_(True)
+        if mask_from_acts and yact is not None:
+            gout = gout * torch.where(yact > 0, torch.ones(()), torch.full((), 0.2))     # lrelu' (ops.py:13-14)
+            act = None
         out = R.conv_nd(xin, rnd(w), b, 1, act)
         gx, gw, gb = torch.autograd.grad(out, [xin, w, b], gout)
         grads[wname + "/weights"], grads[wname + "/biases"] = gw, gb
@@ -141,7 +147,7 @@ def teacher_forced_backward(z, var, acts, dpot, num_conv=4, name="G", operand_ro
         gy = ds
         for c in range(num_conv - 1, -1, -1):
             xin = acts["y"][i][c - 1] if c > 0 else acts["x0"][i]
-            gy = layer_grads(xin, "%s/%d_conv" % (name, i * num_conv + c + 1), R.lrelu, gy)
+            gy = layer_grads(xin, "%s/%d_conv" % (name, i * num_conv + c + 1), R.lrelu, gy, acts["y"][i][c])
         gx0 = gy + ds
         if i > 0:      # adjoint of nearest x2 upsampling: sum over the children
             u = torch.zeros_like(acts["x0"][i - 1]).requires_grad_(True)

@@ -5,8 +5,11 @@ Tolerances (written here as the spec asks): a (hi, lo) bf16 pair carries 16 mant
 product drops the lo*lo term (2^-18), accumulation is fp32 in TMEM.
   * single conv                                  rel-L2 <= 2e-5
   * generator potential (17 layers)              rel-L2 <= 1e-4,   loss within 1e-4 relative
-  * teacher-forced gradients (same lrelu masks)  rel-L2 <= 5e-4 (weights), 2e-3 (biases: cancelling sums)
-  * free-running gradients vs pure fp32          rel-L2 <= 2e-2   (rare lrelu / |.| sign flips, each a 5x / 2x change)
+  * teacher-forced gradients (the oracle's backward fed with the stored activations AND their lrelu masks)
+                                                 rel-L2 <= 2e-4 (weights), 2e-3 (biases: cancelling sums)
+  * free-running gradients vs pure fp32          rel-L2 <= 2e-2   (a 1e-5 relative difference in a pre-activation or
+    in G - x flips ~1e-5 of the lrelu / |.| signs, each a 5x / 2x change of that element: sqrt(1e-5) = 3e-3 measured;
+    the same mechanism separates any two fp32 implementations at the sqrt(1e-7) = 3e-4 level)
 """
 from collections import OrderedDict
 
@@ -146,7 +149,7 @@ def test_generator_fp32x3_vs_fp32_oracle(spatial, num_conv, B):
     assert abs(loss3[0].item() - loss.item()) <= 1e-4 * abs(loss.item())
     assert float(K.divergence(vel).abs().max()) <= 1e-5
     acts = {"x0": [_merge(t) for t in eng.x0], "y": [[_merge(t) for t in row] for row in eng.y], "s": _merge(eng.s)}
-    tf_grads = T.teacher_forced_backward(y, var, acts, dpot.cpu(), num_conv=num_conv)
+    tf_grads = T.teacher_forced_backward(y, var, acts, dpot.cpu(), num_conv=num_conv, mask_from_acts=True)
     last_b = list(var.keys())[-1]
     errs = OrderedDict((k, rel_l2(eng.params.g(k), tf_grads[k])) for k in var if k != last_b)
     errs_e2e = OrderedDict((k, rel_l2(eng.params.g(k), grads[k])) for k in var if k != last_b)
@@ -160,5 +163,5 @@ def test_generator_fp32x3_vs_fp32_oracle(spatial, num_conv, B):
     report = "pot %.2e | chain: weights %.2e (%s) biases %.2e (%s) | e2e: weights %.2e (%s) biases %.2e (%s)" % (
         (e_pot,) + mx(errs, "weights") + mx(errs, "biases") + mx(errs_e2e, "weights") + mx(errs_e2e, "biases"))
     print(report)
-    assert mx(errs, "weights")[0] <= 5e-4 and mx(errs, "biases")[0] <= 2e-3, report
+    assert mx(errs, "weights")[0] <= 2e-4 and mx(errs, "biases")[0] <= 2e-3, report
     assert mx(errs_e2e, "weights")[0] <= 2e-2 and mx(errs_e2e, "biases")[0] <= 5e-2, report
