@@ -497,19 +497,35 @@ static void stencil_plan(int nd, const int64_t* dims, StencilParams& p) {
   }
 }
 
+// dfl_stencil3_lean.cu: all-fp32 3D fast path (persistent CTAs, <= stencil3d_lean_max_blocks() partial sums)
+int stencil3d_lean_max_blocks();
+int stencil3d_lean_launch(const float* A, const float* X, float* dA, float* vel, double* partials, int B, int D, int H,
+                          int W, float c1, float c2, cudaStream_t st, int* nblk);
+
 size_t stencil_loss_workspace_bytes(int nd, const int64_t* dims) {
   StencilParams p{};
   stencil_plan(nd, dims, p);
-  return static_cast<size_t>(stencil_grid(p, nd)) * 2 * sizeof(double);
+  const int blocks = std::max(stencil_grid(p, nd), stencil3d_lean_max_blocks());
+  return static_cast<size_t>(blocks) * 2 * sizeof(double);
 }
 
 template <typename TP, typename TX_, typename TO>
 static int stencil_launch_typed(int nd, const void* pot, const void* x, void* dpot, void* vel, float* loss3,
                                 void* workspace, const StencilParams& p, double n1, double n2, float w1, float w2,
                                 cudaStream_t st) {
-  const int grid = stencil_grid(p, nd);
+  int grid = stencil_grid(p, nd);
   double* part = static_cast<double*>(workspace);
-  if (nd == 3) {
+  int lean_blocks = 0;
+  if (nd == 3 && std::is_same<TP, float>::value && std::is_same<TX_, float>::value && std::is_same<TO, float>::value &&
+      !getenv("DFL_STENCIL_GENERIC")) {
+    const int rc = stencil3d_lean_launch(static_cast<const float*>(pot), static_cast<const float*>(x),
+                                         static_cast<float*>(dpot), static_cast<float*>(vel), part, p.B, p.D, p.H, p.W,
+                                         p.c1, p.c2, st, &lean_blocks);
+    if (rc != DFL_OK) return rc;
+  }
+  if (lean_blocks > 0) {
+    grid = lean_blocks;
+  } else if (nd == 3) {
     dim3 blk(S3_TX, S3_TY);
     if (vel)
       stencil3d_fused_kernel<TP, TX_, TO, true><<<grid, blk, 0, st>>>(

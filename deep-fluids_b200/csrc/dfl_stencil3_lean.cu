@@ -1,0 +1,376 @@
+// deepfluids_b200 -- 3D fused curl + Jacobian-L1 loss + adjoint, "lean" formulation (all-fp32 tensors, W even).
+//
+// Same math and the same reference call sites as dfl_stencil.cu (ops.py:205-262 jacobian3 incl. the 3D curl,
+// trainer3.py:18-51 loss, TF autodiff adjoints); that file's generic kernel remains the path for other dtypes / odd W.
+// This kernel exists because the generic one is instruction-issue bound at ~1470 thread-instructions per voxel
+// (ncu, profiles/ncu_summary.json): with 36 algorithmic bytes per voxel the HBM roofline leaves only ~270
+// thread-instructions per voxel at 70 % of peak, so the formulation -- not the memory system -- is what has to shrink:
+//   * two x-adjacent voxels per thread (float2 everywhere: LDG.64 / LDS.64 / STS.64, half the address arithmetic);
+//   * every forward residual F_a = D_a G - D_a x and its sign is evaluated ONCE per voxel and handed to the -1
+//     neighbour through shared memory (x, y) or a register (z) instead of being recomputed as a backward residual;
+//   * boundary rules (replicate-last difference, folded adjoint) are per-thread constants (signs, weights, offsets),
+//     not per-access index clamps; plane buffers are addressed linearly by thread id (conflict-free);
+//   * halo rows only run the pipeline stages whose results are consumed (2+2 halo rows, staged predication);
+//   * persistent CTAs (one per SM) split the (column, z) work list evenly, so there is no wave quantisation and the
+//     z warm-up (4 planes) is paid about twice per CTA.
+// Pipeline per z-iteration t (one barrier): A[t] -> G[t-1] -> F,sgn[t-2] -> dL/dG[t-3] -> dL/dA[t-4].
+#include "dfl_common.cuh"
+
+namespace dfl {
+
+struct Lean3Params {
+  int B, D, H, W;
+  float c1, c2;
+  int ntx, nty, oxc, oy, tpr, tr, nthr, ncols;
+  int tpr8;          // bytes between two rows of a float2 plane
+};
+
+__device__ __forceinline__ float sg1(float v) { return (v > 0.f ? 1.f : 0.f) - (v < 0.f ? 1.f : 0.f); }
+__device__ __forceinline__ float2 sg2(float2 v) { return make_float2(sg1(v.x), sg1(v.y)); }
+__device__ __forceinline__ float2 operator-(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
+__device__ __forceinline__ float2 operator+(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
+__device__ __forceinline__ float abs2sum(float2 v) { return fabsf(v.x) + fabsf(v.y); }
+
+constexpr int L3_THREADS = 512;
+constexpr int L3_PS = L3_THREADS + 2;            // float2 slots per smem plane (thread-linear + 1 slot of x+1 overrun)
+// smem layout in floats: [parity][family][3][L3_PS] float2 for the families A, G, X, Sy, D; then Sx [parity][3][L3_PS] float.
+// G, Sy, D planes are per component (u, v, w) x (voxel 0, voxel 1); A and X planes hold the three float2 exactly as they
+// are loaded from the interleaved tensors: P0 = (u0, v0), P1 = (w0, u1), P2 = (v1, w1)  (no register shuffling).
+constexpr int L3_FAM = 3 * L3_PS * 2;            // floats per family
+constexpr int L3_PAR = 5 * L3_FAM;               // floats per parity of the float2 families
+constexpr int L3_SX0 = 2 * L3_PAR;               // float offset of the Sx family
+constexpr int L3_SXPAR = 3 * L3_PS;              // floats per parity of Sx
+constexpr int L3_SMEM_FLOATS = L3_SX0 + 2 * L3_SXPAR;
+static_assert(L3_SMEM_FLOATS % 4 == 0, "smem zeroing uses float4");
+enum { FA = 0, FG = 1, FX = 2, FS = 3, FD = 4 };
+
+// interleaved pair of voxels: r[0] = (u0, v0), r[1] = (w0, u1), r[2] = (v1, w1)
+struct Raw3 { float2 r[3]; };
+__device__ __forceinline__ float2 cU(const Raw3& a) { return make_float2(a.r[0].x, a.r[1].y); }
+__device__ __forceinline__ float2 cV(const Raw3& a) { return make_float2(a.r[0].y, a.r[2].x); }
+__device__ __forceinline__ float2 cW(const Raw3& a) { return make_float2(a.r[1].x, a.r[2].y); }
+__device__ __forceinline__ float2 comp(const Raw3& a, int c) { return c == 0 ? cU(a) : (c == 1 ? cV(a) : cW(a)); }
+
+// per-thread constants of one (column, z-range) segment
+struct L3Thread {
+  float wx0, wx1, wy, wym, c2wym, ysgn, xs1;
+  int yo8;                        // byte offset of the replicate-aware y neighbour row
+  int ycase;
+  bool inD, rowG, rowF, rowDG, outp, lastx;
+  int zs, ze;
+};
+
+__device__ __forceinline__ float2 lds2(uint32_t a) {
+  float2 v;
+  asm volatile("ld.shared.v2.f32 {%0,%1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ float lds1(uint32_t a) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ void sts2(uint32_t a, float2 v) { asm volatile("st.shared.v2.f32 [%0], {%1,%2};" ::"r"(a), "f"(v.x), "f"(v.y)); }
+__device__ __forceinline__ void sts1(uint32_t a, float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(a), "f"(v)); }
+__device__ __forceinline__ void ld3(const float* q, Raw3& a) {
+  const float2* q2 = reinterpret_cast<const float2*>(q);
+  a.r[0] = __ldg(q2); a.r[1] = __ldg(q2 + 1); a.r[2] = __ldg(q2 + 2);
+}
+__device__ __forceinline__ void st3(float* q, float2 u, float2 v, float2 w) {
+  float2* o = reinterpret_cast<float2*>(q);
+  o[0] = make_float2(u.x, v.x); o[1] = make_float2(w.x, u.y); o[2] = make_float2(v.y, w.y);
+}
+constexpr uint32_t fam8(int fam, int c) { return static_cast<uint32_t>((fam * L3_FAM + c * L3_PS * 2) * 4); }
+
+// One z-iteration t.  wb / rb: byte addresses of this thread's slot in the parity written now / written last iteration;
+// wsx / rsx the same for the scalar Sx family.  Register roles (ping-pong, swapped by the caller every iteration):
+//   aO = A[t-1] (becomes the landing buffer of A[t+1]),  aN = A[t]
+//   gO = G[t-2], gN <- G[t-1];   xO = x[t-2] (becomes the landing buffer of x[t]),  xN = x[t-1]
+//   dO = dL/dG[t-4], dN <- dL/dG[t-3]
+// pa -> A[t+1], px -> x[t], pd -> dA[t-4], pv -> vel[t-1] of this thread's voxel pair (advanced one plane per call).
+template <bool kVel, bool kSteady>
+__device__ __forceinline__ void l3_iter(const int t, const Lean3Params& p, const L3Thread& T, const uint32_t wb,
+                                        const uint32_t rb, const uint32_t wsx, const uint32_t rsx, Raw3& aO, Raw3& aN,
+                                        float2 (&gO)[3], float2 (&gN)[3], Raw3& xO, Raw3& xN, float2 (&dO)[3],
+                                        float2 (&dN)[3], float2 (&szP)[3], float2 (&dgP)[3], float2 (&ghzP)[2],
+                                        float2& dzu, float2& dzv, float& facc_l1, float& facc_j, const float*& pa,
+                                        const float*& px, float*& pd, float*& pv, const int plane3) {
+  const int D = p.D, zs = T.zs, ze = T.ze;
+  const uint32_t tpr8 = p.tpr8;
+  // ---------------------------------------------------------------- S0/S1: A[t] -> smem;  G[q1] = curl(A)[q1], q1 = t-1
+  if (T.inD) {
+#pragma unroll
+    for (int i = 0; i < 3; ++i) sts2(wb + fam8(FA, i), aN.r[i]);
+  }
+  {
+    const int q1 = t - 1;
+    if (kSteady || (q1 >= 0 && q1 < D && q1 <= ze)) {          // uniform
+      if (T.rowG) {
+        if (kSteady || q1 <= D - 2) { dzu = cU(aN) - cU(aO); dzv = cV(aN) - cV(aO); }   // else: replicate the last z difference
+        const float2 y0 = lds2(rb + fam8(FA, 0) + T.yo8), y1 = lds2(rb + fam8(FA, 1) + T.yo8), y2 = lds2(rb + fam8(FA, 2) + T.yo8);
+        const float2 yw = make_float2(y1.x, y2.y), yu = make_float2(y0.x, y1.y);
+        const float2 aw = cW(aO), av = cV(aO), au = cU(aO);
+        const float nw = T.lastx ? aw.x : lds1(rb + fam8(FA, 1) + 8);        // next thread's w0
+        const float nv = T.lastx ? av.x : lds1(rb + fam8(FA, 0) + 12);       // next thread's v0
+        const float2 dwdx = make_float2(aw.y - aw.x, T.xs1 * (nw - aw.y));
+        const float2 dvdx = make_float2(av.y - av.x, T.xs1 * (nv - av.y));
+        const float2 dwy = yw - aw, duy = yu - au;
+        gN[0] = make_float2(fmaf(T.ysgn, dwy.x, -dzv.x), fmaf(T.ysgn, dwy.y, -dzv.y));     // dwdy - dvdz (ops.py:255)
+        gN[1] = dzu - dwdx;                                                              // dudz - dwdx (ops.py:256)
+        gN[2] = make_float2(fmaf(-T.ysgn, duy.x, dvdx.x), fmaf(-T.ysgn, duy.y, dvdx.y));   // dvdx - dudy (ops.py:257)
+#pragma unroll
+        for (int c = 0; c < 3; ++c) sts2(wb + fam8(FG, c), gN[c]);
+        if (kVel && T.outp && (kSteady || (q1 >= zs && q1 < ze))) st3(pv, gN[0], gN[1], gN[2]);
+      }
+    }
+  }
+  // A[t-1] is dead now: its registers receive A[t+1]
+  if (T.inD && (kSteady || (t + 1 >= 0 && t + 1 < D && t + 1 <= ze + 1))) ld3(pa, aO);
+
+  // ---------------------------------------------------------------- S3: complete dL/dG[q3], q3 = t-3
+  {
+    const int q3 = t - 3;
+    if (kSteady || (q3 >= 0 && q3 < D && q3 >= zs - 1 && q3 <= ze)) {   // uniform
+      if (T.rowDG) {
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          const float sxn = lds1(rsx + c * L3_PS * 4 - 4);
+          const float2 syn = lds2(rb + fam8(FS, c) - tpr8);
+          dN[c].x = fmaf(p.c2, fmaf(T.wym, syn.x, sxn), dgP[c].x);
+          dN[c].y = fmaf(T.c2wym, syn.y, dgP[c].y);
+          sts2(wb + fam8(FD, c), dN[c]);
+        }
+      }
+    }
+  }
+
+  // ---------------------------------------------------------------- S2: residuals, signs, loss at q2 = t-2
+  {
+    const int q2 = t - 2;
+    if (kSteady || (q2 >= 0 && q2 < D && q2 >= zs - 2 && q2 <= ze)) {   // uniform
+      if (T.rowF) {
+        const float wz = kSteady ? 1.f : ((q2 >= D - 1) ? 0.f : (q2 == D - 2 ? 2.f : 1.f));
+        const bool zin = kSteady || (q2 >= zs && q2 < ze);     // uniform
+        Raw3 xy;                                               // x[q2] one row up, and the next thread's voxel 0
+        xy.r[0] = lds2(rb + fam8(FX, 0) + tpr8); xy.r[1] = lds2(rb + fam8(FX, 1) + tpr8); xy.r[2] = lds2(rb + fam8(FX, 2) + tpr8);
+        const float2 xn01 = lds2(rb + fam8(FX, 0) + 8);        // (u0, v0) of the next thread
+        const float xn2 = lds1(rb + fam8(FX, 1) + 8);          // w0 of the next thread
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          const float2 Gy = lds2(rb + fam8(FG, c) + tpr8);
+          const float Gx = lds1(rb + fam8(FG, c) + 8);
+          const float2 Xy = comp(xy, c);
+          const float Xx = c == 0 ? xn01.x : (c == 1 ? xn01.y : xn2);
+          const float2 g = gO[c], x = comp(xO, c);
+          const float2 Fx = make_float2((g.y - g.x) - (x.y - x.x), (Gx - g.y) - (Xx - x.y));
+          const float2 Fy = (Gy - g) - (Xy - x);
+          const float2 Fz = (gN[c] - g) - (comp(xN, c) - x);
+          const float2 e = g - x;
+          const float2 sx = sg2(Fx), sy = sg2(Fy), sz = sg2(Fz), se = sg2(e);
+          const float2 szw = make_float2(wz * sz.x, wz * sz.y);
+          const float wsx0 = T.wx0 * sx.x;
+          const float a0 = fmaf(-T.wy, sy.x, (szP[c].x - szw.x) - wsx0);
+          const float a1 = fmaf(-T.wy, sy.y, fmaf(-T.wx1, sx.y, (szP[c].y - szw.y) + wsx0));
+          dgP[c] = make_float2(fmaf(p.c2, a0, p.c1 * se.x), fmaf(p.c2, a1, p.c1 * se.y));
+          szP[c] = szw;
+          sts1(wsx + c * L3_PS * 4, sx.y);
+          sts2(wb + fam8(FS, c), sy);
+          if (zin && T.outp) {
+            facc_l1 += abs2sum(e);
+            facc_j += fmaf(T.wx0, fabsf(Fx.x), T.wx1 * fabsf(Fx.y)) + fmaf(T.wy, abs2sum(Fy), wz * abs2sum(Fz));
+          }
+        }
+      }
+    }
+  }
+  // x[t-1] -> smem for next iteration's neighbours; x[t-2] is dead: its registers receive x[t]
+  if (T.inD) {
+#pragma unroll
+    for (int i = 0; i < 3; ++i) sts2(wb + fam8(FX, i), xN.r[i]);
+    if (kSteady || (t >= 0 && t < D && t <= ze)) ld3(px, xO);
+  }
+
+  // ---------------------------------------------------------------- S4: dL/dA[r4] = curl^T(dL/dG), r4 = t-4
+  {
+    const int r4 = t - 4;
+    float2 ghz0, ghz1;                        // folded z field gh[r4] of the U, V components (uniform case split)
+    if (!kSteady && (r4 < 0 || r4 >= D - 1)) { ghz0 = ghz1 = make_float2(0.f, 0.f); }
+    else if (!kSteady && r4 == D - 2) { ghz0 = dO[0] + dN[0]; ghz1 = dO[1] + dN[1]; }
+    else { ghz0 = dO[0]; ghz1 = dO[1]; }
+    if ((kSteady || (r4 >= zs && r4 < ze)) && T.outp) {
+      const float2 dzT_U = ghzP[0] - ghz0, dzT_V = ghzP[1] - ghz1;
+      // y: gh[cy-1] - gh[cy] for W (2) and U (0)
+      float2 mW = lds2(rb + fam8(FD, 2) - tpr8), mU = lds2(rb + fam8(FD, 0) - tpr8);
+      float2 hW = dO[2], hU = dO[0];
+      if (T.ycase == 1) { hW = hW + lds2(rb + fam8(FD, 2) + tpr8); hU = hU + lds2(rb + fam8(FD, 0) + tpr8); }
+      if (T.ycase == 2) { mW = mW + dO[2]; mU = mU + dO[0]; hW = make_float2(0.f, 0.f); hU = hW; }
+      const float2 dyT_W = mW - hW, dyT_U = mU - hU;
+      // x: gh[cx-1] - gh[cx] for W (2) and V (1);  g[cx0-1] is the left thread's voxel 1
+      const float lW = lds1(rb + fam8(FD, 2) - 4), lV = lds1(rb + fam8(FD, 1) - 4);
+      const float h0W = T.lastx ? dO[2].x + dO[2].y : dO[2].x, h0V = T.lastx ? dO[1].x + dO[1].y : dO[1].x;
+      const float h1W = T.lastx ? 0.f : dO[2].y, h1V = T.lastx ? 0.f : dO[1].y;
+      const float2 dxT_W = make_float2(lW - h0W, h0W - h1W), dxT_V = make_float2(lV - h0V, h0V - h1V);
+      st3(pd, dzT_V - dyT_W, dxT_W - dzT_U, dyT_U - dxT_V);
+    }
+    ghzP[0] = ghz0; ghzP[1] = ghz1;
+  }
+  pa += plane3; px += plane3; pd += plane3;
+  if (kVel) pv += plane3;
+  __syncthreads();
+}
+
+template <bool kVel>
+__global__ void __launch_bounds__(L3_THREADS, 1)
+stencil3d_lean_kernel(const float* __restrict__ A, const float* __restrict__ X, float* __restrict__ dA,
+                      float* __restrict__ vel, double* __restrict__ partials, const __grid_constant__ Lean3Params p) {
+  extern __shared__ __align__(16) float smem[];
+  const int tid = threadIdx.x;
+  const bool act = tid < p.nthr;
+  const int tpr = p.tpr, tr = p.tr;
+  const int r = tid / tpr, k = tid - r * tpr;
+  const int D = p.D, H = p.H, W = p.W;
+  const int plane3 = H * W * 3;  // floats per z plane (H*W*3 < 2^31 checked on the host)
+  const uint32_t s0 = static_cast<uint32_t>(__cvta_generic_to_shared(smem));
+  const uint32_t slot = s0 + tid * 8, slot_sx = s0 + L3_SX0 * 4 + tid * 4;
+
+  // even split of the (column, plane) work list over the persistent CTAs
+  const long long total = static_cast<long long>(p.ncols) * D;
+  long long u = total * blockIdx.x / gridDim.x;
+  const long long u_end = total * (blockIdx.x + 1) / gridDim.x;
+
+  float facc_l1 = 0.f, facc_j = 0.f;
+
+  while (u < u_end) {
+    const int col = static_cast<int>(u / D);
+    L3Thread T;
+    T.zs = static_cast<int>(u - static_cast<long long>(col) * D);
+    T.ze = static_cast<int>(min(static_cast<long long>(D), T.zs + (u_end - u)));
+    u += T.ze - T.zs;
+    const int tx = col % p.ntx, ty = (col / p.ntx) % p.nty, b = col / (p.ntx * p.nty);
+    const int cy = ty * p.oy - 2 + r, cx0 = tx * p.oxc - 2 + 2 * k;
+    T.inD = act && cy >= 0 && cy < H && cx0 >= 0 && cx0 < W;
+    const bool top = (cy == H - 1);
+    T.rowG = T.inD && r <= tr - 2;
+    T.rowF = T.inD && (r <= tr - 3 || (r == tr - 2 && top));
+    T.rowDG = T.rowF && r >= 1;
+    T.outp = T.inD && r >= 2 && r <= tr - 3 && k >= 1 && k <= (p.oxc >> 1);
+    T.lastx = (cx0 == W - 2);
+    T.wx0 = T.lastx ? 2.f : 1.f;
+    T.wx1 = T.lastx ? 0.f : 1.f;
+    T.wy = (cy >= H - 1) ? 0.f : (cy == H - 2 ? 2.f : 1.f);
+    T.wym = top ? 2.f : 1.f;                      // wgt(cy-1, H) for in-domain cy-1 (cy = 0 reads zeros)
+    T.c2wym = p.c2 * T.wym;
+    T.ysgn = top ? -1.f : 1.f;
+    T.xs1 = T.lastx ? -1.f : 1.f;
+    T.yo8 = top ? -p.tpr8 : p.tpr8;               // replicate-last: the y "forward" neighbour of the last row is row-1
+    T.ycase = (cy == H - 2) ? 1 : (top ? 2 : 0);
+    // voxel (b, z, cy, cx0) = float offset base + z*plane3
+    const size_t base = (static_cast<size_t>(b) * D * H + (T.inD ? cy : 0)) * W * 3 + (T.inD ? cx0 : 0) * 3;
+
+    // ---- reset: zero every smem plane (out-of-domain threads never write; a previous segment's halo must not leak)
+    __syncthreads();
+    for (int i = tid; i < L3_SMEM_FLOATS / 4; i += L3_THREADS) reinterpret_cast<float4*>(smem)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    __syncthreads();
+
+    Raw3 a0, a1, x0, x1;
+    float2 g0[3], g1[3], d0[3], d1[3], szP[3], dgP[3], ghzP[2];
+    const float2 z2 = make_float2(0.f, 0.f);
+    float2 dzu = z2, dzv = z2;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) a0.r[c] = a1.r[c] = x0.r[c] = x1.r[c] = g0[c] = g1[c] = d0[c] = d1[c] = szP[c] = dgP[c] = z2;
+    ghzP[0] = ghzP[1] = z2;
+
+    // iterations t = ts .. te in pairs (ts even-aligned downwards so that buffer parity == t & 1)
+    const int ts = (T.zs - 2) & ~1, te = T.ze + 3;
+    // roles at the first iteration: a1 = A[ts] (aN), x1 = x[ts-1] (xN)
+    if (T.inD) {
+      if (ts >= 0 && ts < D) ld3(A + base + static_cast<size_t>(ts) * plane3, a1);
+      if (ts - 1 >= 0 && ts - 1 < D) ld3(X + base + static_cast<size_t>(ts - 1) * plane3, x1);
+    }
+    // running pointers (may point outside the tensor while the corresponding access is predicated off)
+    const long long off = static_cast<long long>(base) + static_cast<long long>(ts) * plane3;
+    const float* pa = A + (off + plane3);
+    const float* px = X + off;
+    float* pd = dA + (off - 4LL * plane3);
+    float* pv = kVel ? vel + (off - plane3) : nullptr;
+    constexpr uint32_t par8 = L3_PAR * 4, sxpar8 = L3_SXPAR * 4;
+    // steady iterations: every stage active, no z boundary involved -> all uniform conditions are compile-time true
+    const int st_lo = T.zs + 4, st_hi = min(T.ze, D - 2);
+    for (int t = ts; t <= te; t += 2) {
+      if (t >= st_lo && t + 1 <= st_hi) {
+        l3_iter<kVel, true>(t, p, T, slot, slot + par8, slot_sx, slot_sx + sxpar8, a0, a1, g0, g1, x0, x1, d0, d1, szP, dgP,
+                            ghzP, dzu, dzv, facc_l1, facc_j, pa, px, pd, pv, plane3);
+        l3_iter<kVel, true>(t + 1, p, T, slot + par8, slot, slot_sx + sxpar8, slot_sx, a1, a0, g1, g0, x1, x0, d1, d0, szP,
+                            dgP, ghzP, dzu, dzv, facc_l1, facc_j, pa, px, pd, pv, plane3);
+      } else {
+        l3_iter<kVel, false>(t, p, T, slot, slot + par8, slot_sx, slot_sx + sxpar8, a0, a1, g0, g1, x0, x1, d0, d1, szP, dgP,
+                             ghzP, dzu, dzv, facc_l1, facc_j, pa, px, pd, pv, plane3);
+        l3_iter<kVel, false>(t + 1, p, T, slot + par8, slot, slot_sx + sxpar8, slot_sx, a1, a0, g1, g0, x1, x0, d1, d0, szP,
+                             dgP, ghzP, dzu, dzv, facc_l1, facc_j, pa, px, pd, pv, plane3);
+      }
+    }
+  }
+
+  // ---- block reduction of the two loss sums -> partials[block] (fp64 across threads, fixed order)
+  __shared__ double sred[2][L3_THREADS / 32];
+  const double acc_l1 = warp_sum(static_cast<double>(facc_l1));
+  const double acc_j = warp_sum(static_cast<double>(facc_j));
+  if ((tid & 31) == 0) { sred[0][tid >> 5] = acc_l1; sred[1][tid >> 5] = acc_j; }
+  __syncthreads();
+  if (tid == 0) {
+    double a = 0, c = 0;
+    for (int i = 0; i < L3_THREADS / 32; ++i) { a += sred[0][i]; c += sred[1][i]; }
+    partials[2 * blockIdx.x] = a;
+    partials[2 * blockIdx.x + 1] = c;
+  }
+}
+
+// plan + launch; returns the number of partial-sum blocks written (0 = shape not supported by this kernel)
+int stencil3d_lean_max_blocks() { return 256; }
+
+int stencil3d_lean_launch(const float* A, const float* X, float* dA, float* vel, double* partials, int B, int D, int H,
+                          int W, float c1, float c2, cudaStream_t st, int* nblk) {
+  *nblk = 0;
+  if ((W & 1) || W < 2 || H < 2 || D < 2) return DFL_OK;
+  if (static_cast<long long>(H) * W * 3 >= (1LL << 31)) return DFL_OK;
+  Lean3Params p{};
+  p.B = B; p.D = D; p.H = H; p.W = W; p.c1 = c1; p.c2 = c2;
+  p.ntx = (W + 63) / 64;
+  int oxc = (W + p.ntx - 1) / p.ntx;
+  oxc += oxc & 1;
+  p.oxc = oxc;
+  p.tpr = oxc / 2 + 2;
+  int tr_max = L3_THREADS / p.tpr;
+  if (tr_max > H + 4) tr_max = H + 4;
+  if (tr_max < 5) return DFL_OK;
+  const int oy_max = tr_max - 4;
+  p.nty = (H + oy_max - 1) / oy_max;
+  p.oy = (H + p.nty - 1) / p.nty;
+  p.tr = p.oy + 4;
+  p.nthr = p.tpr * p.tr;
+  p.ncols = B * p.nty * p.ntx;
+  p.tpr8 = p.tpr * 8;
+  const size_t smem_bytes = static_cast<size_t>(L3_SMEM_FLOATS) * sizeof(float);
+  static bool attr_done = false;
+  if (!attr_done) {
+    DFL_CUDA_OK(cudaFuncSetAttribute(stencil3d_lean_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    DFL_CUDA_OK(cudaFuncSetAttribute(stencil3d_lean_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    attr_done = true;
+  }
+  DFL_REQUIRE(smem_bytes <= 200 * 1024, "stencil3d_lean: smem plan too large (%zu)", smem_bytes);
+  const long long total = static_cast<long long>(p.ncols) * D;
+  long long grid = num_sms();
+  if (grid > stencil3d_lean_max_blocks()) grid = stencil3d_lean_max_blocks();
+  const long long min_units = 8;                 // do not split below 8 planes per CTA (4 warm-up planes each)
+  if (grid > (total + min_units - 1) / min_units) grid = (total + min_units - 1) / min_units;
+  if (grid < 1) grid = 1;
+  if (vel)
+    stencil3d_lean_kernel<true><<<static_cast<int>(grid), L3_THREADS, smem_bytes, st>>>(A, X, dA, vel, partials, p);
+  else
+    stencil3d_lean_kernel<false><<<static_cast<int>(grid), L3_THREADS, smem_bytes, st>>>(A, X, dA, nullptr, partials, p);
+  DFL_LAUNCH_OK("stencil3d_lean_kernel");
+  *nblk = static_cast<int>(grid);
+  return DFL_OK;
+}
+
+}  // namespace dfl

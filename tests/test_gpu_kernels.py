@@ -76,7 +76,8 @@ def test_stencil2d_vs_oracle(shape):
     np.testing.assert_allclose(dpsi.cpu().numpy(), dp.numpy(), atol=1e-7, rtol=1e-5)
 
 
-@pytest.mark.parametrize("shape", [(2, 2, 2, 2), (1, 7, 13, 30), (2, 16, 16, 16), (1, 40, 12, 29), (1, 3, 64, 64)])
+@pytest.mark.parametrize("shape", [(2, 2, 2, 2), (1, 7, 13, 30), (2, 16, 16, 16), (1, 40, 12, 29), (1, 3, 64, 64),
+                                   (1, 9, 37, 70), (2, 20, 40, 136), (1, 33, 130, 128), (3, 5, 3, 4), (1, 2, 11, 2)])
 def test_stencil3d_vs_oracle(shape):
     from deepfluids_b200 import kernels as K
     B, D, H, W = shape
@@ -90,6 +91,30 @@ def test_stencil3d_vs_oracle(shape):
     assert torch.equal(v.cpu(), G.detach())
     np.testing.assert_allclose(loss3.cpu().numpy(), [loss.item(), l1.item(), jl1.item()], rtol=3e-6)
     np.testing.assert_allclose(dA.cpu().numpy(), dA_ref.numpy(), atol=1e-7, rtol=1e-5)
+
+
+@pytest.mark.parametrize("shape", [(3, 64, 64, 64), (1, 128, 128, 128), (2, 21, 50, 66)])
+def test_stencil3d_lean_matches_generic_kernel(shape, monkeypatch):
+    """The all-fp32 3D fast path (dfl_stencil3_lean.cu: persistent CTAs, 2 voxels per thread) against the generic
+    z-march kernel at BASELINE sizes: identical G_ (bit-exact), loss within 1e-6, dL/dA within fp32 rounding."""
+    from deepfluids_b200 import kernels as K
+    g = torch.Generator(device="cuda").manual_seed(5)
+    A = torch.randn(*shape, 3, device=dev(), generator=g)
+    x = torch.randn(*shape, 3, device=dev(), generator=g)
+    l_fast, d_fast, v_fast = K.stencil_loss_fwdbwd(A, x, 0.8, 1.1, want_vel=True)
+    l_fast, d_fast, v_fast = l_fast.clone(), d_fast.clone(), v_fast.clone()
+    monkeypatch.setenv("DFL_STENCIL_GENERIC", "1")
+    l_gen, d_gen, v_gen = K.stencil_loss_fwdbwd(A, x, 0.8, 1.1, want_vel=True)
+    torch.cuda.synchronize()
+    monkeypatch.delenv("DFL_STENCIL_GENERIC")
+    assert torch.equal(v_fast, v_gen)
+    np.testing.assert_allclose(l_fast.cpu().numpy(), l_gen.cpu().numpy(), rtol=1e-6)
+    scale = float(d_gen.abs().max())
+    assert float((d_fast - d_gen).abs().max()) <= 1e-5 * scale
+    # every voxel written exactly once: no NaN / untouched entries
+    d2 = torch.full_like(d_fast, float("nan"))
+    K.stencil_loss_fwdbwd(A, x, 0.8, 1.1, dpot=d2)
+    assert bool(torch.isfinite(d2).all()) and torch.equal(d2, d_fast)
 
 
 def test_curl_divergence_free_full_size():
