@@ -28,6 +28,7 @@ SIGNATURES = {
     "dfl_pack_conv_weights": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp]),
     "dfl_conv3x3_fwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _dims, _i, _i, _i, _i, _vp]),
     "dfl_conv3x3_wgrad": (_i, [_vp, _vp, _vp, _vp, _dims, _i, _i, _i, _vp]),
+    "dfl_conv3x3_wgrad_split": (_i, [_vp, _vp, _vp, _vp, _dims, _i, _vp]),
     "dfl_bias_grad": (_i, [_vp, _vp, _sz, _vp]),
     "dfl_lastconv_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _dims, _i, _i, _vp]),
     "dfl_pack_conv_weights_ex": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _vp]),

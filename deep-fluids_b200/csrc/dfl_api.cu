@@ -65,7 +65,7 @@ int conv_tc_launch(const void* x, const void* w_packed, const float* bias, void*
                    const void* residual, const void* mask_src, const int64_t* dims, int nd, int cin, int cout,
                    int flags, const int32_t* blkmap, int nphys, cudaStream_t st);
 int wgrad_tc_launch(const void* x, const void* dpre, float* dw, float* db, const int64_t* x_dims, const int64_t* dims,
-                    int nd, int in_stride, int pad, int dw_tap_stride, int dw_row_stride, cudaStream_t st);
+                    int nd, int in_stride, int pad, int dw_tap_stride, int dw_row_stride, cudaStream_t st, int split = 0);
 int conv_tap_launch(const void* x, const void* w_packed, const float* bias, void* out, void* out2,
                     const void* residual, const void* mask_src, const int64_t* in_dims, const int64_t* tile_dims,
                     const int64_t* out_dims, int nd, int cin, int in_stride, int ntap, const int32_t* taps,
@@ -192,6 +192,10 @@ int dfl_conv3x3_wgrad(const void* x, const void* dpre, float* dw, float* db, con
                       int cout, void* stream) {
   DFL_REQUIRE(cin == 128 && cout == 128, "conv3x3_wgrad: Cin = Cout = 128 only (use dfl_conv_wgrad_ex for blocks)");
   return wgrad_tc_launch(x, dpre, dw, db, dims, dims, ndim, 1, 1, 128 * 128, 128, ST(stream));
+}
+int dfl_conv3x3_wgrad_split(const void* x2, const void* dpre2, float* dw, float* db, const int64_t* dims, int ndim,
+                            void* stream) {
+  return wgrad_tc_launch(x2, dpre2, dw, db, dims, dims, ndim, 1, 1, 128 * 128, 128, ST(stream), 1);
 }
 int dfl_conv_wgrad_ex(const void* x, const void* dpre, float* dw, float* db, const int64_t* x_dims, const int64_t* dims,
                       int ndim, int in_stride, int pad, int dw_tap_stride, int dw_row_stride, void* stream) {

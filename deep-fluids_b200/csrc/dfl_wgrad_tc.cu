@@ -14,6 +14,8 @@
 //   with red.global.add at the end.
 //   Roles: warp 0 = TMA producer, warp 1 = TMEM alloc + MMA issuer, warps 2..5 = epilogue.
 #include "dfl_common.cuh"
+#include <cmath>
+#include <cstdlib>
 
 namespace dfl {
 
@@ -41,6 +43,10 @@ struct WgradParams {
   // x-halo variant whose windows start on arbitrary rows measured 2x SLOWER MMAs for these MN-major operands)
   int brick;
   int a_half;         // bytes between the two 64-channel halves of a brick (1024-aligned)
+  // operand combinations accumulated into the same result (fp32-grade split operands: x_hi*dP_hi + x_lo*dP_hi + x_hi*dP_lo):
+  // combination c reads X at batch b + xoff[c] and dP at batch b + poff[c]; bit c of bias_mask = dP of c enters db
+  int ncombo, xoff[3], poff[3], bias_mask;
+  int vec_red;        // dw rows are 16-byte aligned: reduce with red.global.add.v4.f32
 };
 constexpr int WG_BRICK_SLOT = 40960;      // >= 2 * bd*(bh+2)*bw*128 for the tile shapes that use brick mode
 constexpr int WG_BRICK_SLOTS = 3;
@@ -66,8 +72,9 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
   const int tap0 = group * p.taps_per_group;
   const int gtaps = min(p.taps_per_group, ntaps - tap0);
   // this CTA's slab of bricks: [t_begin, t_end)
-  const int per = (p.ntiles + p.nslabs - 1) / p.nslabs;
-  const int t_begin = slab * per, t_end = min(p.ntiles, t_begin + per);
+  const int nvt = p.ntiles * p.ncombo;          // virtual bricks = (brick, operand combination), combination fastest
+  const int per = (nvt + p.nslabs - 1) / p.nslabs;
+  const int t_begin = slab * per, t_end = min(nvt, t_begin + per);
   // The last tap group has a free 128-column TMEM slot (27 = 6*4+3, 9 = 3*3): it also accumulates the bias gradient
   // db[co] = sum_p dP[p][co] as one more GEMM, ones[M x K] (x) dP -- every row of that accumulator equals db.
   const bool do_bias = (p.db != nullptr) && (group == p.ngroups - 1) && (gtaps < WG_MAX_TAPS);
@@ -95,7 +102,8 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
     if (warp == 0) {
       if (lane == 0) {
         uint32_t ia = 0, ib = 0;
-        for (int tile = t_begin; tile < t_end; ++tile, ++ib) {
+        for (int vt = t_begin; vt < t_end; ++vt, ++ib) {
+          const int tile = vt / p.ncombo, combo = vt - tile * p.ncombo;
           // z-fastest traversal: a CTA's consecutive bricks are z-neighbours, so the planes the dz = 0/1/2 tap groups
           // share are re-read from L2 within a few bricks instead of one z-plane (4 MB per slab at 128^3) later --
           // ncu showed 13.0 GB of DRAM reads per launch (3x the algorithmic 4.3 GB) with the x-fastest order
@@ -103,13 +111,13 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
           const int z0 = (r % p.tz) * p.bd; r /= p.tz;
           const int x0 = (r % p.tx) * p.bw; r /= p.tx;
           const int y0 = (r % p.ty) * p.bh; r /= p.ty;
-          const int b = r;
+          const int b = r + p.xoff[combo], bp = r + p.poff[combo];
           {  // B = dP brick (two 64-channel boxes)
             const uint32_t s = ib % WG_B_SLOTS, ph = (ib / WG_B_SLOTS) & 1;
             mbar_wait(&b_empty[s], ph ^ 1);
             mbar_expect_tx(&b_full[s], WG_OP_BYTES);
-            tma_load_5d(sB + s * WG_OP_BYTES, &tmP, &b_full[s], 0, x0, y0, z0, b);
-            tma_load_5d(sB + s * WG_OP_BYTES + WG_OP_BYTES / 2, &tmP, &b_full[s], 64, x0, y0, z0, b);
+            tma_load_5d(sB + s * WG_OP_BYTES, &tmP, &b_full[s], 0, x0, y0, z0, bp);
+            tma_load_5d(sB + s * WG_OP_BYTES + WG_OP_BYTES / 2, &tmP, &b_full[s], 64, x0, y0, z0, bp);
           }
           if (p.brick) {
             const int dx = group % 3, dz = group / 3;
@@ -147,7 +155,9 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
           koff[k] = static_cast<uint32_t>((((l / p.bh) * (p.bh + 2) + (l % p.bh)) * p.bw + xoff) * 128);
         }
         const uint32_t line_bytes = static_cast<uint32_t>(p.bw * 128);
-        for (int tile = t_begin; tile < t_end; ++tile, ++ib) {
+        int combo = t_begin % p.ncombo;
+        bool bias_first = true;
+        for (int tile = t_begin; tile < t_end; ++tile, ++ib) {      // tile = virtual brick index here
           const uint32_t sbs = ib % WG_B_SLOTS, bph = (ib / WG_B_SLOTS) & 1;
           mbar_wait(&b_full[sbs], bph);
           tc_fence_after();
@@ -183,13 +193,15 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
             }
             umma_commit(&a_empty[s]);
           }
-          if (do_bias) {
+          if (do_bias && ((p.bias_mask >> combo) & 1)) {
             const uint32_t so = smem_u32(sOnes);
 #pragma unroll
             for (int k = 0; k < WG_TILE_K / 16; ++k)
               umma_bf16(tmem_base + 3 * 128, umma_desc_sw128(so, 0, 1024), umma_desc_sw128(sb + k * 2048, WG_OP_BYTES / 2, 1024),
-                        idesc, (tile != t_begin || k != 0) ? 1u : 0u);
+                        idesc, (!bias_first || k != 0) ? 1u : 0u);
+            bias_first = false;
           }
+          if (++combo == p.ncombo) combo = 0;
           umma_commit(&b_empty[sbs]);
         }
         umma_commit(acc_full);
@@ -197,6 +209,8 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
     } else {
       const int quarter = warp & 3;
       const int ci = quarter * 32 + lane;
+      bool bias_any = false;                 // did any of this CTA's virtual bricks feed the bias accumulator?
+      for (int vt = t_begin; vt < min(t_end, t_begin + p.ncombo); ++vt) bias_any |= ((p.bias_mask >> (vt % p.ncombo)) & 1) != 0;
       mbar_wait(acc_full, 0);
       tc_fence_after();
       for (int t = 0; t < gtaps; ++t) {
@@ -207,11 +221,19 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
           uint32_t rr[32];
           tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + t * 128 + c0, rr);
           tmem_ld_wait();
+          if (p.vec_red) {
 #pragma unroll
-          for (int k = 0; k < 32; ++k) atomicAdd(dst + c0 + k, __uint_as_float(rr[k]));
+            for (int k = 0; k < 32; k += 4)
+              asm volatile("red.global.add.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(dst + c0 + k), "f"(__uint_as_float(rr[k])),
+                           "f"(__uint_as_float(rr[k + 1])), "f"(__uint_as_float(rr[k + 2])), "f"(__uint_as_float(rr[k + 3]))
+                           : "memory");
+          } else {
+#pragma unroll
+            for (int k = 0; k < 32; ++k) atomicAdd(dst + c0 + k, __uint_as_float(rr[k]));
+          }
         }
       }
-      if (do_bias && quarter == 0) {      // row 0 of the bias accumulator (all rows are equal)
+      if (do_bias && quarter == 0 && bias_any) {      // row 0 of the bias accumulator (all rows are equal)
 #pragma unroll 1
         for (int c0 = 0; c0 < 128; c0 += 32) {
           uint32_t rr[32];
@@ -250,7 +272,7 @@ static void pick_brick_w(int D, int H, int W, int& bd, int& bh, int& bw) {
 // x: [B, xD, xH, xW, 128] bf16 (one 128-channel block), dpre: [B, D, H, W, 128] bf16 (tile domain).  For stride 1
 // x dims == dims; for the gradient of a stride-2 conv x is the fine grid and the TMA walks it with element stride 2.
 int wgrad_tc_launch(const void* x, const void* dpre, float* dw, float* db, const int64_t* x_dims, const int64_t* dims,
-                    int nd, int in_stride, int pad, int dw_tap_stride, int dw_row_stride, cudaStream_t st) {
+                    int nd, int in_stride, int pad, int dw_tap_stride, int dw_row_stride, cudaStream_t st, int split) {
   DFL_REQUIRE(nd == 2 || nd == 3, "wgrad_tc: ndim must be 2 or 3");
   DFL_REQUIRE(in_stride == 1 || in_stride == 2, "wgrad_tc: in_stride must be 1 or 2");
   WgradParams p{};
@@ -272,7 +294,29 @@ int wgrad_tc_launch(const void* x, const void* dpre, float* dw, float* db, const
   p.a_half = p.bd * (p.bh + 2) * p.bw * 128;      // rows * 128 B; bw is a multiple of 8 -> 1024-aligned
   p.taps_per_group = p.brick ? 3 : ((nd == 3) ? 4 : 3);
   p.ngroups = (ntaps + p.taps_per_group - 1) / p.taps_per_group;
-  p.nslabs = std::max(1, std::min(p.ntiles, num_sms() / p.ngroups));
+  // split != 0: x and dpre are (hi, lo) bf16 pairs stacked along the batch axis ([2B, ...]); three operand combinations
+  if (split) {
+    p.ncombo = 3;
+    p.xoff[0] = 0; p.poff[0] = 0;        // x_hi * dP_hi
+    p.xoff[1] = p.B; p.poff[1] = 0;      // x_lo * dP_hi
+    p.xoff[2] = 0; p.poff[2] = p.B;      // x_hi * dP_lo
+    p.bias_mask = 0b101;                 // db = sum(dP_hi) + sum(dP_lo)
+  } else {
+    p.ncombo = 1;
+    p.bias_mask = 1;
+  }
+  // slabs: every CTA ends with a (taps x 64 KB) fp32 reduction into dw whose cost grows with the number of slabs while
+  // the main loop shrinks with it: T ~ a*nvt/ns + b*ns -> ns ~ sqrt(K * nvt).  With the vectorised reduction
+  // (red.global.add.v4.f32; the scalar atomics cost a ~55 us floor per launch) the sweep in
+  // profiles/r01_wgrad_slabs.txt is flat for K >= 4; K = 8 only trims the smallest levels.
+  {
+    const int nvt = p.ntiles * p.ncombo;
+    const int cap = std::max(1, num_sms() / p.ngroups);
+    static const double kslab = getenv("DFL_WGRAD_SLAB_K") ? atof(getenv("DFL_WGRAD_SLAB_K")) : 8.0;
+    int ns = static_cast<int>(std::lround(std::sqrt(kslab * nvt)));
+    p.nslabs = std::max(1, std::min(std::min(nvt, cap), ns));
+  }
+  p.vec_red = (dw_row_stride % 4 == 0 && dw_tap_stride % 4 == 0 && (reinterpret_cast<uintptr_t>(dw) & 15) == 0) ? 1 : 0;
   p.dw = dw;
   p.db = db;
   p.in_stride = in_stride;
@@ -286,7 +330,7 @@ int wgrad_tc_launch(const void* x, const void* dpre, float* dw, float* db, const
               xW = static_cast<int>(x_dims[nd]);
     const uint32_t s = static_cast<uint32_t>(in_stride);
     const uint64_t gd[5] = {128, static_cast<uint64_t>(xW), static_cast<uint64_t>(xH), static_cast<uint64_t>(xD),
-                            static_cast<uint64_t>(x_dims[0])};
+                            static_cast<uint64_t>(x_dims[0]) * (split ? 2 : 1)};
     const uint64_t gs[4] = {256, 256ull * xW, 256ull * xW * xH, 256ull * xW * xH * xD};
     const uint32_t box[5] = {64, p.bw * s, p.brick ? static_cast<uint32_t>(p.bh + 2) : p.bh * s,
                              (xD == 1 ? 1u : p.bd * s), 1};
@@ -296,7 +340,7 @@ int wgrad_tc_launch(const void* x, const void* dpre, float* dw, float* db, const
   }
   {
     const uint64_t gd[5] = {128, static_cast<uint64_t>(p.W), static_cast<uint64_t>(p.H), static_cast<uint64_t>(p.D),
-                            static_cast<uint64_t>(p.B)};
+                            static_cast<uint64_t>(p.B) * (split ? 2 : 1)};
     const uint64_t gs[4] = {256, 256ull * p.W, 256ull * p.W * p.H, 256ull * p.W * p.H * p.D};
     const uint32_t box[5] = {64, static_cast<uint32_t>(p.bw), static_cast<uint32_t>(p.bh), static_cast<uint32_t>(p.bd), 1};
     int rc = encode_tensor_map(&tmP, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, dpre, gd, gs, box, CU_TENSOR_MAP_SWIZZLE_128B);

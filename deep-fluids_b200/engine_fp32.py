@@ -5,7 +5,7 @@ Every activation / gradient tensor is a (hi, lo) pair of bf16 tensors (hi = bf16
 mantissa) stored as two channel blocks [2*B,(D,)H,W,128]; weights are split the same way when the GEMM operands are
 packed.  x*w ~ x_hi*w_hi + x_lo*w_hi + x_hi*w_lo (dropped term 2^-18 relative) is a single launch of the tap-window
 kernel over the virtual input blocks [hi, lo, hi] (3x the K of the bf16 path) with fp32 accumulation in TMEM; weight
-gradients are three launches of the wgrad kernel accumulating into the same fp32 buffer.  Same kernel sequence, same
+gradients are one launch of the wgrad kernel that walks the three operand combinations per brick.  Same kernel sequence, same
 fusions and the same flat fp32 parameter / Adam buffers as engine.GeneratorEngine.
 """
 import numpy as np
@@ -97,9 +97,8 @@ class GeneratorEngineFP32(GeneratorEngine):
 
     # ------------------------------------------------------------------ backward
     def _wgrad3(self, x2, dp2, dw, db):
-        K.conv3x3_wgrad(self._hi(x2), self._hi(dp2), dw, db)
-        K.conv3x3_wgrad(self._lo(x2), self._hi(dp2), dw, None)
-        K.conv3x3_wgrad(self._hi(x2), self._lo(dp2), dw, db)
+        # x_hi^T dP_hi + x_lo^T dP_hi + x_hi^T dP_lo accumulated in one TMEM tile, one reduction into dw
+        K.conv3x3_wgrad_split(x2, dp2, dw, db)
 
     def backward(self, dpot, dz=None):
         assert not self.inference and self.B <= 64

@@ -287,6 +287,15 @@ def conv3x3_wgrad(x, dpre, dw, db=None):
         _p(x), _p(dpre), _p(dw), _p(db), d, nd, x.shape[-1], dpre.shape[-1], _st())))
 
 
+def conv3x3_wgrad_split(x2, dpre2, dw, db=None):
+    """fp32-grade dw += x^T (x) dP on (hi, lo) pairs [2B,...,128]: three operand combinations in ONE launch"""
+    nd = x2.dim() - 2
+    d = dims_array((x2.shape[0] // 2,) + tuple(x2.shape[1:-1]))
+    flops = 2.0 * 3 * (x2.numel() // 256) * 128 * 128 * (3 ** nd)
+    PROF.timed("wgrad_tc", flops, lambda: check(cabi.lib().dfl_conv3x3_wgrad_split(
+        _p(x2), _p(dpre2), _p(dw), _p(db), d, nd, _st())))
+
+
 def bias_grad(dpre, db):
     PROF.launches += 1
     check(cabi.lib().dfl_bias_grad(_p(dpre), _p(db), dpre.numel() // dpre.shape[-1], _st()))

@@ -133,6 +133,11 @@ int dfl_conv_taps(const void* x, const void* w_packed, const float* bias, void* 
                   const void* mask_src, const int64_t* in_dims, const int64_t* tile_dims, const int64_t* out_dims, int ndim,
                   int cin, int in_stride, int ntap, const int32_t* taps, int out_stride, const int32_t* out_off,
                   int64_t w_ld, int flags, void* stream);
+/* fp32-grade weight gradient on split operands: x2, dpre2 are (hi, lo) bf16 pairs [2B,(D,)H,W,128] (see
+ * dfl_split_f32); dw += x_hi^T dP_hi + x_lo^T dP_hi + x_hi^T dP_lo per tap (fp32 accumulate), db += sum(dP_hi + dP_lo).
+ * One launch: the three operand combinations are accumulated in the same TMEM tile before the reduction into dw. */
+int dfl_conv3x3_wgrad_split(const void* x2, const void* dpre2, float* dw, float* db, const int64_t* dims, int ndim,
+                            void* stream);
 /* weight gradient of one (128-channel input block, 128-channel output block) pair; in_stride 2 samples x at
  * 2p + tap - pad (stride-2 conv); element (tap, ci, co) is added at dw[tap*dw_tap_stride + ci*dw_row_stride + co]. */
 int dfl_conv_wgrad_ex(const void* x, const void* dpre, float* dw, float* db, const int64_t* x_dims, const int64_t* dims,

@@ -128,6 +128,27 @@ def test_split_lastconv_and_pool():
     assert rel_l2(_merge(dm2), pooled * mask) <= 2e-5
 
 
+@pytest.mark.parametrize("spatial,B", [([32, 48], 3), ([8, 6], 5), ([8, 16, 16], 2)])
+def test_split_wgrad_vs_fp32_oracle(spatial, B):
+    """dw = sum_p x[p+tap]^T dP[p], db = sum_p dP[p] on (hi, lo) pairs, three operand combinations in one launch"""
+    from deepfluids_b200 import kernels as K
+    dev = torch.device("cuda:0")
+    nd = len(spatial)
+    g = torch.Generator().manual_seed(7)
+    x = torch.randn([B] + spatial + [128], generator=g)
+    dp = torch.randn([B] + spatial + [128], generator=g)
+    w = torch.zeros([3] * nd + [128, 128], requires_grad=True)
+    b = torch.zeros(128, requires_grad=True)
+    gw, gb = torch.autograd.grad(R.conv_nd(x, w, b, 1, None), [w, b], dp)
+    dw = torch.zeros([3] * nd + [128, 128], device=dev)
+    db = torch.zeros(128, device=dev)
+    K.conv3x3_wgrad_split(_split(x, dev), _split(dp, dev), dw, db)
+    K.conv3x3_wgrad_split(_split(x, dev), _split(dp, dev), dw, db)      # accumulates
+    torch.cuda.synchronize()
+    assert rel_l2(dw, 2 * gw) <= 2e-5
+    assert rel_l2(db, 2 * gb) <= 2e-5
+
+
 @pytest.mark.parametrize("spatial,num_conv,B", [([32, 24], 2, 3), ([64, 48], 4, 2), ([16, 16, 16], 2, 2)])
 def test_generator_fp32x3_vs_fp32_oracle(spatial, num_conv, B):
     from deepfluids_b200 import kernels as K
