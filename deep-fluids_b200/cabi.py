@@ -4,7 +4,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libdeepfluids_b200.so")
+LIB_PATH = os.environ.get("DFL_LIB_PATH") or os.path.join(_HERE, "lib", "libdeepfluids_b200.so")   # override: kernel A/B experiments
 
 F32, BF16 = 0, 1
 CONV_LRELU, CONV_OUT2_UPSAMPLE, CONV_MASK_AFTER_RESIDUAL, CONV_SPLIT_IO = 1, 2, 4, 8

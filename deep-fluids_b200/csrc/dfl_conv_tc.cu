@@ -31,6 +31,12 @@
 #include <stdlib.h>
 
 #include "dfl_common.cuh"
+#ifndef DFL_MMA_ISSUE
+#define DFL_MMA_ISSUE 0
+#endif
+#ifndef DFL_DESC_INC
+#define DFL_DESC_INC 1
+#endif
 
 namespace dfl {
 
@@ -376,6 +382,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
+  if (tmem_base != 0) asm volatile("trap;");   // see the MMA issuer: the full-TMEM allocation must start at 0
 
   if (warp == 0) {
     // ================================ brick producer ================================
@@ -425,7 +432,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     }
   } else if (warp == 1) {
     // ================================ MMA issuer ================================
-    if (lane == 0) {
+    if (DFL_MMA_ISSUE == 1 || lane == 0) {   // style 1: the whole warp runs the loop, one elected lane issues
       constexpr uint32_t idesc = umma_idesc_bf16(CT_BLOCK_M, kN, 0, 0);
       const uint32_t brick = smem_u32(smem);
       uint32_t fills[NSLOT];
@@ -436,7 +443,11 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         const uint32_t acc = tcount & 1, aph = (tcount >> 1) & 1;
         mbar_wait(&tempty_bar[acc], aph ^ 1);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + acc * 256;
+        // all 512 TMEM columns are allocated, so the allocation starts at column 0 (checked after the alloc): using the
+        // literal keeps the D address provably warp-uniform -- with `tmem_base` (a shared-memory load) in it the compiler
+        // wrapped EVERY tcgen05.mma in an ELECT / R2UR.BROADCAST loop, and ncu showed the kernel bound by this thread's
+        // instruction stream (~90 issue cycles per MMA against the tensor pipe's 64)
+        const uint32_t d_tmem = acc * 256;
         for (int c = 0; c < p.cin_chunks; ++c, ++phase) {
           for (int dz = 0; dz < p.kd; ++dz) {
             // wait for the brick slots this tap group reads
@@ -462,24 +473,27 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                   const uint32_t a0 = k3D ? brick + (h + dz) * SLOT_BYTES + (dy * HX + dx) * 128
                                           : brick + (phase & 1) * SLOT_BYTES + (dy * HX + dx + 8 * h) * 128;
 #pragma unroll
+                  const uint64_t da0 = umma_desc_sw128(a0, 16, HX * 128), db0 = umma_desc_sw128(sb, 16, 1024);
+#pragma unroll
                   for (int k = 0; k < CT_BLOCK_K / 16; ++k) {
-                    const uint64_t da = umma_desc_sw128(a0 + k * 32, 16, HX * 128);
-                    const uint64_t db = umma_desc_sw128(sb + k * 32, 16, 1024);
-                    umma_bf16(d_tmem + h * CT_BLOCK_N, da, db, idesc, (first && k == 0) ? 0u : 1u);
+                    // K step = +32 B inside the 128-byte swizzle row = +2 in the descriptor's 16-byte address field
+                    const uint64_t da = DFL_DESC_INC ? da0 + 2 * k : umma_desc_sw128(a0 + k * 32, 16, HX * 128);
+                    const uint64_t db = DFL_DESC_INC ? db0 + 2 * k : umma_desc_sw128(sb + k * 32, 16, 1024);
+                    if (DFL_MMA_ISSUE == 0 || elect_one_sync()) umma_bf16(d_tmem + h * CT_BLOCK_N, da, db, idesc, (first && k == 0) ? 0u : 1u);
                   }
                 }
-                umma_commit(&b_empty[s]);
+                if (DFL_MMA_ISSUE == 0 || elect_one_sync()) umma_commit(&b_empty[s]);
               }
             // release the brick slots no later tap group of this phase reads
             if (k3D) {
-              umma_commit(&a_empty[dz]);
-              if (dz == 2) umma_commit(&a_empty[3]);
+              if (DFL_MMA_ISSUE == 0 || elect_one_sync()) umma_commit(&a_empty[dz]);
+              if (dz == 2) if (DFL_MMA_ISSUE == 0 || elect_one_sync()) umma_commit(&a_empty[3]);
             } else {
-              umma_commit(&a_empty[phase & 1]);
+              if (DFL_MMA_ISSUE == 0 || elect_one_sync()) umma_commit(&a_empty[phase & 1]);
             }
           }
         }
-        umma_commit(&tfull_bar[acc]);
+        if (DFL_MMA_ISSUE == 0 || elect_one_sync()) umma_commit(&tfull_bar[acc]);
       }
     }
   } else {

@@ -99,15 +99,17 @@ __device__ __forceinline__ void l3_iter(const int t, const Lean3Params& p, const
                                         const float*& px, float*& pd, float*& pv, const int plane3) {
   const int D = p.D, zs = T.zs, ze = T.ze;
   const uint32_t tpr8 = p.tpr8;
-  // ---------------------------------------------------------------- S0/S1: A[t] -> smem;  G[q1] = curl(A)[q1], q1 = t-1
+  // Every in-domain thread runs every stage (halo rows compute values nobody consumes: their warps would otherwise
+  // idle at the barrier, and one straight-line block lets the compiler interleave the stages' smem loads and math);
+  // out-of-domain threads run nothing and never write, so their smem slots keep the zeros the boundary rules rely on.
   if (T.inD) {
+  // ---------------------------------------------------------------- S0/S1: A[t] -> smem;  G[q1] = curl(A)[q1], q1 = t-1
 #pragma unroll
-    for (int i = 0; i < 3; ++i) sts2(wb + fam8(FA, i), aN.r[i]);
-  }
+  for (int i = 0; i < 3; ++i) sts2(wb + fam8(FA, i), aN.r[i]);
   {
     const int q1 = t - 1;
     if (kSteady || (q1 >= 0 && q1 < D && q1 <= ze)) {          // uniform
-      if (T.rowG) {
+      {
         if (kSteady || q1 <= D - 2) { dzu = cU(aN) - cU(aO); dzv = cV(aN) - cV(aO); }   // else: replicate the last z difference
         const float2 y0 = lds2(rb + fam8(FA, 0) + T.yo8), y1 = lds2(rb + fam8(FA, 1) + T.yo8), y2 = lds2(rb + fam8(FA, 2) + T.yo8);
         const float2 yw = make_float2(y1.x, y2.y), yu = make_float2(y0.x, y1.y);
@@ -127,13 +129,13 @@ __device__ __forceinline__ void l3_iter(const int t, const Lean3Params& p, const
     }
   }
   // A[t-1] is dead now: its registers receive A[t+1]
-  if (T.inD && (kSteady || (t + 1 >= 0 && t + 1 < D && t + 1 <= ze + 1))) ld3(pa, aO);
+  if (kSteady || (t + 1 >= 0 && t + 1 < D && t + 1 <= ze + 1)) ld3(pa, aO);
 
   // ---------------------------------------------------------------- S3: complete dL/dG[q3], q3 = t-3
   {
     const int q3 = t - 3;
     if (kSteady || (q3 >= 0 && q3 < D && q3 >= zs - 1 && q3 <= ze)) {   // uniform
-      if (T.rowDG) {
+      {
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
           const float sxn = lds1(rsx + c * L3_PS * 4 - 4);
@@ -150,7 +152,7 @@ __device__ __forceinline__ void l3_iter(const int t, const Lean3Params& p, const
   {
     const int q2 = t - 2;
     if (kSteady || (q2 >= 0 && q2 < D && q2 >= zs - 2 && q2 <= ze)) {   // uniform
-      if (T.rowF) {
+      {
         const float wz = kSteady ? 1.f : ((q2 >= D - 1) ? 0.f : (q2 == D - 2 ? 2.f : 1.f));
         const bool zin = kSteady || (q2 >= zs && q2 < ze);     // uniform
         Raw3 xy;                                               // x[q2] one row up, and the next thread's voxel 0
@@ -186,7 +188,7 @@ __device__ __forceinline__ void l3_iter(const int t, const Lean3Params& p, const
     }
   }
   // x[t-1] -> smem for next iteration's neighbours; x[t-2] is dead: its registers receive x[t]
-  if (T.inD) {
+  {
 #pragma unroll
     for (int i = 0; i < 3; ++i) sts2(wb + fam8(FX, i), xN.r[i]);
     if (kSteady || (t >= 0 && t < D && t <= ze)) ld3(px, xO);
@@ -215,6 +217,7 @@ __device__ __forceinline__ void l3_iter(const int t, const Lean3Params& p, const
       st3(pd, dzT_V - dyT_W, dxT_W - dzT_U, dyT_U - dxT_V);
     }
     ghzP[0] = ghz0; ghzP[1] = ghz1;
+  }
   }
   pa += plane3; px += plane3; pd += plane3;
   if (kVel) pv += plane3;

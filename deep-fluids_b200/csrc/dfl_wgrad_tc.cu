@@ -97,6 +97,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
+  if (tmem_base != 0) asm volatile("trap;");   // all 512 columns are allocated: the allocation starts at column 0 (see the MMA issuer)
 
   if (t_begin < t_end) {
     if (warp == 0) {
@@ -152,9 +153,14 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
 #pragma unroll
         for (int k = 0; k < WG_TILE_K / 16; ++k) {
           const int v = k * 16, l = v / p.bw, xoff = v % p.bw;
-          koff[k] = static_cast<uint32_t>((((l / p.bh) * (p.bh + 2) + (l % p.bh)) * p.bw + xoff) * 128);
+          koff[k] = static_cast<uint32_t>((((l / p.bh) * (p.bh + 2) + (l % p.bh)) * p.bw + xoff) * 128) >> 4;   // 16-byte units
         }
-        const uint32_t line_bytes = static_cast<uint32_t>(p.bw * 128);
+        const uint32_t line16 = static_cast<uint32_t>(p.bw * 128) >> 4;
+        // The D address uses the literal TMEM base 0 and the descriptors are advanced by adding to their 16-byte address
+        // field: with `tmem_base` (a shared-memory load) in the address the compiler wrapped every tcgen05.mma in an
+        // ELECT / R2UR.BROADCAST loop, and rebuilding both descriptors per MMA cost ~10 more uniform-pipe instructions --
+        // this single thread's instruction stream, not the tensor pipe, was the limiter (see dfl_conv_tc.cu).
+        constexpr uint32_t tmem0 = 0;
         int combo = t_begin % p.ncombo;
         bool bias_first = true;
         for (int tile = t_begin; tile < t_end; ++tile, ++ib) {      // tile = virtual brick index here
@@ -166,14 +172,14 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
             const uint32_t s = ia % WG_BRICK_SLOTS, ph = (ia / WG_BRICK_SLOTS) & 1;
             mbar_wait(&a_full[s], ph);
             tc_fence_after();
-            const uint32_t sa = smem_u32(sA + s * WG_BRICK_SLOT);
+            const uint64_t da0 = umma_desc_sw128(smem_u32(sA + s * WG_BRICK_SLOT), p.a_half, 1024);
+            const uint64_t db0 = umma_desc_sw128(sb, WG_OP_BYTES / 2, 1024);
             const uint32_t acc = (tile != t_begin) ? 1u : 0u;
 #pragma unroll
             for (int t = 0; t < 3; ++t) {                                 // t = dy: window shifted by t x-lines
 #pragma unroll
               for (int k = 0; k < WG_TILE_K / 16; ++k)
-                umma_bf16(tmem_base + t * 128, umma_desc_sw128(sa + koff[k] + t * line_bytes, p.a_half, 1024),
-                          umma_desc_sw128(sb + k * 2048, WG_OP_BYTES / 2, 1024), idesc, (k != 0) ? 1u : acc);
+                umma_bf16(tmem0 + t * 128, da0 + (koff[k] + t * line16), db0 + k * 128, idesc, (k != 0) ? 1u : acc);
             }
             umma_commit(&a_empty[s]);
             ++ia;
@@ -182,23 +188,24 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
             const uint32_t s = ia % WG_A_SLOTS, ph = (ia / WG_A_SLOTS) & 1;
             mbar_wait(&a_full[s], ph);
             tc_fence_after();
-            const uint32_t sa = smem_u32(sA + s * WG_OP_BYTES);
-            const uint32_t d_tmem = tmem_base + t * 128;
+            const uint64_t da0 = umma_desc_sw128(smem_u32(sA + s * WG_OP_BYTES), WG_OP_BYTES / 2, 1024);
+            const uint64_t db0 = umma_desc_sw128(sb, WG_OP_BYTES / 2, 1024);
+            const uint32_t d_tmem = tmem0 + t * 128;
 #pragma unroll
             for (int k = 0; k < WG_TILE_K / 16; ++k) {
-              // 16 voxels (K) = 2 groups of 8 rows x 128 B; the two 64-channel halves are WG_OP_BYTES/2 apart
-              const uint64_t da = umma_desc_sw128(sa + k * 2048, WG_OP_BYTES / 2, 1024);
-              const uint64_t db = umma_desc_sw128(sb + k * 2048, WG_OP_BYTES / 2, 1024);
-              umma_bf16(d_tmem, da, db, idesc, (tile != t_begin || k != 0) ? 1u : 0u);
+              // 16 voxels (K) = 2 groups of 8 rows x 128 B (+2048 B = +128 address units); the 64-channel halves are
+              // WG_OP_BYTES/2 apart
+              umma_bf16(d_tmem, da0 + k * 128, db0 + k * 128, idesc, (tile != t_begin || k != 0) ? 1u : 0u);
             }
             umma_commit(&a_empty[s]);
           }
           if (do_bias && ((p.bias_mask >> combo) & 1)) {
             const uint32_t so = smem_u32(sOnes);
 #pragma unroll
+            const uint64_t dones = umma_desc_sw128(so, 0, 1024), dbb = umma_desc_sw128(sb, WG_OP_BYTES / 2, 1024);
+#pragma unroll
             for (int k = 0; k < WG_TILE_K / 16; ++k)
-              umma_bf16(tmem_base + 3 * 128, umma_desc_sw128(so, 0, 1024), umma_desc_sw128(sb + k * 2048, WG_OP_BYTES / 2, 1024),
-                        idesc, (!bias_first || k != 0) ? 1u : 0u);
+              umma_bf16(tmem0 + 3 * 128, dones, dbb + k * 128, idesc, (!bias_first || k != 0) ? 1u : 0u);
             bias_first = false;
           }
           if (++combo == p.ncombo) combo = 0;
