@@ -164,6 +164,7 @@ conv_tap_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       }
     }
   } else if (warp == 1) {
+    const uint32_t tmem_u = __reduce_max_sync(0xffffffffu, tmem_base);   // uniform-register copy (see conv_tc2_kernel)
     if (lane == 0) {
       constexpr uint32_t idesc = umma_idesc_bf16(CT_BLOCK_M, CT_BLOCK_N, 0, 0);
       uint32_t it = 0, tcount = 0;
@@ -171,7 +172,7 @@ conv_tap_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         const uint32_t acc = tcount & 1, aph = (tcount >> 1) & 1;
         mbar_wait(&tempty_bar[acc], aph ^ 1);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + acc * CT_BLOCK_N;
+        const uint32_t d_tmem = tmem_u + acc * CT_BLOCK_N;
         for (int kb = 0; kb < kblocks; ++kb, ++it) {
           const uint32_t s = it % CT_STAGES, ph = (it / CT_STAGES) & 1;
           mbar_wait(&full_bar[s], ph);
@@ -180,8 +181,8 @@ conv_tap_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           const uint32_t sb = sa + CT_A_BYTES;
 #pragma unroll
           for (int k = 0; k < CT_BLOCK_K / 16; ++k) {
-            const uint64_t da = umma_desc_sw128(sa + k * 32, 16, 1024);
-            const uint64_t db = umma_desc_sw128(sb + k * 32, 16, 1024);
+            const uint64_t da = umma_desc_sw128(sa, 16, 1024) + 2 * k;    // +32 B per K step = +2 address units
+            const uint64_t db = umma_desc_sw128(sb, 16, 1024) + 2 * k;
             umma_bf16(d_tmem, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
           }
           umma_commit(&empty_bar[s]);
@@ -382,7 +383,6 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
-  if (tmem_base != 0) asm volatile("trap;");   // see the MMA issuer: the full-TMEM allocation must start at 0
 
   if (warp == 0) {
     // ================================ brick producer ================================
@@ -432,6 +432,9 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     }
   } else if (warp == 1) {
     // ================================ MMA issuer ================================
+    // warp-uniform copy of the TMEM base (redux.sync writes a uniform register): with the plain shared-memory load in the
+    // D address the compiler cannot prove uniformity and wraps EVERY tcgen05.mma in an ELECT / R2UR.BROADCAST loop
+    const uint32_t tmem_u = __reduce_max_sync(0xffffffffu, tmem_base);
     if (DFL_MMA_ISSUE == 1 || lane == 0) {   // style 1: the whole warp runs the loop, one elected lane issues
       constexpr uint32_t idesc = umma_idesc_bf16(CT_BLOCK_M, kN, 0, 0);
       const uint32_t brick = smem_u32(smem);
@@ -443,11 +446,9 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         const uint32_t acc = tcount & 1, aph = (tcount >> 1) & 1;
         mbar_wait(&tempty_bar[acc], aph ^ 1);
         tc_fence_after();
-        // all 512 TMEM columns are allocated, so the allocation starts at column 0 (checked after the alloc): using the
-        // literal keeps the D address provably warp-uniform -- with `tmem_base` (a shared-memory load) in it the compiler
-        // wrapped EVERY tcgen05.mma in an ELECT / R2UR.BROADCAST loop, and ncu showed the kernel bound by this thread's
-        // instruction stream (~90 issue cycles per MMA against the tensor pipe's 64)
-        const uint32_t d_tmem = acc * 256;
+        // ncu showed the kernel bound by THIS thread's instruction stream (~90 issue cycles per MMA against the tensor
+        // pipe's 64): the D address is built from the uniform TMEM base and the descriptors are advanced by adds
+        const uint32_t d_tmem = tmem_u + acc * 256;
         for (int c = 0; c < p.cin_chunks; ++c, ++phase) {
           for (int dz = 0; dz < p.kd; ++dz) {
             // wait for the brick slots this tap group reads
@@ -456,9 +457,9 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
               else if (dz == 1) { mbar_wait(&a_full[2], fills[2] & 1); ++fills[2]; }
               else { mbar_wait(&a_full[3], fills[3] & 1); ++fills[3]; }
             } else {
-              const int j = phase & 1;
-              mbar_wait(&a_full[j], fills[j] & 1);
-              ++fills[j];
+              // slot (phase & 1) is filled every second phase: its fill count so far is phase >> 1.  (A dynamically indexed
+              // fills[] array here made the compiler treat every MMA operand as non-uniform: 5 R2UR.BROADCAST per MMA.)
+              mbar_wait(&a_full[phase & 1], (phase >> 1) & 1);
             }
             tc_fence_after();
             for (int dy = 0; dy < 3; ++dy)

@@ -115,6 +115,7 @@ lastconv_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmS, LastBwdParams p)
     }
   } else if (warp == 1) {
     // ================================ MMA issuer ================================
+    const uint32_t tmem_u = __reduce_max_sync(0xffffffffu, tmem_base);   // uniform-register copy (see conv_tc2_kernel)
     if (lane == 0) {
       constexpr uint32_t idesc1 = umma_idesc_bf16(128, 128, 0, 0);   // G (K-major) x W' (K-major)
       constexpr uint32_t idesc2 = umma_idesc_bf16(128, 128, 1, 1);   // s^T (MN-major) x G (MN-major)
@@ -127,16 +128,18 @@ lastconv_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmS, LastBwdParams p)
         tc_fence_after();
         const uint32_t g0 = smem_u32(sG + s * LB_OP), s0 = smem_u32(sS + s * LB_OP);
 #pragma unroll
+        const uint64_t dg1 = umma_desc_sw128(g0, 16, 1024), dw1 = umma_desc_sw128(w0, 16, 1024);
+#pragma unroll
         for (int k = 0; k < KSTEPS1; ++k) {
-          const uint32_t off = (k >> 2) * (LB_OP / 2) + (k & 3) * 32;
-          umma_bf16(tmem_base + s * 128, umma_desc_sw128(g0 + off, 16, 1024), umma_desc_sw128(w0 + off, 16, 1024), idesc1,
-                    k != 0 ? 1u : 0u);
+          const uint32_t off16 = ((k >> 2) * (LB_OP / 2) + (k & 3) * 32) >> 4;     // descriptor address units (16 B)
+          umma_bf16(tmem_u + s * 128, dg1 + off16, dw1 + off16, idesc1, k != 0 ? 1u : 0u);
         }
         umma_commit(&d1_full[s]);
 #pragma unroll
+        const uint64_t ds2 = umma_desc_sw128(s0, LB_OP / 2, 1024), dg2 = umma_desc_sw128(g0, LB_OP / 2, 1024);
+#pragma unroll
         for (int k = 0; k < 8; ++k)
-          umma_bf16(tmem_base + 256, umma_desc_sw128(s0 + k * 2048, LB_OP / 2, 1024),
-                    umma_desc_sw128(g0 + k * 2048, LB_OP / 2, 1024), idesc2, (i != 0 || k != 0) ? 1u : 0u);
+          umma_bf16(tmem_u + 256, ds2 + k * 128, dg2 + k * 128, idesc2, (i != 0 || k != 0) ? 1u : 0u);
         umma_commit(&g_empty[s]);
         umma_commit(&s_empty[s]);
       }

@@ -97,7 +97,6 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
-  if (tmem_base != 0) asm volatile("trap;");   // all 512 columns are allocated: the allocation starts at column 0 (see the MMA issuer)
 
   if (t_begin < t_end) {
     if (warp == 0) {
@@ -144,6 +143,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
         }
       }
     } else if (warp == 1) {
+      const uint32_t tmem_u = __reduce_max_sync(0xffffffffu, tmem_base);
       if (lane == 0) {
         constexpr uint32_t idesc = umma_idesc_bf16(128, 128, 1, 1);   // both operands MN-major
         uint32_t ia = 0, ib = 0;
@@ -156,11 +156,12 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
           koff[k] = static_cast<uint32_t>((((l / p.bh) * (p.bh + 2) + (l % p.bh)) * p.bw + xoff) * 128) >> 4;   // 16-byte units
         }
         const uint32_t line16 = static_cast<uint32_t>(p.bw * 128) >> 4;
-        // The D address uses the literal TMEM base 0 and the descriptors are advanced by adding to their 16-byte address
-        // field: with `tmem_base` (a shared-memory load) in the address the compiler wrapped every tcgen05.mma in an
-        // ELECT / R2UR.BROADCAST loop, and rebuilding both descriptors per MMA cost ~10 more uniform-pipe instructions --
-        // this single thread's instruction stream, not the tensor pipe, was the limiter (see dfl_conv_tc.cu).
-        constexpr uint32_t tmem0 = 0;
+        // The D address uses a uniform-register copy of the TMEM base and the descriptors are advanced by adding to their
+        // 16-byte address field: with `tmem_base` (a shared-memory load) in the address the compiler wrapped every
+        // tcgen05.mma in an ELECT / R2UR.BROADCAST loop, and rebuilding both descriptors per MMA cost ~10 more
+        // uniform-pipe instructions -- this single thread's instruction stream, not the tensor pipe, was the limiter
+        // (see dfl_conv_tc.cu).
+        const uint32_t tmem0 = tmem_u;
         int combo = t_begin % p.ncombo;
         bool bias_first = true;
         for (int tile = t_begin; tile < t_end; ++tile, ++ib) {      // tile = virtual brick index here
