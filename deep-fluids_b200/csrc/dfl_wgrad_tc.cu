@@ -75,9 +75,14 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
   const int nvt = p.ntiles * p.ncombo;          // virtual bricks = (brick, operand combination), combination fastest
   const int per = (nvt + p.nslabs - 1) / p.nslabs;
   const int t_begin = slab * per, t_end = min(nvt, t_begin + per);
-  // The last tap group has a free 128-column TMEM slot (27 = 6*4+3, 9 = 3*3): it also accumulates the bias gradient
-  // db[co] = sum_p dP[p][co] as one more GEMM, ones[M x K] (x) dP -- every row of that accumulator equals db.
-  const bool do_bias = (p.db != nullptr) && (group == p.ngroups - 1) && (gtaps < WG_MAX_TAPS);
+  // A tap group with a free 128-column TMEM slot also accumulates the bias gradient db[co] = sum_p dP[p][co] as one more
+  // GEMM, ones[M x K] (x) dP -- every row of that accumulator equals db.  Brick mode: every group has 3 taps, so the
+  // bricks' bias MMAs are dealt round-robin over the groups (brick % ngroups == group).  Giving all of them to one group
+  // made that group's CTAs issue 32 instead of 24 MMAs per brick: they finished last (kernel time = slowest CTA), fell
+  // hundreds of bricks behind their slab's other groups and re-read both operands from HBM instead of L2.
+  // Tap-list mode (4 taps per group): only the last group (27 = 6*4+3, 9 = 2*4+1) has the free slot.
+  const bool bias_rr = p.brick != 0;
+  const bool do_bias = (p.db != nullptr) && (gtaps < WG_MAX_TAPS) && (bias_rr || group == p.ngroups - 1);
   for (int i = threadIdx.x; i < WG_ONES_BYTES / 4; i += WG_THREADS) reinterpret_cast<uint32_t*>(sOnes)[i] = 0x3F803F80u;
 
   if (warp == 0 && lane == 0) {
@@ -163,6 +168,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
         // (see dfl_conv_tc.cu).
         const uint32_t tmem0 = tmem_u;
         int combo = t_begin % p.ncombo;
+        int bphase = bias_rr ? (t_begin / p.ncombo) % p.ngroups : group;     // brick index mod ngroups, kept incrementally
         bool bias_first = true;
         for (int tile = t_begin; tile < t_end; ++tile, ++ib) {      // tile = virtual brick index here
           const uint32_t sbs = ib % WG_B_SLOTS, bph = (ib / WG_B_SLOTS) & 1;
@@ -200,16 +206,18 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
             }
             umma_commit(&a_empty[s]);
           }
-          if (do_bias && ((p.bias_mask >> combo) & 1)) {
+          if (do_bias && bphase == group && ((p.bias_mask >> combo) & 1)) {
             const uint32_t so = smem_u32(sOnes);
-#pragma unroll
             const uint64_t dones = umma_desc_sw128(so, 0, 1024), dbb = umma_desc_sw128(sb, WG_OP_BYTES / 2, 1024);
 #pragma unroll
             for (int k = 0; k < WG_TILE_K / 16; ++k)
               umma_bf16(tmem0 + 3 * 128, dones, dbb + k * 128, idesc, (!bias_first || k != 0) ? 1u : 0u);
             bias_first = false;
           }
-          if (++combo == p.ncombo) combo = 0;
+          if (++combo == p.ncombo) {
+            combo = 0;
+            if (bias_rr && ++bphase == p.ngroups) bphase = 0;
+          }
           umma_commit(&b_empty[sbs]);
         }
         umma_commit(acc_full);
@@ -218,7 +226,16 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
       const int quarter = warp & 3;
       const int ci = quarter * 32 + lane;
       bool bias_any = false;                 // did any of this CTA's virtual bricks feed the bias accumulator?
-      for (int vt = t_begin; vt < min(t_end, t_begin + p.ncombo); ++vt) bias_any |= ((p.bias_mask >> (vt % p.ncombo)) & 1) != 0;
+      if (do_bias && quarter == 0) {         // same walk as the MMA issuer (these warps idle until acc_full anyway)
+        int combo = t_begin % p.ncombo, bphase = bias_rr ? (t_begin / p.ncombo) % p.ngroups : group;
+        for (int vt = t_begin; vt < t_end && !bias_any; ++vt) {
+          bias_any = (bphase == group) && (((p.bias_mask >> combo) & 1) != 0);
+          if (++combo == p.ncombo) {
+            combo = 0;
+            if (bias_rr && ++bphase == p.ngroups) bphase = 0;
+          }
+        }
+      }
       mbar_wait(acc_full, 0);
       tc_fence_after();
       for (int t = 0; t < gtaps; ++t) {
