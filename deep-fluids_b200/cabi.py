@@ -30,6 +30,7 @@ SIGNATURES = {
     "dfl_conv3x3_wgrad": (_i, [_vp, _vp, _vp, _vp, _dims, _i, _i, _i, _vp]),
     "dfl_conv3x3_wgrad_split": (_i, [_vp, _vp, _vp, _vp, _dims, _i, _vp]),
     "dfl_bias_grad": (_i, [_vp, _vp, _sz, _vp]),
+    "dfl_lastconv_fwd": (_i, [_vp, _vp, _vp, _vp, _dims, _i, _i, _vp]),
     "dfl_lastconv_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _dims, _i, _i, _vp]),
     "dfl_pack_conv_weights_ex": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _vp]),
     "dfl_conv_taps": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _dims, _dims, _dims, _i, _i, _i, _i, C.POINTER(C.c_int32), _i,

@@ -89,6 +89,8 @@ int fc_fwd(const float* z, const float* W, const float* bias, void* out, int B, 
            cudaStream_t st);
 int fc_bwd(const float* z, const void* dout, float* dW, float* db, int B, int K, int N, int dout_dtype,
            cudaStream_t st);
+int lastconv_fwd_tc(const void* s, const float* w, const float* bias, float* out, const int64_t* dims, int nd, int cout,
+                    cudaStream_t st);
 int lastconv_bwd_tc(const void* s, const float* dout, const float* w, const void* mask_src, void* ds, void* ds_masked,
                     float* dw, float* db, const int64_t* dims, int nd, int cout, cudaStream_t st);
 int pool_mask(const void* g, const void* mask_src, void* ds, void* dmasked, const int64_t* cdims, int nd,
@@ -230,6 +232,10 @@ int dfl_ae_loss_p(const float* z, const float* y, float* dz, float* loss_p, int 
 }
 int dfl_bias_grad(const void* dpre, float* db, size_t npos, void* stream) {
   return bias_grad(dpre, db, npos, ST(stream));
+}
+int dfl_lastconv_fwd(const void* s, const float* w, const float* bias, float* out, const int64_t* dims, int ndim, int cout,
+                     void* stream) {
+  return lastconv_fwd_tc(s, w, bias, out, dims, ndim, cout, ST(stream));
 }
 int dfl_lastconv_bwd(const void* s, const float* dout, const float* w, const void* mask_src, void* ds, void* ds_masked,
                      float* dw, float* db, const int64_t* dims, int ndim, int cout, void* stream) {

@@ -127,14 +127,13 @@ class GeneratorEngine(object):
     precision = "bf16"
 
     def _alloc_operands(self):
-        """bf16 GEMM operands: forward [Cout, taps*Cin], dgrad [Cin, taps'*Cout], output conv [16, taps*Cin]"""
+        """bf16 GEMM operands: forward [Cout, taps*Cin], dgrad [Cin, taps'*Cout] (the output conv reads the fp32 variable)"""
         filters = self.filters
         self.wf, self.wd = {}, {}
         for row in self.conv_names:
             for cn in row:
                 self.wf[cn] = torch.empty(filters, self.taps * filters, dtype=torch.bfloat16, device=self.device)
                 self.wd[cn] = torch.empty(filters, self.taps * filters, dtype=torch.bfloat16, device=self.device)
-        self.w_last16 = torch.zeros(16, self.taps * filters, dtype=torch.bfloat16, device=self.device)
 
     def _alloc(self):
         """activations (bf16) and gradient scratch"""
@@ -166,7 +165,6 @@ class GeneratorEngine(object):
         for row in self.conv_names:
             for cn in row:
                 K.pack_conv_weights(self.params.p(cn + "/weights"), self.wf[cn], self.wd[cn])
-        K.pack_lastconv_weights(self.params.p(self.last_name + "/weights"), self.w_last16)
 
     # ------------------------------------------------------------------ forward (model.py:5-46 / :48-87)
     def forward(self, z):
@@ -191,7 +189,7 @@ class GeneratorEngine(object):
                     K.conv3x3(cur, self.wf[cn], bias, out=self.y[i][c], out2=self.s, residual=self.x0[i],
                               flags=K.CONV_LRELU)
                 cur = self.y[i][c]
-        K.lastconv_fwd_tc(self.s, self.w_last16, P.p(self.last_name + "/biases"), self.cout, out=self.pot)
+        K.lastconv_fwd(self.s, P.p(self.last_name + "/weights"), P.p(self.last_name + "/biases"), out=self.pot)
         return self.pot
 
     # ------------------------------------------------------------------ backward (TF autodiff of the above)

@@ -323,6 +323,19 @@ def lastconv_fwd_tc(x, w16, bias, cout, out=None):
     return out
 
 
+def lastconv_fwd(x, w, bias, out=None):
+    """128 -> cout (1..3) output conv (model.py:42,84): one GEMM per input plane + shift-sum (z-marching tensor-core
+    kernel); w = the fp32 TF-layout variable [3,(3,)3,128,cout]; out fp32 [.., cout]."""
+    d, nd = _spatial(x)
+    cout = w.shape[-1]
+    if out is None:
+        out = torch.empty(x.shape[:-1] + (cout,), dtype=torch.float32, device=x.device)
+    flops = 2.0 * (x.numel() // 128) * 128 * cout * (3 ** nd)
+    PROF.timed("lastconv_fwd_tc", flops, lambda: check(cabi.lib().dfl_lastconv_fwd(
+        _p(x), _p(w), _p(bias), _p(out), d, nd, cout, _st())))
+    return out
+
+
 def lastconv_bwd(s, dout, w, mask_src, ds, ds_masked, dw, db):
     """fused dgrad + wgrad + bias-grad of the output conv (tensor cores)"""
     d, nd = _spatial(s)

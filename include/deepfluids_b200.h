@@ -105,6 +105,13 @@ int dfl_conv3x3_wgrad(const void* x, const void* dpre, float* dw, float* db, con
 /* db[c] += sum_p dpre[p][c]   (dpre bf16 [npos][128]) */
 int dfl_bias_grad(const void* dpre, float* db, size_t npos, void* stream);
 
+/* Forward of the 128 -> cout (1..3) output conv (model.py:42,84: conv2d/conv3d(x, output_shape[-1], k=3, s=1, act=None)):
+ * out = conv(s, w) + bias, fp32 [..,cout].  s = bf16 [..,128]; w = the fp32 TF-layout variable [3,(3,)3,128,cout] (rounded
+ * to bf16 on chip); bias may be NULL.  One plain GEMM per input plane (P[voxel][tap*cout+co], N <= 96) + a shift-sum over
+ * the taps, marching along z: 13x fewer tensor-core instructions than the cout <= 16 variant of dfl_conv3x3_fwd. */
+int dfl_lastconv_fwd(const void* s, const float* w, const float* bias, float* out, const int64_t* dims, int ndim, int cout,
+                     void* stream);
+
 /* Fused tensor-core backward of the output conv: ds = conv^T(dout, w) (bf16, may be NULL), ds_masked = ds *
  * lrelu'(mask_src) (bf16, may be NULL), dw += s^T (x) dout, db += sum dout (fp32, accumulated).  s = the conv's input
  * (bf16 [..,128]).  Replaces Conv*BackpropInput + Conv*BackpropFilter + BiasAddGrad of model.py:42,84. */

@@ -286,9 +286,12 @@ def test_fc_fwd_bwd(B, K_, N):
 
 
 @pytest.mark.parametrize("shape,nd,cout", [((2, 4, 6, 11), 3, 3), ((1, 8, 8, 8), 3, 3), ((1, 5, 20, 37), 3, 1), ((3, 16, 12), 2, 1),
-                                           ((2, 9, 21), 2, 2), ((2, 40, 33), 2, 3)])
+                                           ((2, 9, 21), 2, 2), ((2, 40, 33), 2, 3), ((2, 40, 20, 37), 3, 3), ((1, 2, 2, 2), 3, 2),
+                                           ((1, 33, 9, 16), 3, 1)])
 def test_lastconv_tensorcore_fwd_and_fused_bwd(shape, nd, cout):
-    """tap-window N=16 forward and the fused im2col-GEMM backward vs autograd on the oracle (bf16 operands, fp32 acc)."""
+    """plane-GEMM + shift-sum forward (and the tap-window N=16 forward the fp32-grade path still uses) and the fused
+    im2col-GEMM backward vs autograd on the oracle (bf16 operands, fp32 acc).  (2,40,20,37): 720 (column, plane) units
+    over 148 CTAs = z-segments that start and end inside a column."""
     from deepfluids_b200 import kernels as K
     g = torch.Generator().manual_seed(41)
     x = (torch.randn(*shape, 128, generator=g) * 0.5).bfloat16()
@@ -303,6 +306,11 @@ def test_lastconv_tensorcore_fwd_and_fused_bwd(shape, nd, cout):
     w16 = K.pack_lastconv_weights(w.to(dev()))
     out = K.lastconv_fwd_tc(x.to(dev()), w16, b.to(dev()), cout)
     assert rel_l2(out, y.detach()) <= 1e-5
+    out2 = torch.full(y.shape, float("nan"), device=dev())                   # every output voxel must be written
+    K.lastconv_fwd(x.to(dev()), w.to(dev()), b.to(dev()), out=out2)
+    assert rel_l2(out2, y.detach()) <= 1e-5
+    out3 = K.lastconv_fwd(x.to(dev()), w.to(dev()), None)                   # bias is optional
+    assert rel_l2(out3, y.detach() - b) <= 1e-5
     mask_src = torch.randn(*shape, 128, generator=g).bfloat16()
     ds = torch.empty(x.shape, dtype=torch.bfloat16, device=dev())
     dsm = torch.empty_like(ds)
@@ -313,6 +321,22 @@ def test_lastconv_tensorcore_fwd_and_fused_bwd(shape, nd, cout):
     assert rel_l2(dsm.float(), gx * torch.where(mask_src.float() >= 0, 1.0, 0.2)) <= 4e-3
     assert rel_l2(dw, gw) <= 1e-4
     assert rel_l2(db, gb) <= 1e-5
+
+
+@pytest.mark.parametrize("shape,nd,cout", [((1, 128, 128, 128), 3, 3), ((64, 128, 96), 2, 1)])
+def test_lastconv_fwd_full_size_two_formulations_agree(shape, nd, cout):
+    """BASELINE-size grids: the z-marching plane-GEMM kernel and the tap-window N=16 kernel (different tilings, different
+    summation orders, both fp32 accumulate of the same bf16 products) must agree to fp32 rounding."""
+    from deepfluids_b200 import kernels as K
+    g = torch.Generator(device="cuda").manual_seed(43)
+    x = (torch.randn(*shape, 128, device=dev(), generator=g) * 0.5).bfloat16()
+    w = (torch.randn((3,) * nd + (128, cout), device=dev(), generator=g) * 0.05).bfloat16().float()
+    b = torch.randn(cout, device=dev(), generator=g) * 0.1
+    ref = K.lastconv_fwd_tc(x, K.pack_lastconv_weights(w), b, cout)
+    out = torch.full_like(ref, float("nan"))
+    K.lastconv_fwd(x, w, b, out=out)
+    assert rel_l2(out, ref) <= 1e-5
+    assert float((out - ref).abs().max()) <= 1e-4
 
 
 @pytest.mark.parametrize("cshape,nd", [((2, 3, 4, 5), 3), ((2, 6, 7), 2)])
