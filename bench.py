@@ -293,6 +293,9 @@ def run_gpu_arm(args):
         a[1] += work
         a[2] += 1
     K.PROF.events = None
+    # every kernel of the step: ms per step and launches per step (CUDA events, eager replay of the same step)
+    kernel_ms = {k: {"ms_per_step": round(v[0] / 2 * 1e3, 4), "launches_per_step": v[2] // 2}
+                 for k, v in sorted(agg.items(), key=lambda kv: -kv[1][0])}
     for extra in ("conv_tap",):           # stride-2 / per-tap launches count as conv work too (AE)
         if extra in agg:
             a, e = agg.setdefault("conv_tc", [0.0, 0.0, 0]), agg[extra]
@@ -316,6 +319,7 @@ def run_gpu_arm(args):
                     "stencil_fused_kernel": {"bound": "hbm", "achieved": st_b / st_t / 1e9, "unit": "GB/s",
                                              "frac": st_b / st_t / 1e9 / peaks["hbm_gbs"],
                                              "share_of_step": st_t / 2 / (ms_per_step * 1e-3)}}}
+    roofline["kernel_ms"] = kernel_ms
     fl = FLOPS_PER_FIELD[args.workload]
     if fl:
         roofline["step_conv_tflops_per_gpu"] = value / world * fl / 1e12

@@ -93,9 +93,16 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
   return *reinterpret_cast<uint32_t*>(&h);
 }
 
-// The shared epilogue (defined below) converts one accumulator row to bf16 outputs.
+// The shared epilogue (defined below) converts one accumulator row to bf16 outputs.  EpiPre carries the global-memory
+// operands of one 32-channel chunk (lrelu-mask source, residual) requested one chunk ahead of their use.
+struct EpiPre { uint4 m[4], r[4]; };
+__device__ __forceinline__ size_t epi_pos(const ConvTcParams& p, int b, int z, int y, int x) {
+  return ((static_cast<size_t>(b) * p.oD + z) * p.oH + y) * p.oW + x;
+}
+__device__ __forceinline__ void epi_prefetch(const ConvTcParams& p, bool valid, size_t pos, int c0, EpiPre& e);
 __device__ __forceinline__ void conv_epilogue_row(const ConvTcParams& p, uint32_t taddr, bool valid, int b, int z,
-                                                  int y, int x, const float* s_bias);
+                                                  int y, int x, const float* s_bias, EpiPre& pre, bool next_valid,
+                                                  size_t next_pos);
 
 // =============================================================================================
 // Generic per-tap kernel (one TMA box per (tap, 64-channel slice); 6 x 32 KB stages).  Used where the tap-window
@@ -204,10 +211,12 @@ conv_tap_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       const int b = r;
       const int xo = x * p.out_stride + p.orx, yo = y * p.out_stride + p.ory, zo = z * p.out_stride + p.orz;
       const bool valid = (x < p.W) && (y < p.H) && (z < p.D) && (xo < p.oW) && (yo < p.oH) && (zo < p.oD);
+      EpiPre pre;
+      epi_prefetch(p, valid, epi_pos(p, b, zo, yo, xo), 0, pre);      // in flight while the tile's MMAs finish
       mbar_wait(&tfull_bar[acc], aph);
       tc_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * CT_BLOCK_N;
-      conv_epilogue_row(p, taddr, valid, b, zo, yo, xo, s_bias);
+      conv_epilogue_row(p, taddr, valid, b, zo, yo, xo, s_bias, pre, false, 0);
       tc_fence_before();
       mbar_arrive(&tempty_bar[acc]);
     }
@@ -247,6 +256,28 @@ __device__ __forceinline__ void epi_load32(const __nv_bfloat16* ptr, float (&f)[
     for (int k = 0; k < 8; ++k) f[q * 8 + k] = t[k];
   }
 }
+__device__ __forceinline__ void epi_unpack32(const uint4 (&q4)[4], float (&f)[32]) {
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    float t[8];
+    unpack_bf16x8(q4[q], t);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) f[q * 8 + k] = t[k];
+  }
+}
+__device__ __forceinline__ void epi_prefetch(const ConvTcParams& p, bool valid, size_t pos, int c0, EpiPre& e) {
+  if (!valid) return;
+  if (p.mask_src) {
+    const uint4* m = reinterpret_cast<const uint4*>(p.mask_src + pos * CT_BLOCK_N + c0);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) e.m[q] = __ldg(m + q);
+  }
+  if (p.out2 && p.residual) {
+    const uint4* r = reinterpret_cast<const uint4*>(p.residual + pos * CT_BLOCK_N + c0);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) e.r[q] = __ldg(r + q);
+  }
+}
 // store 32 channels as bf16; in split mode also the residual lo = bf16(v - float(bf16(v))) one block further
 __device__ __forceinline__ void epi_store32(__nv_bfloat16* ptr, const float (&v)[32], bool split, size_t blkstride) {
   uint4* o = reinterpret_cast<uint4*>(ptr);
@@ -272,19 +303,26 @@ __device__ __forceinline__ void epi_store32(__nv_bfloat16* ptr, const float (&v)
 //   out2 = (v + residual) [* lrelu'(mask_src) if CF_MASK_AFTER_RESIDUAL], nearest-x2 replicated if CF_OUT2_UPSAMPLE
 // CF_SPLIT_IO (fp32-grade mode): every bf16 tensor is a (hi, lo) pair one block (B*voxels*128 elements) apart: residual
 // is read as hi + lo, outputs are written as hi = bf16(v), lo = bf16(v - hi); masks use the hi part (same sign).
+// The mask / residual operands of chunk c0+32 (or of chunk 0 of the row the caller names as `next`) are requested before
+// chunk c0 is processed: with the loads issued on demand every chunk paid a dependent global round trip (8 per 256-voxel
+// tile), which exceeded the MMA time of a 2D tile (K = 1152) and left the 2D data-gradient launches epilogue-bound.
 __device__ __forceinline__ void conv_epilogue_row(const ConvTcParams& p, uint32_t taddr, bool valid, int b, int z,
-                                                  int y, int x, const float* s_bias) {
+                                                  int y, int x, const float* s_bias, EpiPre& pre, bool next_valid,
+                                                  size_t next_pos) {
   const bool ups = (p.flags & CF_OUT2_UPSAMPLE) != 0;
   const bool act = (p.flags & CF_LRELU) != 0;
   const bool mask_after = (p.flags & CF_MASK_AFTER_RESIDUAL) != 0;
   const bool split = (p.flags & CF_SPLIT_IO) != 0;
   const size_t vox = static_cast<size_t>(p.oD) * p.oH * p.oW;
   const size_t blk = static_cast<size_t>(p.B) * vox * CT_BLOCK_N;          // block stride of an output-shaped tensor
-  const size_t pos = ((static_cast<size_t>(b) * p.oD + z) * p.oH + y) * p.oW + x;
+  const size_t pos = epi_pos(p, b, z, y, x);
 #pragma unroll 1
   for (int c0 = 0; c0 < CT_BLOCK_N; c0 += 32) {
     uint32_t rr[32];
     tmem_ld_32x32(taddr + c0, rr);
+    const EpiPre cur = pre;
+    if (c0 + 32 < CT_BLOCK_N) epi_prefetch(p, valid, pos, c0 + 32, pre);
+    else epi_prefetch(p, next_valid, next_pos, 0, pre);
     tmem_ld_wait();
     if (!valid) continue;
     float v[32], m[32];
@@ -294,7 +332,7 @@ __device__ __forceinline__ void conv_epilogue_row(const ConvTcParams& p, uint32_
       v[k] = act ? lrelu_f(t) : t;
     }
     if (p.mask_src) {
-      epi_load32(p.mask_src + pos * CT_BLOCK_N + c0, m);
+      epi_unpack32(cur.m, m);
 #pragma unroll
       for (int k = 0; k < 32; ++k) m[k] = lrelu_grad_from_out(m[k]);
     }
@@ -307,7 +345,7 @@ __device__ __forceinline__ void conv_epilogue_row(const ConvTcParams& p, uint32_
     if (p.out2) {
       if (p.residual) {
         float f[32];
-        epi_load32(p.residual + pos * CT_BLOCK_N + c0, f);
+        epi_unpack32(cur.r, f);
 #pragma unroll
         for (int k = 0; k < 32; ++k) v[k] += f[k];
         if (split) {
@@ -510,6 +548,11 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       const int y0 = (r % p.ty) * TY; r /= p.ty;
       const int z0 = (r % p.tz) * TZ; r /= p.tz;
       const int b = r;
+      EpiPre pre;
+      if (kN == CT_BLOCK_N) {       // half 0's first chunk of mask / residual: in flight while the tile's MMAs finish
+        const int z = k3D ? z0 : 0, y = y0 + line, x = x0 + xi;
+        epi_prefetch(p, (x < p.W) && (y < p.H) && (z < p.D), epi_pos(p, b, z, y, x), 0, pre);
+      }
       mbar_wait(&tfull_bar[acc], aph);
       tc_fence_after();
 #pragma unroll 1
@@ -518,7 +561,10 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         const bool valid = (x < p.W) && (y < p.H) && (z < p.D);
         const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * 256 + h * CT_BLOCK_N;
         if (kN == CT_BLOCK_N) {
-          conv_epilogue_row(p, taddr, valid, b, z, y, x, s_bias);
+          // the row of half 1 (same y; z + 1 in 3D, x + 8 in 2D) is the `next` row of half 0
+          const int zn = k3D ? z0 + 1 : 0, xn = k3D ? x0 + xi : x0 + 8 + xi;
+          const bool nvalid = (h == 0) && (xn < p.W) && (y < p.H) && (zn < p.D);
+          conv_epilogue_row(p, taddr, valid, b, z, y, x, s_bias, pre, nvalid, nvalid ? epi_pos(p, b, zn, y, xn) : 0);
         } else {
           uint32_t rr[32];
           tmem_ld_32x32(taddr, rr);      // columns >= 16 are never written: ignored

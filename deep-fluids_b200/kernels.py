@@ -63,8 +63,7 @@ def _spatial(t):
 def curl_fwd(pot):
     d, nd = _spatial(pot)
     vel = torch.empty(pot.shape[:-1] + (nd,), dtype=pot.dtype, device=pot.device)
-    PROF.launches += 1
-    check(cabi.lib().dfl_curl_fwd(_p(pot), _p(vel), d, nd, pot.shape[-1], _dt(pot), _st()))
+    PROF.timed("curl_fwd", 0.0, lambda: check(cabi.lib().dfl_curl_fwd(_p(pot), _p(vel), d, nd, pot.shape[-1], _dt(pot), _st())))
     return vel
 
 
@@ -73,16 +72,14 @@ def jacobian_fwd(vel, want_jac=True, want_aux=True):
     assert vel.shape[-1] == nd
     jac = torch.empty(vel.shape[:-1] + (nd * nd,), dtype=vel.dtype, device=vel.device) if want_jac else None
     aux = torch.empty(vel.shape[:-1] + (1 if nd == 2 else 3,), dtype=vel.dtype, device=vel.device) if want_aux else None
-    PROF.launches += 1
-    check(cabi.lib().dfl_jacobian_fwd(_p(vel), _p(jac), _p(aux), d, nd, _dt(vel), _st()))
+    PROF.timed("jacobian_fwd", 0.0, lambda: check(cabi.lib().dfl_jacobian_fwd(_p(vel), _p(jac), _p(aux), d, nd, _dt(vel), _st())))
     return jac, aux
 
 
 def divergence(vel):
     d, nd = _spatial(vel)
     out = torch.empty((vel.shape[0],) + tuple(s - 1 for s in vel.shape[1:-1]) + (1,), dtype=vel.dtype, device=vel.device)
-    PROF.launches += 1
-    check(cabi.lib().dfl_divergence(_p(vel), _p(out), d, nd, _dt(vel), _st()))
+    PROF.timed("divergence", 0.0, lambda: check(cabi.lib().dfl_divergence(_p(vel), _p(out), d, nd, _dt(vel), _st())))
     return out
 
 
@@ -115,16 +112,14 @@ def fc_fwd(z, W, bias, out_dtype=torch.bfloat16, out=None):
     N = W.shape[1]
     if out is None:
         out = torch.empty(B, N, dtype=out_dtype, device=z.device)
-    PROF.launches += 1
-    check(cabi.lib().dfl_fc_fwd(_p(z), _p(W), _p(bias), _p(out), B, K, N, _dt(out), _st()))
+    PROF.timed("fc_fwd", 0.0, lambda: check(cabi.lib().dfl_fc_fwd(_p(z), _p(W), _p(bias), _p(out), B, K, N, _dt(out), _st())))
     return out
 
 
 def fc_bwd(z, dout, dW, db):
     B, K = z.shape
     N = dW.shape[1]
-    PROF.launches += 1
-    check(cabi.lib().dfl_fc_bwd(_p(z), _p(dout), _p(dW), _p(db), B, K, N, _dt(dout), _st()))
+    PROF.timed("fc_bwd", 0.0, lambda: check(cabi.lib().dfl_fc_bwd(_p(z), _p(dout), _p(dW), _p(db), B, K, N, _dt(dout), _st())))
 
 
 # ------------------------------------------------------------------ conv
@@ -136,8 +131,7 @@ def pack_conv_weights(w, w_fwd=None, w_dgrad=None):
         w_fwd = torch.empty(cout, taps * cin, dtype=torch.bfloat16, device=w.device)
     if w_dgrad is None:
         w_dgrad = torch.empty(cin, taps * cout, dtype=torch.bfloat16, device=w.device)
-    PROF.launches += 1
-    check(cabi.lib().dfl_pack_conv_weights(_p(w), _p(w_fwd), _p(w_dgrad), taps, cin, cout, _st()))
+    PROF.timed("pack_conv_weights", 0.0, lambda: check(cabi.lib().dfl_pack_conv_weights(_p(w), _p(w_fwd), _p(w_dgrad), taps, cin, cout, _st())))
     return w_fwd, w_dgrad
 
 
@@ -157,8 +151,7 @@ def pack_conv_weights_ex(w, w_fwd, w_dgrad, cin_ld):
     """as pack_conv_weights, forward operand laid out for `cin_ld` (>= Cin) input channels"""
     cin, cout = w.shape[-2], w.shape[-1]
     taps = w.numel() // (cin * cout)
-    PROF.launches += 1
-    check(cabi.lib().dfl_pack_conv_weights_ex(_p(w), _p(w_fwd), _p(w_dgrad), taps, cin, cout, cin_ld, _st()))
+    PROF.timed("pack_conv_weights_ex", 0.0, lambda: check(cabi.lib().dfl_pack_conv_weights_ex(_p(w), _p(w_fwd), _p(w_dgrad), taps, cin, cout, cin_ld, _st())))
 
 
 def conv_taps(x, w_rows, bias, out, out2, residual, mask_src, tile_dims, out_dims, cin, in_stride, taps, out_stride,
@@ -188,51 +181,43 @@ def conv_wgrad_ex(x, dpre, dw_ptr_tensor, db, in_stride, pad, dw_tap_stride, dw_
 
 def pad_cast(x, out):
     """fp32 [..., cin] -> bf16 [..., 128] zero padded"""
-    PROF.launches += 1
-    check(cabi.lib().dfl_pad_cast(_p(x), _p(out), x.numel() // x.shape[-1], x.shape[-1], _st()))
+    PROF.timed("pad_cast", 0.0, lambda: check(cabi.lib().dfl_pad_cast(_p(x), _p(out), x.numel() // x.shape[-1], x.shape[-1], _st())))
 
 
 def add_mask(a, b, y, out):
     """out = (a + b) * lrelu'(y)   (b, y optional)"""
-    PROF.launches += 1
-    check(cabi.lib().dfl_add_mask(_p(a), _p(b), _p(y), _p(out), a.numel(), _st()))
+    PROF.timed("add_mask", 0.0, lambda: check(cabi.lib().dfl_add_mask(_p(a), _p(b), _p(y), _p(out), a.numel(), _st())))
 
 
 def enc_fc_fwd(flat, W, bias, z, nblk):
     B = flat.shape[0] // nblk
     V = flat.numel() // (flat.shape[0] * 128)
-    PROF.launches += 1
-    check(cabi.lib().dfl_enc_fc_fwd(_p(flat), _p(W), _p(bias), _p(z), B, V, nblk, W.shape[1], _st()))
+    PROF.timed("enc_fc_fwd", 0.0, lambda: check(cabi.lib().dfl_enc_fc_fwd(_p(flat), _p(W), _p(bias), _p(z), B, V, nblk, W.shape[1], _st())))
 
 
 def enc_fc_bwd(flat, W, dz, dW, db, dflat, nblk):
     B = flat.shape[0] // nblk
     V = flat.numel() // (flat.shape[0] * 128)
-    PROF.launches += 1
-    check(cabi.lib().dfl_enc_fc_bwd(_p(flat), _p(W), _p(dz), _p(dW), _p(db), _p(dflat), B, V, nblk, W.shape[1], _st()))
+    PROF.timed("enc_fc_bwd", 0.0, lambda: check(cabi.lib().dfl_enc_fc_bwd(_p(flat), _p(W), _p(dz), _p(dW), _p(db), _p(dflat), B, V, nblk, W.shape[1], _st())))
 
 
 def fc_dz(dout, W, dz, accumulate=False):
     B, N = dout.shape
-    PROF.launches += 1
-    check(cabi.lib().dfl_fc_dz(_p(dout), _p(W), _p(dz), B, W.shape[0], N, _dt(dout), 1 if accumulate else 0, _st()))
+    PROF.timed("fc_dz", 0.0, lambda: check(cabi.lib().dfl_fc_dz(_p(dout), _p(W), _p(dz), B, W.shape[0], N, _dt(dout), 1 if accumulate else 0, _st())))
 
 
 def ae_loss_p(z, y_last, dz, loss_p, scale):
     B, Z = z.shape
-    PROF.launches += 1
-    check(cabi.lib().dfl_ae_loss_p(_p(z), _p(y_last), _p(dz), _p(loss_p), B, Z, y_last.shape[1], scale, _st()))
+    PROF.timed("ae_loss_p", 0.0, lambda: check(cabi.lib().dfl_ae_loss_p(_p(z), _p(y_last), _p(dz), _p(loss_p), B, Z, y_last.shape[1], scale, _st())))
 
 
 def ae_sigmoid(z_lin, z):
-    PROF.launches += 1
-    check(cabi.lib().dfl_ae_sigmoid(_p(z_lin), _p(z), z_lin.numel(), _st()))
+    PROF.timed("ae_sigmoid", 0.0, lambda: check(cabi.lib().dfl_ae_sigmoid(_p(z_lin), _p(z), z_lin.numel(), _st())))
 
 
 def ae_sparse_bwd(z, dz, dz_lin, loss_kl, p_num, rho, w5):
     B, Z = z.shape
-    PROF.launches += 1
-    check(cabi.lib().dfl_ae_sparse_bwd(_p(z), _p(dz), _p(dz_lin), _p(loss_kl), B, Z, p_num, rho, w5, _st()))
+    PROF.timed("ae_sparse_bwd", 0.0, lambda: check(cabi.lib().dfl_ae_sparse_bwd(_p(z), _p(dz), _p(dz_lin), _p(loss_kl), B, Z, p_num, rho, w5, _st())))
 
 
 # ------------------------------------------------------------------ fp32-grade mode (bf16x3 split operands)
@@ -243,8 +228,7 @@ def pack_conv_weights_split(w, w_fwd, w_dgrad):
     """fp32 TF-layout weights -> split tensor-core operands [rows][taps*384] (see dfl_pack_conv_weights_split)"""
     cin, cout = w.shape[-2], w.shape[-1]
     taps = w.numel() // (cin * cout)
-    PROF.launches += 1
-    check(cabi.lib().dfl_pack_conv_weights_split(_p(w), _p(w_fwd), _p(w_dgrad), taps, cin, cout, _st()))
+    PROF.timed("pack_conv_weights_split", 0.0, lambda: check(cabi.lib().dfl_pack_conv_weights_split(_p(w), _p(w_fwd), _p(w_dgrad), taps, cin, cout, _st())))
 
 
 def conv3x3_split(x2, w_split, bias=None, out=None, out2=None, residual=None, mask_src=None, flags=0, cout=128):
@@ -262,21 +246,18 @@ def conv3x3_split(x2, w_split, bias=None, out=None, out2=None, residual=None, ma
 def split_f32(x, out, cpad=None):
     """fp32 [..., c] -> (hi, lo) pair written to out [2, ..., cpad]"""
     c = x.shape[-1]
-    PROF.launches += 1
-    check(cabi.lib().dfl_split_f32(_p(x), _p(out), x.numel() // c, c, cpad or c, _st()))
+    PROF.timed("split_f32", 0.0, lambda: check(cabi.lib().dfl_split_f32(_p(x), _p(out), x.numel() // c, c, cpad or c, _st())))
 
 
 def merge_split(x2, out):
-    PROF.launches += 1
-    check(cabi.lib().dfl_merge_split(_p(x2), _p(out), out.numel(), _st()))
+    PROF.timed("merge_split", 0.0, lambda: check(cabi.lib().dfl_merge_split(_p(x2), _p(out), out.numel(), _st())))
 
 
 def pool_mask_split(g2, mask_src, ds2, dmasked2):
     ref = ds2 if ds2 is not None else dmasked2
     nd = ref.dim() - 2
     d = dims_array((ref.shape[0] // 2,) + tuple(ref.shape[1:-1]))
-    PROF.launches += 1
-    check(cabi.lib().dfl_pool_mask_split(_p(g2), _p(mask_src), _p(ds2), _p(dmasked2), d, nd, _st()))
+    PROF.timed("pool_mask_split", 0.0, lambda: check(cabi.lib().dfl_pool_mask_split(_p(g2), _p(mask_src), _p(ds2), _p(dmasked2), d, nd, _st())))
 
 
 def conv3x3_wgrad(x, dpre, dw, db=None):
@@ -297,8 +278,7 @@ def conv3x3_wgrad_split(x2, dpre2, dw, db=None):
 
 
 def bias_grad(dpre, db):
-    PROF.launches += 1
-    check(cabi.lib().dfl_bias_grad(_p(dpre), _p(db), dpre.numel() // dpre.shape[-1], _st()))
+    PROF.timed("bias_grad", 0.0, lambda: check(cabi.lib().dfl_bias_grad(_p(dpre), _p(db), dpre.numel() // dpre.shape[-1], _st())))
 
 
 def pack_lastconv_weights(w, w16=None):
@@ -307,8 +287,7 @@ def pack_lastconv_weights(w, w16=None):
     taps = w.numel() // (cin * cout)
     if w16 is None:
         w16 = torch.zeros(16, taps * cin, dtype=torch.bfloat16, device=w.device)
-    PROF.launches += 1
-    check(cabi.lib().dfl_pack_conv_weights(_p(w), _p(w16), None, taps, cin, cout, _st()))
+    PROF.timed("pack_conv_weights", 0.0, lambda: check(cabi.lib().dfl_pack_conv_weights(_p(w), _p(w16), None, taps, cin, cout, _st())))
     return w16
 
 
@@ -347,27 +326,23 @@ def pool_mask(g, mask_src, ds, dmasked):
     """g: fine-grid gradient [B,(2D,)2H,2W,128]; ds / dmasked: coarse [B,(D,)H,W,128]"""
     ref = ds if ds is not None else dmasked
     d, nd = _spatial(ref)
-    PROF.launches += 1
-    check(cabi.lib().dfl_pool_mask(_p(g), _p(mask_src), _p(ds), _p(dmasked), d, nd, _st()))
+    PROF.timed("pool_mask", 0.0, lambda: check(cabi.lib().dfl_pool_mask(_p(g), _p(mask_src), _p(ds), _p(dmasked), d, nd, _st())))
 
 
 # ------------------------------------------------------------------ optimizer / misc
 def adam_step_dev(param, grad, m, v, lr_t_dev, beta1, beta2, eps=1e-8, grad_scale=1.0):
     """Adam / GD with the step size in device memory (CUDA-graph replayable)."""
-    PROF.launches += 1
-    check(cabi.lib().dfl_adam_step_dev(_p(param), _p(grad), _p(m), _p(v), param.numel(), _p(lr_t_dev), beta1, beta2, eps,
-                                       grad_scale, _st()))
+    PROF.timed("adam_step_dev", 0.0, lambda: check(cabi.lib().dfl_adam_step_dev(_p(param), _p(grad), _p(m), _p(v), param.numel(), _p(lr_t_dev), beta1, beta2, eps,
+                                       grad_scale, _st())))
 
 
 def adam_step(param, grad, m, v, lr_t, beta1, beta2, eps=1e-8, grad_scale=1.0):
-    PROF.launches += 1
-    check(cabi.lib().dfl_adam_step(_p(param), _p(grad), _p(m), _p(v), param.numel(), lr_t, beta1, beta2, eps,
-                                   grad_scale, _st()))
+    PROF.timed("adam_step", 0.0, lambda: check(cabi.lib().dfl_adam_step(_p(param), _p(grad), _p(m), _p(v), param.numel(), lr_t, beta1, beta2, eps,
+                                   grad_scale, _st())))
 
 
 def cast_f32_bf16(a, out=None):
     if out is None:
         out = torch.empty(a.shape, dtype=torch.bfloat16, device=a.device)
-    PROF.launches += 1
-    check(cabi.lib().dfl_cast_f32_bf16(_p(a), _p(out), a.numel(), _st()))
+    PROF.timed("cast_f32_bf16", 0.0, lambda: check(cabi.lib().dfl_cast_f32_bf16(_p(a), _p(out), a.numel(), _st())))
     return out
