@@ -22,7 +22,8 @@ namespace dfl {
 constexpr int LB_THREADS = 320;
 constexpr int LB_OP = 32768;                       // one 128 x 128 bf16 operand image (two 16 KB halves)
 constexpr int LB_STAGE_F = 3 * 180 * 3;            // floats: halo'd dOut tile, <= 3 planes x (10 x 18) positions x 3 channels
-constexpr int LB_SMEM = 5 * LB_OP + 2 * LB_STAGE_F * 4 + 1024 + 1024;   // W' + 2 G + 2 S + 2 dOut stages + ctrl + align slack
+constexpr int LB_TR = 2 * 128 * 128;                // bytes: bf16(v) and bf16(0.2 v) images of one 64-channel half tile
+constexpr int LB_SMEM = 5 * LB_OP + LB_TR + 2 * LB_STAGE_F * 4 + 1024 + 1024;   // W' + 2 G + 2 S + transposition images + 2 dOut stages + ctrl + align slack
 
 struct LastBwdParams {
   int B, D, H, W;
@@ -53,8 +54,9 @@ lastconv_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmS, LastBwdParams p)
   uint8_t* sW = smem;                   // [2 halves][128 rows (ci)][128 B]   K-major, k = tap*C+co
   uint8_t* sG = smem + LB_OP;           // 2 buffers
   uint8_t* sS = smem + 3 * LB_OP;       // 2 buffers
-  float* sD = reinterpret_cast<float*>(smem + 5 * LB_OP);      // 2 x LB_STAGE_F: halo'd dOut tiles (builder warps only)
-  uint8_t* ctrl = smem + 5 * LB_OP + 2 * LB_STAGE_F * 4;
+  uint8_t* sT = smem + 5 * LB_OP;                              // epilogue transposition images (epilogue warps only)
+  float* sD = reinterpret_cast<float*>(sT + LB_TR);            // 2 x LB_STAGE_F: halo'd dOut tiles (builder warps only)
+  uint8_t* ctrl = sT + LB_TR + 2 * LB_STAGE_F * 4;
   uint64_t* s_full = reinterpret_cast<uint64_t*>(ctrl);
   uint64_t* s_empty = s_full + 2;
   uint64_t* g_full = s_empty + 2;
@@ -151,64 +153,96 @@ lastconv_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmS, LastBwdParams p)
     }
   } else if (warp < 6) {
     // ================================ epilogue (warps 2..5) ================================
+    // Accumulator rows are transposed through shared memory so that the global stores are full 128-byte lines: written
+    // straight from the TMEM-row-owning thread, every STG.128 of a warp touched 32 different lines with 16 bytes each
+    // (32 half-filled sectors), and that store pattern -- not HBM, not the tensor pipe -- set the kernel's time (a timing
+    // run without the stores: 3.4 -> 1.7 ms at 128^3 x 4, profiles/r01_diag_nostore_c4.json).
+    //   phase 1 (thread = TMEM row): 64 channels -> bf16(v) and bf16(0.2 v) images [128 rows][128 B], 16-byte chunks
+    //            XOR-swizzled by (row & 7);
+    //   phase 2 (thread = 16-byte piece of a row; a warp = 4 complete 128-byte row segments): ds = the first image,
+    //            ds_masked = per element the first or second image by the sign of the lrelu output (the same values as
+    //            rounding v * lrelu'(y) from fp32).
     const int quarter = warp & 3;
     const int row = quarter * 32 + lane;
-    const int lx = row & 15, ly = row >> 4;
+    const int te = (warp - 2) * 32 + lane;            // 0..127
+    const int px = te >> 3, piece = te & 7;           // phase 2: x column within the tile, 16-byte piece of the 128-byte segment
+    const uint32_t sTa = smem_u32(sT), sTb = sTa + 128 * 128;
+    const uint32_t w_off = row * 128, sw_w = row & 7;
     int i = 0;
     for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++i) {
       int r = tile;
-      const int x = (r % p.tx) * 16 + lx; r /= p.tx;
-      const int y = (r % p.ty) * 8 + ly; r /= p.ty;
+      const int x = (r % p.tx) * 16 + px; r /= p.tx;
+      const int y0 = (r % p.ty) * 8; r /= p.ty;
       const int z = r % p.D;
       const int b = r / p.D;
-      const bool valid = (x < p.W) && (y < p.H);
-      const size_t pos = ((static_cast<size_t>(b) * p.D + z) * p.H + y) * p.W + x;
+      const size_t pos0 = ((static_cast<size_t>(b) * p.D + z) * p.H + y0) * p.W + x;    // row (ly = 0, lx = px) of the tile
       const uint32_t s = i & 1, ph = (i >> 1) & 1;
-      // the row's 128 mask values are requested BEFORE waiting for the accumulator: one global round trip per tile that
-      // overlaps the MMAs, instead of four dependent ones (load -> multiply -> store per 32-channel chunk) after them
-      uint4 mrow[16];
-      if (p.ds_masked && valid) {
-        const uint4* m = reinterpret_cast<const uint4*>(p.mask_src + pos * 128);
-#pragma unroll
-        for (int q = 0; q < 16; ++q) mrow[q] = __ldg(m + q);
-      }
       mbar_wait(&d1_full[s], ph);
       tc_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + s * 128;
+#pragma unroll 1
+      for (int h = 0; h < 2; ++h) {
+        // mask pieces of this half: requested before the transposition so the round trip overlaps it
+        uint4 mv[8];
+        if (p.ds_masked && x < p.W) {
 #pragma unroll
-      for (int c0 = 0; c0 < 128; c0 += 32) {
-        uint32_t rr[32];
-        tmem_ld_32x32(taddr + c0, rr);
-        tmem_ld_wait();
-        if (!valid) continue;
-        if (p.ds) {
-          uint4* o = reinterpret_cast<uint4*>(p.ds + pos * 128 + c0);
-#pragma unroll
-          for (int q = 0; q < 4; ++q)
-            o[q] = make_uint4(lb_pack(__uint_as_float(rr[q * 8]), __uint_as_float(rr[q * 8 + 1])),
-                              lb_pack(__uint_as_float(rr[q * 8 + 2]), __uint_as_float(rr[q * 8 + 3])),
-                              lb_pack(__uint_as_float(rr[q * 8 + 4]), __uint_as_float(rr[q * 8 + 5])),
-                              lb_pack(__uint_as_float(rr[q * 8 + 6]), __uint_as_float(rr[q * 8 + 7])));
+          for (int it = 0; it < 8; ++it)
+            if (y0 + it < p.H)
+              mv[it] = __ldg(reinterpret_cast<const uint4*>(p.mask_src + (pos0 + static_cast<size_t>(it) * p.W) * 128 + h * 64 + piece * 8));
         }
-        if (p.ds_masked) {
-          uint4* o = reinterpret_cast<uint4*>(p.ds_masked + pos * 128 + c0);
+#pragma unroll
+        for (int cc = 0; cc < 2; ++cc) {
+          uint32_t rr[32];
+          tmem_ld_32x32(taddr + h * 64 + cc * 32, rr);
+          tmem_ld_wait();
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
-            const uint4 mv = mrow[(c0 >> 3) + q];
-            const uint32_t mw[4] = {mv.x, mv.y, mv.z, mv.w};
-            uint32_t ow[4];
+            uint32_t wa[4], wb[4];
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
-              const float a = __uint_as_float(rr[q * 8 + 2 * e]) * lrelu_grad_from_out(__uint_as_float(mw[e] << 16));
-              const float c = __uint_as_float(rr[q * 8 + 2 * e + 1]) * lrelu_grad_from_out(__uint_as_float(mw[e] & 0xFFFF0000u));
-              ow[e] = lb_pack(a, c);
+              const float v0 = __uint_as_float(rr[q * 8 + 2 * e]), v1 = __uint_as_float(rr[q * 8 + 2 * e + 1]);
+              wa[e] = lb_pack(v0, v1);
+              wb[e] = lb_pack(v0 * 0.2f, v1 * 0.2f);
             }
-            o[q] = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+            const uint32_t o = w_off + (((cc * 4 + q) ^ sw_w) << 4);
+            asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(sTa + o), "r"(wa[0]), "r"(wa[1]), "r"(wa[2]), "r"(wa[3]) : "memory");
+            if (p.ds_masked)
+              asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(sTb + o), "r"(wb[0]), "r"(wb[1]), "r"(wb[2]), "r"(wb[3]) : "memory");
           }
         }
+        if (h == 1) {
+          tc_fence_before();
+          mbar_arrive(&d1_empty[s]);               // the tensor core may overwrite this accumulator
+        }
+        asm volatile("bar.sync 2, 128;" ::: "memory");   // images complete
+        if (x < p.W) {
+#pragma unroll
+          for (int it = 0; it < 8; ++it) {         // row r = it * 16 + px of the tile: (ly = it, lx = px)
+            if (y0 + it >= p.H) continue;
+            const int rrow = it * 16 + px;
+            const uint32_t o = rrow * 128 + ((piece ^ (rrow & 7)) << 4);
+            const size_t off = (pos0 + static_cast<size_t>(it) * p.W) * 128 + h * 64 + piece * 8;
+            uint4 va;
+            asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(va.x), "=r"(va.y), "=r"(va.z), "=r"(va.w) : "r"(sTa + o));
+            if (p.ds) *reinterpret_cast<uint4*>(p.ds + off) = va;
+            if (p.ds_masked) {
+              uint4 vb;
+              asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(vb.x), "=r"(vb.y), "=r"(vb.z), "=r"(vb.w) : "r"(sTb + o));
+              const uint32_t mw[4] = {mv[it].x, mv[it].y, mv[it].z, mv[it].w};
+              const uint32_t aw[4] = {va.x, va.y, va.z, va.w}, bw[4] = {vb.x, vb.y, vb.z, vb.w};
+              uint32_t ow[4];
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                // lrelu'(y) = 1 for y >= 0 (incl. -0), else 0.2 (NaN -> 0.2): same rule as lrelu_grad_from_out
+                const bool lo1 = __uint_as_float(mw[e] << 16) >= 0.f, hi1 = __uint_as_float(mw[e] & 0xFFFF0000u) >= 0.f;
+                ow[e] = ((lo1 ? aw[e] : bw[e]) & 0x0000FFFFu) | ((hi1 ? aw[e] : bw[e]) & 0xFFFF0000u);
+              }
+              *reinterpret_cast<uint4*>(p.ds_masked + off) = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+            }
+          }
+        }
+        asm volatile("bar.sync 3, 128;" ::: "memory");   // images may be overwritten
       }
-      tc_fence_before();
-      mbar_arrive(&d1_empty[s]);
     }
     // ---- D2 -> dW (fp32 atomics), lane = ci ----
     if (my_tiles > 0) {
