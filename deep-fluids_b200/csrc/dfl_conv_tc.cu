@@ -238,12 +238,16 @@ conv_tap_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 //   phase = (tile, 64-channel slice);  warps: 0 = brick producer, 1 = MMA issuer (+TMEM alloc), 2 = weight producer,
 //   3..6 = epilogue.
 // =============================================================================================
-constexpr int C2_BSTAGES = 8;
+constexpr int C2_BSTAGES_MAX = 8;
+// 3D: 6 weight stages + the 32 KB transposition image of the epilogue; 2D: 8 stages, row-wise epilogue (its tiles have 3x
+// less MMA time to hide an epilogue behind: the two-phase transposed epilogue measured 20 % slower there)
+__host__ __device__ constexpr int c2_bstages(bool k3D) { return k3D ? 6 : 8; }
 constexpr int C2_SLOT_BYTES_3D = 23552;   // 180 rows * 128 B = 23040, padded to a 1024-byte multiple
 constexpr int C2_SLOT_BYTES_2D = 41984;   // 324 rows * 128 B = 41472, padded
 constexpr int C2_BRICK_BYTES = 4 * C2_SLOT_BYTES_3D;   // 94208 >= 2 * C2_SLOT_BYTES_2D (83968)
 constexpr int C2_THREADS = 224;
-constexpr int C2_SMEM_BYTES = C2_BRICK_BYTES + C2_BSTAGES * CT_B_BYTES + 1024 + 1024;
+constexpr int C2_EPI_BYTES = 128 * 256;             // epilogue transposition image: 128 rows x 64 channels fp32
+constexpr int C2_SMEM_BYTES = C2_BRICK_BYTES + 6 * CT_B_BYTES + C2_EPI_BYTES + 1024 + 1024;   // == brick + 8 stages + 2 KB
 
 // ---- epilogue helpers ------------------------------------------------------------------------------------
 __device__ __forceinline__ void epi_load32(const __nv_bfloat16* ptr, float (&f)[32]) {
@@ -294,6 +298,21 @@ __device__ __forceinline__ void epi_store32(__nv_bfloat16* ptr, const float (&v)
       wl[k] = pack_bf16x2(v[2 * k] - __uint_as_float(w[k] << 16), v[2 * k + 1] - __uint_as_float(w[k] & 0xFFFF0000u));
 #pragma unroll
     for (int q = 0; q < 4; ++q) l[q] = make_uint4(wl[4 * q], wl[4 * q + 1], wl[4 * q + 2], wl[4 * q + 3]);
+  }
+}
+
+// 8 channels (one 16-byte piece) as bf16; split mode: lo = bf16(v - float(hi)) one block further
+__device__ __forceinline__ void epi_store8(__nv_bfloat16* ptr, const float (&v)[8], bool split, size_t blkstride) {
+  uint32_t w[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) w[k] = pack_bf16x2(v[2 * k], v[2 * k + 1]);
+  *reinterpret_cast<uint4*>(ptr) = make_uint4(w[0], w[1], w[2], w[3]);
+  if (split) {
+    uint32_t wl[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+      wl[k] = pack_bf16x2(v[2 * k] - __uint_as_float(w[k] << 16), v[2 * k + 1] - __uint_as_float(w[k] & 0xFFFF0000u));
+    *reinterpret_cast<uint4*>(ptr + blkstride) = make_uint4(wl[0], wl[1], wl[2], wl[3]);
   }
 }
 
@@ -376,6 +395,137 @@ __device__ __forceinline__ void conv_epilogue_row(const ConvTcParams& p, uint32_
   }
 }
 
+// ---- transposed epilogue of the tap-window kernel (kN = 128) ------------------------------------------------
+// Same arithmetic as conv_epilogue_row, different thread mapping.  Written straight from the thread that owns a TMEM row,
+// every 16-byte global access of a warp touches 32 different 128-byte lines (32 half-filled sectors per instruction); that
+// access pattern cost 20 % of the 2D conv time and made the store-heavy launches LSU-bound (store-less timing run:
+// profiles/r01_diag_nostore_c2_bf16.json).  Here a 64-channel chunk of the half tile goes through a shared-memory image:
+//   phase 1 (thread = TMEM row):  v = lrelu(acc + bias) as fp32 -> image [128 rows][256 B], 16-byte chunks XOR-swizzled;
+//   phase 2 (thread = 8 channels of a row; a warp = 4 complete 128-byte row segments): mask / residual pieces (requested
+//            before phase 1), rounding to bf16 (and the lo part in split mode), full-line stores, x2 replication.
+struct EpiGeom { int b, z, y0, x, xi_valid; };
+template <bool k3D>
+__device__ __forceinline__ void conv_epilogue_half_t(const ConvTcParams& p, uint32_t taddr, uint32_t img, int row, int te,
+                                                     int b, int z, int y0, int xbase, const float* s_bias,
+                                                     uint64_t* tempty, bool last_half) {
+  const bool ups = (p.flags & CF_OUT2_UPSAMPLE) != 0;
+  const bool act = (p.flags & CF_LRELU) != 0;
+  const bool mask_after = (p.flags & CF_MASK_AFTER_RESIDUAL) != 0;
+  const bool split = (p.flags & CF_SPLIT_IO) != 0;
+  const size_t vox = static_cast<size_t>(p.oD) * p.oH * p.oW;
+  const size_t blk = static_cast<size_t>(p.B) * vox * CT_BLOCK_N;
+  const int r16 = te >> 3, piece = te & 7;           // phase 2: row = it * 16 + r16  ->  line = 2 it + (r16 >> 3), xi = r16 & 7
+  const int x = xbase + (r16 & 7), lsub = r16 >> 3;
+  const bool xz_ok = (x < p.W) && (z < p.D);
+  const size_t pos0 = ((static_cast<size_t>(b) * p.oD + z) * p.oH + (y0 + lsub)) * p.oW + x;     // row of iteration 0
+  const size_t it_stride = 2 * static_cast<size_t>(p.oW);                                       // two y-lines per iteration
+#pragma unroll 1
+  for (int cq = 0; cq < 2; ++cq) {
+    const int c0 = cq * 64;
+    // ---- operands of phase 2, requested first (one round trip, overlapping phase 1)
+    uint4 mv[8], rv[8];
+    const bool need_m = p.mask_src != nullptr, need_r = p.out2 != nullptr && p.residual != nullptr;
+    if (xz_ok) {
+#pragma unroll
+      for (int it = 0; it < 8; ++it) {
+        if (y0 + lsub + 2 * it < p.H) {
+          const size_t off = (pos0 + it * it_stride) * CT_BLOCK_N + c0 + piece * 8;
+          if (need_m) mv[it] = __ldg(reinterpret_cast<const uint4*>(p.mask_src + off));
+          if (need_r) rv[it] = __ldg(reinterpret_cast<const uint4*>(p.residual + off));
+        }
+      }
+    }
+    // ---- phase 1: this thread's TMEM row, 64 channels
+#pragma unroll
+    for (int cc = 0; cc < 2; ++cc) {
+      uint32_t rr[32];
+      tmem_ld_32x32(taddr + c0 + cc * 32, rr);
+      tmem_ld_wait();
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        float t[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float a = __uint_as_float(rr[q * 4 + e]) + s_bias[c0 + cc * 32 + q * 4 + e];
+          t[e] = act ? lrelu_f(a) : a;
+        }
+        const uint32_t o = row * 256 + (((cc * 8 + q) ^ (row & 15)) << 4);
+        asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(img + o), "f"(t[0]), "f"(t[1]), "f"(t[2]), "f"(t[3]) : "memory");
+      }
+    }
+    if (last_half && cq == 1) {           // every TMEM read of this tile is done: the tensor core may reuse the accumulator
+      tc_fence_before();
+      mbar_arrive(tempty);
+    }
+    asm volatile("bar.sync 1, 128;" ::: "memory");       // image complete
+    // ---- phase 2
+    if (xz_ok) {
+#pragma unroll
+      for (int it = 0; it < 8; ++it) {
+        const int y = y0 + lsub + 2 * it;
+        if (y >= p.H) continue;
+        const int prow = it * 16 + r16;
+        float v[8];
+        {
+          const uint32_t a0 = img + prow * 256 + (((2 * piece) ^ (prow & 15)) << 4);
+          const uint32_t a1 = img + prow * 256 + (((2 * piece + 1) ^ (prow & 15)) << 4);
+          asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]) : "r"(a0));
+          asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7]) : "r"(a1));
+        }
+        const size_t pos = pos0 + it * it_stride;
+        const size_t off = pos * CT_BLOCK_N + c0 + piece * 8;
+        float m[8];
+        if (need_m) {
+          unpack_bf16x8(mv[it], m);
+#pragma unroll
+          for (int k = 0; k < 8; ++k) m[k] = lrelu_grad_from_out(m[k]);
+        }
+        if (p.out) {
+          float o[8];
+#pragma unroll
+          for (int k = 0; k < 8; ++k) o[k] = (need_m && !mask_after) ? v[k] * m[k] : v[k];
+          epi_store8(p.out + off, o, split, blk);
+        }
+        if (p.out2) {
+          if (need_r) {
+            float f[8];
+            unpack_bf16x8(rv[it], f);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) v[k] += f[k];
+            if (split) {
+              unpack_bf16x8(__ldg(reinterpret_cast<const uint4*>(p.residual + blk + off)), f);
+#pragma unroll
+              for (int k = 0; k < 8; ++k) v[k] += f[k];
+            }
+          }
+          if (need_m && mask_after) {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) v[k] *= m[k];
+          }
+          if (!ups) {
+            epi_store8(p.out2 + off, v, split, blk);
+          } else {
+            // nearest-neighbour x2 (ops.py:75-91): out[2i+a] = in[i]; the z axis only when the conv is 3D
+            const int zr = k3D ? 2 : 1;
+            const int D2 = p.oD * zr, H2 = p.oH * 2, W2 = p.oW * 2;
+            const size_t blk2 = blk * (zr * 4);
+#pragma unroll
+            for (int a = 0; a < zr; ++a)
+#pragma unroll
+              for (int e = 0; e < 2; ++e)
+#pragma unroll
+                for (int f = 0; f < 2; ++f) {
+                  const size_t pos2 = ((static_cast<size_t>(b) * D2 + (z * zr + a)) * H2 + (2 * y + e)) * W2 + (2 * x + f);
+                  epi_store8(p.out2 + pos2 * CT_BLOCK_N + c0 + piece * 8, v, split, blk2);
+                }
+          }
+        }
+      }
+    }
+    asm volatile("bar.sync 2, 128;" ::: "memory");       // image may be overwritten
+  }
+}
+
 // kN = 128: the 128->128 layers.  kN = 16: the 128 -> 1..3 output conv (model.py:42,84), weights zero-padded to 16
 // output channels; its epilogue writes fp32 [voxel][p.cout_small] (+ bias) = the network output (potential).
 template <bool k3D, int kN>
@@ -390,12 +540,14 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sB = smem + C2_BRICK_BYTES;
   constexpr int B_BYTES = kN * CT_BLOCK_K * 2;
-  uint8_t* ctrl = sB + C2_BSTAGES * CT_B_BYTES;
+  constexpr int C2_BSTAGES = c2_bstages(k3D);
+  uint8_t* sE = sB + C2_BSTAGES * CT_B_BYTES;             // 3D: epilogue transposition image (epilogue warps only)
+  uint8_t* ctrl = sB + 8 * CT_B_BYTES;
   uint64_t* a_full = reinterpret_cast<uint64_t*>(ctrl);   // [4]
   uint64_t* a_empty = a_full + 4;                         // [4]
   uint64_t* b_full = a_empty + 4;                         // [C2_BSTAGES]
-  uint64_t* b_empty = b_full + C2_BSTAGES;                // [C2_BSTAGES]
-  uint64_t* tfull_bar = b_empty + C2_BSTAGES;             // [2]
+  uint64_t* b_empty = b_full + C2_BSTAGES_MAX;            // [C2_BSTAGES]
+  uint64_t* tfull_bar = b_empty + C2_BSTAGES_MAX;         // [2]
   uint64_t* tempty_bar = tfull_bar + 2;                   // [2]
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tempty_bar + 2);
   float* s_bias = reinterpret_cast<float*>(ctrl + 512);   // [128]
@@ -549,9 +701,9 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       const int z0 = (r % p.tz) * TZ; r /= p.tz;
       const int b = r;
       EpiPre pre;
-      if (kN == CT_BLOCK_N) {       // half 0's first chunk of mask / residual: in flight while the tile's MMAs finish
-        const int z = k3D ? z0 : 0, y = y0 + line, x = x0 + xi;
-        epi_prefetch(p, (x < p.W) && (y < p.H) && (z < p.D), epi_pos(p, b, z, y, x), 0, pre);
+      if (kN == CT_BLOCK_N && !k3D) {   // half 0's first chunk of mask / residual: in flight while the tile's MMAs finish
+        const int y = y0 + line, x = x0 + xi;
+        epi_prefetch(p, (x < p.W) && (y < p.H), epi_pos(p, b, 0, y, x), 0, pre);
       }
       mbar_wait(&tfull_bar[acc], aph);
       tc_fence_after();
@@ -560,11 +712,14 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         const int z = k3D ? z0 + h : 0, y = y0 + line, x = k3D ? x0 + xi : x0 + 8 * h + xi;
         const bool valid = (x < p.W) && (y < p.H) && (z < p.D);
         const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * 256 + h * CT_BLOCK_N;
-        if (kN == CT_BLOCK_N) {
-          // the row of half 1 (same y; z + 1 in 3D, x + 8 in 2D) is the `next` row of half 0
-          const int zn = k3D ? z0 + 1 : 0, xn = k3D ? x0 + xi : x0 + 8 + xi;
-          const bool nvalid = (h == 0) && (xn < p.W) && (y < p.H) && (zn < p.D);
-          conv_epilogue_row(p, taddr, valid, b, z, y, x, s_bias, pre, nvalid, nvalid ? epi_pos(p, b, zn, y, xn) : 0);
+        if (kN == CT_BLOCK_N && k3D) {
+          conv_epilogue_half_t<k3D>(p, taddr, smem_u32(sE), row, (warp - 3) * 32 + lane, b, z, y0, x0, s_bias, &tempty_bar[acc],
+                                    h == 1);
+        } else if (kN == CT_BLOCK_N) {
+          // the row of half 1 (x + 8) is the `next` row of half 0
+          const int xn = x0 + 8 + xi;
+          const bool nvalid = (h == 0) && (xn < p.W) && (y < p.H);
+          conv_epilogue_row(p, taddr, valid, b, z, y, x, s_bias, pre, nvalid, nvalid ? epi_pos(p, b, z, y, xn) : 0);
         } else {
           uint32_t rr[32];
           tmem_ld_32x32(taddr, rr);      // columns >= 16 are never written: ignored
@@ -575,8 +730,10 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           }
         }
       }
-      tc_fence_before();
-      mbar_arrive(&tempty_bar[acc]);
+      if (kN != CT_BLOCK_N || !k3D) {   // (the transposed epilogue releases the accumulator itself, after its last TMEM read)
+        tc_fence_before();
+        mbar_arrive(&tempty_bar[acc]);
+      }
     }
   }
 
