@@ -91,8 +91,15 @@ class Trainer(object):
         else:
             self.build_model()
 
-        if self.load_path and os.path.exists(os.path.join(self.load_path, "model.pt")):
-            self.load(os.path.join(self.load_path, "model.pt"))
+        # tf.train.Supervisor restores the latest checkpoint of the log dir (trainer.py:110-123): a TensorFlow bundle
+        # (`checkpoint` + `model.ckpt-<step>.index/.data-*`, e.g. written by the reference itself) wins over `model.pt`
+        if self.load_path:
+            from . import tf_checkpoint as tfc
+            prefix = tfc.latest_checkpoint(self.load_path)
+            if prefix is not None:
+                self.load_tf(prefix)
+            elif os.path.exists(os.path.join(self.load_path, "model.pt")):
+                self.load(os.path.join(self.load_path, "model.pt"))
 
     # ------------------------------------------------------------------ build (trainer.py:136-184)
     def build_model(self):
@@ -236,6 +243,7 @@ class Trainer(object):
             self.update_lr(step)
         if self.model_dir and self.rank == 0:
             self.save(os.path.join(self.model_dir, 'model.pt'))
+            self.save_tf(self.model_dir)          # saver.save(sess, model_dir/model.ckpt, global_step=step), trainer.py:291-292
         self.batch_manager.stop_thread()
 
     # ------------------------------------------------------------------ auto-encoder (trainer.py:357-462, trainer3.py:240-345)
@@ -323,6 +331,7 @@ class Trainer(object):
             self.update_lr(step)
         if self.model_dir and self.rank == 0:
             self.save(os.path.join(self.model_dir, 'model.pt'))
+            self.save_tf(self.model_dir)          # saver.save(sess, model_dir/model.ckpt, global_step=step), trainer.py:291-292
         self.batch_manager.stop_thread()
 
     # ------------------------------------------------------------------ inference (trainer.py:295-354, 750-771)
@@ -380,6 +389,54 @@ class Trainer(object):
         sd = {"variables": self.engine.params.state_dict(), "step": self.step, "g_lr": self.g_lr,
               "adam_t": self.engine.adam_t, "adam_m": self.engine.params.m.cpu(), "adam_v": self.engine.params.v.cpu()}
         torch.save(sd, path)
+
+    def save_tf(self, model_dir):
+        """`self.saver.save(self.sess, model_dir/model.ckpt, global_step=self.step)` (trainer.py:291-292, :460-461;
+        trainer3.py:178-179, :343-344): a TensorFlow tensor bundle with the reference's variable names and layouts, Adam's
+        slots, `step` and `g_lr` -- readable by tf.train.Saver / tf.train.load_checkpoint.  Returns the prefix."""
+        from . import tf_checkpoint as tfc
+        P = self.engine.params
+        tensors = {k: P.p(k).detach().cpu().numpy() for k in P.table}
+        if self.optimizer == 'adam':
+            tensors.update(tfc.adam_state_to_tf(P.table, {k: P._view(P.m, k).cpu().numpy() for k in P.table},
+                                                {k: P._view(P.v, k).cpu().numpy() for k in P.table},
+                                                self.engine.adam_t, self.beta1, self.beta2))
+        tensors["step"] = np.int32(self.step)
+        tensors["g_lr"] = np.float32(self.g_lr)
+        base = "model.ckpt-%d" % self.step
+        tfc.write_checkpoint(os.path.join(model_dir, base), tensors)
+        tfc.update_checkpoint_state(model_dir, base)
+        return os.path.join(model_dir, base)
+
+    def load_tf(self, prefix):
+        """restore from a TensorFlow checkpoint prefix (`.../model.ckpt-<step>`): variables by name (shapes must match),
+        Adam slots / step / g_lr when present (a checkpoint of weights only leaves the optimizer state fresh)."""
+        from . import tf_checkpoint as tfc
+        P = self.engine.params
+        have = {n: shp for n, shp, _ in tfc.list_variables(prefix)}
+        missing = [k for k in P.table if k not in have]
+        if missing:
+            raise KeyError("checkpoint %s lacks variables %s" % (prefix, missing[:4]))
+        for k in P.table:
+            if tuple(have[k]) != tuple(P.table[k]):
+                raise ValueError("variable %s: checkpoint shape %s, model shape %s" % (k, tuple(have[k]), tuple(P.table[k])))
+        slots = [k + sfx for k in P.table for sfx in ("/Adam", "/Adam_1")]
+        with_adam = all(n in have for n in slots) and "beta1_power" in have
+        extra = [n for n in ("step", "g_lr") if n in have]
+        powers = [n for n in ("beta1_power", "beta2_power") if n in have]
+        t = tfc.read_checkpoint(prefix, list(P.table) + (slots + powers if with_adam else []) + extra)
+        P.load_state_dict({k: torch.from_numpy(t[k]) for k in P.table})
+        if with_adam:
+            for k in P.table:
+                P._view(P.m, k).copy_(torch.from_numpy(t[k + "/Adam"]).view(*P.table[k]))
+                P._view(P.v, k).copy_(torch.from_numpy(t[k + "/Adam_1"]).view(*P.table[k]))
+            self.engine.adam_t = tfc.adam_t_from_tf(float(t["beta1_power"]), self.beta1,
+                                                    float(t["beta2_power"]) if "beta2_power" in t else None, self.beta2)
+        if "step" in t:
+            self.step = int(t["step"])
+        if "g_lr" in t:
+            self.g_lr = float(t["g_lr"])
+        self.engine.repack()
 
     def load(self, path):
         sd = torch.load(path, map_location="cpu")
