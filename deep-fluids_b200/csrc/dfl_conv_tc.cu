@@ -239,15 +239,18 @@ conv_tap_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 //   3..6 = epilogue.
 // =============================================================================================
 constexpr int C2_BSTAGES_MAX = 8;
-// 3D: 6 weight stages + the 32 KB transposition image of the epilogue; 2D: 8 stages, row-wise epilogue (its tiles have 3x
-// less MMA time to hide an epilogue behind: the two-phase transposed epilogue measured 20 % slower there)
-__host__ __device__ constexpr int c2_bstages(bool k3D) { return k3D ? 6 : 8; }
+// kN = 128: one 4 KB transposition image per epilogue warp -- 3D: 4 warps, 7 weight stages; 2D: 8 warps (two per TMEM
+// quarter: a 2D tile has a third of the MMA time, and four warps' dependent tmem -> smem -> global chains did not fit
+// under it), 6 weight stages.  The N = 16 variant has no image and 8 stages.
+__host__ __device__ constexpr int c2_epi_warps(bool k3D, int kN) { return (!k3D && kN == 128) ? 8 : 4; }
+__host__ __device__ constexpr int c2_bstages(bool k3D, int kN) { return kN != 128 ? 8 : (k3D ? 7 : 6); }
+__host__ __device__ constexpr int c2_threads(bool k3D, int kN) { return 96 + 32 * c2_epi_warps(k3D, kN); }
 constexpr int C2_SLOT_BYTES_3D = 23552;   // 180 rows * 128 B = 23040, padded to a 1024-byte multiple
 constexpr int C2_SLOT_BYTES_2D = 41984;   // 324 rows * 128 B = 41472, padded
 constexpr int C2_BRICK_BYTES = 4 * C2_SLOT_BYTES_3D;   // 94208 >= 2 * C2_SLOT_BYTES_2D (83968)
 constexpr int C2_THREADS = 224;
-constexpr int C2_EPI_BYTES = 128 * 256;             // epilogue transposition image: 128 rows x 64 channels fp32
-constexpr int C2_SMEM_BYTES = C2_BRICK_BYTES + 6 * CT_B_BYTES + C2_EPI_BYTES + 1024 + 1024;   // == brick + 8 stages + 2 KB
+constexpr int C2_EPI_BYTES = 4 * 32 * 128;           // epilogue transposition images: per warp 32 rows x 32 channels fp32
+constexpr int C2_SMEM_BYTES = C2_BRICK_BYTES + 8 * CT_B_BYTES + 1024 + 1024;   // 8 stages, or 7 stages + the 16 KB of images
 
 // ---- epilogue helpers ------------------------------------------------------------------------------------
 __device__ __forceinline__ void epi_load32(const __nv_bfloat16* ptr, float (&f)[32]) {
@@ -399,84 +402,99 @@ __device__ __forceinline__ void conv_epilogue_row(const ConvTcParams& p, uint32_
 // Same arithmetic as conv_epilogue_row, different thread mapping.  Written straight from the thread that owns a TMEM row,
 // every 16-byte global access of a warp touches 32 different 128-byte lines (32 half-filled sectors per instruction); that
 // access pattern cost 20 % of the 2D conv time and made the store-heavy launches LSU-bound (store-less timing run:
-// profiles/r01_diag_nostore_c2_bf16.json).  Here a 64-channel chunk of the half tile goes through a shared-memory image:
-//   phase 1 (thread = TMEM row):  v = lrelu(acc + bias) as fp32 -> image [128 rows][256 B], 16-byte chunks XOR-swizzled;
-//   phase 2 (thread = 8 channels of a row; a warp = 4 complete 128-byte row segments): mask / residual pieces (requested
-//            before phase 1), rounding to bf16 (and the lo part in split mode), full-line stores, x2 replication.
-struct EpiGeom { int b, z, y0, x, xi_valid; };
+// profiles/r01_diag_nostore_c2_bf16.json).  Here every epilogue warp transposes its own 32 rows, one 32-channel chunk at a
+// time, through a private 4 KB shared-memory image (no CTA-level barrier, only __syncwarp):
+//   phase 1 (lane = TMEM row):  v = lrelu(acc + bias) as fp32 -> image [32 rows][128 B], 16-byte chunks XOR-swizzled;
+//   phase 2 (lane = 8 channels of a row; 4 lanes = one row's 64-byte chunk = 2 complete sectors, a warp instruction = 8
+//            x-adjacent voxels): mask / residual pieces, rounding to bf16 (and the lo part in split mode), stores, x2
+//            replication.
+// The global operand of phase 2 (the lrelu-mask source, else the residual) is requested one chunk ahead; chunk 0's before
+// the wait for the accumulator.  3D: c3 +4.5 %, c4 +2 % over the row-wise epilogue.  In 2D, whose tiles carry a third of a
+// 3D tile's MMA time, ncu showed the row-wise epilogue bound by the L1 data pipe (LSU wavefronts 73 % of peak in the data-
+// gradient launches: 32 wavefronts per scattered 16-byte request), but with four epilogue warps every transposed variant
+// was SLOWER (2D conv per step: row-wise 2.94 ms; this one 3.28 ms; CTA-wide 64-channel images with two named barriers
+// per chunk 3.57-3.73 ms): the serial tmem -> smem -> global chain of a chunk, eight times per tile, exceeded the tile's
+// MMA time.  The 2D kernel therefore runs EIGHT epilogue warps, two per TMEM quarter, alternating chunks.
+struct EpiChunk { uint4 q[4]; };
 template <bool k3D>
-__device__ __forceinline__ void conv_epilogue_half_t(const ConvTcParams& p, uint32_t taddr, uint32_t img, int row, int te,
-                                                     int b, int z, int y0, int xbase, const float* s_bias,
-                                                     uint64_t* tempty, bool last_half) {
+struct EpiWarpT {
+  const ConvTcParams& p;
+  int b, z0, ybase, x0, xi, piece;
+  bool need_m, need_r;
+  __device__ __forceinline__ EpiWarpT(const ConvTcParams& p_, int lane, int b_, int z0_, int ybase_, int x0_)
+      : p(p_), b(b_), z0(z0_), ybase(ybase_), x0(x0_), xi(lane >> 2), piece(lane & 3) {
+    need_m = p.mask_src != nullptr;
+    need_r = p.out2 != nullptr && p.residual != nullptr;
+  }
+  // chunk i = 4 * half + (32-channel chunk);  phase-2 row of iteration it: line = ybase + it, x = xbase(half) + xi
+  __device__ __forceinline__ int cz(int i) const { return k3D ? z0 + (i >> 2) : 0; }
+  __device__ __forceinline__ int cx(int i) const { return (k3D ? x0 : x0 + 8 * (i >> 2)) + xi; }
+  __device__ __forceinline__ bool ok(int i) const { return cx(i) < p.W && cz(i) < p.D; }
+  __device__ __forceinline__ size_t pos0(int i) const {
+    return ((static_cast<size_t>(b) * p.oD + cz(i)) * p.oH + ybase) * p.oW + cx(i);
+  }
+  __device__ __forceinline__ void prefetch(int i, EpiChunk& e) const {
+    if (!(need_m || need_r) || !ok(i)) return;
+    const __nv_bfloat16* src = need_m ? p.mask_src : p.residual;
+    const size_t base = pos0(i) * CT_BLOCK_N + (i & 3) * 32 + piece * 8, st = static_cast<size_t>(p.oW) * CT_BLOCK_N;
+#pragma unroll
+    for (int it = 0; it < 4; ++it)
+      if (ybase + it < p.H) e.q[it] = __ldg(reinterpret_cast<const uint4*>(src + base + it * st));
+  }
+};
+
+template <bool k3D>
+__device__ __forceinline__ void conv_epilogue_warp_t(const ConvTcParams& p, const EpiWarpT<k3D>& T, uint32_t taddr0,
+                                                     uint32_t wimg, int lane, const float* s_bias, EpiChunk& pre,
+                                                     int first, int step) {
   const bool ups = (p.flags & CF_OUT2_UPSAMPLE) != 0;
   const bool act = (p.flags & CF_LRELU) != 0;
   const bool mask_after = (p.flags & CF_MASK_AFTER_RESIDUAL) != 0;
   const bool split = (p.flags & CF_SPLIT_IO) != 0;
   const size_t vox = static_cast<size_t>(p.oD) * p.oH * p.oW;
   const size_t blk = static_cast<size_t>(p.B) * vox * CT_BLOCK_N;
-  const int r16 = te >> 3, piece = te & 7;           // phase 2: row = it * 16 + r16  ->  line = 2 it + (r16 >> 3), xi = r16 & 7
-  const int x = xbase + (r16 & 7), lsub = r16 >> 3;
-  const bool xz_ok = (x < p.W) && (z < p.D);
-  const size_t pos0 = ((static_cast<size_t>(b) * p.oD + z) * p.oH + (y0 + lsub)) * p.oW + x;     // row of iteration 0
-  const size_t it_stride = 2 * static_cast<size_t>(p.oW);                                       // two y-lines per iteration
+  const bool need_m = T.need_m, need_r = T.need_r;
 #pragma unroll 1
-  for (int cq = 0; cq < 2; ++cq) {
-    const int c0 = cq * 64;
-    // ---- operands of phase 2, requested first (one round trip, overlapping phase 1)
-    uint4 mv[8], rv[8];
-    const bool need_m = p.mask_src != nullptr, need_r = p.out2 != nullptr && p.residual != nullptr;
-    if (xz_ok) {
+  for (int i = first; i < 8; i += step) {       // this warp's chunks (two warps per TMEM quarter split them in 2D)
+    const int c0 = (i & 3) * 32;
+    uint32_t rr[32];
+    tmem_ld_32x32(taddr0 + (i >> 2) * CT_BLOCK_N + c0, rr);
+    const EpiChunk cur = pre;
+    if (i + step < 8) T.prefetch(i + step, pre);   // next chunk's operand: in flight across both phases of this one
+    tmem_ld_wait();
+    // ---- phase 1: this lane's TMEM row, 32 channels
 #pragma unroll
-      for (int it = 0; it < 8; ++it) {
-        if (y0 + lsub + 2 * it < p.H) {
-          const size_t off = (pos0 + it * it_stride) * CT_BLOCK_N + c0 + piece * 8;
-          if (need_m) mv[it] = __ldg(reinterpret_cast<const uint4*>(p.mask_src + off));
-          if (need_r) rv[it] = __ldg(reinterpret_cast<const uint4*>(p.residual + off));
-        }
+    for (int q = 0; q < 8; ++q) {
+      float t[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float a = __uint_as_float(rr[q * 4 + e]) + s_bias[c0 + q * 4 + e];
+        t[e] = act ? lrelu_f(a) : a;
       }
+      const uint32_t o = lane * 128 + ((q ^ (lane & 7)) << 4);
+      asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(wimg + o), "f"(t[0]), "f"(t[1]), "f"(t[2]), "f"(t[3]) : "memory");
     }
-    // ---- phase 1: this thread's TMEM row, 64 channels
-#pragma unroll
-    for (int cc = 0; cc < 2; ++cc) {
-      uint32_t rr[32];
-      tmem_ld_32x32(taddr + c0 + cc * 32, rr);
-      tmem_ld_wait();
-#pragma unroll
-      for (int q = 0; q < 8; ++q) {
-        float t[4];
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const float a = __uint_as_float(rr[q * 4 + e]) + s_bias[c0 + cc * 32 + q * 4 + e];
-          t[e] = act ? lrelu_f(a) : a;
-        }
-        const uint32_t o = row * 256 + (((cc * 8 + q) ^ (row & 15)) << 4);
-        asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(img + o), "f"(t[0]), "f"(t[1]), "f"(t[2]), "f"(t[3]) : "memory");
-      }
-    }
-    if (last_half && cq == 1) {           // every TMEM read of this tile is done: the tensor core may reuse the accumulator
-      tc_fence_before();
-      mbar_arrive(tempty);
-    }
-    asm volatile("bar.sync 1, 128;" ::: "memory");       // image complete
+    __syncwarp();
     // ---- phase 2
-    if (xz_ok) {
+    if (T.ok(i)) {
+      const int z = T.cz(i), x = T.cx(i);
+      const size_t pos0 = T.pos0(i);
 #pragma unroll
-      for (int it = 0; it < 8; ++it) {
-        const int y = y0 + lsub + 2 * it;
+      for (int it = 0; it < 4; ++it) {
+        const int y = T.ybase + it;
         if (y >= p.H) continue;
-        const int prow = it * 16 + r16;
+        const int r = it * 8 + T.xi;
         float v[8];
         {
-          const uint32_t a0 = img + prow * 256 + (((2 * piece) ^ (prow & 15)) << 4);
-          const uint32_t a1 = img + prow * 256 + (((2 * piece + 1) ^ (prow & 15)) << 4);
+          const uint32_t a0 = wimg + r * 128 + (((2 * T.piece) ^ (r & 7)) << 4);
+          const uint32_t a1 = wimg + r * 128 + (((2 * T.piece + 1) ^ (r & 7)) << 4);
           asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]) : "r"(a0));
           asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7]) : "r"(a1));
         }
-        const size_t pos = pos0 + it * it_stride;
-        const size_t off = pos * CT_BLOCK_N + c0 + piece * 8;
+        const size_t off = (pos0 + static_cast<size_t>(it) * p.oW) * CT_BLOCK_N + c0 + T.piece * 8;
         float m[8];
         if (need_m) {
-          unpack_bf16x8(mv[it], m);
+          unpack_bf16x8(cur.q[it], m);
 #pragma unroll
           for (int k = 0; k < 8; ++k) m[k] = lrelu_grad_from_out(m[k]);
         }
@@ -489,7 +507,8 @@ __device__ __forceinline__ void conv_epilogue_half_t(const ConvTcParams& p, uint
         if (p.out2) {
           if (need_r) {
             float f[8];
-            unpack_bf16x8(rv[it], f);
+            // the prefetched operand is the residual unless a mask source is present too (AE: mask after residual)
+            unpack_bf16x8(need_m ? __ldg(reinterpret_cast<const uint4*>(p.residual + off)) : cur.q[it], f);
 #pragma unroll
             for (int k = 0; k < 8; ++k) v[k] += f[k];
             if (split) {
@@ -515,21 +534,21 @@ __device__ __forceinline__ void conv_epilogue_half_t(const ConvTcParams& p, uint
               for (int e = 0; e < 2; ++e)
 #pragma unroll
                 for (int f = 0; f < 2; ++f) {
-                  const size_t pos2 = ((static_cast<size_t>(b) * D2 + (z * zr + a)) * H2 + (2 * y + e)) * W2 + (2 * x + f);
-                  epi_store8(p.out2 + pos2 * CT_BLOCK_N + c0 + piece * 8, v, split, blk2);
+                  const size_t pos2 = ((static_cast<size_t>(T.b) * D2 + (z * zr + a)) * H2 + (2 * y + e)) * W2 + (2 * x + f);
+                  epi_store8(p.out2 + pos2 * CT_BLOCK_N + c0 + T.piece * 8, v, split, blk2);
                 }
           }
         }
       }
     }
-    asm volatile("bar.sync 2, 128;" ::: "memory");       // image may be overwritten
+    __syncwarp();                          // the image may be overwritten
   }
 }
 
 // kN = 128: the 128->128 layers.  kN = 16: the 128 -> 1..3 output conv (model.py:42,84), weights zero-padded to 16
 // output channels; its epilogue writes fp32 [voxel][p.cout_small] (+ bias) = the network output (potential).
 template <bool k3D, int kN>
-__global__ void __launch_bounds__(C2_THREADS, 1)
+__global__ void __launch_bounds__(c2_threads(k3D, kN), 1)
 conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, ConvTcParams p) {
   constexpr int NSLOT = k3D ? 4 : 2;
   constexpr int SLOT_BYTES = k3D ? C2_SLOT_BYTES_3D : C2_SLOT_BYTES_2D;
@@ -540,8 +559,8 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sB = smem + C2_BRICK_BYTES;
   constexpr int B_BYTES = kN * CT_BLOCK_K * 2;
-  constexpr int C2_BSTAGES = c2_bstages(k3D);
-  uint8_t* sE = sB + C2_BSTAGES * CT_B_BYTES;             // 3D: epilogue transposition image (epilogue warps only)
+  constexpr int C2_BSTAGES = c2_bstages(k3D, kN);
+  uint8_t* sE = sB + C2_BSTAGES * CT_B_BYTES;             // 3D, kN = 128: the epilogue warps' transposition images
   uint8_t* ctrl = sB + 8 * CT_B_BYTES;
   uint64_t* a_full = reinterpret_cast<uint64_t*>(ctrl);   // [4]
   uint64_t* a_empty = a_full + 4;                         // [4]
@@ -562,7 +581,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     tma_prefetch_desc(&tmB);
     for (int s = 0; s < 4; ++s) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], 1); }
     for (int s = 0; s < C2_BSTAGES; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 1); }
-    for (int a = 0; a < 2; ++a) { mbar_init(&tfull_bar[a], 1); mbar_init(&tempty_bar[a], 128); }
+    for (int a = 0; a < 2; ++a) { mbar_init(&tfull_bar[a], 1); mbar_init(&tempty_bar[a], 32 * c2_epi_warps(k3D, kN)); }
     fence_barrier_init();
   }
   if (warp == 1) {
@@ -700,27 +719,24 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       const int y0 = (r % p.ty) * TY; r /= p.ty;
       const int z0 = (r % p.tz) * TZ; r /= p.tz;
       const int b = r;
-      EpiPre pre;
-      if (kN == CT_BLOCK_N && !k3D) {   // half 0's first chunk of mask / residual: in flight while the tile's MMAs finish
-        const int y = y0 + line, x = x0 + xi;
-        epi_prefetch(p, (x < p.W) && (y < p.H), epi_pos(p, b, 0, y, x), 0, pre);
-      }
-      mbar_wait(&tfull_bar[acc], aph);
-      tc_fence_after();
+      if (kN == CT_BLOCK_N) {
+        const EpiWarpT<k3D> T(p, lane, b, k3D ? z0 : 0, y0 + quarter * 4, x0);
+        constexpr int NSUB = c2_epi_warps(k3D, kN) / 4;       // warps per TMEM quarter; warp (w - 3) >> 2 takes chunks i % NSUB
+        const int esub = (warp - 3) >> 2;
+        EpiChunk pre;
+        T.prefetch(esub, pre);        // first chunk's mask / residual pieces: in flight while the tile's MMAs finish
+        mbar_wait(&tfull_bar[acc], aph);
+        tc_fence_after();
+        conv_epilogue_warp_t<k3D>(p, T, tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * 256,
+                                  smem_u32(sE) + (warp - 3) * 4096, lane, s_bias, pre, esub, NSUB);
+      } else {
+        mbar_wait(&tfull_bar[acc], aph);
+        tc_fence_after();
 #pragma unroll 1
-      for (int h = 0; h < 2; ++h) {
-        const int z = k3D ? z0 + h : 0, y = y0 + line, x = k3D ? x0 + xi : x0 + 8 * h + xi;
-        const bool valid = (x < p.W) && (y < p.H) && (z < p.D);
-        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * 256 + h * CT_BLOCK_N;
-        if (kN == CT_BLOCK_N && k3D) {
-          conv_epilogue_half_t<k3D>(p, taddr, smem_u32(sE), row, (warp - 3) * 32 + lane, b, z, y0, x0, s_bias, &tempty_bar[acc],
-                                    h == 1);
-        } else if (kN == CT_BLOCK_N) {
-          // the row of half 1 (x + 8) is the `next` row of half 0
-          const int xn = x0 + 8 + xi;
-          const bool nvalid = (h == 0) && (xn < p.W) && (y < p.H);
-          conv_epilogue_row(p, taddr, valid, b, z, y, x, s_bias, pre, nvalid, nvalid ? epi_pos(p, b, z, y, xn) : 0);
-        } else {
+        for (int h = 0; h < 2; ++h) {
+          const int z = k3D ? z0 + h : 0, y = y0 + line, x = k3D ? x0 + xi : x0 + 8 * h + xi;
+          const bool valid = (x < p.W) && (y < p.H) && (z < p.D);
+          const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * 256 + h * CT_BLOCK_N;
           uint32_t rr[32];
           tmem_ld_32x32(taddr, rr);      // columns >= 16 are never written: ignored
           tmem_ld_wait();
@@ -730,10 +746,8 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           }
         }
       }
-      if (kN != CT_BLOCK_N || !k3D) {   // (the transposed epilogue releases the accumulator itself, after its last TMEM read)
-        tc_fence_before();
-        mbar_arrive(&tempty_bar[acc]);
-      }
+      tc_fence_before();
+      mbar_arrive(&tempty_bar[acc]);
     }
   }
 
@@ -836,13 +850,13 @@ int conv_tc_launch(const void* x, const void* w_packed, const float* bias, void*
     attr_set = true;
   }
   if (nd == 3 && !small)
-    conv_tc2_kernel<true, 128><<<grid, C2_THREADS, C2_SMEM_BYTES, st>>>(tmA, tmB, p);
+    conv_tc2_kernel<true, 128><<<grid, c2_threads(true, 128), C2_SMEM_BYTES, st>>>(tmA, tmB, p);
   else if (nd == 3)
-    conv_tc2_kernel<true, 16><<<grid, C2_THREADS, C2_SMEM_BYTES, st>>>(tmA, tmB, p);
+    conv_tc2_kernel<true, 16><<<grid, c2_threads(true, 16), C2_SMEM_BYTES, st>>>(tmA, tmB, p);
   else if (!small)
-    conv_tc2_kernel<false, 128><<<grid, C2_THREADS, C2_SMEM_BYTES, st>>>(tmA, tmB, p);
+    conv_tc2_kernel<false, 128><<<grid, c2_threads(false, 128), C2_SMEM_BYTES, st>>>(tmA, tmB, p);
   else
-    conv_tc2_kernel<false, 16><<<grid, C2_THREADS, C2_SMEM_BYTES, st>>>(tmA, tmB, p);
+    conv_tc2_kernel<false, 16><<<grid, c2_threads(false, 16), C2_SMEM_BYTES, st>>>(tmA, tmB, p);
   DFL_LAUNCH_OK("conv_tc2_kernel");
   return DFL_OK;
 }
