@@ -26,6 +26,7 @@ SIGNATURES = {
     "dfl_fc_fwd": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
     "dfl_fc_bwd": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
     "dfl_pack_conv_weights": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp]),
+    "dfl_pack_conv_weights_multi": (_i, [_vp, _i, _i, _i, _i, _vp]),
     "dfl_conv3x3_fwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _dims, _i, _i, _i, _i, _vp]),
     "dfl_conv3x3_wgrad": (_i, [_vp, _vp, _vp, _vp, _dims, _i, _i, _i, _vp]),
     "dfl_conv3x3_wgrad_split": (_i, [_vp, _vp, _vp, _vp, _dims, _i, _vp]),

@@ -97,6 +97,7 @@ int pool_mask(const void* g, const void* mask_src, void* ds, void* dmasked, cons
               cudaStream_t st);
 int bias_grad(const void* d, float* db, size_t npos, cudaStream_t st);
 int pack_conv_weights(const float* W, void* wf, void* wd, int taps, int cin, int cout, int cin_ld, cudaStream_t st);
+int pack_conv_weights_multi(const void* ptrs, int n_layers, int taps, int cin, int cout, cudaStream_t st);
 int adam_step(float* p, const float* g, float* m, float* v, size_t n, float lr_t, const float* lr_t_dev, float b1,
               float b2, float eps, float grad_scale, cudaStream_t st);
 int cast_f32_bf16(const float* a, void* o, size_t n, cudaStream_t st);
@@ -173,6 +174,9 @@ int dfl_fc_bwd(const float* z, const void* dout, float* dW, float* db, int B, in
 }
 int dfl_pack_conv_weights(const float* w, void* w_fwd, void* w_dgrad, int taps, int cin, int cout, void* stream) {
   return pack_conv_weights(w, w_fwd, w_dgrad, taps, cin, cout, cin, ST(stream));
+}
+int dfl_pack_conv_weights_multi(const void* ptr_table, int n_layers, int taps, int cin, int cout, void* stream) {
+  return pack_conv_weights_multi(ptr_table, n_layers, taps, cin, cout, ST(stream));
 }
 int dfl_pack_conv_weights_ex(const float* w, void* w_fwd, void* w_dgrad, int taps, int cin, int cout, int cin_ld,
                              void* stream) {

@@ -216,6 +216,34 @@ int pack_conv_weights(const float* W, void* wf, void* wd, int taps, int cin, int
   return DFL_OK;
 }
 
+// All 128 -> 128 layers of a generator in ONE launch (blockIdx.y = layer): ptrs = device table [3][n] of
+// {W fp32, wf bf16, wd bf16} addresses.  (20 separate launches of ~8 us each were 4 % of the 2D step.)
+__global__ void pack_conv_weights_multi_kernel(const unsigned long long* __restrict__ ptrs, int n_layers, int taps, int cin,
+                                               int cout) {
+  const int l = blockIdx.y;
+  const float* __restrict__ W = reinterpret_cast<const float*>(ptrs[l]);
+  __nv_bfloat16* __restrict__ wf = reinterpret_cast<__nv_bfloat16*>(ptrs[n_layers + l]);
+  __nv_bfloat16* __restrict__ wd = reinterpret_cast<__nv_bfloat16*>(ptrs[2 * n_layers + l]);
+  const size_t n = static_cast<size_t>(taps) * cin * cout;
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int co = i % cout, ci = (i / cout) % cin, t = i / (static_cast<size_t>(cout) * cin);
+    const __nv_bfloat16 v = __float2bfloat16_rn(W[i]);
+    wf[(static_cast<size_t>(co) * taps + t) * cin + ci] = v;
+    wd[(static_cast<size_t>(ci) * taps + (taps - 1 - t)) * cout + co] = v;
+  }
+}
+
+int pack_conv_weights_multi(const void* ptrs, int n_layers, int taps, int cin, int cout, cudaStream_t st) {
+  DFL_REQUIRE(ptrs && n_layers >= 1 && n_layers <= 65535, "pack_conv_weights_multi: bad layer table");
+  const size_t n = static_cast<size_t>(taps) * cin * cout;
+  const int gx = static_cast<int>(std::min<size_t>((n + 255) / 256, static_cast<size_t>(num_sms()) * 2));
+  pack_conv_weights_multi_kernel<<<dim3(gx, n_layers), 256, 0, st>>>(static_cast<const unsigned long long*>(ptrs), n_layers,
+                                                                    taps, cin, cout);
+  DFL_LAUNCH_OK("pack_conv_weights_multi_kernel");
+  return DFL_OK;
+}
+
 // =============================================================================================
 // adam_step (TF semantics): m = b1 m + (1-b1) g; v = b2 v + (1-b2) g^2; p -= lr_t * m / (sqrt(v) + eps)
 //   lr_t = lr * sqrt(1 - b2^t) / (1 - b1^t) is computed by the host and passed in.  grad_scale folds 1/world.

@@ -161,10 +161,14 @@ class GeneratorEngine(object):
         return self._gbuf[k].view(-1)[:n].view(shp)
 
     def repack(self):
-        """fp32 master weights -> bf16 tensor-core operands (after every optimizer step)."""
-        for row in self.conv_names:
-            for cn in row:
-                K.pack_conv_weights(self.params.p(cn + "/weights"), self.wf[cn], self.wd[cn])
+        """fp32 master weights -> bf16 tensor-core operands (after every optimizer step): one launch for all layers."""
+        if getattr(self, "_pack_table", None) is None:
+            names = [cn for row in self.conv_names for cn in row]
+            tab = [[self.params.p(cn + "/weights").data_ptr() for cn in names], [self.wf[cn].data_ptr() for cn in names],
+                   [self.wd[cn].data_ptr() for cn in names]]
+            self._pack_table = torch.tensor(tab, dtype=torch.int64, device=self.device)
+            self._pack_n = len(names)
+        K.pack_conv_weights_multi(self._pack_table, self._pack_n, self.taps, self.filters, self.filters)
 
     # ------------------------------------------------------------------ forward (model.py:5-46 / :48-87)
     def forward(self, z):

@@ -135,6 +135,12 @@ def pack_conv_weights(w, w_fwd=None, w_dgrad=None):
     return w_fwd, w_dgrad
 
 
+def pack_conv_weights_multi(ptr_table, n_layers, taps, cin, cout):
+    """all same-shape layers in one launch; ptr_table = int64 device tensor [3, n_layers] of {w, w_fwd, w_dgrad} addresses"""
+    PROF.timed("pack_conv_weights", 0.0, lambda: check(cabi.lib().dfl_pack_conv_weights_multi(
+        _p(ptr_table), n_layers, taps, cin, cout, _st())))
+
+
 def conv3x3(x, w_packed, bias=None, out=None, out2=None, residual=None, mask_src=None, flags=0, nblk=1):
     """tcgen05 implicit-GEMM conv; see dfl_conv3x3_fwd in include/deepfluids_b200.h.  `nblk` > 1: x is a channel-blocked
     tensor [nblk*B,(D,)H,W,128] holding nblk*128 input channels."""

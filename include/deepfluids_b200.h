@@ -86,6 +86,9 @@ int dfl_fc_bwd(const float* z, const void* dout, float* dW, float* db, int B, in
 /* ---- 3x3 / 3x3x3 convolution, stride 1, SAME (slim.conv2d / slim.conv3d: ops.py:12-16) ----------------- */
 /* fp32 TF-layout weights [taps][Cin][Cout] (HWIO / DHWIO) -> bf16 GEMM operands for forward and dgrad. */
 int dfl_pack_conv_weights(const float* w, void* w_fwd, void* w_dgrad, int taps, int cin, int cout, void* stream);
+/* The same for n_layers layers of identical shape in one launch: ptr_table = DEVICE array of 3 * n_layers 64-bit addresses,
+ * [0,n) the fp32 weights, [n,2n) the forward operands, [2n,3n) the dgrad operands (re-pack after every optimizer step). */
+int dfl_pack_conv_weights_multi(const void* ptr_table, int n_layers, int taps, int cin, int cout, void* stream);
 /* Implicit-GEMM conv on tcgen05 tensor cores, bf16 in / fp32 accumulate, Cin % 64 == 0, Cout == 128.
  *   v    = conv(x, w_packed) + bias;   if (flags & DFL_CONV_LRELU) v = lrelu(v);
  *   if (mask_src) v *= lrelu'(mask_src)                       (dgrad: derivative of the layer below)
