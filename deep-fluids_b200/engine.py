@@ -13,6 +13,7 @@ Data layout in HBM (all channels-last, ops.py:228):
   * GEMM operands bf16 re-packs of the conv weights (forward: [Cout, taps*Cin]; dgrad: [Cin, taps'*Cout]).
 """
 import math
+import os
 from collections import OrderedDict
 
 import numpy as np
@@ -119,6 +120,17 @@ class GeneratorEngine(object):
         self._alloc_operands()
         self.repack()
         self._alloc()
+        # conv tiles per level (3D 2x16x8, 2D 16x16 voxels): levels with fewer tiles than SMs overlap wgrad with dgrad
+        def _tiles(shape):
+            t = self.B
+            for ext, edge in zip(shape, (2, 16, 8) if self.nd == 3 else (16, 16)):
+                t *= -(-int(ext) // edge)
+            return t
+        self._level_tiles = [_tiles(s) for s in self.level_shape]
+        on_gpu = torch.device(self.device).type == "cuda"
+        self._fork_below = int(os.environ.get("DFL_FORK_BELOW_TILES", torch.cuda.get_device_properties(self.device).multi_processor_count
+                                              if on_gpu else 0))
+        self._side = torch.cuda.Stream(device=self.device) if (not inference and on_gpu and self._fork_below > 0) else None
         self.z = None
         self.adam_t = 0
         self.debug = None
@@ -217,12 +229,24 @@ class GeneratorEngine(object):
                 xin = self.y[i][c - 1] if c > 0 else self.x0[i]
                 if self.debug is not None:        # parity debugging: dL/d(pre-activation) of every layer
                     self.debug[cn] = dpre.clone()
-                K.conv3x3_wgrad(xin, dpre, P.g(cn + "/weights"), P.g(cn + "/biases"))
+                # weight and data gradient of a layer both only READ dpre: on the coarse levels, where the data-gradient
+                # grid leaves SMs idle, the weight gradient runs beside it on a second stream (a fork / join per layer,
+                # captured into the step's CUDA graph as parallel branches)
+                fork = self._side is not None and self._level_tiles[i] < self._fork_below
+                if fork:
+                    cur = torch.cuda.current_stream()
+                    self._side.wait_stream(cur)
+                    with torch.cuda.stream(self._side):
+                        K.conv3x3_wgrad(xin, dpre, P.g(cn + "/weights"), P.g(cn + "/biases"))
+                else:
+                    K.conv3x3_wgrad(xin, dpre, P.g(cn + "/weights"), P.g(cn + "/biases"))
                 if c > 0:     # dL/d(pre-activation of layer c-1) = dgrad * lrelu'(y[c-1])
                     K.conv3x3(dpre, self.wd[cn], None, out=other, mask_src=self.y[i][c - 1])
                     dpre, other = other, dpre
                 else:         # dL/dx0 = dgrad + residual-branch gradient ds
                     K.conv3x3(dpre, self.wd[cn], None, out2=gx0, residual=ds)
+                if fork:
+                    cur.wait_stream(self._side)
             if i > 0:         # x0[i] = upscale(y4[i-1] + x0[i-1]): pool the children, then the lrelu derivative
                 ds = self._gview(0, i - 1)
                 dpre = self._gview(1, i - 1)
