@@ -257,28 +257,46 @@ def run_gpu_arm(args):
     # ---------------- end-to-end arm (`e2e`): host pinned inputs -> H2D -> train_step -> D2H loss ----------------
     xh = [x.cpu().pin_memory() for x, _ in bm._pool]
     yh = [y.cpu().pin_memory() for _, y in bm._pool]
-    # H2D straight into the trainer's static (graph-captured) input buffers when they exist
-    xd = tr._xs if tr._xs is not None else torch.empty_like(bm._pool[0][0])
-    yd = tr._ys if tr._ys is not None else torch.empty_like(bm._pool[0][1])
-    loss_h = torch.empty(3, dtype=torch.float32).pin_memory()
+    # Every step: one H2D copy of a pinned host batch (issued one step ahead on the copy stream, data.HostPrefetcher -- the
+    # role of the reference's loader threads + FIFOQueue), the train step, one D2H read of the loss.  The loss of step i is
+    # read (and checked) right after step i+1 has been enqueued, the way a training loop logs asynchronously; the last
+    # step's loss is read before the timed region closes.
+    from deepfluids_b200.data import HostPrefetcher
+    pf = HostPrefetcher(bm._pool[0][0], bm._pool[0][1], dev)
+    loss_h = [torch.empty(3, dtype=torch.float32).pin_memory() for _ in range(2)]
+    loss_ev = [torch.cuda.Event(), torch.cuda.Event()]
     cnt = [0]
+    pending = [None]
+
+    def read_loss(k):
+        loss_ev[k].synchronize()
+        assert loss_h[k][0] == loss_h[k][0], "NaN loss"
 
     def step_e2e():
-        i = cnt[0] % len(xh)
+        i = cnt[0]
         cnt[0] += 1
-        xd.copy_(xh[i], non_blocking=True)
-        yd.copy_(yh[i], non_blocking=True)
+        xd, yd = pf.get()                                # batch i (its copy was started during step i-1)
+        pf.put(xh[(i + 1) % len(xh)], yh[(i + 1) % len(yh)])   # batch i+1 -> the other slot, under this step's kernels
         l3 = tr.train_step(xd, yd)
+        pf.release()
         tr.update_lr(tr.step)
-        loss_h.copy_(l3, non_blocking=True)
-        torch.cuda.current_stream().synchronize()       # the user reads the loss every step
-        assert loss_h[0] == loss_h[0], "NaN loss"
+        loss_h[i & 1].copy_(l3, non_blocking=True)
+        loss_ev[i & 1].record()
+        if pending[0] is not None:
+            read_loss(pending[0])                        # loss of step i-1
+        pending[0] = i & 1
 
-    for _ in range(max(1, args.warmup // 2)):
-        step_e2e()
-    ms_e = timed_region(step_e2e, args.steps)
+    def e2e_region(steps):
+        for _ in range(steps):
+            step_e2e()
+        read_loss(pending[0])                            # the last step's loss, inside the timed region
+        pending[0] = None
+
+    pf.put(xh[0], yh[0])
+    e2e_region(max(1, args.warmup // 2))
+    ms_e = timed_region(lambda: e2e_region(args.steps), 1)
     e2e_value = B * world / (ms_e / args.steps * 1e-3)
-    h2d = xd.numel() * xd.element_size() + yd.numel() * yd.element_size()
+    h2d = sum(t.numel() * t.element_size() for t in pf.slots[0])
 
     # ---------------- per-kernel timing with CUDA events (2 extra instrumented steps, same stream) ----------------
     K.PROF.events = []

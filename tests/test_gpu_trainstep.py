@@ -197,3 +197,31 @@ def test_main_control_flow_and_errors(tmp_path, monkeypatch):
     cfg4, _ = C.get_config(["--synthetic=true", "--optimizer=foo", "--res_x=24", "--res_y=32", "--batch_size=2"])
     with pytest.raises(Exception, match="Invalid opimizer"):
         main(cfg4)
+
+
+@pytest.mark.gpu
+def test_host_prefetcher_orders_and_overlaps():
+    """data.HostPrefetcher: batches come out in put() order with the right contents, at most two in flight, and a slot is
+    not overwritten before its consumer (enqueued on the compute stream) has run."""
+    from deepfluids_b200.data import HostPrefetcher
+    devc = torch.device("cuda", 0)
+    like_x, like_y = torch.empty(2, 8, 8, 8, 3, device=devc), torch.empty(2, 3, device=devc)
+    pf = HostPrefetcher(like_x, like_y, devc)
+    hx = [torch.full((2, 8, 8, 8, 3), float(i)).pin_memory() for i in range(5)]
+    hy = [torch.full((2, 3), float(-i)).pin_memory() for i in range(5)]
+    sums = []
+    pf.put(hx[0], hy[0])
+    for i in range(5):
+        x, y = pf.get()
+        if i + 1 < 5:
+            pf.put(hx[i + 1], hy[i + 1])
+        big = torch.randn(2048, 2048, device=devc)
+        for _ in range(4):                      # keep the compute stream busy while the next copy is in flight
+            big = big @ big * 1e-3
+        sums.append((x.sum() + 0 * big.sum().nan_to_num(), y.sum()))
+        pf.release()
+    torch.cuda.synchronize()
+    for i, (sx, sy) in enumerate(sums):
+        assert float(sx) == float(i) * 2 * 8 * 8 * 8 * 3 and float(sy) == -float(i) * 6
+    with pytest.raises(AssertionError):
+        pf.get()
