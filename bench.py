@@ -371,6 +371,9 @@ def load_traffic(kernel):
 
 
 def main():
+    # a stuck run (cold-box import, a hung kernel) leaves its Python stacks on stderr instead of a silent timeout
+    import faulthandler
+    faulthandler.dump_traceback_later(170, repeat=True, file=sys.stderr)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)

@@ -163,7 +163,10 @@ __device__ __forceinline__ void umma_commit(uint64_t* bar) {
                : "memory");
 }
 // TMEM -> registers: 32 lanes x 32 columns (fp32), warp w%4 owns lanes 32*(w%4)..+31
+// (.sync.aligned: every lane of the warp must execute it together -- __syncwarp() first, because callers reach it after
+// lane-divergent code such as edge-of-domain predicates, and reconvergence is otherwise only the compiler's choice)
 __device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t (&r)[32]) {
+  __syncwarp();
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
       "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
@@ -175,7 +178,10 @@ __device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t (&r)[32])
       : "r"(taddr)
       : "memory");
 }
-__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_ld_wait() {
+  __syncwarp();
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
 
 // ---- UMMA descriptors (bit layouts: cute/arch/mma_sm100_desc.hpp of CUTLASS, re-derived) ----
 // shared-memory matrix descriptor, 128-byte swizzle.

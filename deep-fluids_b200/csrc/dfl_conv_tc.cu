@@ -26,7 +26,7 @@
 // of a TMA-written image and use any row pitch.  The kernel therefore keeps ONE halo'd activation brick resident in
 // smem per 64-channel slice and reads every (dz,dy,dx) tap as a shifted descriptor window over it (no per-tap
 // reload: A traffic / 9..27), processes 256 voxels per tile as two M=128 halves that share each streamed weight
-// tile (B traffic / 2), and spends the freed smem on an 8-deep weight ring (hides the ~2500-cycle TMA latency that
+// tile (B traffic / 2), and spends the freed smem on a 6..8-deep weight ring (hides the ~2500-cycle TMA latency that
 // bound v1: profiles/r01_ncu_conv_tc_v1_c2_fullres.json).
 #include <stdlib.h>
 
@@ -236,21 +236,22 @@ conv_tap_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 //   3D tile = 2(z) x 16(y) x 8(x) voxels; M-half h = z-plane h; brick = 4 plane slots of 18 x 10 rows (128 B each)
 //   2D tile = 16(y) x 16(x) voxels;        M-half h = x-half h;  brick = 18 x 18 rows, 2 slots ping-pong per phase
 //   phase = (tile, 64-channel slice);  warps: 0 = brick producer, 1 = MMA issuer (+TMEM alloc), 2 = weight producer,
-//   3..6 = epilogue.
+//   3..6 = epilogue (2D, kN = 128: 3..10, two warps per TMEM lane quarter).
 // =============================================================================================
 constexpr int C2_BSTAGES_MAX = 8;
 // kN = 128: one 4 KB transposition image per epilogue warp -- 3D: 4 warps, 7 weight stages; 2D: 8 warps (two per TMEM
 // quarter: a 2D tile has a third of the MMA time, and four warps' dependent tmem -> smem -> global chains did not fit
 // under it), 6 weight stages.  The N = 16 variant has no image and 8 stages.
-__host__ __device__ constexpr int c2_epi_warps(bool k3D, int kN) { return (!k3D && kN == 128) ? 8 : 4; }
-__host__ __device__ constexpr int c2_bstages(bool k3D, int kN) { return kN != 128 ? 8 : (k3D ? 7 : 6); }
+#ifndef DFL_EPI_WARPS_3D
+#define DFL_EPI_WARPS_3D 4
+#endif
+__host__ __device__ constexpr int c2_epi_warps(bool k3D, int kN) { return kN != 128 ? 4 : (k3D ? DFL_EPI_WARPS_3D : 8); }
+__host__ __device__ constexpr int c2_bstages(bool k3D, int kN) { return kN != 128 ? 8 : (c2_epi_warps(k3D, kN) == 4 ? 7 : 6); }
 __host__ __device__ constexpr int c2_threads(bool k3D, int kN) { return 96 + 32 * c2_epi_warps(k3D, kN); }
 constexpr int C2_SLOT_BYTES_3D = 23552;   // 180 rows * 128 B = 23040, padded to a 1024-byte multiple
 constexpr int C2_SLOT_BYTES_2D = 41984;   // 324 rows * 128 B = 41472, padded
 constexpr int C2_BRICK_BYTES = 4 * C2_SLOT_BYTES_3D;   // 94208 >= 2 * C2_SLOT_BYTES_2D (83968)
-constexpr int C2_THREADS = 224;
-constexpr int C2_EPI_BYTES = 4 * 32 * 128;           // epilogue transposition images: per warp 32 rows x 32 channels fp32
-constexpr int C2_SMEM_BYTES = C2_BRICK_BYTES + 8 * CT_B_BYTES + 1024 + 1024;   // 8 stages, or 7 stages + the 16 KB of images
+constexpr int C2_SMEM_BYTES = C2_BRICK_BYTES + 8 * CT_B_BYTES + 1024 + 1024;   // 8 stages, or 7 (6) stages + 16 (32) KB of images
 
 // ---- epilogue helpers ------------------------------------------------------------------------------------
 __device__ __forceinline__ void epi_load32(const __nv_bfloat16* ptr, float (&f)[32]) {
