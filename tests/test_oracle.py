@@ -144,3 +144,28 @@ def test_upsample_then_conv_equals_phase_convs():
         out[2 * i] = xw[i] @ w[1, 0] + xw[i + 1] @ (w[1, 1] + w[1, 2])
         out[2 * i + 1] = xw[i + 1] @ (w[1, 0] + w[1, 1]) + xw[i + 2] @ w[1, 2]
     assert torch.allclose(ref, out, atol=1e-12)
+
+
+def test_conv_matches_scipy_correlate_third_witness():
+    """TF's conv is a cross-correlation with zero 'SAME' padding; for stride 2 on an even extent the padding is 0 before /
+    1 after and outputs sit at even input positions (output o reads inputs 2o .. 2o+2).  Third, library-independent witness:
+    scipy.ndimage.correlate (mode='constant') evaluated per channel pair, then sub-sampled."""
+    from scipy import ndimage
+    g = torch.Generator().manual_seed(7)
+    for nd, shape in ((2, (1, 6, 8)), (3, (1, 4, 6, 4))):
+        cin, cout = 3, 2
+        x = torch.randn(*shape, cin, generator=g, dtype=torch.float64)
+        w = torch.randn(*([3] * nd), cin, cout, generator=g, dtype=torch.float64)
+        b = torch.randn(cout, generator=g, dtype=torch.float64)
+        full = np.zeros(shape + (cout,))
+        for co in range(cout):
+            for ci in range(cin):
+                # correlate centres the kernel: out[p] = sum_t w[t] x[p + t - 1]  == TF SAME for stride 1, k = 3
+                full[0, ..., co] += ndimage.correlate(x[0, ..., ci].numpy(), w[..., ci, co].numpy(), mode="constant", cval=0.0)
+            full[..., co] += float(b[co])
+        y1 = R.conv_nd(x, w, b, 1, None).numpy()
+        np.testing.assert_allclose(y1, full, rtol=1e-12, atol=1e-12)
+        # stride 2, even extents: TF pads (0, 1) -> window of output o starts at input 2o, i.e. it is centred on 2o + 1
+        y2 = R.conv_nd(x, w, b, 2, None).numpy()
+        sub = full[(slice(None),) + (slice(1, None, 2),) * nd]
+        np.testing.assert_allclose(y2, sub, rtol=1e-12, atol=1e-12)
