@@ -225,3 +225,34 @@ def test_host_prefetcher_orders_and_overlaps():
         assert float(sx) == float(i) * 2 * 8 * 8 * 8 * 3 and float(sy) == -float(i) * 6
     with pytest.raises(AssertionError):
         pf.get()
+
+
+@pytest.mark.gpu
+def test_tf_checkpoint_written_by_train_and_restored(tmp_path, monkeypatch):
+    """train_ ends with saver.save(model_dir/model.ckpt, global_step) (trainer.py:291-292): the TensorFlow bundle holds the
+    variables, Adam slots, step and g_lr under the reference's names, and a Trainer built with load_path restores exactly
+    that state (Supervisor semantics, trainer.py:110-123)."""
+    from deepfluids_b200 import config as C, tf_checkpoint as tfc, util
+    from deepfluids_b200.data import BatchManager
+    from deepfluids_b200.main import main
+    from deepfluids_b200.trainer import Trainer
+    monkeypatch.chdir(tmp_path)
+    args = ["--synthetic=true", "--res_x=24", "--res_y=32", "--batch_size=2", "--num_conv=1", "--log_step=1"]
+    cfg, _ = C.get_config(args + ["--max_step=3"])
+    tr = main(cfg)
+    prefix = tfc.latest_checkpoint(cfg.model_dir)
+    assert prefix is not None and prefix.endswith("model.ckpt-3")
+    t = tfc.read_checkpoint(prefix)
+    P = tr.engine.params
+    for k in P.table:
+        np.testing.assert_array_equal(t[k], P.p(k).cpu().numpy())
+        np.testing.assert_array_equal(t[k + "/Adam"], P._view(P.m, k).cpu().numpy())
+        np.testing.assert_array_equal(t[k + "/Adam_1"], P._view(P.v, k).cpu().numpy())
+    assert int(t["step"]) == 3 and t["step"].dtype == np.int32 and abs(float(t["g_lr"]) - tr.g_lr) < 1e-10
+    assert t["G/1_conv/weights"].shape == (3, 3, 128, 128) and t["G/0_fc/weights"].shape[0] == 3     # HWIO / [in, out]
+    os.remove(os.path.join(cfg.model_dir, "model.pt"))                    # only the TensorFlow bundle is left
+    cfg2, _ = C.get_config(args + ["--max_step=5", "--load_path=" + cfg.model_dir])
+    util.prepare_dirs_and_logger(cfg2)
+    tr2 = Trainer(cfg2, BatchManager(cfg2))
+    assert tr2.step == 3 and tr2.engine.adam_t == 3 and abs(tr2.g_lr - tr.g_lr) < 1e-10
+    assert torch.equal(tr2.engine.params.data, P.data) and torch.equal(tr2.engine.params.m, P.m) and torch.equal(tr2.engine.params.v, P.v)
