@@ -324,7 +324,7 @@ def run_gpu_arm(args):
     conv_f /= terms                     # PROF counts executed MMA flops; the roofline numerator is algorithmic flops
     wg_f /= terms
     achieved = conv_f / conv_t / 1e12
-    roofline = {"kernel": "conv_tc_kernel (tcgen05 implicit-GEMM conv, fwd + dgrad launches)", "bound": "tensor",
+    roofline = {"kernel": "conv_tc2_kernel (tcgen05 tap-window implicit-GEMM conv, fwd + dgrad launches)", "bound": "tensor",
                 "achieved": achieved, "peak": peaks["tf_sustained"], "unit": "TFLOP/s",
                 "frac": achieved / peaks["tf_sustained"], "peak_source": "%s (sustained bf16, kernel timed inside a long step)" % peaks["src"],
                 "mma_terms_per_flop": terms, "executed_tflops": achieved * terms,
