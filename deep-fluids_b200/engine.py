@@ -120,17 +120,14 @@ class GeneratorEngine(object):
         self._alloc_operands()
         self.repack()
         self._alloc()
-        # conv tiles per level (3D 2x16x8, 2D 16x16 voxels): levels with fewer tiles than SMs overlap wgrad with dgrad
-        def _tiles(shape):
-            t = self.B
-            for ext, edge in zip(shape, (2, 16, 8) if self.nd == 3 else (16, 16)):
-                t *= -(-int(ext) // edge)
-            return t
-        self._level_tiles = [_tiles(s) for s in self.level_shape]
+        # conv tiles per level (3D 2x16x8, 2D 16x16 voxels): on levels with fewer tiles than SMs the weight gradient runs
+        # beside the data gradient on a second stream (backward()); DFL_FORK_BELOW_TILES overrides the threshold (0 = off)
+        edges = (2, 16, 8) if self.nd == 3 else (16, 16)
+        self._level_tiles = [self.B * int(np.prod([-(-int(ext) // e) for ext, e in zip(shp, edges)])) for shp in self.level_shape]
         on_gpu = torch.device(self.device).type == "cuda"
-        self._fork_below = int(os.environ.get("DFL_FORK_BELOW_TILES", torch.cuda.get_device_properties(self.device).multi_processor_count
-                                              if on_gpu else 0))
-        self._side = torch.cuda.Stream(device=self.device) if (not inference and on_gpu and self._fork_below > 0) else None
+        n_sm = torch.cuda.get_device_properties(self.device).multi_processor_count if on_gpu else 0
+        self._fork_below = int(os.environ.get("DFL_FORK_BELOW_TILES", n_sm))
+        self._side = torch.cuda.Stream(device=self.device) if (on_gpu and not inference and self._fork_below > 0) else None
         self.z = None
         self.adam_t = 0
         self.debug = None
