@@ -1,0 +1,33 @@
+"""TEST INFRASTRUCTURE ONLY.  Writes tests/golden/reference_model_signatures.json IN THE BUILD CONTAINER: the parameter
+names and literal defaults of the reference's model builders (model.py:5,48,118,154,190,204), read from the source with
+`ast` (model.py cannot be imported: TensorFlow 1.15 is not installable).  The fixture travels to the GPU box, where
+/root/reference does not exist.
+
+    python -m oracle.make_signatures
+"""
+import ast
+import json
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+NAMES = ("GeneratorBE", "GeneratorBE3", "EncoderBE", "EncoderBE3", "AE", "AE3")
+
+
+def main(reference_root="/root/reference", out_dir=os.path.join(ROOT, "tests", "golden")):
+    tree = ast.parse(open(os.path.join(reference_root, "model.py")).read())
+    out = {}
+    for node in tree.body:
+        if isinstance(node, ast.FunctionDef) and node.name in NAMES:
+            args = [a.arg for a in node.args.args]
+            defaults = [ast.unparse(d) for d in node.args.defaults]
+            pad = [None] * (len(args) - len(defaults))
+            out[node.name] = {"lineno": node.lineno, "params": [[a, d] for a, d in zip(args, pad + defaults)]}
+    assert set(out) == set(NAMES), sorted(set(NAMES) - set(out))
+    with open(os.path.join(out_dir, "reference_model_signatures.json"), "w") as f:
+        json.dump(out, f, indent=1, sort_keys=True)
+    print("written", os.path.join(out_dir, "reference_model_signatures.json"))
+
+
+if __name__ == "__main__":
+    main()

@@ -27,3 +27,22 @@ def test_unknown_flags_are_tolerated_like_the_reference():
 
 def test_str2bool():
     assert C.str2bool("True") and C.str2bool("1") and not C.str2bool("no")
+
+
+def test_model_builders_keep_the_reference_signatures(golden_dir):
+    """GeneratorBE(3) / EncoderBE(3) / AE(3): same parameter names, order and literal defaults as reference model.py
+    (fixture written by oracle/make_signatures.py from the reference source)."""
+    import inspect
+    from deepfluids_b200 import model as M
+    ref = json.load(open(os.path.join(golden_dir, "reference_model_signatures.json")))
+    for name, spec in ref.items():
+        fn = getattr(M, name)
+        mine = list(inspect.signature(fn).parameters.values())
+        assert [p.name for p in mine] == [a for a, _ in spec["params"]], name
+        for p, (a, d) in zip(mine, spec["params"]):
+            if d is None:
+                assert p.default is inspect.Parameter.empty, (name, a)
+            elif d == "lrelu":
+                assert p.default is M.lrelu, (name, a)
+            else:
+                assert p.default == eval(d), (name, a, p.default, d)    # literals only: 'G', 4, 3, 0, False
