@@ -360,9 +360,12 @@ class Trainer(object):
         return torch.cat(outs)
 
     def test(self):
-        if 'ae' in self.arch:
-            raise NotImplementedError("test_ae is part of the AE row (next)")
-        self.test_()
+        if 'ae' in self.arch:                       # trainer.py:306-312
+            self.test_ae()
+        elif 'nn' in self.arch:
+            self.test_nn()
+        else:
+            self.test_()
 
     def test_(self):
         """Sweep the last parameter at fixed p1,p2 = 10,2, de-normalise and dump `<model_dir>/10_2/%d.npz`
@@ -383,6 +386,32 @@ class Trainer(object):
         for i, G_ in enumerate(G):
             np.savez_compressed(os.path.join(out_dir, '%d.npz' % i), x=G_)
         return out_dir
+
+    # ------------------------------------------------------------------ reference methods outside the hot path
+    # (kept on the class so a call fails with the reason instead of an AttributeError)
+    def _out_of_scope(self, what, where):
+        raise NotImplementedError("%s (%s) is outside the B200 hot path this package replaces" % (what, where))
+
+    def generate(self, inputs, root_path=None, idx=None):
+        self._out_of_scope("generate(): PNG sample grids", "trainer.py:750-771; use generate_velocity(z) for the fields")
+
+    def get_vort_image(self, x):
+        self._out_of_scope("get_vort_image(): vorticity PNG rendering", "trainer.py:773-790")
+
+    def build_test_model_ae(self):
+        self._out_of_scope("build_test_model_ae(): AE test graph", "trainer.py:464-473; use encode() / decode() / autoencode()")
+
+    def test_ae(self):
+        self._out_of_scope("test_ae(): latent-code and image dumps", "trainer.py:475-583")
+
+    def build_model_nn(self):
+        self._out_of_scope("arch='nn' (latent-space integrator)", "trainer.py:586-640, model.py:218-224")
+
+    def train_nn(self):
+        self._out_of_scope("arch='nn' (latent-space integrator)", "trainer.py:642-696")
+
+    def test_nn(self):
+        self._out_of_scope("arch='nn' (latent-space integrator)", "trainer.py:698-747")
 
     # ------------------------------------------------------------------ checkpoint (state_dict with TF variable names)
     def save(self, path):

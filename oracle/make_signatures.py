@@ -1,6 +1,7 @@
 """TEST INFRASTRUCTURE ONLY.  Writes tests/golden/reference_model_signatures.json IN THE BUILD CONTAINER: the parameter
 names and literal defaults of the reference's model builders (model.py:5,48,118,154,190,204), read from the source with
-`ast` (model.py cannot be imported: TensorFlow 1.15 is not installable).  The fixture travels to the GPU box, where
+`ast` (model.py cannot be imported: TensorFlow 1.15 is not installable), and tests/golden/reference_trainer_methods.json: the
+method names of Trainer (trainer.py) and Trainer3 (trainer3.py).  The fixture travels to the GPU box, where
 /root/reference does not exist.
 
     python -m oracle.make_signatures
@@ -27,6 +28,14 @@ def main(reference_root="/root/reference", out_dir=os.path.join(ROOT, "tests", "
     with open(os.path.join(out_dir, "reference_model_signatures.json"), "w") as f:
         json.dump(out, f, indent=1, sort_keys=True)
     print("written", os.path.join(out_dir, "reference_model_signatures.json"))
+    methods = {}
+    for fname, cname in (("trainer.py", "Trainer"), ("trainer3.py", "Trainer3")):
+        t = ast.parse(open(os.path.join(reference_root, fname)).read())
+        cls = [n for n in t.body if isinstance(n, ast.ClassDef) and n.name == cname][0]
+        methods[cname] = [n.name for n in cls.body if isinstance(n, ast.FunctionDef)]
+    with open(os.path.join(out_dir, "reference_trainer_methods.json"), "w") as f:
+        json.dump(methods, f, indent=1, sort_keys=True)
+    print("written", os.path.join(out_dir, "reference_trainer_methods.json"))
 
 
 if __name__ == "__main__":

@@ -46,3 +46,22 @@ def test_model_builders_keep_the_reference_signatures(golden_dir):
                 assert p.default is M.lrelu, (name, a)
             else:
                 assert p.default == eval(d), (name, a, p.default, d)    # literals only: 'G', 4, 3, 0, False
+
+
+def test_trainer_method_surface_matches_reference(golden_dir):
+    """every method of the reference's Trainer / Trainer3 exists on the mirror (hot-path ones implemented, the others raise
+    NotImplementedError naming the reason); names recorded from the reference source by oracle/make_signatures.py"""
+    from deepfluids_b200.trainer import Trainer
+    from deepfluids_b200.trainer3 import Trainer3
+    ref = json.load(open(os.path.join(golden_dir, "reference_trainer_methods.json")))
+    for m in ref["Trainer"]:
+        assert callable(getattr(Trainer, m, None)), "Trainer.%s missing" % m
+    for m in ref["Trainer3"]:
+        assert callable(getattr(Trainer3, m, None)), "Trainer3.%s missing" % m
+    t = Trainer.__new__(Trainer)
+    for m in ("generate", "get_vort_image", "build_test_model_ae", "test_ae", "build_model_nn", "train_nn", "test_nn"):
+        try:
+            getattr(t, m)(*([None] * (1 if m in ("generate", "get_vort_image") else 0)))
+            raise AssertionError("%s should raise" % m)
+        except NotImplementedError as e:
+            assert "outside the B200 hot path" in str(e)
