@@ -387,6 +387,32 @@ class Trainer(object):
             np.savez_compressed(os.path.join(out_dir, '%d.npz' % i), x=G_)
         return out_dir
 
+    # ------------------------------------------------------------------ graph tensors other code pokes (trainer.py:29-32,146,361)
+    # The train step never materialises them (the fused stencil kernel works on residuals); they are evaluated on demand
+    # with the stand-alone kernels from the tensors of the last step.
+    @property
+    def x_jaco(self):
+        """jacobian(self.x)[0] (trainer.py:29-32 / trainer3 via jacobian3)"""
+        return K.jacobian_fwd(self.x.contiguous())[0]
+
+    @property
+    def x_vort(self):
+        return K.jacobian_fwd(self.x.contiguous())[1]
+
+    @property
+    def G_jaco_(self):
+        """jacobian(self.G_)[0] of the last `train_step(want_vel=True)` (trainer.py:146)"""
+        return None if self.G_ is None else K.jacobian_fwd(self.G_.contiguous())[0]
+
+    @property
+    def G_vort_(self):
+        return None if self.G_ is None else K.jacobian_fwd(self.G_.contiguous())[1]
+
+    @property
+    def s(self):
+        """AE: the decoder's stream function / vector potential of the last step (trainer.py:359-361)"""
+        return self.ae.dec.pot if hasattr(self, "ae") else None
+
     # ------------------------------------------------------------------ reference methods outside the hot path
     # (kept on the class so a call fails with the reason instead of an AttributeError; SURVEY.md section 2, rows 6, 11, 12, 18)
     def _out_of_scope(self, what, where):
