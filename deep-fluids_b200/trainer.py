@@ -113,6 +113,7 @@ class Trainer(object):
                                        num_conv=self.num_conv, repeat=self.repeat, name="G", device=self.device,
                                        seed=self.config.random_seed)
         self.G_var = self.engine.variables
+        self.g_optim = self.train_step          # `sess.run(self.g_optim)` == `self.g_optim()` (trainer.py:184,269)
         self.G_s = self.engine.pot
         self._loss3 = torch.zeros(3, dtype=torch.float32, device=self.device)
         self._dpot = torch.empty_like(self.engine.pot)
@@ -258,6 +259,7 @@ class Trainer(object):
                            self.config.random_seed, use_sparse=self.use_sparse)
         self.engine = self.ae                        # checkpoint / DP code paths use `.engine.params`
         self.var = self.ae.variables
+        self.optim = self.train_step_ae         # `sess.run(self.optim)` == `self.optim()` (trainer.py:396,437)
         self._loss3 = torch.zeros(3, dtype=torch.float32, device=self.device)
         self._loss_p = torch.zeros(1, dtype=torch.float32, device=self.device)
         self._dpot = torch.empty_like(self.ae.dec.pot)
@@ -407,6 +409,16 @@ class Trainer(object):
     @property
     def G_vort_(self):
         return None if self.G_ is None else K.jacobian_fwd(self.G_.contiguous())[1]
+
+    @property
+    def z(self):
+        """AE: latent code of the last step (`self.s, self.z, self.var = AE(...)`, trainer.py:359)"""
+        return self.ae.enc.z if hasattr(self, "ae") else None
+
+    @property
+    def x_(self):
+        """AE: reconstructed velocity curl(s) of the last step (trainer.py:361)"""
+        return K.curl_fwd(self.ae.dec.pot) if hasattr(self, "ae") else None
 
     @property
     def s(self):
