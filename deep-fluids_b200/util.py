@@ -7,7 +7,7 @@ from datetime import datetime
 
 
 def prepare_dirs_and_logger(config):
-    # (the reference chdir()s to its own source directory, util.py:18; paths here stay relative to the caller's cwd)
+    # (the reference chdir()s to its own source directory, util.py:19; paths here stay relative to the caller's cwd)
     formatter = logging.Formatter("%(asctime)s:%(levelname)s::%(message)s")
     logger = logging.getLogger()
     for hdlr in list(logger.handlers):
