@@ -14,7 +14,10 @@ Used only by `oracle/make_golden.py` (in the build container, where
 fixtures under `tests/golden/`.  Everything the reference delegates to TF
 *library kernels* (slim.conv2d/conv3d/fully_connected, AdamOptimizer) is NOT
 covered by this shim -- see `oracle/ref_ops.py` for the restatement and the
-"parity unpinned" note there.
+"parity unpinned" note there.  `install_structural` (used by
+`oracle/make_golden_model.py`) additionally lets the reference's `model.py` run
+unchanged with the layers' arithmetic delegated to the restated primitives: it
+pins the model STRUCTURE and variable layout, not the primitives.
 """
 import sys
 import types
@@ -70,6 +73,11 @@ def install():
     if not hasattr(torch.Tensor, "get_shape"):
         torch.Tensor.get_shape = lambda self: _Shape(self.shape)
 
+    nn = types.ModuleType("tensorflow.nn")          # model.py:218 names tf.nn.elu in a default argument (NN arch, unused here)
+    nn.elu = torch.nn.functional.elu
+    tf.nn = nn
+    sys.modules["tensorflow.nn"] = nn
+
     contrib = types.ModuleType("tensorflow.contrib")
     slim = types.ModuleType("tensorflow.contrib.slim")
     contrib.slim = slim
@@ -79,6 +87,104 @@ def install():
     sys.modules["tensorflow.contrib"] = contrib
     sys.modules["tensorflow.contrib.slim"] = slim
     return tf
+
+
+class VariableStore(object):
+    """Variables the reference's model builders ask for, in the order they ask (what tf.get_variable + slim's layer
+    scopes would create).  `values` (name -> tensor) must be pre-filled by the caller; a request for a missing name or a
+    different shape is an error -- that is how the oracle's layout tables get pinned against the reference's own code."""
+
+    def __init__(self, values):
+        self.values = values
+        self.requested = []            # [(name, shape)] in creation order
+        self.scopes = []
+
+    def full(self, leaf):
+        return "/".join(self.scopes + [leaf])
+
+    def get(self, leaf, shape):
+        name = self.full(leaf)
+        if name not in self.values:
+            raise KeyError("the reference asked for variable %r %s which the oracle layout does not have" % (name, tuple(shape)))
+        v = self.values[name]
+        if tuple(v.shape) != tuple(shape):
+            raise ValueError("variable %r: reference shape %s, oracle layout %s" % (name, tuple(shape), tuple(v.shape)))
+        if name not in [n for n, _ in self.requested]:
+            self.requested.append((name, tuple(shape)))
+        return v
+
+
+def install_structural(store, conv_nd, linear):
+    """Extend the shim so that the reference's model.py (GeneratorBE/BE3, EncoderBE/BE3, AE/AE3) runs UNCHANGED:
+    tf.variable_scope, slim.conv2d / conv3d / fully_connected (variable creation order, names `<scope>/weights|biases`,
+    shapes [k,(k,)k,Cin,Cout] / [in,out]) and tf.contrib.framework.get_variables.  The layers' ARITHMETIC is delegated to
+    the oracle's restated primitives `conv_nd` / `linear` (TF's kernels are not available), so this pins the model
+    STRUCTURE -- layer order, residual / concat / upsample wiring, strides, variable naming -- not the primitives."""
+    import contextlib
+
+    tf = install()
+    slim = sys.modules["tensorflow.contrib.slim"]
+
+    class _VS(object):
+        def __init__(self, name):
+            self.name = name
+
+    @contextlib.contextmanager
+    def variable_scope(name, reuse=None):
+        store.scopes.append(name)
+        try:
+            yield _VS("/".join(store.scopes))
+        finally:
+            store.scopes.pop()
+
+    def _conv(nd):
+        def conv(x, o_dim, k, stride=1, activation_fn=None, scope=None, data_format=None):
+            x = _t(x)
+            assert data_format in (None, "NHWC", "NDHWC"), data_format
+            store.scopes.append(scope)
+            try:
+                w = store.get("weights", (k,) * nd + (x.shape[-1], o_dim))
+                b = store.get("biases", (o_dim,))
+            finally:
+                store.scopes.pop()
+            return conv_nd(x, w, b, stride, activation_fn)
+        return conv
+
+    def fully_connected(x, o_dim, activation_fn=None, scope=None):
+        x = _t(x)
+        store.scopes.append(scope)
+        try:
+            w = store.get("weights", (x.shape[-1], o_dim))
+            b = store.get("biases", (o_dim,))
+        finally:
+            store.scopes.pop()
+        y = linear(x, w, b)
+        return activation_fn(y) if activation_fn is not None else y
+
+    slim.conv2d, slim.conv3d, slim.fully_connected = _conv(2), _conv(3), fully_connected
+    tf.variable_scope = variable_scope
+    tf.sigmoid = torch.sigmoid
+    framework = types.ModuleType("tensorflow.contrib.framework")
+    framework.get_variables = lambda vs: [n for n, _ in store.requested if n == vs.name or n.startswith(vs.name + "/")]
+    sys.modules["tensorflow"].contrib.framework = framework
+    sys.modules["tensorflow.contrib.framework"] = framework
+    return tf
+
+
+def import_reference_model(reference_root="/root/reference"):
+    """Import the reference's model.py verbatim (read-only); it does `from ops import *`, so the reference's ops.py is
+    registered under that module name first.  Call install_structural() before using the builders."""
+    import importlib.util
+
+    ops = import_reference_ops(reference_root)
+    sys.modules["ops"] = ops
+    try:
+        spec = importlib.util.spec_from_file_location("_dfl_reference_model", reference_root + "/model.py")
+        mod = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mod)
+    finally:
+        sys.modules.pop("ops", None)
+    return mod
 
 
 def import_reference_ops(reference_root="/root/reference"):

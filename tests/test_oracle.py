@@ -1,6 +1,7 @@
 """CPU tests (run with -m "not gpu"): the oracle against the committed golden vectors produced by the reference's
 own ops.py (oracle/make_golden.py), plus known-answer tests for the parts the reference never tested."""
 import math
+import os
 
 import numpy as np
 import pytest
@@ -169,3 +170,47 @@ def test_conv_matches_scipy_correlate_third_witness():
         y2 = R.conv_nd(x, w, b, 2, None).numpy()
         sub = full[(slice(None),) + (slice(1, None, 2),) * nd]
         np.testing.assert_allclose(y2, sub, rtol=1e-12, atol=1e-12)
+
+
+def test_model_structure_pinned_by_reference_source(golden_dir):
+    """tests/golden/model_structure.npz was produced by running the reference's OWN model.py (GeneratorBE/BE3, EncoderBE/BE3,
+    AE/AE3) under oracle/tf_shim.install_structural (oracle/make_golden_model.py): variable names / shapes / creation order
+    and outputs.  The oracle's restatement must reproduce those outputs bit for bit from the same seeded variables."""
+    from oracle import make_golden_model as G
+    blob = np.load(os.path.join(golden_dir, "model_structure.npz"))
+    for name, (builder, shape, kw) in G.CASES.items():
+        g = torch.Generator().manual_seed(G.SEED + sum(map(ord, name)))
+        B = 2
+        if builder.startswith("Generator"):
+            tab, _, _ = M.generator_layout(shape, G.FILTERS, kw.get("num_conv", 4), kw.get("repeat", 0), z_dim=3, name="G")
+            inp = torch.rand(B, 3, generator=g) * 2 - 1
+        elif builder.startswith("Encoder"):
+            tab, _ = M.encoder_layout(shape, G.FILTERS, G.Z_NUM, kw.get("num_conv", 3), kw.get("repeat", 0), name="enc")
+            inp = torch.randn(B, *shape, generator=g)
+        else:
+            tab = M.ae_layout(shape, G.FILTERS, G.Z_NUM, kw.get("num_conv", 4), kw.get("repeat", 0), name="AE")
+            inp = torch.randn(B, *shape, generator=g)
+        var = M.init_variables(tab, G.SEED)
+        for k in var:
+            if k.endswith("biases"):
+                var[k] = torch.randn(var[k].shape, generator=g) * 0.1
+        np.testing.assert_array_equal(inp.numpy(), blob[name + "/in"])
+        assert list(blob[name + "/variables"]) == list(tab.keys()), name
+        if builder.startswith("Generator"):
+            out = M.generator_forward(inp, var, shape, G.FILTERS, kw.get("num_conv", 4), kw.get("repeat", 0), "G")
+        elif builder.startswith("Encoder"):
+            out = M.encoder_forward(inp, var, G.FILTERS, kw.get("num_conv", 3), kw.get("repeat", 0), "enc")
+        else:
+            out, z = M.ae_forward(inp, var, G.FILTERS, G.Z_NUM, kw.get("num_conv", 4), kw.get("repeat", 0), "AE", kw.get("use_sparse", False))
+            np.testing.assert_array_equal(z.numpy(), blob[name + "/z"])
+        np.testing.assert_array_equal(out.numpy(), blob[name + "/out"])
+
+
+def test_reference_model_source_runs_under_the_shim_when_present():
+    """in the build container (where /root/reference exists) re-run the pinning itself"""
+    if not os.path.exists("/root/reference/model.py"):
+        pytest.skip("reference source not present on this machine")
+    from oracle import make_golden_model as G, tf_shim
+    model = tf_shim.import_reference_model("/root/reference")
+    for name in G.CASES:
+        G.run_case(model, name)          # asserts names / shapes / order / outputs
