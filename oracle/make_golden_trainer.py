@@ -1,0 +1,136 @@
+"""TEST INFRASTRUCTURE ONLY.  Pins the oracle's LOSS / OPTIMIZER WIRING against the reference's own trainers, IN THE BUILD
+CONTAINER.
+
+The reference's `Trainer.build_model`, `Trainer3.build_model`, `Trainer.build_model_ae`, `Trainer3.build_model_ae`
+(trainer.py:136-184, :357-396; trainer3.py:14-63, :240-279) are imported unchanged and run on a stub `self` under the
+structural shim (oracle/tf_shim.py): the generator / AE graph, curl, Jacobians, the loss expression, the optimizer
+construction and the `minimize(loss, global_step, var_list)` call are the reference's code; layer arithmetic is the
+oracle's restated primitives; the build stops at the first placeholder (TensorBoard summaries follow).  Asserted while
+generating:
+  * loss, loss_l1, loss_j_l1 (and loss_p / the KL term for the AE) == oracle/ref_train.py bit for bit,
+  * d loss / d variables through torch autograd of the reference-built expression == the oracle's gradients,
+  * `var_list` == the oracle's variable table (names, order), `global_step` is the trainer's step variable,
+  * the optimizer is AdamOptimizer(g_lr, beta1=, beta2=) with no epsilon argument (TF default 1e-8).
+Writes tests/golden/trainer_wiring.npz (inputs, losses, gradient checksums).
+
+    python -m oracle.make_golden_trainer
+"""
+import os
+import sys
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+sys.path.insert(0, ROOT)
+
+from oracle import tf_shim  # noqa: E402
+from oracle import ref_model as M  # noqa: E402
+from oracle import ref_ops as R  # noqa: E402
+from oracle import ref_train as T  # noqa: E402
+
+FILTERS, Z_NUM, SEED, P_NUM = 8, 6, 20261018, 2
+CASES = {  # name: (is_3d, arch, spatial, num_conv, use_sparse)
+    "de2d": (False, "de", [16, 12], 2, False),
+    "de3d": (True, "de", [16, 16, 8], 2, False),
+    "ae2d": (False, "ae", [16, 12], 3, False),
+    "ae3d": (True, "ae", [16, 16, 8], 2, False),
+    "ae2d_sparse": (False, "ae", [16, 12], 2, True),
+}
+W1, W2, W4, W5, SPARSITY = 0.7, 1.3, 0.9, 0.5, 0.05
+
+
+class _Q(object):
+    def size(self):
+        return 0
+
+
+class _BM(object):
+    q = _Q()
+
+
+def make_inputs(name):
+    is3d, arch, spatial, num_conv, use_sparse = CASES[name]
+    g = torch.Generator().manual_seed(SEED + sum(map(ord, name)))
+    B, C = 2, (3 if is3d else 2)
+    x = torch.randn(B, *spatial, C, generator=g).clamp_(-1, 1)
+    if arch == "de":
+        y = torch.rand(B, 3, generator=g) * 2 - 1
+        tab, _, _ = M.generator_layout(spatial + [3 if is3d else 1], FILTERS, num_conv, 0, z_dim=3, name="G")
+    else:
+        y = torch.rand(B, P_NUM, 4, generator=g) * 2 - 1              # [B, dof, frames]; the loss uses y[:, :, -1]
+        tab = M.ae_layout(spatial + [C], FILTERS, Z_NUM, num_conv, 0, name="AE")
+    var = M.init_variables(tab, SEED)
+    for k in var:
+        if k.endswith("biases"):
+            var[k] = torch.randn(var[k].shape, generator=g) * 0.1
+    return x, y, tab, var
+
+
+def run_case(trainer_mod, trainer3_mod, ref_ops, name):
+    is3d, arch, spatial, num_conv, use_sparse = CASES[name]
+    x, y, tab, var = make_inputs(name)
+    leaves = {k: v.clone().requires_grad_(True) for k, v in var.items()}
+    store = tf_shim.VariableStore(leaves)
+    tf_shim.install_structural(store, R.conv_nd, R.linear)
+    record = {}
+    tf_shim.install_training(record)
+    cls = trainer3_mod.Trainer3 if is3d else trainer_mod.Trainer
+    t = object.__new__(cls)
+    t.batch_manager = _BM()
+    t.x, t.y = x, y
+    t.x_jaco, t.x_vort = (ref_ops.jacobian3 if is3d else ref_ops.jacobian)(x)      # trainer.py:28-32
+    t.arch, t.use_c, t.filters, t.num_conv, t.repeat = arch, True, FILTERS, num_conv, 0
+    t.output_shape = spatial + [3 if is3d else 1]                                  # trainer.py:48-53
+    t.optimizer, t.g_lr, t.beta1, t.beta2, t.step = "adam", "g_lr-variable", 0.5, 0.999, "step-variable"
+    t.w1, t.w2 = W1, W2
+    if arch == "ae":
+        t.z_num, t.use_sparse, t.sparsity, t.w4, t.w5, t.p_num = Z_NUM, use_sparse, SPARSITY, W4, W5, P_NUM
+    try:
+        (cls.build_model if arch == "de" else cls.build_model_ae)(t)
+        raise AssertionError("the build did not reach its first placeholder")
+    except tf_shim.BuildDone:
+        pass
+    opt, mini = record["optimizer"], record["minimize"]
+    assert opt["kind"] == "adam" and opt["args"] == ("g_lr-variable",) and opt["kwargs"] == {"beta1": 0.5, "beta2": 0.999}, opt
+    assert mini["global_step"] == "step-variable" and mini["var_list"] == list(tab.keys()), name
+    loss = mini["loss"]
+    grads = torch.autograd.grad(loss, [leaves[k] for k in tab])
+    out = {"x": x.numpy(), "y": y.numpy()}
+    if arch == "de":
+        o_loss, o_l1, o_jl1, _, _, o_grads = T.generator_loss_and_grads(y, x, var, FILTERS, num_conv, 0, W1, W2, True, "G")
+        assert loss is t.g_loss
+        assert torch.equal(t.g_loss.detach(), o_loss) and torch.equal(t.g_loss_l1.detach(), o_l1) and torch.equal(t.g_loss_j_l1.detach(), o_jl1), name
+        out.update(loss=o_loss.numpy(), l1=o_l1.numpy(), jl1=o_jl1.numpy())
+    else:
+        o_loss, o_l1, o_jl1, o_lp, _, o_z, o_grads = T.ae_loss_and_grads(x, y[:, :, -1], var, P_NUM, FILTERS, Z_NUM, num_conv, 0, W1, W2, W4, True,
+                                                                         "AE", use_sparse, SPARSITY, W5)
+        assert loss is t.loss
+        assert torch.equal(t.loss_l1.detach(), o_l1) and torch.equal(t.loss_j_l1.detach(), o_jl1) and torch.equal(t.loss_p.detach(), o_lp), name
+        assert torch.allclose(t.loss.detach(), o_loss, rtol=1e-6, atol=0), (name, float(t.loss), float(o_loss))
+        assert torch.equal(t.z.detach(), o_z), name
+        out.update(loss=o_loss.numpy(), l1=o_l1.numpy(), jl1=o_jl1.numpy(), loss_p=o_lp.numpy())
+    # relative to the largest gradient entry of the model: the output conv's bias gradient is mathematically zero (the curl
+    # of a constant vanishes), so a per-variable relative measure would compare rounding noise with rounding noise
+    scale = max(float(o_grads[k].abs().max()) for k in tab)
+    worst = max(float((g - o_grads[k]).abs().max()) for k, g in zip(tab, grads)) / scale
+    assert worst <= 1e-5, (name, worst)
+    out["grad_abs_sums"] = np.array([float(o_grads[k].abs().sum()) for k in tab])
+    return out, worst
+
+
+def main(reference_root="/root/reference", out_dir=os.path.join(ROOT, "tests", "golden")):
+    trainer_mod, trainer3_mod, ref_ops = tf_shim.import_reference_trainers(reference_root)
+    blob = {}
+    for name in CASES:
+        out, worst = run_case(trainer_mod, trainer3_mod, ref_ops, name)
+        for k, v in out.items():
+            blob[name + "/" + k] = v
+        print("%-12s loss %.6f: reference wiring == oracle (max relative gradient difference %.1e)" % (name, float(out["loss"]), worst))
+    np.savez_compressed(os.path.join(out_dir, "trainer_wiring.npz"), **blob)
+    print("written", os.path.join(out_dir, "trainer_wiring.npz"))
+
+
+if __name__ == "__main__":
+    main()

@@ -171,6 +171,95 @@ def install_structural(store, conv_nd, linear):
     return tf
 
 
+class BuildDone(Exception):
+    """raised by the shim's tf.placeholder: in the reference's build_model / build_model_ae the first placeholder
+    (`self.epoch`) is created right AFTER the losses and the optimizer op -- everything that follows is TensorBoard
+    summaries (out of scope), so the build is stopped there."""
+
+
+def install_training(record):
+    """Shim surface for the loss / optimizer wiring of the reference's trainers (trainer.py:160-184,372-396;
+    trainer3.py:39-63,255-279): tf.train.AdamOptimizer / GradientDescentOptimizer record their constructor arguments and
+    `minimize(loss, global_step, var_list)` records what is minimised over which variables; tf.placeholder stops the build
+    (see BuildDone).  `record` is a dict that receives 'optimizer', 'minimize'."""
+    tf = sys.modules["tensorflow"]
+
+    class _Opt(object):
+        kind = None
+
+        def __init__(self, *args, **kwargs):
+            record["optimizer"] = {"kind": self.kind, "args": args, "kwargs": kwargs}
+
+        def minimize(self, loss, global_step=None, var_list=None):
+            record["minimize"] = {"loss": loss, "global_step": global_step, "var_list": list(var_list)}
+            return "optim-op"
+
+    train = types.ModuleType("tensorflow.train")
+    train.AdamOptimizer = type("AdamOptimizer", (_Opt,), {"kind": "adam"})
+    train.GradientDescentOptimizer = type("GradientDescentOptimizer", (_Opt,), {"kind": "gd"})
+    tf.train = train
+    sys.modules["tensorflow.train"] = train
+
+    def placeholder(*a, **k):
+        raise BuildDone()
+
+    tf.placeholder = placeholder
+    tf.square = lambda x: _t(x) ** 2
+    tf.sqrt = lambda x: torch.sqrt(_t(x))
+    tf.squared_difference = lambda a, b: (_t(a) - _t(b)) ** 2
+    tf.reduce_sum = lambda x, axis=None: torch.sum(x) if axis is None else torch.sum(x, dim=axis)
+
+    # tf.distributions.Bernoulli / kl_divergence (use_sparse, trainer.py:389-394): published closed form
+    #   KL(Bern(p) || Bern(q)) = p log(p/q) + (1-p) log((1-p)/(1-q))      -- a restatement, like the layer primitives
+    ds = types.ModuleType("tensorflow.distributions")
+
+    class Bernoulli(object):
+        def __init__(self, probs):
+            self.probs = torch.as_tensor(probs, dtype=torch.float32)
+
+    def kl_divergence(a, b):
+        p, q = a.probs, b.probs
+        return p * (p.log() - q.log()) + (1 - p) * ((1 - p).log() - (1 - q).log())
+
+    ds.Bernoulli, ds.kl_divergence = Bernoulli, kl_divergence
+    tf.distributions = ds
+    sys.modules["tensorflow.distributions"] = ds
+    return tf
+
+
+def import_reference_trainers(reference_root="/root/reference"):
+    """Import the reference's trainer.py and trainer3.py verbatim.  `util` (matplotlib / PIL plotting helpers, not
+    installable here and never used by build_model) is replaced by an empty module for the import; the visualisation /
+    debug helpers the build functions call on the way (`denorm_img`, `denorm_img3`, `show_all_variables`) are replaced by
+    no-ops in the imported modules' namespaces -- nothing that enters a loss."""
+    import importlib.util
+
+    model = import_reference_model(reference_root)
+    ops = import_reference_ops(reference_root)
+    saved = {k: sys.modules.get(k) for k in ("ops", "model", "util", "trainer")}
+    sys.modules["ops"], sys.modules["model"], sys.modules["util"] = ops, model, types.ModuleType("util")
+    mods = {}
+    try:
+        for fname, key in (("trainer.py", "trainer"), ("trainer3.py", "trainer3")):
+            spec = importlib.util.spec_from_file_location("_dfl_reference_" + key, reference_root + "/" + fname)
+            mod = importlib.util.module_from_spec(spec)
+            spec.loader.exec_module(mod)
+            mods[key] = mod
+            if key == "trainer":
+                sys.modules["trainer"] = mod
+    finally:
+        for k, v in saved.items():
+            if v is None:
+                sys.modules.pop(k, None)
+            else:
+                sys.modules[k] = v
+    for mod in mods.values():
+        mod.denorm_img = lambda *a, **k: None
+        mod.denorm_img3 = lambda *a, **k: None
+        mod.show_all_variables = lambda: None
+    return mods["trainer"], mods["trainer3"], ops
+
+
 def import_reference_model(reference_root="/root/reference"):
     """Import the reference's model.py verbatim (read-only); it does `from ops import *`, so the reference's ops.py is
     registered under that module name first.  Call install_structural() before using the builders."""

@@ -202,8 +202,10 @@ def test_model_structure_pinned_by_reference_source(golden_dir):
             out = M.encoder_forward(inp, var, G.FILTERS, kw.get("num_conv", 3), kw.get("repeat", 0), "enc")
         else:
             out, z = M.ae_forward(inp, var, G.FILTERS, G.Z_NUM, kw.get("num_conv", 4), kw.get("repeat", 0), "AE", kw.get("use_sparse", False))
-            np.testing.assert_array_equal(z.numpy(), blob[name + "/z"])
-        np.testing.assert_array_equal(out.numpy(), blob[name + "/out"])
+            np.testing.assert_allclose(z.numpy(), blob[name + "/z"], rtol=1e-5, atol=1e-6)
+        # (bit-equality is asserted where both sides run in one process -- the generating script and the test below; against
+        # the stored fixture a different CPU / oneDNN kernel choice may round differently)
+        np.testing.assert_allclose(out.numpy(), blob[name + "/out"], rtol=1e-5, atol=1e-6)
 
 
 def test_reference_model_source_runs_under_the_shim_when_present():
@@ -214,3 +216,36 @@ def test_reference_model_source_runs_under_the_shim_when_present():
     model = tf_shim.import_reference_model("/root/reference")
     for name in G.CASES:
         G.run_case(model, name)          # asserts names / shapes / order / outputs
+
+
+def test_trainer_wiring_pinned_by_reference_source(golden_dir):
+    """tests/golden/trainer_wiring.npz was produced by running the reference's OWN build_model / build_model_ae (Trainer and
+    Trainer3) under the shim (oracle/make_golden_trainer.py).  The oracle's loss functions must reproduce the recorded
+    losses bit for bit and the recorded gradient checksums from the same seeded inputs."""
+    from oracle import make_golden_trainer as G
+    # (bit-equality of the losses is asserted by the generating script and by the test below, where the reference-built
+    # expression and the oracle run in one process; against the stored fixture: fp32 tolerance)
+    blob = np.load(os.path.join(golden_dir, "trainer_wiring.npz"))
+    for name, (is3d, arch, spatial, num_conv, use_sparse) in G.CASES.items():
+        x, y, tab, var = G.make_inputs(name)
+        np.testing.assert_array_equal(x.numpy(), blob[name + "/x"])
+        np.testing.assert_array_equal(y.numpy(), blob[name + "/y"])
+        if arch == "de":
+            loss, l1, jl1, _, _, grads = T.generator_loss_and_grads(y, x, var, G.FILTERS, num_conv, 0, G.W1, G.W2, True, "G")
+        else:
+            loss, l1, jl1, lp, _, _, grads = T.ae_loss_and_grads(x, y[:, :, -1], var, G.P_NUM, G.FILTERS, G.Z_NUM, num_conv, 0, G.W1,
+                                                                 G.W2, G.W4, True, "AE", use_sparse, G.SPARSITY, G.W5)
+            np.testing.assert_allclose(lp.numpy(), blob[name + "/loss_p"], rtol=1e-5)
+        np.testing.assert_allclose(loss.numpy(), blob[name + "/loss"], rtol=1e-5)
+        np.testing.assert_allclose(l1.numpy(), blob[name + "/l1"], rtol=1e-5)
+        np.testing.assert_allclose(jl1.numpy(), blob[name + "/jl1"], rtol=1e-5)
+        np.testing.assert_allclose([float(grads[k].abs().sum()) for k in tab], blob[name + "/grad_abs_sums"], rtol=1e-4, atol=1e-7)
+
+
+def test_reference_trainer_source_runs_under_the_shim_when_present():
+    if not os.path.exists("/root/reference/trainer.py"):
+        pytest.skip("reference source not present on this machine")
+    from oracle import make_golden_trainer as G, tf_shim
+    tm, t3, ops = tf_shim.import_reference_trainers("/root/reference")
+    for name in G.CASES:
+        G.run_case(tm, t3, ops, name)      # asserts losses, gradients, var_list, optimizer arguments
