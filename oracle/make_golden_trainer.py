@@ -120,6 +120,79 @@ def run_case(trainer_mod, trainer3_mod, ref_ops, name):
     return out, worst
 
 
+def run_init_case(trainer_mod, trainer3_mod, is3d, lr_update, start_step):
+    """Run the reference's Trainer.__init__ itself (trainer.py:13-105) on a stub config / batch manager: input wiring,
+    target Jacobian, output_shape rule, max_step, the learning-rate variable and its update expression; __init__ then
+    enters build_model, which the shim stops at its first placeholder.  Returns the half-constructed trainer + record."""
+    import argparse
+    spatial = [16, 16, 8] if is3d else [16, 12]
+    g = torch.Generator().manual_seed(SEED + start_step)
+    B, C = 2, (3 if is3d else 2)
+    x = torch.randn(B, *spatial, C, generator=g).clamp_(-1, 1)
+    y = torch.rand(B, 3, generator=g) * 2 - 1
+    tab, _, _ = M.generator_layout(spatial + [3 if is3d else 1], FILTERS, 2, 0, z_dim=3, name="G")
+    leaves = {k: v.clone().requires_grad_(True) for k, v in M.init_variables(tab, SEED).items()}
+    store = tf_shim.VariableStore(leaves)
+    tf_shim.install_structural(store, R.conv_nd, R.linear)
+    record = {}
+    tf_shim.install_training(record)
+
+    class BM(_BM):
+        c_num, dof = 3, 0
+        epochs_per_step = 8.0 / 21000.0                       # batch_size / num_samples (data.py:52)
+
+        def batch(self):
+            return x, y
+
+    cfg = argparse.Namespace(is_3d=is3d, dataset="smoke", data_type="velocity", arch="de", res_x=spatial[-1], res_y=spatial[-2],
+                             res_z=spatial[0] if is3d else 0, batch_size=B, test_batch_size=100, repeat=0, filters=FILTERS, num_conv=2,
+                             w1=W1, w2=W2, use_curl=True, optimizer="adam", beta1=0.5, beta2=0.999, model_dir="unused", load_path="",
+                             start_step=start_step, max_epoch=100, lr_update=lr_update, lr_min=2.5e-6, lr_max=1e-4, lr_update_step=120000,
+                             log_step=500, test_step=1000, save_sec=3600, is_train=True)
+    cls = trainer3_mod.Trainer3 if is3d else trainer_mod.Trainer
+    t = object.__new__(cls)
+    try:
+        cls.__init__(t, cfg, BM())
+        raise AssertionError("__init__ did not reach the first placeholder of build_model")
+    except tf_shim.BuildDone:
+        pass
+    return t, record, x, cfg
+
+
+def check_init(trainer_mod, trainer3_mod, ref_ops):
+    """learning-rate schedules (trainer.py:69-80) and the input wiring of __init__ vs the oracle"""
+    out = {}
+    for is3d in (False, True):
+        max_step = int(100 // (8.0 / 21000.0))                 # = 262499: float floor division, as the reference evaluates it
+        steps = (0, 1, 7, 1000, max_step // 2, max_step)
+        vals = []
+        for s in steps:
+            t, rec, x, cfg = run_init_case(trainer_mod, trainer3_mod, is3d, "decay", s)
+            assert t.max_step == max_step == 262499
+            assert t.output_shape == list(x.shape[1:-1]) + [3 if is3d else 1]                     # trainer.py:48-53
+            ref_j, ref_w = (ref_ops.jacobian3 if is3d else ref_ops.jacobian)(x)
+            assert torch.equal(t.x_jaco, ref_j) and torch.equal(t.x_vort, ref_w) and t.c_num == 3
+            a = [r for r in rec["assign"] if r["name"] == "g_lr_update"]
+            assert len(a) == 1 and a[0]["ref"] is t.g_lr and float(t.g_lr.value) == float(torch.tensor(cfg.lr_max, dtype=torch.float32))
+            assert rec["optimizer"]["args"] == (t.g_lr,) and rec["minimize"]["global_step"] is t.step
+            v = float(a[0]["value"])
+            want = T.lr_decay(s, t.max_step, cfg.lr_max, cfg.lr_min)
+            assert abs(v - want) <= 2e-7 * cfg.lr_max, (s, v, want)                                 # fp32 vs double evaluation
+            vals.append(v)
+        assert vals[0] == float(torch.tensor(1e-4, dtype=torch.float32)) and abs(vals[-1] - 2.5e-6) < 1e-11    # lr_max at step 0, lr_min at max_step
+        out["lr_decay_3d" if is3d else "lr_decay_2d"] = np.array(vals)
+        t, rec, x, cfg = run_init_case(trainer_mod, trainer3_mod, is3d, "step", 0)
+        a = [r for r in rec["assign"] if r["name"] == "g_lr_update"]
+        assert abs(float(a[0]["value"]) - T.lr_step(cfg.lr_max, cfg.lr_min)) <= 1e-11
+    out["lr_steps"] = np.array(steps)
+    try:
+        run_init_case(trainer_mod, trainer3_mod, False, "bogus", 0)
+        raise AssertionError("invalid lr_update accepted")
+    except Exception as e:                                                                        # trainer.py:80
+        assert "Invalid lr update method" in str(e)
+    return out
+
+
 def main(reference_root="/root/reference", out_dir=os.path.join(ROOT, "tests", "golden")):
     trainer_mod, trainer3_mod, ref_ops = tf_shim.import_reference_trainers(reference_root)
     blob = {}
@@ -128,6 +201,9 @@ def main(reference_root="/root/reference", out_dir=os.path.join(ROOT, "tests", "
         for k, v in out.items():
             blob[name + "/" + k] = v
         print("%-12s loss %.6f: reference wiring == oracle (max relative gradient difference %.1e)" % (name, float(out["loss"]), worst))
+    for k, v in check_init(trainer_mod, trainer3_mod, ref_ops).items():
+        blob["init/" + k] = v
+    print("Trainer.__init__ / Trainer3.__init__: input wiring, output_shape, max_step, cosine and step LR schedules == oracle")
     np.savez_compressed(os.path.join(out_dir, "trainer_wiring.npz"), **blob)
     print("written", os.path.join(out_dir, "trainer_wiring.npz"))
 

@@ -203,6 +203,27 @@ def install_training(record):
     def placeholder(*a, **k):
         raise BuildDone()
 
+    class Variable(object):
+        """tf.Variable used by Trainer.__init__ for `step` and `g_lr` (trainer.py:64,72,76): a named value holder that
+        takes part in arithmetic as a tensor of TF's inferred dtype (python int -> int32, python float -> float32)."""
+
+        def __init__(self, initial_value, name=None, trainable=True):
+            self.name, self.trainable = name, trainable
+            self.value = torch.tensor(initial_value, dtype=torch.int32 if isinstance(initial_value, int) else torch.float32)
+
+        def __mul__(self, other):
+            return self.value * other
+
+        __rmul__ = __mul__
+
+    def assign(ref, value, name=None):
+        record.setdefault("assign", []).append({"ref": ref, "value": value, "name": name})
+        return "assign-op:%s" % name
+
+    tf.Variable, tf.assign = Variable, assign
+    tf.cast = lambda x, dtype: (x.value if isinstance(x, Variable) else _t(x)).to(dtype)
+    tf.cos = lambda x: torch.cos(_t(x))
+
     tf.placeholder = placeholder
     tf.square = lambda x: _t(x) ** 2
     tf.sqrt = lambda x: torch.sqrt(_t(x))

@@ -249,3 +249,26 @@ def test_reference_trainer_source_runs_under_the_shim_when_present():
     tm, t3, ops = tf_shim.import_reference_trainers("/root/reference")
     for name in G.CASES:
         G.run_case(tm, t3, ops, name)      # asserts losses, gradients, var_list, optimizer arguments
+
+
+def test_lr_schedule_pinned_by_reference_init(golden_dir):
+    """`init/lr_decay_*` in trainer_wiring.npz are the values of the reference's own `g_lr_update` expression (built by
+    Trainer.__init__ / Trainer3.__init__, trainer.py:69-75, evaluated in fp32 at the recorded global steps).  The oracle's
+    lr_decay and the product mirror's Trainer.update_lr (pure host code) must give the same schedule."""
+    from deepfluids_b200.trainer import Trainer
+    blob = np.load(os.path.join(golden_dir, "trainer_wiring.npz"))
+    steps = [int(s) for s in blob["init/lr_steps"]]
+    max_step = steps[-1]
+    for key in ("init/lr_decay_2d", "init/lr_decay_3d"):
+        for s, v in zip(steps, blob[key]):
+            assert abs(T.lr_decay(s, max_step, 1e-4, 2.5e-6) - float(v)) <= 2e-7 * 1e-4
+            tr = Trainer.__new__(Trainer)
+            tr.lr_update, tr.lr_min, tr.lr_max, tr.max_step, tr.step, tr.g_lr = "decay", 2.5e-6, 1e-4, max_step, s, 1e-4
+            tr.update_lr(s - 1)
+            assert abs(tr.g_lr - float(v)) <= 2e-7 * 1e-4, (s, tr.g_lr, float(v))
+    tr = Trainer.__new__(Trainer)
+    tr.lr_update, tr.lr_min, tr.lr_max, tr.lr_update_step, tr.g_lr, tr.step = "step", 2.5e-6, 1e-4, 10, 1e-4, 10
+    tr.update_lr(8)
+    assert tr.g_lr == 1e-4            # trainer.py:284-286: only when step % lr_update_step == lr_update_step - 1
+    tr.update_lr(9)
+    assert tr.g_lr == 5e-5
