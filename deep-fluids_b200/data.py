@@ -139,15 +139,17 @@ def preprocess(file_path, data_type, x_range, y_range):
     y[i] -> [-1, 1] by its [min, max]."""
     import numpy as np
     with np.load(file_path) as data:
-        x = data['x'].astype(np.float32)
-        y = np.array(data['y'], dtype=np.float32)
+        x = data['x']
+        y = np.array(data['y'], dtype=np.float64)
+    # The reference divides the fp32 field in place by the float64 range read with np.loadtxt (`x /= x_range`): numpy
+    # evaluates that in double and rounds once to fp32; the labels stay double until TensorFlow casts the feed to fp32.
     if data_type[0] == 'd':
-        x = x * 2 - 1
+        x = (x * 2 - 1).astype(np.float32)
     else:
-        x = x / x_range
+        x = (x.astype(np.float64) / np.float64(x_range)).astype(np.float32)
     for i, ri in enumerate(y_range):
         y[i] = (y[i] - ri[0]) / (ri[1] - ri[0]) * 2 - 1
-    return x, y
+    return x, y.astype(np.float32)
 
 
 class DatasetBatchManager(object):

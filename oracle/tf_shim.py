@@ -281,6 +281,46 @@ def import_reference_trainers(reference_root="/root/reference"):
     return mods["trainer"], mods["trainer3"], ops
 
 
+def import_reference_data(reference_root="/root/reference"):
+    """Import the reference's data.py verbatim (BatchManager, preprocess).  Its graph-side members are inert stand-ins:
+    tf.FIFOQueue / tf.placeholder only have to exist for BatchManager.__init__ (data.py:73-77); matplotlib (imported at
+    data.py:12 for the smoke tests at the bottom of the file, not installable here) is an empty module."""
+    import importlib.util
+
+    tf = install()
+
+    class FIFOQueue(object):
+        def __init__(self, capacity, dtypes, shapes):
+            self.capacity, self.dtypes, self.shapes = capacity, dtypes, shapes
+
+        def enqueue(self, vals):
+            return "enqueue-op"
+
+        def size(self):
+            return 0
+
+    tf.FIFOQueue = FIFOQueue
+    keep = getattr(tf, "placeholder", None)
+    tf.placeholder = lambda dtype=None, shape=None, name=None: ("placeholder", shape)
+    saved = {k: sys.modules.get(k) for k in ("ops", "matplotlib", "matplotlib.pyplot")}
+    mpl, plt = types.ModuleType("matplotlib"), types.ModuleType("matplotlib.pyplot")
+    mpl.pyplot = plt
+    sys.modules["matplotlib"], sys.modules["matplotlib.pyplot"] = mpl, plt
+    sys.modules["ops"] = import_reference_ops(reference_root)
+    try:
+        spec = importlib.util.spec_from_file_location("_dfl_reference_data", reference_root + "/data.py")
+        mod = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mod)
+    finally:
+        for k, v in saved.items():
+            if v is None:
+                sys.modules.pop(k, None)
+            else:
+                sys.modules[k] = v
+    mod._restore_placeholder = keep
+    return mod
+
+
 def import_reference_model(reference_root="/root/reference"):
     """Import the reference's model.py verbatim (read-only); it does `from ops import *`, so the reference's ops.py is
     registered under that module name first.  Call install_structural() before using the builders."""

@@ -58,3 +58,54 @@ def test_factory_falls_back_to_synthetic_without_dataset(tmp_path):
     # no args.txt -> synthetic source class is selected (constructing it needs the GPU, so only the choice is checked)
     root = os.path.join(cfg.data_dir, cfg.dataset)
     assert not os.path.exists(os.path.join(root, "args.txt"))
+
+
+def test_mirror_matches_the_reference_batch_manager(tmp_path):
+    """The reference's own data.BatchManager.__init__ / preprocess / denorm (imported unchanged through oracle/tf_shim.py;
+    only in the build container, where /root/reference exists) on the same toy dataset: file order, counts, ranges,
+    normalisation and de-normalisation must agree with the mirror -- for the `de` layout and the `ae` layout (files sorted
+    by scene * num_frames + frame, labels [dof, frames])."""
+    import argparse
+    import pytest
+    if not os.path.exists("/root/reference/data.py"):
+        pytest.skip("reference source not present on this machine")
+    from oracle import tf_shim
+    ref = tf_shim.import_reference_data("/root/reference")
+    root = str(tmp_path / "data" / "toy")
+    _write_dataset(root)
+    for arch in ("de", "ae"):
+        if arch == "ae":       # AE scenes: files "<scene>_<frame>.npz", y = [dof, frames] history, args carry num_dof
+            import shutil
+            shutil.rmtree(os.path.join(root, "v"))
+            os.makedirs(os.path.join(root, "v"))
+            with open(os.path.join(root, "args.txt"), "a") as f:
+                f.write("num_dof: 2\n")
+            rng = np.random.RandomState(1)
+            for sc in range(11):
+                for fr in range(4):
+                    np.savez_compressed(os.path.join(root, "v", "%d_%d.npz" % (sc, fr)),
+                                        x=rng.randn(8, 6, 2).astype(np.float32), y=rng.rand(2, 4).astype(np.float32) * 2 - 1)
+        cfg, _ = C.get_config(["--dataset=toy", "--data_dir=" + str(tmp_path / "data"), "--res_x=6", "--res_y=8", "--batch_size=4",
+                               "--num_worker=2", "--arch=" + arch])
+        cfg.data_path = root
+        rb = ref.BatchManager(argparse.Namespace(**vars(cfg)))
+        mb = D.BatchManager(cfg, device=torch.device("cpu"))
+        assert isinstance(mb, D.DatasetBatchManager)
+        assert [os.path.basename(p) for p in mb.paths] == [os.path.basename(p) for p in rb.paths]
+        assert mb.num_samples == rb.num_samples and mb.epochs_per_step == rb.epochs_per_step and mb.c_num == rb.c_num
+        assert mb.depth == rb.depth and list(mb.y_num) == list(rb.y_num) and mb.batch_size == rb.batch_size
+        assert abs(mb.x_range - float(rb.x_range)) < 1e-12 and [list(r) for r in mb.y_range] == [list(r) for r in rb.y_range]
+        if arch == "ae":
+            assert mb.dof == rb.dof == 2 and os.path.basename(mb.paths[5]) == "1_1.npz" and os.path.basename(mb.paths[-1]) == "10_3.npz"
+        for path in (mb.paths[0], mb.paths[len(mb.paths) // 2], mb.paths[-1]):
+            xr, yr = ref.preprocess(path, cfg.data_type, rb.x_range, rb.y_range)
+            xm, ym = D.preprocess(path, cfg.data_type, mb.x_range, mb.y_range)
+            assert np.asarray(xm).dtype == np.float32 == np.asarray(xr).dtype
+            np.testing.assert_array_equal(np.asarray(xm), np.asarray(xr))
+            np.testing.assert_array_equal(np.asarray(ym), np.asarray(yr).astype(np.float32))     # TF casts the fed labels to fp32
+            if arch == "de":
+                xd_r, yd_r = rb.denorm(x=np.array(xr, copy=True), y=np.array(yr, copy=True)[None])
+                xd_m, yd_m = mb.denorm(torch.from_numpy(np.array(xm, copy=True)), torch.from_numpy(np.array(ym, copy=True)[None]))
+                np.testing.assert_allclose(xd_m.numpy(), xd_r, rtol=1e-6)
+                np.testing.assert_allclose(yd_m.numpy(), yd_r, rtol=1e-6)
+        mb.stop_thread()
