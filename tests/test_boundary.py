@@ -77,3 +77,53 @@ def test_trainer_graph_tensor_names_exist():
     for a in ("G_s", "G_", "G_var", "g_loss", "g_loss_l1", "g_loss_j_l1", "g_optim", "g_lr", "step", "loss", "loss_l1",
               "loss_j_l1", "loss_p", "optim"):
         assert ("self.%s " % a) in src or ("self.%s=" % a) in src or ("self.%s," % a) in src, a
+
+
+def test_parameter_sweep_dump_matches_reference_test_(tmp_path):
+    """Trainer.test_ (trainer.py:314-354): the reference's own method (imported unchanged through the shim, build container
+    only) and the mirror's, both driven by the same stand-in generator, must write the same `<model_dir>/10_2/<i>.npz`
+    files: z_c construction (p1, p2 fixed, last parameter swept over linspace(-1, 1, y3)), batching by test_b_num, denorm."""
+    import numpy as np
+    import pytest
+    import torch
+    if not os.path.exists("/root/reference/trainer.py"):
+        pytest.skip("reference source not present on this machine")
+    from oracle import tf_shim
+    from deepfluids_b200.trainer import Trainer
+    ref_trainer, _, _ = tf_shim.import_reference_trainers("/root/reference")
+
+    def fake_generator(z):                       # any deterministic map z [n,3] -> fields [n,4,3,2]
+        z = np.asarray(z, dtype=np.float32)
+        base = np.arange(24, dtype=np.float32).reshape(4, 3, 2) / 24
+        return (z[:, 0, None, None, None] + 2 * z[:, 1, None, None, None] + 3 * z[:, 2, None, None, None] * base).astype(np.float32)
+
+    class BM(object):
+        y_num = [11, 5, 8]
+        x_range = 2.5
+
+        def denorm(self, x=None, y=None):
+            return (x * self.x_range if x is not None else None), y
+
+    class Sess(object):
+        def run(self, fetch, feed):
+            assert fetch == "G_-tensor" and list(feed) == ["z-placeholder"]
+            assert feed["z-placeholder"].shape == (4, 3)           # exactly test_b_num rows per run
+            return fake_generator(feed["z-placeholder"])
+
+    r = object.__new__(ref_trainer.Trainer)
+    r.build_test_model = lambda: None
+    r.batch_manager, r.test_b_num, r.c_num, r.model_dir, r.sess, r.G_, r.z = BM(), 4, 3, str(tmp_path / "ref"), Sess(), "G_-tensor", "z-placeholder"
+    ref_trainer.Trainer.test_(r)
+
+    m = Trainer.__new__(Trainer)
+    m.build_test_model = lambda: None
+    m.batch_manager, m.test_b_num, m.c_num, m.model_dir = BM(), 4, 3, str(tmp_path / "mine")
+    m.generate_velocity = lambda z: torch.from_numpy(fake_generator(z))
+    out_dir = m.test_()
+    assert out_dir == os.path.join(str(tmp_path / "mine"), "10_2")
+    ref_files = sorted(os.listdir(os.path.join(str(tmp_path / "ref"), "10_2")))
+    assert sorted(os.listdir(out_dir)) == ref_files == sorted("%d.npz" % i for i in range(8))
+    for f in ref_files:
+        a = np.load(os.path.join(str(tmp_path / "ref"), "10_2", f))["x"]
+        b = np.load(os.path.join(out_dir, f))["x"]
+        np.testing.assert_array_equal(b, a)
