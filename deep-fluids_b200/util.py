@@ -19,7 +19,7 @@ def prepare_dirs_and_logger(config):
     config.data_path = os.path.join(config.data_dir, config.dataset)     # util.py:33
     if config.load_path:                                                 # util.py:37-38
         config.model_dir = config.load_path
-    else:                                                                # util.py:40-44
+    elif not hasattr(config, 'model_dir'):                               # util.py:40-44 (a preset model_dir is kept)
         model_name = "{}/{}_{}_{}".format(config.dataset, datetime.now().strftime("%m%d_%H%M%S"), config.arch,
                                           config.tag)
         config.model_dir = os.path.join(config.log_dir, model_name)

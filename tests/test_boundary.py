@@ -127,3 +127,58 @@ def test_parameter_sweep_dump_matches_reference_test_(tmp_path):
         a = np.load(os.path.join(str(tmp_path / "ref"), "10_2", f))["x"]
         b = np.load(os.path.join(out_dir, f))["x"]
         np.testing.assert_array_equal(b, a)
+
+
+def test_prepare_dirs_matches_reference_util(tmp_path, monkeypatch):
+    """util.prepare_dirs_and_logger / save_config (util.py:17-59): the reference's own functions (imported with empty
+    stand-ins for its plotting imports; build container only) and the mirror's produce the same data_path, the same
+    model_dir rule (load_path wins; a preset model_dir is kept; else log_dir/<dataset>/<MMDD_HHMMSS>_<arch>_<tag>) and the
+    same params.json."""
+    import argparse
+    import importlib.util
+    import re
+    import sys
+    import types
+    import pytest
+    if not os.path.exists("/root/reference/util.py"):
+        pytest.skip("reference source not present on this machine")
+    from deepfluids_b200 import util as U
+    fakes = {}
+    for name in ("PIL", "PIL.Image", "PIL.ImageOps", "imageio", "matplotlib", "matplotlib.pyplot"):
+        if name not in sys.modules:
+            fakes[name] = types.ModuleType(name)
+    if "PIL" in fakes:
+        fakes["PIL"].Image = fakes.get("PIL.Image")
+    for k, v in fakes.items():
+        monkeypatch.setitem(sys.modules, k, v)
+    spec = importlib.util.spec_from_file_location("_dfl_reference_util", "/root/reference/util.py")
+    ref = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(ref)
+    cwd = os.getcwd()
+
+    def cfg(**kw):
+        base = dict(data_dir="data", dataset="smoke_pos21_size5_f200", log_dir=str(tmp_path / "log"), arch="de", tag="test", load_path="")
+        base.update(kw)
+        return argparse.Namespace(**base)
+
+    try:
+        for kw in ({}, {"load_path": str(tmp_path / "resume")}, {"model_dir": str(tmp_path / "preset")}):
+            a, b = cfg(**kw), cfg(**kw)
+            ref.prepare_dirs_and_logger(a)
+            os.chdir(cwd)                                     # (the reference chdir()s into its source directory)
+            U.prepare_dirs_and_logger(b)
+            assert a.data_path == b.data_path == os.path.join("data", "smoke_pos21_size5_f200")
+            if kw:
+                assert a.model_dir == b.model_dir == list(kw.values())[0]
+            else:
+                pat = re.escape(os.path.join(str(tmp_path / "log"), "smoke_pos21_size5_f200", "")) + r"\d{4}_\d{6}_de_test$"
+                assert re.match(pat, a.model_dir) and re.match(pat, b.model_dir)
+            assert os.path.isdir(a.model_dir) and os.path.isdir(b.model_dir)
+            ref.save_config(a)
+            U.save_config(b)
+            ja = json.load(open(os.path.join(a.model_dir, "params.json")))
+            jb = json.load(open(os.path.join(b.model_dir, "params.json")))
+            ja.pop("model_dir"), jb.pop("model_dir")
+            assert ja == jb
+    finally:
+        os.chdir(cwd)
