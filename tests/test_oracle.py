@@ -272,3 +272,39 @@ def test_lr_schedule_pinned_by_reference_init(golden_dir):
     assert tr.g_lr == 1e-4            # trainer.py:284-286: only when step % lr_update_step == lr_update_step - 1
     tr.update_lr(9)
     assert tr.g_lr == 5e-5
+
+
+def test_tf_adam_algebra_vs_torch_adam_independent_witness():
+    """tf.train.AdamOptimizer and torch.optim.Adam differ ONLY in where epsilon enters (TF: lr_t*m/(sqrt(v)+eps) with
+    lr_t = lr*sqrt(1-b2^t)/(1-b1^t); torch: bias-corrected v inside the root).  With eps = 0 the two are algebraically
+    identical, so torch's implementation is an independent witness of the moment / bias-correction algebra of the oracle's
+    TFAdam; with eps > 0 TF's update equals torch's with eps' = eps / sqrt(1 - b2^t), checked per step."""
+    g = torch.Generator().manual_seed(11)
+    p0 = torch.randn(257, generator=g, dtype=torch.float64)
+    grads = [torch.randn(257, generator=g, dtype=torch.float64) for _ in range(6)]
+    # eps = 0
+    var = {"w": p0.clone()}
+    opt = T.TFAdam(var, 0.5, 0.999, 0.0)
+    q = p0.clone().requires_grad_(True)
+    topt = torch.optim.Adam([q], lr=1e-3, betas=(0.5, 0.999), eps=0.0)
+    for gr in grads:
+        opt.step(var, {"w": gr}, 1e-3)
+        q.grad = gr.clone()
+        topt.step()
+        np.testing.assert_allclose(var["w"].numpy(), q.detach().numpy(), rtol=1e-12, atol=1e-15)
+    # eps = 1e-8 (TF default): one TF step from a given (m, v, t) == one torch step with the rescaled epsilon
+    var = {"w": p0.clone()}
+    opt = T.TFAdam(var, 0.5, 0.999, 1e-8)
+    for t, gr in enumerate(grads, 1):
+        before, m, v = var["w"].clone(), opt.m["w"].clone(), opt.v["w"].clone()
+        opt.step(var, {"w": gr}, 1e-3)
+        q = before.clone().requires_grad_(True)
+        topt = torch.optim.Adam([q], lr=1e-3, betas=(0.5, 0.999), eps=1e-8 / math.sqrt(1 - 0.999 ** t))
+        q.grad = gr.clone()
+        topt.step()                                    # creates its state; overwrite it with the running moments and redo
+        st = topt.state[q]
+        st["exp_avg"].copy_(m), st["exp_avg_sq"].copy_(v), st["step"].fill_(t - 1)
+        with torch.no_grad():
+            q.copy_(before)
+        topt.step()
+        np.testing.assert_allclose(var["w"].numpy(), q.detach().numpy(), rtol=1e-10, atol=1e-14)
