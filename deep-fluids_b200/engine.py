@@ -171,7 +171,10 @@ class GeneratorEngine(object):
 
     def repack(self):
         """fp32 master weights -> bf16 tensor-core operands (after every optimizer step): one launch for all layers."""
-        if getattr(self, "_pack_table", None) is None:
+        # the table holds raw pointers into the flat parameter buffer: rebuild it whenever that buffer was replaced
+        # (AEEngine swaps in its shared FlatParams after construction)
+        if getattr(self, "_pack_table", None) is None or self._pack_src != self.params.data.data_ptr():
+            self._pack_src = self.params.data.data_ptr()
             names = [cn for row in self.conv_names for cn in row]
             tab = [[self.params.p(cn + "/weights").data_ptr() for cn in names], [self.wf[cn].data_ptr() for cn in names],
                    [self.wd[cn].data_ptr() for cn in names]]

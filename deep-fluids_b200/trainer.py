@@ -146,7 +146,6 @@ class Trainer(object):
         self._xs.copy_(self.x)
         self._ys.copy_(self.y)
         self._lr_dev = torch.zeros(1, dtype=torch.float32, device=self.device)
-        self._lr_host = torch.zeros(1, dtype=torch.float32).pin_memory()
         scale = 1.0 / self.world
         # one eager pass on a side stream: sets every kernel's attributes, warms allocator (grad buffers stay zeroed
         # at the end because lr = 0 leaves the weights untouched)
@@ -190,8 +189,10 @@ class Trainer(object):
             if y.data_ptr() != self._ys.data_ptr():
                 self._ys.copy_(y, non_blocking=True)
             lr_t = eng.adam_lr_t(self.g_lr, self.beta1, self.beta2) if self.optimizer == 'adam' else self.g_lr
-            self._lr_host[0] = lr_t
-            self._lr_dev.copy_(self._lr_host, non_blocking=True)
+            # by value: the scalar travels as a launch argument of a fill kernel.  (A pinned host slot + async H2D copy is
+            # read when the STREAM reaches the copy, so a host running ahead would overwrite it: step k would see the
+            # lr_t of step k+n.)
+            self._lr_dev.fill_(float(lr_t))
             self._graph_a.replay()
             if self._graph_b is not None:
                 dp.allreduce_grads_(eng.params.grad)     # ONE NCCL all-reduce over the flat gradient buffer

@@ -113,7 +113,8 @@ def synthetic_batch(batch, spatial, seed=123, z_dim=3, dtype=torch.float32, smoo
     return x.to(dtype), y.to(dtype)
 
 
-def teacher_forced_backward(z, var, acts, dpot, num_conv=4, name="G", operand_round=None, mask_from_acts=False):
+def teacher_forced_backward(z, var, acts, dpot, num_conv=4, name="G", operand_round=None, mask_from_acts=False,
+                            min_level=0, return_dz=False):
     """Backward pass of the generator evaluated layer by layer with torch autograd, where every layer's INPUT is the
     activation tensor the device path actually stored (`acts` = {"x0": [per level], "y": [[per conv] per level],
     "s": top-level residual sum}, fp32 CPU copies).  Because the leaky-ReLU masks are then computed from the same
@@ -122,7 +123,9 @@ def teacher_forced_backward(z, var, acts, dpot, num_conv=4, name="G", operand_ro
     `operand_round` (e.g. ref_model.bf16_round_ste) models the bf16 operand copy of the conv weights.
     `mask_from_acts`: take the leaky-ReLU derivative from the sign of the STORED layer output instead of recomputing
     the pre-activation here (a recomputation that differs by 1e-5 relative still flips ~1e-5 of the signs, each flip a
-    5x change of that element: rel-L2 ~ sqrt(1e-5) = 3e-3, which would hide a 1e-4-grade kernel error)."""
+    5x change of that element: rel-L2 ~ sqrt(1e-5) = 3e-3, which would hide a 1e-4-grade kernel error).
+    `min_level` > 0 stops after that level's convolutions (BASELINE-size checks of the finest levels only; `acts` then only
+    needs those levels' tensors).  `return_dz`: also return dL/dz (the AE decoder's gradient into the latent code)."""
     rnd = operand_round if operand_round is not None else (lambda t: t)
     nd = acts["s"].dim() - 2
     rep = len(acts["x0"])
@@ -142,13 +145,16 @@ def teacher_forced_backward(z, var, acts, dpot, num_conv=4, name="G", operand_ro
         return gx
 
     g = layer_grads(acts["s"], "%s/%d_conv" % (name, n_last), None, dpot)      # ds
-    for i in range(rep - 1, -1, -1):
+    gz = None
+    for i in range(rep - 1, min_level - 1, -1):
         ds = g
         gy = ds
         for c in range(num_conv - 1, -1, -1):
             xin = acts["y"][i][c - 1] if c > 0 else acts["x0"][i]
             gy = layer_grads(xin, "%s/%d_conv" % (name, i * num_conv + c + 1), R.lrelu, gy, acts["y"][i][c])
         gx0 = gy + ds
+        if i == min_level and i > 0:
+            break
         if i > 0:      # adjoint of nearest x2 upsampling: sum over the children
             u = torch.zeros_like(acts["x0"][i - 1]).requires_grad_(True)
             up = R.upscale(u, 2) if nd == 2 else R.upscale3(u, 2)
@@ -157,4 +163,54 @@ def teacher_forced_backward(z, var, acts, dpot, num_conv=4, name="G", operand_ro
             flat = gx0.reshape(gx0.shape[0], -1)
             grads["%s/0_fc/weights" % name] = z.t() @ flat
             grads["%s/0_fc/biases" % name] = flat.sum(0)
+            gz = flat @ var["%s/0_fc/weights" % name].t()
+    return (grads, gz) if return_dz else grads
+
+
+def teacher_forced_backward_encoder(x, var, acts, dz, num_conv=3, name="enc", operand_round=None):
+    """Backward pass of EncoderBE / EncoderBE3 (model.py:118-188) layer by layer with torch autograd, every layer fed with
+    the activation the device stored (same idea as `teacher_forced_backward`).  `acts` (fp32 CPU):
+      "cat":  per level idx the concat tensor [B,(D,)H,W,128*(idx+2)] = concat([x, x0]) of model.py:144 / :180
+              (channels 0..127 = output of the level's last conv, the rest = x0);
+      "ylev": per level the outputs of its convs 0..num_conv-2.
+    dz: upstream gradient w.r.t. the latent code [B, z_num].  Returns the gradients of every encoder variable."""
+    rnd = operand_round if operand_round is not None else (lambda t: t)
+    rep = len(acts["cat"])
+    grads = OrderedDict()
+    # variable numbering (model.py:129-149): 0 = first conv; per level num_conv convs (+ one stride-2 conv below the top)
+    n_conv, n_s2, n = [], [], 1
+    for idx in range(rep):
+        n_conv.append(list(range(n, n + num_conv)))
+        n += num_conv
+        if idx < rep - 1:
+            n_s2.append(n)
+            n += 1
+    n_fc = n
+
+    def layer_grads(xin, num, stride, gout):
+        wname = "%s/%d_conv" % (name, num)
+        xin = xin.detach().clone().requires_grad_(True)
+        w = var[wname + "/weights"].detach().clone().requires_grad_(True)
+        b = var[wname + "/biases"].detach().clone().requires_grad_(True)
+        out = R.conv_nd(xin, rnd(w), b, stride, R.lrelu)
+        gx, gw, gb = torch.autograd.grad(out, [xin, w, b], gout)
+        grads[wname + "/weights"], grads[wname + "/biases"] = gw, gb
+        return gx
+
+    top = acts["cat"][-1]
+    flat = top.reshape(top.shape[0], -1)
+    grads["%s/%d_fc/weights" % (name, n_fc)] = flat.t() @ dz
+    grads["%s/%d_fc/biases" % (name, n_fc)] = dz.sum(0)
+    gcat = (dz @ var["%s/%d_fc/weights" % (name, n_fc)].t()).reshape(top.shape)
+    for idx in range(rep - 1, -1, -1):
+        cat = acts["cat"][idx]
+        g, gx0 = gcat[..., :128], gcat[..., 128:]
+        for c in range(num_conv - 1, -1, -1):
+            xin = acts["ylev"][idx][c - 1] if c > 0 else cat[..., 128:]
+            g = layer_grads(xin, n_conv[idx][c], 1, g)
+        gx0 = gx0 + g
+        if idx > 0:
+            gcat = layer_grads(acts["cat"][idx - 1], n_s2[idx - 1], 2, gx0)
+        else:
+            layer_grads(x, 0, 1, gx0)
     return grads

@@ -19,6 +19,7 @@ covered by this shim -- see `oracle/ref_ops.py` for the restatement and the
 unchanged with the layers' arithmetic delegated to the restated primitives: it
 pins the model STRUCTURE and variable layout, not the primitives.
 """
+import importlib.machinery
 import sys
 import types
 
@@ -30,11 +31,26 @@ def _t(x):
     return x if isinstance(x, torch.Tensor) else torch.as_tensor(x)
 
 
+def _mod(name):
+    """Fake module WITH a real ModuleSpec: importlib.util.find_spec(name) (torch._dynamo probes 'tensorflow' that way)
+    raises ValueError on a sys.modules entry whose __spec__ is None."""
+    m = types.ModuleType(name)
+    m.__spec__ = importlib.machinery.ModuleSpec(name, None)
+    m._dfl_shim = True
+    return m
+
+
+def uninstall():
+    """Remove every shim module from sys.modules (tests call this so the fake never outlives them)."""
+    for k in [k for k, v in sys.modules.items() if k.split(".")[0] == "tensorflow" and getattr(v, "_dfl_shim", False)]:
+        del sys.modules[k]
+
+
 def install():
     """Install the fake `tensorflow` (+ `tensorflow.contrib.slim`) modules."""
     if "tensorflow" in sys.modules and getattr(sys.modules["tensorflow"], "_dfl_shim", False):
         return sys.modules["tensorflow"]
-    tf = types.ModuleType("tensorflow")
+    tf = _mod("tensorflow")
     tf._dfl_shim = True
     tf.float32 = torch.float32
     tf.concat = lambda values, axis=0, name=None: torch.cat([_t(v) for v in values], dim=axis)
@@ -46,7 +62,7 @@ def install():
     tf.abs = torch.abs
     tf.reduce_mean = lambda x, axis=None: torch.mean(x) if axis is None else torch.mean(x, dim=axis)
 
-    image = types.ModuleType("tensorflow.image")
+    image = _mod("tensorflow.image")
 
     def resize_nearest_neighbor(x, new_size):
         # tf.image.resize_nearest_neighbor, align_corners=False: out[i] = in[floor(i*in/out)]
@@ -73,13 +89,13 @@ def install():
     if not hasattr(torch.Tensor, "get_shape"):
         torch.Tensor.get_shape = lambda self: _Shape(self.shape)
 
-    nn = types.ModuleType("tensorflow.nn")          # model.py:218 names tf.nn.elu in a default argument (NN arch, unused here)
+    nn = _mod("tensorflow.nn")          # model.py:218 names tf.nn.elu in a default argument (NN arch, unused here)
     nn.elu = torch.nn.functional.elu
     tf.nn = nn
     sys.modules["tensorflow.nn"] = nn
 
-    contrib = types.ModuleType("tensorflow.contrib")
-    slim = types.ModuleType("tensorflow.contrib.slim")
+    contrib = _mod("tensorflow.contrib")
+    slim = _mod("tensorflow.contrib.slim")
     contrib.slim = slim
     tf.contrib = contrib
     sys.modules["tensorflow"] = tf
@@ -164,7 +180,7 @@ def install_structural(store, conv_nd, linear):
     slim.conv2d, slim.conv3d, slim.fully_connected = _conv(2), _conv(3), fully_connected
     tf.variable_scope = variable_scope
     tf.sigmoid = torch.sigmoid
-    framework = types.ModuleType("tensorflow.contrib.framework")
+    framework = _mod("tensorflow.contrib.framework")
     framework.get_variables = lambda vs: [n for n, _ in store.requested if n == vs.name or n.startswith(vs.name + "/")]
     sys.modules["tensorflow"].contrib.framework = framework
     sys.modules["tensorflow.contrib.framework"] = framework
@@ -194,7 +210,7 @@ def install_training(record):
             record["minimize"] = {"loss": loss, "global_step": global_step, "var_list": list(var_list)}
             return "optim-op"
 
-    train = types.ModuleType("tensorflow.train")
+    train = _mod("tensorflow.train")
     train.AdamOptimizer = type("AdamOptimizer", (_Opt,), {"kind": "adam"})
     train.GradientDescentOptimizer = type("GradientDescentOptimizer", (_Opt,), {"kind": "gd"})
     tf.train = train
@@ -232,7 +248,7 @@ def install_training(record):
 
     # tf.distributions.Bernoulli / kl_divergence (use_sparse, trainer.py:389-394): published closed form
     #   KL(Bern(p) || Bern(q)) = p log(p/q) + (1-p) log((1-p)/(1-q))      -- a restatement, like the layer primitives
-    ds = types.ModuleType("tensorflow.distributions")
+    ds = _mod("tensorflow.distributions")
 
     class Bernoulli(object):
         def __init__(self, probs):

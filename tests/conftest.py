@@ -22,3 +22,12 @@ def pytest_configure(config):
 @pytest.fixture(scope="session")
 def golden_dir():
     return os.path.join(ROOT, "tests", "golden")
+
+
+@pytest.fixture(autouse=True)
+def _no_shim_leak():
+    """oracle/tf_shim.py installs a fake `tensorflow` in sys.modules; never let it outlive the test that asked for it."""
+    yield
+    shim = sys.modules.get("oracle.tf_shim")
+    if shim is not None:
+        shim.uninstall()

@@ -1,0 +1,262 @@
+"""CUDA path vs the CPU ORACLE at the BASELINE.json 3D sizes (64^3, 128^3) and an AE at repeat >= 3.
+
+Round-1 review: the largest oracle comparisons were 128x96 / 32x64x112; at 64^3 and 128^3 only the repo's own kernels were
+compared with each other.  These tests put the oracle beside the device at the sizes the bench runs:
+  * 64^3  B=2 num_conv=4: potential, loss, divergence, teacher-forced gradients of every layer      (BASELINE configs[2])
+  * 128^3 B=1 num_conv=4: potential, loss, teacher-forced gradients of the finest level + output conv (configs[3])
+  * the fused stencil (the lean kernel the train step runs) vs oracle autograd on WHOLE fields 4 x 128^3 and 16 x 64^3
+  * AE teacher-forced backward at repeat = 3 (256- and 384-channel stride-2 convolutions), 3D and 2D  (configs[4] path)
+Tolerances (bf16 operands / activation storage, fp32 accumulation; oracle fp32): potential rel-L2 <= 1e-2 against the
+oracle that stores activations in bf16 like the device does, <= 2e-2 against pure fp32; loss <= 1e-2 relative;
+teacher-forced weight gradients rel-L2 <= 2e-2, biases <= 5e-2 (see test_gpu_trainstep.py for why free-running gradient
+comparisons cannot be tight); stencil: loss 3e-6 relative, gradient 1e-7 absolute of max|g|-scale, velocity bit-exact.
+"""
+import gc
+import os
+from collections import OrderedDict
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from oracle import ref_model as M
+from oracle import ref_ops as R
+from oracle import ref_train as T
+
+
+def rel_l2(a, b):
+    a, b = a.double().cpu(), b.double().cpu()
+    return float((a - b).norm() / b.norm().clamp_min(1e-30))
+
+
+def dev():
+    return torch.device("cuda:0")
+
+
+def _acts(eng, levels):
+    return {"x0": [eng.x0[i].float().cpu() if i in levels else None for i in range(eng.rep)],
+            "y": [[t.float().cpu() for t in eng.y[i]] if i in levels else None for i in range(eng.rep)],
+            "s": eng.s.float().cpu()}
+
+
+def test_c3_64cube_chain_vs_oracle():
+    """BASELINE configs[2] geometry (64^3, filters 128, num_conv 4), batch 2."""
+    from deepfluids_b200 import kernels as K
+    from deepfluids_b200.engine import GeneratorEngine
+    spatial, B = [64, 64, 64], 2
+    eng = GeneratorEngine(B, spatial + [3], z_dim=3, num_conv=4, device=dev(), seed=31)
+    assert eng.rep == 4 and eng.level_shape[0] == [8, 8, 8]
+    x, y = T.synthetic_batch(B, spatial, seed=17)
+    pot = eng.forward(y.to(dev()))
+    loss3, dpot, vel = K.stencil_loss_fwdbwd(pot, x.to(dev()), want_vel=True)
+    eng.zero_grad()
+    eng.backward(dpot)
+    var = eng.params.state_dict()
+    pot_ref = M.generator_forward(y, var, spatial + [3], num_conv=4)
+    loss_ref, l1_ref, jl1_ref, vel_ref = T.stencil_loss(pot_ref, x)
+    pot_bf = M.generator_forward(y, var, spatial + [3], num_conv=4, store=M.bf16_round_ste)
+    e_pot, e_pot_bf = rel_l2(pot, pot_ref), rel_l2(pot, pot_bf)
+    print("64^3: pot vs fp32 oracle %.2e, vs bf16-storage oracle %.2e" % (e_pot, e_pot_bf))
+    assert e_pot <= 2e-2 and e_pot_bf <= 1e-2
+    assert abs(loss3[0].item() - loss_ref.item()) <= 1e-2 * abs(loss_ref.item())
+    assert abs(loss3[1].item() - l1_ref.item()) <= 1e-2 * abs(l1_ref.item())
+    assert abs(loss3[2].item() - jl1_ref.item()) <= 1e-2 * abs(jl1_ref.item())
+    # the device's velocity is the reference curl of the device's potential, bit for bit, and divergence-free to 1e-5
+    assert torch.equal(vel.cpu(), R.curl3(pot.cpu()))
+    assert float(K.divergence(vel).abs().max()) <= 1e-5
+    del pot_ref, pot_bf, vel_ref
+    tf = T.teacher_forced_backward(y, var, _acts(eng, range(eng.rep)), dpot.cpu(), num_conv=4, operand_round=M.bf16_round_ste)
+    errs = OrderedDict((k, rel_l2(eng.params.g(k), tf[k])) for k in list(var)[:-1])     # (last bias: exactly-zero sum, see trainstep test)
+    ew = max(v for k, v in errs.items() if k.endswith("weights"))
+    eb = max(v for k, v in errs.items() if k.endswith("biases"))
+    print("64^3: teacher-forced weights %.2e biases %.2e" % (ew, eb))
+    assert ew <= 2e-2 and eb <= 5e-2, errs
+
+
+def test_c4_128cube_forward_and_top_level_backward_vs_oracle():
+    """BASELINE configs[3] geometry (128^3, filters 128, num_conv 4), one field (the oracle needs ~14 s per forward)."""
+    from deepfluids_b200 import kernels as K
+    from deepfluids_b200.engine import GeneratorEngine
+    spatial, B = [128, 128, 128], 1
+    eng = GeneratorEngine(B, spatial + [3], z_dim=3, num_conv=4, device=dev(), seed=41)
+    assert eng.rep == 5 and eng.level_shape[-1] == [128, 128, 128]
+    x, y = T.synthetic_batch(B, spatial, seed=19)
+    pot = eng.forward(y.to(dev()))
+    loss3, dpot, vel = K.stencil_loss_fwdbwd(pot, x.to(dev()), want_vel=True)
+    eng.zero_grad()
+    eng.backward(dpot)
+    var = eng.params.state_dict()
+    with torch.no_grad():
+        pot_ref = M.generator_forward(y, var, spatial + [3], num_conv=4)
+        loss_ref = T.stencil_loss(pot_ref, x)[0]
+    e_pot = rel_l2(pot, pot_ref)
+    print("128^3: pot vs fp32 oracle %.2e, loss %.6f vs %.6f" % (e_pot, loss3[0].item(), loss_ref.item()))
+    assert e_pot <= 2e-2
+    assert abs(loss3[0].item() - loss_ref.item()) <= 1e-2 * abs(loss_ref.item())
+    assert torch.equal(vel.cpu(), R.curl3(pot.cpu()))
+    assert float(K.divergence(vel).abs().max()) <= 1e-5
+    del pot_ref
+    gc.collect()
+    top = eng.rep - 1
+    tf = T.teacher_forced_backward(y, var, _acts(eng, [top]), dpot.cpu(), num_conv=4, operand_round=M.bf16_round_ste,
+                                   min_level=top)
+    names = ["G/%d_conv" % n for n in range(top * 4 + 1, top * 4 + 6)]       # the finest level's four convs + the output conv
+    assert sorted(k.rsplit("/", 1)[0] for k in tf if k.endswith("weights")) == sorted(names)
+    errs = OrderedDict((k, rel_l2(eng.params.g(k), tf[k])) for k in tf if k != names[-1] + "/biases")
+    ew = max(v for k, v in errs.items() if k.endswith("weights"))
+    eb = max(v for k, v in errs.items() if k.endswith("biases"))
+    print("128^3: teacher-forced (finest level) weights %.2e biases %.2e" % (ew, eb))
+    assert ew <= 2e-2 and eb <= 5e-2, errs
+
+
+@pytest.mark.parametrize("B,n", [(4, 128), (16, 64)])
+def test_stencil_lean_path_whole_fields_vs_oracle(B, n):
+    """`dfl_stencil_loss_fwdbwd` on the shapes the bench's train step gives it (all-fp32, even W -> the lean persistent
+    kernel with its per-CTA z segments) against the oracle's loss and torch autograd, on whole fields."""
+    from deepfluids_b200 import kernels as K
+    g = torch.Generator().manual_seed(100 + n)
+    x, _ = T.synthetic_batch(B, [n, n, n], seed=5, smooth=1)
+    pot = torch.randn(B, n, n, n, 3, generator=g) * 0.05
+    pot = (pot + torch.roll(pot, 1, 1) + torch.roll(pot, 1, 2) + torch.roll(pot, 1, 3)) / 4
+    loss3, dpot, vel = K.stencil_loss_fwdbwd(pot.to(dev()), x.to(dev()), 1.0, 1.0, want_vel=True)
+    p = pot.clone().requires_grad_(True)
+    loss, l1, jl1, vel_ref = T.stencil_loss(p, x)
+    (gref,) = torch.autograd.grad(loss, p)
+    assert torch.equal(vel.cpu(), vel_ref.detach())
+    # loss values: against the oracle evaluated in fp64 (an fp32 mean over 2e8 elements carries its own 1e-6 error;
+    # the kernel sums fp64 partials), and loosely against the fp32 oracle's own number
+    with torch.no_grad():
+        loss64, l164, jl164, _ = T.stencil_loss(pot.double(), x.double())
+    assert abs(loss3[0].item() - loss64.item()) <= 3e-6 * abs(loss64.item())
+    assert abs(loss3[1].item() - l164.item()) <= 3e-6 * abs(l164.item()) and abs(loss3[2].item() - jl164.item()) <= 3e-6 * abs(jl164.item())
+    assert abs(loss3[0].item() - loss.item()) <= 1e-4 * abs(loss.item())
+    # every entry of the gradient is a small integer combination of 1/N1 and 1/N2: compare absolutely
+    scale = float(gref.abs().max())
+    err = float((dpot.cpu() - gref).abs().max())
+    print("stencil %dx%d^3: max|dA - dA_ref| = %.2e (max|dA_ref| %.2e)" % (B, n, err, scale))
+    assert err <= 1e-6 * scale + 1e-12
+
+
+def _ae_acts(ae):
+    enc, B = ae.enc, ae.enc.B
+    cat = [torch.cat([enc.C[i][j * B:(j + 1) * B].float().cpu() for j in range(enc.nblk[i])], dim=-1) for i in range(enc.rep)]
+    ylev = [[t.float().cpu() for t in row] for row in enc.ylev]
+    return {"cat": cat, "ylev": ylev}
+
+
+@pytest.mark.parametrize("spatial,B,nc", [([16, 16, 32], 2, 3), ([32, 32], 2, 3)])
+def test_ae_teacher_forced_backward_rep3(spatial, B, nc):
+    """AE / AE3 (model.py:190-216) at repeat = 3: the encoder's stride-2 convolutions are 256->256 and 384->384 channels,
+    the concat gradients route through three levels.  Both halves are checked teacher-forced: the decoder against
+    `teacher_forced_backward` (incl. dL/dz), the encoder against `teacher_forced_backward_encoder` fed with the dz the device
+    handed it -- every layer sees the activation the device stored, so the lrelu masks agree and the bound is tight."""
+    from deepfluids_b200 import kernels as K
+    from deepfluids_b200.encoder import AEEngine
+    nd = len(spatial)
+    cin = 3 if nd == 3 else 2
+    ae = AEEngine(B, spatial + [cin], z_num=16, num_conv=nc, device=dev(), seed=13)
+    assert ae.enc.rep == 3 and ae.dec.rep == 3
+    var = ae.params.state_dict()
+    assert list(var.keys()) == list(M.ae_layout(spatial + [cin], num_conv=nc).keys())
+    x, _ = T.synthetic_batch(B, spatial, seed=23)
+    ylast = torch.rand(B, 2, generator=torch.Generator().manual_seed(4)) * 2 - 1
+    ae.zero_grad()
+    pot, z = ae.forward(x.to(dev()))
+    dpot = torch.empty_like(pot)
+    loss3, _, _ = K.stencil_loss_fwdbwd(pot, x.to(dev()), dpot=dpot)
+    lpd = torch.empty(1, device=dev())
+    K.ae_loss_p(z, ylast.to(dev()), ae.dz, lpd, 1.0)
+    dz_p = ae.dz.clone().cpu()                       # d(loss_p)/dz
+    ae.backward(dpot)
+    dz_dev = ae.dz.clone().cpu()                     # + the decoder's FC input gradient = what the encoder received
+    # forward agreement with the fp32 oracle
+    total, l1, jl1, lp, g, zref, grads = T.ae_loss_and_grads(x, ylast, var, 2, num_conv=nc)
+    assert rel_l2(z, zref) <= 2e-2
+    assert abs(loss3[0].item() + lpd.item() - total.item()) <= 1e-2 * abs(total.item())
+    # decoder, teacher-forced
+    dec = ae.dec
+    acts = {"x0": [t.float().cpu() for t in dec.x0], "y": [[t.float().cpu() for t in row] for row in dec.y], "s": dec.s.float().cpu()}
+    tfd, gz = T.teacher_forced_backward(z.cpu(), var, acts, dpot.cpu(), num_conv=nc, name="AE/dec",
+                                        operand_round=M.bf16_round_ste, return_dz=True)
+    last_b = [k for k in var if k.startswith("AE/dec")][-1]
+    e_dec = OrderedDict((k, rel_l2(ae.params.g(k), tfd[k])) for k in tfd if k != last_b)
+    e_dz = rel_l2(dz_dev - dz_p, gz)
+    # encoder, teacher-forced with the device's dz
+    tfe = T.teacher_forced_backward_encoder(x, var, _ae_acts(ae), dz_dev, num_conv=nc - 1, name="AE/enc",
+                                            operand_round=M.bf16_round_ste)
+    e_enc = OrderedDict((k, rel_l2(ae.params.g(k), tfe[k])) for k in tfe)
+    assert set(e_enc) | set(e_dec) | {last_b} == set(var)
+    wmax = lambda d: max((v, k) for k, v in d.items() if k.endswith("weights"))
+    bmax = lambda d: max((v, k) for k, v in d.items() if k.endswith("biases"))
+    report = "dec W %.2e (%s) b %.2e (%s) dz %.2e | enc W %.2e (%s) b %.2e (%s)" % (wmax(e_dec) + bmax(e_dec) + (e_dz,) + wmax(e_enc) + bmax(e_enc))
+    print(report)
+    assert wmax(e_dec)[0] <= 2e-2 and wmax(e_enc)[0] <= 2e-2 and e_dz <= 2e-2, report
+    assert bmax(e_dec)[0] <= 5e-2 and bmax(e_enc)[0] <= 5e-2, report
+    # stride-2 layers really are the wide ones
+    s2 = [k for k in var if k.startswith("AE/enc") and k.endswith("weights") and var[k].shape[-1] in (256, 384)]
+    assert sorted(var[k].shape[-1] for k in s2) == [256, 384]
+
+
+def test_ae_adam_steps_keep_decoder_operands_fresh(tmp_path):
+    """Round-1 advisor finding: the decoder's bf16 conv operands must be re-packed from the LIVE shared parameter buffer after
+    every optimizer step and after a checkpoint load (a stale pointer table left them at their initial values)."""
+    from deepfluids_b200 import config as C, kernels as K
+    from deepfluids_b200.data import BatchManager
+    from deepfluids_b200.trainer3 import Trainer3
+    cfg, _ = C.get_config(["--synthetic=true", "--arch=ae", "--is_3d=true", "--res_x=16", "--res_y=16", "--res_z=16",
+                           "--batch_size=2", "--num_conv=2", "--max_step=6", "--lr_max=0.001"])
+    cfg.model_dir = str(tmp_path)
+    bm = BatchManager(cfg, pool=1)
+    tr = Trainer3(cfg, bm)
+    dec = tr.ae.dec
+    cn = dec.conv_names[0][0]
+    wf0 = dec.wf[cn].clone()
+    for i in range(3):
+        tr.train_step()
+    assert not torch.equal(dec.wf[cn], wf0), "decoder operands did not follow the optimizer"
+    # a fresh pack of the live fp32 variable equals the operand the engine holds
+    wf_chk, wd_chk = torch.empty_like(dec.wf[cn]), torch.empty_like(dec.wd[cn])
+    K.pack_conv_weights(tr.ae.params.p(cn + "/weights"), wf_chk, wd_chk)
+    assert torch.equal(wf_chk, dec.wf[cn]) and torch.equal(wd_chk, dec.wd[cn])
+    # save / load round trip reaches the decoder: decode() of the restored trainer equals the original's
+    z = torch.rand(2, cfg.z_num, device=dev()) * 2 - 1
+    v0 = tr.decode(z).clone()
+    path = os.path.join(str(tmp_path), "m.pt")
+    tr.save(path)
+    tr2 = Trainer3(cfg, BatchManager(cfg, pool=1))
+    assert not torch.equal(tr2.decode(z), v0)
+    tr2.load(path)
+    assert torch.equal(tr2.decode(z), v0)
+
+
+def test_graph_and_eager_steps_agree_on_weights():
+    """Round-1 advisor finding: the CUDA-graph step must apply the lr_t of ITS OWN step even when the host runs ahead.
+    Five steps in graph mode (no host sync in between) and in eager mode from the same state: identical Adam step sizes;
+    weights agree up to the run-to-run noise of the atomically reduced weight gradients."""
+    from deepfluids_b200 import config as C
+    from deepfluids_b200.data import BatchManager
+    from deepfluids_b200.trainer import Trainer
+    args = ["--synthetic=true", "--res_x=24", "--res_y=32", "--batch_size=4", "--num_conv=2", "--max_step=50", "--lr_max=0.001"]
+    out = []
+    for graph in ("1", "0"):
+        os.environ["DFL_CUDA_GRAPH"] = graph
+        try:
+            cfg, _ = C.get_config(args)
+            bm = BatchManager(cfg, pool=1)
+            tr = Trainer(cfg, bm)
+            for i in range(5):
+                tr.train_step()
+                tr.update_lr(i)
+            torch.cuda.synchronize()
+            out.append(tr.engine.params.data.clone())
+        finally:
+            os.environ.pop("DFL_CUDA_GRAPH", None)
+    w0 = Trainer(C.get_config(args)[0], BatchManager(C.get_config(args)[0], pool=1)).engine.params.data
+    moved = (out[1] - w0).double().norm().item()
+    diff = (out[0] - out[1]).double().norm().item()
+    # Adam's first steps move each weight by ~lr_t per step; a wrong lr_t (step k+n's bias-correction factor applied at
+    # step k: up to 1.7x off in the first steps) shows up as a difference of the order of the movement itself, while
+    # the noise of the atomically reduced gradients only flips the few weights whose gradient is ~0
+    print("moved %.3e, graph-vs-eager diff %.3e" % (moved, diff))
+    assert moved > 0 and diff <= 0.05 * moved

@@ -308,3 +308,40 @@ def test_tf_adam_algebra_vs_torch_adam_independent_witness():
             q.copy_(before)
         topt.step()
         np.testing.assert_allclose(var["w"].numpy(), q.detach().numpy(), rtol=1e-10, atol=1e-14)
+
+
+def test_teacher_forced_encoder_backward_equals_autograd():
+    """oracle.ref_train.teacher_forced_backward_encoder (used by the GPU AE parity tests) fed with the oracle's OWN
+    activations must reproduce plain autograd through encoder_forward (fp64: to rounding), incl. the stride-2 levels."""
+    from collections import OrderedDict
+    spatial, B, nc, name = [8, 8, 16], 1, 2, "AE/enc"
+    var = M.init_variables(M.encoder_layout(spatial + [3], num_conv=nc, name=name)[0], seed=3, dtype=torch.float64)
+    g = torch.Generator().manual_seed(0)
+    for k in var:
+        if k.endswith("biases"):
+            var[k] = torch.randn(var[k].shape, generator=g, dtype=torch.float64) * 0.1
+    x = torch.randn([B] + spatial + [3], generator=g, dtype=torch.float64)
+    leaves = OrderedDict((k, v.clone().requires_grad_(True)) for k, v in var.items())
+    cv = lambda h, n, s: R.conv_nd(h, leaves["%s/%d_conv/weights" % (name, n)], leaves["%s/%d_conv/biases" % (name, n)], s, R.lrelu)
+    rep, n = 2, 0
+    h = cv(x, n, 1); x0 = h; n += 1
+    cats, ylev = [], []
+    for idx in range(rep):
+        row = []
+        for c in range(nc):
+            h = cv(h, n, 1); n += 1
+            if c < nc - 1:
+                row.append(h.detach())
+        ylev.append(row)
+        h = torch.cat([h, x0], -1)
+        cats.append(h.detach())
+        if idx < rep - 1:
+            h = cv(h, n, 2); n += 1; x0 = h
+    z = R.linear(h.reshape(B, -1), leaves["%s/%d_fc/weights" % (name, n)], leaves["%s/%d_fc/biases" % (name, n)])
+    assert torch.equal(z.detach(), M.encoder_forward(x, var, num_conv=nc, name=name))
+    dz = torch.randn(z.shape, generator=g, dtype=torch.float64)
+    gs = torch.autograd.grad(z, list(leaves.values()), dz)
+    tf = T.teacher_forced_backward_encoder(x, var, {"cat": cats, "ylev": ylev}, dz, num_conv=nc, name=name)
+    assert list(tf.keys()) != [] and set(tf) == set(var)
+    for k, gk in zip(leaves, gs):
+        assert float((gk - tf[k]).abs().max()) <= 1e-12 * max(1.0, float(gk.abs().max())), k
