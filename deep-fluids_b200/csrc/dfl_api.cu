@@ -61,6 +61,12 @@ int stencil_loss_fwdbwd(int nd, const int64_t* dims, const void* pot, int pot_ch
                         int dt_x, int dpot_channels, cudaStream_t st);
 int fwd_stencils(int op, int nd, const int64_t* dims, const void* in, int in_cs, void* out0, void* out1, int dtype,
                  cudaStream_t st);
+int bwd_stencils(int op, int nd, const int64_t* dims, const float* g0, const float* g1, float* out, int out_cs,
+                 cudaStream_t st);
+int mse_loss(const float* d, float target, float* loss, float* dd, size_t n, float scale, cudaStream_t st);
+int gemm_f32(const float* A, const float* B, const float* bias, float* C, int M, int N, int K, int transA, int transB,
+             int accumulate, cudaStream_t st);
+int colsum_f32(const float* x, float* out, int M, int N, cudaStream_t st);
 int conv_tc_launch(const void* x, const void* w_packed, const float* bias, void* out, void* out2,
                    const void* residual, const void* mask_src, const int64_t* dims, int nd, int cin, int cout,
                    int flags, const int32_t* blkmap, int nphys, cudaStream_t st);
@@ -149,6 +155,20 @@ int dfl_jacobian_fwd(const void* vel, void* jac, void* vort_or_curl, const int64
 int dfl_divergence(const void* vel, void* div, const int64_t* dims, int ndim, int dtype, void* stream) {
   return fwd_stencils(2, ndim, dims, vel, ndim, div, nullptr, dtype, ST(stream));
 }
+int dfl_curl_bwd(const float* dvel, float* dpot, const int64_t* dims, int ndim, int dpot_channels, void* stream) {
+  return bwd_stencils(0, ndim, dims, dvel, nullptr, dpot, dpot_channels, ST(stream));
+}
+int dfl_jacobian_bwd(const float* djac, const float* daux, float* dvel, const int64_t* dims, int ndim, void* stream) {
+  return bwd_stencils(1, ndim, dims, djac, daux, dvel, ndim, ST(stream));
+}
+int dfl_mse_loss(const float* d, float target, float* loss, float* dd, size_t n, float scale, void* stream) {
+  return mse_loss(d, target, loss, dd, n, scale, ST(stream));
+}
+int dfl_gemm_f32(const float* A, const float* B, const float* bias, float* C, int M, int N, int K, int transA, int transB,
+                 int accumulate, void* stream) {
+  return gemm_f32(A, B, bias, C, M, N, K, transA, transB, accumulate, ST(stream));
+}
+int dfl_colsum_f32(const float* x, float* out, int M, int N, void* stream) { return colsum_f32(x, out, M, N, ST(stream)); }
 size_t dfl_stencil_loss_workspace_bytes(const int64_t* dims, int ndim) {
   return stencil_loss_workspace_bytes(ndim, dims);
 }

@@ -83,6 +83,35 @@ def divergence(vel):
     return out
 
 
+def curl_bwd(dvel, pot_channels=None):
+    """dpot = curl^T(dvel) (fp32); 2D: `pot_channels` channels (gradient in channel 0), 3D: 3"""
+    d, nd = _spatial(dvel)
+    assert dvel.dtype == torch.float32 and dvel.shape[-1] == nd
+    cs = 3 if nd == 3 else int(pot_channels or 1)
+    dpot = torch.empty(dvel.shape[:-1] + (cs,), dtype=torch.float32, device=dvel.device)
+    PROF.timed("curl_bwd", 0.0, lambda: check(cabi.lib().dfl_curl_bwd(_p(dvel), _p(dpot), d, nd, cs, _st())))
+    return dpot
+
+
+def jacobian_bwd(djac, daux):
+    """dvel = J^T djac + aux^T daux (fp32; either may be None)"""
+    ref = djac if djac is not None else daux
+    d, nd = _spatial(ref)
+    assert all(t is None or t.dtype == torch.float32 for t in (djac, daux))
+    dvel = torch.empty(ref.shape[:-1] + (nd,), dtype=torch.float32, device=ref.device)
+    PROF.timed("jacobian_bwd", 0.0, lambda: check(cabi.lib().dfl_jacobian_bwd(_p(djac), _p(daux), _p(dvel), d, nd, _st())))
+    return dvel
+
+
+def mse_loss(dvals, target, scale=1.0, want_grad=True):
+    """LSGAN term: (mean((d - target)^2) as a 1-element fp32 tensor, scale * dloss/dd or None)"""
+    assert dvals.dtype == torch.float32
+    loss = torch.empty(1, dtype=torch.float32, device=dvals.device)
+    dd = torch.empty_like(dvals) if want_grad else None
+    PROF.timed("mse_loss", 0.0, lambda: check(cabi.lib().dfl_mse_loss(_p(dvals), float(target), _p(loss), _p(dd), dvals.numel(), float(scale), _st())))
+    return loss, dd
+
+
 def stencil_loss_fwdbwd(pot, x, w1=1.0, w2=1.0, grad_scale=1.0, want_vel=False, dpot=None, loss3=None, workspace=None):
     """-> (loss3 [total,l1,jl1] float32 device tensor, dpot, vel|None).  If `dpot` is given with more than one channel in
     2D, the gradient is written full-shape (channel 0 = d/d psi, the rest 0)."""
@@ -120,6 +149,26 @@ def fc_bwd(z, dout, dW, db):
     B, K = z.shape
     N = dW.shape[1]
     PROF.timed("fc_bwd", 0.0, lambda: check(cabi.lib().dfl_fc_bwd(_p(z), _p(dout), _p(dW), _p(db), B, K, N, _dt(dout), _st())))
+
+
+def gemm(a, b, bias=None, out=None, trans_a=False, trans_b=False, accumulate=False):
+    """fp32 C[M,N] = op(a) op(b) (+ bias) (+ C): the general fully connected layer (dfl_gemm_f32)"""
+    assert a.dtype == torch.float32 and b.dtype == torch.float32 and a.dim() == 2 and b.dim() == 2
+    M, Kd = (a.shape[1], a.shape[0]) if trans_a else a.shape
+    N = b.shape[0] if trans_b else b.shape[1]
+    assert (b.shape[1] if trans_b else b.shape[0]) == Kd, "gemm: inner dimensions differ"
+    if out is None:
+        assert not accumulate
+        out = torch.empty(M, N, dtype=torch.float32, device=a.device)
+    PROF.timed("gemm_f32", 0.0, lambda: check(cabi.lib().dfl_gemm_f32(_p(a), _p(b), _p(bias), _p(out), M, N, Kd, int(trans_a),
+                                                                  int(trans_b), int(accumulate), _st())))
+    return out
+
+
+def colsum(x):
+    out = torch.empty(x.shape[1], dtype=torch.float32, device=x.device)
+    PROF.timed("colsum_f32", 0.0, lambda: check(cabi.lib().dfl_colsum_f32(_p(x), _p(out), x.shape[0], x.shape[1], _st())))
+    return out
 
 
 # ------------------------------------------------------------------ conv

@@ -8,7 +8,7 @@ the ordered TF-named variable list.  `EncoderBE(3)(x, filters, z_num, ...) -> (z
 so `reuse=True` re-applies the same variables, as tf.variable_scope(reuse=True) does.
 """
 from .engine import GeneratorEngine
-from .ops import lrelu
+from .ops import conv2d, conv3d, get_variables, lrelu, variable_scope
 
 _ENGINES = {}
 
@@ -37,6 +37,39 @@ def GeneratorBE(z, filters, output_shape, name='G', num_conv=4, conv_k=3, last_k
 def GeneratorBE3(z, filters, output_shape, name='G', num_conv=4, conv_k=3, last_k=3, repeat=0, skip_concat=False,
                  act=lrelu, reuse=False):
     return _generator(z, filters, output_shape, name, num_conv, conv_k, last_k, repeat, skip_concat, act, reuse, 3)
+
+
+def _discriminator(x, filters, name, reuse, conv):
+    """Patch discriminator of arch=dg (model.py:89-116): three stride-2 convs (filters/2, filters, 2*filters channels), one
+    stride-1 conv (4*filters), one stride-1 conv to a single channel; k=3, lrelu on all but the last.  Built on the ops-level
+    layers (ops.py), i.e. differentiable tcgen05 kernels with slim's default variable names D/Conv ... D/Conv_4."""
+    with variable_scope(name, reuse=reuse) as vs:
+        width = int(filters / 2)
+        for _ in range(3):
+            x = conv(x, width, k=3, act=lrelu)            # default stride 2 (ops.py:12,15)
+            width *= 2
+        x = conv(x, width, k=3, s=1, act=lrelu)
+        out = conv(x, 1, k=3, s=1)
+    return out, get_variables(vs)
+
+
+def DiscriminatorPatch(x, filters, name='D', train=True, reuse=False):
+    return _discriminator(x, filters, name, reuse, conv2d)
+
+
+def DiscriminatorPatch3(x, filters, name='D', train=True, reuse=False):
+    return _discriminator(x, filters, name, reuse, conv3d)
+
+
+def elu(x):
+    """tf.nn.elu: the default activation of NN (model.py:218)"""
+    raise NotImplementedError("arch='nn' (latent-space integrator, model.py:218-224) is outside the B200 hot path")
+
+
+def NN(x, filters, onum, name='NN', act=elu, dropout=0.1, train=True, reuse=False):
+    """latent-space MLP of arch=nn (model.py:218-224): linear(2*filters) + batch_norm + dropout, linear(filters) +
+    batch_norm + dropout, linear(onum).  Not built: it is not on the conv / stencil hot path."""
+    raise NotImplementedError("arch='nn' (latent-space integrator, model.py:218-224) is outside the B200 hot path")
 
 
 def _encoder(x, filters, z_num, name, num_conv, conv_k, repeat, act, reuse, nd):

@@ -9,7 +9,8 @@ the same computation as a fixed sequence of sm_100a kernels through the C-ABI:
     g_lr update                                       (trainer.py:284-288)
 Data parallelism (new; the reference is single-GPU): when torch.distributed is initialised the flat fp32 gradient
 buffer is summed with ONE NCCL all-reduce per step and the 1/world factor is folded into the Adam kernel.
-Out of scope here: arch 'dg'/'nn', summaries/images, test()/generate() dumps.
+arch=dg (generator + patch discriminator, LSGAN terms) runs the same fused step plus an adversarial branch over the
+differentiable layer ops (ops.py / layers.py).  Out of scope here: arch 'nn', summaries / PNG images.
 """
 import math
 import os
@@ -35,8 +36,8 @@ class Trainer(object):
         self.dataset = config.dataset
         self.data_type = config.data_type
         self.arch = config.arch
-        if 'nn' in self.arch or 'dg' in self.arch:
-            raise NotImplementedError("arch '%s' is outside the B200 hot path (SURVEY.md 2: de/ae only)" % self.arch)
+        if 'nn' in self.arch:
+            raise NotImplementedError("arch '%s' is outside the B200 hot path (SURVEY.md 2: de/ae/dg)" % self.arch)
 
         self.res_x, self.res_y, self.res_z = config.res_x, config.res_y, config.res_z
         self.c_num = batch_manager.c_num
@@ -46,6 +47,7 @@ class Trainer(object):
         self.filters = config.filters
         self.num_conv = config.num_conv
         self.w1, self.w2 = config.w1, config.w2
+        self.w3 = getattr(config, "w3", 0.005)      # weight of the adversarial term (arch=dg, trainer.py:178)
 
         self.use_c = config.use_curl
         spatial = list(self.x.shape[1:-1])
@@ -124,6 +126,93 @@ class Trainer(object):
         self.use_graph = bool(int(os.environ.get("DFL_CUDA_GRAPH", "1")))
         self._captured = False
         self._xs = self._ys = None
+        if 'dg' in self.arch:
+            self._build_discriminator()
+
+    # ------------------------------------------------------------------ arch=dg (trainer.py:149-156,174-184; trainer3.py:27-34,53-63)
+    def _build_discriminator(self):
+        """D_x = DiscriminatorPatch(concat(x, x_vort)); D_G = DiscriminatorPatch(concat(G_, G_vort_), reuse=True): the
+        variables D/Conv ... D/Conv_4 are created by the first call, like building the TF graph does."""
+        from . import model as Mo, ops
+        if self.precision != "bf16":
+            raise NotImplementedError("arch=dg runs the bf16 tensor-core path (precision=%s requested)" % self.precision)
+        self._ops = ops
+        self._disc = Mo.DiscriminatorPatch3 if self.is_3d else Mo.DiscriminatorPatch
+        ops.reset_variables(self.config.random_seed + 1)
+        with torch.no_grad():
+            d_in = torch.cat([self.x, K.jacobian_fwd(self.x.contiguous(), want_jac=False)[1]], dim=-1)
+            _, self.D_var = self._disc(d_in, self.filters)
+        self._d_params = [ops.get_variable(n) for n in self.D_var]
+        self._d_m = [torch.zeros_like(p) for p in self._d_params]
+        self._d_v = [torch.zeros_like(p) for p in self._d_params]
+        self.use_graph = False                    # the adversarial branch is an autograd graph over the layer ops
+        self.d_optim = self.train_step            # `sess.run([self.g_optim, self.d_optim])` is ONE train_step() here
+        self.g_loss_real = self.d_loss_fake = self.d_loss_real = self.d_loss = None
+        self._dg4 = None
+
+    def _train_step_dg(self, x, y):
+        """one `sess.run([self.g_optim, self.d_optim])` (trainer.py:266): both updates are computed from the same forward.
+          g_loss = w1*L1 + w2*L1(J) + w3*mean((D_G - 1)^2)   -> generator variables
+          d_loss = mean((D_x - 1)^2) + mean(D_G^2)           -> discriminator variables
+        The supervised part and its gradient come from the fused stencil kernel as in arch=de; the adversarial part runs
+        through the differentiable layer ops (curl / jacobian adjoints, tensor-core convs) and is added to dL/dpot.
+        Adam: the reference minimises both losses with ONE AdamOptimizer object, whose beta-power accumulators therefore
+        advance twice per step; within a step TF does not order the two updates, here both read the powers at the start of
+        the step, i.e. bias correction with t = 2n - 1 at step n."""
+        ops, eng = self._ops, self.engine
+        eng.zero_grad()
+        pot = eng.forward(y)
+        K.stencil_loss_fwdbwd(pot, x, self.w1, self.w2, 1.0, dpot=self._dpot, loss3=self._loss3, workspace=self._ws)
+        leaf = pot.detach().requires_grad_(True)
+        jac = ops.jacobian3 if self.is_3d else ops.jacobian
+        G_ = jac(leaf)[1] if self.is_3d else ops.curl(leaf)                       # trainer3.py:18 / trainer.py:140
+        G_in = torch.cat([G_, jac(G_)[1]], dim=-1)                                # trainer.py:155
+        with torch.no_grad():
+            D_in = torch.cat([x, K.jacobian_fwd(x.contiguous(), want_jac=False)[1]], dim=-1)
+        D_x, _ = self._disc(D_in, self.filters, reuse=True)
+        D_G, _ = self._disc(G_in, self.filters, reuse=True)
+        l_adv, seed_adv = K.mse_loss(D_G.detach(), 1.0, scale=self.w3)            # g_loss_real, d(w3 * it)/dD_G
+        l_fake, seed_fake = K.mse_loss(D_G.detach(), 0.0)
+        l_real, seed_real = K.mse_loss(D_x.detach(), 1.0)
+        d_grads = torch.autograd.grad([D_x, D_G], self._d_params, [seed_real, seed_fake], retain_graph=True)
+        (dpot_adv,) = torch.autograd.grad(D_G, leaf, seed_adv)
+        self._dpot.add_(dpot_adv)
+        eng.backward(self._dpot)
+        self.G_, self.D_x, self.D_G = G_.detach(), D_x.detach(), D_G.detach()
+        self._dg4 = torch.cat([l_adv, l_fake, l_real])
+        # ---- gradient exchange + the two updates
+        scale = dp.allreduce_grads_(eng.params.grad)
+        if self.world > 1:
+            flat = torch.cat([g.reshape(-1) for g in d_grads])
+            dist.all_reduce(flat)
+            d_grads = [t.view_as(g) for t, g in zip(flat.split([g.numel() for g in d_grads]), d_grads)]
+        if self.optimizer == 'adam':
+            t = 2 * (eng.adam_t // 2) + 1
+            eng.adam_t += 2
+            lr_t = self.g_lr * math.sqrt(1.0 - self.beta2 ** t) / (1.0 - self.beta1 ** t)
+            P = eng.params
+            K.adam_step(P.data, P.grad, P.m, P.v, lr_t, self.beta1, self.beta2, 1e-8, scale)
+            for p_, g_, m_, v_ in zip(self._d_params, d_grads, self._d_m, self._d_v):
+                K.adam_step(p_.data, g_.contiguous(), m_, v_, lr_t, self.beta1, self.beta2, 1e-8, scale)
+        else:
+            P = eng.params
+            K.adam_step(P.data, P.grad, None, None, self.g_lr, 0.0, 0.0, 0.0, scale)
+            for p_, g_ in zip(self._d_params, d_grads):
+                K.adam_step(p_.data, g_.contiguous(), None, None, self.g_lr, 0.0, 0.0, 0.0, scale)
+        eng.repack()
+        self._d_grads = d_grads
+        self.step += 1
+        return self._loss3
+
+    def losses_dg(self):
+        """(g_loss, g_loss_l1, g_loss_j_l1, g_loss_real, d_loss_fake, d_loss_real, d_loss) of the last step"""
+        l = self._loss3.tolist()
+        adv, fake, real = self._dg4.tolist()
+        self.g_loss_l1, self.g_loss_j_l1 = l[1], l[2]
+        self.g_loss_real, self.d_loss_fake, self.d_loss_real = adv, fake, real
+        self.g_loss = l[0] + self.w3 * adv
+        self.d_loss = real + fake
+        return self.g_loss, l[1], l[2], adv, fake, real, self.d_loss
 
     # ------------------------------------------------------------------ one `sess.run(self.g_optim)`
     def _step_body_a(self, x, y, want_vel=False):
@@ -181,6 +270,8 @@ class Trainer(object):
             x, y = self.batch_manager.batch()
         self.x, self.y = x, y
         eng = self.engine
+        if 'dg' in self.arch:
+            return self._train_step_dg(x, y)
         if self.use_graph and not want_vel:
             if not self._captured:
                 self._capture()
@@ -222,6 +313,8 @@ class Trainer(object):
 
     def losses(self):
         """(g_loss, g_loss_l1, g_loss_j_l1) of the last step as Python floats (one D2H read)."""
+        if 'dg' in self.arch and self._dg4 is not None:
+            return list(self.losses_dg()[:3])
         l = self._loss3.tolist()
         self.g_loss, self.g_loss_l1, self.g_loss_j_l1 = l
         return l

@@ -55,6 +55,18 @@ int dfl_jacobian_fwd(const void* vel, void* jac, void* vort_or_curl, const int64
 /* ops.divergence / ops.divergence3 (ops.py:276-290): out [B,(D-1,)H-1,W-1,1]. */
 int dfl_divergence(const void* vel, void* div, const int64_t* dims, int ndim, int dtype, void* stream);
 
+/* Adjoints of the three stencils above (fp32): what TF autodiff derives from the slice / sub / concat graphs of
+ * ops.py:205-274 when curl / jacobian / jacobian3 sit inside a differentiated graph -- e.g. arch=dg, whose discriminator
+ * sees concat(G_, vorticity(G_)) (trainer.py:149-156, trainer3.py:27-34).  The train step of arch=de/ae does not use them
+ * (dfl_stencil_loss_fwdbwd emits dL/dpot directly).
+ *   dfl_curl_bwd:     dpot [..,dpot_channels] = curl^T(dvel)   (2D: channel 0, the others 0; 3D: dpot_channels = 3)
+ *   dfl_jacobian_bwd: dvel [..,ndim] = J^T(djac) + aux^T(daux); djac [..,ndim^2] or NULL, daux [..,1|3] or NULL */
+int dfl_curl_bwd(const float* dvel, float* dpot, const int64_t* dims, int ndim, int dpot_channels, void* stream);
+int dfl_jacobian_bwd(const float* djac, const float* daux, float* dvel, const int64_t* dims, int ndim, void* stream);
+/* LSGAN terms of arch=dg (trainer.py:174-176, trainer3.py:53-55): loss[0] = mean((d - target)^2) over n values;
+ * dd (may be NULL) = scale * d loss / d d.  Deterministic single-block reduction. */
+int dfl_mse_loss(const float* d, float target, float* loss, float* dd, size_t n, float scale, void* stream);
+
 /* Fused loss + gradient (SURVEY.md 8a "S").  Replaces, in one pass: curl (trainer.py:140 / trainer3.py:18),
  * jacobian of prediction and target (trainer.py:32,146 / trainer3.py:24), both L1 means (trainer.py:170-172 /
  * trainer3.py:49-51) and the TF autodiff of all of it w.r.t. the network output.
@@ -82,6 +94,13 @@ int dfl_fc_fwd(const float* z, const float* W, const float* bias, void* out, int
 /* dW[k,n] = sum_b z[b,k] dout[b,n];  db[n] = sum_b dout[b,n]   (overwritten) */
 int dfl_fc_bwd(const float* z, const void* dout, float* dW, float* db, int B, int K, int N, int dout_dtype,
                void* stream);
+
+/* General fully connected layer (slim.fully_connected at the ops level, ops.py:23-24; the MLP of arch=nn, model.py:218-224):
+ * C[M,N] = op(A)[M,K] op(B)[K,N] (+ bias[N]) (+ C if accumulate), fp32.  A row-major [M,K] ([K,M] if transA), B row-major
+ * [K,N] ([N,K] if transB).  forward: A = x, B = W;  dx = dy W^T: transB;  dW = x^T dy: transA;  db = dfl_colsum_f32(dy). */
+int dfl_gemm_f32(const float* A, const float* B, const float* bias, float* C, int M, int N, int K, int transA, int transB,
+                 int accumulate, void* stream);
+int dfl_colsum_f32(const float* x, float* out, int M, int N, void* stream);
 
 /* ---- 3x3 / 3x3x3 convolution, stride 1, SAME (slim.conv2d / slim.conv3d: ops.py:12-16) ----------------- */
 /* fp32 TF-layout weights [taps][Cin][Cout] (HWIO / DHWIO) -> bf16 GEMM operands for forward and dgrad. */

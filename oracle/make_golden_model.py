@@ -37,6 +37,9 @@ CASES = {  # name: (builder, spatial+[C], kwargs)
     "ae2d": ("AE", [16, 12, 2], dict(num_conv=3)),
     "ae3d": ("AE3", [16, 16, 8, 3], dict(num_conv=2)),
     "ae2d_sparse": ("AE", [16, 12, 2], dict(num_conv=2, use_sparse=True)),
+    # arch=dg: the patch discriminator sees concat(velocity, vorticity): 2+1 channels in 2D, 3+3 in 3D (trainer.py:153)
+    "disc2d": ("DiscriminatorPatch", [16, 24, 3], dict()),
+    "disc3d": ("DiscriminatorPatch3", [16, 8, 16, 6], dict()),
 }
 
 
@@ -47,6 +50,9 @@ def run_case(model, name):
     if builder.startswith("Generator"):
         tab, _, _ = M.generator_layout(shape, FILTERS, kw.get("num_conv", 4), kw.get("repeat", 0), z_dim=3, name="G")
         inp = torch.rand(B, 3, generator=g) * 2 - 1
+    elif builder.startswith("Discriminator"):
+        tab = M.discriminator_layout(shape[-1], FILTERS, len(shape) - 1, name="D")
+        inp = torch.randn(B, *shape, generator=g)
     elif builder.startswith("Encoder"):
         tab, _ = M.encoder_layout(shape, FILTERS, Z_NUM, kw.get("num_conv", 3), kw.get("repeat", 0), name="enc")
         inp = torch.randn(B, *shape, generator=g)
@@ -65,6 +71,16 @@ def run_case(model, name):
         mine = M.generator_forward(inp, var, shape, FILTERS, kw.get("num_conv", 4), kw.get("repeat", 0), "G")
         outs = {"out": out}
         assert torch.equal(out, mine), name
+    elif builder.startswith("Discriminator"):
+        out, variables = fn(inp, FILTERS)
+        mine = M.discriminator_forward(inp, var, "D")
+        outs = {"out": out}
+        assert torch.equal(out, mine), name
+        # reuse=True (trainer.py:156: the generated field goes through the SAME discriminator): no new variable is requested
+        n_req = len(store.requested)
+        out2, variables2 = fn(inp * 0.5, FILTERS, reuse=True)
+        assert len(store.requested) == n_req and list(variables2) == list(variables), name
+        assert torch.equal(out2, M.discriminator_forward(inp * 0.5, var, "D")), name
     elif builder.startswith("Encoder"):
         out, variables = fn(inp, FILTERS, Z_NUM, **kw)
         mine = M.encoder_forward(inp, var, FILTERS, kw.get("num_conv", 3), kw.get("repeat", 0), "enc")

@@ -37,8 +37,12 @@ CASES = {  # name: (is_3d, arch, spatial, num_conv, use_sparse)
     "ae2d": (False, "ae", [16, 12], 3, False),
     "ae3d": (True, "ae", [16, 16, 8], 2, False),
     "ae2d_sparse": (False, "ae", [16, 12], 2, True),
+    # arch=dg (trainer.py:149-156,174-182 / trainer3.py:27-34,53-61): generator + patch discriminator, LSGAN terms
+    "dg2d": (False, "dg", [16, 16], 2, False),
+    "dg3d": (True, "dg", [16, 16, 16], 1, False),
 }
 W1, W2, W4, W5, SPARSITY = 0.7, 1.3, 0.9, 0.5, 0.05
+W3 = 0.6
 
 
 class _Q(object):
@@ -55,9 +59,12 @@ def make_inputs(name):
     g = torch.Generator().manual_seed(SEED + sum(map(ord, name)))
     B, C = 2, (3 if is3d else 2)
     x = torch.randn(B, *spatial, C, generator=g).clamp_(-1, 1)
-    if arch == "de":
+    if arch in ("de", "dg"):
         y = torch.rand(B, 3, generator=g) * 2 - 1
         tab, _, _ = M.generator_layout(spatial + [3 if is3d else 1], FILTERS, num_conv, 0, z_dim=3, name="G")
+        if arch == "dg":
+            tab = type(tab)(tab)
+            tab.update(M.discriminator_layout(6 if is3d else 3, FILTERS, 3 if is3d else 2, "D"))
     else:
         y = torch.rand(B, P_NUM, 4, generator=g) * 2 - 1              # [B, dof, frames]; the loss uses y[:, :, -1]
         tab = M.ae_layout(spatial + [C], FILTERS, Z_NUM, num_conv, 0, name="AE")
@@ -85,15 +92,19 @@ def run_case(trainer_mod, trainer3_mod, ref_ops, name):
     t.output_shape = spatial + [3 if is3d else 1]                                  # trainer.py:48-53
     t.optimizer, t.g_lr, t.beta1, t.beta2, t.step = "adam", "g_lr-variable", 0.5, 0.999, "step-variable"
     t.w1, t.w2 = W1, W2
+    if arch == "dg":
+        t.w3 = W3
     if arch == "ae":
         t.z_num, t.use_sparse, t.sparsity, t.w4, t.w5, t.p_num = Z_NUM, use_sparse, SPARSITY, W4, W5, P_NUM
     try:
-        (cls.build_model if arch == "de" else cls.build_model_ae)(t)
+        (cls.build_model_ae if arch == "ae" else cls.build_model)(t)
         raise AssertionError("the build did not reach its first placeholder")
     except tf_shim.BuildDone:
         pass
     opt, mini = record["optimizer"], record["minimize"]
     assert opt["kind"] == "adam" and opt["args"] == ("g_lr-variable",) and opt["kwargs"] == {"beta1": 0.5, "beta2": 0.999}, opt
+    if arch == "dg":
+        return run_dg_case(name, t, record, x, y, tab, var, leaves, num_conv)
     assert mini["global_step"] == "step-variable" and mini["var_list"] == list(tab.keys()), name
     loss = mini["loss"]
     grads = torch.autograd.grad(loss, [leaves[k] for k in tab])
@@ -117,6 +128,34 @@ def run_case(trainer_mod, trainer3_mod, ref_ops, name):
     worst = max(float((g - o_grads[k]).abs().max()) for k, g in zip(tab, grads)) / scale
     assert worst <= 1e-5, (name, worst)
     out["grad_abs_sums"] = np.array([float(o_grads[k].abs().sum()) for k in tab])
+    return out, worst
+
+
+def run_dg_case(name, t, record, x, y, tab, var, leaves, num_conv):
+    """arch=dg: TWO minimize calls on ONE optimizer object (trainer.py:181,184): d_optim = minimize(d_loss, var_list=D_var)
+    without global_step, then g_optim = minimize(g_loss, global_step=step, var_list=G_var)."""
+    g_names = [k for k in tab if k.startswith("G/")]
+    d_names = [k for k in tab if k.startswith("D/")]
+    m_d, m_g = record["minimize_all"]
+    assert m_d["optimizer_id"] == m_g["optimizer_id"], "the reference uses one AdamOptimizer for both (shared beta powers)"
+    assert m_d["var_list"] == d_names and m_d["global_step"] is None and m_d["loss"] is t.d_loss
+    assert m_g["var_list"] == g_names and m_g["global_step"] == "step-variable" and m_g["loss"] is t.g_loss
+    assert list(t.G_var) == g_names and list(t.D_var) == d_names
+    losses, o_gg, o_dg = T.dg_losses_and_grads(y, x, {k: var[k] for k in g_names}, {k: var[k] for k in d_names}, FILTERS,
+                                               num_conv, 0, W1, W2, W3)
+    for k in ("g_loss", "g_loss_l1", "g_loss_j_l1", "g_loss_real", "d_loss_fake", "d_loss_real", "d_loss", "D_x", "D_G"):
+        assert torch.equal(getattr(t, k).detach(), losses[k]), (name, k)
+    gg = torch.autograd.grad(t.g_loss, [leaves[k] for k in g_names], retain_graph=True)
+    dg = torch.autograd.grad(t.d_loss, [leaves[k] for k in d_names])
+    worst = 0.0
+    for names, mine, ora in ((g_names, gg, o_gg), (d_names, dg, o_dg)):
+        scale = max(float(ora[k].abs().max()) for k in names)
+        worst = max(worst, max(float((g - ora[k]).abs().max()) for k, g in zip(names, mine)) / scale)
+    assert worst <= 1e-5, (name, worst)
+    out = {"x": x.numpy(), "y": y.numpy(), "loss": losses["g_loss"].numpy(), "d_loss": losses["d_loss"].numpy(),
+           "g_loss_real": losses["g_loss_real"].numpy(), "D_x": losses["D_x"].numpy(), "D_G": losses["D_G"].numpy(),
+           "g_grad_abs_sums": np.array([float(o_gg[k].abs().sum()) for k in g_names]),
+           "d_grad_abs_sums": np.array([float(o_dg[k].abs().sum()) for k in d_names])}
     return out, worst
 
 

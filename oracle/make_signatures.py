@@ -12,19 +12,31 @@ import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
-NAMES = ("GeneratorBE", "GeneratorBE3", "EncoderBE", "EncoderBE3", "AE", "AE3")
+NAMES = ("GeneratorBE", "GeneratorBE3", "EncoderBE", "EncoderBE3", "AE", "AE3", "DiscriminatorPatch", "DiscriminatorPatch3", "NN")
+# ops.py functions of the drop-in boundary (SURVEY.md 8b "Ops"): layer wrappers, resampling, stencils, numpy twins
+OPS_NAMES = ("lrelu", "conv2d", "conv3d", "linear", "upscale", "upscale3", "jacobian", "jacobian3", "curl",
+             "divergence", "divergence3", "vort_np", "curl_np", "grad_np", "jacobian_np3")
 
 
-def main(reference_root="/root/reference", out_dir=os.path.join(ROOT, "tests", "golden")):
-    tree = ast.parse(open(os.path.join(reference_root, "model.py")).read())
+def _signatures(path, names):
+    tree = ast.parse(open(path).read())
     out = {}
     for node in tree.body:
-        if isinstance(node, ast.FunctionDef) and node.name in NAMES:
+        if isinstance(node, ast.FunctionDef) and node.name in names:
             args = [a.arg for a in node.args.args]
             defaults = [ast.unparse(d) for d in node.args.defaults]
             pad = [None] * (len(args) - len(defaults))
             out[node.name] = {"lineno": node.lineno, "params": [[a, d] for a, d in zip(args, pad + defaults)]}
-    assert set(out) == set(NAMES), sorted(set(NAMES) - set(out))
+    assert set(out) == set(names), sorted(set(names) - set(out))
+    return out
+
+
+def main(reference_root="/root/reference", out_dir=os.path.join(ROOT, "tests", "golden")):
+    out = _signatures(os.path.join(reference_root, "model.py"), NAMES)
+    ops = _signatures(os.path.join(reference_root, "ops.py"), OPS_NAMES)
+    with open(os.path.join(out_dir, "reference_ops_signatures.json"), "w") as f:
+        json.dump(ops, f, indent=1, sort_keys=True)
+    print("written", os.path.join(out_dir, "reference_ops_signatures.json"))
     with open(os.path.join(out_dir, "reference_model_signatures.json"), "w") as f:
         json.dump(out, f, indent=1, sort_keys=True)
     print("written", os.path.join(out_dir, "reference_model_signatures.json"))

@@ -162,5 +162,31 @@ def ae_forward(x, var, filters=128, z_num=16, num_conv=4, repeat=0, name="AE", u
     return out, z
 
 
+def discriminator_layout(in_channels, filters=128, nd=2, name="D"):
+    """DiscriminatorPatch / DiscriminatorPatch3 (model.py:89-116): three stride-2 k3 convs with filters/2, filters,
+    2*filters channels, one stride-1 conv with 4*filters, one stride-1 conv to 1 channel; slim's default layer names
+    (`conv2d(x, d, k=3, act=lrelu)` passes no scope): D/Conv, D/Conv_1, ..., D/Conv_4."""
+    tab = OrderedDict()
+    cin, d = in_channels, int(filters / 2)
+    widths = [d, 2 * d, 4 * d, 8 * d, 1]
+    for i, co in enumerate(widths):
+        ln = "%s/Conv" % name if i == 0 else "%s/Conv_%d" % (name, i)
+        tab[ln + "/weights"] = (3,) * nd + (cin, co)
+        tab[ln + "/biases"] = (co,)
+        cin = co
+    return tab
+
+
+def discriminator_forward(x, var, name="D", store=None):
+    """forward of DiscriminatorPatch(3) on a channels-last tensor; strides 2,2,2,1,1; lrelu on all but the last conv"""
+    st = store if store is not None else (lambda t: t)
+    for i, stride in enumerate((2, 2, 2, 1, 1)):
+        ln = "%s/Conv" % name if i == 0 else "%s/Conv_%d" % (name, i)
+        x = R.conv_nd(x, st(var[ln + "/weights"]), var[ln + "/biases"], stride, R.lrelu if i < 4 else None)
+        if i < 4:
+            x = st(x)
+    return x
+
+
 def count_params(table):
     return int(sum(int(np.prod(s)) for s in table.values()))

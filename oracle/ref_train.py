@@ -79,6 +79,33 @@ def generator_loss_and_grads(z, x, var, filters=128, num_conv=4, repeat=0, w1=1.
     return loss.detach(), l1.detach(), jl1.detach(), g.detach(), pot.detach(), grads
 
 
+def dg_losses_and_grads(z, x, g_var, d_var, filters=128, num_conv=4, repeat=0, w1=1.0, w2=1.0, w3=1.0):
+    """One `sess.run([g_optim, d_optim])` worth of losses and gradients of arch=dg (trainer.py:138-184 /
+    trainer3.py:16-63): D sees concat(velocity, vorticity) of the target and of the generated field;
+        g_loss = w1*L1 + w2*L1(J) + w3*mean((D_G - 1)^2)            minimised over the generator variables,
+        d_loss = mean((D_x - 1)^2) + mean(D_G^2)                    minimised over the discriminator variables.
+    Returns (dict of loss scalars, generator grads, discriminator grads)."""
+    is3d = x.dim() == 5
+    gl = OrderedDict((k, v.detach().clone().requires_grad_(True)) for k, v in g_var.items())
+    dl = OrderedDict((k, v.detach().clone().requires_grad_(True)) for k, v in d_var.items())
+    pot = M.generator_forward(z, gl, list(x.shape[1:-1]) + [3 if is3d else 1], filters, num_conv, repeat, "G")
+    loss, l1, jl1, g = stencil_loss(pot, x, w1, w2, True)
+    jac = R.jacobian3 if is3d else R.jacobian
+    d_x = M.discriminator_forward(torch.cat([x, jac(x)[1]], dim=-1), dl)
+    d_g = M.discriminator_forward(torch.cat([g, jac(g)[1]], dim=-1), dl)
+    g_loss_real = ((d_g - 1) ** 2).mean()
+    d_loss_fake = (d_g ** 2).mean()
+    d_loss_real = ((d_x - 1) ** 2).mean()
+    g_loss = loss + w3 * g_loss_real
+    d_loss = d_loss_real + d_loss_fake
+    gg = torch.autograd.grad(g_loss, list(gl.values()), retain_graph=True)
+    dg = torch.autograd.grad(d_loss, list(dl.values()))
+    losses = {"g_loss": g_loss.detach(), "g_loss_l1": l1.detach(), "g_loss_j_l1": jl1.detach(), "g_loss_real": g_loss_real.detach(),
+              "d_loss_fake": d_loss_fake.detach(), "d_loss_real": d_loss_real.detach(), "d_loss": d_loss.detach(),
+              "D_x": d_x.detach(), "D_G": d_g.detach(), "pot": pot.detach(), "G_": g.detach()}
+    return losses, OrderedDict(zip(gl.keys(), gg)), OrderedDict(zip(dl.keys(), dg))
+
+
 def ae_loss_and_grads(x, y_last, var, p_num, filters=128, z_num=16, num_conv=4, repeat=0,
                       w1=1.0, w2=1.0, w4=1.0, use_curl=True, name="AE", use_sparse=False, sparsity=0.01, w5=1.0):
     """One forward+backward of `build_model_ae` (trainer.py:357-396 / trainer3.py:240-279).

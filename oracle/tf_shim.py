@@ -145,19 +145,33 @@ def install_structural(store, conv_nd, linear):
         def __init__(self, name):
             self.name = name
 
+    # slim layers called with scope=None open variable_scope(None, default_name='Conv' / 'fully_connected'): TF makes the
+    # name unique WITHIN the enclosing variable scope (Conv, Conv_1, ...) and forgets those counts when the enclosing scope
+    # closes, which is what lets DiscriminatorPatch(..., reuse=True) (model.py:89-116) find D/Conv ... D/Conv_4 again.
+    default_counts = {}
+
+    def _unique_default(default_name):
+        cnt = default_counts.setdefault("/".join(store.scopes), {})
+        i = cnt.get(default_name, 0)
+        cnt[default_name] = i + 1
+        return default_name if i == 0 else "%s_%d" % (default_name, i)
+
     @contextlib.contextmanager
     def variable_scope(name, reuse=None):
         store.scopes.append(name)
+        path = "/".join(store.scopes)
         try:
-            yield _VS("/".join(store.scopes))
+            yield _VS(path)
         finally:
+            for k in [k for k in default_counts if k == path or k.startswith(path + "/")]:
+                del default_counts[k]
             store.scopes.pop()
 
     def _conv(nd):
         def conv(x, o_dim, k, stride=1, activation_fn=None, scope=None, data_format=None):
             x = _t(x)
             assert data_format in (None, "NHWC", "NDHWC"), data_format
-            store.scopes.append(scope)
+            store.scopes.append(scope if scope is not None else _unique_default("Conv"))
             try:
                 w = store.get("weights", (k,) * nd + (x.shape[-1], o_dim))
                 b = store.get("biases", (o_dim,))
@@ -168,7 +182,7 @@ def install_structural(store, conv_nd, linear):
 
     def fully_connected(x, o_dim, activation_fn=None, scope=None):
         x = _t(x)
-        store.scopes.append(scope)
+        store.scopes.append(scope if scope is not None else _unique_default("fully_connected"))
         try:
             w = store.get("weights", (x.shape[-1], o_dim))
             b = store.get("biases", (o_dim,))
@@ -207,7 +221,8 @@ def install_training(record):
             record["optimizer"] = {"kind": self.kind, "args": args, "kwargs": kwargs}
 
         def minimize(self, loss, global_step=None, var_list=None):
-            record["minimize"] = {"loss": loss, "global_step": global_step, "var_list": list(var_list)}
+            record["minimize"] = {"loss": loss, "global_step": global_step, "var_list": list(var_list), "optimizer_id": id(self)}
+            record.setdefault("minimize_all", []).append(record["minimize"])     # arch=dg minimises twice (d_optim, g_optim)
             return "optim-op"
 
     train = _mod("tensorflow.train")

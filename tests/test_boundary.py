@@ -44,6 +44,8 @@ def test_model_builders_keep_the_reference_signatures(golden_dir):
                 assert p.default is inspect.Parameter.empty, (name, a)
             elif d == "lrelu":
                 assert p.default is M.lrelu, (name, a)
+            elif d == "tf.nn.elu":
+                assert p.default is M.elu, (name, a)
             else:
                 assert p.default == eval(d), (name, a, p.default, d)    # literals only: 'G', 4, 3, 0, False
 
@@ -182,3 +184,76 @@ def test_prepare_dirs_matches_reference_util(tmp_path, monkeypatch):
             assert ja == jb
     finally:
         os.chdir(cwd)
+
+
+def test_ops_keep_the_reference_signatures(golden_dir):
+    """ops.py of the boundary (SURVEY 8b "Ops"): same parameter names, order and literal defaults as reference ops.py
+    (fixture written by oracle/make_signatures.py from the reference source); DiscriminatorPatch(3) likewise."""
+    import inspect
+    from deepfluids_b200 import model as M, ops as O
+    ref = json.load(open(os.path.join(golden_dir, "reference_ops_signatures.json")))
+    assert {"conv2d", "conv3d", "linear", "curl", "jacobian", "jacobian3", "lrelu", "upscale", "upscale3", "divergence",
+            "divergence3", "curl_np", "vort_np", "grad_np", "jacobian_np3"} <= set(ref)
+    for name, spec in ref.items():
+        mine = list(inspect.signature(getattr(O, name)).parameters.values())
+        assert [p.name for p in mine] == [a for a, _ in spec["params"]], name
+        for p, (a, d) in zip(mine, spec["params"]):
+            if d is None:
+                assert p.default is inspect.Parameter.empty, (name, a)
+            else:
+                assert p.default == eval(d), (name, a, p.default, d)
+    refm = json.load(open(os.path.join(golden_dir, "reference_model_signatures.json")))
+    for name in ("DiscriminatorPatch", "DiscriminatorPatch3"):
+        mine = list(inspect.signature(getattr(M, name)).parameters.values())
+        assert [(p.name, None if p.default is inspect.Parameter.empty else repr(p.default)) for p in mine] == \
+               [(a, d) for a, d in refm[name]["params"]], name
+
+
+def test_variable_scope_naming_follows_slim():
+    """tf.variable_scope / slim default layer names as the reference's models rely on them: unnamed layers are `Conv`,
+    `Conv_1`, ... within their scope, re-entering the scope with reuse=True finds the same variables, creating an existing
+    variable without reuse raises, asking for a missing one under reuse raises."""
+    import pytest
+    from deepfluids_b200 import ops as O
+    st = O.reset_variables(7)
+    with O.variable_scope("D") as vs:
+        names = [O._STORE.unique_default("Conv") for _ in range(3)]
+        assert names == ["Conv", "Conv_1", "Conv_2"] and vs.name == "D"
+        with O.variable_scope("Conv"):
+            w = st.get("weights", (3, 3, 4, 8), "cpu")
+            st.get("biases", (8,), "cpu", zeros=True)
+    assert O.get_variables("D") == ["D/Conv/weights", "D/Conv/biases"] and float(O.get_variable("D/Conv/biases").abs().sum()) == 0.0
+    lim = (6.0 / (9 * 4 + 9 * 8)) ** 0.5
+    assert float(w.abs().max()) <= lim and float(w.abs().max()) > 0.5 * lim            # xavier-uniform (slim default)
+    with O.variable_scope("D", reuse=True):
+        assert O._STORE.unique_default("Conv") == "Conv"                                # counters restart on re-entry
+        with O.variable_scope("Conv"):
+            assert st.get("weights", (3, 3, 4, 8), "cpu") is w
+            with pytest.raises(ValueError, match="shape"):
+                st.get("weights", (3, 3, 4, 9), "cpu")
+        with O.variable_scope("Conv_9"):
+            with pytest.raises(ValueError, match="does not exist"):
+                st.get("weights", (3, 3, 4, 8), "cpu")
+    with O.variable_scope("D"):
+        with O.variable_scope("Conv"):
+            with pytest.raises(ValueError, match="already exists"):
+                st.get("weights", (3, 3, 4, 8), "cpu")
+    O.reset_variables()
+
+
+def test_numpy_twins_match_the_oracle():
+    """ops.vort_np / curl_np / grad_np / jacobian_np3 (reference ops.py:305-374) == the pinned oracle stencils, bit for bit"""
+    import numpy as np
+    import torch
+    from deepfluids_b200 import ops as O
+    from oracle import ref_ops as R
+    g = np.random.default_rng(3)
+    x = g.standard_normal((2, 6, 7, 2)).astype(np.float32)
+    assert np.array_equal(O.curl_np(x), R.curl(torch.from_numpy(x)).numpy())
+    assert np.array_equal(O.vort_np(x), R.jacobian(torch.from_numpy(x))[1].numpy())
+    j2 = R.jacobian(torch.from_numpy(np.repeat(x[..., :1], 2, -1)))[0].numpy()
+    assert np.array_equal(O.grad_np(x), np.stack([j2[..., 0], j2[..., 1]], -1))
+    x3 = g.standard_normal((2, 5, 6, 7, 3)).astype(np.float32)
+    j, c = O.jacobian_np3(x3)
+    jr, cr = R.jacobian3(torch.from_numpy(x3))
+    assert np.array_equal(j, jr.numpy()) and np.array_equal(c, cr.numpy())

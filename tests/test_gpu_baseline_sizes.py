@@ -183,14 +183,25 @@ def test_ae_teacher_forced_backward_rep3(spatial, B, nc):
     e_dec = OrderedDict((k, rel_l2(ae.params.g(k), tfd[k])) for k in tfd if k != last_b)
     e_dz = rel_l2(dz_dev - dz_p, gz)
     # encoder, teacher-forced with the device's dz
-    tfe = T.teacher_forced_backward_encoder(x, var, _ae_acts(ae), dz_dev, num_conv=nc - 1, name="AE/enc",
+    # the first conv's operand on the device is bf16(x) (dfl_pad_cast): teacher-forcing feeds exactly that stored tensor.
+    # Its weight gradient sum_v x[v+tap] * dpre[v] is a product of a smooth field with a derivative-like field that sums
+    # to ~0 (like a bias gradient), so it is ill-conditioned w.r.t. the 2^-9 input rounding: against the un-rounded fp32
+    # x the same kernel output differs by 2-3e-2 (reported below, bounded at 5e-2 like the bias gradients).
+    x_dev = ae.enc.xpad[..., :cin].float().cpu()
+    tfe = T.teacher_forced_backward_encoder(x_dev, var, _ae_acts(ae), dz_dev, num_conv=nc - 1, name="AE/enc",
                                             operand_round=M.bf16_round_ste)
     e_enc = OrderedDict((k, rel_l2(ae.params.g(k), tfe[k])) for k in tfe)
+    tfe32 = T.teacher_forced_backward_encoder(x, var, _ae_acts(ae), dz_dev, num_conv=nc - 1, name="AE/enc",
+                                              operand_round=M.bf16_round_ste)
+    e0_fp32 = rel_l2(ae.params.g("AE/enc/0_conv/weights"), tfe32["AE/enc/0_conv/weights"])
+    print("enc 0_conv weights vs oracle fed with fp32 x: %.2e" % e0_fp32)
+    assert e0_fp32 <= 5e-2
     assert set(e_enc) | set(e_dec) | {last_b} == set(var)
     wmax = lambda d: max((v, k) for k, v in d.items() if k.endswith("weights"))
     bmax = lambda d: max((v, k) for k, v in d.items() if k.endswith("biases"))
     report = "dec W %.2e (%s) b %.2e (%s) dz %.2e | enc W %.2e (%s) b %.2e (%s)" % (wmax(e_dec) + bmax(e_dec) + (e_dz,) + wmax(e_enc) + bmax(e_enc))
     print(report)
+    print("enc per layer:", " ".join("%s=%.1e" % (k.replace("AE/enc/", ""), v) for k, v in e_enc.items() if k.endswith("weights")))
     assert wmax(e_dec)[0] <= 2e-2 and wmax(e_enc)[0] <= 2e-2 and e_dz <= 2e-2, report
     assert bmax(e_dec)[0] <= 5e-2 and bmax(e_enc)[0] <= 5e-2, report
     # stride-2 layers really are the wide ones
