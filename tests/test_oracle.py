@@ -184,6 +184,9 @@ def test_model_structure_pinned_by_reference_source(golden_dir):
         if builder.startswith("Generator"):
             tab, _, _ = M.generator_layout(shape, G.FILTERS, kw.get("num_conv", 4), kw.get("repeat", 0), z_dim=3, name="G")
             inp = torch.rand(B, 3, generator=g) * 2 - 1
+        elif builder.startswith("Discriminator"):
+            tab = M.discriminator_layout(shape[-1], G.FILTERS, len(shape) - 1, name="D")
+            inp = torch.randn(B, *shape, generator=g)
         elif builder.startswith("Encoder"):
             tab, _ = M.encoder_layout(shape, G.FILTERS, G.Z_NUM, kw.get("num_conv", 3), kw.get("repeat", 0), name="enc")
             inp = torch.randn(B, *shape, generator=g)
@@ -198,6 +201,8 @@ def test_model_structure_pinned_by_reference_source(golden_dir):
         assert list(blob[name + "/variables"]) == list(tab.keys()), name
         if builder.startswith("Generator"):
             out = M.generator_forward(inp, var, shape, G.FILTERS, kw.get("num_conv", 4), kw.get("repeat", 0), "G")
+        elif builder.startswith("Discriminator"):
+            out = M.discriminator_forward(inp, var, "D")
         elif builder.startswith("Encoder"):
             out = M.encoder_forward(inp, var, G.FILTERS, kw.get("num_conv", 3), kw.get("repeat", 0), "enc")
         else:
@@ -230,6 +235,16 @@ def test_trainer_wiring_pinned_by_reference_source(golden_dir):
         x, y, tab, var = G.make_inputs(name)
         np.testing.assert_array_equal(x.numpy(), blob[name + "/x"])
         np.testing.assert_array_equal(y.numpy(), blob[name + "/y"])
+        if arch == "dg":
+            gv = {k: v for k, v in var.items() if k.startswith("G/")}
+            dv = {k: v for k, v in var.items() if k.startswith("D/")}
+            losses, gg, dg = T.dg_losses_and_grads(y, x, gv, dv, G.FILTERS, num_conv, 0, G.W1, G.W2, G.W3)
+            np.testing.assert_allclose(losses["g_loss"].numpy(), blob[name + "/loss"], rtol=1e-5)
+            np.testing.assert_allclose(losses["d_loss"].numpy(), blob[name + "/d_loss"], rtol=1e-5)
+            np.testing.assert_allclose(losses["D_G"].numpy(), blob[name + "/D_G"], rtol=1e-4, atol=1e-6)
+            np.testing.assert_allclose([float(gg[k].abs().sum()) for k in gv], blob[name + "/g_grad_abs_sums"], rtol=1e-4, atol=1e-7)
+            np.testing.assert_allclose([float(dg[k].abs().sum()) for k in dv], blob[name + "/d_grad_abs_sums"], rtol=1e-4, atol=1e-7)
+            continue
         if arch == "de":
             loss, l1, jl1, _, _, grads = T.generator_loss_and_grads(y, x, var, G.FILTERS, num_conv, 0, G.W1, G.W2, True, "G")
         else:
