@@ -33,7 +33,7 @@ def to_blocks(x):
     """[B,(D,)H,W,C] fp32 / bf16 -> (bf16 channel blocks [nb*B,(D,)H,W,128] zero padded, nb)"""
     B, C = x.shape[0], x.shape[-1]
     nb = _cdiv(C, 128)
-    if nb == 1 and x.dtype == torch.float32:
+    if C <= 8 and x.dtype == torch.float32:              # dfl_pad_cast: the 2..6-channel network inputs
         out = torch.empty(x.shape[:-1] + (128,), dtype=BF, device=x.device)
         K.pad_cast(x.contiguous(), out)
         return out, 1
