@@ -412,8 +412,10 @@ __global__ void jacobian2d_kernel(const T* __restrict__ v, T* __restrict__ jac, 
       d[2 * c] = ldf(v + (px0 + 1) * 2 + c) - ldf(v + px0 * 2 + c);
       d[2 * c + 1] = ldf(v + (py0 + W) * 2 + c) - ldf(v + py0 * 2 + c);
     }
+    if (jac) {
 #pragma unroll
-    for (int k = 0; k < 4; ++k) stf(jac + idx * 4 + k, d[k]);
+      for (int k = 0; k < 4; ++k) stf(jac + idx * 4 + k, d[k]);
+    }
     if (vort) stf(vort + idx, d[2] - d[1]);
   }
 }
