@@ -23,6 +23,8 @@ SIGNATURES = {
     "dfl_curl_bwd": (_i, [_vp, _vp, _dims, _i, _i, _vp]),
     "dfl_jacobian_bwd": (_i, [_vp, _vp, _vp, _dims, _i, _vp]),
     "dfl_mse_loss": (_i, [_vp, _f, _vp, _vp, _sz, _f, _vp]),
+    "dfl_l1_loss_workspace_bytes": (_sz, []),
+    "dfl_l1_loss": (_i, [_vp, _vp, _vp, _vp, _sz, _f, _i, _vp, _vp]),
     "dfl_gemm_f32": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
     "dfl_colsum_f32": (_i, [_vp, _vp, _i, _i, _vp]),
     "dfl_stencil_loss_workspace_bytes": (_sz, [_dims, _i]),

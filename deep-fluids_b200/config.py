@@ -83,6 +83,10 @@ b200_arg.add_argument('--precision', type=str, default='bf16', choices=['bf16', 
                       help="conv arithmetic: 'bf16' operands/activations, or 'fp32x3' = fp32-grade via split bf16 "
                            "operands (hi/lo pairs, 3 MMA terms, fp32 accumulate) matching the reference's fp32 graphs")
 
+b200_arg.add_argument('--grad_accum', type=int, default=1,
+                      help='micro-batches of batch_size samples per optimizer step (strong scaling at a fixed global batch: '
+                           'gradients are summed on the device, ONE all-reduce and ONE Adam update per optimizer step)')
+
 
 def get_config(argv=None):
     config, unparsed = parser.parse_known_args(argv)

@@ -64,6 +64,9 @@ int fwd_stencils(int op, int nd, const int64_t* dims, const void* in, int in_cs,
 int bwd_stencils(int op, int nd, const int64_t* dims, const float* g0, const float* g1, float* out, int out_cs,
                  cudaStream_t st);
 int mse_loss(const float* d, float target, float* loss, float* dd, size_t n, float scale, cudaStream_t st);
+size_t l1_loss_workspace_bytes();
+int l1_loss(const float* a, const float* b, float* loss, float* dd, size_t n, float scale, int accumulate, void* ws,
+            cudaStream_t st);
 int gemm_f32(const float* A, const float* B, const float* bias, float* C, int M, int N, int K, int transA, int transB,
              int accumulate, cudaStream_t st);
 int colsum_f32(const float* x, float* out, int M, int N, cudaStream_t st);
@@ -163,6 +166,11 @@ int dfl_jacobian_bwd(const float* djac, const float* daux, float* dvel, const in
 }
 int dfl_mse_loss(const float* d, float target, float* loss, float* dd, size_t n, float scale, void* stream) {
   return mse_loss(d, target, loss, dd, n, scale, ST(stream));
+}
+size_t dfl_l1_loss_workspace_bytes(void) { return l1_loss_workspace_bytes(); }
+int dfl_l1_loss(const float* a, const float* b, float* loss, float* dd, size_t n, float scale, int accumulate,
+                void* workspace, void* stream) {
+  return l1_loss(a, b, loss, dd, n, scale, accumulate, workspace, ST(stream));
 }
 int dfl_gemm_f32(const float* A, const float* B, const float* bias, float* C, int M, int N, int K, int transA, int transB,
                  int accumulate, void* stream) {

@@ -116,6 +116,57 @@ int mse_loss(const float* d, float target, float* loss, float* dd, size_t n, flo
   return DFL_OK;
 }
 
+// L1 term of the loss when it is NOT fused with the curl (use_curl=False, trainer.py:141-144,170-171): loss = mean|a - b|,
+// dd (+)= scale * sgn(a - b) / n.  Per-block fp64 partials, summed in block order by the last block to finish (atomic
+// ticket) -> deterministic.  workspace: (L1_MAX_BLOCKS + 1) doubles, zeroed by the caller once (the ticket resets itself).
+constexpr int L1_MAX_BLOCKS = 1024;
+__global__ void __launch_bounds__(256) l1_loss_kernel(const float* __restrict__ a, const float* __restrict__ b,
+                                                      float* __restrict__ loss, float* __restrict__ dd, size_t n, float scale,
+                                                      int accumulate, double* __restrict__ ws) {
+  __shared__ double sred[8];
+  __shared__ bool last;
+  double acc = 0.0;
+  const float k = scale / static_cast<float>(n);
+  for (size_t i = blockIdx.x * 256ull + threadIdx.x; i < n; i += 256ull * gridDim.x) {
+    const float e = a[i] - b[i];
+    acc += fabsf(e);
+    if (dd) {
+      const float g = k * ((e > 0.f ? 1.f : 0.f) - (e < 0.f ? 1.f : 0.f));
+      dd[i] = accumulate ? dd[i] + g : g;
+    }
+  }
+  acc = warp_sum(acc);
+  if ((threadIdx.x & 31) == 0) sred[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0;
+    for (int i = 0; i < 8; ++i) t += sred[i];
+    ws[1 + blockIdx.x] = t;
+    __threadfence();
+    unsigned long long* ticket = reinterpret_cast<unsigned long long*>(ws);
+    last = (atomicAdd(ticket, 1ull) == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (last && threadIdx.x == 0) {
+    __threadfence();
+    double t = 0;
+    for (unsigned i = 0; i < gridDim.x; ++i) t += reinterpret_cast<volatile double*>(ws)[1 + i];
+    *loss = static_cast<float>(t / static_cast<double>(n));
+    *reinterpret_cast<unsigned long long*>(ws) = 0ull;
+  }
+}
+
+size_t l1_loss_workspace_bytes() { return (L1_MAX_BLOCKS + 1) * sizeof(double); }
+
+int l1_loss(const float* a, const float* b, float* loss, float* dd, size_t n, float scale, int accumulate, void* ws,
+            cudaStream_t st) {
+  DFL_REQUIRE(a && b && loss && ws && n > 0, "l1_loss: null tensor or empty");
+  const int grid = static_cast<int>(std::min<size_t>((n + 255) / 256, std::min<size_t>(L1_MAX_BLOCKS, static_cast<size_t>(num_sms()) * 4)));
+  l1_loss_kernel<<<grid, 256, 0, st>>>(a, b, loss, dd, n, scale, accumulate, static_cast<double*>(ws));
+  DFL_LAUNCH_OK("l1_loss_kernel");
+  return DFL_OK;
+}
+
 // op 0: dpot = curl^T(dvel) (2D: dpot_cs channels, 3D: 3);  op 1: dvel = jacobian^T(dj, daux)
 int bwd_stencils(int op, int nd, const int64_t* dims, const float* g0, const float* g1, float* out, int out_cs,
                  cudaStream_t st) {

@@ -5,7 +5,8 @@ The reference's FIFOQueue + GIL-bound npz loader threads (data.py:110-159) are r
 tensor source of identical shape and range: params y ~ U[-1,1] [B,c_num], target velocity x = curl of
 a smoothed random potential scaled to max|x| = 1 (mirrors x /= x_range, data.py:329).  A pool of `pool` distinct
 batches is generated once with the seeded generator and served round-robin.  Real-dataset loading (args.txt,
-v/*.npz) is SURVEY 8(f) row N2, not built yet."""
+v/*.npz) is `DatasetBatchManager` below: the reference's file order, ranges and normalisation, loader
+threads feeding pinned host batches one step ahead."""
 import os
 
 import torch
@@ -267,6 +268,17 @@ class DatasetBatchManager(object):
             for i, ri in enumerate(self.y_range):
                 y[..., i] = (y[..., i] + 1) * 0.5 * (ri[1] - ri[0]) + ri[0]
         return x, y
+
+    def batch_(self, b_num):
+        """the whole dataset in FILE ORDER, b_num normalised fields at a time (data.py:173-183; test_ae's latent dump)"""
+        assert len(self.paths) % b_num == 0
+        xb = []
+        for i, path in enumerate(self.paths):
+            x, _ = preprocess(path, self.data_type, self.x_range, self.y_range)
+            xb.append(x)
+            if (i + 1) % b_num == 0:
+                yield np.array(xb), []
+                xb = []
 
     def random_list(self, num):
         xs, ys = [], []

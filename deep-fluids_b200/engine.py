@@ -79,7 +79,7 @@ class GeneratorEngine(object):
 
     def __init__(self, batch, output_shape, z_dim=3, filters=128, num_conv=4, repeat=0, name="G", device=None,
                  seed=123, init=None, inference=False):
-        assert filters == 128, "the tensor-core conv kernels are specialised for filters=128 (config.py:21 default)"
+        assert filters == 128, "the fused engine is specialised for filters=128 (config.py:21 default); other widths run ops_engine.OpsGeneratorEngine"
         self.device = device or torch.device("cuda", torch.cuda.current_device())
         self.B, self.name, self.filters, self.num_conv = int(batch), name, filters, int(num_conv)
         self.spatial = [int(s) for s in output_shape[:-1]]
@@ -252,7 +252,17 @@ class GeneratorEngine(object):
                 dpre = self._gview(1, i - 1)
                 K.pool_mask(gx0, self.y[i - 1][nc - 1], ds, dpre)
             else:
-                K.fc_bwd(self.z, gx0.view(self.B, -1), P.g(self.name + "/0_fc/weights"), P.g(self.name + "/0_fc/biases"))
+                gw, gb = P.g(self.name + "/0_fc/weights"), P.g(self.name + "/0_fc/biases")
+                if getattr(self, "accumulate_fc", False):
+                    # dfl_fc_bwd OVERWRITES its outputs; under gradient accumulation (several backward passes per
+                    # optimizer step) the FC gradient goes through a scratch pair and is added
+                    if getattr(self, "_fc_scratch", None) is None:
+                        self._fc_scratch = (torch.empty_like(gw), torch.empty_like(gb))
+                    K.fc_bwd(self.z, gx0.view(self.B, -1), *self._fc_scratch)
+                    gw.add_(self._fc_scratch[0])
+                    gb.add_(self._fc_scratch[1])
+                else:
+                    K.fc_bwd(self.z, gx0.view(self.B, -1), gw, gb)
                 if dz is not None:
                     K.fc_dz(gx0.view(self.B, -1), P.p(self.name + "/0_fc/weights"), dz, accumulate=True)
 

@@ -112,6 +112,45 @@ def mse_loss(dvals, target, scale=1.0, want_grad=True):
     return loss, dd
 
 
+_L1_WS = {}
+
+
+def l1_loss(a, b, scale=1.0, dd=None, accumulate=False, want_grad=True):
+    """(mean|a - b| as a 1-element tensor, dd (+)= scale * sgn(a - b) / n): the un-fused L1 term (use_curl=False)"""
+    assert a.dtype == torch.float32 and b.dtype == torch.float32 and a.shape == b.shape
+    ws = _L1_WS.get(a.device)
+    if ws is None:
+        ws = _L1_WS[a.device] = torch.zeros(cabi.lib().dfl_l1_loss_workspace_bytes(), dtype=torch.uint8, device=a.device)
+    loss = torch.empty(1, dtype=torch.float32, device=a.device)
+    if dd is None and want_grad:
+        assert not accumulate
+        dd = torch.empty_like(a)
+    PROF.timed("l1_loss", 0.0, lambda: check(cabi.lib().dfl_l1_loss(_p(a), _p(b), _p(loss), _p(dd), a.numel(), float(scale),
+                                                                  int(accumulate), _p(ws), _st())))
+    return loss, dd
+
+
+def velocity_loss_fwdbwd(vel, x, w1=1.0, w2=1.0, dvel=None, loss3=None):
+    """use_curl=False (trainer.py:141-144,170-172): the network output IS the velocity G_.
+    loss = w1*mean|G_ - x| + w2*mean|J(G_) - J(x)|;  -> (loss3 [total, l1, jl1], d loss / d G_).  Un-fused sequence of the
+    standalone kernels: jacobian (x2), L1 (x2), jacobian adjoint."""
+    vel, x = vel.contiguous(), x.contiguous()
+    jv, _ = jacobian_fwd(vel, want_aux=False)
+    jx, _ = jacobian_fwd(x, want_aux=False)
+    jl1, gj = l1_loss(jv, jx, w2)
+    g = jacobian_bwd(gj, None)
+    if dvel is not None:
+        dvel.copy_(g)
+        g = dvel
+    l1, _ = l1_loss(vel, x, w1, dd=g, accumulate=True)
+    if loss3 is None:
+        loss3 = torch.empty(3, dtype=torch.float32, device=vel.device)
+    loss3[1:2].copy_(l1)
+    loss3[2:3].copy_(jl1)
+    loss3[0:1].copy_(w1 * l1 + w2 * jl1)
+    return loss3, g
+
+
 def stencil_loss_fwdbwd(pot, x, w1=1.0, w2=1.0, grad_scale=1.0, want_vel=False, dpot=None, loss3=None, workspace=None):
     """-> (loss3 [total,l1,jl1] float32 device tensor, dpot, vel|None).  If `dpot` is given with more than one channel in
     2D, the gradient is written full-shape (channel 0 = d/d psi, the rest 0)."""

@@ -7,17 +7,101 @@ the ordered TF-named variable list.  `EncoderBE(3)(x, filters, z_num, ...) -> (z
 `AE(3)(x, filters, z_num, ...) -> (out, z, variables)` likewise.  The engine object (buffers, weights) is cached per `name`
 so `reuse=True` re-applies the same variables, as tf.variable_scope(reuse=True) does.
 """
+import numpy as np
+import torch
+
 from .engine import GeneratorEngine
-from .ops import conv2d, conv3d, get_variables, lrelu, variable_scope
+from .ops import conv2d, conv3d, get_variables, linear, lrelu, upscale, upscale3, variable_scope
 
 _ENGINES = {}
 
 
+# ---------------------------------------------------------------------------------------------------------------------
+# General form on the differentiable ops-level layers (ops.py / layers.py): any `filters`, skip_concat, any scope.  The
+# fused engines below cover the configuration every BASELINE workload uses (filters=128, skip_concat=False); everything
+# else a reference recipe can ask for (run.bat:56,73 train the AE with filters=64; skip_concat is a model.py option) runs
+# here, layer by layer, on the same tensor-core kernels (channels zero-padded to 128-blocks), with torch autograd as the
+# tape.  The model functions keep the statement order of reference model.py:5-87 / :118-216.
+# ---------------------------------------------------------------------------------------------------------------------
+def _repeat_num(spatial, repeat):
+    rep = int(np.log2(np.max(spatial))) - 2 if repeat == 0 else repeat
+    assert rep > 0 and sum(int(i) % (2 ** (rep - 1)) for i in spatial) == 0
+    return rep
+
+
+def generator_ops(z, filters, output_shape, name='G', num_conv=4, conv_k=3, last_k=3, repeat=0, skip_concat=False,
+                  act=lrelu, reuse=False):
+    nd = len(output_shape) - 1
+    conv, up = (conv2d, lambda t: upscale(t, 2)) if nd == 2 else (conv3d, lambda t: upscale3(t, 2))
+    with variable_scope(name, reuse=reuse) as vs:
+        rep = _repeat_num(output_shape[:-1], repeat)
+        x0_shape = [int(i // 2 ** (rep - 1)) for i in output_shape[:-1]] + [filters]
+        n = 0
+        x = linear(z, int(np.prod(x0_shape)), name='%d_fc' % n)
+        n += 1
+        x = x.reshape([z.shape[0]] + x0_shape)
+        x0 = x
+        for idx in range(rep):
+            for _ in range(num_conv):
+                x = conv(x, filters, k=conv_k, s=1, act=act, name='%d_conv' % n)
+                n += 1
+            if idx < rep - 1:
+                if skip_concat:                          # model.py:30-33 / :72-75
+                    x, x0 = up(x), up(x0)
+                    x = torch.cat([x, x0.to(x.dtype)], dim=-1)
+                else:                                    # model.py:35-37 / :77-79
+                    x = up(x + x0.to(x.dtype))
+                    x0 = x
+            elif not skip_concat:
+                x = x + x0.to(x.dtype)
+        out = conv(x, output_shape[-1], k=last_k, s=1, name='%d_conv' % n)
+    return out, get_variables(vs)
+
+
+def encoder_ops(x, filters, z_num, name='enc', num_conv=4, conv_k=3, repeat=0, act=lrelu, reuse=False):
+    nd = x.dim() - 2
+    conv = conv2d if nd == 2 else conv3d
+    with variable_scope(name, reuse=reuse) as vs:
+        rep = _repeat_num(list(x.shape[1:-1]), repeat)
+        n = 0
+        x = conv(x, filters, k=conv_k, s=1, act=act, name='%d_conv' % n)
+        n += 1
+        x0 = x
+        ch = filters
+        for idx in range(rep):
+            for _ in range(num_conv):
+                x = conv(x, filters, k=conv_k, s=1, act=act, name='%d_conv' % n)
+                n += 1
+            x = torch.cat([x, x0], dim=-1)               # model.py:144 / :180
+            ch += filters
+            if idx < rep - 1:
+                x = conv(x, ch, k=conv_k, s=2, act=act, name='%d_conv' % n)
+                n += 1
+                x0 = x
+        out = linear(x.reshape(x.shape[0], -1).float(), z_num, name='%d_fc' % n)
+    return out, get_variables(vs)
+
+
+def ae_ops(x, filters, z_num, name='AE', num_conv=4, conv_k=3, last_k=3, repeat=0, act=lrelu, skip_concat=False,
+           use_sparse=False, reuse=False):
+    with variable_scope(name, reuse=reuse) as vs:
+        z, _ = encoder_ops(x, filters, z_num, 'enc', num_conv - 1, conv_k, repeat, act, reuse)
+        if use_sparse:
+            z = torch.sigmoid(z)
+        out, _ = generator_ops(z, filters, list(x.shape[1:]), 'dec', num_conv, conv_k, last_k, repeat, skip_concat, act, reuse)
+    return out, z, get_variables(vs)
+
+
+def _needs_ops_path(filters, skip_concat):
+    return filters != 128 or bool(skip_concat)
+
+
 def _generator(z, filters, output_shape, name, num_conv, conv_k, last_k, repeat, skip_concat, act, reuse, nd):
     assert conv_k == 3 and last_k == 3, "k=3 only (the reference never uses another size on this path)"
-    assert not skip_concat, "skip_concat=True is never enabled by the reference's trainers"
     assert act is lrelu
     assert len(output_shape) == nd + 1
+    if _needs_ops_path(filters, skip_concat):
+        return generator_ops(z, filters, list(output_shape), name, num_conv, conv_k, last_k, repeat, skip_concat, act, reuse)
     key = (name, nd)
     eng = _ENGINES.get(key)
     if eng is None or not reuse or eng.B != z.shape[0]:
@@ -77,6 +161,8 @@ def _encoder(x, filters, z_num, name, num_conv, conv_k, repeat, act, reuse, nd):
     assert conv_k == 3, "k=3 only (the reference never uses another size on this path)"
     assert act is lrelu
     assert x.dim() == nd + 2, "x must be channels-last [B,(D,)H,W,C]"
+    if _needs_ops_path(filters, False):
+        return encoder_ops(x, filters, z_num, name, num_conv, conv_k, repeat, act, reuse)
     key = (name, nd, "enc")
     eng = _ENGINES.get(key)
     if eng is None or not reuse or eng.B != x.shape[0]:
@@ -97,9 +183,10 @@ def EncoderBE3(x, filters, z_num, name='enc', num_conv=3, conv_k=3, repeat=0, ac
 def _ae(x, filters, z_num, name, num_conv, conv_k, last_k, repeat, act, skip_concat, use_sparse, reuse, nd):
     from .encoder import AEEngine
     assert conv_k == 3 and last_k == 3, "k=3 only"
-    assert not skip_concat, "skip_concat=True is never enabled by the reference's trainers"
     assert act is lrelu
     assert x.dim() == nd + 2, "x must be channels-last [B,(D,)H,W,C]"
+    if _needs_ops_path(filters, skip_concat):
+        return ae_ops(x, filters, z_num, name, num_conv, conv_k, last_k, repeat, act, skip_concat, use_sparse, reuse)
     key = (name, nd, "ae")
     eng = _ENGINES.get(key)
     if eng is None or not reuse or eng.enc.B != x.shape[0]:

@@ -14,6 +14,7 @@ differentiable layer ops (ops.py / layers.py).  Out of scope here: ar
 """
 import math
 import os
+import time
 
 import numpy as np
 import torch
@@ -105,15 +106,24 @@ class Trainer(object):
 
     # ------------------------------------------------------------------ build (trainer.py:136-184)
     def build_model(self):
-        if not self.use_c:
-            raise NotImplementedError("use_curl=False output path is not built yet (BASELINE configs all use curl)")
         if self.optimizer not in ('adam', 'gd'):
             raise Exception("[!] Invalid opimizer")              # sic, trainer.py:167
         self.precision = getattr(self.config, "precision", "bf16")
-        self._engine_cls = GeneratorEngineFP32 if self.precision == "fp32x3" else GeneratorEngine
-        self.engine = self._engine_cls(self.b_num, self.output_shape, z_dim=self.c_num, filters=self.filters,
-                                       num_conv=self.num_conv, repeat=self.repeat, name="G", device=self.device,
-                                       seed=self.config.random_seed)
+        self.accum = max(1, int(getattr(self.config, "grad_accum", 1)))     # micro-batches per optimizer step (strong scaling)
+        if self.filters != 128:
+            # run.bat:56,73-style widths: the general ops-level engine (same kernels, channels padded to 128-blocks)
+            from .ops_engine import OpsGeneratorEngine
+            if self.precision != "bf16":
+                raise NotImplementedError("filters=%d runs the bf16 ops-level engine (precision=%s requested)" % (self.filters, self.precision))
+            self._engine_cls = None
+            self.engine = OpsGeneratorEngine(self.b_num, self.output_shape, z_dim=self.c_num, filters=self.filters,
+                                             num_conv=self.num_conv, repeat=self.repeat, name="G", device=self.device,
+                                             seed=self.config.random_seed)
+        else:
+            self._engine_cls = GeneratorEngineFP32 if self.precision == "fp32x3" else GeneratorEngine
+            self.engine = self._engine_cls(self.b_num, self.output_shape, z_dim=self.c_num, filters=self.filters,
+                                           num_conv=self.num_conv, repeat=self.repeat, name="G", device=self.device,
+                                           seed=self.config.random_seed)
         self.G_var = self.engine.variables
         self.g_optim = self.train_step          # `sess.run(self.g_optim)` == `self.g_optim()` (trainer.py:184,269)
         self.G_s = self.engine.pot
@@ -123,9 +133,14 @@ class Trainer(object):
         self._ws = torch.empty(nb, dtype=torch.uint8, device=self.device)
         self.G_ = None
         self.g_loss = self.g_loss_l1 = self.g_loss_j_l1 = None
-        self.use_graph = bool(int(os.environ.get("DFL_CUDA_GRAPH", "1")))
+        self.use_graph = bool(int(os.environ.get("DFL_CUDA_GRAPH", "1"))) and self._engine_cls is not None
         self._captured = False
         self._xs = self._ys = None
+        if self.accum > 1:
+            if self._engine_cls is not GeneratorEngine or 'dg' in self.arch:
+                raise NotImplementedError("gradient accumulation is built for the bf16 fused generator engine (arch=de)")
+            self.engine.accumulate_fc = True
+            self._loss3_acc = torch.zeros_like(self._loss3)
         if 'dg' in self.arch:
             self._build_discriminator()
 
@@ -215,14 +230,27 @@ class Trainer(object):
         return self.g_loss, l[1], l[2], adv, fake, real, self.d_loss
 
     # ------------------------------------------------------------------ one `sess.run(self.g_optim)`
-    def _step_body_a(self, x, y, want_vel=False):
+    def _loss_and_grad(self, pot, x, want_vel=False):
+        """loss terms + d loss / d (network output).  use_curl (trainer.py:138-140 / trainer3.py:16-18): ONE fused kernel
+        (curl, both Jacobians, both L1 means and their adjoints).  use_curl=False (trainer.py:141-144): the output is the
+        velocity itself -- nothing to fuse the curl with; un-fused standalone kernels."""
+        if self.use_c:
+            _, _, vel = K.stencil_loss_fwdbwd(pot, x, self.w1, self.w2, 1.0, want_vel=want_vel, dpot=self._dpot,
+                                              loss3=self._loss3, workspace=self._ws)
+            return vel
+        K.velocity_loss_fwdbwd(pot, x, self.w1, self.w2, dvel=self._dpot, loss3=self._loss3)
+        return pot
+
+    def _step_body_a(self, x, y, want_vel=False, zero=True):
         """zero grads, forward, fused loss + dL/dpot, backward (everything before the gradient exchange)"""
         eng = self.engine
-        eng.zero_grad()
+        if zero:
+            eng.zero_grad()
         pot = eng.forward(y)
-        _, _, vel = K.stencil_loss_fwdbwd(pot, x, self.w1, self.w2, 1.0, want_vel=want_vel, dpot=self._dpot,
-                                          loss3=self._loss3, workspace=self._ws)
+        vel = self._loss_and_grad(pot, x, want_vel)
         eng.backward(self._dpot)
+        if self.accum > 1:
+            self._loss3_acc.add_(self._loss3)
         return vel
 
     def _step_body_b(self, scale):
@@ -235,7 +263,7 @@ class Trainer(object):
         self._xs.copy_(self.x)
         self._ys.copy_(self.y)
         self._lr_dev = torch.zeros(1, dtype=torch.float32, device=self.device)
-        scale = 1.0 / self.world
+        scale = 1.0 / (self.world * self.accum)
         # one eager pass on a side stream: sets every kernel's attributes, warms allocator (grad buffers stay zeroed
         # at the end because lr = 0 leaves the weights untouched)
         m0, v0 = self.engine.params.m.clone(), self.engine.params.v.clone()   # (a resumed run has non-zero moments)
@@ -249,14 +277,18 @@ class Trainer(object):
         self.engine.params.m.copy_(m0)
         self.engine.params.v.copy_(v0)
         del m0, v0
+        if self.accum > 1:
+            self.engine.zero_grad()
+            self._loss3_acc.zero_()
         l0 = K.PROF.launches
         self._graph_a = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self._graph_a):
-            self._step_body_a(self._xs, self._ys)
-            if self.world == 1:
+            # with gradient accumulation graph_a is ONE micro-batch (no zeroing, no update): it is replayed accum times
+            self._step_body_a(self._xs, self._ys, zero=(self.accum == 1))
+            if self.world == 1 and self.accum == 1:
                 self._step_body_b(scale)
         self._graph_b = None
-        if self.world > 1:
+        if self.world > 1 or self.accum > 1:
             self._graph_b = torch.cuda.CUDAGraph()
             with torch.cuda.graph(self._graph_b):
                 self._step_body_b(scale)
@@ -284,14 +316,31 @@ class Trainer(object):
             # read when the STREAM reaches the copy, so a host running ahead would overwrite it: step k would see the
             # lr_t of step k+n.)
             self._lr_dev.fill_(float(lr_t))
-            self._graph_a.replay()
+            if self.accum > 1:
+                # strong scaling: one optimizer step over `accum` micro-batches of b_num samples each (gradients summed in
+                # params.grad, the mean's 1/accum folded into the Adam kernel's grad_scale), ONE all-reduce per optimizer step
+                eng.params.grad.zero_()
+                self._loss3_acc.zero_()
+                self._graph_a.replay()
+                for _ in range(self.accum - 1):
+                    xm, ym = self.batch_manager.batch()
+                    self._xs.copy_(xm, non_blocking=True)
+                    self._ys.copy_(ym, non_blocking=True)
+                    self._graph_a.replay()
+                self._loss3.copy_(self._loss3_acc / self.accum)
+                K.PROF.launches += self.launches_per_step * (self.accum - 1)
+            else:
+                self._graph_a.replay()
             if self._graph_b is not None:
-                dp.allreduce_grads_(eng.params.grad)     # ONE NCCL all-reduce over the flat gradient buffer
+                if self.world > 1:
+                    dp.allreduce_grads_(eng.params.grad)     # ONE NCCL all-reduce over the flat gradient buffer
                 self._graph_b.replay()
             K.PROF.launches += self.launches_per_step
             self.step += 1
             return self._loss3
-        # ---- eager path (debug / per-kernel timing / want_vel) ----
+        # ---- eager path (debug / per-kernel timing / want_vel / ops-level engine) ----
+        if self.accum > 1:
+            raise NotImplementedError("gradient accumulation runs through the captured step (DFL_CUDA_GRAPH=1)")
         vel = self._step_body_a(x, y, want_vel)
         if want_vel:
             self.G_ = vel
@@ -326,6 +375,20 @@ class Trainer(object):
         else:
             self.train_()
 
+    def _checkpoint(self):
+        if self.model_dir and self.rank == 0:
+            self.save(os.path.join(self.model_dir, 'model.pt'))
+            self.save_tf(self.model_dir)          # saver.save(sess, model_dir/model.ckpt, global_step=step), trainer.py:291-292
+
+    def _periodic_checkpoint(self):
+        """tf.train.Supervisor(save_model_secs=self.save_sec) (trainer.py:110-118): a checkpoint every save_sec seconds"""
+        now = time.time()
+        if not hasattr(self, "_last_save"):
+            self._last_save = now
+        elif self.save_sec and now - self._last_save >= self.save_sec:
+            self._checkpoint()
+            self._last_save = now
+
     def train_(self):
         for step in range(self.start_step, self.max_step):
             self.train_step()
@@ -336,21 +399,26 @@ class Trainer(object):
                 if self.rank == 0:
                     print("\n[{}/{}/ep{:.2f}] Loss: {:.6f}".format(step, self.max_step, ep, loss))
             self.update_lr(step)
-        if self.model_dir and self.rank == 0:
-            self.save(os.path.join(self.model_dir, 'model.pt'))
-            self.save_tf(self.model_dir)          # saver.save(sess, model_dir/model.ckpt, global_step=step), trainer.py:291-292
+            self._periodic_checkpoint()
+        self._checkpoint()
         self.batch_manager.stop_thread()
 
     # ------------------------------------------------------------------ auto-encoder (trainer.py:357-462, trainer3.py:240-345)
     def build_model_ae(self):
         from .encoder import AEEngine
-        if not self.use_c:
-            raise NotImplementedError("use_curl=False is not built")
         if self.optimizer not in ('adam', 'gd'):
             raise Exception("[!] Invalid opimizer")
+        if getattr(self.config, "grad_accum", 1) > 1:
+            raise NotImplementedError("gradient accumulation is built for arch=de")
+        self.accum = 1
         x_shape = list(self.x.shape[1:])
-        self.ae = AEEngine(self.b_num, x_shape, self.filters, self.z_num, self.num_conv, self.repeat, "AE", self.device,
-                           self.config.random_seed, use_sparse=self.use_sparse)
+        if self.filters != 128:      # run.bat:56,73 (--filters=64): the general ops-level engine
+            from .ops_engine import OpsAEEngine
+            self.ae = OpsAEEngine(self.b_num, x_shape, self.filters, self.z_num, self.num_conv, self.repeat, "AE", self.device,
+                                  self.config.random_seed, use_sparse=self.use_sparse)
+        else:
+            self.ae = AEEngine(self.b_num, x_shape, self.filters, self.z_num, self.num_conv, self.repeat, "AE", self.device,
+                               self.config.random_seed, use_sparse=self.use_sparse)
         self.engine = self.ae                        # checkpoint / DP code paths use `.engine.params`
         self.var = self.ae.variables
         self.optim = self.train_step_ae         # `sess.run(self.optim)` == `self.optim()` (trainer.py:396,437)
@@ -374,7 +442,7 @@ class Trainer(object):
         y_last = y[:, :, -1].contiguous() if y.dim() == 3 else y[:, -self.p_num:].contiguous()
         ae.zero_grad()
         pot, z = ae.forward(x)
-        K.stencil_loss_fwdbwd(pot, x, self.w1, self.w2, 1.0, dpot=self._dpot, loss3=self._loss3, workspace=self._ws)
+        self._loss_and_grad(pot, x)       # use_curl: x_ = curl(s) (trainer.py:359-361); else x_ = the decoder output (:363)
         K.ae_loss_p(z, y_last, ae.dz, self._loss_p, self.w4)
         ae.backward(self._dpot, self.p_num, self.sparsity, self.w5)
         scale = dp.allreduce_grads_(ae.params.grad)
@@ -395,12 +463,24 @@ class Trainer(object):
     def encode(self, x):
         """latent codes z [n, z_num] of velocity fields x [n,(D,)H,W,C]  (`sess.run(self.z, {self.x: x})`, trainer.py:504)"""
         x = torch.as_tensor(x, dtype=torch.float32, device=self.device)
-        return torch.cat([self.ae.enc.forward(c)[:k].clone() for c, k in self._chunks(x)])
+        with torch.no_grad():
+            return torch.cat([self._encode_chunk(c)[:k].clone() for c, k in self._chunks(x)])
+
+    def _encode_chunk(self, c):
+        if hasattr(self.ae.enc, "forward"):
+            z = self.ae.enc.forward(c)
+            if self.use_sparse:                       # model.py:196 / :210: the code IS the sigmoid output
+                zs = torch.empty_like(z)
+                K.ae_sigmoid(z, zs)
+                z = zs
+            return z
+        return self.ae.forward(c)[1]
 
     def decode(self, z):
         """velocity fields from latent codes (`sess.run(self.x_, {self.z: z})`, trainer.py:551-552), normalised units"""
         z = torch.as_tensor(z, dtype=torch.float32, device=self.device)
-        return torch.cat([K.curl_fwd(self.ae.dec.forward(c))[:k].clone() for c, k in self._chunks(z)])
+        with torch.no_grad():
+            return torch.cat([self._velocity(self.ae.dec.forward(c))[:k].clone() for c, k in self._chunks(z)])
 
     def autoencode(self, x):
         return self.decode(self.encode(x))
@@ -425,9 +505,8 @@ class Trainer(object):
                 if self.rank == 0:
                     print("\n[{}/{}/ep{:.2f}] Loss: {:.6f}".format(step, self.max_step, ep, loss))
             self.update_lr(step)
-        if self.model_dir and self.rank == 0:
-            self.save(os.path.join(self.model_dir, 'model.pt'))
-            self.save_tf(self.model_dir)          # saver.save(sess, model_dir/model.ckpt, global_step=step), trainer.py:291-292
+            self._periodic_checkpoint()
+        self._checkpoint()
         self.batch_manager.stop_thread()
 
     # ------------------------------------------------------------------ inference (trainer.py:295-354, 750-771)
@@ -436,6 +515,9 @@ class Trainer(object):
         trained variables.  The 3D trainer uses the 3D curl here (the reference's trainer3.py:188 applies the 2D curl
         to the 3-channel potential -- a bug that is not reproduced)."""
         cls = getattr(self, "_engine_cls", GeneratorEngine)
+        if cls is None:                   # ops-level engine: the layer functions take any batch size
+            self.test_engine = self.engine
+            return
         self.test_engine = cls(self.test_b_num, self.output_shape, z_dim=self.c_num, filters=self.filters,
                                num_conv=self.num_conv, repeat=self.repeat, name="G", device=self.device,
                                init=self.engine.params.state_dict(), inference=True)
@@ -451,9 +533,14 @@ class Trainer(object):
             n = zb.shape[0]
             if n < self.test_b_num:
                 zb = torch.cat([zb, zb.new_zeros(self.test_b_num - n, zb.shape[1])])
-            pot = self.test_engine.forward(zb)
-            outs.append(K.curl_fwd(pot)[:n].clone())
+            with torch.no_grad():
+                pot = self.test_engine.forward(zb)
+            outs.append(self._velocity(pot)[:n].clone())
         return torch.cat(outs)
+
+    def _velocity(self, out):
+        """G_ of the network output: curl(G_s) with use_curl (trainer.py:140 / trainer3.py:18), else the output itself"""
+        return K.curl_fwd(out) if self.use_c else out
 
     def test(self):
         if 'ae' in self.arch:                       # trainer.py:306-312
@@ -512,7 +599,7 @@ class Trainer(object):
     @property
     def x_(self):
         """AE: reconstructed velocity curl(s) of the last step (trainer.py:361)"""
-        return K.curl_fwd(self.ae.dec.pot) if hasattr(self, "ae") else None
+        return self._velocity(self.ae.dec.pot) if hasattr(self, "ae") else None
 
     @property
     def s(self):
@@ -531,10 +618,45 @@ class Trainer(object):
         self._out_of_scope("get_vort_image(): vorticity PNG rendering", "trainer.py:773-790")
 
     def build_test_model_ae(self):
-        self._out_of_scope("build_test_model_ae(): AE test graph", "trainer.py:464-473; use encode() / decode() / autoencode()")
+        """trainer.py:464-473 re-declares the AE on a [test_b_num, ...] placeholder with reuse=True.  The engines here take
+        the trained variables as they are: encode() / decode() chunk any number of fields through the training engines."""
+        self.code_path = getattr(self.config, "code_path", "")
 
     def test_ae(self):
-        self._out_of_scope("test_ae(): latent-code and image dumps", "trainer.py:475-583")
+        """trainer.py:475-583.  Without --code_path: encode the WHOLE dataset in file order (`batch_manager.batch_`) and dump
+        `<load_path>/code<z_num>.npz` = {x: codes of frames 0..f-2 of every simulation, y: codes of frames 1..f-1, p: the
+        per-frame parameter increments from <dataset>/n.npz, s: #simulations, f: #frames} -- the training set of arch=nn.
+        With --code_path: decode `code_out.npz` ({z_out, z_gt}: [sims][frames, z_num]) back to velocity fields, de-normalise
+        and dump `<load_path>/v<s>.npz` = {v, v_gt} (the reference renders them to PNG frame pairs instead -- rendering is
+        out of scope; the arrays are what its own commented-out `np.savez_compressed(v_path, v=v, v_gt=v_gt)` would write)."""
+        self.build_test_model_ae()
+        bm = self.batch_manager
+        out_root = self.load_path or self.model_dir
+        if not self.code_path:
+            with np.load(os.path.join(bm.root, 'n.npz')) as data:
+                nx = data['nx']
+                nz = data['nz'] if self.is_3d else None
+            num_sims, num_frames = int(nx.shape[0]), int(nx.shape[1])
+            p_list = (nx[:, 1:] - nx[:, :-1]).reshape([-1, 1])
+            if self.is_3d:
+                p_list = np.concatenate((p_list, (nz[:, 1:] - nz[:, :-1]).reshape([-1, 1])), axis=-1)
+            c_list = np.concatenate([self.encode(xb).cpu().numpy() for xb, _ in bm.batch_(self.test_b_num)])
+            assert c_list.shape[0] == num_sims * num_frames, (c_list.shape, num_sims, num_frames)
+            c = c_list.reshape(num_sims, num_frames, -1)
+            x_list = c[:, :-1].reshape(-1, c.shape[-1])
+            y_list = c[:, 1:].reshape(-1, c.shape[-1])
+            code_path = os.path.join(out_root, 'code%d.npz' % self.z_num)
+            np.savez_compressed(code_path, x=x_list, y=y_list, p=p_list, s=num_sims, f=num_frames)
+            return code_path
+        with np.load(os.path.join(self.code_path, 'code_out.npz'), allow_pickle=True) as data:
+            z_, z_gt_ = data['z_out'], data['z_gt']
+        paths = []
+        for s_ in range(len(z_)):
+            v, _ = bm.denorm(x=self.decode(np.asarray(z_[s_], dtype=np.float32)))
+            v_gt, _ = bm.denorm(x=self.decode(np.asarray(z_gt_[s_], dtype=np.float32)))
+            paths.append(os.path.join(out_root, 'v%d.npz' % s_))
+            np.savez_compressed(paths[-1], v=v.cpu().numpy(), v_gt=v_gt.cpu().numpy())
+        return paths
 
     def build_model_nn(self):
         self._out_of_scope("arch='nn' (latent-space integrator)", "trainer.py:586-640, model.py:218-224")

@@ -67,6 +67,14 @@ int dfl_jacobian_bwd(const float* djac, const float* daux, float* dvel, const in
  * dd (may be NULL) = scale * d loss / d d.  Deterministic single-block reduction. */
 int dfl_mse_loss(const float* d, float target, float* loss, float* dd, size_t n, float scale, void* stream);
 
+/* Un-fused L1 term for use_curl=False (trainer.py:141-144: the generator emits the velocity itself, so there is no curl to
+ * fuse with): loss[0] = mean|a - b| over n values; dd (may be NULL) = scale * sgn(a - b) / n, added to dd when `accumulate`.
+ * The Jacobian term is the same call on dfl_jacobian_fwd outputs, its gradient goes back through dfl_jacobian_bwd.
+ * workspace: dfl_l1_loss_workspace_bytes() bytes, zeroed once by the caller; deterministic (ordered fp64 partials). */
+size_t dfl_l1_loss_workspace_bytes(void);
+int dfl_l1_loss(const float* a, const float* b, float* loss, float* dd, size_t n, float scale, int accumulate,
+                void* workspace, void* stream);
+
 /* Fused loss + gradient (SURVEY.md 8a "S").  Replaces, in one pass: curl (trainer.py:140 / trainer3.py:18),
  * jacobian of prediction and target (trainer.py:32,146 / trainer3.py:24), both L1 means (trainer.py:170-172 /
  * trainer3.py:49-51) and the TF autodiff of all of it w.r.t. the network output.

@@ -15,7 +15,7 @@ def test_flag_names_and_defaults_match_reference(golden_dir):
         assert k in mine, "missing reference flag --%s" % k
         assert mine[k] == v, (k, mine[k], v)
     extra = set(mine) - set(ref)
-    assert extra == {"synthetic", "synthetic_samples", "max_step", "precision"}   # new knobs are optional, defaults inert
+    assert extra == {"synthetic", "synthetic_samples", "max_step", "precision", "grad_accum"}   # new knobs are optional, defaults inert
     assert cfg.synthetic is False and cfg.max_step == 0
 
 
@@ -61,7 +61,7 @@ def test_trainer_method_surface_matches_reference(golden_dir):
     for m in ref["Trainer3"]:
         assert callable(getattr(Trainer3, m, None)), "Trainer3.%s missing" % m
     t = Trainer.__new__(Trainer)
-    for m in ("generate", "get_vort_image", "build_test_model_ae", "test_ae", "build_model_nn", "train_nn", "test_nn"):
+    for m in ("generate", "get_vort_image", "build_model_nn", "train_nn", "test_nn"):
         try:
             getattr(t, m)(*([None] * (1 if m in ("generate", "get_vort_image") else 0)))
             raise AssertionError("%s should raise" % m)

@@ -224,3 +224,213 @@ def test_dg_train_step_vs_oracle(is3d):
         tr.train_step(x, y)
     after = tr.losses_dg()
     assert all(v == v and abs(v) < 1e6 for v in after) and after[-1] < d0, (d0, after)     # the discriminator learns to separate
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# reference flag values that used to hard-fail (round-1 review): --filters != 128, use_curl=False, skip_concat=True
+# ---------------------------------------------------------------------------------------------------------------------
+def _ops_vars(names):
+    from deepfluids_b200 import ops as O
+    return OrderedDict((k, O.get_variable(k).detach().cpu().clone()) for k in names)
+
+
+@pytest.mark.parametrize("spatial,skip", [([32, 24], False), ([16, 16, 16], False), ([32, 24], True)])
+def test_generator_filters64_and_skip_concat_vs_oracle(spatial, skip):
+    """model.GeneratorBE(3) with filters=64 (run.bat:56,73 widths) and skip_concat=True (model.py:29-33): the ops-level
+    network (zero-padded 128-channel blocks on the same kernels) vs the oracle's generator on the same variables."""
+    from deepfluids_b200 import model as Mo, ops as O
+    nd = len(spatial)
+    cout = 3 if nd == 3 else 1
+    O.reset_variables(5)
+    g = torch.Generator().manual_seed(3)
+    z = torch.rand(2, 3, generator=g) * 2 - 1
+    fn = Mo.GeneratorBE3 if nd == 3 else Mo.GeneratorBE
+    zd = z.to(dev())
+    out, names = fn(zd, 64, spatial + [cout], num_conv=2, skip_concat=skip)
+    var = _ops_vars(names)
+    if skip:
+        # oracle restatement of the skip_concat branch (model.py:29-33): upsample both, concatenate, no residual add
+        x = R.linear(z, var["G/0_fc/weights"], var["G/0_fc/biases"]).reshape(2, 8, 6, 64)
+        x0, n = x, 1
+        for idx in range(3):
+            for _ in range(2):
+                x = R.conv_nd(x, var["G/%d_conv/weights" % n], var["G/%d_conv/biases" % n], 1, R.lrelu)
+                n += 1
+            if idx < 2:
+                x, x0 = R.upscale(x, 2), R.upscale(x0, 2)
+                x = torch.cat([x, x0], -1)
+        ref = R.conv_nd(x, var["G/%d_conv/weights" % n], var["G/%d_conv/biases" % n], 1, None)
+        assert var["G/3_conv/weights"].shape[-2] == 128 and var["G/5_conv/weights"].shape[-2] == 192      # growing concat
+    else:
+        assert list(var.keys()) == list(M.generator_layout(spatial + [cout], 64, 2)[0].keys())
+        ref = M.generator_forward(z, var, spatial + [cout], 64, 2)
+    assert out.shape == ref.shape and rel_l2(out, ref) <= 2e-2, rel_l2(out, ref)
+    # gradient w.r.t. every variable through the autograd tape of kernels
+    gy = torch.randn(ref.shape, generator=g)
+    O_vars = [O.get_variable(k) for k in names]
+    out2, _ = fn(zd, 64, spatial + [cout], num_conv=2, skip_concat=skip, reuse=True)
+    grads = torch.autograd.grad(out2, O_vars, gy.to(dev()).to(out2.dtype))
+    assert all(torch.isfinite(t).all() for t in grads)
+    if not skip:
+        leaves = OrderedDict((k, v.clone().requires_grad_(True)) for k, v in var.items())
+        refg = torch.autograd.grad(M.generator_forward(z, leaves, spatial + [cout], 64, 2), list(leaves.values()), gy)
+        errs = {k: rel_l2(a, b) for k, a, b in zip(names, grads, refg) if k.endswith("weights")}
+        assert max(errs.values()) <= 1.5e-1, errs                           # free-running bf16 (see test_gpu_trainstep.py)
+
+
+@pytest.mark.parametrize("is3d", [False, True])
+def test_trainer_filters64_ae_recipe_vs_oracle(is3d):
+    """run.bat:56,73: the AE recipes train with --filters=64.  One train step through the reference-style Trainer on the
+    ops-level engine: latent code, losses and the Adam direction vs the oracle; then the loss must fall."""
+    from deepfluids_b200 import config as C
+    from deepfluids_b200.data import BatchManager
+    from deepfluids_b200.trainer import Trainer
+    from deepfluids_b200.trainer3 import Trainer3
+    args = ["--synthetic=true", "--arch=ae", "--filter=64", "--batch_size=2", "--num_conv=2", "--max_step=20", "--lr_max=0.0005"]
+    args += ["--is_3d=true", "--res_x=16", "--res_y=16", "--res_z=16"] if is3d else ["--res_x=24", "--res_y=32"]
+    cfg, _ = C.get_config(args)
+    assert cfg.filters == 64
+    bm = BatchManager(cfg, pool=1)
+    tr = (Trainer3 if is3d else Trainer)(cfg, bm)
+    spatial = [16, 16, 16] if is3d else [32, 24]
+    cin = 3 if is3d else 2
+    assert tr.var == list(M.ae_layout(spatial + [cin], 64, 16, 2).keys())
+    var = tr.engine.params.state_dict()
+    x, y = bm.batch()
+    ylast = y[:, :, -1] if y.dim() == 3 else y[:, -tr.p_num:]
+    total, l1, jl1, lp, g, zref, grads = T.ae_loss_and_grads(x.cpu(), ylast.cpu(), var, tr.p_num, 64, 16, 2)
+    tr.train_step_ae(x, y)
+    got = tr.losses_ae()
+    assert rel_l2(tr.z, zref) <= 2e-2
+    assert abs(got[0] - float(total)) <= 2e-2 * abs(float(total)), (got, float(total))
+    new = tr.engine.params.state_dict()
+    for k in ("AE/enc/1_conv/weights", "AE/dec/2_conv/weights"):
+        agree = float((torch.sign(new[k] - var[k]) == -torch.sign(grads[k])).float().mean())
+        assert agree >= 0.85, (k, agree)
+    first = got[0]
+    for i in range(15):
+        tr.train_step_ae(x, y)
+    assert tr.losses_ae()[0] < first
+
+
+@pytest.mark.parametrize("is3d", [False, True])
+def test_use_curl_false_vs_oracle(is3d):
+    """use_curl=False (trainer.py:141-144): the generator emits the velocity itself (2 / 3 channels); loss and its gradient
+    w.r.t. the output from the un-fused kernels vs oracle autograd, then one trainer step end to end."""
+    from deepfluids_b200 import config as C, kernels as K
+    from deepfluids_b200.data import BatchManager
+    from deepfluids_b200.trainer import Trainer
+    from deepfluids_b200.trainer3 import Trainer3
+    spatial = [12, 10, 14] if is3d else [18, 14]
+    nd = len(spatial)
+    g = torch.Generator().manual_seed(7)
+    vel = torch.randn([2] + spatial + [nd], generator=g)
+    x = torch.randn([2] + spatial + [nd], generator=g)
+    loss3, dvel = K.velocity_loss_fwdbwd(vel.to(dev()), x.to(dev()), 0.7, 1.3)
+    v = vel.clone().requires_grad_(True)
+    loss, l1, jl1, _ = T.stencil_loss(v, x, 0.7, 1.3, use_curl=False)
+    (gref,) = torch.autograd.grad(loss, v)
+    assert abs(loss3[0].item() - loss.item()) <= 3e-6 * abs(loss.item())
+    assert abs(loss3[1].item() - l1.item()) <= 3e-6 * abs(l1.item()) and abs(loss3[2].item() - jl1.item()) <= 3e-6 * abs(jl1.item())
+    assert float((dvel.cpu() - gref).abs().max()) <= 1e-6 * float(gref.abs().max())
+    args = ["--synthetic=true", "--use_curl=false", "--batch_size=2", "--num_conv=2", "--max_step=20", "--lr_max=0.0005"]
+    args += ["--is_3d=true", "--res_x=16", "--res_y=16", "--res_z=16"] if is3d else ["--res_x=24", "--res_y=32"]
+    cfg, _ = C.get_config(args)
+    bm = BatchManager(cfg, pool=1)
+    tr = (Trainer3 if is3d else Trainer)(cfg, bm)
+    assert tr.output_shape[-1] == (3 if is3d else 2)                       # trainer.py:54-55
+    var = tr.engine.params.state_dict()
+    xb, yb = bm.batch()
+    ref = T.generator_loss_and_grads(yb.cpu(), xb.cpu(), var, num_conv=2, use_curl=False)
+    tr.train_step(xb, yb)
+    got = tr.losses()
+    assert abs(got[0] - float(ref[0])) <= 1e-2 * abs(float(ref[0])), (got, float(ref[0]))
+    first = got[0]
+    for i in range(15):
+        tr.train_step(xb, yb)
+    assert tr.losses()[0] < first
+    vgen = tr.generate_velocity(yb)
+    assert vgen.shape == xb.shape
+
+
+def test_gradient_accumulation_equals_one_large_batch():
+    """--grad_accum (strong scaling at a fixed global batch): 2 micro-batches of 2 == the gradient of one batch of 4"""
+    from deepfluids_b200 import config as C
+    from deepfluids_b200.data import BatchManager
+    from deepfluids_b200.trainer import Trainer
+    base = ["--synthetic=true", "--res_x=24", "--res_y=32", "--num_conv=2", "--max_step=50", "--lr_max=0.001"]
+    cfg_a, _ = C.get_config(base + ["--batch_size=2", "--grad_accum=2"])
+    bm_a = BatchManager(cfg_a, pool=2)
+    tr_a = Trainer(cfg_a, bm_a)
+    cfg_b, _ = C.get_config(base + ["--batch_size=4"])
+    tr_b = Trainer(cfg_b, BatchManager(cfg_b, pool=1))
+    assert torch.equal(tr_a.engine.params.data, tr_b.engine.params.data)
+    (x0, y0), (x1, y1) = bm_a._pool[0], bm_a._pool[1]
+    bm_a._i = 1                                      # the step draws micro-batch 0 itself, then pool[1]
+    w0 = tr_a.engine.params.data.clone()
+    tr_a.train_step(x0, y0)
+    tr_b.train_step(torch.cat([x0, x1]), torch.cat([y0, y1]))
+    torch.cuda.synchronize()
+    la, lb = tr_a.losses(), tr_b.losses()
+    assert abs(la[0] - lb[0]) <= 1e-5 * abs(lb[0]), (la, lb)
+    ga, gb = tr_a.engine.params.grad / 2, tr_b.engine.params.grad
+    assert rel_l2(ga, gb) <= 2e-3, rel_l2(ga, gb)    # (wgrad reduces with fp32 atomics: order differs between the two)
+    da, db = tr_a.engine.params.data - w0, tr_b.engine.params.data - w0
+    assert rel_l2(da, db) <= 5e-2 and tr_a.engine.adam_t == 1 and tr_a.step == 1
+
+
+def test_test_ae_latent_dump_and_decode(tmp_path):
+    """Trainer.test_ae (trainer.py:475-583): latent codes of the whole dataset in file order -> code<z>.npz with the
+    reference's x / y / p / s / f arrays; then decode-from-code_out.npz."""
+    import numpy as np
+    from deepfluids_b200 import config as C
+    from deepfluids_b200.data import BatchManager
+    from deepfluids_b200.trainer import Trainer
+    root = tmp_path / "data" / "toy_ae"
+    (root / "v").mkdir(parents=True)
+    sims, frames, H, W = 2, 4, 32, 24
+    rng = np.random.default_rng(0)
+    with open(root / "args.txt", "w") as f:               # AE scene layout (scene/smoke_mov.py-style): <scene>_<frame>.npz
+        for k, v in [("num_param", 2), ("p0", "scenes"), ("p1", "frames"), ("min_scenes", 0), ("max_scenes", sims - 1),
+                     ("num_scenes", sims), ("min_frames", 0), ("max_frames", frames - 1), ("num_frames", frames),
+                     ("num_dof", 1), ("resolution_x", W), ("resolution_y", H)]:
+            f.write("%s: %s\n" % (k, v))
+    vr = 0.0
+    for s_ in range(sims):
+        for t in range(frames):
+            x = rng.standard_normal((H, W, 2)).astype(np.float32)
+            vr = max(vr, float(np.abs(x).max()))
+            np.savez_compressed(root / "v" / ("%d_%d.npz" % (s_, t)), x=x, y=(rng.random((1, frames)) * 2 - 1).astype(np.float32))
+    with open(root / "v_range.txt", "w") as f:
+        f.write("%f\n%f" % (-vr, vr))
+    nx = np.cumsum(rng.random((sims, frames)), axis=1)
+    np.savez_compressed(root / "n.npz", nx=nx)
+    args = ["--arch=ae", "--dataset=toy_ae", "--data_dir=%s" % (tmp_path / "data"), "--res_x=%d" % W, "--res_y=%d" % H,
+            "--batch_size=2", "--test_batch_size=4", "--num_conv=2", "--max_step=2", "--num_worker=1"]
+    cfg, _ = C.get_config(args)
+    cfg.model_dir = str(tmp_path / "run")
+    cfg.load_path = ""
+    (tmp_path / "run").mkdir()
+    bm = BatchManager(cfg)
+    tr = Trainer(cfg, bm)
+    tr.load_path = str(tmp_path / "run")
+    path = tr.test_ae()
+    d = np.load(path)
+    assert d["x"].shape == (sims * (frames - 1), cfg.z_num) and d["y"].shape == d["x"].shape
+    assert d["p"].shape == (sims * (frames - 1), 1) and int(d["s"]) == sims and int(d["f"]) == frames
+    np.testing.assert_allclose(d["p"][:, 0], (nx[:, 1:] - nx[:, :-1]).reshape(-1), rtol=1e-6)
+    # x / y are the SAME code sequence shifted by one frame inside each simulation
+    np.testing.assert_array_equal(d["x"].reshape(sims, frames - 1, -1)[:, 1:], d["y"].reshape(sims, frames - 1, -1)[:, :-1])
+    # and they are the encoder's codes of the files in path order
+    xs = np.stack([np.load(p)["x"] for p in bm.paths]) / bm.x_range
+    z = tr.encode(xs.astype(np.float32)).cpu().numpy().reshape(sims, frames, -1)
+    np.testing.assert_allclose(d["x"], z[:, :-1].reshape(-1, cfg.z_num), rtol=1e-4, atol=1e-5)
+    # decode branch
+    cdir = tmp_path / "codes"
+    cdir.mkdir()
+    np.savez_compressed(cdir / "code_out.npz", z_out=z[:, :2], z_gt=z[:, 2:])
+    tr.config.code_path = str(cdir)
+    outs = tr.test_ae()
+    assert len(outs) == sims
+    v = np.load(outs[1])
+    assert v["v"].shape == (2, H, W, 2) and v["v_gt"].shape == (2, H, W, 2) and np.isfinite(v["v"]).all()
