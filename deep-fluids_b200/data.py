@@ -9,6 +9,7 @@ v/*.npz) is `DatasetBatchManager` below: the reference's fil
 threads feeding pinned host batches one step ahead."""
 import os
 
+import numpy as np
 import torch
 
 from . import kernels as K

@@ -260,7 +260,8 @@ def test_generator_filters64_and_skip_concat_vs_oracle(spatial, skip):
                 x, x0 = R.upscale(x, 2), R.upscale(x0, 2)
                 x = torch.cat([x, x0], -1)
         ref = R.conv_nd(x, var["G/%d_conv/weights" % n], var["G/%d_conv/biases" % n], 1, None)
-        assert var["G/3_conv/weights"].shape[-2] == 128 and var["G/5_conv/weights"].shape[-2] == 192      # growing concat
+        # x0 is only up-sampled, never replaced (model.py:31-33): every later block's first conv sees filters + filters channels
+        assert var["G/3_conv/weights"].shape[-2] == 128 and var["G/5_conv/weights"].shape[-2] == 128 and var["G/7_conv/weights"].shape[-2] == 64
     else:
         assert list(var.keys()) == list(M.generator_layout(spatial + [cout], 64, 2)[0].keys())
         ref = M.generator_forward(z, var, spatial + [cout], 64, 2)
