@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """bench.py -- deep-fluids generator train step (fwd + curl/Jacobian loss + bwd + Adam) on N B200s of one node.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c2|c3|c4|tiny] [--impl reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c2|c2sq|c3|c4|c5|tiny] [--scaling weak|strong] [--impl reference]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N --steps K --warmup W
 
 A "step" = one pass of the hot path over one batch of synthetic input = one `sess.run(g_optim)` of the reference
@@ -31,6 +31,7 @@ UNIT = "fields/s"
 WORKLOADS = {
     # name: (is_3d, res_z, res_y, res_x, per_gpu_batch, description)
     "c2": (False, 1, 128, 96, 64, "2D smoke_pos_size 128x96 generator+curl, batch 64/GPU (BASELINE configs[1])"),
+    "c2sq": (False, 1, 128, 128, 64, "2D 128x128 generator+curl, batch 64/GPU (the metric's '128^2' grid; the reference's own 2D recipe is 128x96 = c2)"),
     "c3": (True, 64, 64, 64, 16, "3D smoke3_vel_buo 64^3 generator+curl, batch 16/GPU (BASELINE configs[2])"),
     "c4": (True, 128, 128, 128, 4, "3D smoke3_vel_buo 128^3 generator+curl+grad-loss, batch 4/GPU (BASELINE configs[3])"),
     "c5": (True, 128, 128, 128, 4, "3D AE 128^3 encoder-decoder (arch=ae), batch 4/GPU (BASELINE configs[4])"),
@@ -38,14 +39,18 @@ WORKLOADS = {
 }
 ARCH = {"c5": "ae"}
 # BASELINE configs[1] is quoted in fp32 (the reference's TF graphs are fp32): it runs the fp32-grade split-operand path
-DEFAULT_PRECISION = {"c2": "fp32x3"}
+DEFAULT_PRECISION = {"c2": "fp32x3", "c2sq": "fp32x3"}
 PRECISION_NOTE = {
     "bf16": "bf16 operands/activations, fp32 accumulate (TMEM), fp32 master weights + Adam",
     "fp32x3": "fp32-grade: activations/gradients/weights as (hi, lo) bf16 pairs (16-bit mantissa), x*w = 3 tcgen05 MMA "
               "terms (hi*hi + lo*hi + hi*lo), fp32 accumulate (TMEM), fp32 master weights + Adam",
 }
 # algorithmic conv FLOPs per field, fwd+bwd
-FLOPS_PER_FIELD = {"c2": 58.0e9, "c3": 3196.0e9, "c4": 25575.0e9, "c5": 49471.0e9, "tiny": None}
+FLOPS_PER_FIELD = {"c2": 58.0e9, "c2sq": 77.3e9, "c3": 3196.0e9, "c4": 25575.0e9, "c5": 49471.0e9, "tiny": None}
+# strong scaling: the GLOBAL batch is fixed and split over the ranks; a rank whose share
+# exceeds its per-GPU micro-batch accumulates gradients over share / micro-batch micro-steps (ONE all-reduce + ONE Adam
+# update per optimizer step).  A "step" is then one optimizer step over the global batch.
+STRONG_GLOBAL_BATCH = {"c2": 512, "c2sq": 512, "c3": 128, "c4": 32, "c5": 32, "tiny": 32}
 
 
 # stdout carries exactly ONE line (the JSON): everything else any library prints to fd 1 (e.g. NCCL's version banner)
@@ -169,7 +174,7 @@ def cpu_oracle_fields_per_sec(workload, steps, warmup, budget_s=25.0):
         if time.time() - t_begin > budget_s and len(times) >= 1:
             break
     per_step = sum(times) / len(times)
-    return {"value": b / per_step, "unit": UNIT, "cores": cores, "kind": "port",
+    return {"value": b / per_step, "unit": UNIT, "cores": cores, "kind": "port", "steps_timed": len(times),
             "sample": "%d timed step(s) of batch %d (fwd+bwd+TF-Adam) of workload %s, fp32 torch-CPU/oneDNN oracle"
                       % (len(times), b, workload) + " (%d of %d host cores: fastest thread count measured)" % (cores, ncpu),
             "ms_per_step": per_step * 1e3, "batch": b}
@@ -180,8 +185,11 @@ def run_reference_arm(args):
     if rank != 0:
         return
     r = cpu_oracle_fields_per_sec(args.workload, max(1, args.steps), min(args.warmup, 1), budget_s=150.0)
+    # `steps` is the number of steps actually TIMED (the bounded sample stops at its wall-clock budget); the request is
+    # kept beside it so the line never claims more work than it measured
     out = {"impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": args.gpus,
-           "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True,
+           "steps": r["steps_timed"], "steps_requested": args.steps, "warmup": min(args.warmup, 1),
+           "ms_per_step": r["ms_per_step"], "higher_is_better": True,
            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
            "config": {"workload": WORKLOADS[args.workload][5], "batch_per_step": r["batch"],
                       "note": "reference CPU path = TensorFlow 1.15 (not installable); timed = oracle/ torch-CPU port"},
@@ -212,11 +220,18 @@ def run_gpu_arm(args):
     from deepfluids_b200.trainer3 import Trainer3
 
     precision = args.precision or DEFAULT_PRECISION.get(args.workload, "bf16")
-    cfg = make_config(args.workload, ["--precision=%s" % precision])
+    extra = ["--precision=%s" % precision]
+    accum = 1
+    if args.scaling == "strong":
+        gb, micro = STRONG_GLOBAL_BATCH[args.workload], WORKLOADS[args.workload][4]
+        assert gb % (micro * world) == 0, "global batch %d is not a multiple of %d ranks x micro-batch %d" % (gb, world, micro)
+        accum = gb // (micro * world)
+        extra.append("--grad_accum=%d" % accum)
+    cfg = make_config(args.workload, extra)
     terms = 3 if precision == "fp32x3" else 1      # MMA terms executed per algorithmic multiply-add
     bm = BatchManager(cfg, device=dev, pool=2, rank=rank)
     tr = (Trainer3 if cfg.is_3d else Trainer)(cfg, bm)
-    B = cfg.batch_size
+    B = cfg.batch_size * accum          # fields per rank per (optimizer) step
     peaks = load_peaks()
 
     def barrier():
@@ -272,6 +287,17 @@ def run_gpu_arm(args):
         loss_ev[k].synchronize()
         assert loss_h[k][0] == loss_h[k][0], "NaN loss"
 
+    class _HostSource(object):
+        """micro-batches 2..accum of an optimizer step (strong scaling): pulled from the pinned host pool through the same
+        one-step-ahead prefetcher, so every field of the step crosses PCIe inside the timed region"""
+        def batch(self_inner):
+            i = cnt[0]
+            cnt[0] += 1
+            pf.release()
+            xd, yd = pf.get()
+            pf.put(xh[(i + 1) % len(xh)], yh[(i + 1) % len(yh)])
+            return xd, yd
+
     def step_e2e():
         i = cnt[0]
         cnt[0] += 1
@@ -292,15 +318,19 @@ def run_gpu_arm(args):
         read_loss(pending[0])                            # the last step's loss, inside the timed region
         pending[0] = None
 
+    if accum > 1:
+        tr.batch_manager = _HostSource()
     pf.put(xh[0], yh[0])
     e2e_region(max(1, args.warmup // 2))
     ms_e = timed_region(lambda: e2e_region(args.steps), 1)
     e2e_value = B * world / (ms_e / args.steps * 1e-3)
-    h2d = sum(t.numel() * t.element_size() for t in pf.slots[0])
+    h2d = sum(t.numel() * t.element_size() for t in pf.slots[0]) * accum
+    tr.batch_manager = bm
 
     # ---------------- per-kernel timing with CUDA events (2 extra instrumented steps, same stream) ----------------
     K.PROF.events = []
     tr.use_graph = False          # eager launches so every kernel can be bracketed by events
+    tr.accum = 1                  # (per-kernel times are per micro-batch; with accumulation a step holds `accum` of them)
     for _ in range(2):
         tr.train_step()
     torch.cuda.synchronize()
@@ -329,14 +359,16 @@ def run_gpu_arm(args):
                 "frac": achieved / peaks["tf_sustained"], "peak_source": "%s (sustained bf16, kernel timed inside a long step)" % peaks["src"],
                 "mma_terms_per_flop": terms, "executed_tflops": achieved * terms,
                 "launches_timed": conv_n, "avg_launch_ms": conv_t / conv_n * 1e3, "traffic": load_traffic("conv_tc_kernel"),
-                "share_of_step": conv_t / 2 / (ms_per_step * 1e-3),
+                "traffic_source": "STATIC: dram bytes per launch of a full-resolution launch from the committed ncu --set full "
+                                  "capture (profiles/ncu_summary.json), not measured in this run",
+                "share_of_step": conv_t / 2 * accum / (ms_per_step * 1e-3),
                 "others": {
                     "wgrad_tc_kernel": {"bound": "tensor", "achieved": wg_f / wg_t / 1e12, "unit": "TFLOP/s",
                                         "frac": wg_f / wg_t / 1e12 / peaks["tf_sustained"],
-                                        "share_of_step": wg_t / 2 / (ms_per_step * 1e-3)},
+                                        "share_of_step": wg_t / 2 * accum / (ms_per_step * 1e-3)},
                     "stencil_fused_kernel": {"bound": "hbm", "achieved": st_b / st_t / 1e9, "unit": "GB/s",
                                              "frac": st_b / st_t / 1e9 / peaks["hbm_gbs"],
-                                             "share_of_step": st_t / 2 / (ms_per_step * 1e-3)}}}
+                                             "share_of_step": st_t / 2 * accum / (ms_per_step * 1e-3)}}}
     roofline["kernel_ms"] = kernel_ms
     fl = FLOPS_PER_FIELD[args.workload]
     if fl:
@@ -346,9 +378,10 @@ def run_gpu_arm(args):
     if rank == 0:
         cpu = cpu_oracle_fields_per_sec(args.workload, 3, 1) if world == 1 and not args.no_cpu else None
         out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-               "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+               "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": args.scaling,
                "vs_baseline": None, "dtype": "bf16" if terms == 1 else "f32 (bf16x3 split operands)", "data": "synthetic",
                "config": {"workload": WORKLOADS[args.workload][5], "global_batch": B * world, "per_gpu_batch": B,
+                          "micro_batch": cfg.batch_size, "grad_accum_micro_steps": accum,
                           "parallelism": "dp%d" % world, "filters": 128, "num_conv": 4,
                           "l2": "per-step working set (>= %.0f MB of activations) exceeds the 126 MB L2; no flush needed"
                                 % (B * float(np.prod(bm._pool[0][0].shape[1:-1])) * 128 * 2 * 6 / 1e6),
@@ -383,6 +416,9 @@ def main():
     ap.add_argument("--precision", type=str, default=None, choices=["bf16", "fp32x3"],
                     help="default: fp32x3 for c2 (BASELINE quotes it in fp32), bf16 otherwise")
     ap.add_argument("--no-cpu", dest="no_cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--scaling", type=str, default="weak", choices=["weak", "strong"],
+                    help="weak: per-GPU batch fixed (default).  strong: global batch fixed (c4/c5: 32), gradient accumulation "
+                         "over global/(micro*N) micro-steps per optimizer step")
     args = ap.parse_args()
     _guard_stdout()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup

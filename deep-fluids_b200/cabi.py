@@ -23,6 +23,10 @@ SIGNATURES = {
     "dfl_curl_bwd": (_i, [_vp, _vp, _dims, _i, _i, _vp]),
     "dfl_jacobian_bwd": (_i, [_vp, _vp, _vp, _dims, _i, _vp]),
     "dfl_mse_loss": (_i, [_vp, _f, _vp, _vp, _sz, _f, _vp]),
+    "dfl_comm_unique_id": (_i, [_vp]),
+    "dfl_comm_init": (_i, [C.POINTER(_vp), _i, _vp, _i]),
+    "dfl_allreduce": (_i, [_vp, _sz, _i, _vp, _vp]),
+    "dfl_comm_destroy": (_i, [_vp]),
     "dfl_l1_loss_workspace_bytes": (_sz, []),
     "dfl_l1_loss": (_i, [_vp, _vp, _vp, _vp, _sz, _f, _i, _vp, _vp]),
     "dfl_gemm_f32": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),

@@ -64,6 +64,10 @@ int fwd_stencils(int op, int nd, const int64_t* dims, const void* in, int in_cs,
 int bwd_stencils(int op, int nd, const int64_t* dims, const float* g0, const float* g1, float* out, int out_cs,
                  cudaStream_t st);
 int mse_loss(const float* d, float target, float* loss, float* dd, size_t n, float scale, cudaStream_t st);
+int comm_unique_id(void* id128);
+int comm_init(void** comm, int nranks, const void* id128, int rank);
+int allreduce(void* buf, size_t count, int dtype, void* comm, cudaStream_t st);
+int comm_destroy(void* comm);
 size_t l1_loss_workspace_bytes();
 int l1_loss(const float* a, const float* b, float* loss, float* dd, size_t n, float scale, int accumulate, void* ws,
             cudaStream_t st);
@@ -167,6 +171,12 @@ int dfl_jacobian_bwd(const float* djac, const float* daux, float* dvel, const in
 int dfl_mse_loss(const float* d, float target, float* loss, float* dd, size_t n, float scale, void* stream) {
   return mse_loss(d, target, loss, dd, n, scale, ST(stream));
 }
+int dfl_comm_unique_id(void* id128) { return comm_unique_id(id128); }
+int dfl_comm_init(void** comm, int nranks, const void* id128, int rank) { return comm_init(comm, nranks, id128, rank); }
+int dfl_allreduce(void* buf, size_t count, int dtype, void* comm, void* stream) {
+  return allreduce(buf, count, dtype, comm, ST(stream));
+}
+int dfl_comm_destroy(void* comm) { return comm_destroy(comm); }
 size_t dfl_l1_loss_workspace_bytes(void) { return l1_loss_workspace_bytes(); }
 int dfl_l1_loss(const float* a, const float* b, float* loss, float* dd, size_t n, float scale, int accumulate,
                 void* workspace, void* stream) {

@@ -280,15 +280,22 @@ class Trainer(object):
         if self.accum > 1:
             self.engine.zero_grad()
             self._loss3_acc.zero_()
+        # DFL_NATIVE_NCCL=1: the gradient all-reduce goes through the library's own communicator (dfl_allreduce) on the
+        # capture stream, so forward, backward, exchange and update are ONE graph launch per step at any world size
+        native = dp.use_native()
+        if native:
+            dp.native_comm()
         l0 = K.PROF.launches
         self._graph_a = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self._graph_a):
             # with gradient accumulation graph_a is ONE micro-batch (no zeroing, no update): it is replayed accum times
             self._step_body_a(self._xs, self._ys, zero=(self.accum == 1))
-            if self.world == 1 and self.accum == 1:
+            if self.accum == 1 and (self.world == 1 or native):
+                if native:
+                    dp.allreduce_grads_(self.engine.params.grad)
                 self._step_body_b(scale)
         self._graph_b = None
-        if self.world > 1 or self.accum > 1:
+        if (self.world > 1 and not native) or self.accum > 1:
             self._graph_b = torch.cuda.CUDAGraph()
             with torch.cuda.graph(self._graph_b):
                 self._step_body_b(scale)

@@ -227,6 +227,18 @@ int dfl_adam_step(float* param, const float* grad, float* m, float* v, size_t n,
 int dfl_adam_step_dev(float* param, const float* grad, float* m, float* v, size_t n, const float* lr_t_dev, float beta1,
                       float beta2, float eps, float grad_scale, void* stream);
 
+/* ---- data-parallel exchange (new -- the reference is single-GPU) ------------------------------------
+ * One process per GPU, every rank a full replica, ONE in-place ncclAllReduce(sum) over the flat fp32 gradient buffer per
+ * optimizer step; the 1/world (and 1/grad_accum) factor is the grad_scale of dfl_adam_step.  NCCL is dlopen'ed
+ * (libnccl.so.2, preferring the copy already mapped into the process).  dfl_allreduce is asynchronous on `stream` and may
+ * be captured into a CUDA graph together with the kernels around it.
+ *   id128: 128 bytes (ncclUniqueId) created on rank 0 by dfl_comm_unique_id and distributed out of band;
+ *   dfl_comm_init binds the communicator to the CURRENT CUDA device (collective: every rank calls it). */
+int dfl_comm_unique_id(void* id128);
+int dfl_comm_init(void** comm, int nranks, const void* id128, int rank);
+int dfl_allreduce(void* buf, size_t count, int dtype, void* comm, void* stream);
+int dfl_comm_destroy(void* comm);
+
 /* ---- misc ------------------------------------------------------------------------------------------- */
 int dfl_cast_f32_bf16(const float* in, void* out, size_t n, void* stream);
 
