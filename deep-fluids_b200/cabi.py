@@ -23,6 +23,9 @@ SIGNATURES = {
     "dfl_curl_bwd": (_i, [_vp, _vp, _dims, _i, _i, _vp]),
     "dfl_jacobian_bwd": (_i, [_vp, _vp, _vp, _dims, _i, _vp]),
     "dfl_mse_loss": (_i, [_vp, _f, _vp, _vp, _sz, _f, _vp]),
+    "dfl_lastconv_curl_loss_workspace_bytes": (_sz, []),
+    "dfl_lastconv_curl_loss_fwd": (_i, [_vp, _vp, _vp, _vp, _dims, _i, _i, _vp]),
+    "dfl_lastconv_curl_loss_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _dims, _i, _f, _f, _f, _vp]),
     "dfl_comm_unique_id": (_i, [_vp]),
     "dfl_comm_init": (_i, [C.POINTER(_vp), _i, _vp, _i]),
     "dfl_allreduce": (_i, [_vp, _sz, _i, _vp, _vp]),

@@ -64,6 +64,10 @@ int fwd_stencils(int op, int nd, const int64_t* dims, const void* in, int in_cs,
 int bwd_stencils(int op, int nd, const int64_t* dims, const float* g0, const float* g1, float* out, int out_cs,
                  cudaStream_t st);
 int mse_loss(const float* d, float target, float* loss, float* dd, size_t n, float scale, cudaStream_t st);
+size_t lastconv_curl_loss_bwd_workspace_bytes();
+int lastconv_curl_loss_bwd(const void* s, const float* pot, const float* x, const float* w, const void* mask_src, void* ds,
+                           void* ds_masked, float* dw, float* db, float* dpot, float* vel, float* loss3, void* workspace,
+                           const int64_t* dims, float w1, float w2, float grad_scale, cudaStream_t st);
 int comm_unique_id(void* id128);
 int comm_init(void** comm, int nranks, const void* id128, int rank);
 int allreduce(void* buf, size_t count, int dtype, void* comm, cudaStream_t st);
@@ -170,6 +174,23 @@ int dfl_jacobian_bwd(const float* djac, const float* daux, float* dvel, const in
 }
 int dfl_mse_loss(const float* d, float target, float* loss, float* dd, size_t n, float scale, void* stream) {
   return mse_loss(d, target, loss, dd, n, scale, ST(stream));
+}
+size_t dfl_lastconv_curl_loss_workspace_bytes(void) { return lastconv_curl_loss_bwd_workspace_bytes(); }
+int dfl_lastconv_curl_loss_fwd(const void* s, const float* w, const float* bias, float* pot, const int64_t* dims, int ndim,
+                               int cout, void* stream) {
+  return lastconv_fwd_tc(s, w, bias, pot, dims, ndim, cout, ST(stream));
+}
+int dfl_lastconv_curl_loss_bwd(const void* s, const float* pot, const float* x, const float* w, const void* mask_src,
+                               void* ds, void* ds_masked, float* dw, float* db, float* dpot, float* vel, float* loss3,
+                               void* workspace, const int64_t* dims, int ndim, float w1, float w2, float grad_scale,
+                               void* stream) {
+  if (ndim != 3) {
+    set_last_error("dfl_lastconv_curl_loss_bwd: the fused kernel is the 3D (128^3 / 64^3) path; 2D runs "
+                   "dfl_stencil_loss_fwdbwd + dfl_lastconv_bwd");
+    return DFL_ERR_UNSUPPORTED;
+  }
+  return lastconv_curl_loss_bwd(s, pot, x, w, mask_src, ds, ds_masked, dw, db, dpot, vel, loss3, workspace, dims, w1, w2,
+                                grad_scale, ST(stream));
 }
 int dfl_comm_unique_id(void* id128) { return comm_unique_id(id128); }
 int dfl_comm_init(void** comm, int nranks, const void* id128, int rank) { return comm_init(comm, nranks, id128, rank); }

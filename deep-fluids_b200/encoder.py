@@ -273,10 +273,11 @@ class AEEngine(object):
         pot = self.dec.forward(z)
         return pot, z
 
-    def backward(self, dpot, p_num=0, sparsity=0.01, w5=1.0):
+    def backward(self, dpot, p_num=0, sparsity=0.01, w5=1.0, fused=None):
         """dz must already hold d(loss_p)/dz (ae_loss_p); the decoder adds its FC input gradient, then the encoder runs.
-        With use_sparse the Bernoulli-KL term (trainer.py:389-394) and the sigmoid derivative are applied in between."""
-        self.dec.backward(dpot, dz=self.dz)
+        With use_sparse the Bernoulli-KL term (trainer.py:389-394) and the sigmoid derivative are applied in between.
+        fused: see GeneratorEngine.backward (3D: loss + adjoint in the prologue of the output conv's backward)."""
+        self.dec.backward(dpot, dz=self.dz, fused=fused)
         if self.use_sparse:
             K.ae_sparse_bwd(self.z_sig, self.dz, self.dz_lin, self.loss_kl, p_num, sparsity, w5)
             self.enc.backward(self.dz_lin)

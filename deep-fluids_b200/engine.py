@@ -209,9 +209,12 @@ class GeneratorEngine(object):
         return self.pot
 
     # ------------------------------------------------------------------ backward (TF autodiff of the above)
-    def backward(self, dpot, dz=None):
+    def backward(self, dpot, dz=None, fused=None):
         """dpot: fp32 gradient w.r.t. the generator output.  Accumulates into params.grad (call zero_grad first).
-        dz (fp32 [B, z_dim], optional): the gradient w.r.t. the generator input is ADDED to it (AE decoder)."""
+        dz (fp32 [B, z_dim], optional): the gradient w.r.t. the generator input is ADDED to it (AE decoder).
+        fused (3D, optional): dict(x=target velocity, w1=, w2=, loss3=, workspace=[, dpot=, vel=]) -- the curl / Jacobian-L1
+        loss and its adjoint run in the PROLOGUE of the output conv's backward kernel (dfl_lastconv_curl_loss_bwd): `dpot` is
+        then not read (pass None) and nothing is launched between the output conv's forward and backward kernels."""
         assert not self.inference, "inference engine has no backward pass"
         assert self.B <= 64, "fc_bwd keeps <= 64 parameter rows in smem"
         P = self.params
@@ -219,8 +222,14 @@ class GeneratorEngine(object):
         top = self.rep - 1
         ds = self._gview(0, top)
         dpre = self._gview(1, top)
-        K.lastconv_bwd(self.s, dpot, P.p(self.last_name + "/weights"), self.y[top][nc - 1], ds, dpre,
-                       P.g(self.last_name + "/weights"), P.g(self.last_name + "/biases"))
+        if fused is not None:
+            K.lastconv_curl_loss_bwd(self.s, self.pot, fused["x"], P.p(self.last_name + "/weights"), self.y[top][nc - 1], ds,
+                                     dpre, P.g(self.last_name + "/weights"), P.g(self.last_name + "/biases"), fused["loss3"],
+                                     fused["workspace"], fused.get("w1", 1.0), fused.get("w2", 1.0), 1.0,
+                                     dpot=fused.get("dpot"), vel=fused.get("vel"))
+        else:
+            K.lastconv_bwd(self.s, dpot, P.p(self.last_name + "/weights"), self.y[top][nc - 1], ds, dpre,
+                           P.g(self.last_name + "/weights"), P.g(self.last_name + "/biases"))
         for i in range(top, -1, -1):
             other = self._gview(2, i)
             gx0 = self._gview(3, i)

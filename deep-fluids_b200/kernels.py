@@ -416,6 +416,23 @@ def lastconv_bwd(s, dout, w, mask_src, ds, ds_masked, dw, db):
         _p(s), _p(dout), _p(w), _p(mask_src), _p(ds), _p(ds_masked), _p(dw), _p(db), d, nd, w.shape[-1], _st())))
 
 
+def lastconv_curl_loss_workspace(device):
+    """zeroed workspace of the fused kernel (per-CTA loss partials + the CTA ticket); allocate ONCE per trainer"""
+    return torch.zeros(cabi.lib().dfl_lastconv_curl_loss_workspace_bytes(), dtype=torch.uint8, device=device)
+
+
+def lastconv_curl_loss_bwd(s, pot, x, w, mask_src, ds, ds_masked, dw, db, loss3, workspace, w1=1.0, w2=1.0, grad_scale=1.0,
+                           dpot=None, vel=None):
+    """FUSED curl + Jacobian-L1 loss + adjoints + output-conv backward (3D): see dfl_lastconv_curl_loss_bwd"""
+    d, nd = _spatial(s)
+    assert nd == 3 and pot.dtype == torch.float32 and x.dtype == torch.float32 and pot.shape[-1] == 3 and x.shape[-1] == 3
+    nvox = x.numel() // 3
+    work = nvox * (128 * 2 * 4 + 24)       # algorithmic bytes: read s + mask, write ds + ds_masked (bf16 x 128), read A + x
+    PROF.timed("lastconv_bwd_fused", work, lambda: check(cabi.lib().dfl_lastconv_curl_loss_bwd(
+        _p(s), _p(pot), _p(x), _p(w), _p(mask_src), _p(ds), _p(ds_masked), _p(dw), _p(db), _p(dpot), _p(vel), _p(loss3),
+        _p(workspace), d, nd, float(w1), float(w2), float(grad_scale), _st())))
+
+
 def pool_mask(g, mask_src, ds, dmasked):
     """g: fine-grid gradient [B,(2D,)2H,2W,128]; ds / dmasked: coarse [B,(D,)H,W,128]"""
     ref = ds if ds is not None else dmasked

@@ -241,14 +241,36 @@ class Trainer(object):
         K.velocity_loss_fwdbwd(pot, x, self.w1, self.w2, dvel=self._dpot, loss3=self._loss3)
         return pot
 
+    def _fused_args(self, x, want_vel=False):
+        """3D + use_curl on the fused bf16 engine: the loss stencil runs in the prologue of the output conv's backward
+        kernel (DFL_FUSED_LOSS=0 restores the separate stencil launches for A/B runs)."""
+        from .encoder import AEEngine
+        ok = (self.is_3d and self.use_c and x.dtype == torch.float32 and x.shape[-2] % 2 == 0
+              and (getattr(self, "_engine_cls", None) is GeneratorEngine or isinstance(self.engine, AEEngine))
+              and os.environ.get("DFL_FUSED_LOSS", "1") != "0")
+        if not ok:
+            return None
+        if getattr(self, "_fws", None) is None:
+            self._fws = K.lastconv_curl_loss_workspace(self.device)
+        f = dict(x=x, w1=self.w1, w2=self.w2, loss3=self._loss3, workspace=self._fws)
+        if want_vel:
+            self._vel = torch.empty_like(x)
+            f["vel"] = self._vel
+        return f
+
     def _step_body_a(self, x, y, want_vel=False, zero=True):
         """zero grads, forward, fused loss + dL/dpot, backward (everything before the gradient exchange)"""
         eng = self.engine
         if zero:
             eng.zero_grad()
         pot = eng.forward(y)
-        vel = self._loss_and_grad(pot, x, want_vel)
-        eng.backward(self._dpot)
+        fused = self._fused_args(x, want_vel)
+        if fused is not None:
+            eng.backward(None, fused=fused)
+            vel = fused.get("vel")
+        else:
+            vel = self._loss_and_grad(pot, x, want_vel)
+            eng.backward(self._dpot)
         if self.accum > 1:
             self._loss3_acc.add_(self._loss3)
         return vel
@@ -449,9 +471,14 @@ class Trainer(object):
         y_last = y[:, :, -1].contiguous() if y.dim() == 3 else y[:, -self.p_num:].contiguous()
         ae.zero_grad()
         pot, z = ae.forward(x)
-        self._loss_and_grad(pot, x)       # use_curl: x_ = curl(s) (trainer.py:359-361); else x_ = the decoder output (:363)
+        fused = self._fused_args(x)
+        if fused is None:
+            self._loss_and_grad(pot, x)   # use_curl: x_ = curl(s) (trainer.py:359-361); else x_ = the decoder output (:363)
         K.ae_loss_p(z, y_last, ae.dz, self._loss_p, self.w4)
-        ae.backward(self._dpot, self.p_num, self.sparsity, self.w5)
+        if fused is None:
+            ae.backward(self._dpot, self.p_num, self.sparsity, self.w5)
+        else:
+            ae.backward(None, self.p_num, self.sparsity, self.w5, fused=fused)
         scale = dp.allreduce_grads_(ae.params.grad)
         ae.optimizer_step(self.g_lr, self.optimizer == 'adam', self.beta1, self.beta2, 1e-8, scale)
         self.step += 1

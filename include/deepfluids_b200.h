@@ -148,6 +148,28 @@ int dfl_lastconv_fwd(const void* s, const float* w, const float* bias, float* ou
 int dfl_lastconv_bwd(const void* s, const float* dout, const float* w, const void* mask_src, void* ds, void* ds_masked,
                      float* dw, float* db, const int64_t* dims, int ndim, int cout, void* stream);
 
+/* FUSED last-generator-epilogue / first-backward-prologue pair of the 3D train step (north_star; SURVEY.md 8a "S" + a3-last).
+ * Replaces trainer3.py:16-24,49-51 (curl, jacobian3 of prediction and target, both L1 means) + TF autodiff of all of it +
+ * Conv3DBackpropInput / Conv3DBackpropFilter / BiasAddGrad of model.py:84 -- with NOTHING launched in between:
+ *   dfl_lastconv_curl_loss_fwd: the output conv; its epilogue adds the bias and stores the fp32 potential A = G_s
+ *       (same kernel as dfl_lastconv_fwd -- the curl / loss half needs a +-2 voxel halo of A that a forward tile does not
+ *       own, so it lives in the backward kernel's prologue, where only the 3-channel A and x are re-read);
+ *   dfl_lastconv_curl_loss_bwd: ONE kernel.  Six stencil warps compute G_ = curl(A), the residuals J(G_) - J(x), their signs,
+ *       dL/dG_ and dL/dA = curl^T(dL/dG_) plane by plane (z-march, in-plane neighbours in shared memory) and hand each dL/dA
+ *       plane through a shared-memory ring to the im2col builders of the tensor-core backward (ds = conv^T(dL/dA, w), ds_masked
+ *       = ds * lrelu'(mask_src), dw += s^T (x) dL/dA, db += sum dL/dA).  dL/dA is never written to global memory unless the
+ *       caller passes `dpot` (and `vel` for G_); loss3 = {w1*l1 + w2*jl1, l1, jl1} is complete when the kernel ends
+ *       (ordered fp64 partials, last CTA adds them: deterministic).
+ *   pot, x: fp32 [B,D,H,W,3];  s: bf16 [B,D,H,W,128];  W even.  workspace: dfl_lastconv_curl_loss_workspace_bytes() bytes,
+ *   ZEROED ONCE by the caller before the first launch (it holds the CTA ticket, which resets itself). */
+size_t dfl_lastconv_curl_loss_workspace_bytes(void);
+int dfl_lastconv_curl_loss_fwd(const void* s, const float* w, const float* bias, float* pot, const int64_t* dims, int ndim,
+                               int cout, void* stream);
+int dfl_lastconv_curl_loss_bwd(const void* s, const float* pot, const float* x, const float* w, const void* mask_src,
+                               void* ds, void* ds_masked, float* dw, float* db, float* dpot, float* vel, float* loss3,
+                               void* workspace, const int64_t* dims, int ndim, float w1, float w2, float grad_scale,
+                               void* stream);
+
 /* adjoint of nearest-x2 upsampling fused with the lrelu derivative (model.py:35-36 / :77-78 backward):
  *   ds = sum of the 2x2(x2) children of g;  dmasked = ds * lrelu'(mask_src).  cdims = COARSE dims. */
 int dfl_pool_mask(const void* g, const void* mask_src, void* ds, void* dmasked, const int64_t* cdims, int ndim,
