@@ -139,7 +139,7 @@ def test_fused_bwd_full_size_128cube_vs_unfused_pair():
     dw_u, db_u = torch.zeros_like(w), torch.zeros(3, device=d)
     K.lastconv_bwd(s, dpu, w, mask, ds_u, dsm_u, dw_u, db_u)
     assert torch.equal(ds_u, ds) and torch.equal(dsm_u, dsm)
-    assert rel_l2(dw, dw_u) <= 1e-5
+    assert rel_l2(dw, dw_u) <= 1e-4          # both reduce 2 M voxels with fp32 atomics in different orders
 
 
 def test_trainer_step_same_weights_with_and_without_the_fusion():
