@@ -415,11 +415,24 @@ lastconv_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmS, const __grid_
     int i = 0;
     long long u = u0;
     FBSeg sg;
+    const size_t plane_vox = static_cast<size_t>(p.H) * p.W;
+    uint4 mvn[4];                                     // mask pieces of the NEXT 32-channel round (one round in flight)
     while (fb_next(u, u1, p.D, sg)) {
       int r = sg.col;
       const int tx0 = (r % p.tx) * 16; r /= p.tx;
       const int y0 = (r % p.ty) * 8;
       const int b = r / p.ty;
+      // lrelu-derivative operand (the layer below's output): requested a whole round ahead of its use, so the DRAM round
+      // trip hides behind the previous round's TMEM load, transposition and stores
+      auto load_mask = [&](size_t t0, int hh) {
+#pragma unroll
+        for (int it = 0; it < 4; ++it) {
+          const int rr_ = it * 32 + prow, ly = rr_ >> 4, lx = rr_ & 15;
+          if (p.ds_masked && tx0 + lx < p.W && y0 + ly < p.H)
+            mvn[it] = __ldg(reinterpret_cast<const uint4*>(p.mask_src + (t0 + static_cast<size_t>(ly) * p.W + lx) * 128 + hh * 32 + piece * 8));
+        }
+      };
+      load_mask(((static_cast<size_t>(b) * p.D + sg.zs) * p.H + y0) * p.W + tx0, 0);
       for (int z = sg.zs; z < sg.ze; ++z, ++i) {
         const size_t tile0 = ((static_cast<size_t>(b) * p.D + z) * p.H + y0) * p.W + tx0;    // voxel (ly = 0, lx = 0) of the tile
         const uint32_t s = i & 1, ph = (i >> 1) & 1;
@@ -428,14 +441,11 @@ lastconv_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmS, const __grid_
         const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + s * 128;
 #pragma unroll 1
         for (int h = 0; h < 4; ++h) {
-          // mask pieces of this chunk: requested before the transposition so the round trip overlaps it
           uint4 mv[4];
 #pragma unroll
-          for (int it = 0; it < 4; ++it) {
-            const int rr_ = it * 32 + prow, ly = rr_ >> 4, lx = rr_ & 15;
-            if (p.ds_masked && tx0 + lx < p.W && y0 + ly < p.H)
-              mv[it] = __ldg(reinterpret_cast<const uint4*>(p.mask_src + (tile0 + static_cast<size_t>(ly) * p.W + lx) * 128 + h * 32 + piece * 8));
-          }
+          for (int it = 0; it < 4; ++it) mv[it] = mvn[it];
+          if (h < 3) load_mask(tile0, h + 1);
+          else if (z + 1 < sg.ze) load_mask(tile0 + plane_vox, 0);
           {
             uint32_t rr[32];
             tmem_ld_32x32(taddr + h * 32, rr);
