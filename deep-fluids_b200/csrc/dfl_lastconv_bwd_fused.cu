@@ -38,7 +38,9 @@ constexpr int FB_OP = 32768;                      // one 128 x 128 bf16 operand 
 constexpr int FB_TR = 2 * 128 * 64;               // bf16(v), bf16(0.2 v) images of one 32-channel chunk of a tile
 constexpr int FB_RING = 4;                        // dL/dA planes in flight between the stencil and the builders
 constexpr int FB_PY = 10, FB_PX = 20;             // plane footprint: rows y0-1 .. y0+8, columns x0-2 .. x0+17
-constexpr int FB_PLANE_F = FB_PY * FB_PX * 3;     // floats per ring plane
+constexpr int FB_PITCH = 80;                      // floats per footprint row in the ring: 60 used; 80 = 16 (mod 32) keeps the
+                                                  // builders' half-warps (one tile row each, 3-float lane stride) on disjoint banks
+constexpr int FB_PLANE_F = FB_PY * FB_PITCH;      // floats per ring plane
 constexpr int FB_TPR = FB_PX / 2 + 2;             // stencil thread columns (voxel pairs): footprint + 2 + 2 halo voxels
 constexpr int FB_TR_ROWS = FB_PY + 4;             // stencil thread rows
 constexpr int FB_NTHR = FB_TPR * FB_TR_ROWS;      // 168 active stencil threads
@@ -521,6 +523,7 @@ lastconv_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmS, const __grid_
     // stencil warps write zeros there).  Plane i of a segment holds z = zs - 1 + i; slots are claimed in production order.
     const int row = (warp - 6) * 32 + lane;
     const int lx = row & 15, ly = row >> 4;
+    const uint32_t ring0 = smem_u32(sRing);
     float bsum[C];
 #pragma unroll
     for (int c = 0; c < C; ++c) bsum[c] = 0.f;
@@ -538,9 +541,9 @@ lastconv_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmS, const __grid_
         const uint32_t s = i & 1, ph = (i >> 1) & 1;
         mbar_wait(&g_empty[s], ph ^ 1);
         uint8_t* grow = sG + s * FB_OP + row * 128;
-        const float* pl[3];
+        uint32_t pl[3];                           // shared-space byte addresses (explicit ld.shared: no generic loads)
 #pragma unroll
-        for (int k = 0; k < 3; ++k) pl[k] = sRing + ((pbase + j + k) & 3) * FB_PLANE_F + (ly * FB_PX + lx) * C;
+        for (int k = 0; k < 3; ++k) pl[k] = ring0 + (((pbase + j + k) & 3) * FB_PLANE_F + ly * FB_PITCH + lx * C) * 4;
 #pragma unroll
         for (int jc = 0; jc < NCHUNK; ++jc) {
           float v[8];
@@ -552,7 +555,7 @@ lastconv_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmS, const __grid_
               const int t = k / C, co = k % C;
               const int dx = t % 3, dy = (t / 3) % 3, dz = t / 9;
               // source voxel q - (tap - 1): plane 2 - dz, row ly + 2 - dy, column lx + 3 - dx of the footprint
-              v[e] = pl[2 - dz][((2 - dy) * FB_PX + (3 - dx)) * C + co];
+              v[e] = fb_lds1(pl[2 - dz] + (((2 - dy) * FB_PITCH + (3 - dx) * C + co) * 4));
             }
           }
           const int half = jc >> 3, jj = jc & 7;
@@ -561,7 +564,7 @@ lastconv_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmS, const __grid_
         }
         // bias gradient: the tile's own voxels = centre positions of plane z (zero outside the domain)
 #pragma unroll
-        for (int c = 0; c < C; ++c) bsum[c] += pl[1][(1 * FB_PX + 2) * C + c];
+        for (int c = 0; c < C; ++c) bsum[c] += fb_lds1(pl[1] + ((1 * FB_PITCH + 2 * C + c) * 4));
         fence_proxy_async();
         mbar_arrive(&g_full[s]);
         fb_bar_arrive(FB_BAR_EMPTY + ((pbase + j) & 3), FB_ST_THREADS + FB_BUILD);     // plane z-1 is dead
@@ -587,7 +590,7 @@ lastconv_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmS, const __grid_
     const uint32_t slot = st0 + tid * 8, slot_sx = st0 + FB_SX0 * 4 + tid * 4;
     // this thread's 6 floats of a ring plane (footprint rows 0..9 = thread rows 2..11, pairs 0..9 = thread columns 1..10)
     const bool region = act && r >= 2 && r <= FB_TR_ROWS - 3 && k >= 1 && k <= FB_PX / 2;
-    const int ring_off = region ? ((r - 2) * FB_PX + (k - 1) * 2) * 3 : 0;
+    const uint32_t ring_off = smem_u32(sRing) + (region ? ((r - 2) * FB_PITCH + (k - 1) * 6) * 4 : 0);
     float facc_l1 = 0.f, facc_j = 0.f;
     uint32_t pprod = 0;                                  // ring planes produced so far
 
@@ -595,9 +598,11 @@ lastconv_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmS, const __grid_
       // hand one dL/dA plane to the builders: wait until the slot's previous plane has been consumed, write, signal
       if (pprod >= FB_RING) fb_bar_sync(FB_BAR_EMPTY + (pprod & 3), FB_ST_THREADS + FB_BUILD);
       if (region) {
-        float2* o = reinterpret_cast<float2*>(sRing + (pprod & 3) * FB_PLANE_F + ring_off);
-        if (valid) { o[0] = make_float2(oU.x, oV.x); o[1] = make_float2(oW.x, oU.y); o[2] = make_float2(oV.y, oW.y); }
-        else { o[0] = o[1] = o[2] = make_float2(0.f, 0.f); }
+        const uint32_t o = ring_off + (pprod & 3) * (FB_PLANE_F * 4);
+        const float2 z0 = make_float2(0.f, 0.f);
+        fb_sts2(o, valid ? make_float2(oU.x, oV.x) : z0);
+        fb_sts2(o + 8, valid ? make_float2(oW.x, oU.y) : z0);
+        fb_sts2(o + 16, valid ? make_float2(oV.y, oW.y) : z0);
       }
       fb_bar_arrive(FB_BAR_FULL + (pprod & 3), FB_ST_THREADS + FB_BUILD);
       ++pprod;
@@ -615,6 +620,9 @@ lastconv_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmS, const __grid_
       T.zs = max(sg.zs - 1, 0); T.ze = min(sg.ze + 1, D);
       const int cy = y0 - 3 + r, cx0 = x0 - 4 + 2 * k;
       T.inD = act && cy >= 0 && cy < H && cx0 >= 0 && cx0 < W;
+#ifdef FB_DIAG_NO_STENCIL      // timing diagnostic only (results are garbage): the stencil warps publish zero planes
+      T.inD = false;
+#endif
       const bool top = (cy == H - 1);
       T.region = region;
       T.outp = T.inD && region;
