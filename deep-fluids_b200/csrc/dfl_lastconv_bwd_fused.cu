@@ -35,7 +35,7 @@ constexpr int FB_ST_WARP0 = 10;
 constexpr int FB_ST_THREADS = 192;                // warps 10..15
 constexpr int FB_BUILD = 128;                     // warps 6..9
 constexpr int FB_OP = 32768;                      // one 128 x 128 bf16 operand image (two 16 KB halves)
-constexpr int FB_TR = 2 * 128 * 64;               // bf16(v), bf16(0.2 v) images of one 32-channel chunk of a tile
+constexpr int FB_TR = 2 * 128 * 64;               // two alternating bf16(v) images of one 32-channel chunk of a tile
 constexpr int FB_RING = 4;                        // dL/dA planes in flight between the stencil and the builders
 constexpr int FB_PY = 10, FB_PX = 20;             // plane footprint: rows y0-1 .. y0+8, columns x0-2 .. x0+17
 constexpr int FB_PITCH = 80;                      // floats per footprint row in the ring: 60 used; 80 = 16 (mod 32) keeps the
@@ -404,15 +404,15 @@ lastconv_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmS, const __grid_
     // ================================ epilogue (warps 2..5) ================================
     // TMEM rows leave through a swizzled shared-memory transposition so that global stores are complete 64-byte row
     // chunks (two full sectors, 4 lanes per row), 32 channels at a time:
-    //   phase 1 (thread = TMEM row): 32 channels -> bf16(v) and bf16(0.2 v) images [128 rows][64 B], 16-byte chunks
-    //            XOR-swizzled by (row >> 1) & 3;
-    //   phase 2 (thread = 16-byte piece of a row): ds = the first image, ds_masked = per element the first or second image
-    //            by the sign of the lrelu output (== rounding v * lrelu'(y) from fp32).
+    //   phase 1 (thread = TMEM row): 32 channels -> bf16(v) image [128 rows][64 B], 16-byte chunks XOR-swizzled by
+    //            (row >> 1) & 3; two images alternate, so one named barrier per round suffices;
+    //   phase 2 (thread = 16-byte piece of a row): ds = the image, ds_masked = ds or bf16(0.2 * ds) per element by the sign
+    //            of the lrelu output.
     const int quarter = warp & 3;
     const int row = quarter * 32 + lane;
     const int te = (warp - 2) * 32 + lane;            // 0..127
     const int prow = te >> 2, piece = te & 3;         // phase 2: row within a pass of 32 rows, 16-byte piece of its 64 bytes
-    const uint32_t sTa = smem_u32(sT), sTb = sTa + 128 * 64;
+    const uint32_t sT0 = smem_u32(sT);
     const uint32_t w_off = row * 64, sw_w = (row >> 1) & 3;
     int i = 0;
     long long u = u0;
@@ -448,30 +448,27 @@ lastconv_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmS, const __grid_
           for (int it = 0; it < 4; ++it) mv[it] = mvn[it];
           if (h < 3) load_mask(tile0, h + 1);
           else if (z + 1 < sg.ze) load_mask(tile0 + plane_vox, 0);
+          const uint32_t sTa = sT0 + (h & 1) * (128 * 64);     // alternating images: ONE barrier per round
           {
             uint32_t rr[32];
             tmem_ld_32x32(taddr + h * 32, rr);
             tmem_ld_wait();
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
-              uint32_t wa[4], wb[4];
+              uint32_t wa[4];
 #pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                const float v0 = __uint_as_float(rr[q * 8 + 2 * e]), v1 = __uint_as_float(rr[q * 8 + 2 * e + 1]);
-                wa[e] = fb_pack(v0, v1);
-                wb[e] = fb_pack(v0 * 0.2f, v1 * 0.2f);
-              }
+              for (int e = 0; e < 4; ++e)
+                wa[e] = fb_pack(__uint_as_float(rr[q * 8 + 2 * e]), __uint_as_float(rr[q * 8 + 2 * e + 1]));
               const uint32_t o = w_off + ((q ^ sw_w) << 4);
               asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(sTa + o), "r"(wa[0]), "r"(wa[1]), "r"(wa[2]), "r"(wa[3]) : "memory");
-              if (p.ds_masked)
-                asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(sTb + o), "r"(wb[0]), "r"(wb[1]), "r"(wb[2]), "r"(wb[3]) : "memory");
             }
           }
           if (h == 3) {
             tc_fence_before();
             mbar_arrive(&d1_empty[s]);               // the tensor core may overwrite this accumulator
           }
-          fb_bar_sync(2, 128);                       // images complete
+          fb_bar_sync(2, 128);                       // image complete (the other image is free: its readers passed the
+                                                     // previous round's barrier)
 #pragma unroll
           for (int it = 0; it < 4; ++it) {
             const int rr_ = it * 32 + prow, ly = rr_ >> 4, lx = rr_ & 15;
@@ -482,8 +479,18 @@ lastconv_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmS, const __grid_
             asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(va.x), "=r"(va.y), "=r"(va.z), "=r"(va.w) : "r"(sTa + o));
             if (p.ds) *reinterpret_cast<uint4*>(p.ds + off) = va;
             if (p.ds_masked) {
+              // ds * lrelu'(y): 0.2 * ds for y < 0, evaluated on the bf16 image (a second image holding bf16(0.2 v) rounded
+              // from fp32 doubled the shared-memory traffic of this loop -- the resource that bounds the kernel -- for a
+              // difference of at most one bf16 ulp in the elements whose two roundings disagree)
               uint4 vb;
-              asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(vb.x), "=r"(vb.y), "=r"(vb.z), "=r"(vb.w) : "r"(sTb + o));
+              {
+                const uint32_t ain[4] = {va.x, va.y, va.z, va.w};
+                uint32_t bo[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e)
+                  bo[e] = fb_pack(__uint_as_float(ain[e] << 16) * 0.2f, __uint_as_float(ain[e] & 0xFFFF0000u) * 0.2f);
+                vb = make_uint4(bo[0], bo[1], bo[2], bo[3]);
+              }
               const uint32_t mw[4] = {mv[it].x, mv[it].y, mv[it].z, mv[it].w};
               const uint32_t aw[4] = {va.x, va.y, va.z, va.w}, bw[4] = {vb.x, vb.y, vb.z, vb.w};
               uint32_t ow[4];
@@ -496,7 +503,6 @@ lastconv_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmS, const __grid_
               *reinterpret_cast<uint4*>(p.ds_masked + off) = make_uint4(ow[0], ow[1], ow[2], ow[3]);
             }
           }
-          fb_bar_sync(3, 128);                       // images may be overwritten
         }
       }
     }
