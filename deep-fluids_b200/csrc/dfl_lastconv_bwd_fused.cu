@@ -287,6 +287,51 @@ __device__ __forceinline__ void fb_iter(const int t, const FusedBwdParams& p, co
 }
 
 // ------------------------------------------------------------------------------------------------------------------
+// Phase 2 of the epilogue, shared by the epilogue warps (row passes 0, 1) and the im2col builder warps (passes 2, 3): one
+// pass = 32 tile rows x one 32-channel chunk; 4 lanes move one row's 64 bytes (two complete sectors) from the transposition
+// image to ds and ds * lrelu'(y).  The kernel is bound by the instruction latency chain of the warps that run this loop
+// (one epilogue warp per scheduler), not by HBM or the tensor pipe, so it is split over eight warps.
+struct FBStoreLane { int prow, piece; };
+__device__ __forceinline__ void fb_load_mask(const FusedBwdParams& p, const FBStoreLane L, size_t t0, int tx0, int y0, int hh,
+                                             int it0, uint4 (&m)[2]) {
+#pragma unroll
+  for (int q = 0; q < 2; ++q) {
+    const int rr_ = (it0 + q) * 32 + L.prow, ly = rr_ >> 4, lx = rr_ & 15;
+    if (p.ds_masked && tx0 + lx < p.W && y0 + ly < p.H)
+      m[q] = __ldg(reinterpret_cast<const uint4*>(p.mask_src + (t0 + static_cast<size_t>(ly) * p.W + lx) * 128 + hh * 32 + L.piece * 8));
+  }
+}
+__device__ __forceinline__ void fb_store_passes(const FusedBwdParams& p, const FBStoreLane L, uint32_t sTa, size_t tile0, int tx0,
+                                                int y0, int h, int it0, const uint4 (&mv)[2]) {
+#pragma unroll
+  for (int q = 0; q < 2; ++q) {
+    const int rr_ = (it0 + q) * 32 + L.prow, ly = rr_ >> 4, lx = rr_ & 15;
+    if (tx0 + lx >= p.W || y0 + ly >= p.H) continue;
+    const uint32_t o = rr_ * 64 + ((L.piece ^ ((rr_ >> 1) & 3)) << 4);
+    const size_t off = (tile0 + static_cast<size_t>(ly) * p.W + lx) * 128 + h * 32 + L.piece * 8;
+    uint4 va;
+    asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(va.x), "=r"(va.y), "=r"(va.z), "=r"(va.w) : "r"(sTa + o));
+    if (p.ds) *reinterpret_cast<uint4*>(p.ds + off) = va;
+    if (p.ds_masked) {
+      // ds * lrelu'(y): 0.2 * ds for y < 0, evaluated on the bf16 image (a second image holding bf16(0.2 v) rounded from
+      // fp32 doubled the shared-memory traffic and the length of this loop for a difference of at most one bf16 ulp in
+      // the elements whose two roundings disagree).  lrelu'(y) = 1 for y >= 0 (incl. -0), else 0.2 (NaN -> 0.2): the rule of
+      // lrelu_grad_from_out.
+      const uint32_t aw[4] = {va.x, va.y, va.z, va.w};
+      const uint32_t mw[4] = {mv[q].x, mv[q].y, mv[q].z, mv[q].w};
+      uint32_t ow[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float a0 = __uint_as_float(aw[e] << 16), a1 = __uint_as_float(aw[e] & 0xFFFF0000u);
+        const float k0 = __uint_as_float(mw[e] << 16) >= 0.f ? 1.f : 0.2f, k1 = __uint_as_float(mw[e] & 0xFFFF0000u) >= 0.f ? 1.f : 0.2f;
+        ow[e] = fb_pack(a0 * k0, a1 * k1);           // (x * 1.0f is exact: unmasked elements pass through unchanged)
+      }
+      *reinterpret_cast<uint4*>(p.ds_masked + off) = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(FB_THREADS, 1)
 lastconv_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmS, const __grid_constant__ FusedBwdParams p) {
   constexpr int C = 3, NT = 27;
@@ -411,14 +456,14 @@ lastconv_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmS, const __grid_
     const int quarter = warp & 3;
     const int row = quarter * 32 + lane;
     const int te = (warp - 2) * 32 + lane;            // 0..127
-    const int prow = te >> 2, piece = te & 3;         // phase 2: row within a pass of 32 rows, 16-byte piece of its 64 bytes
+    const FBStoreLane L{te >> 2, te & 3};             // phase 2: row within a pass of 32 rows, 16-byte piece of its 64 bytes
     const uint32_t sT0 = smem_u32(sT);
     const uint32_t w_off = row * 64, sw_w = (row >> 1) & 3;
     int i = 0;
     long long u = u0;
     FBSeg sg;
     const size_t plane_vox = static_cast<size_t>(p.H) * p.W;
-    uint4 mvn[4];                                     // mask pieces of the NEXT 32-channel round (one round in flight)
+    uint4 mvn[2];                                     // mask pieces of the NEXT 32-channel round (one round in flight)
     while (fb_next(u, u1, p.D, sg)) {
       int r = sg.col;
       const int tx0 = (r % p.tx) * 16; r /= p.tx;
@@ -426,15 +471,7 @@ lastconv_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmS, const __grid_
       const int b = r / p.ty;
       // lrelu-derivative operand (the layer below's output): requested a whole round ahead of its use, so the DRAM round
       // trip hides behind the previous round's TMEM load, transposition and stores
-      auto load_mask = [&](size_t t0, int hh) {
-#pragma unroll
-        for (int it = 0; it < 4; ++it) {
-          const int rr_ = it * 32 + prow, ly = rr_ >> 4, lx = rr_ & 15;
-          if (p.ds_masked && tx0 + lx < p.W && y0 + ly < p.H)
-            mvn[it] = __ldg(reinterpret_cast<const uint4*>(p.mask_src + (t0 + static_cast<size_t>(ly) * p.W + lx) * 128 + hh * 32 + piece * 8));
-        }
-      };
-      load_mask(((static_cast<size_t>(b) * p.D + sg.zs) * p.H + y0) * p.W + tx0, 0);
+      fb_load_mask(p, L, ((static_cast<size_t>(b) * p.D + sg.zs) * p.H + y0) * p.W + tx0, tx0, y0, 0, 0, mvn);
       for (int z = sg.zs; z < sg.ze; ++z, ++i) {
         const size_t tile0 = ((static_cast<size_t>(b) * p.D + z) * p.H + y0) * p.W + tx0;    // voxel (ly = 0, lx = 0) of the tile
         const uint32_t s = i & 1, ph = (i >> 1) & 1;
@@ -443,11 +480,10 @@ lastconv_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmS, const __grid_
         const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + s * 128;
 #pragma unroll 1
         for (int h = 0; h < 4; ++h) {
-          uint4 mv[4];
-#pragma unroll
-          for (int it = 0; it < 4; ++it) mv[it] = mvn[it];
-          if (h < 3) load_mask(tile0, h + 1);
-          else if (z + 1 < sg.ze) load_mask(tile0 + plane_vox, 0);
+          uint4 mv[2];
+          mv[0] = mvn[0]; mv[1] = mvn[1];
+          if (h < 3) fb_load_mask(p, L, tile0, tx0, y0, h + 1, 0, mvn);
+          else if (z + 1 < sg.ze) fb_load_mask(p, L, tile0 + plane_vox, tx0, y0, 0, 0, mvn);
           const uint32_t sTa = sT0 + (h & 1) * (128 * 64);     // alternating images: ONE barrier per round
           {
             uint32_t rr[32];
@@ -467,42 +503,10 @@ lastconv_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmS, const __grid_
             tc_fence_before();
             mbar_arrive(&d1_empty[s]);               // the tensor core may overwrite this accumulator
           }
-          fb_bar_sync(2, 128);                       // image complete (the other image is free: its readers passed the
-                                                     // previous round's barrier)
-#pragma unroll
-          for (int it = 0; it < 4; ++it) {
-            const int rr_ = it * 32 + prow, ly = rr_ >> 4, lx = rr_ & 15;
-            if (tx0 + lx >= p.W || y0 + ly >= p.H) continue;
-            const uint32_t o = rr_ * 64 + ((piece ^ ((rr_ >> 1) & 3)) << 4);
-            const size_t off = (tile0 + static_cast<size_t>(ly) * p.W + lx) * 128 + h * 32 + piece * 8;
-            uint4 va;
-            asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(va.x), "=r"(va.y), "=r"(va.z), "=r"(va.w) : "r"(sTa + o));
-            if (p.ds) *reinterpret_cast<uint4*>(p.ds + off) = va;
-            if (p.ds_masked) {
-              // ds * lrelu'(y): 0.2 * ds for y < 0, evaluated on the bf16 image (a second image holding bf16(0.2 v) rounded
-              // from fp32 doubled the shared-memory traffic of this loop -- the resource that bounds the kernel -- for a
-              // difference of at most one bf16 ulp in the elements whose two roundings disagree)
-              uint4 vb;
-              {
-                const uint32_t ain[4] = {va.x, va.y, va.z, va.w};
-                uint32_t bo[4];
-#pragma unroll
-                for (int e = 0; e < 4; ++e)
-                  bo[e] = fb_pack(__uint_as_float(ain[e] << 16) * 0.2f, __uint_as_float(ain[e] & 0xFFFF0000u) * 0.2f);
-                vb = make_uint4(bo[0], bo[1], bo[2], bo[3]);
-              }
-              const uint32_t mw[4] = {mv[it].x, mv[it].y, mv[it].z, mv[it].w};
-              const uint32_t aw[4] = {va.x, va.y, va.z, va.w}, bw[4] = {vb.x, vb.y, vb.z, vb.w};
-              uint32_t ow[4];
-#pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                // lrelu'(y) = 1 for y >= 0 (incl. -0), else 0.2 (NaN -> 0.2): same rule as lrelu_grad_from_out
-                const bool lo1 = __uint_as_float(mw[e] << 16) >= 0.f, hi1 = __uint_as_float(mw[e] & 0xFFFF0000u) >= 0.f;
-                ow[e] = ((lo1 ? aw[e] : bw[e]) & 0x0000FFFFu) | ((hi1 ? aw[e] : bw[e]) & 0xFFFF0000u);
-              }
-              *reinterpret_cast<uint4*>(p.ds_masked + off) = make_uint4(ow[0], ow[1], ow[2], ow[3]);
-            }
-          }
+          // image complete; the other image is free (its readers passed the previous round's barrier).  The builder warps
+          // take row passes 2 and 3 of this round.
+          fb_bar_sync(2, 128 + FB_BUILD);
+          fb_store_passes(p, L, sTa, tile0, tx0, y0, h, 0, mv);
         }
       }
     }
@@ -527,58 +531,94 @@ lastconv_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmS, const __grid_
     // ================================ im2col builders (warps 6..9) ================================
     // G[q][k = tap*C+co] = dL/dA[q - (tap-1)][co] from the three ring planes z-1, z, z+1 (zero outside the domain: the
     // stencil warps write zeros there).  Plane i of a segment holds z = zs - 1 + i; slots are claimed in production order.
+    // They also run HALF of the epilogue's store loop (row passes 2, 3 of every 32-channel round): the im2col tile of tile
+    // i+1 is built first (so the tensor core never waits for it), then the warps join the four rounds of tile i.
     const int row = (warp - 6) * 32 + lane;
     const int lx = row & 15, ly = row >> 4;
     const uint32_t ring0 = smem_u32(sRing);
+    const FBStoreLane L{row >> 2, row & 3};
+    const uint32_t sT0 = smem_u32(sT);
+    const size_t plane_vox = static_cast<size_t>(p.H) * p.W;
     float bsum[C];
 #pragma unroll
     for (int c = 0; c < C; ++c) bsum[c] = 0.f;
-    int i = 0;
-    uint32_t pbase = 0, waited = 0;           // ring planes produced before this segment / FULL barriers passed so far
+    // ---- build cursor (one tile ahead of the store cursor)
+    int ib = 0, jb = 0;
+    uint32_t pbase = 0, waited = 0;           // ring planes produced before the build segment / FULL barriers passed so far
+    long long ub = u0;
+    FBSeg sb_;
+    bool have_b = fb_next(ub, u1, p.D, sb_);
+    auto build_next = [&]() {
+      if (!have_b) return;
+      const int n = sb_.ze - sb_.zs, j = jb;
+      while (waited < pbase + j + 3) {
+        fb_bar_sync(FB_BAR_FULL + (waited & 3), FB_ST_THREADS + FB_BUILD);
+        ++waited;
+      }
+      const uint32_t s = ib & 1, ph = (ib >> 1) & 1;
+      mbar_wait(&g_empty[s], ph ^ 1);
+      uint8_t* grow = sG + s * FB_OP + row * 128;
+      uint32_t pl[3];                           // shared-space byte addresses (explicit ld.shared: no generic loads)
+#pragma unroll
+      for (int k = 0; k < 3; ++k) pl[k] = ring0 + (((pbase + j + k) & 3) * FB_PLANE_F + ly * FB_PITCH + lx * C) * 4;
+#pragma unroll
+      for (int jc = 0; jc < NCHUNK; ++jc) {
+        float v[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          const int k = jc * 8 + e;
+          v[e] = 0.f;
+          if (k < KREAL) {
+            const int t = k / C, co = k % C;
+            const int dx = t % 3, dy = (t / 3) % 3, dz = t / 9;
+            // source voxel q - (tap - 1): plane 2 - dz, row ly + 2 - dy, column lx + 3 - dx of the footprint
+            v[e] = fb_lds1(pl[2 - dz] + (((2 - dy) * FB_PITCH + (3 - dx) * C + co) * 4));
+          }
+        }
+        const int half = jc >> 3, jj = jc & 7;
+        *reinterpret_cast<uint4*>(grow + half * (FB_OP / 2) + ((jj ^ (row & 7)) * 16)) =
+            make_uint4(fb_pack(v[0], v[1]), fb_pack(v[2], v[3]), fb_pack(v[4], v[5]), fb_pack(v[6], v[7]));
+      }
+      // bias gradient: the tile's own voxels = centre positions of plane z (zero outside the domain)
+#pragma unroll
+      for (int c = 0; c < C; ++c) bsum[c] += fb_lds1(pl[1] + ((1 * FB_PITCH + 2 * C + c) * 4));
+      fence_proxy_async();
+      mbar_arrive(&g_full[s]);
+      fb_bar_arrive(FB_BAR_EMPTY + ((pbase + j) & 3), FB_ST_THREADS + FB_BUILD);     // plane z-1 is dead
+      ++ib;
+      if (++jb == n) {
+        // the segment's last two planes (z = ze-1, ze) were only needed by tiles of this segment
+        fb_bar_arrive(FB_BAR_EMPTY + ((pbase + n) & 3), FB_ST_THREADS + FB_BUILD);
+        fb_bar_arrive(FB_BAR_EMPTY + ((pbase + n + 1) & 3), FB_ST_THREADS + FB_BUILD);
+        pbase += n + 2;
+        jb = 0;
+        have_b = fb_next(ub, u1, p.D, sb_);
+      }
+    };
+    build_next();                               // tile 0
+    // ---- store cursor
     long long u = u0;
     FBSeg sg;
+    uint4 mvn[2];
     while (fb_next(u, u1, p.D, sg)) {
-      const int n = sg.ze - sg.zs;
-      for (int j = 0; j < n; ++j, ++i) {
-        while (waited < pbase + j + 3) {
-          fb_bar_sync(FB_BAR_FULL + (waited & 3), FB_ST_THREADS + FB_BUILD);
-          ++waited;
+      int r = sg.col;
+      const int tx0 = (r % p.tx) * 16; r /= p.tx;
+      const int y0 = (r % p.ty) * 8;
+      const int b = r / p.ty;
+      fb_load_mask(p, L, ((static_cast<size_t>(b) * p.D + sg.zs) * p.H + y0) * p.W + tx0, tx0, y0, 0, 2, mvn);
+      for (int z = sg.zs; z < sg.ze; ++z) {
+        const size_t tile0 = ((static_cast<size_t>(b) * p.D + z) * p.H + y0) * p.W + tx0;
+        build_next();                           // the NEXT tile's im2col operand, before this tile's store rounds
+#pragma unroll 1
+        for (int h = 0; h < 4; ++h) {
+          uint4 mv[2];
+          mv[0] = mvn[0]; mv[1] = mvn[1];
+          if (h < 3) fb_load_mask(p, L, tile0, tx0, y0, h + 1, 2, mvn);
+          else if (z + 1 < sg.ze) fb_load_mask(p, L, tile0 + plane_vox, tx0, y0, 0, 2, mvn);
+          fb_bar_sync(2, 128 + FB_BUILD);
+          fb_store_passes(p, L, sT0 + (h & 1) * (128 * 64), tile0, tx0, y0, h, 2, mv);
         }
-        const uint32_t s = i & 1, ph = (i >> 1) & 1;
-        mbar_wait(&g_empty[s], ph ^ 1);
-        uint8_t* grow = sG + s * FB_OP + row * 128;
-        uint32_t pl[3];                           // shared-space byte addresses (explicit ld.shared: no generic loads)
-#pragma unroll
-        for (int k = 0; k < 3; ++k) pl[k] = ring0 + (((pbase + j + k) & 3) * FB_PLANE_F + ly * FB_PITCH + lx * C) * 4;
-#pragma unroll
-        for (int jc = 0; jc < NCHUNK; ++jc) {
-          float v[8];
-#pragma unroll
-          for (int e = 0; e < 8; ++e) {
-            const int k = jc * 8 + e;
-            v[e] = 0.f;
-            if (k < KREAL) {
-              const int t = k / C, co = k % C;
-              const int dx = t % 3, dy = (t / 3) % 3, dz = t / 9;
-              // source voxel q - (tap - 1): plane 2 - dz, row ly + 2 - dy, column lx + 3 - dx of the footprint
-              v[e] = fb_lds1(pl[2 - dz] + (((2 - dy) * FB_PITCH + (3 - dx) * C + co) * 4));
-            }
-          }
-          const int half = jc >> 3, jj = jc & 7;
-          *reinterpret_cast<uint4*>(grow + half * (FB_OP / 2) + ((jj ^ (row & 7)) * 16)) =
-              make_uint4(fb_pack(v[0], v[1]), fb_pack(v[2], v[3]), fb_pack(v[4], v[5]), fb_pack(v[6], v[7]));
-        }
-        // bias gradient: the tile's own voxels = centre positions of plane z (zero outside the domain)
-#pragma unroll
-        for (int c = 0; c < C; ++c) bsum[c] += fb_lds1(pl[1] + ((1 * FB_PITCH + 2 * C + c) * 4));
-        fence_proxy_async();
-        mbar_arrive(&g_full[s]);
-        fb_bar_arrive(FB_BAR_EMPTY + ((pbase + j) & 3), FB_ST_THREADS + FB_BUILD);     // plane z-1 is dead
       }
-      // the segment's last two planes (z = ze-1, ze) were only needed by tiles of this segment
-      fb_bar_arrive(FB_BAR_EMPTY + ((pbase + n) & 3), FB_ST_THREADS + FB_BUILD);
-      fb_bar_arrive(FB_BAR_EMPTY + ((pbase + n + 1) & 3), FB_ST_THREADS + FB_BUILD);
-      pbase += n + 2;
     }
 #pragma unroll
     for (int c = 0; c < C; ++c) {
