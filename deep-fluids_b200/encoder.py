@@ -292,6 +292,15 @@ class AEEngine(object):
         t = self.adam_t
         return lr * math.sqrt(1.0 - beta2 ** t) / (1.0 - beta1 ** t)
 
+    def optimizer_step_dev(self, lr_t_dev, adam, beta1=0.5, beta2=0.999, eps=1e-8, grad_scale=1.0):
+        """optimizer update with the step size read from device memory + operand repack (CUDA-graph capturable)"""
+        P = self.params
+        if adam:
+            K.adam_step_dev(P.data, P.grad, P.m, P.v, lr_t_dev, beta1, beta2, eps, grad_scale)
+        else:
+            K.adam_step_dev(P.data, P.grad, None, None, lr_t_dev, 0.0, 0.0, 0.0, grad_scale)
+        self.repack()
+
     def optimizer_step(self, lr, adam=True, beta1=0.5, beta2=0.999, eps=1e-8, grad_scale=1.0):
         P = self.params
         if adam:

@@ -258,8 +258,26 @@ class Trainer(object):
             f["vel"] = self._vel
         return f
 
+    def _step_body_ae(self, x, y):
+        """AE: s, z = AE(x); x_ = curl(s); loss = w1*L1 + w2*L1(J) + w4*mean((y[:,:,-1] - z[:,-p_num:])^2) (trainer.py:359-387)
+        and its backward (everything before the gradient exchange)"""
+        ae = self.ae
+        y_last = y[:, :, -1].contiguous() if y.dim() == 3 else y[:, -self.p_num:].contiguous()
+        ae.zero_grad()
+        pot, z = ae.forward(x)
+        fused = self._fused_args(x)
+        if fused is None:
+            self._loss_and_grad(pot, x)   # use_curl: x_ = curl(s) (trainer.py:359-361); else x_ = the decoder output (:363)
+        K.ae_loss_p(z, y_last, ae.dz, self._loss_p, self.w4)
+        if fused is None:
+            ae.backward(self._dpot, self.p_num, self.sparsity, self.w5)
+        else:
+            ae.backward(None, self.p_num, self.sparsity, self.w5, fused=fused)
+
     def _step_body_a(self, x, y, want_vel=False, zero=True):
         """zero grads, forward, fused loss + dL/dpot, backward (everything before the gradient exchange)"""
+        if 'ae' in self.arch:
+            return self._step_body_ae(x, y)
         eng = self.engine
         if zero:
             eng.zero_grad()
@@ -334,6 +352,25 @@ class Trainer(object):
         if 'dg' in self.arch:
             return self._train_step_dg(x, y)
         if self.use_graph and not want_vel:
+            return self._replay_step(x, y)
+        # ---- eager path (debug / per-kernel timing / want_vel / ops-level engine) ----
+        if self.accum > 1:
+            raise NotImplementedError("gradient accumulation runs through the captured step (DFL_CUDA_GRAPH=1)")
+        vel = self._step_body_a(x, y, want_vel)
+        if want_vel:
+            self.G_ = vel
+        scale = dp.allreduce_grads_(eng.params.grad)
+        if self.optimizer == 'adam':
+            eng.adam_step(self.g_lr, self.beta1, self.beta2, 1e-8, scale)
+        else:
+            eng.sgd_step(self.g_lr, scale)
+        self.step += 1
+        return self._loss3
+
+    def _replay_step(self, x, y):
+        """one optimizer step through the captured CUDA graph(s) (generator and AE)"""
+        eng = self.engine
+        if True:
             if not self._captured:
                 self._capture()
             if x.data_ptr() != self._xs.data_ptr():
@@ -367,19 +404,6 @@ class Trainer(object):
             K.PROF.launches += self.launches_per_step
             self.step += 1
             return self._loss3
-        # ---- eager path (debug / per-kernel timing / want_vel / ops-level engine) ----
-        if self.accum > 1:
-            raise NotImplementedError("gradient accumulation runs through the captured step (DFL_CUDA_GRAPH=1)")
-        vel = self._step_body_a(x, y, want_vel)
-        if want_vel:
-            self.G_ = vel
-        scale = dp.allreduce_grads_(eng.params.grad)
-        if self.optimizer == 'adam':
-            eng.adam_step(self.g_lr, self.beta1, self.beta2, 1e-8, scale)
-        else:
-            eng.sgd_step(self.g_lr, scale)
-        self.step += 1
-        return self._loss3
 
     def update_lr(self, step_in_loop):
         """`sess.run(self.g_lr_update)` (trainer.py:284-288): evaluated with the already-incremented global step."""
@@ -456,7 +480,9 @@ class Trainer(object):
         self._dpot = torch.empty_like(self.ae.dec.pot)
         nb = K.cabi.lib().dfl_stencil_loss_workspace_bytes(K.dims_array(self.x.shape[:-1]), self.x.dim() - 2)
         self._ws = torch.empty(nb, dtype=torch.uint8, device=self.device)
-        self.use_graph = False
+        # the whole AE step (~450 launches at 128^3) replays as one CUDA graph, like the generator's
+        self.use_graph = bool(int(os.environ.get("DFL_CUDA_GRAPH", "1"))) and isinstance(self.ae, AEEngine)
+        self._engine_cls = None
         self._captured = False
         self._xs = self._ys = None
         self.loss = self.loss_l1 = self.loss_j_l1 = self.loss_p = None
@@ -468,17 +494,10 @@ class Trainer(object):
             x, y = self.batch_manager.batch()
         self.x, self.y = x, y
         ae = self.ae
-        y_last = y[:, :, -1].contiguous() if y.dim() == 3 else y[:, -self.p_num:].contiguous()
-        ae.zero_grad()
-        pot, z = ae.forward(x)
-        fused = self._fused_args(x)
-        if fused is None:
-            self._loss_and_grad(pot, x)   # use_curl: x_ = curl(s) (trainer.py:359-361); else x_ = the decoder output (:363)
-        K.ae_loss_p(z, y_last, ae.dz, self._loss_p, self.w4)
-        if fused is None:
-            ae.backward(self._dpot, self.p_num, self.sparsity, self.w5)
-        else:
-            ae.backward(None, self.p_num, self.sparsity, self.w5, fused=fused)
+        if self.use_graph:
+            self._replay_step(x, y)
+            return self._loss3, self._loss_p
+        self._step_body_ae(x, y)
         scale = dp.allreduce_grads_(ae.params.grad)
         ae.optimizer_step(self.g_lr, self.optimizer == 'adam', self.beta1, self.beta2, 1e-8, scale)
         self.step += 1
