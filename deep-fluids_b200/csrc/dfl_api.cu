@@ -68,6 +68,7 @@ size_t lastconv_curl_loss_bwd_workspace_bytes();
 int lastconv_curl_loss_bwd(const void* s, const float* pot, const float* x, const float* w, const void* mask_src, void* ds,
                            void* ds_masked, float* dw, float* db, float* dpot, float* vel, float* loss3, void* workspace,
                            const int64_t* dims, float w1, float w2, float grad_scale, cudaStream_t st);
+int pack_phase_weights(const float* W, void* wf, void* wd, int nd, int cin, int cout, cudaStream_t st);
 int comm_unique_id(void* id128);
 int comm_init(void** comm, int nranks, const void* id128, int rank);
 int allreduce(void* buf, size_t count, int dtype, void* comm, cudaStream_t st);
@@ -111,7 +112,7 @@ int lastconv_fwd_tc(const void* s, const float* w, const float* bias, float* out
 int lastconv_bwd_tc(const void* s, const float* dout, const float* w, const void* mask_src, void* ds, void* ds_masked,
                     float* dw, float* db, const int64_t* dims, int nd, int cout, cudaStream_t st);
 int pool_mask(const void* g, const void* mask_src, void* ds, void* dmasked, const int64_t* cdims, int nd,
-              cudaStream_t st);
+              cudaStream_t st, const void* addend = nullptr);
 int bias_grad(const void* d, float* db, size_t npos, cudaStream_t st);
 int pack_conv_weights(const float* W, void* wf, void* wd, int taps, int cin, int cout, int cin_ld, cudaStream_t st);
 int pack_conv_weights_multi(const void* ptrs, int n_layers, int taps, int cin, int cout, cudaStream_t st);
@@ -191,6 +192,9 @@ int dfl_lastconv_curl_loss_bwd(const void* s, const float* pot, const float* x, 
   }
   return lastconv_curl_loss_bwd(s, pot, x, w, mask_src, ds, ds_masked, dw, db, dpot, vel, loss3, workspace, dims, w1, w2,
                                 grad_scale, ST(stream));
+}
+int dfl_pack_phase_weights(const float* w, void* w_fwd, void* w_dgrad, int ndim, int cin, int cout, void* stream) {
+  return pack_phase_weights(w, w_fwd, w_dgrad, ndim, cin, cout, ST(stream));
 }
 int dfl_comm_unique_id(void* id128) { return comm_unique_id(id128); }
 int dfl_comm_init(void** comm, int nranks, const void* id128, int rank) { return comm_init(comm, nranks, id128, rank); }
@@ -308,6 +312,10 @@ int dfl_pool_mask(const void* g, const void* mask_src, void* ds, void* dmasked, 
                   void* stream) {
   DFL_REQUIRE(!(dmasked && !mask_src), "pool_mask: dmasked requested without mask_src");
   return pool_mask(g, mask_src, ds, dmasked, cdims, ndim, ST(stream));
+}
+int dfl_pool_mask_add(const void* g, const void* addend, const void* mask_src, void* ds, void* dmasked, const int64_t* cdims,
+                      int ndim, void* stream) {
+  return pool_mask(g, mask_src, ds, dmasked, cdims, ndim, ST(stream), addend);
 }
 int dfl_adam_step(float* param, const float* grad, float* m, float* v, size_t n, float lr_t, float beta1, float beta2,
                   float eps, float grad_scale, void* stream) {

@@ -51,7 +51,8 @@ constexpr int CT_THREADS = 192;
 constexpr int CT_SMEM_BYTES = CT_STAGES * CT_STAGE_BYTES + 1024 /*align slack*/ + 1024 /*barriers, bias*/;
 
 enum : int { CF_LRELU = 1, CF_OUT2_UPSAMPLE = 2, CF_MASK_AFTER_RESIDUAL = 4, CF_SPLIT_IO = 8 };
-constexpr int CT_MAX_TAPS = 27;
+constexpr int CT_MAX_TAPS = 64;                    // 27 for a 3x3x3 layer; 64 = 8 output phases x 2x2x2 taps of the
+                                                  // data gradient of a phase-decomposed upsample-conv (engine.py)
 
 struct ConvTcParams {
   int B, D, H, W;
@@ -871,7 +872,7 @@ int conv_tap_launch(const void* x, const void* w_packed, const float* bias, void
                     int out_stride, const int32_t* out_off, int64_t w_ld, int flags, cudaStream_t st) {
   DFL_REQUIRE(nd == 2 || nd == 3, "conv_tap: ndim must be 2 or 3");
   DFL_REQUIRE(cin == 64 || (cin >= 128 && cin % 128 == 0), "conv_tap: Cin must be 64 or a multiple of 128 (got %d)", cin);
-  DFL_REQUIRE(ntap >= 1 && ntap <= CT_MAX_TAPS, "conv_tap: 1..27 taps (got %d)", ntap);
+  DFL_REQUIRE(ntap >= 1 && ntap <= CT_MAX_TAPS, "conv_tap: 1..64 taps (got %d)", ntap);
   DFL_REQUIRE(in_stride == 1 || in_stride == 2, "conv_tap: in_stride must be 1 or 2");
   DFL_REQUIRE(out || out2, "conv_tap: no output buffer given");
   ConvTcParams p{};

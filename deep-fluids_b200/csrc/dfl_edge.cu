@@ -91,9 +91,9 @@ int fc_bwd(const float* z, const void* dout, float* dW, float* db, int B, int K,
 // =============================================================================================
 // pool_mask: ds[b,z,y,x,c] = sum over the 2x2(x2) children of g (fine grid);  dmasked = ds * lrelu'(mask_src)
 // =============================================================================================
-__global__ void pool_mask_kernel(const __nv_bfloat16* __restrict__ g, const __nv_bfloat16* __restrict__ mask_src,
-                                 __nv_bfloat16* __restrict__ ds, __nv_bfloat16* __restrict__ dmasked, int B, int D,
-                                 int H, int W, int zr) {
+__global__ void pool_mask_kernel(const __nv_bfloat16* __restrict__ g, const __nv_bfloat16* __restrict__ addend,
+                                 const __nv_bfloat16* __restrict__ mask_src, __nv_bfloat16* __restrict__ ds,
+                                 __nv_bfloat16* __restrict__ dmasked, int B, int D, int H, int W, int zr) {
   // coarse dims D,H,W; fine dims D*zr, 2H, 2W; 16 threads per voxel (8 channels each)
   const size_t n = static_cast<size_t>(B) * D * H * W * 16;
   for (size_t idx = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; idx < n;
@@ -121,6 +121,15 @@ __global__ void pool_mask_kernel(const __nv_bfloat16* __restrict__ g, const __nv
           }
         }
     const size_t off = (idx >> 4) * 128 + q * 8;
+    if (addend) {        // a coarse-grid term of the same gradient (phase-decomposed upsample-conv: its data gradient)
+      const uint4 av = __ldg(reinterpret_cast<const uint4*>(addend + off));
+      const uint32_t w[4] = {av.x, av.y, av.z, av.w};
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        s[2 * k] += __uint_as_float(w[k] << 16);
+        s[2 * k + 1] += __uint_as_float(w[k] & 0xFFFF0000u);
+      }
+    }
     auto pack = [](float a, float b2) {
       __nv_bfloat162 h = __floats2bfloat162_rn(a, b2);
       return *reinterpret_cast<uint32_t*>(&h);
@@ -141,14 +150,68 @@ __global__ void pool_mask_kernel(const __nv_bfloat16* __restrict__ g, const __nv
 }
 
 int pool_mask(const void* g, const void* mask_src, void* ds, void* dmasked, const int64_t* cdims, int nd,
-              cudaStream_t st) {
+              cudaStream_t st, const void* addend) {
   const int B = cdims[0], D = nd == 3 ? cdims[1] : 1, H = cdims[nd - 1], W = cdims[nd];
   const size_t n = static_cast<size_t>(B) * D * H * W * 16;
   const int grid = static_cast<int>(std::min<size_t>((n + 255) / 256, static_cast<size_t>(num_sms()) * 16));
-  pool_mask_kernel<<<grid, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(g), static_cast<const __nv_bfloat16*>(mask_src),
+  pool_mask_kernel<<<grid, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(g), static_cast<const __nv_bfloat16*>(addend),
+                                         static_cast<const __nv_bfloat16*>(mask_src),
                                          static_cast<__nv_bfloat16*>(ds), static_cast<__nv_bfloat16*>(dmasked), B, D, H, W,
                                          nd == 3 ? 2 : 1);
   DFL_LAUNCH_OK("pool_mask_kernel");
+  return DFL_OK;
+}
+
+// =============================================================================================
+// pack_phase_weights: operands of the PHASE-DECOMPOSED upsample-conv.
+// conv3(upsample_x2(s)) (model.py:76-79 followed by :67-69) evaluated at the fine voxel 2p + r (r = phase, one bit per
+// axis) only ever sees TWO distinct coarse voxels per axis -- r = 0: s[p-1] (tap 0) and s[p] (taps 1 + 2); r = 1: s[p]
+// (taps 0 + 1) and s[p+1] (tap 2) -- so it equals 2^nd convolutions with 2^nd taps on the coarse tensor whose weights are
+// sums of the layer's 3^nd taps: 8/27 of the dense FLOPs in 3D, 4/9 in 2D; the zero padding carries over unchanged.
+//   w   fp32 TF layout [3^nd][cin][cout]
+//   wf  bf16 [P][cout][T*cin]      forward operand of phase r (rows co, columns (tap o, ci))          P = T = 2^nd
+//   wd  bf16 [cin][P*T*cout]       data-gradient operand (rows ci, columns (phase r, tap o, co))
+// phase / tap indices: most significant bit = first spatial axis (z in 3D); tap bit o_a = 0 -> the lower coarse offset.
+// =============================================================================================
+__global__ void pack_phase_weights_kernel(const float* __restrict__ W, __nv_bfloat16* __restrict__ wf,
+                                          __nv_bfloat16* __restrict__ wd, int nd, int cin, int cout) {
+  const int P = 1 << nd, T = 1 << nd;
+  const size_t n = static_cast<size_t>(P) * T * cin * cout;
+  for (size_t idx = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; idx < n;
+       idx += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int co = idx % cout;
+    size_t v = idx / cout;
+    const int ci = v % cin; v /= cin;
+    const int o = v % T;
+    const int r = static_cast<int>(v / T);
+    // per axis: the fine taps [lo, hi] that fold onto coarse offset bit o_a in phase bit r_a
+    float acc = 0.f;
+    int lo[3], hi[3];
+    for (int a = 0; a < nd; ++a) {
+      const int ra = (r >> (nd - 1 - a)) & 1, oa = (o >> (nd - 1 - a)) & 1;
+      if (ra == 0) { lo[a] = oa ? 1 : 0; hi[a] = oa ? 2 : 0; }
+      else { lo[a] = oa ? 2 : 0; hi[a] = oa ? 2 : 1; }
+    }
+    if (nd == 2) { lo[2] = hi[2] = 0; }
+    for (int t0 = lo[0]; t0 <= hi[0]; ++t0)
+      for (int t1 = lo[1]; t1 <= hi[1]; ++t1)
+        for (int t2 = lo[2]; t2 <= hi[2]; ++t2) {
+          const int t = nd == 3 ? (t0 * 3 + t1) * 3 + t2 : t0 * 3 + t1;
+          acc += __ldg(W + (static_cast<size_t>(t) * cin + ci) * cout + co);
+        }
+    const __nv_bfloat16 h = __float2bfloat16_rn(acc);
+    wf[(static_cast<size_t>(r) * cout + co) * (static_cast<size_t>(T) * cin) + static_cast<size_t>(o) * cin + ci] = h;
+    wd[static_cast<size_t>(ci) * (static_cast<size_t>(P) * T * cout) + (static_cast<size_t>(r) * T + o) * cout + co] = h;
+  }
+}
+
+int pack_phase_weights(const float* W, void* wf, void* wd, int nd, int cin, int cout, cudaStream_t st) {
+  DFL_REQUIRE(nd == 2 || nd == 3, "pack_phase_weights: ndim must be 2 or 3");
+  DFL_REQUIRE(W && wf && wd, "pack_phase_weights: null tensor");
+  const size_t n = static_cast<size_t>(1 << nd) * (1 << nd) * cin * cout;
+  const int grid = static_cast<int>(std::min<size_t>((n + 255) / 256, static_cast<size_t>(num_sms()) * 8));
+  pack_phase_weights_kernel<<<grid, 256, 0, st>>>(W, static_cast<__nv_bfloat16*>(wf), static_cast<__nv_bfloat16*>(wd), nd, cin, cout);
+  DFL_LAUNCH_OK("pack_phase_weights_kernel");
   return DFL_OK;
 }
 

@@ -117,6 +117,11 @@ class GeneratorEngine(object):
                     self.params.p(k).copy_(xavier_uniform(tuple(shp), g, self.device))
         self.variables = list(tab.keys())
         self.inference = bool(inference)
+        # Phase-decomposed upsample-conv (DFL_PHASE_UPCONV=1): the first conv of blocks 1.. reads upscale(s), i.e. each fine
+        # voxel 2p + r only sees two coarse voxels per axis -> 2^nd convolutions with 2^nd taps and pre-summed weights on
+        # the coarse tensor: 8/27 (3D) / 4/9 (2D) of the dense layer's forward and data-gradient FLOPs, and the data
+        # gradient lands on the coarse grid (no full-resolution gradient of the up-sampled tensor is written or pooled).
+        self.phase = (os.environ.get("DFL_PHASE_UPCONV", "0") == "1" and type(self).precision == "bf16" and self.rep > 1)
         self._alloc_operands()
         self.repack()
         self._alloc()
@@ -143,6 +148,13 @@ class GeneratorEngine(object):
             for cn in row:
                 self.wf[cn] = torch.empty(filters, self.taps * filters, dtype=torch.bfloat16, device=self.device)
                 self.wd[cn] = torch.empty(filters, self.taps * filters, dtype=torch.bfloat16, device=self.device)
+        self.wf_phase, self.wd_phase = {}, {}
+        if getattr(self, "phase", False):
+            P = 2 ** self.nd
+            for row in self.conv_names[1:]:
+                cn = row[0]
+                self.wf_phase[cn] = torch.empty(P, filters, P * filters, dtype=torch.bfloat16, device=self.device)
+                self.wd_phase[cn] = torch.empty(filters, P * P * filters, dtype=torch.bfloat16, device=self.device)
 
     def _alloc(self):
         """activations (bf16) and gradient scratch"""
@@ -181,6 +193,45 @@ class GeneratorEngine(object):
             self._pack_table = torch.tensor(tab, dtype=torch.int64, device=self.device)
             self._pack_n = len(names)
         K.pack_conv_weights_multi(self._pack_table, self._pack_n, self.taps, self.filters, self.filters)
+        for cn in self.wf_phase:
+            K.pack_phase_weights(self.params.p(cn + "/weights"), self.wf_phase[cn], self.wd_phase[cn])
+
+    # ------------------------------------------------------------------ phase-decomposed upsample-conv
+    def _phase_bits(self, r):
+        return [(r >> (self.nd - 1 - a)) & 1 for a in range(self.nd)]
+
+    def _phase_fwd(self, i, cn, bias):
+        """first conv of block i >= 1 on x0[i] = upscale(s): one launch per output phase r; coarse voxel p reads
+        x0[2 (p + off)] = s[p + off] (TMA element stride 2), off in {-1, 0} (r_a = 0) / {0, +1} (r_a = 1) per axis, and the
+        result goes to the fine voxel 2p + r."""
+        nd, F, P = self.nd, self.filters, 2 ** self.nd
+        coarse, fine = self.level_shape[i - 1], self.level_shape[i]
+        dense = 2.0 * self.B * float(np.prod(fine)) * F * F * self.taps
+        for r in range(P):
+            rr = self._phase_bits(r)
+            taps = []
+            for o in range(P):
+                ob = self._phase_bits(o)
+                off = [(ob[a] - 1) if rr[a] == 0 else ob[a] for a in range(nd)]
+                taps.append([0] * (3 - nd) + [2 * v for v in off] + [o * F])
+            K.conv_taps(self.x0[i], self.wf_phase[cn][r], bias, self.y[i][0], None, None, None, [self.B] + coarse, fine, F, 2,
+                        taps, 2, rr, flags=K.CONV_LRELU, alg_flops=dense / P)
+
+    def _phase_dgrad(self, i, cn, dpre, out):
+        """data gradient of that layer w.r.t. the COARSE tensor s: dS[q] = sum_r sum_off dY[2 (q - off) + r] Wp[r][off]^T,
+        ONE launch with all 2^nd x 2^nd (phase, tap) pairs accumulated in TMEM."""
+        nd, F, P = self.nd, self.filters, 2 ** self.nd
+        coarse, fine = self.level_shape[i - 1], self.level_shape[i]
+        dense = 2.0 * self.B * float(np.prod(fine)) * F * F * self.taps
+        taps = []
+        for r in range(P):
+            rr = self._phase_bits(r)
+            for o in range(P):
+                ob = self._phase_bits(o)
+                off = [(ob[a] - 1) if rr[a] == 0 else ob[a] for a in range(nd)]
+                taps.append([0] * (3 - nd) + [rr[a] - 2 * off[a] for a in range(nd)] + [(r * P + o) * F])
+        K.conv_taps(dpre, self.wd_phase[cn], None, out, None, None, None, [self.B] + coarse, coarse, F, 2, taps, 1, [0] * nd,
+                    alg_flops=dense)
 
     # ------------------------------------------------------------------ forward (model.py:5-46 / :48-87)
     def forward(self, z):
@@ -196,7 +247,9 @@ class GeneratorEngine(object):
             for c in range(self.num_conv):
                 cn = self.conv_names[i][c]
                 bias = P.p(cn + "/biases")
-                if c < self.num_conv - 1:
+                if c == 0 and i > 0 and self.phase and self.num_conv > 1:
+                    self._phase_fwd(i, cn, bias)
+                elif c < self.num_conv - 1:
                     K.conv3x3(cur, self.wf[cn], bias, out=self.y[i][c], flags=K.CONV_LRELU)
                 elif i < self.rep - 1:   # x += x0; x = upscale(x, 2); x0 = x   (model.py:34-37 / :76-79)
                     K.conv3x3(cur, self.wf[cn], bias, out=self.y[i][c], out2=self.x0[i + 1], residual=self.x0[i],
@@ -230,9 +283,15 @@ class GeneratorEngine(object):
         else:
             K.lastconv_bwd(self.s, dpot, P.p(self.last_name + "/weights"), self.y[top][nc - 1], ds, dpre,
                            P.g(self.last_name + "/weights"), P.g(self.last_name + "/biases"))
+        # gradient scratch: four full-resolution buffers re-viewed per level; roles rotate so that no kernel reads and
+        # writes different voxels of the same buffer (b_ds holds ds, b_dp the running dL/d(pre-activation))
+        b_ds, b_dp, b_a, b_b = 0, 1, 2, 3
         for i in range(top, -1, -1):
-            other = self._gview(2, i)
-            gx0 = self._gview(3, i)
+            ds = self._gview(b_ds, i)
+            dpre = self._gview(b_dp, i)
+            other = self._gview(b_a, i)
+            cur_b, oth_b = b_dp, b_a
+            phase0 = self.phase and i > 0 and nc > 1
             for c in range(nc - 1, -1, -1):
                 cn = self.conv_names[i][c]
                 xin = self.y[i][c - 1] if c > 0 else self.x0[i]
@@ -252,15 +311,28 @@ class GeneratorEngine(object):
                 if c > 0:     # dL/d(pre-activation of layer c-1) = dgrad * lrelu'(y[c-1])
                     K.conv3x3(dpre, self.wd[cn], None, out=other, mask_src=self.y[i][c - 1])
                     dpre, other = other, dpre
+                    cur_b, oth_b = oth_b, cur_b
+                elif phase0:  # data gradient straight onto the coarse grid (the residual branch's ds is pooled below)
+                    self._phase_dgrad(i, cn, dpre, self._gview(b_b, i - 1))
                 else:         # dL/dx0 = dgrad + residual-branch gradient ds
+                    gx0 = self._gview(b_b, i)
                     K.conv3x3(dpre, self.wd[cn], None, out2=gx0, residual=ds)
                 if fork:
                     cur.wait_stream(self._side)
             if i > 0:         # x0[i] = upscale(y4[i-1] + x0[i-1]): pool the children, then the lrelu derivative
-                ds = self._gview(0, i - 1)
-                dpre = self._gview(1, i - 1)
-                K.pool_mask(gx0, self.y[i - 1][nc - 1], ds, dpre)
+                ysrc = self.y[i - 1][nc - 1]
+                if phase0:
+                    # ds_low = pool(ds) + (phase data gradient, already coarse, in b_b): written in place over the addend;
+                    # dpre_low overwrites the fine dpre (its readers are queued ahead on the stream)
+                    t = self._gview(b_b, i - 1)
+                    K.pool_mask(ds, ysrc, t, self._gview(cur_b, i - 1), addend=t)
+                    b_ds, b_b = b_b, b_ds
+                    b_dp, b_a = cur_b, oth_b
+                else:
+                    K.pool_mask(gx0, ysrc, self._gview(b_ds, i - 1), self._gview(cur_b, i - 1))
+                    b_dp, b_a = cur_b, oth_b
             else:
+                gx0 = self._gview(b_b, 0)
                 gw, gb = P.g(self.name + "/0_fc/weights"), P.g(self.name + "/0_fc/biases")
                 if getattr(self, "accumulate_fc", False):
                     # dfl_fc_bwd OVERWRITES its outputs; under gradient accumulation (several backward passes per

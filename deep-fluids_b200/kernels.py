@@ -17,6 +17,7 @@ _DT = {torch.float32: F32, torch.bfloat16: BF16}
 class _Prof(object):
     """Launch counter (bench.py's `gpu_launches` claim) and optional per-kernel CUDA-event timing."""
     launches = 0
+    exec_flops = 0.0     # MMA FLOPs actually executed by conv_taps launches (== algorithmic unless alg_flops is passed)
     events = None        # when a list: (kernel name, start event, end event, algorithmic work) tuples are appended
 
     @classmethod
@@ -223,6 +224,12 @@ def pack_conv_weights(w, w_fwd=None, w_dgrad=None):
     return w_fwd, w_dgrad
 
 
+def pack_phase_weights(w, w_fwd, w_dgrad):
+    """fp32 TF-layout [3,(3,)3,Cin,Cout] -> operands of the phase-decomposed upsample-conv (dfl_pack_phase_weights)"""
+    nd = w.dim() - 2
+    PROF.timed("pack_conv_weights", 0.0, lambda: check(cabi.lib().dfl_pack_phase_weights(_p(w), _p(w_fwd), _p(w_dgrad), nd, w.shape[-2], w.shape[-1], _st())))
+
+
 def pack_conv_weights_multi(ptr_table, n_layers, taps, cin, cout):
     """all same-shape layers in one launch; ptr_table = int64 device tensor [3, n_layers] of {w, w_fwd, w_dgrad} addresses"""
     PROF.timed("pack_conv_weights", 0.0, lambda: check(cabi.lib().dfl_pack_conv_weights_multi(
@@ -249,7 +256,7 @@ def pack_conv_weights_ex(w, w_fwd, w_dgrad, cin_ld):
 
 
 def conv_taps(x, w_rows, bias, out, out2, residual, mask_src, tile_dims, out_dims, cin, in_stride, taps, out_stride,
-              out_off, flags=0):
+              out_off, flags=0, alg_flops=None):
     """generic per-tap tensor-core conv (dfl_conv_taps).  x: channel-blocked input [nblk*B,(D,)H,W,128]; w_rows: bf16
     2-D view [128, w_ld] of the packed weight rows of this output block; taps: list of (dz, dy, dx, kcol)."""
     nd = x.dim() - 2
@@ -257,6 +264,9 @@ def conv_taps(x, w_rows, bias, out, out2, residual, mask_src, tile_dims, out_dim
     oarr = (C.c_int32 * 3)(*([int(v) for v in out_off] + [0] * (3 - len(out_off))))
     assert w_rows.shape[0] == 128 and w_rows.stride(1) == 1
     flops = 2.0 * float(torch.tensor(tile_dims).prod()) * cin * 128 * len(taps)
+    PROF.exec_flops += flops
+    if alg_flops is not None:      # phase-decomposed upsample-conv: the roofline numerator stays the dense layer's FLOPs
+        flops = alg_flops
     PROF.timed("conv_tap", flops, lambda: check(cabi.lib().dfl_conv_taps(
         _p(x), C.c_void_p(w_rows.data_ptr()), _p(bias), _p(out), _p(out2), _p(residual), _p(mask_src),
         dims_array(x.shape[:-1]), dims_array(tile_dims), dims_array(out_dims), nd, cin, in_stride, len(taps), tarr,
@@ -433,11 +443,14 @@ def lastconv_curl_loss_bwd(s, pot, x, w, mask_src, ds, ds_masked, dw, db, loss3,
         _p(workspace), d, nd, float(w1), float(w2), float(grad_scale), _st())))
 
 
-def pool_mask(g, mask_src, ds, dmasked):
-    """g: fine-grid gradient [B,(2D,)2H,2W,128]; ds / dmasked: coarse [B,(D,)H,W,128]"""
+def pool_mask(g, mask_src, ds, dmasked, addend=None):
+    """g: fine-grid gradient [B,(2D,)2H,2W,128]; ds / dmasked: coarse [B,(D,)H,W,128]; addend: optional coarse term"""
     ref = ds if ds is not None else dmasked
     d, nd = _spatial(ref)
-    PROF.timed("pool_mask", 0.0, lambda: check(cabi.lib().dfl_pool_mask(_p(g), _p(mask_src), _p(ds), _p(dmasked), d, nd, _st())))
+    if addend is None:
+        PROF.timed("pool_mask", 0.0, lambda: check(cabi.lib().dfl_pool_mask(_p(g), _p(mask_src), _p(ds), _p(dmasked), d, nd, _st())))
+    else:
+        PROF.timed("pool_mask", 0.0, lambda: check(cabi.lib().dfl_pool_mask_add(_p(g), _p(addend), _p(mask_src), _p(ds), _p(dmasked), d, nd, _st())))
 
 
 # ------------------------------------------------------------------ optimizer / misc

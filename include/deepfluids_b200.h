@@ -174,6 +174,18 @@ int dfl_lastconv_curl_loss_bwd(const void* s, const float* pot, const float* x, 
  *   ds = sum of the 2x2(x2) children of g;  dmasked = ds * lrelu'(mask_src).  cdims = COARSE dims. */
 int dfl_pool_mask(const void* g, const void* mask_src, void* ds, void* dmasked, const int64_t* cdims, int ndim,
                   void* stream);
+/* Operands of the phase-decomposed upsample-conv: conv3(upsample_x2(s)) at the fine voxel 2p + r equals, per phase r (one
+ * bit per axis), a convolution with 2 taps per axis on the COARSE tensor whose weights are sums of the layer's taps
+ * (r = 0: {w0 | w1 + w2} on offsets {-1, 0}; r = 1: {w0 + w1 | w2} on {0, +1}): 8/27 of the dense FLOPs in 3D, 4/9 in 2D.
+ *   w fp32 TF layout [3^nd][cin][cout] -> w_fwd bf16 [P][cout][T*cin], w_dgrad bf16 [cin][P*T*cout], P = T = 2^ndim;
+ * run through dfl_conv_taps: forward = P launches (in_stride 2 on the up-sampled tensor = its coarse source, out_stride 2,
+ * out_off = phase), data gradient = ONE launch with all P*T taps on the coarse grid. */
+int dfl_pack_phase_weights(const float* w, void* w_fwd, void* w_dgrad, int ndim, int cin, int cout, void* stream);
+/* same with a coarse-grid addend: ds = sum of the children of g + addend.  Used by the phase-decomposed upsample-conv
+ * (model.py:76-79 followed by :67-69 = eight 2x2x2 convolutions on the coarse tensor): the first conv's data gradient lands
+ * on the coarse grid directly (`addend`), only the residual branch's gradient `g` still has to be pooled. */
+int dfl_pool_mask_add(const void* g, const void* addend, const void* mask_src, void* ds, void* dmasked, const int64_t* cdims,
+                      int ndim, void* stream);
 
 /* ---- encoder / auto-encoder extensions (EncoderBE/EncoderBE3, AE/AE3: model.py:118-216; trainer.py:357-396) ------
  * Activations wider than 128 channels are stored as channel blocks [nblk*B,(D,)H,W,128] (block-major), so the concat
