@@ -83,7 +83,9 @@ int conv_tc_launch(const void* x, const void* w_packed, const float* bias, void*
                    const void* residual, const void* mask_src, const int64_t* dims, int nd, int cin, int cout,
                    int flags, const int32_t* blkmap, int nphys, cudaStream_t st);
 int wgrad_tc_launch(const void* x, const void* dpre, float* dw, float* db, const int64_t* x_dims, const int64_t* dims,
-                    int nd, int in_stride, int pad, int dw_tap_stride, int dw_row_stride, cudaStream_t st, int split = 0);
+                    int nd, int in_stride, int pad, int dw_tap_stride, int dw_row_stride, cudaStream_t st, int split = 0,
+                    int ksize = 3);
+int phase_wgrad_fold(const float* t64, float* dw, int nd, int cin, int cout, cudaStream_t st);
 int conv_tap_launch(const void* x, const void* w_packed, const float* bias, void* out, void* out2,
                     const void* residual, const void* mask_src, const int64_t* in_dims, const int64_t* tile_dims,
                     const int64_t* out_dims, int nd, int cin, int in_stride, int ntap, const int32_t* taps,
@@ -269,6 +271,14 @@ int dfl_conv3x3_wgrad_split(const void* x2, const void* dpre2, float* dw, float*
 int dfl_conv_wgrad_ex(const void* x, const void* dpre, float* dw, float* db, const int64_t* x_dims, const int64_t* dims,
                       int ndim, int in_stride, int pad, int dw_tap_stride, int dw_row_stride, void* stream) {
   return wgrad_tc_launch(x, dpre, dw, db, x_dims, dims, ndim, in_stride, pad, dw_tap_stride, dw_row_stride, ST(stream));
+}
+int dfl_phase_wgrad(const void* dy_fine, const void* s_coarse, float* t_scratch, const int64_t* fine_dims,
+                    const int64_t* coarse_dims, int ndim, void* stream) {
+  return wgrad_tc_launch(dy_fine, s_coarse, t_scratch, nullptr, fine_dims, coarse_dims, ndim, 2, 1, 128 * 128, 128, ST(stream),
+                         0, 4);
+}
+int dfl_phase_wgrad_fold(const float* t_scratch, float* dw, int ndim, int cin, int cout, void* stream) {
+  return phase_wgrad_fold(t_scratch, dw, ndim, cin, cout, ST(stream));
 }
 int dfl_conv_taps(const void* x, const void* w_packed, const float* bias, void* out, void* out2, const void* residual,
                   const void* mask_src, const int64_t* in_dims, const int64_t* tile_dims, const int64_t* out_dims, int ndim,

@@ -216,6 +216,49 @@ int pack_phase_weights(const float* W, void* wf, void* wd, int nd, int cin, int 
 }
 
 // =============================================================================================
+// phase_wgrad_fold: weight gradient of the phase-decomposed upsample-conv, folded back onto the layer's 3^nd taps.
+// dfl_phase_wgrad (the tensor-core weight-gradient kernel run as a 4^nd-tap stride-2 correlation between dY on the fine grid
+// and the layer's COARSE input s) leaves T[k][co][ci] = sum_q dY[2q + k - 1][co] * s[q][ci], k in {0..3}^nd, i.e. the gradients
+// of the pre-summed phase weights, transposed.  Per axis the phase (r, off) that reads fine offset k - 1 = r - 2 off carries
+// the taps {0} (k=3), {1,2} (k=1), {0,1} (k=2), {2} (k=0); hence tap t receives k in {3,2} (t=0), {1,2} (t=1), {1,0} (t=2):
+//     dW[t][ci][co] += sum_{k_a in M[t_a]} T[k][co][ci].
+// =============================================================================================
+__global__ void phase_wgrad_fold_kernel(const float* __restrict__ T, float* __restrict__ dw, int nd, int cin, int cout) {
+  const int ntap = nd == 3 ? 27 : 9;
+  const size_t n = static_cast<size_t>(ntap) * cin * cout;
+  for (size_t idx = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; idx < n;
+       idx += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int ci = idx % cin;                 // ci fastest: coalesced reads of T[k][co][ci]
+    size_t v = idx / cin;
+    const int co = v % cout;
+    const int t = static_cast<int>(v / cout);
+    int ta[3] = {0, 0, 0};
+    if (nd == 3) { ta[0] = t / 9; ta[1] = (t / 3) % 3; ta[2] = t % 3; } else { ta[0] = t / 3; ta[1] = t % 3; }
+    float acc = 0.f;
+    const int nk = 1 << nd;
+    for (int m = 0; m < nk; ++m) {
+      int k = 0;
+      for (int a = 0; a < nd; ++a) {
+        const int sel = (m >> (nd - 1 - a)) & 1;
+        const int ka = ta[a] == 0 ? (sel ? 2 : 3) : (ta[a] == 1 ? (sel ? 2 : 1) : (sel ? 0 : 1));
+        k = k * 4 + ka;
+      }
+      acc += __ldg(T + (static_cast<size_t>(k) * cout + co) * cin + ci);
+    }
+    dw[(static_cast<size_t>(t) * cin + ci) * cout + co] += acc;
+  }
+}
+
+int phase_wgrad_fold(const float* T, float* dw, int nd, int cin, int cout, cudaStream_t st) {
+  DFL_REQUIRE(nd == 2 || nd == 3, "phase_wgrad_fold: ndim must be 2 or 3");
+  const size_t n = static_cast<size_t>(nd == 3 ? 27 : 9) * cin * cout;
+  const int grid = static_cast<int>(std::min<size_t>((n + 255) / 256, static_cast<size_t>(num_sms()) * 8));
+  phase_wgrad_fold_kernel<<<grid, 256, 0, st>>>(T, dw, nd, cin, cout);
+  DFL_LAUNCH_OK("phase_wgrad_fold_kernel");
+  return DFL_OK;
+}
+
+// =============================================================================================
 // bias_grad: db[c] += sum_pos d[pos][c]      d bf16 [npos][128]
 // =============================================================================================
 __global__ void __launch_bounds__(256) bias_grad_kernel(const __nv_bfloat16* __restrict__ d, float* __restrict__ db,

@@ -297,7 +297,8 @@ static void pick_brick_w(int D, int H, int W, int& bd, int& bh, int& bw) {
 // x: [B, xD, xH, xW, 128] bf16 (one 128-channel block), dpre: [B, D, H, W, 128] bf16 (tile domain).  For stride 1
 // x dims == dims; for the gradient of a stride-2 conv x is the fine grid and the TMA walks it with element stride 2.
 int wgrad_tc_launch(const void* x, const void* dpre, float* dw, float* db, const int64_t* x_dims, const int64_t* dims,
-                    int nd, int in_stride, int pad, int dw_tap_stride, int dw_row_stride, cudaStream_t st, int split) {
+                    int nd, int in_stride, int pad, int dw_tap_stride, int dw_row_stride, cudaStream_t st, int split,
+                    int ksize) {
   DFL_REQUIRE(nd == 2 || nd == 3, "wgrad_tc: ndim must be 2 or 3");
   DFL_REQUIRE(in_stride == 1 || in_stride == 2, "wgrad_tc: in_stride must be 1 or 2");
   WgradParams p{};
@@ -305,9 +306,12 @@ int wgrad_tc_launch(const void* x, const void* dpre, float* dw, float* db, const
   p.D = nd == 3 ? static_cast<int>(dims[1]) : 1;
   p.H = static_cast<int>(dims[nd - 1]);
   p.W = static_cast<int>(dims[nd]);
-  p.kd = nd == 3 ? 3 : 1;
-  p.kh = 3;
-  p.kw = 3;
+  // ksize = 4 (with in_stride 2, pad 1): the 4x4(x4) stride-2 correlation behind the weight gradient of a phase-decomposed
+  // upsample-conv (tap offsets -1 .. 2 on the fine grid)
+  DFL_REQUIRE(ksize == 3 || ksize == 4, "wgrad_tc: kernel size must be 3 or 4");
+  p.kd = nd == 3 ? ksize : 1;
+  p.kh = ksize;
+  p.kw = ksize;
   pick_brick_w(p.D, p.H, p.W, p.bd, p.bh, p.bw);
   p.tx = (p.W + p.bw - 1) / p.bw;
   p.ty = (p.H + p.bh - 1) / p.bh;

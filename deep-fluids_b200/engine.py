@@ -122,6 +122,7 @@ class GeneratorEngine(object):
         # the coarse tensor: 8/27 (3D) / 4/9 (2D) of the dense layer's forward and data-gradient FLOPs, and the data
         # gradient lands on the coarse grid (no full-resolution gradient of the up-sampled tensor is written or pooled).
         self.phase = (os.environ.get("DFL_PHASE_UPCONV", "0") == "1" and type(self).precision == "bf16" and self.rep > 1)
+        self.phase_wgrad = self.phase and os.environ.get("DFL_PHASE_WGRAD", "1") == "1"
         self._alloc_operands()
         self.repack()
         self._alloc()
@@ -155,6 +156,7 @@ class GeneratorEngine(object):
                 cn = row[0]
                 self.wf_phase[cn] = torch.empty(P, filters, P * filters, dtype=torch.bfloat16, device=self.device)
                 self.wd_phase[cn] = torch.empty(filters, P * P * filters, dtype=torch.bfloat16, device=self.device)
+            self._t_phase = torch.empty(4 ** self.nd, filters, filters, dtype=torch.float32, device=self.device)
 
     def _alloc(self):
         """activations (bf16) and gradient scratch"""
@@ -301,7 +303,18 @@ class GeneratorEngine(object):
                 # grid leaves SMs idle, the weight gradient runs beside it on a second stream (a fork / join per layer,
                 # captured into the step's CUDA graph as parallel branches)
                 fork = self._side is not None and self._level_tiles[i] < self._fork_below
-                if fork:
+                if c == 0 and phase0 and self.phase_wgrad:
+                    # weight gradient on the phase weights (8/27 of the dense FLOPs in 3D): a 4^nd-tap stride-2 correlation of
+                    # dpre (fine) with the layer's coarse input s = x0[i][::2, ::2(, ::2)] (exactly the values the forward
+                    # read), folded back onto the 3^nd taps; the bias gradient is a column sum of dpre
+                    s_c = self._gview(oth_b, i - 1)
+                    sl = (slice(None),) + (slice(None, None, 2),) * self.nd
+                    s_c.copy_(self.x0[i][sl])
+                    dense = 2.0 * self.B * float(np.prod(self.level_shape[i])) * self.filters * self.filters * self.taps
+                    K.phase_wgrad(dpre, s_c, self._t_phase, P.g(cn + "/weights"), alg_flops=dense)
+                    K.bias_grad(dpre, P.g(cn + "/biases"))
+                    fork = False
+                elif fork:
                     cur = torch.cuda.current_stream()
                     self._side.wait_stream(cur)
                     with torch.cuda.stream(self._side):

@@ -230,6 +230,17 @@ def pack_phase_weights(w, w_fwd, w_dgrad):
     PROF.timed("pack_conv_weights", 0.0, lambda: check(cabi.lib().dfl_pack_phase_weights(_p(w), _p(w_fwd), _p(w_dgrad), nd, w.shape[-2], w.shape[-1], _st())))
 
 
+def phase_wgrad(dy_fine, s_coarse, t_scratch, dw, alg_flops=None):
+    """weight gradient of a phase-decomposed upsample-conv: 4^nd-tap stride-2 tensor-core correlation + fold onto dw"""
+    nd = dy_fine.dim() - 2
+    t_scratch.zero_()
+    flops = 2.0 * (s_coarse.numel() // 128) * 128 * 128 * (4 ** nd)
+    PROF.exec_flops += flops
+    PROF.timed("wgrad_tc", alg_flops if alg_flops is not None else flops, lambda: check(cabi.lib().dfl_phase_wgrad(
+        _p(dy_fine), _p(s_coarse), _p(t_scratch), dims_array(dy_fine.shape[:-1]), dims_array(s_coarse.shape[:-1]), nd, _st())))
+    PROF.timed("phase_wgrad_fold", 0.0, lambda: check(cabi.lib().dfl_phase_wgrad_fold(_p(t_scratch), _p(dw), nd, dw.shape[-2], dw.shape[-1], _st())))
+
+
 def pack_conv_weights_multi(ptr_table, n_layers, taps, cin, cout):
     """all same-shape layers in one launch; ptr_table = int64 device tensor [3, n_layers] of {w, w_fwd, w_dgrad} addresses"""
     PROF.timed("pack_conv_weights", 0.0, lambda: check(cabi.lib().dfl_pack_conv_weights_multi(

@@ -181,6 +181,13 @@ int dfl_pool_mask(const void* g, const void* mask_src, void* ds, void* dmasked, 
  * run through dfl_conv_taps: forward = P launches (in_stride 2 on the up-sampled tensor = its coarse source, out_stride 2,
  * out_off = phase), data gradient = ONE launch with all P*T taps on the coarse grid. */
 int dfl_pack_phase_weights(const float* w, void* w_fwd, void* w_dgrad, int ndim, int cin, int cout, void* stream);
+/* Weight gradient of that layer on 8/27 (3D) of the dense FLOPs: dfl_phase_wgrad runs the tensor-core weight-gradient kernel
+ * as a 4^ndim-tap stride-2 correlation between dy on the FINE grid ([B,(2D,)2H,2W,128] bf16) and the layer's COARSE input s
+ * ([B,(D,)H,W,128] bf16) into t_scratch (fp32 [4^ndim][128][128], zero it first); dfl_phase_wgrad_fold adds the folded result
+ * to the TF-layout gradient dw [3^ndim][cin][cout].  The bias gradient is dfl_bias_grad(dy). */
+int dfl_phase_wgrad(const void* dy_fine, const void* s_coarse, float* t_scratch, const int64_t* fine_dims,
+                    const int64_t* coarse_dims, int ndim, void* stream);
+int dfl_phase_wgrad_fold(const float* t_scratch, float* dw, int ndim, int cin, int cout, void* stream);
 /* same with a coarse-grid addend: ds = sum of the children of g + addend.  Used by the phase-decomposed upsample-conv
  * (model.py:76-79 followed by :67-69 = eight 2x2x2 convolutions on the coarse tensor): the first conv's data gradient lands
  * on the coarse grid directly (`addend`), only the residual branch's gradient `g` still has to be pooled. */
