@@ -335,23 +335,24 @@ def run_gpu_arm(args):
         tr.train_step()
     torch.cuda.synchronize()
     agg = {}
-    for name, s, e, work in K.PROF.events:
-        a = agg.setdefault(name, [0.0, 0.0, 0])
+    for name, s, e, work, xwork in K.PROF.events:
+        a = agg.setdefault(name, [0.0, 0.0, 0, 0.0])
         a[0] += s.elapsed_time(e) * 1e-3
         a[1] += work
         a[2] += 1
+        a[3] += xwork
     K.PROF.events = None
     # every kernel of the step: ms per step and launches per step (CUDA events, eager replay of the same step)
     kernel_ms = {k: {"ms_per_step": round(v[0] / 2 * 1e3, 4), "launches_per_step": v[2] // 2}
                  for k, v in sorted(agg.items(), key=lambda kv: -kv[1][0])}
     for extra in ("conv_tap",):           # stride-2 / per-tap launches count as conv work too (AE)
         if extra in agg:
-            a, e = agg.setdefault("conv_tc", [0.0, 0.0, 0]), agg[extra]
-            a[0] += e[0]; a[1] += e[1]; a[2] += e[2]
-    conv_t, conv_f, conv_n = agg.get("conv_tc", [1e-9, 0.0, 1])
-    wg_t, wg_f, wg_n = agg.get("wgrad_tc", [1e-9, 0.0, 1])
-    st_t, st_b, st_n = agg.get("stencil_fused", [0.0, 0.0, 0])
-    fb_t, fb_b, fb_n = agg.get("lastconv_bwd_fused", [0.0, 0.0, 0])
+            a, e = agg.setdefault("conv_tc", [0.0, 0.0, 0, 0.0]), agg[extra]
+            a[0] += e[0]; a[1] += e[1]; a[2] += e[2]; a[3] += e[3]
+    conv_t, conv_f, conv_n, conv_x = agg.get("conv_tc", [1e-9, 0.0, 1, 0.0])
+    wg_t, wg_f, wg_n, wg_x = agg.get("wgrad_tc", [1e-9, 0.0, 1, 0.0])
+    st_t, st_b, st_n = agg.get("stencil_fused", [0.0, 0.0, 0, 0.0])[:3]
+    fb_t, fb_b, fb_n = agg.get("lastconv_bwd_fused", [0.0, 0.0, 0, 0.0])[:3]
     stencil_note = "inside the step"
     if st_n == 0 and cfg.is_3d:
         # 3D: the loss stencil runs in the prologue of the fused first-backward kernel, so the step has no stencil launch.
@@ -367,24 +368,36 @@ def run_gpu_arm(args):
             flush.zero_()
             K.stencil_loss_fwdbwd(pot_b, xs, dpot=dscr)
         torch.cuda.synchronize()
-        ev = [(s_.elapsed_time(e_) * 1e-3, w_) for n_, s_, e_, w_ in K.PROF.events if n_ == "stencil_fused"][1:]
+        ev = [(s_.elapsed_time(e_) * 1e-3, w_) for n_, s_, e_, w_, _ in K.PROF.events if n_ == "stencil_fused"][1:]
         K.PROF.events = None
         st_t, st_b, st_n = sum(t for t, _ in ev), sum(w_ for _, w_ in ev), len(ev)
         del flush, dscr
     st_t = max(st_t, 1e-12)
     conv_f /= terms                     # PROF counts executed MMA flops; the roofline numerator is algorithmic flops
     wg_f /= terms
+    # phase-decomposed upsample-conv launches are booked with the DENSE layer's algorithmic FLOPs (the roofline numerator
+    # stays algorithmic); what the tensor cores executed is reported beside it
+    eng_ = tr.engine.dec if hasattr(tr.engine, "dec") else tr.engine
+    phase_on = bool(getattr(eng_, "phase", False))
+    nd_ = 3 if cfg.is_3d else 2
+    phase_note = None
+    if phase_on:
+        phase_note = ("first conv of every block after the first = conv3(upscale(s)): forward and data gradient run 2^nd taps "
+                      "per output phase on the coarse tensor (%.3f of the dense FLOPs)%s" % (
+                          (2.0 / 3.0) ** nd_, "; weight gradient = 4^nd-tap stride-2 correlation on the coarse grid (same ratio)"
+                          if getattr(eng_, "phase_wgrad", False) else ""))
     achieved = conv_f / conv_t / 1e12
     roofline = {"kernel": "conv_tc2_kernel (tcgen05 tap-window implicit-GEMM conv, fwd + dgrad launches)", "bound": "tensor",
                 "achieved": achieved, "peak": peaks["tf_sustained"], "unit": "TFLOP/s",
                 "frac": achieved / peaks["tf_sustained"], "peak_source": "%s (sustained bf16, kernel timed inside a long step)" % peaks["src"],
-                "mma_terms_per_flop": terms, "executed_tflops": achieved * terms,
+                "mma_terms_per_flop": terms, "executed_tflops": conv_x / conv_t / 1e12, "phase_upconv": phase_note,
                 "launches_timed": conv_n, "avg_launch_ms": conv_t / conv_n * 1e3, "traffic": load_traffic("conv_tc_kernel"),
                 "traffic_source": "STATIC: dram bytes per launch of a full-resolution launch from the committed ncu --set full "
                                   "capture (profiles/ncu_summary.json), not measured in this run",
                 "share_of_step": conv_t / 2 * accum / (ms_per_step * 1e-3),
                 "others": {
                     "wgrad_tc_kernel": {"bound": "tensor", "achieved": wg_f / wg_t / 1e12, "unit": "TFLOP/s",
+                                        "executed_tflops": wg_x / wg_t / 1e12,
                                         "frac": wg_f / wg_t / 1e12 / peaks["tf_sustained"],
                                         "share_of_step": wg_t / 2 * accum / (ms_per_step * 1e-3)},
                     "stencil_fused_kernel": {"bound": "hbm", "achieved": st_b / st_t / 1e9, "unit": "GB/s",
@@ -399,9 +412,10 @@ def run_gpu_arm(args):
     roofline["kernel_ms"] = kernel_ms
     fl = FLOPS_PER_FIELD[args.workload]
     if fl:
-        roofline["step_conv_tflops_per_gpu"] = value / world * fl / 1e12
+        roofline["step_conv_tflops_per_gpu"] = value / world * fl / 1e12      # algorithmic (dense-layer) FLOPs
         roofline["step_frac_of_peak"] = value / world * fl / 1e12 / peaks["tf_sustained"]
 
+    phase_on_cfg = phase_on
     if rank == 0:
         cpu = cpu_oracle_fields_per_sec(args.workload, 3, 1) if world == 1 and not args.no_cpu else None
         out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
@@ -409,7 +423,7 @@ def run_gpu_arm(args):
                "vs_baseline": None, "dtype": "bf16" if terms == 1 else "f32 (bf16x3 split operands)", "data": "synthetic",
                "config": {"workload": WORKLOADS[args.workload][5], "global_batch": B * world, "per_gpu_batch": B,
                           "micro_batch": cfg.batch_size, "grad_accum_micro_steps": accum,
-                          "parallelism": "dp%d" % world, "filters": 128, "num_conv": 4,
+                          "parallelism": "dp%d" % world, "filters": 128, "num_conv": 4, "phase_upconv": phase_on_cfg,
                           "l2": "per-step working set (>= %.0f MB of activations) exceeds the 126 MB L2; no flush needed"
                                 % (B * float(np.prod(bm._pool[0][0].shape[1:-1])) * 128 * 2 * 6 / 1e6),
                           "precision": PRECISION_NOTE[precision]},

@@ -117,11 +117,12 @@ class GeneratorEngine(object):
                     self.params.p(k).copy_(xavier_uniform(tuple(shp), g, self.device))
         self.variables = list(tab.keys())
         self.inference = bool(inference)
-        # Phase-decomposed upsample-conv (DFL_PHASE_UPCONV=1): the first conv of blocks 1.. reads upscale(s), i.e. each fine
+        # Phase-decomposed upsample-conv (default; DFL_PHASE_UPCONV=0 selects the dense layer): the first conv of blocks 1..
+        # reads upscale(s), i.e. each fine
         # voxel 2p + r only sees two coarse voxels per axis -> 2^nd convolutions with 2^nd taps and pre-summed weights on
         # the coarse tensor: 8/27 (3D) / 4/9 (2D) of the dense layer's forward and data-gradient FLOPs, and the data
         # gradient lands on the coarse grid (no full-resolution gradient of the up-sampled tensor is written or pooled).
-        self.phase = (os.environ.get("DFL_PHASE_UPCONV", "0") == "1" and type(self).precision == "bf16" and self.rep > 1)
+        self.phase = (os.environ.get("DFL_PHASE_UPCONV", "1") == "1" and type(self).precision == "bf16" and self.rep > 1)
         self.phase_wgrad = self.phase and os.environ.get("DFL_PHASE_WGRAD", "1") == "1"
         self._alloc_operands()
         self.repack()

@@ -17,11 +17,12 @@ _DT = {torch.float32: F32, torch.bfloat16: BF16}
 class _Prof(object):
     """Launch counter (bench.py's `gpu_launches` claim) and optional per-kernel CUDA-event timing."""
     launches = 0
-    exec_flops = 0.0     # MMA FLOPs actually executed by conv_taps launches (== algorithmic unless alg_flops is passed)
-    events = None        # when a list: (kernel name, start event, end event, algorithmic work) tuples are appended
+    # when a list: (kernel name, start event, end event, ALGORITHMIC work, EXECUTED work) tuples are appended.  The two differ
+    # only for the phase-decomposed upsample-conv launches, which are booked with the dense layer's algorithmic FLOPs
+    events = None
 
     @classmethod
-    def timed(cls, name, work, fn):
+    def timed(cls, name, work, fn, exec_work=None):
         cls.launches += 1
         if cls.events is None:
             return fn()
@@ -29,7 +30,7 @@ class _Prof(object):
         s.record()
         fn()
         e.record()
-        cls.events.append((name, s, e, work))
+        cls.events.append((name, s, e, work, work if exec_work is None else exec_work))
 
 
 PROF = _Prof
@@ -235,9 +236,9 @@ def phase_wgrad(dy_fine, s_coarse, t_scratch, dw, alg_flops=None):
     nd = dy_fine.dim() - 2
     t_scratch.zero_()
     flops = 2.0 * (s_coarse.numel() // 128) * 128 * 128 * (4 ** nd)
-    PROF.exec_flops += flops
     PROF.timed("wgrad_tc", alg_flops if alg_flops is not None else flops, lambda: check(cabi.lib().dfl_phase_wgrad(
-        _p(dy_fine), _p(s_coarse), _p(t_scratch), dims_array(dy_fine.shape[:-1]), dims_array(s_coarse.shape[:-1]), nd, _st())))
+        _p(dy_fine), _p(s_coarse), _p(t_scratch), dims_array(dy_fine.shape[:-1]), dims_array(s_coarse.shape[:-1]), nd, _st())),
+        exec_work=flops)
     PROF.timed("phase_wgrad_fold", 0.0, lambda: check(cabi.lib().dfl_phase_wgrad_fold(_p(t_scratch), _p(dw), nd, dw.shape[-2], dw.shape[-1], _st())))
 
 
@@ -275,13 +276,11 @@ def conv_taps(x, w_rows, bias, out, out2, residual, mask_src, tile_dims, out_dim
     oarr = (C.c_int32 * 3)(*([int(v) for v in out_off] + [0] * (3 - len(out_off))))
     assert w_rows.shape[0] == 128 and w_rows.stride(1) == 1
     flops = 2.0 * float(torch.tensor(tile_dims).prod()) * cin * 128 * len(taps)
-    PROF.exec_flops += flops
-    if alg_flops is not None:      # phase-decomposed upsample-conv: the roofline numerator stays the dense layer's FLOPs
-        flops = alg_flops
-    PROF.timed("conv_tap", flops, lambda: check(cabi.lib().dfl_conv_taps(
+    # alg_flops (phase-decomposed upsample-conv): the roofline numerator stays the dense layer's FLOPs
+    PROF.timed("conv_tap", flops if alg_flops is None else alg_flops, lambda: check(cabi.lib().dfl_conv_taps(
         _p(x), C.c_void_p(w_rows.data_ptr()), _p(bias), _p(out), _p(out2), _p(residual), _p(mask_src),
         dims_array(x.shape[:-1]), dims_array(tile_dims), dims_array(out_dims), nd, cin, in_stride, len(taps), tarr,
-        out_stride, oarr, w_rows.stride(0), flags, _st())))
+        out_stride, oarr, w_rows.stride(0), flags, _st())), exec_work=flops)
 
 
 def conv_wgrad_ex(x, dpre, dw_ptr_tensor, db, in_stride, pad, dw_tap_stride, dw_row_stride):
