@@ -48,7 +48,7 @@ def test_generator_fwd_bwd_vs_oracle(spatial, num_conv, B):
     #     tools/chain_debug.py: 3-7 % rel-L2 per level, with NO kernel error.)   Bound: rel-L2 <= 2e-2.
     acts = {"x0": [t.float().cpu() for t in eng.x0], "y": [[t.float().cpu() for t in row] for row in eng.y],
             "s": eng.s.float().cpu()}
-    tf_grads = T.teacher_forced_backward(y, var, acts, dpot.cpu(), num_conv=num_conv, operand_round=M.bf16_round_ste)
+    tf_grads = T.teacher_forced_backward(y, var, acts, dpot.cpu(), num_conv=num_conv, operand_round=M.bf16_round_ste, mask_from_acts=True)
     pot_o = M.generator_forward(y, var, spatial + [cout], num_conv=num_conv, store=M.bf16_round_ste)
     e_pot = rel_l2(pot, pot_o)
     errs = OrderedDict((k, rel_l2(eng.params.g(k), tf_grads[k])) for k in var)
@@ -170,7 +170,7 @@ def test_reference_recipe_shapes(spatial, B):
     assert float(K.divergence(vel).abs().max()) <= 1e-5
     acts = {"x0": [t.float().cpu() for t in eng.x0], "y": [[t.float().cpu() for t in row] for row in eng.y],
             "s": eng.s.float().cpu()}
-    tf_grads = T.teacher_forced_backward(y, var, acts, dpot.cpu(), num_conv=4, operand_round=M.bf16_round_ste)
+    tf_grads = T.teacher_forced_backward(y, var, acts, dpot.cpu(), num_conv=4, operand_round=M.bf16_round_ste, mask_from_acts=True)
     worst = max(rel_l2(eng.params.g(k), tf_grads[k]) for k in var if k.endswith("weights"))
     assert worst <= 2e-2, worst
 
