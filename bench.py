@@ -345,11 +345,10 @@ def run_gpu_arm(args):
     # every kernel of the step: ms per step and launches per step (CUDA events, eager replay of the same step)
     kernel_ms = {k: {"ms_per_step": round(v[0] / 2 * 1e3, 4), "launches_per_step": v[2] // 2}
                  for k, v in sorted(agg.items(), key=lambda kv: -kv[1][0])}
-    for extra in ("conv_tap",):           # stride-2 / per-tap launches count as conv work too (AE)
-        if extra in agg:
-            a, e = agg.setdefault("conv_tc", [0.0, 0.0, 0, 0.0]), agg[extra]
-            a[0] += e[0]; a[1] += e[1]; a[2] += e[2]; a[3] += e[3]
+    # dominant kernel = the tap-window conv (its executed FLOPs == its algorithmic FLOPs); the per-tap kernel's launches
+    # (stride-2 layers of the AE, phase-decomposed upsample-convs) are reported as their own entry below
     conv_t, conv_f, conv_n, conv_x = agg.get("conv_tc", [1e-9, 0.0, 1, 0.0])
+    tap_t, tap_f, tap_n, tap_x = agg.get("conv_tap", [0.0, 0.0, 0, 0.0])
     wg_t, wg_f, wg_n, wg_x = agg.get("wgrad_tc", [1e-9, 0.0, 1, 0.0])
     st_t, st_b, st_n = agg.get("stencil_fused", [0.0, 0.0, 0, 0.0])[:3]
     fb_t, fb_b, fb_n = agg.get("lastconv_bwd_fused", [0.0, 0.0, 0, 0.0])[:3]
@@ -390,7 +389,7 @@ def run_gpu_arm(args):
     roofline = {"kernel": "conv_tc2_kernel (tcgen05 tap-window implicit-GEMM conv, fwd + dgrad launches)", "bound": "tensor",
                 "achieved": achieved, "peak": peaks["tf_sustained"], "unit": "TFLOP/s",
                 "frac": achieved / peaks["tf_sustained"], "peak_source": "%s (sustained bf16, kernel timed inside a long step)" % peaks["src"],
-                "mma_terms_per_flop": terms, "executed_tflops": conv_x / conv_t / 1e12, "phase_upconv": phase_note,
+                "mma_terms_per_flop": terms, "executed_tflops": conv_x / conv_t / 1e12,
                 "launches_timed": conv_n, "avg_launch_ms": conv_t / conv_n * 1e3, "traffic": load_traffic("conv_tc_kernel"),
                 "traffic_source": "STATIC: dram bytes per launch of a full-resolution launch from the committed ncu --set full "
                                   "capture (profiles/ncu_summary.json), not measured in this run",
@@ -403,6 +402,13 @@ def run_gpu_arm(args):
                     "stencil_fused_kernel": {"bound": "hbm", "achieved": st_b / st_t / 1e9, "unit": "GB/s",
                                              "frac": st_b / st_t / 1e9 / peaks["hbm_gbs"], "measured": stencil_note,
                                              "avg_launch_ms": st_t / max(st_n, 1) * 1e3}}}
+    if tap_n:
+        roofline["others"]["conv_tap_kernel"] = {
+            "what": "per-tap tcgen05 conv: stride-2 layers" + ("; " + phase_note if phase_note else ""),
+            "bound": "tensor", "achieved": tap_f / terms / tap_t / 1e12, "unit": "TFLOP/s",
+            "achieved_is": "ALGORITHMIC FLOPs of the dense layer / time (can exceed the peak: the decomposition skips work)",
+            "executed_tflops": tap_x / tap_t / 1e12, "frac_executed": tap_x / tap_t / 1e12 / peaks["tf_sustained"],
+            "share_of_step": tap_t / 2 * accum / (ms_per_step * 1e-3)}
     if fb_n:
         roofline["others"]["lastconv_bwd_fused_kernel"] = {
             "what": "loss stencil (curl + Jacobian-L1 + adjoints) in the prologue of the output conv's backward (dgrad + wgrad + bias-grad)",
@@ -414,6 +420,12 @@ def run_gpu_arm(args):
     if fl:
         roofline["step_conv_tflops_per_gpu"] = value / world * fl / 1e12      # algorithmic (dense-layer) FLOPs
         roofline["step_frac_of_peak"] = value / world * fl / 1e12 / peaks["tf_sustained"]
+        if phase_on:
+            exec_per_step = (conv_x + wg_x + tap_x) / 2 * accum
+            roofline["step_executed_tflops_per_gpu"] = exec_per_step / (ms_per_step * 1e-3) / 1e12
+            roofline["step_executed_frac_of_peak"] = roofline["step_executed_tflops_per_gpu"] / peaks["tf_sustained"]
+            roofline["step_note"] = ("step_conv_tflops_per_gpu / step_frac_of_peak count the DENSE layers' algorithmic FLOPs; the "
+                                     "phase-decomposed upsample-convs execute 8/27 (3D) / 4/9 (2D) of theirs: " + phase_note)
 
     phase_on_cfg = phase_on
     if rank == 0:
