@@ -85,6 +85,7 @@ int conv_tc_launch(const void* x, const void* w_packed, const float* bias, void*
 int wgrad_tc_launch(const void* x, const void* dpre, float* dw, float* db, const int64_t* x_dims, const int64_t* dims,
                     int nd, int in_stride, int pad, int dw_tap_stride, int dw_row_stride, cudaStream_t st, int split = 0,
                     int ksize = 3);
+int gather_stride2(const void* fine, void* coarse, const int64_t* cdims, int nd, cudaStream_t st);
 int phase_wgrad_fold(const float* t64, float* dw, int nd, int cin, int cout, cudaStream_t st);
 int conv_tap_launch(const void* x, const void* w_packed, const float* bias, void* out, void* out2,
                     const void* residual, const void* mask_src, const int64_t* in_dims, const int64_t* tile_dims,
@@ -276,6 +277,9 @@ int dfl_phase_wgrad(const void* dy_fine, const void* s_coarse, float* t_scratch,
                     const int64_t* coarse_dims, int ndim, void* stream) {
   return wgrad_tc_launch(dy_fine, s_coarse, t_scratch, nullptr, fine_dims, coarse_dims, ndim, 2, 1, 128 * 128, 128, ST(stream),
                          0, 4);
+}
+int dfl_gather_stride2(const void* fine, void* coarse, const int64_t* cdims, int ndim, void* stream) {
+  return gather_stride2(fine, coarse, cdims, ndim, ST(stream));
 }
 int dfl_phase_wgrad_fold(const float* t_scratch, float* dw, int ndim, int cin, int cout, void* stream) {
   return phase_wgrad_fold(t_scratch, dw, ndim, cin, cout, ST(stream));

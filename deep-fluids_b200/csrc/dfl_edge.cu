@@ -216,6 +216,36 @@ int pack_phase_weights(const float* W, void* wf, void* wd, int nd, int cin, int 
 }
 
 // =============================================================================================
+// gather_stride2: coarse[b,z,y,x,:] = fine[b,2z,2y,2x,:]  (bf16, 128 channels).  The up-sampled tensor x0 = upscale(s) read at
+// every second voxel IS s: the coarse operand of the phase-decomposed weight gradient, exactly as the forward pass read it.
+// =============================================================================================
+__global__ void gather_stride2_kernel(const __nv_bfloat16* __restrict__ fine, __nv_bfloat16* __restrict__ coarse, int B,
+                                      int D, int H, int W, int zr) {
+  const size_t n = static_cast<size_t>(B) * D * H * W * 16;      // 16 threads per coarse voxel (8 channels = 16 bytes each)
+  for (size_t idx = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; idx < n;
+       idx += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int q = idx & 15;
+    size_t v = idx >> 4;
+    const int x = v % W; v /= W;
+    const int y = v % H; v /= H;
+    const int z = v % D;
+    const int b = v / D;
+    const size_t pos2 = ((static_cast<size_t>(b) * (D * zr) + z * zr) * (2 * H) + 2 * y) * (2 * W) + 2 * x;
+    reinterpret_cast<uint4*>(coarse)[idx] = __ldg(reinterpret_cast<const uint4*>(fine + pos2 * 128) + q);
+  }
+}
+
+int gather_stride2(const void* fine, void* coarse, const int64_t* cdims, int nd, cudaStream_t st) {
+  const int B = cdims[0], D = nd == 3 ? cdims[1] : 1, H = cdims[nd - 1], W = cdims[nd];
+  const size_t n = static_cast<size_t>(B) * D * H * W * 16;
+  const int grid = static_cast<int>(std::min<size_t>((n + 255) / 256, static_cast<size_t>(num_sms()) * 16));
+  gather_stride2_kernel<<<grid, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(fine), static_cast<__nv_bfloat16*>(coarse), B, D, H,
+                                             W, nd == 3 ? 2 : 1);
+  DFL_LAUNCH_OK("gather_stride2_kernel");
+  return DFL_OK;
+}
+
+// =============================================================================================
 // phase_wgrad_fold: weight gradient of the phase-decomposed upsample-conv, folded back onto the layer's 3^nd taps.
 // dfl_phase_wgrad (the tensor-core weight-gradient kernel run as a 4^nd-tap stride-2 correlation between dY on the fine grid
 // and the layer's COARSE input s) leaves T[k][co][ci] = sum_q dY[2q + k - 1][co] * s[q][ci], k in {0..3}^nd, i.e. the gradients

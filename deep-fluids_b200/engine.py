@@ -309,8 +309,7 @@ class GeneratorEngine(object):
                     # dpre (fine) with the layer's coarse input s = x0[i][::2, ::2(, ::2)] (exactly the values the forward
                     # read), folded back onto the 3^nd taps; the bias gradient is a column sum of dpre
                     s_c = self._gview(oth_b, i - 1)
-                    sl = (slice(None),) + (slice(None, None, 2),) * self.nd
-                    s_c.copy_(self.x0[i][sl])
+                    K.gather_stride2(self.x0[i], s_c)
                     dense = 2.0 * self.B * float(np.prod(self.level_shape[i])) * self.filters * self.filters * self.taps
                     K.phase_wgrad(dpre, s_c, self._t_phase, P.g(cn + "/weights"), alg_flops=dense)
                     K.bias_grad(dpre, P.g(cn + "/biases"))

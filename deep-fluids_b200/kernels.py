@@ -231,6 +231,12 @@ def pack_phase_weights(w, w_fwd, w_dgrad):
     PROF.timed("pack_conv_weights", 0.0, lambda: check(cabi.lib().dfl_pack_phase_weights(_p(w), _p(w_fwd), _p(w_dgrad), nd, w.shape[-2], w.shape[-1], _st())))
 
 
+def gather_stride2(fine, coarse):
+    """coarse = fine[:, ::2, ::2(, ::2), :]  (bf16 [.., 128])"""
+    d, nd = _spatial(coarse)
+    PROF.timed("gather_stride2", 0.0, lambda: check(cabi.lib().dfl_gather_stride2(_p(fine), _p(coarse), d, nd, _st())))
+
+
 def phase_wgrad(dy_fine, s_coarse, t_scratch, dw, alg_flops=None):
     """weight gradient of a phase-decomposed upsample-conv: 4^nd-tap stride-2 tensor-core correlation + fold onto dw"""
     nd = dy_fine.dim() - 2

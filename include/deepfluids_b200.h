@@ -188,6 +188,8 @@ int dfl_pack_phase_weights(const float* w, void* w_fwd, void* w_dgrad, int ndim,
 int dfl_phase_wgrad(const void* dy_fine, const void* s_coarse, float* t_scratch, const int64_t* fine_dims,
                     const int64_t* coarse_dims, int ndim, void* stream);
 int dfl_phase_wgrad_fold(const float* t_scratch, float* dw, int ndim, int cin, int cout, void* stream);
+/* coarse[b,(z,)y,x,:] = fine[b,(2z,)2y,2x,:] (bf16, 128 channels): the coarse source s of an up-sampled tensor upscale(s) */
+int dfl_gather_stride2(const void* fine, void* coarse, const int64_t* cdims, int ndim, void* stream);
 /* same with a coarse-grid addend: ds = sum of the children of g + addend.  Used by the phase-decomposed upsample-conv
  * (model.py:76-79 followed by :67-69 = eight 2x2x2 convolutions on the coarse tensor): the first conv's data gradient lands
  * on the coarse grid directly (`addend`), only the residual branch's gradient `g` still has to be pooled. */
