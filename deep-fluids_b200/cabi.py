@@ -67,6 +67,9 @@ SIGNATURES = {
     "dfl_pool_mask": (_i, [_vp, _vp, _vp, _vp, _dims, _i, _vp]),
     "dfl_pack_phase_weights": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp]),
     "dfl_phase_wgrad": (_i, [_vp, _vp, _vp, _dims, _dims, _i, _vp]),
+    "dfl_bn_act_fwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _f, _f, _i, _i, _vp]),
+    "dfl_bn_act_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp]),
+    "dfl_dropout": (_i, [_vp, _vp, _sz, _f, C.c_uint64, C.c_uint64, _vp]),
     "dfl_gather_stride2": (_i, [_vp, _vp, _dims, _i, _vp]),
     "dfl_phase_wgrad_fold": (_i, [_vp, _vp, _i, _i, _i, _vp]),
     "dfl_pool_mask_add": (_i, [_vp, _vp, _vp, _vp, _vp, _dims, _i, _vp]),

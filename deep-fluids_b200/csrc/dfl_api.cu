@@ -85,6 +85,11 @@ int conv_tc_launch(const void* x, const void* w_packed, const float* bias, void*
 int wgrad_tc_launch(const void* x, const void* dpre, float* dw, float* db, const int64_t* x_dims, const int64_t* dims,
                     int nd, int in_stride, int pad, int dw_tap_stride, int dw_row_stride, cudaStream_t st, int split = 0,
                     int ksize = 3);
+int bn_act_fwd(const float* x, const float* gamma, const float* beta, float* mmean, float* mvar, float* y, float* save_mean,
+               float* save_rstd, int M, int N, float eps, float decay, int training, int act, cudaStream_t st);
+int bn_act_bwd(const float* x, const float* y, const float* dy, const float* gamma, const float* save_mean,
+               const float* save_rstd, float* dx, float* dgamma, float* dbeta, int M, int N, int act, cudaStream_t st);
+int dropout(const float* x, float* y, size_t n, float keep, unsigned long long seed, unsigned long long offset, cudaStream_t st);
 int gather_stride2(const void* fine, void* coarse, const int64_t* cdims, int nd, cudaStream_t st);
 int phase_wgrad_fold(const float* t64, float* dw, int nd, int cin, int cout, cudaStream_t st);
 int conv_tap_launch(const void* x, const void* w_packed, const float* bias, void* out, void* out2,
@@ -277,6 +282,18 @@ int dfl_phase_wgrad(const void* dy_fine, const void* s_coarse, float* t_scratch,
                     const int64_t* coarse_dims, int ndim, void* stream) {
   return wgrad_tc_launch(dy_fine, s_coarse, t_scratch, nullptr, fine_dims, coarse_dims, ndim, 2, 1, 128 * 128, 128, ST(stream),
                          0, 4);
+}
+int dfl_bn_act_fwd(const float* x, const float* gamma, const float* beta, float* moving_mean, float* moving_var, float* y,
+                   float* save_mean, float* save_rstd, int M, int N, float eps, float decay, int training, int act,
+                   void* stream) {
+  return bn_act_fwd(x, gamma, beta, moving_mean, moving_var, y, save_mean, save_rstd, M, N, eps, decay, training, act, ST(stream));
+}
+int dfl_bn_act_bwd(const float* x, const float* y, const float* dy, const float* gamma, const float* save_mean,
+                   const float* save_rstd, float* dx, float* dgamma, float* dbeta, int M, int N, int act, void* stream) {
+  return bn_act_bwd(x, y, dy, gamma, save_mean, save_rstd, dx, dgamma, dbeta, M, N, act, ST(stream));
+}
+int dfl_dropout(const float* x, float* y, size_t n, float keep_prob, uint64_t seed, uint64_t offset, void* stream) {
+  return dropout(x, y, n, keep_prob, seed, offset, ST(stream));
 }
 int dfl_gather_stride2(const void* fine, void* coarse, const int64_t* cdims, int ndim, void* stream) {
   return gather_stride2(fine, coarse, cdims, ndim, ST(stream));

@@ -86,8 +86,17 @@ __device__ __forceinline__ bool fb_next(long long& u, long long u_end, int D, FB
   return true;
 }
 
-__device__ __forceinline__ void fb_bar_sync(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
-__device__ __forceinline__ void fb_bar_arrive(int id, int n) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(n) : "memory"); }
+// bar.sync / bar.arrive are warp-ALIGNED instructions: every lane of the warp must execute them together.  Callers reach them
+// after lane-divergent code (edge-of-domain predicates in the store loop, in-domain tests of the stencil), and reconvergence
+// is otherwise only the compiler's choice (compute-sanitizer synccheck flagged exactly that on overhanging tiles).
+__device__ __forceinline__ void fb_bar_sync(int id, int n) {
+  __syncwarp();
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory");
+}
+__device__ __forceinline__ void fb_bar_arrive(int id, int n) {
+  __syncwarp();
+  asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(n) : "memory");
+}
 
 __device__ __forceinline__ uint32_t fb_pack(float a, float b) {
   __nv_bfloat162 h = __floats2bfloat162_rn(a, b);

@@ -57,7 +57,11 @@ __device__ __forceinline__ bool lf_next(long long& u, long long u_end, int D, LF
   u += s.ze - s.zs;
   return true;
 }
-__device__ __forceinline__ void lf_bar(int id) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(LF_EPI) : "memory"); }
+// (warp-aligned instruction reached after lane-divergent code: reconverge explicitly, see dfl_lastconv_bwd_fused.cu)
+__device__ __forceinline__ void lf_bar(int id) {
+  __syncwarp();
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(LF_EPI) : "memory");
+}
 
 template <int C, bool k3D>
 __global__ void __launch_bounds__(LF_THREADS, 1)

@@ -214,6 +214,7 @@ lastconv_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmS, LastBwdParams p)
           tc_fence_before();
           mbar_arrive(&d1_empty[s]);               // the tensor core may overwrite this accumulator
         }
+        __syncwarp();      // warp-aligned barrier after lane-divergent code
         asm volatile("bar.sync 2, 128;" ::: "memory");   // images complete
         if (x < p.W) {
 #pragma unroll
@@ -241,6 +242,7 @@ lastconv_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmS, LastBwdParams p)
             }
           }
         }
+        __syncwarp();      // warp-aligned barrier after lane-divergent code
         asm volatile("bar.sync 3, 128;" ::: "memory");   // images may be overwritten
       }
     }
@@ -293,6 +295,7 @@ lastconv_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmS, LastBwdParams p)
 #pragma unroll
         for (int c = 0; c < C; ++c) st[pos * C + c] = inb ? __ldg(src + c) : 0.f;
       }
+      __syncwarp();      // warp-aligned barrier after lane-divergent code
       asm volatile("bar.sync 1, 128;" ::: "memory");     // stage complete (double-buffered: one barrier per tile suffices)
       mbar_wait(&g_empty[s], ph ^ 1);
       uint8_t* grow = sG + s * LB_OP + row * 128;

@@ -212,6 +212,36 @@ def colsum(x):
     return out
 
 
+ACT_NONE, ACT_LRELU, ACT_ELU = 0, 1, 2
+
+
+def bn_act_fwd(x, gamma, beta, moving_mean, moving_var, eps, decay, training, act):
+    """slim.batch_norm + activation on [M, N] fp32 -> (y, save_mean, save_rstd); moving statistics updated in place"""
+    M, N = x.shape
+    y = torch.empty_like(x)
+    sm = torch.empty(N, dtype=torch.float32, device=x.device) if training else None
+    sr = torch.empty(N, dtype=torch.float32, device=x.device) if training else None
+    PROF.timed("bn_act_fwd", 0.0, lambda: check(cabi.lib().dfl_bn_act_fwd(_p(x), _p(gamma), _p(beta), _p(moving_mean), _p(moving_var), _p(y), _p(sm), _p(sr), M, N,
+                                        float(eps), float(decay), int(bool(training)), int(act), _st())))
+    return y, sm, sr
+
+
+def bn_act_bwd(x, y, dy, gamma, save_mean, save_rstd, act, want_dx=True):
+    M, N = x.shape
+    dx = torch.empty_like(x) if want_dx else None
+    dgamma = torch.empty(N, dtype=torch.float32, device=x.device)
+    dbeta = torch.empty(N, dtype=torch.float32, device=x.device)
+    PROF.timed("bn_act_bwd", 0.0, lambda: check(cabi.lib().dfl_bn_act_bwd(_p(x), _p(y), _p(dy), _p(gamma), _p(save_mean), _p(save_rstd), _p(dx), _p(dgamma), _p(dbeta), M, N,
+                                        int(act), _st())))
+    return dx, dgamma, dbeta
+
+
+def dropout(x, keep_prob, seed, offset):
+    y = torch.empty_like(x)
+    PROF.timed("dropout", 0.0, lambda: check(cabi.lib().dfl_dropout(_p(x), _p(y), x.numel(), float(keep_prob), int(seed), int(offset), _st())))
+    return y
+
+
 # ------------------------------------------------------------------ conv
 def pack_conv_weights(w, w_fwd=None, w_dgrad=None):
     """w fp32 TF layout [k,(k,)k,Cin,Cout] -> (bf16 [Cout, taps*Cin], bf16 [Cin, taps*Cout])"""

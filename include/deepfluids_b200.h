@@ -270,6 +270,21 @@ int dfl_adam_step(float* param, const float* grad, float* m, float* v, size_t n,
 int dfl_adam_step_dev(float* param, const float* grad, float* m, float* v, size_t n, const float* lr_t_dev, float beta1,
                       float beta2, float eps, float grad_scale, void* stream);
 
+/* ---- latent-space MLP of arch=nn (reference model.py:218-224, ops.py:26-36) ------------------------------------------
+ * slim.batch_norm(decay, epsilon, scale=True, fused=True, is_training, activation_fn) on [M, N] fp32 + the activation:
+ * training: normalise with the batch statistics (biased variance), update moving_mean / moving_var in place (the variance
+ * Bessel-corrected, as fused batch norm returns it), keep save_mean / save_rstd for the backward; inference: moving
+ * statistics.  act: 0 none, 1 leaky-ReLU 0.2 (ops.batch_norm's default), 2 ELU (NN's default tf.nn.elu).
+ * dfl_bn_act_bwd: dx (may be NULL), dgamma, dbeta (overwritten) from dy = d loss / d y. */
+int dfl_bn_act_fwd(const float* x, const float* gamma, const float* beta, float* moving_mean, float* moving_var, float* y,
+                   float* save_mean, float* save_rstd, int M, int N, float eps, float decay, int training, int act,
+                   void* stream);
+int dfl_bn_act_bwd(const float* x, const float* y, const float* dy, const float* gamma, const float* save_mean,
+                   const float* save_rstd, float* dx, float* dgamma, float* dbeta, int M, int N, int act, void* stream);
+/* slim.dropout(x, keep_prob, is_training=True): y = x * mask / keep_prob, mask from a counter-based generator keyed by
+ * (seed, offset + index); the backward pass is the same call on dy with the same (seed, offset). */
+int dfl_dropout(const float* x, float* y, size_t n, float keep_prob, uint64_t seed, uint64_t offset, void* stream);
+
 /* ---- data-parallel exchange (new -- the reference is single-GPU) ------------------------------------
  * One process per GPU, every rank a full replica, ONE in-place ncclAllReduce(sum) over the flat fp32 gradient buffer per
  * optimizer step; the 1/world (and 1/grad_accum) factor is the grad_scale of dfl_adam_step.  NCCL is dlopen'ed
