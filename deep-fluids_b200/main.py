@@ -21,12 +21,14 @@ def main(config):
             dist.init_process_group("nccl")
         rank = dist.get_rank()
 
-    if 'nn' in config.arch:
-        raise NotImplementedError("arch 'nn' (data_nn.BatchManager) is outside the B200 hot path")
-    from .data import BatchManager
     from .trainer import Trainer
     from .trainer3 import Trainer3
-    batch_manager = BatchManager(config, rank=rank)
+    if 'nn' in config.arch:                                  # main.py:14-17
+        from .data_nn import BatchManager
+        batch_manager = BatchManager(config)
+    else:
+        from .data import BatchManager
+        batch_manager = BatchManager(config, rank=rank)
 
     if config.is_3d:
         trainer = Trainer3(config, batch_manager)

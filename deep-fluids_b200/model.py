@@ -11,7 +11,8 @@ import numpy as np
 import torch
 
 from .engine import GeneratorEngine
-from .ops import conv2d, conv3d, get_variables, linear, lrelu, upscale, upscale3, variable_scope
+from .ops import batch_norm, conv2d, conv3d, elu, get_variables, linear, lrelu, upscale, upscale3, variable_scope
+from .ops import dropout as ops_dropout
 
 _ENGINES = {}
 
@@ -145,15 +146,15 @@ def DiscriminatorPatch3(x, filters, name='D', train=True, reuse=False):
     return _discriminator(x, filters, name, reuse, conv3d)
 
 
-def elu(x):
-    """tf.nn.elu: the default activation of NN (model.py:218)"""
-    raise NotImplementedError("arch='nn' (latent-space integrator, model.py:218-224) is outside the B200 hot path")
-
-
 def NN(x, filters, onum, name='NN', act=elu, dropout=0.1, train=True, reuse=False):
-    """latent-space MLP of arch=nn (model.py:218-224): linear(2*filters) + batch_norm + dropout, linear(filters) +
-    batch_norm + dropout, linear(onum).  Not built: it is not on the conv / stencil hot path."""
-    raise NotImplementedError("arch='nn' (latent-space integrator, model.py:218-224) is outside the B200 hot path")
+    """latent-space integrator of arch=nn (model.py:218-224): linear(2*filters) -> batch_norm(act) -> dropout,
+    linear(filters) -> batch_norm(act) -> dropout, linear(onum); slim's default variable names NN/fully_connected{,_1,_2}
+    and NN/BatchNorm{,_1}.  (`dropout` reaches slim.dropout as its keep_prob argument, as in the reference.)"""
+    with variable_scope(name, reuse=reuse) as vs:
+        x = ops_dropout(batch_norm(linear(x, filters * 2), train, act=act), dropout, is_training=train)
+        x = ops_dropout(batch_norm(linear(x, filters), train, act=act), dropout, is_training=train)
+        out = linear(x, onum)
+    return out, get_variables(vs)
 
 
 def _encoder(x, filters, z_num, name, num_conv, conv_k, repeat, act, reuse, nd):

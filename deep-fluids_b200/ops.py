@@ -4,6 +4,7 @@ Same names, argument order, defaults and returns as reference ops.py:
     lrelu(x, leak)                                              ops.py:9-10
     conv2d / conv3d(x, o_dim, data_format, name, k, s, act)     ops.py:12-16   (slim.conv2d / conv3d, SAME padding)
     linear(x, o_dim, name, act)                                 ops.py:23-24   (slim.fully_connected)
+    batch_norm(x, train, data_format, name, act, epsilon, momentum)  ops.py:26-36 (slim.batch_norm, [batch, features] only)
     upscale(x, scale, data_format) / upscale3(x, scale)         ops.py:75-91
     jacobian(x, data_format) -> (j, w) / jacobian3(x) -> (j, c) ops.py:205-262
     curl(x, data_format)                                        ops.py:264-274
@@ -49,7 +50,7 @@ class VariableStore(object):
         cnt[default_name] = i + 1
         return default_name if i == 0 else "%s_%d" % (default_name, i)
 
-    def get(self, name, shape, device, zeros=False):
+    def get(self, name, shape, device, zeros=False, fill=None, trainable=True):
         full = self.path() + "/" + name if self.scopes else name
         v = self.vars.get(full)
         if v is not None:
@@ -61,7 +62,9 @@ class VariableStore(object):
         if self.reuse():
             raise ValueError("Variable %s does not exist, or was not created in this store (reuse=True)" % full)
         data = torch.zeros(shape, dtype=torch.float32, device=device) if zeros else xavier_uniform(tuple(shape), self.generator, device)
-        v = torch.nn.Parameter(data)
+        if fill is not None:
+            data.fill_(fill)
+        v = torch.nn.Parameter(data, requires_grad=trainable)
         self.vars[full] = v
         return v
 
@@ -129,6 +132,88 @@ class _LreluFn(torch.autograd.Function):
         g = torch.empty_like(y)
         K.add_mask(gy.to(torch.bfloat16).contiguous(), None, y, g)
         return g.to(ctx.dtype)
+
+
+def elu(x):
+    """tf.nn.elu -- the activation of model.NN (model.py:218).  As a standalone op it runs through the batch-norm kernel's
+    activation stage with an identity normalisation (gamma = 1, beta = 0, moving statistics 0 / 1 - eps)."""
+    flat = x.reshape(-1, x.shape[-1]).float().contiguous()
+    n = flat.shape[1]
+    one, zero = torch.ones(n, device=x.device), torch.zeros(n, device=x.device)
+    return _BnActFn.apply(flat, one, zero, zero.clone(), one.clone(), 0.0, 1.0, False, K.ACT_ELU).reshape(x.shape)
+
+
+class _BnActFn(torch.autograd.Function):
+    """slim.batch_norm (+ activation) on [M, N] fp32: dfl_bn_act_fwd / dfl_bn_act_bwd"""
+
+    @staticmethod
+    def forward(ctx, x, gamma, beta, mmean, mvar, eps, decay, training, act):
+        x = x.float().contiguous()
+        y, sm, sr = K.bn_act_fwd(x, gamma.detach(), beta.detach(), mmean, mvar, eps, decay, training, act)
+        ctx.training, ctx.act = training, act
+        if training:
+            ctx.save_for_backward(x, y, gamma.detach(), sm, sr)
+        else:   # inference statistics are constants: the layer is an affine map followed by the activation
+            ctx.save_for_backward(x, y, gamma.detach(), mmean.clone(), torch.rsqrt(mvar + eps))
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, y, gamma, sm, sr = ctx.saved_tensors
+        dy = dy.float().contiguous()
+        if ctx.training:
+            dx, dg, db = K.bn_act_bwd(x, y, dy, gamma, sm, sr, ctx.act, want_dx=ctx.needs_input_grad[0])
+            return dx, dg, db, None, None, None, None, None, None
+        raise NotImplementedError("batch_norm(train=False) is not differentiated on this path (the reference only "
+                                  "differentiates the training-mode graph)")
+
+
+_DROPOUT = {"seed": 0x5EED, "offset": 0}
+
+
+def dropout_seed(seed):
+    _DROPOUT["seed"], _DROPOUT["offset"] = int(seed), 0
+
+
+class _DropoutFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, keep_prob):
+        x = x.float().contiguous()
+        ctx.keep, ctx.seed, ctx.offset = keep_prob, _DROPOUT["seed"], _DROPOUT["offset"]
+        _DROPOUT["offset"] += x.numel()
+        return K.dropout(x, keep_prob, ctx.seed, ctx.offset)
+
+    @staticmethod
+    def backward(ctx, dy):
+        return K.dropout(dy.float().contiguous(), ctx.keep, ctx.seed, ctx.offset), None
+
+
+def dropout(x, keep_prob, is_training=True):
+    """slim.dropout(x, keep_prob, is_training): identity at inference; y = x * mask / keep_prob in training (counter-based
+    mask, re-created in the backward pass).  NOTE model.NN passes its `dropout=0.1` argument as the KEEP probability."""
+    if not is_training or keep_prob >= 1.0:
+        return x
+    return _DropoutFn.apply(x, float(keep_prob))
+
+
+def batch_norm(x, train, data_format='NHWC', name=None, act=lrelu, epsilon=1e-5, momentum=0.9):
+    """slim.batch_norm(decay=momentum, epsilon, scale=True, fused=True, updates_collections=None, is_training=train,
+    activation_fn=act) (ops.py:26-36) for the [batch, features] tensors of model.NN.  Variables beta, gamma, moving_mean,
+    moving_variance under `name` (default scope BatchNorm, BatchNorm_1, ...); the moving statistics are updated in place by
+    every training-mode call, as updates_collections=None does."""
+    if x.dim() != 2:
+        raise NotImplementedError("batch_norm: [batch, features] tensors only (the conv stacks of this path have no batch norm)")
+    code = {None: K.ACT_NONE, lrelu: K.ACT_LRELU, elu: K.ACT_ELU}.get(act)
+    if code is None:
+        raise NotImplementedError("batch_norm activation %r: None, ops.lrelu or ops.elu" % (act,))
+    n = int(x.shape[1])
+    scope = name if name is not None else _STORE.unique_default("BatchNorm")
+    with variable_scope(scope):
+        beta = _STORE.get("beta", (n,), x.device, zeros=True)
+        gamma = _STORE.get("gamma", (n,), x.device, zeros=True, fill=1.0)
+        mmean = _STORE.get("moving_mean", (n,), x.device, zeros=True, trainable=False)
+        mvar = _STORE.get("moving_variance", (n,), x.device, zeros=True, fill=1.0, trainable=False)
+    return _BnActFn.apply(x, gamma, beta, mmean.data, mvar.data, float(epsilon), float(momentum), bool(train), code)
 
 
 def upscale(x, scale, data_format='NHWC'):

@@ -157,3 +157,48 @@ class OpsAEEngine(_Steps):
         grads = torch.autograd.grad(self._z_lin, self._enc_plist, dz)
         self._accumulate(self._enc_names, grads)
         self._z_lin = None
+
+
+class OpsNNEngine(_Steps):
+    """arch=nn: the latent-space integrator model.NN (model.py:218-224) and the windowed roll-out of Trainer.build_model_nn
+    (trainer.py:586-640) on the ops-level layers (dfl_gemm_f32, dfl_bn_act_*, dfl_dropout), torch autograd as the tape.
+    All variables -- incl. the batch-norm moving statistics, which carry no gradient -- live in one flat buffer."""
+
+    def __init__(self, batch, in_dim, filters, z_num, p_num, w_num, out_std, code_std, device=None, seed=123, dropout=0.1):
+        self.device = device or torch.device("cuda", torch.cuda.current_device())
+        self.B, self.in_dim, self.filters, self.z_num, self.p_num, self.w_num = int(batch), int(in_dim), int(filters), int(z_num), int(p_num), int(w_num)
+        self.rescale = float(out_std) / float(code_std)
+        self.dropout = dropout
+        self.adam_t = 0
+        ops.reset_variables(seed)
+        ops.dropout_seed(seed)
+        with torch.no_grad():      # declares the variables (inference mode: the moving statistics stay at their initial values)
+            _, names = Mo.NN(torch.zeros(self.B, self.in_dim, device=self.device), self.filters, self.z_num, dropout=dropout,
+                             train=False, reuse=False)
+        self._adopt(names)
+        self._trainable = [n for n in names if ops.get_variable(n).requires_grad]
+        self._tparams = [ops.get_variable(n) for n in self._trainable]
+
+    def net(self, x, train):
+        return Mo.NN(x, self.filters, self.z_num, dropout=self.dropout, train=train, reuse=True)[0]
+
+    def rollout(self, xw, train):
+        """w_num chained predictions (trainer.py:590-612): the predicted code increment, re-normalised to the scale of x, is
+        added to the code part of the input; the parameter part comes from the next frame of the window"""
+        x_ = xw[:, 0, :]
+        outs = []
+        for i in range(self.w_num):
+            y_ = self.net(x_, train)
+            outs.append(y_.unsqueeze(1))
+            if i < self.w_num - 1:
+                x_ = torch.cat([x_[:, :-self.p_num] + y_ * self.rescale, xw[:, i + 1, -self.p_num:]], dim=-1)
+        return torch.cat(outs, dim=1)
+
+    def loss_and_grads(self, xw, yw):
+        """loss = tf.losses.mean_squared_error(yw, yw_) (trainer.py:627,629); gradients accumulate into params.grad"""
+        yw_ = self.rollout(xw, True)
+        diff = (yw_ - yw).contiguous()
+        loss, g = K.mse_loss(diff.detach(), 0.0)
+        grads = torch.autograd.grad(yw_, self._tparams, g.view_as(yw_))
+        self._accumulate(self._trainable, grads)
+        return loss

@@ -37,8 +37,10 @@ class Trainer(object):
         self.dataset = config.dataset
         self.data_type = config.data_type
         self.arch = config.arch
-        if 'nn' in self.arch:
-            raise NotImplementedError("arch '%s' is outside the B200 hot path (SURVEY.md 2: de/ae/dg)" % self.arch)
+        if 'nn' in self.arch:                       # trainer.py:24-27
+            self.xt, self.yt = batch_manager.test_batch()
+            self.xtw, self.ytw = batch_manager.test_batch(is_window=True)
+            self.xw, self.yw = batch_manager.batch(is_window=True)
 
         self.res_x, self.res_y, self.res_z = config.res_x, config.res_y, config.res_z
         self.c_num = batch_manager.c_num
@@ -51,6 +53,9 @@ class Trainer(object):
         self.w3 = getattr(config, "w3", 0.005)      # weight of the adversarial term (arch=dg, trainer.py:178)
 
         self.use_c = config.use_curl
+        if 'nn' in self.arch:
+            self._init_nn(config, batch_manager)
+            return
         spatial = list(self.x.shape[1:-1])
         if self.use_c:                              # trainer.py:48-55
             self.output_shape = spatial + [3 if self.is_3d else 1]
@@ -425,6 +430,8 @@ class Trainer(object):
     def train(self):
         if 'ae' in self.arch:
             self.train_ae()
+        elif 'nn' in self.arch:
+            self.train_nn()
         else:
             self.train_()
 
@@ -711,14 +718,115 @@ class Trainer(object):
             np.savez_compressed(paths[-1], v=v.cpu().numpy(), v_gt=v_gt.cpu().numpy())
         return paths
 
+    # ------------------------------------------------------------------ arch=nn (trainer.py:586-747)
+    def _init_nn(self, config, batch_manager):
+        self.optimizer = config.optimizer
+        self.beta1, self.beta2 = config.beta1, config.beta2
+        self.model_dir = getattr(config, "model_dir", "")
+        self.load_path = config.load_path
+        self.start_step = config.start_step
+        self.step = self.start_step
+        self.max_step = int(config.max_epoch // batch_manager.epochs_per_step)
+        if getattr(config, "max_step", 0):
+            self.max_step = int(config.max_step)
+        self.lr_update, self.lr_min, self.lr_max = config.lr_update, config.lr_min, config.lr_max
+        if self.lr_update not in ('decay', 'step'):
+            raise Exception("[!] Invalid lr update method")
+        self.g_lr = config.lr_max
+        self.lr_update_step, self.test_step, self.save_sec = config.lr_update_step, config.test_step, config.save_sec
+        self.is_train = config.is_train
+        self.log_step = batch_manager.train_steps                    # trainer.py:126-128
+        self.world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+        self.rank = dist.get_rank() if self.world > 1 else 0
+        self.z_num, self.p_num, self.w_num = config.z_num, batch_manager.dof, config.w_size
+        self.accum = 1
+        self.build_model_nn()
+        if self.load_path and os.path.exists(os.path.join(self.load_path, "model.pt")):
+            self.load(os.path.join(self.load_path, "model.pt"))
+
     def build_model_nn(self):
-        self._out_of_scope("arch='nn' (latent-space integrator)", "trainer.py:586-640, model.py:218-224")
+        """y_ = NN(x); roll-out over the window; loss = mean squared error of the w_num chained predictions
+        (trainer.py:586-640).  Only Adam (the reference raises otherwise, trainer.py:622)."""
+        from .ops_engine import OpsNNEngine
+        if self.optimizer != 'adam':
+            raise Exception("[!] Caution! Paper didn't use {} opimizer other than Adam".format(self.optimizer))
+        bm = self.batch_manager
+        self.engine = OpsNNEngine(self.b_num, self.z_num + self.p_num, self.filters, self.z_num, self.p_num, self.w_num,
+                                  bm.out_std, bm.code_std, self.device, self.config.random_seed)
+        self.var = self.engine.variables
+        self.optim = self.train_step_nn
+        self.use_graph = False
+        self.loss = self.loss_train_w = self.l_test = self.l_test_w = None
+
+    def train_step_nn(self, xw=None, yw=None):
+        """one `sess.run(self.optim)` (trainer.py:645)"""
+        if xw is None:
+            xw, yw = self.batch_manager.batch(is_window=True)
+        eng = self.engine
+        eng.zero_grad()
+        self.loss_train_w = eng.loss_and_grads(xw, yw)
+        scale = dp.allreduce_grads_(eng.params.grad)
+        eng.adam_step(self.g_lr, self.beta1, self.beta2, 1e-8, scale)
+        self.step += 1
+        return self.loss_train_w
+
+    def _test_losses_nn(self):
+        """mean test losses over one pass of the test iterators (trainer.py:650-662), inference mode"""
+        bm, eng = self.batch_manager, self.engine
+        bm.init_test_it()
+        with torch.no_grad():
+            tl = []
+            for _ in range(bm.test_steps):
+                xt, yt = bm.test_batch()
+                tl.append(float(K.mse_loss((eng.net(xt, False) - yt).contiguous(), 0.0, want_grad=False)[0]))
+            tw = []
+            for _ in range(bm.test_w_steps):
+                xtw, ytw = bm.test_batch(is_window=True)
+                tw.append(float(K.mse_loss((eng.rollout(xtw, False) - ytw).contiguous(), 0.0, want_grad=False)[0]))
+        self.l_test, self.l_test_w = sum(tl) / len(tl), sum(tw) / len(tw)
+        return self.l_test, self.l_test_w
 
     def train_nn(self):
-        self._out_of_scope("arch='nn' (latent-space integrator)", "trainer.py:642-696")
+        for step in range(self.start_step, self.max_step):
+            self.train_step_nn()
+            if step % self.log_step == 0 or step == self.max_step - 1:
+                test_loss, test_loss_w = self._test_losses_nn()
+                self.loss = float(self.loss_train_w)
+                assert not np.isnan(self.loss), 'Model diverged with loss = NaN'      # trainer.py:668
+                if self.rank == 0:
+                    print("\n[{}/{}] Loss: {:.6f}/{:.6f}/{:.6f}".format(step, self.max_step, self.loss, test_loss, test_loss_w))
+            self.update_lr(step)
+            self._periodic_checkpoint()
+        self._checkpoint()
 
     def test_nn(self):
-        self._out_of_scope("arch='nn' (latent-space integrator)", "trainer.py:698-747")
+        """integrate every test simulation in latent space from its first frame and dump `<load_path>/code_out.npz` =
+        {z_out, z_gt} ([simulations][frames, z_num], de-normalised codes) -- the input of test_ae's decode branch
+        (trainer.py:698-747)"""
+        bm, eng = self.batch_manager, self.engine
+        z_out_list, z_gt_list = [], []
+        nf, p = bm.num_frames, self.p_num
+        with torch.no_grad():
+            for i in range(bm.num_test_scenes):
+                z0 = bm.x_test[i * (nf - 1)]
+                z_in = z0.reshape(1, -1)
+                z_out = [z0[:-p].reshape(1, -1) * bm.code_std]
+                z_gt = [z0[:-p].reshape(1, -1) * bm.code_std]
+                for t in range(nf - 1):
+                    y_gt = bm.y_test[i * (nf - 1) + t] * bm.out_std + bm.x_test[i * (nf - 1) + t, :-p] * bm.code_std
+                    z_gt.append(y_gt.reshape(1, -1))
+                    pred = eng.net(torch.as_tensor(z_in, dtype=torch.float32, device=self.device), False).cpu().numpy()
+                    y_ = pred * bm.out_std + z_in[:, :-p] * bm.code_std
+                    y_[0, -p:] = y_gt[-p:]
+                    z_out.append(y_)
+                    if t < nf - 2:
+                        zt = bm.x_test[i * (nf - 1) + t + 1]
+                        z_in = np.append(y_.flatten() / bm.code_std, zt[-p:]).reshape(1, -1)
+                z_out_list.append(np.concatenate(z_out))
+                z_gt_list.append(np.concatenate(z_gt))
+        code_path = os.path.join(self.load_path or self.model_dir, 'code_out.npz')
+        np.savez_compressed(code_path, z_out=np.stack(z_out_list), z_gt=np.stack(z_gt_list))
+        return code_path
 
     # ------------------------------------------------------------------ checkpoint (state_dict with TF variable names)
     def save(self, path):

@@ -14,7 +14,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 NAMES = ("GeneratorBE", "GeneratorBE3", "EncoderBE", "EncoderBE3", "AE", "AE3", "DiscriminatorPatch", "DiscriminatorPatch3", "NN")
 # ops.py functions of the drop-in boundary (SURVEY.md 8b "Ops"): layer wrappers, resampling, stencils, numpy twins
-OPS_NAMES = ("lrelu", "conv2d", "conv3d", "linear", "upscale", "upscale3", "jacobian", "jacobian3", "curl",
+OPS_NAMES = ("lrelu", "conv2d", "conv3d", "linear", "batch_norm", "upscale", "upscale3", "jacobian", "jacobian3", "curl",
              "divergence", "divergence3", "vort_np", "curl_np", "grad_np", "jacobian_np3")
 
 

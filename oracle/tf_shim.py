@@ -54,7 +54,9 @@ def install():
     tf._dfl_shim = True
     tf.float32 = torch.float32
     tf.concat = lambda values, axis=0, name=None: torch.cat([_t(v) for v in values], dim=axis)
-    tf.expand_dims = lambda x, axis=None, name=None: torch.unsqueeze(_t(x), axis)
+    # .clone(): a TF op returns a NEW tensor; trainer.py:598-608 multiplies y_ in place (`y_ *= ...`, a rebind in TF) after
+    # taking expand_dims(y_), which must not alias it
+    tf.expand_dims = lambda x, axis=None, name=None: torch.unsqueeze(_t(x), axis).clone()
     tf.stack = lambda values, axis=0, name=None: torch.stack([_t(v) for v in values], dim=axis)
     tf.transpose = lambda x, perm=None: _t(x).permute(*perm)
     tf.maximum = lambda a, b: torch.maximum(_t(a), _t(b))
@@ -192,6 +194,7 @@ def install_structural(store, conv_nd, linear):
         return activation_fn(y) if activation_fn is not None else y
 
     slim.conv2d, slim.conv3d, slim.fully_connected = _conv(2), _conv(3), fully_connected
+    tf._dfl_unique_default = _unique_default
     tf.variable_scope = variable_scope
     tf.sigmoid = torch.sigmoid
     framework = _mod("tensorflow.contrib.framework")
@@ -199,6 +202,39 @@ def install_structural(store, conv_nd, linear):
     sys.modules["tensorflow"].contrib.framework = framework
     sys.modules["tensorflow.contrib.framework"] = framework
     return tf
+
+
+def install_nn(store, batch_norm, dropout, masks, mse):
+    """Shim surface of arch=nn (model.py:218-224, trainer.py:586-629): slim.batch_norm (variables beta, gamma,
+    moving_mean, moving_variance under the default scope BatchNorm / BatchNorm_1), slim.dropout, tf.add,
+    tf.losses.mean_squared_error.  Arithmetic is delegated to the oracle's restated primitives; `masks` is a list the
+    dropout masks are popped from in call order (training-mode calls only).  Call install_structural() first."""
+    tf = sys.modules["tensorflow"]
+    slim = sys.modules["tensorflow.contrib.slim"]
+    _default = tf._dfl_unique_default      # per enclosing scope, forgotten when it closes (NN(..., reuse=True) starts over)
+
+    def slim_batch_norm(x, decay=0.999, updates_collections="update_ops", epsilon=0.001, scale=False, fused=None,
+                        is_training=True, activation_fn=None, data_format="NHWC", scope=None):
+        assert updates_collections is None and scale and fused and data_format == "NHWC"
+        x = _t(x)
+        store.scopes.append(scope if scope is not None else _default("BatchNorm"))
+        try:
+            n = x.shape[-1]
+            beta, gamma = store.get("beta", (n,)), store.get("gamma", (n,))
+            mm, mv = store.get("moving_mean", (n,)), store.get("moving_variance", (n,))
+        finally:
+            store.scopes.pop()
+        return batch_norm(x, gamma, beta, mm, mv, is_training, epsilon, decay, activation_fn)
+
+    def slim_dropout(x, keep_prob=0.5, is_training=True):
+        return dropout(_t(x), keep_prob, masks.pop(0)) if is_training else _t(x)
+
+    slim.batch_norm, slim.dropout = slim_batch_norm, slim_dropout
+    tf.add = lambda a, b: _t(a) + _t(b)
+    losses = _mod("tensorflow.losses")
+    losses.mean_squared_error = lambda labels, predictions: mse(_t(labels), _t(predictions))
+    tf.losses = losses
+    sys.modules["tensorflow.losses"] = losses
 
 
 class BuildDone(Exception):
