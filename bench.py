@@ -390,6 +390,9 @@ def run_gpu_arm(args):
                 "achieved": achieved, "peak": peaks["tf_sustained"], "unit": "TFLOP/s",
                 "frac": achieved / peaks["tf_sustained"], "peak_source": "%s (sustained bf16, kernel timed inside a long step)" % peaks["src"],
                 "mma_terms_per_flop": terms, "executed_tflops": conv_x / conv_t / 1e12,
+                "frac_executed": conv_x / conv_t / 1e12 / peaks["tf_sustained"],
+                "frac_note": "achieved / frac count the reference formulation's dense FLOPs (SURVEY 8d); with the phase "
+                             "decomposition the tensor cores execute fewer (executed_tflops / frac_executed), so frac may exceed 1",
                 "launches_timed": conv_n, "avg_launch_ms": conv_t / conv_n * 1e3, "traffic": load_traffic("conv_tc_kernel"),
                 "traffic_source": "STATIC: dram bytes per launch of a full-resolution launch from the committed ncu --set full "
                                   "capture (profiles/ncu_summary.json), not measured in this run",
@@ -397,6 +400,7 @@ def run_gpu_arm(args):
                 "others": {
                     "wgrad_tc_kernel": {"bound": "tensor", "achieved": wg_f / wg_t / 1e12, "unit": "TFLOP/s",
                                         "executed_tflops": wg_x / wg_t / 1e12,
+                                        "frac_executed": wg_x / wg_t / 1e12 / peaks["tf_sustained"],
                                         "frac": wg_f / wg_t / 1e12 / peaks["tf_sustained"],
                                         "share_of_step": wg_t / 2 * accum / (ms_per_step * 1e-3)},
                     "stencil_fused_kernel": {"bound": "hbm", "achieved": st_b / st_t / 1e9, "unit": "GB/s",

@@ -98,6 +98,15 @@ __device__ __forceinline__ void fb_bar_arrive(int id, int n) {
   asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(n) : "memory");
 }
 
+// The epilogue warps and the builder warps meet at barrier 2 from two different places of the role-split code.  That is
+// legal PTX, but compute-sanitizer's synccheck models a bar.sync as one instruction all participants must reach ("Barrier
+// error: divergent thread(s) in block" otherwise; tools/synccheck_probe.cu isolates the pattern, kernels B / F).  Routing
+// both roles through ONE non-inlined function leaves a single bar.sync instruction in the binary for this barrier.
+__device__ __noinline__ void fb_bar_sync_shared(int id, int n) {
+  __syncwarp();
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory");
+}
+
 __device__ __forceinline__ uint32_t fb_pack(float a, float b) {
   __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
   return *reinterpret_cast<uint32_t*>(&h);
@@ -514,7 +523,7 @@ lastconv_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmS, const __grid_
           }
           // image complete; the other image is free (its readers passed the previous round's barrier).  The builder warps
           // take row passes 2 and 3 of this round.
-          fb_bar_sync(2, 128 + FB_BUILD);
+          fb_bar_sync_shared(2, 128 + FB_BUILD);
           fb_store_passes(p, L, sTa, tile0, tx0, y0, h, 0, mv);
         }
       }
@@ -624,7 +633,7 @@ lastconv_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmS, const __grid_
           mv[0] = mvn[0]; mv[1] = mvn[1];
           if (h < 3) fb_load_mask(p, L, tile0, tx0, y0, h + 1, 2, mvn);
           else if (z + 1 < sg.ze) fb_load_mask(p, L, tile0 + plane_vox, tx0, y0, 0, 2, mvn);
-          fb_bar_sync(2, 128 + FB_BUILD);
+          fb_bar_sync_shared(2, 128 + FB_BUILD);
           fb_store_passes(p, L, sT0 + (h & 1) * (128 * 64), tile0, tx0, y0, h, 2, mv);
         }
       }

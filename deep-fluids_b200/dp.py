@@ -46,14 +46,20 @@ def allreduce_grads_(flat_grad):
     """Sum the flat gradient buffer over ranks in place; returns the grad_scale (1/world) for the optimizer."""
     w = world()
     if w > 1:
-        if use_native():
-            import ctypes as C
-            from . import cabi
-            cabi.check(cabi.lib().dfl_allreduce(C.c_void_p(flat_grad.data_ptr()), flat_grad.numel(), cabi.F32, native_comm(),
-                                                C.c_void_p(torch.cuda.current_stream().cuda_stream)))
-        else:
-            dist.all_reduce(flat_grad, op=dist.ReduceOp.SUM)
+        from .kernels import nvtx_range
+        with nvtx_range("gradient all-reduce"):
+            _allreduce(flat_grad)
     return 1.0 / w
+
+
+def _allreduce(flat_grad):
+    if use_native():
+        import ctypes as C
+        from . import cabi
+        cabi.check(cabi.lib().dfl_allreduce(C.c_void_p(flat_grad.data_ptr()), flat_grad.numel(), cabi.F32, native_comm(),
+                                            C.c_void_p(torch.cuda.current_stream().cuda_stream)))
+    else:
+        dist.all_reduce(flat_grad, op=dist.ReduceOp.SUM)
 
 
 def max_over_ranks(value, device=None):

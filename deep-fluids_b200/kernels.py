@@ -3,7 +3,9 @@
 torch is plumbing here: it owns the device memory and the stream; every call passes raw pointers through
 ctypes to hand-written sm_100a kernels.  Nothing in this module computes on the CPU or through torch ops.
 """
+import contextlib
 import ctypes as C
+import os
 
 import torch
 
@@ -21,9 +23,24 @@ class _Prof(object):
     # only for the phase-decomposed upsample-conv launches, which are booked with the dense layer's algorithmic FLOPs
     events = None
 
+    # DFL_NVTX=1: every launch (and the trainers' step phases, see `nvtx_range`) is wrapped in an NVTX range, so that
+    # `ncu --nvtx --nvtx-include "conv3x3_fwd/"` / an Nsight Systems timeline can address them by name.  Off by default: the
+    # push / pop pair costs ~1 us per launch on the host, and captured graphs replay without host-side ranges anyway.
+    nvtx = os.environ.get("DFL_NVTX", "0") == "1"
+
     @classmethod
     def timed(cls, name, work, fn, exec_work=None):
         cls.launches += 1
+        if cls.nvtx:
+            torch.cuda.nvtx.range_push(name)
+            try:
+                return cls._timed(name, work, fn, exec_work)
+            finally:
+                torch.cuda.nvtx.range_pop()
+        return cls._timed(name, work, fn, exec_work)
+
+    @classmethod
+    def _timed(cls, name, work, fn, exec_work=None):
         if cls.events is None:
             return fn()
         s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -34,6 +51,19 @@ class _Prof(object):
 
 
 PROF = _Prof
+
+
+@contextlib.contextmanager
+def nvtx_range(name):
+    """NVTX range around a phase of the step (forward / loss+first backward / backward / exchange / optimizer) when DFL_NVTX=1"""
+    if not PROF.nvtx:
+        yield
+        return
+    torch.cuda.nvtx.range_push(name)
+    try:
+        yield
+    finally:
+        torch.cuda.nvtx.range_pop()
 
 
 def _p(t):

@@ -286,19 +286,27 @@ class Trainer(object):
         eng = self.engine
         if zero:
             eng.zero_grad()
-        pot = eng.forward(y)
+        with K.nvtx_range("forward"):
+            pot = eng.forward(y)
         fused = self._fused_args(x, want_vel)
         if fused is not None:
-            eng.backward(None, fused=fused)
+            with K.nvtx_range("loss+backward"):
+                eng.backward(None, fused=fused)
             vel = fused.get("vel")
         else:
-            vel = self._loss_and_grad(pot, x, want_vel)
-            eng.backward(self._dpot)
+            with K.nvtx_range("loss"):
+                vel = self._loss_and_grad(pot, x, want_vel)
+            with K.nvtx_range("backward"):
+                eng.backward(self._dpot)
         if self.accum > 1:
             self._loss3_acc.add_(self._loss3)
         return vel
 
     def _step_body_b(self, scale):
+        with K.nvtx_range("optimizer"):
+            self._step_body_b_(scale)
+
+    def _step_body_b_(self, scale):
         self.engine.optimizer_step_dev(self._lr_dev, self.optimizer == 'adam', self.beta1, self.beta2, 1e-8, scale)
 
     def _capture(self):
