@@ -92,6 +92,8 @@ int bn_act_bwd(const float* x, const float* y, const float* dy, const float* gam
 int dropout(const float* x, float* y, size_t n, float keep, unsigned long long seed, unsigned long long offset, cudaStream_t st);
 int gather_stride2(const void* fine, void* coarse, const int64_t* cdims, int nd, cudaStream_t st);
 int phase_wgrad_fold(const float* t64, float* dw, int nd, int cin, int cout, cudaStream_t st);
+size_t deterministic_workspace_bytes();
+int set_deterministic(void* ws, size_t bytes);
 int conv_tap_launch(const void* x, const void* w_packed, const float* bias, void* out, void* out2,
                     const void* residual, const void* mask_src, const int64_t* in_dims, const int64_t* tile_dims,
                     const int64_t* out_dims, int nd, int cin, int in_stride, int ntap, const int32_t* taps,
@@ -298,6 +300,8 @@ int dfl_dropout(const float* x, float* y, size_t n, float keep_prob, uint64_t se
 int dfl_gather_stride2(const void* fine, void* coarse, const int64_t* cdims, int ndim, void* stream) {
   return gather_stride2(fine, coarse, cdims, ndim, ST(stream));
 }
+size_t dfl_deterministic_workspace_bytes(void) { return deterministic_workspace_bytes(); }
+int dfl_set_deterministic(void* workspace, size_t bytes) { return set_deterministic(workspace, bytes); }
 int dfl_phase_wgrad_fold(const float* t_scratch, float* dw, int ndim, int cin, int cout, void* stream) {
   return phase_wgrad_fold(t_scratch, dw, ndim, cin, cout, ST(stream));
 }

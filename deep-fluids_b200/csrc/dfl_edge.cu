@@ -291,8 +291,10 @@ int phase_wgrad_fold(const float* T, float* dw, int nd, int cin, int cout, cudaS
 // =============================================================================================
 // bias_grad: db[c] += sum_pos d[pos][c]      d bf16 [npos][128]
 // =============================================================================================
+// `partial` != nullptr (deterministic mode): block sums go to partial[blockIdx.x][128]; bias_grad_reduce_kernel adds them
+// to db in block order
 __global__ void __launch_bounds__(256) bias_grad_kernel(const __nv_bfloat16* __restrict__ d, float* __restrict__ db,
-                                                        size_t npos) {
+                                                        size_t npos, float* __restrict__ partial) {
   __shared__ float red[16][128];
   const int q = threadIdx.x & 15, r = threadIdx.x >> 4;
   float s[8] = {0, 0, 0, 0, 0, 0, 0, 0};
@@ -312,14 +314,29 @@ __global__ void __launch_bounds__(256) bias_grad_kernel(const __nv_bfloat16* __r
     float t = 0.f;
 #pragma unroll
     for (int k = 0; k < 16; ++k) t += red[k][threadIdx.x];
-    atomicAdd(db + threadIdx.x, t);
+    if (partial) partial[static_cast<size_t>(blockIdx.x) * 128 + threadIdx.x] = t;
+    else atomicAdd(db + threadIdx.x, t);
   }
 }
+__global__ void __launch_bounds__(128) bias_grad_reduce_kernel(const float* __restrict__ partial, float* __restrict__ db, int n) {
+  float t = 0.f;
+  for (int i = 0; i < n; ++i) t += partial[static_cast<size_t>(i) * 128 + threadIdx.x];
+  db[threadIdx.x] += t;
+}
+
+float* deterministic_workspace(size_t* bytes);      // dfl_wgrad_tc.cu
 
 int bias_grad(const void* d, float* db, size_t npos, cudaStream_t st) {
   const int grid = static_cast<int>(std::min<size_t>((npos + 15) / 16, static_cast<size_t>(num_sms()) * 8));
-  bias_grad_kernel<<<grid, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(d), db, npos);
+  size_t wb = 0;
+  float* ws = deterministic_workspace(&wb);
+  DFL_REQUIRE(!ws || static_cast<size_t>(grid) * 128 * sizeof(float) <= wb, "bias_grad: deterministic workspace too small");
+  bias_grad_kernel<<<grid, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(d), db, npos, ws);
   DFL_LAUNCH_OK("bias_grad_kernel");
+  if (ws) {
+    bias_grad_reduce_kernel<<<1, 128, 0, st>>>(ws, db, grid);
+    DFL_LAUNCH_OK("bias_grad_reduce_kernel");
+  }
   return DFL_OK;
 }
 

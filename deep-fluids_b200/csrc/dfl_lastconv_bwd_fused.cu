@@ -53,7 +53,8 @@ static_assert(FB_ST_F % 2 == 0, "stencil plane storage is zeroed with float2");
 constexpr int FB_SMEM = 5 * FB_OP + FB_TR + FB_RING * FB_PLANE_F * 4 + FB_ST_F * 4 + 1024 + 1024;
 static_assert(FB_SMEM <= 227 * 1024, "fused backward: shared-memory plan exceeds 227 KB");
 enum { FB_FA = 0, FB_FG = 1, FB_FX = 2, FB_FS = 3, FB_FD = 4 };
-// named barriers: 0 = __syncthreads, 1 = builders, 2/3 = epilogue images, 4 = stencil warps, 5..8 ring FULL, 9..12 ring EMPTY
+// named barriers: 0 = __syncthreads, 1 = builders, 2/3 = image READY, 4 = stencil warps, 5..8 ring FULL, 9..12 ring EMPTY,
+// 13 = epilogue warps, 14/15 = image FREE
 constexpr int FB_BAR_ST = 4, FB_BAR_FULL = 5, FB_BAR_EMPTY = 9;
 
 struct FusedBwdParams {
@@ -98,14 +99,17 @@ __device__ __forceinline__ void fb_bar_arrive(int id, int n) {
   asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(n) : "memory");
 }
 
-// The epilogue warps and the builder warps meet at barrier 2 from two different places of the role-split code.  That is
-// legal PTX, but compute-sanitizer's synccheck models a bar.sync as one instruction all participants must reach ("Barrier
-// error: divergent thread(s) in block" otherwise; tools/synccheck_probe.cu isolates the pattern, kernels B / F).  Routing
-// both roles through ONE non-inlined function leaves a single bar.sync instruction in the binary for this barrier.
-__device__ __noinline__ void fb_bar_sync_shared(int id, int n) {
-  __syncwarp();
-  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory");
-}
+// Epilogue <-> builder hand-over of the transposition images.  A symmetric `bar.sync 2, 256` reached by the two roles from
+// two different places of the role-split code is legal PTX, but compute-sanitizer's synccheck models a bar.sync as ONE
+// instruction that all participants must reach ("Barrier error: divergent thread(s) in block"; tools/synccheck_probe.cu
+// isolates the pattern: kernels B / D flagged, the arrive / sync pair of kernel C accepted), and routing both roles through
+// one non-inlined function cost 0.5 ms per launch (ABI register saves in the store loop).  The hand-over is therefore
+// written as producer / consumer pairs, every bar.sync site being reached by one role only:
+//   READY[img] (ids 2, 3):   epilogue arrives after writing image img, builders sync before reading it;
+//   E-wide     (id 13):      the epilogue warps' own "image complete" barrier;
+//   FREE[img]  (ids 14, 15): builders arrive after their row passes of image img, the epilogue syncs two rounds later,
+//                            before it overwrites that image (the last two rounds arrive nowhere and are skipped).
+constexpr int FB_BAR_READY = 2, FB_BAR_EPI = 13, FB_BAR_FREE = 14;
 
 __device__ __forceinline__ uint32_t fb_pack(float a, float b) {
   __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
@@ -502,7 +506,8 @@ lastconv_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmS, const __grid_
           mv[0] = mvn[0]; mv[1] = mvn[1];
           if (h < 3) fb_load_mask(p, L, tile0, tx0, y0, h + 1, 0, mvn);
           else if (z + 1 < sg.ze) fb_load_mask(p, L, tile0 + plane_vox, tx0, y0, 0, 0, mvn);
-          const uint32_t sTa = sT0 + (h & 1) * (128 * 64);     // alternating images: ONE barrier per round
+          const uint32_t sTa = sT0 + (h & 1) * (128 * 64);     // alternating images
+          if (i > 0 || h >= 2) fb_bar_sync(FB_BAR_FREE + (h & 1), 128 + FB_BUILD);   // the builders are done with this image
           {
             uint32_t rr[32];
             tmem_ld_32x32(taddr + h * 32, rr);
@@ -521,9 +526,10 @@ lastconv_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmS, const __grid_
             tc_fence_before();
             mbar_arrive(&d1_empty[s]);               // the tensor core may overwrite this accumulator
           }
-          // image complete; the other image is free (its readers passed the previous round's barrier).  The builder warps
-          // take row passes 2 and 3 of this round.
-          fb_bar_sync_shared(2, 128 + FB_BUILD);
+          // image complete: hand it to the builder warps (row passes 2 and 3 of this round) and to the other epilogue
+          // warps (passes 0 and 1)
+          fb_bar_arrive(FB_BAR_READY + (h & 1), 128 + FB_BUILD);
+          fb_bar_sync(FB_BAR_EPI, 128);
           fb_store_passes(p, L, sTa, tile0, tx0, y0, h, 0, mv);
         }
       }
@@ -618,13 +624,14 @@ lastconv_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmS, const __grid_
     long long u = u0;
     FBSeg sg;
     uint4 mvn[2];
+    int is = 0;                                 // tiles stored so far
     while (fb_next(u, u1, p.D, sg)) {
       int r = sg.col;
       const int tx0 = (r % p.tx) * 16; r /= p.tx;
       const int y0 = (r % p.ty) * 8;
       const int b = r / p.ty;
       fb_load_mask(p, L, ((static_cast<size_t>(b) * p.D + sg.zs) * p.H + y0) * p.W + tx0, tx0, y0, 0, 2, mvn);
-      for (int z = sg.zs; z < sg.ze; ++z) {
+      for (int z = sg.zs; z < sg.ze; ++z, ++is) {
         const size_t tile0 = ((static_cast<size_t>(b) * p.D + z) * p.H + y0) * p.W + tx0;
         build_next();                           // the NEXT tile's im2col operand, before this tile's store rounds
 #pragma unroll 1
@@ -633,8 +640,9 @@ lastconv_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmS, const __grid_
           mv[0] = mvn[0]; mv[1] = mvn[1];
           if (h < 3) fb_load_mask(p, L, tile0, tx0, y0, h + 1, 2, mvn);
           else if (z + 1 < sg.ze) fb_load_mask(p, L, tile0 + plane_vox, tx0, y0, 0, 2, mvn);
-          fb_bar_sync_shared(2, 128 + FB_BUILD);
+          fb_bar_sync(FB_BAR_READY + (h & 1), 128 + FB_BUILD);
           fb_store_passes(p, L, sT0 + (h & 1) * (128 * 64), tile0, tx0, y0, h, 2, mv);
+          if (is + 1 < my_tiles || h < 2) fb_bar_arrive(FB_BAR_FREE + (h & 1), 128 + FB_BUILD);   // (nobody waits for the last two)
         }
       }
     }

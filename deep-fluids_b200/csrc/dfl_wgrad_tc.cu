@@ -47,7 +47,11 @@ struct WgradParams {
   // combination c reads X at batch b + xoff[c] and dP at batch b + poff[c]; bit c of bias_mask = dP of c enters db
   int ncombo, xoff[3], poff[3], bias_mask;
   int vec_red;        // dw rows are 16-byte aligned: reduce with red.global.add.v4.f32
+  // deterministic mode (dfl_set_deterministic): instead of red.global.add into dw / db every CTA stores its accumulators to
+  // its own WG_PART_FLOATS slot of this workspace; wgrad_reduce_kernel then sums the slabs in a fixed order
+  float* partial;
 };
+constexpr size_t WG_PART_FLOATS = static_cast<size_t>(WG_MAX_TAPS) * 128 * 128 + 128;
 constexpr int WG_BRICK_SLOT = 40960;      // >= 2 * bd*(bh+2)*bw*128 for the tile shapes that use brick mode
 constexpr int WG_BRICK_SLOTS = 3;
 
@@ -238,15 +242,21 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
       }
       mbar_wait(acc_full, 0);
       tc_fence_after();
+      float* part = p.partial ? p.partial + static_cast<size_t>(blockIdx.x) * WG_PART_FLOATS : nullptr;
       for (int t = 0; t < gtaps; ++t) {
         const int tap = p.brick ? ((group / 3) * 3 + t) * 3 + (group % 3) : tap0 + t;   // brick: group = (dz,dx), t = dy
-        float* dst = p.dw + static_cast<size_t>(tap) * p.dw_tap_stride + static_cast<size_t>(ci) * p.dw_row_stride;
+        float* dst = part ? part + (static_cast<size_t>(t) * 128 + ci) * 128
+                          : p.dw + static_cast<size_t>(tap) * p.dw_tap_stride + static_cast<size_t>(ci) * p.dw_row_stride;
 #pragma unroll 1
         for (int c0 = 0; c0 < 128; c0 += 32) {
           uint32_t rr[32];
           tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + t * 128 + c0, rr);
           tmem_ld_wait();
-          if (p.vec_red) {
+          if (part) {
+#pragma unroll
+            for (int k = 0; k < 32; k += 4)
+              *reinterpret_cast<uint4*>(dst + c0 + k) = make_uint4(rr[k], rr[k + 1], rr[k + 2], rr[k + 3]);
+          } else if (p.vec_red) {
 #pragma unroll
             for (int k = 0; k < 32; k += 4)
               asm volatile("red.global.add.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(dst + c0 + k), "f"(__uint_as_float(rr[k])),
@@ -258,6 +268,9 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
           }
         }
       }
+      if (part && p.db && quarter == 0 && !(do_bias && bias_any)) {      // deterministic mode: every CTA publishes a bias row
+        for (int c = lane; c < 128; c += 32) part[WG_PART_FLOATS - 128 + c] = 0.f;
+      }
       if (do_bias && quarter == 0 && bias_any) {      // row 0 of the bias accumulator (all rows are equal)
 #pragma unroll 1
         for (int c0 = 0; c0 < 128; c0 += 32) {
@@ -266,7 +279,10 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
           tmem_ld_wait();
           if (lane == 0) {
 #pragma unroll
-            for (int k = 0; k < 32; ++k) atomicAdd(p.db + c0 + k, __uint_as_float(rr[k]));
+            for (int k = 0; k < 32; ++k) {
+              if (part) part[WG_PART_FLOATS - 128 + c0 + k] = __uint_as_float(rr[k]);
+              else atomicAdd(p.db + c0 + k, __uint_as_float(rr[k]));
+            }
           }
         }
       }
@@ -280,6 +296,47 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
     tc_fence_after();
     tmem_dealloc(tmem_base, 512);
   }
+}
+
+// Deterministic mode, second pass: dw[tap][ci][:] += sum over the non-empty slabs, in slab order, of the owning tap group's
+// partial accumulators; the last block does the same for db over all CTAs.  One block per (tap, ci) row, thread = co.
+__global__ void __launch_bounds__(128) wgrad_reduce_kernel(WgradParams p, int nslabs_eff) {
+  const int ntaps = p.kd * p.kh * p.kw, co = threadIdx.x;
+  const int row = blockIdx.x;
+  if (row < ntaps * 128) {
+    const int tap = row >> 7, ci = row & 127;
+    int group, t;
+    if (p.brick) {                       // tap = (dz*3 + dy)*3 + dx, group = dz*3 + dx, t = dy
+      const int dx = tap % 3, dy = (tap / 3) % 3, dz = tap / 9;
+      group = dz * 3 + dx; t = dy;
+    } else {
+      group = tap / p.taps_per_group; t = tap - group * p.taps_per_group;
+    }
+    float acc = 0.f;
+    for (int s = 0; s < nslabs_eff; ++s)
+      acc += p.partial[static_cast<size_t>(s * p.ngroups + group) * WG_PART_FLOATS + (static_cast<size_t>(t) * 128 + ci) * 128 + co];
+    p.dw[static_cast<size_t>(tap) * p.dw_tap_stride + static_cast<size_t>(ci) * p.dw_row_stride + co] += acc;
+  } else if (p.db) {
+    float acc = 0.f;
+    for (int c = 0; c < nslabs_eff * p.ngroups; ++c) acc += p.partial[static_cast<size_t>(c) * WG_PART_FLOATS + WG_PART_FLOATS - 128 + co];
+    p.db[co] += acc;
+  }
+}
+
+// process-wide switch (dfl_set_deterministic): a caller-owned workspace of dfl_deterministic_workspace_bytes() bytes
+static float* g_det_ws = nullptr;
+static size_t g_det_bytes = 0;
+size_t deterministic_workspace_bytes() { return static_cast<size_t>(num_sms()) * WG_PART_FLOATS * sizeof(float); }
+int set_deterministic(void* ws, size_t bytes) {
+  if (ws) DFL_REQUIRE(bytes >= deterministic_workspace_bytes(), "set_deterministic: workspace of %zu bytes, need %zu", bytes,
+                      deterministic_workspace_bytes());
+  g_det_ws = static_cast<float*>(ws);
+  g_det_bytes = ws ? bytes : 0;
+  return DFL_OK;
+}
+float* deterministic_workspace(size_t* bytes) {
+  if (bytes) *bytes = g_det_bytes;
+  return g_det_ws;
 }
 
 static void pick_brick_w(int D, int H, int W, int& bd, int& bh, int& bw) {
@@ -380,8 +437,17 @@ int wgrad_tc_launch(const void* x, const void* dpre, float* dw, float* db, const
     DFL_CUDA_OK(cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, WG_SMEM_BYTES));
     attr_set = true;
   }
+  p.partial = g_det_ws;
+  DFL_REQUIRE(!p.partial || static_cast<size_t>(p.ngroups) * p.nslabs * WG_PART_FLOATS * sizeof(float) <= g_det_bytes,
+              "wgrad_tc: deterministic workspace too small for %d CTAs", p.ngroups * p.nslabs);
   wgrad_tc_kernel<<<p.ngroups * p.nslabs, WG_THREADS, WG_SMEM_BYTES, st>>>(tmX, tmP, p);
   DFL_LAUNCH_OK("wgrad_tc_kernel");
+  if (p.partial) {
+    const int nvt = p.ntiles * p.ncombo, per = (nvt + p.nslabs - 1) / p.nslabs;
+    const int nslabs_eff = (nvt + per - 1) / per;                 // slabs that own at least one brick
+    wgrad_reduce_kernel<<<ntaps * 128 + (p.db ? 1 : 0), 128, 0, st>>>(p, nslabs_eff);
+    DFL_LAUNCH_OK("wgrad_reduce_kernel");
+  }
   return DFL_OK;
 }
 

@@ -134,6 +134,12 @@ class GeneratorEngine(object):
         on_gpu = torch.device(self.device).type == "cuda"
         n_sm = torch.cuda.get_device_properties(self.device).multi_processor_count if on_gpu else 0
         self._fork_below = int(os.environ.get("DFL_FORK_BELOW_TILES", n_sm))
+        # DFL_DETERMINISTIC=1: split-K gradient reductions in a fixed order (dfl_set_deterministic); their shared workspace
+        # rules out the second stream
+        if on_gpu and not inference and os.environ.get("DFL_DETERMINISTIC", "0") == "1" and not K.deterministic():
+            K.set_deterministic(True, self.device)
+        if on_gpu and K.deterministic():
+            self._fork_below = 0
         self._side = torch.cuda.Stream(device=self.device) if (on_gpu and not inference and self._fork_below > 0) else None
         self.z = None
         self.adam_t = 0

@@ -91,6 +91,28 @@ def _spatial(t):
     return dims_array(t.shape[:-1]), nd
 
 
+_DET = {"ws": None}
+
+
+def set_deterministic(on, device=None):
+    """dfl_set_deterministic: weight / bias gradients of the 128 -> 128 layers reduce their split-K partial sums in a fixed
+    order (through a workspace this module owns) instead of fp32 atomics.  Process-wide; launches that use the workspace must
+    stay on one stream."""
+    lib = cabi.lib()
+    if not on:
+        check(lib.dfl_set_deterministic(None, 0))
+        _DET["ws"] = None
+        return
+    n = int(lib.dfl_deterministic_workspace_bytes())
+    ws = torch.empty(n, dtype=torch.uint8, device=device or torch.device("cuda", torch.cuda.current_device()))
+    check(lib.dfl_set_deterministic(_p(ws), n))
+    _DET["ws"] = ws
+
+
+def deterministic():
+    return _DET["ws"] is not None
+
+
 # ------------------------------------------------------------------ stencils
 def curl_fwd(pot):
     d, nd = _spatial(pot)
