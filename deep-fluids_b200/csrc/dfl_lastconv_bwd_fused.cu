@@ -323,6 +323,8 @@ __device__ __forceinline__ void fb_load_mask(const FusedBwdParams& p, const FBSt
       m[q] = __ldg(reinterpret_cast<const uint4*>(p.mask_src + (t0 + static_cast<size_t>(ly) * p.W + lx) * 128 + hh * 32 + L.piece * 8));
   }
 }
+// (Measured and dropped: a prefetch.global.L2 of the next tile's operand lines a whole tile ahead -- 2.05 vs 2.05 ms at
+// 4 x 128^3; the long-scoreboard stalls ncu shows on these warps are not what bounds the kernel.)
 __device__ __forceinline__ void fb_store_passes(const FusedBwdParams& p, const FBStoreLane L, uint32_t sTa, size_t tile0, int tx0,
                                                 int y0, int h, int it0, const uint4 (&mv)[2]) {
 #pragma unroll

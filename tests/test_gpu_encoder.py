@@ -223,7 +223,7 @@ def test_ae_step_vs_oracle():
     errs = {k: rel_l2(ae.params.g(k), grads[k]) for k in var if not k.endswith("biases")}
     worst = max(errs, key=errs.get)
     print("AE worst weight-grad rel-L2 %.3e (%s)" % (errs[worst], worst))
-    assert errs[worst] <= 2.5e-1, (worst, errs[worst])
+    assert errs[worst] <= 1.5e-1, (worst, errs[worst])      # free-running (sign flips, see test_gpu_trainstep); teacher-forced: test_gpu_baseline_sizes
     for k in var:
         assert torch.isfinite(ae.params.g(k)).all(), k
 
@@ -251,7 +251,7 @@ def test_ae2d_step_vs_oracle():
     assert abs(loss3[0].item() + lpd.item() - total.item()) <= 1e-2 * abs(total.item())
     errs = {k: rel_l2(ae.params.g(k), grads[k]) for k in var if k.endswith("weights")}
     worst = max(errs, key=errs.get)
-    assert errs[worst] <= 2.5e-1, (worst, errs[worst])
+    assert errs[worst] <= 1.5e-1, (worst, errs[worst])      # free-running (sign flips, see test_gpu_trainstep); teacher-forced: test_gpu_baseline_sizes
 
 
 def test_trainer_ae_api_runs_and_loss_decreases():

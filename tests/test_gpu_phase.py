@@ -58,7 +58,7 @@ def test_phase_generator_vs_oracle_and_dense_path(spatial, num_conv, B):
     pot_ref = M.generator_forward(y, var, spatial + [cout], num_conv=num_conv)
     loss_ref = T.stencil_loss(pot_ref, x)[0]
     e_pot, e_dense = rel_l2(outs[0][0], pot_ref), rel_l2(outs[0][0], outs[1][0])
-    assert e_pot <= 2e-2 and e_dense <= 1e-2, (e_pot, e_dense)
+    assert e_pot <= 1e-2 and e_dense <= 1e-2, (e_pot, e_dense)
     assert abs(outs[0][1][0].item() - loss_ref.item()) <= 1e-2 * abs(loss_ref.item())
     # teacher-forced backward: every layer fed with what the device stored (the oracle runs the DENSE layer on upscale(s))
     acts = {"x0": [t.float().cpu() for t in eng.x0], "y": [[t.float().cpu() for t in row] for row in eng.y], "s": eng.s.float().cpu()}
@@ -74,7 +74,7 @@ def test_phase_generator_vs_oracle_and_dense_path(spatial, num_conv, B):
     ed = max(rel_l2(eng.params.g(k), ref_eng.params.g(k)) for k in var if k.endswith("weights"))
     print("phase %s nc=%d: pot vs oracle %.2e vs dense %.2e | teacher-forced W %.2e b %.2e | vs dense grads %.2e" % (
         spatial, num_conv, e_pot, e_dense, ew, eb, ed))
-    assert ew <= 2e-2 and eb <= 5e-2, errs
+    assert ew <= 1.2e-2 and eb <= 2e-2, errs      # measured <= 7.1e-3 / 1.0e-2
     assert ed <= 1.5e-1
 
 

@@ -1,7 +1,8 @@
 """GPU parity of the whole generator train step (engine = chain of sm_100a kernels) against the fp32 CPU oracle.
 
-bf16 path tolerances (operands/activations bf16, fp32 accumulate, fp32 master weights): rel-L2 <= 2e-2 on the
-potential and on every gradient tensor, loss within 1e-2 relative (SURVEY 8c proposal); Adam update compared on the
+bf16 path tolerances (operands/activations bf16, fp32 accumulate, fp32 master weights): rel-L2 <= 1e-2 on the
+potential and on every teacher-forced weight gradient (1.5e-2 for the 16-layer 128x96 recipe and for bias gradients), loss
+within 1e-2 relative (SURVEY 8c proposal); Adam update compared on the
 fp32 parameters after 2 steps."""
 import os
 from collections import OrderedDict
@@ -37,7 +38,7 @@ def test_generator_fwd_bwd_vs_oracle(spatial, num_conv, B):
     var = eng.params.state_dict()
     assert list(var.keys()) == list(M.generator_layout(spatial + [cout], num_conv=num_conv)[0].keys())
     loss, l1, jl1, g_ref, pot_ref, grads = T.generator_loss_and_grads(y, x, var, num_conv=num_conv)
-    assert rel_l2(pot, pot_ref) <= 2e-2
+    assert rel_l2(pot, pot_ref) <= 1e-2          # measured 2.9e-3 .. 4.4e-3
     assert abs(loss3[0].item() - loss.item()) <= 1e-2 * abs(loss.item())
     # divergence-free output (north_star: <= 1e-5)
     assert float(K.divergence(vel).abs().max()) <= 1e-5
@@ -45,7 +46,7 @@ def test_generator_fwd_bwd_vs_oracle(spatial, num_conv, B):
     #     by layer through torch autograd, each layer fed with the activation the device actually stored, so the
     #     leaky-ReLU masks are identical.  (A free-running comparison cannot be tight: two bf16 pipelines disagree on
     #     ~1e-3 of the lrelu signs, and every flipped sign changes that element's gradient by 5x -- measured with
-    #     tools/chain_debug.py: 3-7 % rel-L2 per level, with NO kernel error.)   Bound: rel-L2 <= 2e-2.
+    #     tools/chain_debug.py: 3-7 % rel-L2 per level, with NO kernel error.)   Bound: rel-L2 <= 1e-2.
     acts = {"x0": [t.float().cpu() for t in eng.x0], "y": [[t.float().cpu() for t in row] for row in eng.y],
             "s": eng.s.float().cpu()}
     tf_grads = T.teacher_forced_backward(y, var, acts, dpot.cpu(), num_conv=num_conv, operand_round=M.bf16_round_ste, mask_from_acts=True)
@@ -73,8 +74,8 @@ def test_generator_fwd_bwd_vs_oracle(spatial, num_conv, B):
         (e_pot,) + mx(errs, "weights") + mx(errs, "biases") + mx(errs_e2e, "weights") + mx(errs_e2e, "biases"))
     print(report)
     assert e_pot <= 1e-2, report
-    assert mx(errs, "weights")[0] <= 2e-2 and mx(errs, "biases")[0] <= 5e-2, report
-    assert mx(errs_e2e, "weights")[0] <= 2e-1 and mx(errs_e2e, "biases")[0] <= 3e-1, report
+    assert mx(errs, "weights")[0] <= 1e-2 and mx(errs, "biases")[0] <= 1.5e-2, report       # measured <= 6.9e-3 / 8.9e-3
+    assert mx(errs_e2e, "weights")[0] <= 1.5e-1 and mx(errs_e2e, "biases")[0] <= 2e-1, report   # measured <= 1.1e-1 / 1.3e-1
 
 
 def test_train_steps_match_oracle_adam():
@@ -165,7 +166,7 @@ def test_reference_recipe_shapes(spatial, B):
     var = eng.params.state_dict()
     pot_ref = M.generator_forward(y, var, spatial + [cout], num_conv=4)
     loss_ref = T.stencil_loss(pot_ref, x)[0]
-    assert rel_l2(pot, pot_ref) <= 2e-2
+    assert rel_l2(pot, pot_ref) <= 1e-2          # measured 4.9e-3 / 5.1e-3
     assert abs(loss3[0].item() - loss_ref.item()) <= 1e-2 * abs(loss_ref.item())
     assert float(K.divergence(vel).abs().max()) <= 1e-5
     acts = {"x0": [t.float().cpu() for t in eng.x0], "y": [[t.float().cpu() for t in row] for row in eng.y],
@@ -173,7 +174,7 @@ def test_reference_recipe_shapes(spatial, B):
     tf_grads = T.teacher_forced_backward(y, var, acts, dpot.cpu(), num_conv=4, operand_round=M.bf16_round_ste, mask_from_acts=True)
     worst = max(rel_l2(eng.params.g(k), tf_grads[k]) for k in var if k.endswith("weights"))
     print("recipe %s: pot %.2e, teacher-forced weight gradients worst %.2e" % (spatial, rel_l2(pot, pot_ref), worst))
-    assert worst <= 2e-2, worst
+    assert worst <= 1.5e-2, worst                # measured 1.01e-2 (128x96, 16 layers deep) / 5.6e-3
 
 
 def test_main_control_flow_and_errors(tmp_path, monkeypatch):
