@@ -417,7 +417,7 @@ def run_gpu_arm(args):
         roofline["others"]["lastconv_bwd_fused_kernel"] = {
             "what": "loss stencil (curl + Jacobian-L1 + adjoints) in the prologue of the output conv's backward (dgrad + wgrad + bias-grad)",
             "bound": "hbm", "achieved": fb_b / fb_t / 1e9, "unit": "GB/s", "frac": fb_b / fb_t / 1e9 / peaks["hbm_gbs"],
-            "algorithmic_bytes_per_voxel": 1048, "avg_launch_ms": fb_t / fb_n * 1e3,
+            "algorithmic_bytes_per_voxel": 1048 if cfg.is_3d else 1036, "avg_launch_ms": fb_t / fb_n * 1e3,
             "share_of_step": fb_t / 2 * accum / (ms_per_step * 1e-3)}
     roofline["kernel_ms"] = kernel_ms
     fl = FLOPS_PER_FIELD[args.workload]

@@ -65,6 +65,9 @@ int bwd_stencils(int op, int nd, const int64_t* dims, const float* g0, const flo
                  cudaStream_t st);
 int mse_loss(const float* d, float target, float* loss, float* dd, size_t n, float scale, cudaStream_t st);
 size_t lastconv_curl_loss_bwd_workspace_bytes();
+int lastconv_curl_loss_bwd_2d(const void* s, const float* pot, const float* x, const float* w, const void* mask_src, void* ds,
+                              void* ds_masked, float* dw, float* db, float* dpot, float* vel, float* loss3, void* workspace,
+                              const int64_t* dims, float w1, float w2, float grad_scale, cudaStream_t st);
 int lastconv_curl_loss_bwd(const void* s, const float* pot, const float* x, const float* w, const void* mask_src, void* ds,
                            void* ds_masked, float* dw, float* db, float* dpot, float* vel, float* loss3, void* workspace,
                            const int64_t* dims, float w1, float w2, float grad_scale, cudaStream_t st);
@@ -195,11 +198,10 @@ int dfl_lastconv_curl_loss_bwd(const void* s, const float* pot, const float* x, 
                                void* ds, void* ds_masked, float* dw, float* db, float* dpot, float* vel, float* loss3,
                                void* workspace, const int64_t* dims, int ndim, float w1, float w2, float grad_scale,
                                void* stream) {
-  if (ndim != 3) {
-    set_last_error("dfl_lastconv_curl_loss_bwd: the fused kernel is the 3D (128^3 / 64^3) path; 2D runs "
-                   "dfl_stencil_loss_fwdbwd + dfl_lastconv_bwd");
-    return DFL_ERR_UNSUPPORTED;
-  }
+  DFL_REQUIRE(ndim == 2 || ndim == 3, "dfl_lastconv_curl_loss_bwd: ndim must be 2 or 3");
+  if (ndim == 2)
+    return lastconv_curl_loss_bwd_2d(s, pot, x, w, mask_src, ds, ds_masked, dw, db, dpot, vel, loss3, workspace, dims, w1, w2,
+                                     grad_scale, ST(stream));
   return lastconv_curl_loss_bwd(s, pot, x, w, mask_src, ds, ds_masked, dw, db, dpot, vel, loss3, workspace, dims, w1, w2,
                                 grad_scale, ST(stream));
 }

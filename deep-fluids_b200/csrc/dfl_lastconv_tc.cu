@@ -35,16 +35,45 @@ struct LastBwdParams {
   __nv_bfloat16* ds_masked;    // [B,D,H,W,128] or nullptr
   float* dw;                   // [taps][128][C] fp32, accumulated
   float* db;                   // [C] fp32, accumulated
+  // ---- kFuse (2D, C = 1): dOut = dL/dpsi is COMPUTED by the builder warps from the potential and the target (see below)
+  const float* pot;            // [B,H,W,1] fp32 stream function psi (the forward kernel's output)
+  const float* xt;             // [B,H,W,2] fp32 target velocity
+  float* dpot;                 // optional [B,H,W,1]: dL/dpsi for callers that want it
+  float* vel;                  // optional [B,H,W,2]: G_ = curl(psi)
+  double* partials;            // 2 per CTA
+  unsigned int* ticket;
+  float* loss3;
+  float c1, c2, w1, w2;        // c1 = w1 * grad_scale / N1, c2 = w2 * grad_scale / N2
+  double inv_n1, inv_n2;
 };
+
+// ---- 2D loss stencil inside the builder warps (kFuse) ------------------------------------------------------------------
+// Same formulation and evaluation order as stencil2d_fused_kernel (dfl_stencil.cu): G = curl(psi) (ops.py:264-274), the
+// residuals of the four forward differences of G and of the target (ops.py:205-225 on both, trainer.py:145-147,170-172),
+// their signs, dL/dG and dL/dpsi = curl^T(dL/dG) with the replicate-last edge folded into the adjoint.  The tile's im2col
+// rows need dL/dpsi on the 10 x 18 halo'd tile; that needs psi and x on a 15 x 23 footprint (2 before, 3 after), which the
+// 128 builder threads walk in three passes per stage.  The footprint is 3 floats per position against the 256 bytes per
+// voxel of the conv's input, so recomputing the halo (2.7x) costs nothing measurable.
+constexpr int LS_FY = 15, LS_FX = 23, LS_N = LS_FY * LS_FX;     // 345 footprint positions
+__device__ __forceinline__ float ls_sgn(float v) { return (v > 0.f ? 1.f : 0.f) - (v < 0.f ? 1.f : 0.f); }
+__device__ __forceinline__ float ls_wgt(int k, int n) { return (k < 0 || k >= n - 1) ? 0.f : (k == n - 2 ? 2.f : 1.f); }
+__device__ __forceinline__ float ls_fold(float g0, float g1, int k, int n) {
+  return (k < 0 || k >= n - 1) ? 0.f : (k == n - 2 ? g0 + g1 : g0);
+}
+__device__ __forceinline__ void ls_bar() {
+  __syncwarp();
+  asm volatile("bar.sync 1, 128;" ::: "memory");
+}
 
 __device__ __forceinline__ uint32_t lb_pack(float a, float b) {
   __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
   return *reinterpret_cast<uint32_t*>(&h);
 }
 
-template <int C, bool k3D>
+template <int C, bool k3D, bool kFuse = false>
 __global__ void __launch_bounds__(LB_THREADS, 1)
 lastconv_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmS, LastBwdParams p) {
+  static_assert(!kFuse || (C == 1 && !k3D), "the fused loss prologue of this kernel is the 2D (C = 1) path");
   constexpr int NT = k3D ? 27 : 9;
   constexpr int KREAL = NT * C;                   // <= 81
   constexpr int KSTEPS1 = (KREAL + 15) / 16;      // K16 steps of the dgrad GEMM
@@ -275,6 +304,7 @@ lastconv_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmS, LastBwdParams p)
     float bsum[C];
 #pragma unroll
     for (int c = 0; c < C; ++c) bsum[c] = 0.f;
+    double acc_l1 = 0.0, acc_j = 0.0;       // kFuse: loss terms of the pixels this CTA owns
     int i = 0;
     for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++i) {
       int r = tile;
@@ -285,6 +315,90 @@ lastconv_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmS, LastBwdParams p)
       const uint32_t s = i & 1, ph = (i >> 1) & 1;
       float* st = sD + s * LB_STAGE_F;
       const float* base = p.dout + (static_cast<size_t>(b) * p.D * p.H * p.W) * C;
+      if constexpr (kFuse) {
+        // stage buffers hold 2 x 180 floats in 2D; the stencil planes live behind them (2 x LB_STAGE_F floats are reserved)
+        float* sP = sD + 2 * 180;
+        float* sX = sP + LS_N;
+        float* sGv = sX + 2 * LS_N;
+        float* sDg = sGv + 2 * LS_N;
+        static_assert(2 * 180 + 7 * LS_N <= 2 * LB_STAGE_F, "stencil planes do not fit behind the stage buffers");
+        const int H = p.H, W = p.W;
+        const size_t img = static_cast<size_t>(b) * H * W;
+        // S0: psi and x on the footprint (zero outside the domain)
+        for (int pos = row; pos < LS_N; pos += 128) {
+          const int j = pos / LS_FX, ii = pos - j * LS_FX;
+          const int cx = x0 - 3 + ii, cy = y0 - 3 + j;
+          const bool in = cx >= 0 && cx < W && cy >= 0 && cy < H;
+          const size_t pix = img + static_cast<size_t>(in ? cy : 0) * W + (in ? cx : 0);
+          sP[pos] = in ? __ldg(p.pot + pix) : 0.f;
+          sX[2 * pos] = in ? __ldg(p.xt + pix * 2) : 0.f;
+          sX[2 * pos + 1] = in ? __ldg(p.xt + pix * 2 + 1) : 0.f;
+        }
+        ls_bar();
+        // S1: G = curl(psi): u = d psi / dy, v = psi[x] - psi[x+1]
+        for (int pos = row; pos < LS_N; pos += 128) {
+          const int j = pos / LS_FX, ii = pos - j * LS_FX;
+          const int cx = x0 - 3 + ii, cy = y0 - 3 + j;
+          const bool in = cx >= 0 && cx < W && cy >= 0 && cy < H;
+          const int im = max(ii - 1, 0), ip = min(ii + 1, LS_FX - 1), jm = max(j - 1, 0), jp = min(j + 1, LS_FY - 1);
+          const int ix_lo = (cx <= W - 2) ? ii : im, ix_hi = (cx <= W - 2) ? ip : ii;
+          const int jy_lo = (cy <= H - 2) ? j : jm, jy_hi = (cy <= H - 2) ? jp : j;
+          float g0 = 0.f, g1 = 0.f;
+          if (in) {
+            g0 = sP[jy_hi * LS_FX + ii] - sP[jy_lo * LS_FX + ii];
+            g1 = sP[j * LS_FX + ix_lo] - sP[j * LS_FX + ix_hi];
+            if (p.vel && ii >= 3 && ii < 19 && j >= 3 && j < 11) {        // the tile's own pixels
+              float* vd = p.vel + (img + static_cast<size_t>(cy) * W + cx) * 2;
+              vd[0] = g0; vd[1] = g1;
+            }
+          }
+          sGv[2 * pos] = g0;
+          sGv[2 * pos + 1] = g1;
+        }
+        ls_bar();
+        // S2: dL/dG and the loss terms of the tile's own pixels
+        for (int pos = row; pos < LS_N; pos += 128) {
+          const int j = pos / LS_FX, ii = pos - j * LS_FX;
+          const int cx = x0 - 3 + ii, cy = y0 - 3 + j;
+          const bool in = cx >= 0 && cx < W && cy >= 0 && cy < H;
+          const bool own = in && ii >= 3 && ii < 19 && j >= 3 && j < 11;
+          const int im = max(ii - 1, 0), ip = min(ii + 1, LS_FX - 1), jm = max(j - 1, 0), jp = min(j + 1, LS_FY - 1);
+          const float wxm = ls_wgt(cx - 1, W), wx0 = ls_wgt(cx, W), wym = ls_wgt(cy - 1, H), wy0 = ls_wgt(cy, H);
+#pragma unroll
+          for (int c = 0; c < 2; ++c) {
+            const float g = sGv[2 * pos + c], xx = sX[2 * pos + c];
+            const float e = g - xx;
+            const float dxp = (sGv[2 * (j * LS_FX + ip) + c] - g) - (sX[2 * (j * LS_FX + ip) + c] - xx);
+            const float dxm = (g - sGv[2 * (j * LS_FX + im) + c]) - (xx - sX[2 * (j * LS_FX + im) + c]);
+            const float dyp = (sGv[2 * (jp * LS_FX + ii) + c] - g) - (sX[2 * (jp * LS_FX + ii) + c] - xx);
+            const float dym = (g - sGv[2 * (jm * LS_FX + ii) + c]) - (xx - sX[2 * (jm * LS_FX + ii) + c]);
+            const float dg = p.c1 * ls_sgn(e) +
+                             p.c2 * ((wxm * ls_sgn(dxm) - wx0 * ls_sgn(dxp)) + (wym * ls_sgn(dym) - wy0 * ls_sgn(dyp)));
+            sDg[2 * pos + c] = in ? dg : 0.f;
+            if (own) {
+              acc_l1 += fabsf(e);
+              acc_j += static_cast<double>(wx0 * fabsf(dxp) + wy0 * fabsf(dyp));
+            }
+          }
+        }
+        ls_bar();
+        // S3: dL/dpsi = D_y^T gU - D_x^T gV on the halo'd tile -> the staged dOut positions (zero outside the domain)
+        for (int pos = row; pos < 180; pos += 128) {
+          const int yy = pos / 18, xx_ = pos - yy * 18;
+          const int j = yy + 2, ii = xx_ + 2;
+          const int cx = x0 - 1 + xx_, cy = y0 - 1 + yy;
+          const bool in = cx >= 0 && cx < W && cy >= 0 && cy < H;
+          float v = 0.f;
+          if (in) {
+            const int q = j * LS_FX + ii;
+            const float dyT_U = ls_fold(sDg[2 * (q - LS_FX)], sDg[2 * q], cy - 1, H) - ls_fold(sDg[2 * q], sDg[2 * (q + LS_FX)], cy, H);
+            const float dxT_V = ls_fold(sDg[2 * (q - 1) + 1], sDg[2 * q + 1], cx - 1, W) - ls_fold(sDg[2 * q + 1], sDg[2 * (q + 1) + 1], cx, W);
+            v = dyT_U - dxT_V;
+            if (p.dpot && xx_ >= 1 && xx_ < 17 && yy >= 1 && yy < 9) p.dpot[img + static_cast<size_t>(cy) * W + cx] = v;
+          }
+          st[pos] = v;
+        }
+      } else
       // ---- stage: position pos = (plane, yy, xx) of the halo'd tile <- dOut[z-1+plane (3D), y0-1+yy, x0-1+xx]
       for (int pos = row; pos < NZ * 180; pos += 128) {
         const int pl = pos / 180, rem = pos - pl * 180;
@@ -329,6 +443,35 @@ lastconv_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmS, LastBwdParams p)
       const float t = warp_sum(bsum[c]);
       if (lane == 0 && my_tiles > 0) atomicAdd(p.db + c, t);
     }
+    if constexpr (kFuse) {
+      // loss: one fp64 pair per CTA; the last CTA (atomic ticket) adds all pairs in CTA order -> deterministic, no finalize
+      // launch (same scheme as lastconv_bwd_fused_kernel)
+      double* sred = reinterpret_cast<double*>(sD + 2 * 180);      // the stencil planes are dead
+      ls_bar();
+      acc_l1 = warp_sum(acc_l1);
+      acc_j = warp_sum(acc_j);
+      if (lane == 0) { sred[warp - 6] = acc_l1; sred[4 + warp - 6] = acc_j; }
+      ls_bar();
+      if (row == 0) {
+        double a = 0, c = 0;
+        for (int q = 0; q < 4; ++q) { a += sred[q]; c += sred[4 + q]; }
+        p.partials[2 * blockIdx.x] = a;
+        p.partials[2 * blockIdx.x + 1] = c;
+        __threadfence();
+        const unsigned int done = atomicAdd(p.ticket, 1u);
+        if (done == gridDim.x - 1) {
+          __threadfence();
+          double sa = 0, sc = 0;
+          const volatile double* pp = p.partials;
+          for (unsigned int q = 0; q < gridDim.x; ++q) { sa += pp[2 * q]; sc += pp[2 * q + 1]; }
+          const double l1 = sa * p.inv_n1, jl = sc * p.inv_n2;
+          p.loss3[0] = static_cast<float>(p.w1 * l1 + p.w2 * jl);
+          p.loss3[1] = static_cast<float>(l1);
+          p.loss3[2] = static_cast<float>(jl);
+          *p.ticket = 0u;
+        }
+      }
+    }
   }
 
   tc_fence_before();
@@ -340,17 +483,57 @@ lastconv_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmS, LastBwdParams p)
   }
 }
 
-template <int C, bool k3D>
+template <int C, bool k3D, bool kFuse = false>
 static int lastconv_bwd_launch_t(const CUtensorMap& tmS, const LastBwdParams& p, cudaStream_t st) {
   static bool attr_set = false;
   if (!attr_set) {
-    DFL_CUDA_OK(cudaFuncSetAttribute(lastconv_bwd_tc_kernel<C, k3D>, cudaFuncAttributeMaxDynamicSharedMemorySize, LB_SMEM));
+    DFL_CUDA_OK(cudaFuncSetAttribute(lastconv_bwd_tc_kernel<C, k3D, kFuse>, cudaFuncAttributeMaxDynamicSharedMemorySize, LB_SMEM));
     attr_set = true;
   }
   const int grid = std::min(p.ntiles, num_sms());
-  lastconv_bwd_tc_kernel<C, k3D><<<grid, LB_THREADS, LB_SMEM, st>>>(tmS, p);
-  DFL_LAUNCH_OK("lastconv_bwd_tc_kernel");
+  lastconv_bwd_tc_kernel<C, k3D, kFuse><<<grid, LB_THREADS, LB_SMEM, st>>>(tmS, p);
+  DFL_LAUNCH_OK(kFuse ? "lastconv_bwd_tc_kernel (fused 2D loss)" : "lastconv_bwd_tc_kernel");
   return DFL_OK;
+}
+
+static int lastconv_bwd_map(CUtensorMap* tmS, const void* s, const LastBwdParams& p) {
+  const uint64_t gd[5] = {128, static_cast<uint64_t>(p.W), static_cast<uint64_t>(p.H), static_cast<uint64_t>(p.D),
+                          static_cast<uint64_t>(p.B)};
+  const uint64_t gs[4] = {256, 256ull * p.W, 256ull * p.W * p.H, 256ull * p.W * p.H * p.D};
+  const uint32_t box[5] = {64, 16, 8, 1, 1};
+  return encode_tensor_map(tmS, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, s, gd, gs, box, CU_TENSOR_MAP_SWIZZLE_128B);
+}
+
+// 2D half of dfl_lastconv_curl_loss_bwd: pot fp32 [B,H,W,1], x fp32 [B,H,W,2], s bf16 [B,H,W,128]; workspace as for 3D
+int lastconv_curl_loss_bwd_2d(const void* s, const float* pot, const float* x, const float* w, const void* mask_src, void* ds,
+                              void* ds_masked, float* dw, float* db, float* dpot, float* vel, float* loss3, void* workspace,
+                              const int64_t* dims, float w1, float w2, float grad_scale, cudaStream_t st) {
+  DFL_REQUIRE(s && pot && x && w && dw && db && loss3 && workspace, "lastconv_curl_loss_bwd: null tensor");
+  DFL_REQUIRE(!(ds_masked && !mask_src), "lastconv_curl_loss_bwd: ds_masked requested without mask_src");
+  LastBwdParams p{};
+  p.B = static_cast<int>(dims[0]); p.D = 1; p.H = static_cast<int>(dims[1]); p.W = static_cast<int>(dims[2]);
+  DFL_REQUIRE(p.H >= 2 && p.W >= 2, "lastconv_curl_loss_bwd: extents >= 2 required (got %d x %d)", p.H, p.W);
+  p.tx = (p.W + 15) / 16;
+  p.ty = (p.H + 7) / 8;
+  p.ntiles = p.B * p.ty * p.tx;
+  p.w = w;
+  p.mask_src = static_cast<const __nv_bfloat16*>(mask_src);
+  p.ds = static_cast<__nv_bfloat16*>(ds);
+  p.ds_masked = static_cast<__nv_bfloat16*>(ds_masked);
+  p.dw = dw; p.db = db;
+  p.pot = pot; p.xt = x; p.dpot = dpot; p.vel = vel;
+  p.partials = static_cast<double*>(workspace);
+  p.ticket = reinterpret_cast<unsigned int*>(p.partials + 2 * 160);
+  p.loss3 = loss3;
+  const double pix = static_cast<double>(p.B) * p.H * p.W, n1 = pix * 2, n2 = pix * 4;
+  p.c1 = static_cast<float>(static_cast<double>(w1) * grad_scale / n1);
+  p.c2 = static_cast<float>(static_cast<double>(w2) * grad_scale / n2);
+  p.w1 = w1; p.w2 = w2;
+  p.inv_n1 = 1.0 / n1; p.inv_n2 = 1.0 / n2;
+  CUtensorMap tmS;
+  int rc = lastconv_bwd_map(&tmS, s, p);
+  if (rc) return rc;
+  return lastconv_bwd_launch_t<1, false, true>(tmS, p, st);
 }
 
 int lastconv_bwd_tc(const void* s, const float* dout, const float* w, const void* mask_src, void* ds, void* ds_masked,

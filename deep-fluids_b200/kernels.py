@@ -531,11 +531,14 @@ def lastconv_curl_loss_workspace(device):
 
 def lastconv_curl_loss_bwd(s, pot, x, w, mask_src, ds, ds_masked, dw, db, loss3, workspace, w1=1.0, w2=1.0, grad_scale=1.0,
                            dpot=None, vel=None):
-    """FUSED curl + Jacobian-L1 loss + adjoints + output-conv backward (3D): see dfl_lastconv_curl_loss_bwd"""
+    """FUSED curl + Jacobian-L1 loss + adjoints + output-conv backward: see dfl_lastconv_curl_loss_bwd.
+    3D: pot, x [B,D,H,W,3];  2D: pot [B,H,W,1] (stream function), x [B,H,W,2]"""
     d, nd = _spatial(s)
-    assert nd == 3 and pot.dtype == torch.float32 and x.dtype == torch.float32 and pot.shape[-1] == 3 and x.shape[-1] == 3
-    nvox = x.numel() // 3
-    work = nvox * (128 * 2 * 4 + 24)       # algorithmic bytes: read s + mask, write ds + ds_masked (bf16 x 128), read A + x
+    assert pot.dtype == torch.float32 and x.dtype == torch.float32
+    assert (nd == 3 and pot.shape[-1] == 3 and x.shape[-1] == 3) or (nd == 2 and pot.shape[-1] == 1 and x.shape[-1] == 2)
+    nvox = x.numel() // x.shape[-1]
+    # algorithmic bytes: read s + mask, write ds + ds_masked (bf16 x 128), read the potential and the target
+    work = nvox * (128 * 2 * 4 + 4 * (pot.shape[-1] + x.shape[-1]))
     PROF.timed("lastconv_bwd_fused", work, lambda: check(cabi.lib().dfl_lastconv_curl_loss_bwd(
         _p(s), _p(pot), _p(x), _p(w), _p(mask_src), _p(ds), _p(ds_masked), _p(dw), _p(db), _p(dpot), _p(vel), _p(loss3),
         _p(workspace), d, nd, float(w1), float(w2), float(grad_scale), _st())))

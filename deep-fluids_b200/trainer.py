@@ -101,6 +101,9 @@ class Trainer(object):
 
         # tf.train.Supervisor restores the latest checkpoint of the log dir (trainer.py:110-123): a TensorFlow bundle
         # (`checkpoint` + `model.ckpt-<step>.index/.data-*`, e.g. written by the reference itself) wins over `model.pt`
+        self._restore()
+
+    def _restore(self):
         if self.load_path:
             from . import tf_checkpoint as tfc
             prefix = tfc.latest_checkpoint(self.load_path)
@@ -108,6 +111,11 @@ class Trainer(object):
                 self.load_tf(prefix)
             elif os.path.exists(os.path.join(self.load_path, "model.pt")):
                 self.load(os.path.join(self.load_path, "model.pt"))
+
+    def _slot_variables(self):
+        """variables that own Adam slots in a TensorFlow checkpoint: the trainable ones (arch=nn keeps the batch-norm moving
+        statistics, which have none, in the same flat buffer)"""
+        return list(getattr(self.engine, "_trainable", None) or self.engine.params.table)
 
     # ------------------------------------------------------------------ build (trainer.py:136-184)
     def build_model(self):
@@ -247,10 +255,10 @@ class Trainer(object):
         return pot
 
     def _fused_args(self, x, want_vel=False):
-        """3D + use_curl on the fused bf16 engine: the loss stencil runs in the prologue of the output conv's backward
-        kernel (DFL_FUSED_LOSS=0 restores the separate stencil launches for A/B runs)."""
+        """use_curl on the fused bf16 engines, 2D and 3D: the loss stencil runs in the prologue of the output conv's backward
+        kernel (DFL_FUSED_LOSS=0 restores the separate stencil launch for A/B runs)."""
         from .encoder import AEEngine
-        ok = (self.is_3d and self.use_c and x.dtype == torch.float32 and x.shape[-2] % 2 == 0
+        ok = (self.use_c and x.dtype == torch.float32 and (not self.is_3d or x.shape[-2] % 2 == 0)
               and (getattr(self, "_engine_cls", None) is GeneratorEngine or isinstance(self.engine, AEEngine))
               and os.environ.get("DFL_FUSED_LOSS", "1") != "0")
         if not ok:
@@ -749,8 +757,7 @@ class Trainer(object):
         self.z_num, self.p_num, self.w_num = config.z_num, batch_manager.dof, config.w_size
         self.accum = 1
         self.build_model_nn()
-        if self.load_path and os.path.exists(os.path.join(self.load_path, "model.pt")):
-            self.load(os.path.join(self.load_path, "model.pt"))
+        self._restore()
 
     def build_model_nn(self):
         """y_ = NN(x); roll-out over the window; loss = mean squared error of the w_num chained predictions
@@ -850,8 +857,9 @@ class Trainer(object):
         P = self.engine.params
         tensors = {k: P.p(k).detach().cpu().numpy() for k in P.table}
         if self.optimizer == 'adam':
-            tensors.update(tfc.adam_state_to_tf(P.table, {k: P._view(P.m, k).cpu().numpy() for k in P.table},
-                                                {k: P._view(P.v, k).cpu().numpy() for k in P.table},
+            slot_tab = type(P.table)((k, P.table[k]) for k in self._slot_variables())
+            tensors.update(tfc.adam_state_to_tf(slot_tab, {k: P._view(P.m, k).cpu().numpy() for k in slot_tab},
+                                                {k: P._view(P.v, k).cpu().numpy() for k in slot_tab},
                                                 self.engine.adam_t, self.beta1, self.beta2))
         tensors["step"] = np.int32(self.step)
         tensors["g_lr"] = np.float32(self.g_lr)
@@ -872,14 +880,15 @@ class Trainer(object):
         for k in P.table:
             if tuple(have[k]) != tuple(P.table[k]):
                 raise ValueError("variable %s: checkpoint shape %s, model shape %s" % (k, tuple(have[k]), tuple(P.table[k])))
-        slots = [k + sfx for k in P.table for sfx in ("/Adam", "/Adam_1")]
+        slot_vars = self._slot_variables()
+        slots = [k + sfx for k in slot_vars for sfx in ("/Adam", "/Adam_1")]
         with_adam = all(n in have for n in slots) and "beta1_power" in have
         extra = [n for n in ("step", "g_lr") if n in have]
         powers = [n for n in ("beta1_power", "beta2_power") if n in have]
         t = tfc.read_checkpoint(prefix, list(P.table) + (slots + powers if with_adam else []) + extra)
         P.load_state_dict({k: torch.from_numpy(t[k]) for k in P.table})
         if with_adam:
-            for k in P.table:
+            for k in slot_vars:
                 P._view(P.m, k).copy_(torch.from_numpy(t[k + "/Adam"]).view(*P.table[k]))
                 P._view(P.v, k).copy_(torch.from_numpy(t[k + "/Adam_1"]).view(*P.table[k]))
             self.engine.adam_t = tfc.adam_t_from_tf(float(t["beta1_power"]), self.beta1,

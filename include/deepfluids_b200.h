@@ -148,7 +148,8 @@ int dfl_lastconv_fwd(const void* s, const float* w, const float* bias, float* ou
 int dfl_lastconv_bwd(const void* s, const float* dout, const float* w, const void* mask_src, void* ds, void* ds_masked,
                      float* dw, float* db, const int64_t* dims, int ndim, int cout, void* stream);
 
-/* FUSED last-generator-epilogue / first-backward-prologue pair of the 3D train step (north_star; SURVEY.md 8a "S" + a3-last).
+/* FUSED last-generator-epilogue / first-backward-prologue pair of the train step (north_star; SURVEY.md 8a "S" + a3-last); 3D
+ * described first, 2D (ndim = 2) at the end.
  * Replaces trainer3.py:16-24,49-51 (curl, jacobian3 of prediction and target, both L1 means) + TF autodiff of all of it +
  * Conv3DBackpropInput / Conv3DBackpropFilter / BiasAddGrad of model.py:84 -- with NOTHING launched in between:
  *   dfl_lastconv_curl_loss_fwd: the output conv; its epilogue adds the bias and stores the fp32 potential A = G_s
@@ -161,7 +162,11 @@ int dfl_lastconv_bwd(const void* s, const float* dout, const float* w, const voi
  *       caller passes `dpot` (and `vel` for G_); loss3 = {w1*l1 + w2*jl1, l1, jl1} is complete when the kernel ends
  *       (ordered fp64 partials, last CTA adds them: deterministic).
  *   pot, x: fp32 [B,D,H,W,3];  s: bf16 [B,D,H,W,128];  W even.  workspace: dfl_lastconv_curl_loss_workspace_bytes() bytes,
- *   ZEROED ONCE by the caller before the first launch (it holds the CTA ticket, which resets itself). */
+ *   ZEROED ONCE by the caller before the first launch (it holds the CTA ticket, which resets itself).
+ *   ndim = 2 (trainer.py:140-147,170-172 + model.py:42): pot = the stream function psi fp32 [B,H,W,1], x fp32 [B,H,W,2], s bf16
+ *   [B,H,W,128], w [3,3,128,1].  The four im2col-builder warps of the output conv's backward compute G_ = curl(psi), the
+ *   Jacobian residuals, the loss terms and dL/dpsi on each 8 x 16 tile's 15 x 23 footprint (three barrier-separated passes in
+ *   shared memory) instead of loading a dL/dpsi tile: same outputs, same workspace, same deterministic loss reduction. */
 size_t dfl_lastconv_curl_loss_workspace_bytes(void);
 int dfl_lastconv_curl_loss_fwd(const void* s, const float* w, const float* bias, float* pot, const int64_t* dims, int ndim,
                                int cout, void* stream);

@@ -184,3 +184,99 @@ def test_trainer_gradients_and_loss_with_and_without_the_fusion():
     assert abs(losses[0][0] - losses[1][0]) <= 2e-6 * abs(losses[1][0]), losses
     assert rel_l2(grads[0], grads[1]) <= 5e-3, rel_l2(grads[0], grads[1])
     # (after ten sign-like early Adam steps at lr 1e-3 the two runs are a few % apart in loss: both fell, asserted above)
+
+
+# ------------------------------------------------------------------ 2D: the same entry point with ndim = 2
+SHAPES_2D = [(2, 16, 32), (1, 8, 16), (3, 5, 7), (1, 2, 2), (2, 20, 38), (4, 128, 96), (2, 128, 128)]
+
+
+def _inputs_2d(shape, seed):
+    g = torch.Generator().manual_seed(seed)
+    B, H, W = shape
+    pot = torch.randn(B, H, W, 1, generator=g) * 0.05
+    pot = (pot + torch.roll(pot, 1, 1) + torch.roll(pot, 1, 2)) / 3
+    x, _ = T.synthetic_batch(B, [H, W], seed=seed + 1, smooth=1)
+    s = (torch.randn(B, H, W, 128, generator=g) * 0.5).bfloat16()
+    mask = torch.randn(B, H, W, 128, generator=g).bfloat16()
+    w = R.xavier_uniform_((3, 3, 128, 1), g).bfloat16().float()
+    return pot, x, s, mask, w
+
+
+@pytest.mark.parametrize("shape", SHAPES_2D)
+def test_fused_bwd_2d_vs_oracle_and_unfused_pair(shape):
+    """2D (stream function psi, C = 1): the builder warps of the output conv's backward compute curl, both Jacobians, the
+    loss terms and dL/dpsi on the tile's 15 x 23 footprint.  Oracle: loss (fp64), dL/dpsi (fp32 autograd), G_ bit for bit;
+    un-fused pair (dfl_stencil_loss_fwdbwd + dfl_lastconv_bwd): every output bit for bit (same arithmetic, same kernel body)."""
+    from deepfluids_b200 import kernels as K
+    d = dev()
+    pot, x, s, mask, w = _inputs_2d(shape, 23 + sum(shape))
+    ds = torch.full(s.shape, float("nan"), dtype=torch.bfloat16, device=d)
+    dsm = torch.full(s.shape, float("nan"), dtype=torch.bfloat16, device=d)
+    dw, db, loss3 = torch.zeros(w.shape, device=d), torch.zeros(1, device=d), torch.zeros(3, device=d)
+    dpot = torch.full(pot.shape, float("nan"), device=d)
+    vel = torch.full(x.shape, float("nan"), device=d)
+    ws = K.lastconv_curl_loss_workspace(d)
+    for _ in range(2):                       # twice: the CTA ticket must reset itself
+        dw.zero_(); db.zero_()
+        K.lastconv_curl_loss_bwd(s.to(d), pot.to(d), x.to(d), w.to(d), mask.to(d), ds, dsm, dw, db, loss3, ws, 0.7, 1.3, 1.0,
+                                 dpot=dpot, vel=vel)
+    torch.cuda.synchronize()
+    p = pot.clone().requires_grad_(True)
+    loss, l1, jl1, vel_ref = T.stencil_loss(p, x, 0.7, 1.3)
+    (gref,) = torch.autograd.grad(loss, p)
+    with torch.no_grad():
+        l64, l164, jl164, _ = T.stencil_loss(pot.double(), x.double(), 0.7, 1.3)
+    assert torch.equal(vel.cpu(), vel_ref.detach())
+    if shape[1] > 2:
+        assert float(K.divergence(vel).abs().max()) <= 1e-5
+    for got, want in zip(loss3.tolist(), (l64.item(), l164.item(), jl164.item())):
+        assert abs(got - want) <= 3e-6 * abs(want), (loss3.tolist(), l64.item(), l164.item(), jl164.item())
+    scale = float(gref.abs().max())
+    assert float((dpot.cpu() - gref).abs().max()) <= 1e-6 * scale + 1e-12
+    # output conv backward fed with the bf16 copy of that gradient (torch's CPU conv backward rejects the 2 x 2 image: that
+    # shape is covered by the comparison with the un-fused pair below)
+    if shape[1] * shape[2] >= 16:
+        sin, wt, bt = s.float().requires_grad_(True), w.clone().requires_grad_(True), torch.zeros(1, requires_grad=True)
+        y = R.conv_nd(sin, wt, bt, 1, None)
+        gx, gw, gb = torch.autograd.grad(y, [sin, wt, bt], gref.bfloat16().float())
+        assert rel_l2(ds.float(), gx) <= 4e-3
+        assert rel_l2(dsm.float(), gx * torch.where(mask.float() >= 0, 1.0, 0.2)) <= 4e-3
+        assert rel_l2(dw, gw) <= 2e-4
+        assert float((db.cpu() - gb).abs().max()) <= 1e-3 * float(gref.abs().sum())
+    # the un-fused pair
+    l3u, dpu, velu = K.stencil_loss_fwdbwd(pot.to(d), x.to(d), 0.7, 1.3, want_vel=True)
+    assert torch.equal(dpu, dpot) and torch.equal(velu, vel)
+    ds_u, dsm_u = torch.empty_like(ds), torch.empty_like(dsm)
+    dw_u, db_u = torch.zeros_like(dw), torch.zeros_like(db)
+    K.lastconv_bwd(s.to(d), dpu, w.to(d), mask.to(d), ds_u, dsm_u, dw_u, db_u)
+    assert torch.equal(ds_u, ds) and torch.equal(dsm_u, dsm)
+    assert rel_l2(dw, dw_u) <= 1e-5 and abs(l3u[0].item() - loss3[0].item()) <= 2e-6 * abs(l3u[0].item())
+    # optional outputs off: same ds_masked, dw and loss
+    dsm2, dw2, db2, l32 = torch.empty_like(dsm), torch.zeros_like(dw), torch.zeros_like(db), torch.zeros(3, device=d)
+    K.lastconv_curl_loss_bwd(s.to(d), pot.to(d), x.to(d), w.to(d), mask.to(d), None, dsm2, dw2, db2, l32, ws, 0.7, 1.3)
+    assert torch.equal(dsm2, dsm) and rel_l2(dw2, dw) <= 1e-5 and torch.equal(l32, loss3)
+
+
+def test_trainer_2d_step_fused_equals_unfused(monkeypatch):
+    """one 2D train-step body with and without the fusion: same loss terms, same gradients (the weight-gradient atomics
+    reorder sums: 1e-5)"""
+    import importlib
+    C = importlib.import_module("deepfluids_b200.config")
+    from deepfluids_b200.data import BatchManager
+    from deepfluids_b200.trainer import Trainer
+    grads, losses = [], []
+    monkeypatch.setenv("DFL_CUDA_GRAPH", "0")
+    for flag in ("1", "0"):
+        monkeypatch.setenv("DFL_FUSED_LOSS", flag)
+        cfg, _ = C.get_config(["--synthetic=true", "--is_3d=false", "--res_x=32", "--res_y=48", "--batch_size=4", "--num_conv=2",
+                               "--max_step=10"])
+        bm = BatchManager(cfg, pool=1)
+        tr = Trainer(cfg, bm)
+        x, y = bm.batch()
+        assert (tr._fused_args(x) is not None) == (flag == "1")
+        tr._step_body_a(x, y)
+        torch.cuda.synchronize()
+        grads.append(tr.engine.params.grad.clone())
+        losses.append(tr._loss3.clone())
+    assert torch.allclose(losses[0], losses[1], rtol=2e-6, atol=0)
+    assert float((grads[0] - grads[1]).abs().max()) <= 1e-5 * float(grads[1].abs().max())

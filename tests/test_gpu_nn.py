@@ -171,6 +171,11 @@ def test_trainer_nn_end_to_end(tmp_path):
     assert np.isfinite(first) and np.isfinite(l1[0]) and np.isfinite(l1[1])
     assert l1[0] < l0[0]                                     # the single-step test loss goes down
     assert os.path.exists(os.path.join(cfg.model_dir, "model.pt"))
+    # the TensorFlow bundle carries slim's names; Adam slots only for the trainable variables
+    tfc = importlib.import_module("deep-fluids_b200.tf_checkpoint")
+    names = {n for n, _, _ in tfc.list_variables(tfc.latest_checkpoint(cfg.model_dir))}
+    assert {"NN/BatchNorm/moving_mean", "NN/BatchNorm_1/moving_variance", "NN/fully_connected_2/weights/Adam_1", "beta1_power"} <= names
+    assert "NN/BatchNorm/moving_mean/Adam" not in names
     # a fresh trainer restored from the checkpoint integrates identically
     cfg2 = _nn_config(root, is_train=False, load_path=cfg.model_dir)
     bm2 = data_nn.BatchManager(cfg2, device=dev())
