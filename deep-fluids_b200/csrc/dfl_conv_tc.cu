@@ -49,6 +49,8 @@ constexpr int CT_B_BYTES = CT_BLOCK_N * CT_BLOCK_K * 2;   // 16 KB
 constexpr int CT_STAGE_BYTES = CT_A_BYTES + CT_B_BYTES;
 constexpr int CT_THREADS = 192;
 constexpr int CT_SMEM_BYTES = CT_STAGES * CT_STAGE_BYTES + 1024 /*align slack*/ + 1024 /*barriers, bias*/;
+constexpr int CT_STAGES_PAIR = 4;                 // paired bricks: 4 x (2 x 16 KB activations + 16 KB weights)
+constexpr int CT_SMEM_BYTES_PAIR = CT_STAGES_PAIR * (2 * CT_A_BYTES + CT_B_BYTES) + 1024 + 1024;
 
 enum : int { CF_LRELU = 1, CF_OUT2_UPSAMPLE = 2, CF_MASK_AFTER_RESIDUAL = 4, CF_SPLIT_IO = 8 };
 constexpr int CT_MAX_TAPS = 64;                    // 27 for a 3x3x3 layer; 64 = 8 output phases x 2x2x2 taps of the
@@ -112,13 +114,22 @@ __device__ __forceinline__ void conv_epilogue_row(const ConvTcParams& p, uint32_
 // any explicit tap list.  Inputs wider than 128 channels are stored as channel blocks [nblk*B, D, H, W, 128]:
 // 64-channel slice c lives in block c>>1, i.e. at batch coordinate b + (c>>1)*B.
 // =============================================================================================
+// kPair: the CTA processes TWO bricks (tiles 2q, 2q+1) per step of its schedule; they share every streamed weight tile, so
+// a stage carries 2 x 16 KB of activations + 16 KB of weights for 8 MMAs instead of 16 + 16 KB for 4: 96 instead of 128
+// bytes of L2->SM traffic per tensor-core clock.  ncu on the phase-decomposed launches of the 128^3 step showed this
+// kernel pulling 58-67 B/clk/SM from L2 with the tensor pipe 46-53 % active -- operand delivery, not the epilogue, is its
+// limit (profiles/r02_ncu_conv_tap.txt).  Used when the launch has at least two bricks per SM.
+template <bool kPair>
 __global__ void __launch_bounds__(CT_THREADS, 1)
 conv_tap_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, ConvTcParams p) {
+  constexpr int NA = kPair ? 2 : 1;
+  constexpr int STAGES = kPair ? CT_STAGES_PAIR : CT_STAGES;
+  constexpr int STAGE_BYTES = NA * CT_A_BYTES + CT_B_BYTES;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* ctrl = smem + CT_STAGES * CT_STAGE_BYTES;
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(ctrl);            // [CT_STAGES]
-  uint64_t* empty_bar = full_bar + CT_STAGES;                        // [CT_STAGES]
+  uint8_t* ctrl = smem + STAGES * STAGE_BYTES;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(ctrl);            // [STAGES]
+  uint64_t* empty_bar = full_bar + CT_STAGES;                        // [STAGES]
   uint64_t* tfull_bar = empty_bar + CT_STAGES;                       // [2]
   uint64_t* tempty_bar = tfull_bar + 2;                              // [2]
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tempty_bar + 2);  // [1]
@@ -126,12 +137,13 @@ conv_tap_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int kblocks = p.ntap * p.cin_chunks;
+  const int nsteps = kPair ? (p.ntiles + 1) / 2 : p.ntiles;          // schedule steps (brick pairs / bricks)
 
   if (threadIdx.x < CT_BLOCK_N) s_bias[threadIdx.x] = p.bias ? p.bias[threadIdx.x] : 0.f;
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
-    for (int s = 0; s < CT_STAGES; ++s) {
+    for (int s = 0; s < STAGES; ++s) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
     }
@@ -142,7 +154,7 @@ conv_tap_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     fence_barrier_init();
   }
   if (warp == 1) {
-    tmem_alloc(tmem_ptr, 256);
+    tmem_alloc(tmem_ptr, 256 * NA);
     tmem_relinquish();
   }
   tc_fence_before();
@@ -153,21 +165,27 @@ conv_tap_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   if (warp == 0) {
     if (lane == 0) {
       uint32_t it = 0;
-      for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
-        int r = tile;
-        const int x0 = (r % p.tx) * p.bw; r /= p.tx;
-        const int y0 = (r % p.ty) * p.bh; r /= p.ty;
-        const int z0 = (r % p.tz) * p.bd; r /= p.tz;
-        const int b = r;
+      for (int step = blockIdx.x; step < nsteps; step += gridDim.x) {
+        int x0[NA], y0[NA], z0[NA], bb[NA];
+#pragma unroll
+        for (int h = 0; h < NA; ++h) {
+          int r = min(NA * step + h, p.ntiles - 1);       // an odd brick count: the ghost half re-loads the last brick
+          x0[h] = (r % p.tx) * p.bw; r /= p.tx;
+          y0[h] = (r % p.ty) * p.bh; r /= p.ty;
+          z0[h] = (r % p.tz) * p.bd; r /= p.tz;
+          bb[h] = r;
+        }
         for (int t = 0; t < p.ntap; ++t)
           for (int c = 0; c < p.cin_chunks; ++c, ++it) {
-            const uint32_t s = it % CT_STAGES, ph = (it / CT_STAGES) & 1;
+            const uint32_t s = it % STAGES, ph = (it / STAGES) & 1;
             mbar_wait(&empty_bar[s], ph ^ 1);
-            mbar_expect_tx(&full_bar[s], CT_STAGE_BYTES);
-            uint8_t* sa = smem + s * CT_STAGE_BYTES;
-            tma_load_5d(sa, &tmA, &full_bar[s], (c & 1) * CT_BLOCK_K, x0 * p.in_stride + p.tap_dx[t],
-                        y0 * p.in_stride + p.tap_dy[t], z0 * p.in_stride + p.tap_dz[t], b + p.blkmap[c >> 1] * p.B);
-            tma_load_2d(sa + CT_A_BYTES, &tmB, &full_bar[s], p.tap_col[t] + c * CT_BLOCK_K, 0);
+            mbar_expect_tx(&full_bar[s], STAGE_BYTES);
+            uint8_t* sa = smem + s * STAGE_BYTES;
+#pragma unroll
+            for (int h = 0; h < NA; ++h)
+              tma_load_5d(sa + h * CT_A_BYTES, &tmA, &full_bar[s], (c & 1) * CT_BLOCK_K, x0[h] * p.in_stride + p.tap_dx[t],
+                          y0[h] * p.in_stride + p.tap_dy[t], z0[h] * p.in_stride + p.tap_dz[t], bb[h] + p.blkmap[c >> 1] * p.B);
+            tma_load_2d(sa + NA * CT_A_BYTES, &tmB, &full_bar[s], p.tap_col[t] + c * CT_BLOCK_K, 0);
           }
       }
     }
@@ -176,22 +194,24 @@ conv_tap_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     if (lane == 0) {
       constexpr uint32_t idesc = umma_idesc_bf16(CT_BLOCK_M, CT_BLOCK_N, 0, 0);
       uint32_t it = 0, tcount = 0;
-      for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++tcount) {
+      for (int step = blockIdx.x; step < nsteps; step += gridDim.x, ++tcount) {
         const uint32_t acc = tcount & 1, aph = (tcount >> 1) & 1;
         mbar_wait(&tempty_bar[acc], aph ^ 1);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_u + acc * CT_BLOCK_N;
+        const uint32_t d_tmem = tmem_u + acc * (NA * CT_BLOCK_N);
         for (int kb = 0; kb < kblocks; ++kb, ++it) {
-          const uint32_t s = it % CT_STAGES, ph = (it / CT_STAGES) & 1;
+          const uint32_t s = it % STAGES, ph = (it / STAGES) & 1;
           mbar_wait(&full_bar[s], ph);
           tc_fence_after();
-          const uint32_t sa = smem_u32(smem + s * CT_STAGE_BYTES);
-          const uint32_t sb = sa + CT_A_BYTES;
+          const uint32_t sa = smem_u32(smem + s * STAGE_BYTES);
+          const uint32_t sb = sa + NA * CT_A_BYTES;
+          const uint64_t db0 = umma_desc_sw128(sb, 16, 1024);
 #pragma unroll
-          for (int k = 0; k < CT_BLOCK_K / 16; ++k) {
-            const uint64_t da = umma_desc_sw128(sa, 16, 1024) + 2 * k;    // +32 B per K step = +2 address units
-            const uint64_t db = umma_desc_sw128(sb, 16, 1024) + 2 * k;
-            umma_bf16(d_tmem, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+          for (int h = 0; h < NA; ++h) {
+            const uint64_t da0 = umma_desc_sw128(sa + h * CT_A_BYTES, 16, 1024);
+#pragma unroll
+            for (int k = 0; k < CT_BLOCK_K / 16; ++k)      // +32 B per K step = +2 address units
+              umma_bf16(d_tmem + h * CT_BLOCK_N, da0 + 2 * k, db0 + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
           }
           umma_commit(&empty_bar[s]);
         }
@@ -203,21 +223,27 @@ conv_tap_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     const int row = quarter * 32 + lane;
     const int lw = row % p.bw, lh = (row / p.bw) % p.bh, ld = row / (p.bw * p.bh);
     uint32_t tcount = 0;
-    for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++tcount) {
+    for (int step = blockIdx.x; step < nsteps; step += gridDim.x, ++tcount) {
       const uint32_t acc = tcount & 1, aph = (tcount >> 1) & 1;
-      int r = tile;
-      const int x = (r % p.tx) * p.bw + lw; r /= p.tx;
-      const int y = (r % p.ty) * p.bh + lh; r /= p.ty;
-      const int z = (r % p.tz) * p.bd + ld; r /= p.tz;
-      const int b = r;
-      const int xo = x * p.out_stride + p.orx, yo = y * p.out_stride + p.ory, zo = z * p.out_stride + p.orz;
-      const bool valid = (x < p.W) && (y < p.H) && (z < p.D) && (xo < p.oW) && (yo < p.oH) && (zo < p.oD);
-      EpiPre pre;
-      epi_prefetch(p, valid, epi_pos(p, b, zo, yo, xo), 0, pre);      // in flight while the tile's MMAs finish
-      mbar_wait(&tfull_bar[acc], aph);
-      tc_fence_after();
-      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * CT_BLOCK_N;
-      conv_epilogue_row(p, taddr, valid, b, zo, yo, xo, s_bias, pre, false, 0);
+#pragma unroll 1
+      for (int h = 0; h < NA; ++h) {
+        const int tile = NA * step + h;
+        int r = min(tile, p.ntiles - 1);
+        const int x = (r % p.tx) * p.bw + lw; r /= p.tx;
+        const int y = (r % p.ty) * p.bh + lh; r /= p.ty;
+        const int z = (r % p.tz) * p.bd + ld; r /= p.tz;
+        const int b = r;
+        const int xo = x * p.out_stride + p.orx, yo = y * p.out_stride + p.ory, zo = z * p.out_stride + p.orz;
+        const bool valid = (tile < p.ntiles) && (x < p.W) && (y < p.H) && (z < p.D) && (xo < p.oW) && (yo < p.oH) && (zo < p.oD);
+        EpiPre pre;
+        epi_prefetch(p, valid, epi_pos(p, b, zo, yo, xo), 0, pre);      // in flight while the tile's MMAs finish
+        if (h == 0) {
+          mbar_wait(&tfull_bar[acc], aph);
+          tc_fence_after();
+        }
+        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + (acc * NA + h) * CT_BLOCK_N;
+        conv_epilogue_row(p, taddr, valid, b, zo, yo, xo, s_bias, pre, false, 0);
+      }
       tc_fence_before();
       mbar_arrive(&tempty_bar[acc]);
     }
@@ -228,7 +254,7 @@ conv_tap_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   if (warp == 1) {
     __syncwarp();
     tc_fence_after();
-    tmem_dealloc(tmem_base, 256);
+    tmem_dealloc(tmem_base, 256 * NA);
   }
 }
 
@@ -927,11 +953,18 @@ int conv_tap_launch(const void* x, const void* w_packed, const float* bias, void
   }
   static bool attr_set = false;
   if (!attr_set) {
-    DFL_CUDA_OK(cudaFuncSetAttribute(conv_tap_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, CT_SMEM_BYTES));
+    DFL_CUDA_OK(cudaFuncSetAttribute(conv_tap_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, CT_SMEM_BYTES));
+    DFL_CUDA_OK(cudaFuncSetAttribute(conv_tap_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, CT_SMEM_BYTES_PAIR));
     attr_set = true;
   }
-  const int grid = std::min(p.ntiles, num_sms());
-  conv_tap_kernel<<<grid, CT_THREADS, CT_SMEM_BYTES, st>>>(tmA, tmB, p);
+  static const int pair_mode = getenv("DFL_CONV_TAP_PAIR") ? atoi(getenv("DFL_CONV_TAP_PAIR")) : 1;
+  if (pair_mode && p.ntiles >= 2 * num_sms()) {        // at least two bricks per SM: pair them (shared weight tiles)
+    const int grid = std::min((p.ntiles + 1) / 2, num_sms());
+    conv_tap_kernel<true><<<grid, CT_THREADS, CT_SMEM_BYTES_PAIR, st>>>(tmA, tmB, p);
+  } else {
+    const int grid = std::min(p.ntiles, num_sms());
+    conv_tap_kernel<false><<<grid, CT_THREADS, CT_SMEM_BYTES, st>>>(tmA, tmB, p);
+  }
   DFL_LAUNCH_OK("conv_tap_kernel");
   return DFL_OK;
 }
