@@ -214,4 +214,12 @@ int encode_tensor_map(CUtensorMap* out, CUtensorMapDataType dt, int rank, const 
                       const uint64_t* strides_bytes /* rank-1 entries */, const uint32_t* box, CUtensorMapSwizzle sw,
                       const uint32_t* elem_strides = nullptr /* traversal strides, default 1 */);
 
+
+// ---- deterministic gradient reductions (dfl_set_deterministic; dfl_wgrad_tc.cu owns the workspace) --------------------
+// Output conv (128 -> C <= 3): every CTA stores its [k = tap*C+co][ci] partial of dW (LC_PART_DB floats) and four bias rows
+// (one per builder warp) to slot blockIdx.x; lastconv_grad_reduce adds the slots to dw / db in CTA order.
+constexpr int LC_PART_DB = 96 * 128;                 // float offset of the 4 x 4 bias partials inside a slot
+constexpr int LC_PART_FLOATS = LC_PART_DB + 16;      // <= the weight-gradient kernel's slot size
+float* deterministic_workspace(size_t* bytes);
+int lastconv_grad_reduce(const float* partial, int ncta, float* dw, float* db, int kreal, int C, cudaStream_t st);
 }  // namespace dfl

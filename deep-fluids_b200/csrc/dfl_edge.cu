@@ -324,8 +324,6 @@ __global__ void __launch_bounds__(128) bias_grad_reduce_kernel(const float* __re
   db[threadIdx.x] += t;
 }
 
-float* deterministic_workspace(size_t* bytes);      // dfl_wgrad_tc.cu
-
 int bias_grad(const void* d, float* db, size_t npos, cudaStream_t st) {
   const int grid = static_cast<int>(std::min<size_t>((npos + 15) / 16, static_cast<size_t>(num_sms()) * 8));
   size_t wb = 0;

@@ -72,6 +72,7 @@ struct FusedBwdParams {
   float* vel;                   // optional: G = curl(A) of the owned voxels
   double* partials;             // 2 x gridDim.x
   unsigned int* ticket;
+  float* det_partial;          // deterministic mode: per-CTA slots (LC_PART_FLOATS) instead of atomics into dw / db
   float* loss3;
   float c1, c2, w1, w2;
   double inv_n1, inv_n2;
@@ -549,9 +550,15 @@ lastconv_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmS, const __grid_
 #pragma unroll
         for (int e = 0; e < 32; ++e) {
           const int k = c0 + e;
-          if (k < KREAL) atomicAdd(p.dw + (static_cast<size_t>(k / C) * 128 + ci) * C + (k % C), __uint_as_float(rr[e]));
+          if (k < KREAL) {
+            if (p.det_partial) p.det_partial[static_cast<size_t>(blockIdx.x) * LC_PART_FLOATS + k * 128 + ci] = __uint_as_float(rr[e]);
+            else atomicAdd(p.dw + (static_cast<size_t>(k / C) * 128 + ci) * C + (k % C), __uint_as_float(rr[e]));
+          }
         }
       }
+    } else if (p.det_partial) {
+      // a CTA without tiles (fewer (column, plane) units than CTAs) still owns a slot of the ordered reduction
+      for (int k = 0; k < KREAL; ++k) p.det_partial[static_cast<size_t>(blockIdx.x) * LC_PART_FLOATS + k * 128 + row] = 0.f;
     }
   } else if (warp < FB_ST_WARP0) {
     // ================================ im2col builders (warps 6..9) ================================
@@ -651,7 +658,8 @@ lastconv_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmS, const __grid_
 #pragma unroll
     for (int c = 0; c < C; ++c) {
       const float t = warp_sum(bsum[c]);
-      if (lane == 0 && my_tiles > 0) atomicAdd(p.db + c, t);
+      if (lane == 0 && p.det_partial) p.det_partial[static_cast<size_t>(blockIdx.x) * LC_PART_FLOATS + LC_PART_DB + (warp - 6) * 4 + c] = t;
+      else if (lane == 0 && my_tiles > 0) atomicAdd(p.db + c, t);
     }
   } else {
     // ================================ stencil warps (10..15) ================================
@@ -849,8 +857,13 @@ int lastconv_curl_loss_bwd(const void* s, const float* pot, const float* x, cons
   }
   const long long total = static_cast<long long>(p.ncols) * p.D;
   const int grid = static_cast<int>(std::min<long long>(total, std::min(num_sms(), 160)));
+  size_t wb = 0;
+  p.det_partial = deterministic_workspace(&wb);
+  DFL_REQUIRE(!p.det_partial || static_cast<size_t>(grid) * LC_PART_FLOATS * sizeof(float) <= wb,
+              "lastconv_curl_loss_bwd: deterministic workspace too small");
   lastconv_bwd_fused_kernel<<<grid, FB_THREADS, FB_SMEM, st>>>(tmS, p);
   DFL_LAUNCH_OK("lastconv_bwd_fused_kernel");
+  if (p.det_partial) return lastconv_grad_reduce(p.det_partial, grid, p.dw, p.db, 81, 3, st);
   return DFL_OK;
 }
 

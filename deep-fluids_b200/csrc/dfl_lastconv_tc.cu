@@ -35,6 +35,7 @@ struct LastBwdParams {
   __nv_bfloat16* ds_masked;    // [B,D,H,W,128] or nullptr
   float* dw;                   // [taps][128][C] fp32, accumulated
   float* db;                   // [C] fp32, accumulated
+  float* det_partial;          // deterministic mode: per-CTA slots of LC_PART_FLOATS floats instead of atomics into dw / db
   // ---- kFuse (2D, C = 1): dOut = dL/dpsi is COMPUTED by the builder warps from the potential and the target (see below)
   const float* pot;            // [B,H,W,1] fp32 stream function psi (the forward kernel's output)
   const float* xt;             // [B,H,W,2] fp32 target velocity
@@ -288,7 +289,10 @@ lastconv_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmS, LastBwdParams p)
 #pragma unroll
         for (int e = 0; e < 32; ++e) {
           const int k = c0 + e;
-          if (k < KREAL) atomicAdd(p.dw + (static_cast<size_t>(k / C) * 128 + ci) * C + (k % C), __uint_as_float(rr[e]));
+          if (k < KREAL) {
+            if (p.det_partial) p.det_partial[static_cast<size_t>(blockIdx.x) * LC_PART_FLOATS + k * 128 + ci] = __uint_as_float(rr[e]);
+            else atomicAdd(p.dw + (static_cast<size_t>(k / C) * 128 + ci) * C + (k % C), __uint_as_float(rr[e]));
+          }
         }
       }
     }
@@ -441,7 +445,10 @@ lastconv_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmS, LastBwdParams p)
 #pragma unroll
     for (int c = 0; c < C; ++c) {
       const float t = warp_sum(bsum[c]);
-      if (lane == 0 && my_tiles > 0) atomicAdd(p.db + c, t);
+      if (lane == 0 && my_tiles > 0) {
+        if (p.det_partial) p.det_partial[static_cast<size_t>(blockIdx.x) * LC_PART_FLOATS + LC_PART_DB + (warp - 6) * 4 + c] = t;
+        else atomicAdd(p.db + c, t);
+      }
     }
     if constexpr (kFuse) {
       // loss: one fp64 pair per CTA; the last CTA (atomic ticket) adds all pairs in CTA order -> deterministic, no finalize
@@ -491,8 +498,35 @@ static int lastconv_bwd_launch_t(const CUtensorMap& tmS, const LastBwdParams& p,
     attr_set = true;
   }
   const int grid = std::min(p.ntiles, num_sms());
-  lastconv_bwd_tc_kernel<C, k3D, kFuse><<<grid, LB_THREADS, LB_SMEM, st>>>(tmS, p);
+  LastBwdParams q = p;
+  size_t wb = 0;
+  q.det_partial = deterministic_workspace(&wb);
+  DFL_REQUIRE(!q.det_partial || static_cast<size_t>(grid) * LC_PART_FLOATS * sizeof(float) <= wb,
+              "lastconv_bwd: deterministic workspace too small");
+  lastconv_bwd_tc_kernel<C, k3D, kFuse><<<grid, LB_THREADS, LB_SMEM, st>>>(tmS, q);
   DFL_LAUNCH_OK(kFuse ? "lastconv_bwd_tc_kernel (fused 2D loss)" : "lastconv_bwd_tc_kernel");
+  if (q.det_partial) return lastconv_grad_reduce(q.det_partial, grid, q.dw, q.db, (k3D ? 27 : 9) * C, C, st);
+  return DFL_OK;
+}
+
+// deterministic mode, second pass for both output-conv backward kernels: dw / db += the CTA slots in CTA order
+__global__ void __launch_bounds__(128) lastconv_grad_reduce_kernel(const float* __restrict__ partial, int ncta, float* __restrict__ dw,
+                                                                   float* __restrict__ db, int kreal, int C) {
+  const int k = blockIdx.x, ci = threadIdx.x;
+  if (k < kreal) {
+    float a = 0.f;
+    for (int c = 0; c < ncta; ++c) a += partial[static_cast<size_t>(c) * LC_PART_FLOATS + k * 128 + ci];
+    dw[(static_cast<size_t>(k / C) * 128 + ci) * C + (k % C)] += a;
+  } else if (ci < C) {
+    float a = 0.f;
+    for (int c = 0; c < ncta; ++c)
+      for (int w = 0; w < 4; ++w) a += partial[static_cast<size_t>(c) * LC_PART_FLOATS + LC_PART_DB + w * 4 + ci];
+    db[ci] += a;
+  }
+}
+int lastconv_grad_reduce(const float* partial, int ncta, float* dw, float* db, int kreal, int C, cudaStream_t st) {
+  lastconv_grad_reduce_kernel<<<kreal + 1, 128, 0, st>>>(partial, ncta, dw, db, kreal, C);
+  DFL_LAUNCH_OK("lastconv_grad_reduce_kernel");
   return DFL_OK;
 }
 

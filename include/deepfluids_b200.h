@@ -195,12 +195,14 @@ int dfl_phase_wgrad(const void* dy_fine, const void* s_coarse, float* t_scratch,
 int dfl_phase_wgrad_fold(const float* t_scratch, float* dw, int ndim, int cin, int cout, void* stream);
 /* Deterministic weight / bias gradients (new; TF's own GPU kernels for Conv*BackpropFilter are not bitwise reproducible
  * either).  By default the split-K partial sums of dfl_conv3x3_wgrad / dfl_conv_wgrad_ex / dfl_phase_wgrad / dfl_bias_grad
- * meet in dw / db through fp32 red.global.add, whose order varies from run to run.  After
+ * meet in dw / db through fp32 red.global.add / atomicAdd, whose order varies from run to run.  After
  * dfl_set_deterministic(workspace, bytes) with a caller-owned device buffer of dfl_deterministic_workspace_bytes() bytes,
  * every CTA stores its partial accumulators to its own slot of the workspace and a second, stream-ordered launch adds them
  * to dw / db in slab order: two runs on the same inputs then give bit-identical gradients.  The launches that use the
  * workspace must not overlap each other (one stream).  dfl_set_deterministic(NULL, 0) restores the atomic reduction.
- * Still order-dependent in this library: the 128 -> 1..3 output conv's dW / db (dfl_lastconv_bwd*, fp32 atomics over CTAs). */
+ * The 128 -> 1..3 output conv's dW / db (dfl_lastconv_bwd, dfl_lastconv_curl_loss_bwd) follow the same switch (per-CTA
+ * slots, added in CTA order), so a whole generator train step is reproducible.  Still order-dependent: the split-K fp32
+ * atomics of dfl_enc_fc_fwd (auto-encoder) and of dfl_gemm_f32. */
 size_t dfl_deterministic_workspace_bytes(void);
 int dfl_set_deterministic(void* workspace, size_t bytes);
 /* coarse[b,(z,)y,x,:] = fine[b,(2z,)2y,2x,:] (bf16, 128 channels): the coarse source s of an up-sampled tensor upscale(s) */
