@@ -72,6 +72,8 @@ SIGNATURES = {
     "dfl_dropout": (_i, [_vp, _vp, _sz, _f, C.c_uint64, C.c_uint64, _vp]),
     "dfl_gather_stride2": (_i, [_vp, _vp, _dims, _i, _vp]),
     "dfl_phase_wgrad_fold": (_i, [_vp, _vp, _i, _i, _i, _vp]),
+    "dfl_upscale2": (_i, [_vp, _vp, _dims, _i, _i, _i, _vp]),
+    "dfl_pool2": (_i, [_vp, _vp, _dims, _i, _i, _i, _vp]),
     "dfl_deterministic_workspace_bytes": (C.c_size_t, []),
     "dfl_set_deterministic": (_i, [_vp, C.c_size_t]),
     "dfl_pool_mask_add": (_i, [_vp, _vp, _vp, _vp, _vp, _dims, _i, _vp]),

@@ -132,6 +132,8 @@ int pack_conv_weights_multi(const void* ptrs, int n_layers, int taps, int cin, i
 int adam_step(float* p, const float* g, float* m, float* v, size_t n, float lr_t, const float* lr_t_dev, float b1,
               float b2, float eps, float grad_scale, cudaStream_t st);
 int cast_f32_bf16(const float* a, void* o, size_t n, cudaStream_t st);
+int upscale2(const void* in, void* out, const int64_t* cdims, int nd, int channels, int dtype, cudaStream_t st);
+int pool2(const void* g, void* out, const int64_t* cdims, int nd, int channels, int dtype, cudaStream_t st);
 
 }  // namespace dfl
 
@@ -362,6 +364,12 @@ int dfl_adam_step_dev(float* param, const float* grad, float* m, float* v, size_
                       float beta2, float eps, float grad_scale, void* stream) {
   DFL_REQUIRE(lr_t_dev != nullptr, "adam_step_dev: lr_t_dev is NULL");
   return adam_step(param, grad, m, v, n, 0.f, lr_t_dev, beta1, beta2, eps, grad_scale, ST(stream));
+}
+int dfl_upscale2(const void* in, void* out, const int64_t* cdims, int ndim, int channels, int dtype, void* stream) {
+  return upscale2(in, out, cdims, ndim, channels, dtype, ST(stream));
+}
+int dfl_pool2(const void* g, void* out, const int64_t* cdims, int ndim, int channels, int dtype, void* stream) {
+  return pool2(g, out, cdims, ndim, channels, dtype, ST(stream));
 }
 int dfl_cast_f32_bf16(const float* in, void* out, size_t n, void* stream) {
   return cast_f32_bf16(in, out, n, ST(stream));

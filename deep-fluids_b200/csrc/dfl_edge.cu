@@ -851,4 +851,76 @@ int pool_mask_split(const void* g, const void* mask_src, void* ds, void* dmasked
   return DFL_OK;
 }
 
+
+// =============================================================================================
+// upscale2 / pool2: nearest x2 up-sampling of a channels-last tensor (ops.py:66-91: out[2i+a] = in[i]) and its adjoint (sum of
+// the 2^nd children), for the ops-level API (any channel count, bf16 or fp32).  In the fused engines the up-sampling is the
+// conv epilogue's replicated store and the adjoint is pool_mask; these two serve `ops.upscale(3)` as standalone layers.
+// =============================================================================================
+template <typename U>
+__global__ void upscale2_kernel(const U* __restrict__ in, U* __restrict__ out, int B, int D, int H, int W, int units, int nd) {
+  // one thread per (fine voxel, unit); units = bytes per voxel / sizeof(U)
+  const int zr = nd == 3 ? 2 : 1;
+  const size_t n = static_cast<size_t>(B) * (D * zr) * (H * 2) * (W * 2) * units;
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n; i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    size_t r = i;
+    const int u = r % units; r /= units;
+    const int x = r % (W * 2); r /= (W * 2);
+    const int y = r % (H * 2); r /= (H * 2);
+    const int z = r % (D * zr); r /= (D * zr);
+    const size_t src = (((r * D + z / zr) * H + (y >> 1)) * W + (x >> 1)) * units + u;
+    out[i] = in[src];
+  }
+}
+template <typename T>
+__global__ void pool2_kernel(const T* __restrict__ g, T* __restrict__ out, int B, int D, int H, int W, int C, int nd) {
+  // one thread per (coarse voxel, channel): fp32 sum of the children in a fixed order
+  const int zr = nd == 3 ? 2 : 1;
+  const size_t n = static_cast<size_t>(B) * D * H * W * C;
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n; i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    size_t r = i;
+    const int c = r % C; r /= C;
+    const int x = r % W; r /= W;
+    const int y = r % H; r /= H;
+    const int z = r % D; r /= D;
+    float a = 0.f;
+    for (int dz = 0; dz < zr; ++dz)
+      for (int dy = 0; dy < 2; ++dy)
+        for (int dx = 0; dx < 2; ++dx)
+          a += ldf(g + ((((r * (D * zr) + z * zr + dz) * (H * 2) + 2 * y + dy) * (W * 2)) + 2 * x + dx) * C + c);
+    stf(out + i, a);
+  }
+}
+int upscale2(const void* in, void* out, const int64_t* cdims, int nd, int channels, int dtype, cudaStream_t st) {
+  DFL_REQUIRE(in && out && (nd == 2 || nd == 3) && channels > 0, "upscale2: null tensor, ndim not 2 / 3 or no channels");
+  DFL_REQUIRE(dtype == DFL_F32 || dtype == DFL_BF16, "upscale2: dtype must be DFL_F32 or DFL_BF16");
+  const int B = static_cast<int>(cdims[0]), D = nd == 3 ? static_cast<int>(cdims[1]) : 1, H = static_cast<int>(cdims[nd - 1]),
+            W = static_cast<int>(cdims[nd]);
+  const size_t vb = static_cast<size_t>(channels) * (dtype == DFL_F32 ? 4 : 2);
+  const size_t nvox = static_cast<size_t>(B) * D * H * W * (nd == 3 ? 8 : 4);
+  if (nvox == 0) return DFL_OK;
+  const bool a16 = vb % 16 == 0 && (reinterpret_cast<uintptr_t>(in) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0;
+  const int unit = a16 ? 16 : (vb % 4 == 0 ? 4 : 2);
+  const int units = static_cast<int>(vb / unit);
+  const int grid = static_cast<int>(std::min<size_t>((nvox * units + 255) / 256, static_cast<size_t>(num_sms()) * 16));
+  if (unit == 16) upscale2_kernel<uint4><<<grid, 256, 0, st>>>(static_cast<const uint4*>(in), static_cast<uint4*>(out), B, D, H, W, units, nd);
+  else if (unit == 4) upscale2_kernel<uint32_t><<<grid, 256, 0, st>>>(static_cast<const uint32_t*>(in), static_cast<uint32_t*>(out), B, D, H, W, units, nd);
+  else upscale2_kernel<uint16_t><<<grid, 256, 0, st>>>(static_cast<const uint16_t*>(in), static_cast<uint16_t*>(out), B, D, H, W, units, nd);
+  DFL_LAUNCH_OK("upscale2_kernel");
+  return DFL_OK;
+}
+int pool2(const void* g, void* out, const int64_t* cdims, int nd, int channels, int dtype, cudaStream_t st) {
+  DFL_REQUIRE(g && out && (nd == 2 || nd == 3) && channels > 0, "pool2: null tensor, ndim not 2 / 3 or no channels");
+  DFL_REQUIRE(dtype == DFL_F32 || dtype == DFL_BF16, "pool2: dtype must be DFL_F32 or DFL_BF16");
+  const int B = static_cast<int>(cdims[0]), D = nd == 3 ? static_cast<int>(cdims[1]) : 1, H = static_cast<int>(cdims[nd - 1]),
+            W = static_cast<int>(cdims[nd]);
+  const size_t n = static_cast<size_t>(B) * D * H * W * channels;
+  if (n == 0) return DFL_OK;
+  const int grid = static_cast<int>(std::min<size_t>((n + 255) / 256, static_cast<size_t>(num_sms()) * 16));
+  if (dtype == DFL_F32) pool2_kernel<float><<<grid, 256, 0, st>>>(static_cast<const float*>(g), static_cast<float*>(out), B, D, H, W, channels, nd);
+  else pool2_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(g), static_cast<__nv_bfloat16*>(out), B, D, H, W, channels, nd);
+  DFL_LAUNCH_OK("pool2_kernel");
+  return DFL_OK;
+}
+
 }  // namespace dfl

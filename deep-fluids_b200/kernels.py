@@ -544,6 +544,23 @@ def lastconv_curl_loss_bwd(s, pot, x, w, mask_src, ds, ds_masked, dw, db, loss3,
         _p(workspace), d, nd, float(w1), float(w2), float(grad_scale), _st())))
 
 
+def upscale2(x):
+    """nearest x2 of a channels-last tensor [B,(D,)H,W,C] (fp32 / bf16)"""
+    d, nd = _spatial(x)
+    out = torch.empty((x.shape[0],) + tuple(2 * int(e) for e in x.shape[1:-1]) + (x.shape[-1],), dtype=x.dtype, device=x.device)
+    PROF.timed("upscale2", 0.0, lambda: check(cabi.lib().dfl_upscale2(_p(x), _p(out), d, nd, x.shape[-1], _dt(x), _st())))
+    return out
+
+
+def pool2(g):
+    """adjoint of upscale2: sum of the 2^nd children"""
+    nd = g.dim() - 2
+    out = torch.empty((g.shape[0],) + tuple(int(e) // 2 for e in g.shape[1:-1]) + (g.shape[-1],), dtype=g.dtype, device=g.device)
+    d, _ = _spatial(out)
+    PROF.timed("pool2", 0.0, lambda: check(cabi.lib().dfl_pool2(_p(g), _p(out), d, nd, g.shape[-1], _dt(g), _st())))
+    return out
+
+
 def pool_mask(g, mask_src, ds, dmasked, addend=None):
     """g: fine-grid gradient [B,(2D,)2H,2W,128]; ds / dmasked: coarse [B,(D,)H,W,128]; addend: optional coarse term"""
     ref = ds if ds is not None else dmasked

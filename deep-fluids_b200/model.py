@@ -12,6 +12,7 @@ import torch
 
 from .engine import GeneratorEngine
 from .ops import batch_norm, conv2d, conv3d, elu, get_variables, linear, lrelu, upscale, upscale3, variable_scope
+from .ops import add as ops_add
 from .ops import dropout as ops_dropout
 
 _ENGINES = {}
@@ -51,10 +52,10 @@ def generator_ops(z, filters, output_shape, name='G', num_conv=4, conv_k=3, last
                     x, x0 = up(x), up(x0)
                     x = torch.cat([x, x0.to(x.dtype)], dim=-1)
                 else:                                    # model.py:35-37 / :77-79
-                    x = up(x + x0.to(x.dtype))
+                    x = up(ops_add(x, x0.to(x.dtype)))
                     x0 = x
             elif not skip_concat:
-                x = x + x0.to(x.dtype)
+                x = ops_add(x, x0.to(x.dtype))
         out = conv(x, output_shape[-1], k=last_k, s=1, name='%d_conv' % n)
     return out, get_variables(vs)
 

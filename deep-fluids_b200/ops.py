@@ -216,17 +216,54 @@ def batch_norm(x, train, data_format='NHWC', name=None, act=lrelu, epsilon=1e-5,
     return _BnActFn.apply(x, gamma, beta, mmean.data, mvar.data, float(epsilon), float(momentum), bool(train), code)
 
 
+class _UpscaleFn(torch.autograd.Function):
+    """nearest x2 (dfl_upscale2) and its adjoint (dfl_pool2)"""
+
+    @staticmethod
+    def forward(ctx, x):
+        return K.upscale2(x.contiguous())
+
+    @staticmethod
+    def backward(ctx, g):
+        return K.pool2(g.contiguous())
+
+
+class _AddFn(torch.autograd.Function):
+    """residual add of two bf16 activations (dfl_add_mask without a mask)"""
+
+    @staticmethod
+    def forward(ctx, a, b):
+        out = torch.empty_like(a)
+        K.add_mask(a.contiguous(), b.contiguous(), None, out)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        return g, g
+
+
+def add(a, b):
+    """x + x0 of the residual blocks (model.py:35,77) on the library when both are bf16 activations"""
+    if a.dtype == torch.bfloat16 and b.dtype == torch.bfloat16 and a.shape == b.shape and a.numel() % 8 == 0 and a.is_cuda:
+        return _AddFn.apply(a, b)
+    return a + b
+
+
 def upscale(x, scale, data_format='NHWC'):
     """nearest x2 (ops.py:75-77); standalone only -- in the generator it is the conv epilogue's replicated store"""
     if data_format != 'NHWC' or scale != 2:
         raise NotImplementedError("upscale: NHWC, scale 2 only")
-    return x.repeat_interleave(2, dim=1).repeat_interleave(2, dim=2)
+    if x.dim() != 4:
+        raise ValueError("upscale expects [B,H,W,C]")
+    return _UpscaleFn.apply(x)
 
 
 def upscale3(x, scale):
     if scale != 2:
         raise NotImplementedError("upscale3: scale 2 only")
-    return x.repeat_interleave(2, dim=1).repeat_interleave(2, dim=2).repeat_interleave(2, dim=3)
+    if x.dim() != 5:
+        raise ValueError("upscale3 expects [B,D,H,W,C]")
+    return _UpscaleFn.apply(x)
 
 
 # ------------------------------------------------------------------ layers

@@ -241,6 +241,11 @@ int dfl_conv_wgrad_ex(const void* x, const void* dpre, float* dw, float* db, con
                       int ndim, int in_stride, int pad, int dw_tap_stride, int dw_row_stride, void* stream);
 /* fp32 [n][cin] -> bf16 [n][128] with zero padding (encoder input) */
 int dfl_pad_cast(const float* in, void* out, size_t n, int cin, void* stream);
+/* ops.upscale / ops.upscale3 (ops.py:66-91) as standalone layers: out[b,(2z+c,)2y+a,2x+e,:] = in[b,(z,)y,x,:] and the adjoint
+ * out[b,(z,)y,x,:] = sum of the 2^ndim children of g.  cdims = COARSE {B,(D,)H,W}; any channel count; DFL_F32 or DFL_BF16.
+ * (Inside the fused engines the up-sampling is the conv epilogue's replicated store and the adjoint is dfl_pool_mask.) */
+int dfl_upscale2(const void* in, void* out, const int64_t* cdims, int ndim, int channels, int dtype, void* stream);
+int dfl_pool2(const void* g, void* out, const int64_t* cdims, int ndim, int channels, int dtype, void* stream);
 /* out = (a + b) * lrelu'(y);  b, y may be NULL;  bf16, n % 8 == 0 */
 int dfl_add_mask(const void* a, const void* b, const void* y, void* out, size_t n, void* stream);
 /* encoder FC (model.py:149,185) on the channel-blocked concat tensor [nblk][B][V][128]: z = flat W + bias (Z<=16,B<=8)*/

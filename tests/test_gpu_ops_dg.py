@@ -435,3 +435,26 @@ def test_test_ae_latent_dump_and_decode(tmp_path):
     assert len(outs) == sims
     v = np.load(outs[1])
     assert v["v"].shape == (2, H, W, 2) and v["v_gt"].shape == (2, H, W, 2) and np.isfinite(v["v"]).all()
+
+
+@pytest.mark.parametrize("shape,dtype", [((2, 5, 7, 3), torch.float32), ((1, 4, 6, 64), torch.bfloat16), ((2, 3, 4, 5, 3), torch.float32),
+                                         ((1, 2, 3, 4, 128), torch.bfloat16), ((1, 3, 3, 1), torch.float32), ((1, 2, 2, 2, 7), torch.bfloat16)])
+def test_ops_upscale_forward_and_adjoint_vs_oracle(shape, dtype):
+    """ops.upscale / ops.upscale3 (ops.py:66-91) as standalone differentiable layers on dfl_upscale2 / dfl_pool2: bit-exact
+    copies forward; the adjoint = sum of the children, vs torch autograd through the oracle's (reference-pinned) upscale"""
+    from deepfluids_b200 import ops as O
+    g = torch.Generator().manual_seed(sum(shape))
+    x = torch.randn(*shape, generator=g).to(dtype)
+    nd = len(shape) - 2
+    ref_up = R.upscale3 if nd == 3 else R.upscale
+    xd = x.to(dev()).requires_grad_(True)
+    y = O.upscale3(xd, 2) if nd == 3 else O.upscale(xd, 2)
+    assert y.dtype == dtype and torch.equal(y.detach().cpu(), ref_up(x, 2))
+    dy = torch.randn(*y.shape, generator=g).to(dtype)
+    (gx,) = torch.autograd.grad(y, xd, dy.to(dev()))
+    xr = x.float().requires_grad_(True)
+    (gr,) = torch.autograd.grad(ref_up(xr, 2), xr, dy.float())
+    tol = 1e-6 if dtype == torch.float32 else 8e-3          # bf16: one rounding of the fp32 sum of 4 / 8 children
+    assert float((gx.float().cpu() - gr).abs().max()) <= tol * float(gr.abs().max())
+    with pytest.raises(NotImplementedError):
+        O.upscale(xd, 3) if nd == 2 else O.upscale3(xd, 3)
