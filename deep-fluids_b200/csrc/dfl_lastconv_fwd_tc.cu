@@ -13,22 +13,33 @@
 // registers of the thread that owns the output voxel.
 //   smem:  3 stages x [2 x 64-channel halves][184 rows x 128 B] (TMA, 128B swizzle = K-major A operand),
 //          W' bf16 [2 halves][NP rows (k)][128 B] (K-major B operand, built once per CTA from the fp32 TF weights),
-//          P fp32 [k][192 rows]  (k-major: both the row-wise writes and the shifted row-wise reads are conflict-free)
+//          P fp32: a ring of 2 chunks of [32 k][192 rows]  (k-major: both the row-wise writes and the shifted row-wise reads
+//          are conflict-free)
 //   TMEM:  2 buffers x 2 M-tiles (rows 0..127, 128..255 of the stage) x 128 columns
-//   warps: 0 = TMA producer, 1 = TMEM alloc + MMA issuer, 4..7 = TMEM -> P (M-tile 0) + shift-sum + store,
-//          8..9 = TMEM -> P (rows 128..179 of M-tile 1)
+//   warps: 0 = TMA producer, 1 = TMEM alloc + MMA issuer, 4..7 = TMEM -> P (M-tile 0), 8..9 = TMEM -> P (rows 128..179 of
+//          M-tile 1), 10..13 = shift-sum + store (one thread per output voxel).
+//   The copy warps and the gather warps are a producer / consumer pair over the chunk ring (named barriers FULL[slot]:
+//   copy arrives, gather syncs; EMPTY[slot]: gather arrives, copy syncs): the 32-column chunks of plane i+1 are copied while
+//   plane i is still being summed.  (Round 1's version ran copy -> barrier -> gather -> barrier on ONE P image with four of the
+//   six warps doing both jobs: ~3000 clocks per plane against ~810 clocks of shared-memory instructions and an HBM floor of
+//   ~1500.  Measured at 4 x 128^3 inside the step: 0.88 ms -> 0.77 ms with 2 input stages + 3 chunks -> 0.74 ms with 3 input
+//   stages + 2 chunks (two stages = 92 KB in flight per SM were TMA-latency-bound).)
 #include "dfl_common.cuh"
 
 namespace dfl {
 
-constexpr int LF_THREADS = 320;
-constexpr int LF_NST = 3;                  // input stages (TMA latency ~ 2 plane times)
+constexpr int LF_THREADS = 448;
+constexpr int LF_NST = 3;                  // input stages (two were latency-bound: 92 KB in flight per SM)
 constexpr int LF_ROWS = 180;               // 10 x 18 halo'd rows per plane tile
 constexpr int LF_HALF = 23552;             // 184 rows x 128 B: one 64-channel half of a stage (1024-aligned)
 constexpr int LF_STAGE = 2 * LF_HALF;
 constexpr int LF_TX = 2 * LF_ROWS * 128;   // bytes landed per stage fill
 constexpr int LF_PR = 192;                 // row pitch of P in floats (multiple of 32: bank = row & 31)
-constexpr int LF_EPI = 192;                // epilogue threads (warps 4..9)
+constexpr int LF_EPI = 192;                // copy threads (warps 4..9)
+constexpr int LF_GATHER = 128;             // gather threads (warps 10..13)
+constexpr int LF_RING = 2;                 // P chunk ring (3 input stages + 2 chunks = 217 KB)
+constexpr int LF_CHUNK_F = 32 * LF_PR;     // floats per chunk: 32 k-columns x 192 rows
+constexpr int LF_BAR_FULL = 1, LF_BAR_EMPTY = 4;   // named barrier ids 1..3 / 4..6
 
 struct LastFwdParams {
   int B, D, H, W;
@@ -44,7 +55,8 @@ struct LFCfg {
   static constexpr int KREAL = NT * C;                     // <= 81
   static constexpr int NP = ((KREAL + 15) / 16) * 16;      // MMA N
   static constexpr int W_HALF = NP * 128;                  // bytes per 64-channel half of W'
-  static constexpr int SMEM = LF_NST * LF_STAGE + 2 * W_HALF + KREAL * LF_PR * 4 + 1024 /*ctrl*/ + 1024 /*align*/;
+  static constexpr int NCH = (KREAL + 31) / 32;            // 32-column chunks of P per plane (3D, C = 3: 3)
+  static constexpr int SMEM = LF_NST * LF_STAGE + 2 * W_HALF + LF_RING * LF_CHUNK_F * 4 + 1024 /*ctrl*/ + 1024 /*align*/;
 };
 
 struct LFSeg { int col, zs, ze; };
@@ -57,10 +69,26 @@ __device__ __forceinline__ bool lf_next(long long& u, long long u_end, int D, LF
   u += s.ze - s.zs;
   return true;
 }
-// (warp-aligned instruction reached after lane-divergent code: reconverge explicitly, see dfl_lastconv_bwd_fused.cu)
-__device__ __forceinline__ void lf_bar(int id) {
+// (warp-aligned instructions reached after lane-divergent code: reconverge explicitly, see dfl_lastconv_bwd_fused.cu; every
+// bar.sync site below is reached by ONE role only, the other side arrives -- the form compute-sanitizer's synccheck accepts)
+__device__ __forceinline__ void lf_bar_sync(int id) {
   __syncwarp();
-  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(LF_EPI) : "memory");
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(LF_EPI + LF_GATHER) : "memory");
+}
+__device__ __forceinline__ void lf_bar_arrive(int id) {
+  __syncwarp();
+  asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(LF_EPI + LF_GATHER) : "memory");
+}
+// number of input planes this CTA's share touches (the same walk as every role's loop)
+__device__ __forceinline__ int lf_count_planes(long long u0, long long u1, int D, bool k3D) {
+  int n = 0;
+  long long u = u0;
+  LFSeg sg;
+  while (lf_next(u, u1, D, sg)) {
+    const int zlo = k3D ? sg.zs - 1 : sg.zs, zhi = k3D ? sg.ze : sg.ze - 1;
+    n += min(zhi, D - 1) - max(zlo, 0) + 1;
+  }
+  return n;
 }
 
 template <int C, bool k3D>
@@ -72,8 +100,9 @@ lastconv_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmS, LastFwdParams p)
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sW = smem + LF_NST * LF_STAGE;
+  constexpr int NCH = Cfg::NCH;
   float* sP = reinterpret_cast<float*>(sW + 2 * W_HALF);
-  uint8_t* ctrl = reinterpret_cast<uint8_t*>(sP) + KREAL * LF_PR * 4;
+  uint8_t* ctrl = reinterpret_cast<uint8_t*>(sP) + LF_RING * LF_CHUNK_F * 4;
   uint64_t* full = reinterpret_cast<uint64_t*>(ctrl);
   uint64_t* empty = full + LF_NST;
   uint64_t* d_full = empty + LF_NST;
@@ -173,18 +202,44 @@ lastconv_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmS, LastFwdParams p)
         }
       }
     }
-  } else if (warp >= 4) {
-    // ================================ epilogue: TMEM -> P (smem) -> shift-sum -> out ================================
+  } else if (warp >= 4 && warp < 10) {
+    // ================================ copy warps: TMEM -> P chunk ring ================================
     const int mt = (warp - 4) >> 2;                   // M-tile this warp drains: warps 4..7 -> 0, warps 8,9 -> 1
     const int quarter = warp & 3;                     // TMEM lane quarter a warp may access = warp id % 4
     const int prow = mt * 128 + quarter * 32 + lane;  // row of the halo'd plane tile (10 x 18)
-    const bool gather = (mt == 0);
-    const int ot = quarter * 32 + lane, lx = ot & 15, ly = ot >> 4;      // output voxel of a gather thread
+    const int nplanes = lf_count_planes(u0, u1, p.D, k3D);
+    for (int it = 0; it < nplanes; ++it) {
+      const uint32_t bb = it & 1, bph = (it >> 1) & 1;
+      mbar_wait(&d_full[bb], bph);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + bb * 256 + mt * 128;
+#pragma unroll
+      for (int q = 0; q < NCH; ++q) {
+        const int cc = it * NCH + q, slot = cc % LF_RING;          // chunk counter, ring slot
+        uint32_t rr[32];
+        tmem_ld_32x32(taddr + q * 32, rr);                        // columns >= NP are never written: ignored
+        if (cc >= LF_RING) lf_bar_sync(LF_BAR_EMPTY + slot);      // the gather warps are done with this slot
+        tmem_ld_wait();
+        if (prow < LF_ROWS) {
+          float* dst = sP + slot * LF_CHUNK_F + prow;
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (q * 32 + j < KREAL) dst[j * LF_PR] = __uint_as_float(rr[j]);
+        }
+        lf_bar_arrive(LF_BAR_FULL + slot);
+      }
+      tc_fence_before();
+      mbar_arrive(&d_empty[bb]);                      // the tensor core may overwrite this TMEM buffer
+    }
+  } else if (warp >= 10) {
+    // ================================ gather warps: shift-sum over the chunk ring -> out ================================
+    const int ot = (warp - 10) * 32 + lane, lx = ot & 15, ly = ot >> 4;      // output voxel of this thread
     const float* gp = sP + ly * 18 + lx;
+    const int total_chunks = lf_count_planes(u0, u1, p.D, k3D) * NCH;
     float bias[C];
 #pragma unroll
     for (int c = 0; c < C; ++c) bias[c] = p.bias ? __ldg(p.bias + c) : 0.f;
-    uint32_t it = 0;
+    int cc = 0;                                       // chunk counter (same sequence as the copy warps')
     long long u = u0;
     LFSeg sg;
     while (lf_next(u, u1, p.D, sg)) {
@@ -192,7 +247,7 @@ lastconv_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmS, LastFwdParams p)
       const int x = (r % p.tx) * 16 + lx; r /= p.tx;
       const int y = (r % p.ty) * 8 + ly;
       const int b = r / p.ty;
-      const bool valid = gather && (x < p.W) && (y < p.H);
+      const bool valid = (x < p.W) && (y < p.H);
       float* obase = p.out + ((static_cast<size_t>(b) * p.D * p.H + (valid ? y : 0)) * p.W + (valid ? x : 0)) * C;
       const size_t plane = static_cast<size_t>(p.H) * p.W * C;
       float a0[C], a1[C];                             // partial sums of out[zi-1] and out[zi]
@@ -206,37 +261,22 @@ lastconv_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmS, LastFwdParams p)
 #pragma unroll
           for (int c = 0; c < C; ++c) ps[dz][c] = 0.f;
         if (zi >= 0 && zi < p.D) {
-          const uint32_t bb = it & 1, bph = (it >> 1) & 1;
-          mbar_wait(&d_full[bb], bph);
-          tc_fence_after();
-          const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + bb * 256 + mt * 128;
 #pragma unroll
-          for (int c0 = 0; c0 < NP; c0 += 32) {
-            uint32_t rr[32];
-            tmem_ld_32x32(taddr + c0, rr);            // columns >= NP are never written: ignored
-            tmem_ld_wait();
-            if (prow < LF_ROWS) {
+          for (int q = 0; q < NCH; ++q, ++cc) {
+            const int slot = cc % LF_RING;
+            lf_bar_sync(LF_BAR_FULL + slot);          // chunk q of this plane has landed
+            const float* gq = gp + slot * LF_CHUNK_F;
 #pragma unroll
-              for (int j = 0; j < 32; ++j)
-                if (c0 + j < KREAL) sP[(c0 + j) * LF_PR + prow] = __uint_as_float(rr[j]);
+            for (int j = 0; j < 32; ++j) {
+              const int k = q * 32 + j;               // k = tap * C + c, tap = (dz*3 + dy)*3 + dx   (compile-time)
+              if (k < KREAL) {
+                const int tap = k / C, c = k - tap * C;
+                const int dz = tap / 9, dy = (tap / 3) % 3, dx = tap % 3;
+                ps[dz][c] += gq[j * LF_PR + dy * 18 + dx];
+              }
             }
+            if (cc + LF_RING < total_chunks) lf_bar_arrive(LF_BAR_EMPTY + slot);   // (nobody waits for the last LF_RING)
           }
-          tc_fence_before();
-          mbar_arrive(&d_empty[bb]);                  // the tensor core may overwrite this TMEM buffer
-          lf_bar(1);                                  // P complete
-          if (gather) {
-#pragma unroll
-            for (int dz = 0; dz < NDZ; ++dz)
-#pragma unroll
-              for (int dy = 0; dy < 3; ++dy)
-#pragma unroll
-                for (int dx = 0; dx < 3; ++dx)
-#pragma unroll
-                  for (int c = 0; c < C; ++c)
-                    ps[dz][c] += gp[(((dz * 3 + dy) * 3 + dx) * C + c) * LF_PR + dy * 18 + dx];
-          }
-          lf_bar(2);                                  // P may be overwritten
-          ++it;
         }
         if (k3D) {
           // input plane zi: tap dz = 2 completes out[zi-1], dz = 1 adds to out[zi], dz = 0 opens out[zi+1]
