@@ -317,3 +317,26 @@ def test_ae_encode_decode_inference():
     direct = K.curl_fwd(tr.ae.dec.forward(z[:2].contiguous()))
     assert torch.equal(v[:2], direct)
     assert torch.equal(tr.decode(z), v)
+
+
+def test_conv_taps_paired_bricks_with_an_odd_brick_count():
+    """the per-tap kernel pairs bricks (two per schedule step share every weight tile) when a launch has >= 2 bricks per SM; an
+    odd count leaves a ghost half in the last pair.  297 bricks of 1 x 8 x 16 voxels, explicit 27-tap list, against the
+    tap-window kernel (itself checked against the oracle) on the same operands: same values up to the fp32 summation order."""
+    from deepfluids_b200 import kernels as K
+    g = torch.Generator().manual_seed(72)
+    shape = (1, 11, 72, 48)
+    x = (torch.randn(*shape, 128, generator=g) * 0.5).bfloat16().to(dev())
+    w = R.xavier_uniform_((3, 3, 3, 128, 128), g).bfloat16()
+    b = (torch.randn(128, generator=g) * 0.1).to(dev())
+    wf, _ = K.pack_conv_weights(w.float().to(dev()))
+    ref = torch.empty(*shape, 128, dtype=torch.bfloat16, device=dev())
+    K.conv3x3(x, wf, b, out=ref, flags=K.CONV_LRELU)
+    tl = [[t // 9 - 1, (t // 3) % 3 - 1, t % 3 - 1, t * 128] for t in range(27)]
+    out = torch.full(ref.shape, float("nan"), dtype=torch.bfloat16, device=dev())
+    K.conv_taps(x, wf, b, out, None, None, None, list(shape), list(shape[1:]), 128, 1, tl, 1, [0, 0, 0], flags=K.CONV_LRELU)
+    assert not torch.isnan(out.float()).any()
+    assert rel_l2(out.float(), ref.float()) <= 2e-3
+    # the last brick (the ghost's partner) and the first one, element-wise: within one bf16 ulp of each other
+    for a, r_ in ((out[0, -1, -8:, -16:].float(), ref[0, -1, -8:, -16:].float()), (out[0, 0, :8, :16].float(), ref[0, 0, :8, :16].float())):
+        assert float((a - r_).abs().max()) <= 2.0 ** -7 * float(r_.abs().max())
