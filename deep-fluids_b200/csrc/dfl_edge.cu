@@ -517,7 +517,7 @@ int add_mask(const void* a, const void* b, const void* y, void* out, size_t n, c
 constexpr int EF_MAXB = 8, EF_Z = 16;
 __global__ void __launch_bounds__(256)
 enc_fc_fwd_kernel(const __nv_bfloat16* __restrict__ flat, const float* __restrict__ W, const float* __restrict__ bias,
-                  float* __restrict__ z, int B, int V, int nblk, int Z) {
+                  float* __restrict__ z, int B, int V, int nblk, int Z, float* __restrict__ partial) {
   __shared__ float red[8][EF_MAXB * EF_Z];
   const size_t F = static_cast<size_t>(V) * nblk * 128;
   float acc[EF_MAXB][EF_Z];
@@ -556,10 +556,23 @@ enc_fc_fwd_kernel(const __nv_bfloat16* __restrict__ flat, const float* __restric
     if (b < B && j < Z) {
       float t = 0.f;
       for (int w8 = 0; w8 < 8; ++w8) t += red[w8][threadIdx.x];
-      if (blockIdx.x == 0) t += bias[j];
-      atomicAdd(z + b * Z + j, t);
+      if (partial) {                       // deterministic mode: block sums, added in block order by enc_fc_reduce_kernel
+        partial[static_cast<size_t>(blockIdx.x) * (EF_MAXB * EF_Z) + threadIdx.x] = t;
+      } else {
+        if (blockIdx.x == 0) t += bias[j];
+        atomicAdd(z + b * Z + j, t);
+      }
     }
   }
+}
+__global__ void __launch_bounds__(EF_MAXB* EF_Z)
+enc_fc_reduce_kernel(const float* __restrict__ partial, int nblocks, const float* __restrict__ bias, float* __restrict__ z, int B,
+                     int Z) {
+  const int b = threadIdx.x / EF_Z, j = threadIdx.x % EF_Z;
+  if (b >= B || j >= Z) return;
+  float t = bias[j];
+  for (int k = 0; k < nblocks; ++k) t += partial[static_cast<size_t>(k) * (EF_MAXB * EF_Z) + threadIdx.x];
+  z[b * Z + j] = t;
 }
 int enc_fc_fwd(const void* flat, const float* W, const float* bias, float* z, int B, int V, int nblk, int Z,
                cudaStream_t st) {
@@ -567,8 +580,15 @@ int enc_fc_fwd(const void* flat, const float* W, const float* bias, float* z, in
   DFL_CUDA_OK(cudaMemsetAsync(z, 0, sizeof(float) * B * Z, st));
   const size_t F = static_cast<size_t>(V) * nblk * 128;
   const int grid = static_cast<int>(std::min<size_t>((F + 255) / 256, static_cast<size_t>(num_sms()) * 4));
-  enc_fc_fwd_kernel<<<grid, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(flat), W, bias, z, B, V, nblk, Z);
+  size_t wb = 0;
+  float* ws = deterministic_workspace(&wb);
+  DFL_REQUIRE(!ws || static_cast<size_t>(grid) * EF_MAXB * EF_Z * sizeof(float) <= wb, "enc_fc_fwd: deterministic workspace too small");
+  enc_fc_fwd_kernel<<<grid, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(flat), W, bias, z, B, V, nblk, Z, ws);
   DFL_LAUNCH_OK("enc_fc_fwd_kernel");
+  if (ws) {
+    enc_fc_reduce_kernel<<<1, EF_MAXB * EF_Z, 0, st>>>(ws, grid, bias, z, B, Z);
+    DFL_LAUNCH_OK("enc_fc_reduce_kernel");
+  }
   return DFL_OK;
 }
 

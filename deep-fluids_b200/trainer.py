@@ -258,7 +258,11 @@ class Trainer(object):
         """use_curl on the fused bf16 engines, 2D and 3D: the loss stencil runs in the prologue of the output conv's backward
         kernel (DFL_FUSED_LOSS=0 restores the separate stencil launch for A/B runs)."""
         from .encoder import AEEngine
+        # 2D arch=ae: the decoder emits x's two channels and curl reads channel 0 only (ops.py:267-268) -- the fused kernel
+        # takes a one-channel stream function, so that case keeps the standalone stencil (full-shape gradient, channel 1 = 0)
+        pot_c = getattr(self.engine.dec if isinstance(self.engine, AEEngine) else self.engine, "cout", None)
         ok = (self.use_c and x.dtype == torch.float32 and (not self.is_3d or x.shape[-2] % 2 == 0)
+              and (self.is_3d or pot_c == 1)
               and (getattr(self, "_engine_cls", None) is GeneratorEngine or isinstance(self.engine, AEEngine))
               and os.environ.get("DFL_FUSED_LOSS", "1") != "0")
         if not ok:

@@ -194,3 +194,33 @@ def test_training_runs_are_bit_reproducible(monkeypatch, is_3d):
         assert finals[0][1] == finals[1][1]
     finally:
         K.set_deterministic(False)
+
+
+@pytest.mark.parametrize("is_3d", [True, False])
+def test_autoencoder_training_runs_are_bit_reproducible(monkeypatch, is_3d):
+    """arch=ae under DFL_DETERMINISTIC=1: encoder (stride-2 weight gradients over channel blocks, the split-K encoder FC),
+    decoder and the fused loss kernel -- two fresh trainers, three steps, identical parameters"""
+    from deepfluids_b200 import config as C
+    from deepfluids_b200 import kernels as K
+    from deepfluids_b200.data import BatchManager
+    from deepfluids_b200.trainer import Trainer
+    from deepfluids_b200.trainer3 import Trainer3
+    monkeypatch.setenv("DFL_DETERMINISTIC", "1")
+    args = (["--synthetic=true", "--arch=ae", "--is_3d=true", "--res_x=16", "--res_y=16", "--res_z=16", "--batch_size=2",
+             "--num_conv=2", "--max_step=20", "--lr_max=0.001"] if is_3d else
+            ["--synthetic=true", "--arch=ae", "--is_3d=false", "--res_x=32", "--res_y=48", "--batch_size=4", "--num_conv=2",
+             "--max_step=20", "--lr_max=0.001"])
+    finals = []
+    try:
+        for _ in range(2):
+            cfg, _u = C.get_config(args)
+            bm = BatchManager(cfg, pool=2)
+            tr = (Trainer3 if is_3d else Trainer)(cfg, bm)
+            assert K.deterministic()
+            for _i in range(3):
+                tr.train_step()
+            torch.cuda.synchronize()
+            finals.append(tr.engine.params.data.clone())
+        assert torch.equal(finals[0], finals[1])
+    finally:
+        K.set_deterministic(False)
