@@ -30,6 +30,13 @@
 
 namespace dfl {
 
+// Measured and NOT adopted (4 x 128^3, same box, tools/fused_ab.sh; baseline 2.05-2.13 ms): mask loads with L1::no_allocate
+// 2.34 ms; the builder warps' mask pieces staged by cp.async two rounds ahead 2.08 ms; two register sets of mask pieces per
+// store thread 2.40-2.49 ms (ptxas tracks every mask LDG of the loop on ONE scoreboard, so waiting for the older set also
+// waits for the newer); TMEM base re-read from shared memory instead of its spill reload 2.05 ms; both image reads of a
+// store pass before its first store 2.08 ms.  The long-scoreboard samples ncu shows on the store warps' mask loads are slack,
+// not the critical path.  Adopted: the stencil warps' spill-free state (below), 2.00-2.02 ms.
+
 constexpr int FB_THREADS = 512;
 constexpr int FB_ST_WARP0 = 10;
 constexpr int FB_ST_THREADS = 192;                // warps 10..15
@@ -50,7 +57,10 @@ constexpr int FB_FAM = 3 * FB_PS * 2;             // floats per family (three co
 constexpr int FB_SX0 = 5 * FB_FAM;                // float offset of the scalar Sx family
 constexpr int FB_ST_F = FB_SX0 + 3 * FB_PS;       // floats of stencil plane storage (single-buffered)
 static_assert(FB_ST_F % 2 == 0, "stencil plane storage is zeroed with float2");
-constexpr int FB_SMEM = 5 * FB_OP + FB_TR + FB_RING * FB_PLANE_F * 4 + FB_ST_F * 4 + 1024 + 1024;
+// stencil state slots: float2 [szP 3][dgP 3][(wym, c2wym)], each [FB_ST_THREADS] (conflict-free, thread-private)
+constexpr int FB_XT_SLOTS = 7, FB_XT_STRIDE = FB_ST_THREADS * 8;
+constexpr int FB_XSTATE = FB_XT_SLOTS * FB_XT_STRIDE;
+constexpr int FB_SMEM = 5 * FB_OP + FB_TR + FB_RING * FB_PLANE_F * 4 + FB_ST_F * 4 + 1024 + 1024 + FB_XSTATE;
 static_assert(FB_SMEM <= 227 * 1024, "fused backward: shared-memory plan exceeds 227 KB");
 enum { FB_FA = 0, FB_FG = 1, FB_FX = 2, FB_FS = 3, FB_FD = 4 };
 // named barriers: 0 = __syncthreads, 1 = builders, 2/3 = image READY, 4 = stencil warps, 5..8 ring FULL, 9..12 ring EMPTY,
@@ -133,10 +143,14 @@ __device__ __forceinline__ float2 fbV(const FBRaw& a) { return make_float2(a.r[0
 __device__ __forceinline__ float2 fbW(const FBRaw& a) { return make_float2(a.r[1].x, a.r[2].y); }
 __device__ __forceinline__ float2 fbC(const FBRaw& a, int c) { return c == 0 ? fbU(a) : (c == 1 ? fbV(a) : fbW(a)); }
 
+// running addresses of the stencil pipeline: plane t of this thread's voxel pair
+struct FBCur { long long eo; };          // element offset; A[t+1], x[t], G[t-1] and dA[t-4] are addressed relative to it
+
 struct FBThread {
   float wx0, wx1, wy, wym, c2wym, ysgn, xs1;
   int yo8, ycase;
   bool inD, outp, own, lastx, region;
+  uint32_t xs;         // byte address of this thread's state slot 0 (FB_XT_SLOTS float2 slots, FB_XT_STRIDE apart)
   int zs, ze;          // planes whose dL/dA this segment produces (clipped to the domain)
   int zo_s, zo_e;      // planes this CTA OWNS (loss terms, optional global outputs)
 };
@@ -166,14 +180,20 @@ constexpr uint32_t fb_fam8(int fam, int c) { return static_cast<uint32_t>((fam *
 // One z-iteration t of the pipeline for this thread's voxel pair.  sb / ssx: byte addresses of the thread's slot in the
 // (single-buffered) float2 planes / the scalar Sx planes.  Register roles as in the lean kernel (ping-pong, swapped by the
 // caller): aO = A[t-1] (receives A[t+1]), aN = A[t]; gO = G[t-2], gN <- G[t-1]; xO = x[t-2] (receives x[t]), xN = x[t-1];
-// dO = dL/dG[t-4], dN <- dL/dG[t-3].  Returns dL/dA[t-4] of the pair in (oU, oV, oW) (valid when the caller's uniform test
+// dO = dL/dG[t-4], dN <- dL/dG[t-3].  The carried state that is read once and written once per iteration -- the weighted z
+// signs szP (F_z of plane t-3 for the adjoint at t-2) and the partial gradient dgP (completed next iteration by its -1
+// neighbours) -- and the (wym, c2 wym) boundary weights live in thread-private shared-memory slots (T.xs): in registers they
+// put the stencil warps over the 128-register cap, and the spill reloads (L1 misses beside the streaming traffic) were a third of
+// these warps' time in the ncu source page.  Returns dL/dA[t-4] of the pair in (oU, oV, oW) (valid when the caller's uniform test
 // says plane t-4 is produced and T.outp).
 __device__ __forceinline__ void fb_iter(const int t, const FusedBwdParams& p, const FBThread& T, const uint32_t sb,
                                         const uint32_t ssx, FBRaw& aO, FBRaw& aN, float2 (&gO)[3], float2 (&gN)[3],
-                                        FBRaw& xO, FBRaw& xN, float2 (&dO)[3], float2 (&dN)[3], float2 (&szP)[3],
-                                        float2 (&dgP)[3], float2 (&ghzP)[2], float2& dzu, float2& dzv, float& facc_l1,
-                                        float& facc_j, const float*& pa, const float*& px, float*& pv, const int plane3,
-                                        float2& oU, float2& oV, float2& oW) {
+                                        FBRaw& xO, FBRaw& xN, float2 (&dO)[3], float2 (&dN)[3], float2 (&ghzP)[2],
+                                        float2& dzu, float2& dzv, float& facc_l1,
+                                        float& facc_j, FBCur& cur, const int plane3, float2& oU, float2& oV, float2& oW) {
+  const float* const pa = p.pot + (cur.eo + plane3);
+  const float* const px = p.xt + cur.eo;
+  float* const pv = p.vel + (cur.eo - plane3);
   const int D = p.D, zs = T.zs, ze = T.ze;
   constexpr uint32_t tpr8 = FB_TPR * 8;
   bool didG = false, didS = false, didD = false;
@@ -208,12 +228,14 @@ __device__ __forceinline__ void fb_iter(const int t, const FusedBwdParams& p, co
     {
       const int q3 = t - 3;
       if (q3 >= 0 && q3 < D && q3 >= zs - 1 && q3 <= ze) {
+        const float2 wy2 = fb_lds2(T.xs + 6 * FB_XT_STRIDE);        // (wym, c2 * wym)
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
           const float sxn = fb_lds1(ssx + c * FB_PS * 4 - 4);
           const float2 syn = fb_lds2(sb + fb_fam8(FB_FS, c) - tpr8);
-          dN[c].x = fmaf(p.c2, fmaf(T.wym, syn.x, sxn), dgP[c].x);
-          dN[c].y = fmaf(T.c2wym, syn.y, dgP[c].y);
+          const float2 dg = fb_lds2(T.xs + (3 + c) * FB_XT_STRIDE);
+          dN[c].x = fmaf(p.c2, fmaf(wy2.x, syn.x, sxn), dg.x);
+          dN[c].y = fmaf(wy2.y, syn.y, dg.y);
         }
         didD = true;
       }
@@ -244,10 +266,11 @@ __device__ __forceinline__ void fb_iter(const int t, const FusedBwdParams& p, co
           const float2 sx = fb_sg2(Fx), sy = fb_sg2(Fy), sz = fb_sg2(Fz), se = fb_sg2(e);
           const float2 szw = make_float2(wz * sz.x, wz * sz.y);
           const float wsx0 = T.wx0 * sx.x;
-          const float a0 = fmaf(-T.wy, sy.x, (szP[c].x - szw.x) - wsx0);
-          const float a1 = fmaf(-T.wy, sy.y, fmaf(-T.wx1, sx.y, (szP[c].y - szw.y) + wsx0));
-          dgP[c] = make_float2(fmaf(p.c2, a0, p.c1 * se.x), fmaf(p.c2, a1, p.c1 * se.y));
-          szP[c] = szw;
+          const float2 szp = fb_lds2(T.xs + c * FB_XT_STRIDE);
+          const float a0 = fmaf(-T.wy, sy.x, (szp.x - szw.x) - wsx0);
+          const float a1 = fmaf(-T.wy, sy.y, fmaf(-T.wx1, sx.y, (szp.y - szw.y) + wsx0));
+          fb_sts2(T.xs + (3 + c) * FB_XT_STRIDE, make_float2(fmaf(p.c2, a0, p.c1 * se.x), fmaf(p.c2, a1, p.c1 * se.y)));
+          fb_sts2(T.xs + c * FB_XT_STRIDE, szw);
           sxy[c] = sx.y;
           syv[c] = sy;
           if (zin && T.own) {
@@ -304,8 +327,7 @@ __device__ __forceinline__ void fb_iter(const int t, const FusedBwdParams& p, co
       for (int c = 0; c < 3; ++c) { fb_sts1(ssx + c * FB_PS * 4, sxy[c]); fb_sts2(sb + fb_fam8(FB_FS, c), syv[c]); }
     }
   }
-  pa += plane3; px += plane3;
-  if (pv) pv += plane3;
+  cur.eo += plane3;
   fb_bar_sync(FB_BAR_ST, FB_ST_THREADS);
 }
 
@@ -372,6 +394,7 @@ lastconv_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmS, const __grid_
   float* sRing = reinterpret_cast<float*>(sT + FB_TR);         // FB_RING dL/dA planes
   float* sSt = sRing + FB_RING * FB_PLANE_F;                   // stencil planes
   uint8_t* ctrl = reinterpret_cast<uint8_t*>(sSt + FB_ST_F);
+  uint8_t* sXt = ctrl + 1024;                                  // stencil warps' thread-private state slots (8-byte aligned)
   uint64_t* s_full = reinterpret_cast<uint64_t*>(ctrl);
   uint64_t* s_empty = s_full + 2;
   uint64_t* g_full = s_empty + 2;
@@ -670,6 +693,7 @@ lastconv_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmS, const __grid_
     const int plane3 = H * W * 3;
     const uint32_t st0 = smem_u32(sSt);
     const uint32_t slot = st0 + tid * 8, slot_sx = st0 + FB_SX0 * 4 + tid * 4;
+    const uint32_t xs0 = smem_u32(sXt) + tid * 8;
     // this thread's 6 floats of a ring plane (footprint rows 0..9 = thread rows 2..11, pairs 0..9 = thread columns 1..10)
     const bool region = act && r >= 2 && r <= FB_TR_ROWS - 3 && k >= 1 && k <= FB_PX / 2;
     const uint32_t ring_off = smem_u32(sRing) + (region ? ((r - 2) * FB_PITCH + (k - 1) * 6) * 4 : 0);
@@ -715,6 +739,10 @@ lastconv_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmS, const __grid_
       T.wy = (cy >= H - 1) ? 0.f : (cy == H - 2 ? 2.f : 1.f);
       T.wym = top ? 2.f : 1.f;
       T.c2wym = p.c2 * T.wym;
+      T.xs = xs0;
+      fb_sts2(xs0 + 6 * FB_XT_STRIDE, make_float2(T.wym, T.c2wym));
+#pragma unroll
+      for (int c = 0; c < 6; ++c) fb_sts2(xs0 + c * FB_XT_STRIDE, make_float2(0.f, 0.f));      // szP = dgP = 0
       T.ysgn = top ? -1.f : 1.f;
       T.xs1 = T.lastx ? -1.f : 1.f;
       T.yo8 = top ? -FB_TPR * 8 : FB_TPR * 8;
@@ -727,11 +755,11 @@ lastconv_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmS, const __grid_
       fb_bar_sync(FB_BAR_ST, FB_ST_THREADS);
 
       FBRaw a0, a1, xr0, xr1;
-      float2 g0[3], g1[3], d0[3], d1[3], szP[3], dgP[3], ghzP[2];
+      float2 g0[3], g1[3], d0[3], d1[3], ghzP[2];
       const float2 z2 = make_float2(0.f, 0.f);
       float2 dzu = z2, dzv = z2;
 #pragma unroll
-      for (int c = 0; c < 3; ++c) a0.r[c] = a1.r[c] = xr0.r[c] = xr1.r[c] = g0[c] = g1[c] = d0[c] = d1[c] = szP[c] = dgP[c] = z2;
+      for (int c = 0; c < 3; ++c) a0.r[c] = a1.r[c] = xr0.r[c] = xr1.r[c] = g0[c] = g1[c] = d0[c] = d1[c] = z2;
       ghzP[0] = ghzP[1] = z2;
 
       // a zero plane stands in for z = -1 (conv padding)
@@ -746,32 +774,27 @@ lastconv_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmS, const __grid_
       // the A plane of iteration ts must be in shared memory before iteration ts + 1 reads its neighbours: the iteration
       // publishes aN itself (end-of-iteration stores), so nothing to do here.
       const long long off = static_cast<long long>(base) + static_cast<long long>(ts) * plane3;
-      const float* pa = p.pot + (off + plane3);
-      const float* px = p.xt + off;
-      float* pv = p.vel ? p.vel + (off - plane3) : nullptr;
-      float* pd = p.dpot ? p.dpot + (off - 4LL * plane3) : nullptr;
+      FBCur cur{off};
       for (int t = ts; t <= te; t += 2) {
         float2 oU = z2, oV = z2, oW = z2;
-        fb_iter(t, p, T, slot, slot_sx, a0, a1, g0, g1, xr0, xr1, d0, d1, szP, dgP, ghzP, dzu, dzv, facc_l1, facc_j, pa, px,
-                pv, plane3, oU, oV, oW);
+        fb_iter(t, p, T, slot, slot_sx, a0, a1, g0, g1, xr0, xr1, d0, d1, ghzP, dzu, dzv, facc_l1, facc_j, cur,
+                plane3, oU, oV, oW);
         {
           const int r4 = t - 4;
           if (r4 >= T.zs && r4 < T.ze) {                      // uniform
             publish(T.outp, oU, oV, oW);
-            if (pd && T.own && r4 >= T.zo_s && r4 < T.zo_e) fb_st3(pd, oU, oV, oW);
+            if (p.dpot && T.own && r4 >= T.zo_s && r4 < T.zo_e) fb_st3(p.dpot + (cur.eo - 5LL * plane3), oU, oV, oW);   // eo: plane t+1
           }
-          if (pd) pd += plane3;
         }
         oU = oV = oW = z2;
-        fb_iter(t + 1, p, T, slot, slot_sx, a1, a0, g1, g0, xr1, xr0, d1, d0, szP, dgP, ghzP, dzu, dzv, facc_l1, facc_j, pa,
-                px, pv, plane3, oU, oV, oW);
+        fb_iter(t + 1, p, T, slot, slot_sx, a1, a0, g1, g0, xr1, xr0, d1, d0, ghzP, dzu, dzv, facc_l1, facc_j, cur,
+                plane3, oU, oV, oW);
         {
           const int r4 = t - 3;
           if (r4 >= T.zs && r4 < T.ze) {
             publish(T.outp, oU, oV, oW);
-            if (pd && T.own && r4 >= T.zo_s && r4 < T.zo_e) fb_st3(pd, oU, oV, oW);
+            if (p.dpot && T.own && r4 >= T.zo_s && r4 < T.zo_e) fb_st3(p.dpot + (cur.eo - 5LL * plane3), oU, oV, oW);
           }
-          if (pd) pd += plane3;
         }
       }
       // a zero plane stands in for z = D

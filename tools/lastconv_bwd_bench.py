@@ -68,13 +68,12 @@ def main():
     out = {"peak_gbs": peak, "cases": []}
     for name, shape in (("c4 128^3 B4", (4, 128, 128, 128)), ("c3 64^3 B16", (16, 64, 64, 64))):
         row = {"case": name}
-        for mode in ("fused", "pair"):
+        for mode in (("fused",) if "--fused-only" in sys.argv else ("fused", "pair")):
             t, gbs = run(shape, mode)
             row[mode] = {"ms": t * 1e3, "algorithmic_gbs": gbs, "frac_of_hbm_peak": gbs / peak}
         out["cases"].append(row)
-        print("%-12s fused %.3f ms (%.0f GB/s, %.2f of HBM)   pair %.3f ms (%.0f GB/s, %.2f)" % (
-            name, row["fused"]["ms"], row["fused"]["algorithmic_gbs"], row["fused"]["frac_of_hbm_peak"],
-            row["pair"]["ms"], row["pair"]["algorithmic_gbs"], row["pair"]["frac_of_hbm_peak"]))
+        print("%-12s " % name + "   ".join("%s %.3f ms (%.0f GB/s, %.3f of HBM)" % (
+            m, row[m]["ms"], row[m]["algorithmic_gbs"], row[m]["frac_of_hbm_peak"]) for m in ("fused", "pair") if m in row))
     if "--json" in sys.argv:
         json.dump(out, open(sys.argv[sys.argv.index("--json") + 1], "w"), indent=1)
 
