@@ -234,7 +234,7 @@ class AEEngine(object):
     with the reference's variable names (`AE/enc/...`, `AE/dec/...`)."""
 
     def __init__(self, batch, x_shape, filters=128, z_num=16, num_conv=4, repeat=0, name="AE", device=None, seed=123,
-                 use_sparse=False):
+                 use_sparse=False, params=None):
         self.device = device or torch.device("cuda", torch.cuda.current_device())
         self.use_sparse = bool(use_sparse)
         # build both tables first so they can share ONE flat buffer (one Adam launch / one all-reduce)
@@ -244,11 +244,17 @@ class AEEngine(object):
         tab = OrderedDict()
         tab.update(self.enc.table)
         tab.update(self.dec.params.table)
-        flat = FlatParams(tab, self.device)
-        for k in self.enc.table:
-            flat.p(k).copy_(self.enc.params.p(k))
-        for k in self.dec.params.table:
-            flat.p(k).copy_(self.dec.params.p(k))
+        if params is not None:        # reuse=True: the variables of an existing AE (same names and shapes)
+            missing = [k for k in tab if k not in params.table or tuple(params.table[k]) != tuple(tab[k])]
+            if missing:
+                raise ValueError("reuse: variable %s does not exist with this shape" % missing[0])
+            flat = params
+        else:
+            flat = FlatParams(tab, self.device)
+            for k in self.enc.table:
+                flat.p(k).copy_(self.enc.params.p(k))
+            for k in self.dec.params.table:
+                flat.p(k).copy_(self.dec.params.p(k))
         self.params = flat
         self.enc.params = flat
         self.dec.params = flat

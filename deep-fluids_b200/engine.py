@@ -78,7 +78,7 @@ class GeneratorEngine(object):
     """GeneratorBE / GeneratorBE3 (skip_concat=False) forward + backward on hand-written sm_100a kernels."""
 
     def __init__(self, batch, output_shape, z_dim=3, filters=128, num_conv=4, repeat=0, name="G", device=None,
-                 seed=123, init=None, inference=False):
+                 seed=123, init=None, inference=False, params=None):
         assert filters == 128, "the fused engine is specialised for filters=128 (config.py:21 default); other widths run ops_engine.OpsGeneratorEngine"
         self.device = device or torch.device("cuda", torch.cuda.current_device())
         self.B, self.name, self.filters, self.num_conv = int(batch), name, filters, int(num_conv)
@@ -107,8 +107,16 @@ class GeneratorEngine(object):
         self.last_name = "%s/%d_conv" % (name, n)
         tab[self.last_name + "/weights"] = (3,) * self.nd + (filters, self.cout)
         tab[self.last_name + "/biases"] = (self.cout,)
-        self.params = FlatParams(tab, self.device)
-        if init is not None:
+        if params is not None:      # tf.variable_scope(reuse=True): the SAME variables (a FlatParams holding every name of `tab`)
+            missing = [k for k in tab if k not in params.table or tuple(params.table[k]) != tuple(tab[k])]
+            if missing:
+                raise ValueError("reuse: variable %s does not exist with this shape" % missing[0])
+            self.params = params
+        else:
+            self.params = FlatParams(tab, self.device)
+        if params is not None:
+            pass
+        elif init is not None:
             self.params.load_state_dict(init)
         else:
             g = torch.Generator().manual_seed(seed)

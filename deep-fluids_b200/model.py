@@ -98,19 +98,40 @@ def _needs_ops_path(filters, skip_concat):
     return filters != 128 or bool(skip_concat)
 
 
+def _scope_engine(key, reuse, batch, build):
+    """tf.variable_scope(name, reuse=reuse) for the fused engines.  reuse=False (re)creates the scope's variables;
+    reuse=True must find them (TF: "Variable ... does not exist") and applies THE SAME variables: at the scope's own batch
+    size the scope's engine itself, at another batch size a sibling engine built over the same flat parameter buffer (no
+    copy -- an update of the variables, e.g. continued training or a checkpoint load, is seen by every sibling).  The bf16
+    tensor-core operands are re-packed from the live variables on every reuse call."""
+    eng = _ENGINES.get(key)
+    if not reuse:
+        eng = build(None)
+        _ENGINES[key] = eng
+        for k in [k for k in _ENGINES if len(k) == len(key) + 1 and k[:-1] == key and isinstance(k[-1], tuple)]:
+            del _ENGINES[k]                  # siblings of the replaced variables
+        return eng
+    if eng is None:
+        raise ValueError("Variable scope %r does not exist: reuse=True before the scope was built" % (key[0],))
+    B = getattr(eng, "B", None) or eng.enc.B
+    if B != batch:
+        sib = key + (("batch", int(batch)),)
+        if sib not in _ENGINES:
+            _ENGINES[sib] = build(eng.params)
+        eng = _ENGINES[sib]
+    eng.repack()
+    return eng
+
+
 def _generator(z, filters, output_shape, name, num_conv, conv_k, last_k, repeat, skip_concat, act, reuse, nd):
     assert conv_k == 3 and last_k == 3, "k=3 only (the reference never uses another size on this path)"
     assert act is lrelu
     assert len(output_shape) == nd + 1
     if _needs_ops_path(filters, skip_concat):
         return generator_ops(z, filters, list(output_shape), name, num_conv, conv_k, last_k, repeat, skip_concat, act, reuse)
-    key = (name, nd)
-    eng = _ENGINES.get(key)
-    if eng is None or not reuse or eng.B != z.shape[0]:
-        init = eng.params.state_dict() if (eng is not None and reuse) else None   # reuse=True shares the variables
-        eng = GeneratorEngine(z.shape[0], list(output_shape), z_dim=z.shape[1], filters=filters, num_conv=num_conv,
-                              repeat=repeat, name=name, device=z.device, init=init)
-        _ENGINES[key] = eng
+    eng = _scope_engine((name, nd), reuse, z.shape[0], lambda shared: GeneratorEngine(
+        z.shape[0], list(output_shape), z_dim=z.shape[1], filters=filters, num_conv=num_conv, repeat=repeat, name=name,
+        device=z.device, params=shared))
     out = eng.forward(z)
     return out, eng.variables
 
@@ -165,12 +186,8 @@ def _encoder(x, filters, z_num, name, num_conv, conv_k, repeat, act, reuse, nd):
     assert x.dim() == nd + 2, "x must be channels-last [B,(D,)H,W,C]"
     if _needs_ops_path(filters, False):
         return encoder_ops(x, filters, z_num, name, num_conv, conv_k, repeat, act, reuse)
-    key = (name, nd, "enc")
-    eng = _ENGINES.get(key)
-    if eng is None or not reuse or eng.B != x.shape[0]:
-        params = eng.params if (eng is not None and reuse and eng.B == x.shape[0]) else None
-        eng = EncoderEngine(x.shape[0], list(x.shape[1:]), filters, z_num, num_conv, repeat, name, x.device, params=params)
-        _ENGINES[key] = eng
+    eng = _scope_engine((name, nd, "enc"), reuse, x.shape[0], lambda shared: EncoderEngine(
+        x.shape[0], list(x.shape[1:]), filters, z_num, num_conv, repeat, name, x.device, params=shared))
     return eng.forward(x), eng.variables
 
 
@@ -189,11 +206,8 @@ def _ae(x, filters, z_num, name, num_conv, conv_k, last_k, repeat, act, skip_con
     assert x.dim() == nd + 2, "x must be channels-last [B,(D,)H,W,C]"
     if _needs_ops_path(filters, skip_concat):
         return ae_ops(x, filters, z_num, name, num_conv, conv_k, last_k, repeat, act, skip_concat, use_sparse, reuse)
-    key = (name, nd, "ae")
-    eng = _ENGINES.get(key)
-    if eng is None or not reuse or eng.enc.B != x.shape[0]:
-        eng = AEEngine(x.shape[0], list(x.shape[1:]), filters, z_num, num_conv, repeat, name, x.device, use_sparse=use_sparse)
-        _ENGINES[key] = eng
+    eng = _scope_engine((name, nd, "ae"), reuse, x.shape[0], lambda shared: AEEngine(
+        x.shape[0], list(x.shape[1:]), filters, z_num, num_conv, repeat, name, x.device, use_sparse=use_sparse, params=shared))
     out, z = eng.forward(x)          # z = Enc(x, num_conv - 1) (sigmoid if use_sparse); out = Gen(z, x.shape[1:], num_conv)
     return out, z, eng.variables
 

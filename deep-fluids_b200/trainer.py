@@ -598,15 +598,19 @@ class Trainer(object):
         if cls is None:                   # ops-level engine: the layer functions take any batch size
             self.test_engine = self.engine
             return
+        # the SAME variables (the engine's flat parameter buffer, not a snapshot): a sweep run after further training steps or
+        # after load() / load_tf() sees the current weights; its bf16 operands are re-packed before every sweep
         self.test_engine = cls(self.test_b_num, self.output_shape, z_dim=self.c_num, filters=self.filters,
                                num_conv=self.num_conv, repeat=self.repeat, name="G", device=self.device,
-                               init=self.engine.params.state_dict(), inference=True)
+                               params=self.engine.params, inference=True)
 
     def generate_velocity(self, z):
         """G_ = curl(G_s(z)) for parameters z [n, c_num], n a multiple of test_b_num or <= it (sess.run(self.G_, {z}))."""
         if not hasattr(self, "test_engine"):
             self.build_test_model()
         z = torch.as_tensor(z, dtype=torch.float32, device=self.device)
+        if self.test_engine is not self.engine:
+            self.test_engine.repack()
         outs = []
         for b0 in range(0, z.shape[0], self.test_b_num):
             zb = z[b0:b0 + self.test_b_num]

@@ -262,3 +262,18 @@ def test_numpy_twins_match_the_oracle():
     j, c = O.jacobian_np3(x3)
     jr, cr = R.jacobian3(torch.from_numpy(x3))
     assert np.array_equal(j, jr.numpy()) and np.array_equal(c, cr.numpy())
+
+
+def test_fused_engine_scopes_raise_on_reuse_before_creation():
+    """tf.variable_scope(reuse=True) on variables that do not exist raises in TF; the fused-engine scopes do the same instead
+    of silently building fresh seed-123 weights (no CUDA call is reached)"""
+    import pytest
+    import torch
+    from deepfluids_b200 import model as M
+    M.reset()
+    with pytest.raises(ValueError):
+        M.GeneratorBE(torch.zeros(2, 3), 128, [32, 48, 1], reuse=True)
+    with pytest.raises(ValueError):
+        M.EncoderBE3(torch.zeros(2, 16, 16, 16, 3), 128, 16, reuse=True)
+    with pytest.raises(ValueError):
+        M.AE(torch.zeros(2, 32, 48, 2), 128, 16, reuse=True)

@@ -140,6 +140,15 @@ def test_inference_path_matches_training_forward(tmp_path):
     vel_train = K.curl_fwd(tr.engine.forward(y)).clone()
     vel_test = tr.generate_velocity(y)
     assert torch.equal(vel_train, vel_test)
+    # the forward-only engine applies the LIVE variables (tf reuse=True), not a snapshot taken when it was built: after
+    # further optimizer steps a sweep still equals the training engine's forward
+    assert tr.test_engine.params is tr.engine.params
+    tr.train_step()
+    tr.train_step()
+    torch.cuda.synchronize()
+    vel_train2 = K.curl_fwd(tr.engine.forward(y)).clone()
+    assert not torch.equal(vel_train2, vel_train)
+    assert torch.equal(tr.generate_velocity(y), vel_train2)
     out_dir = tr.test_()
     d = np.load(out_dir + "/199.npz")["x"]
     assert d.shape == (32, 24, 2) and np.isfinite(d).all()
