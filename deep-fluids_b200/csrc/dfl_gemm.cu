@@ -4,7 +4,8 @@
 // on the channel-blocked concat tensor (dfl_enc_fc_*), and -- at the ops level / in the latent-space MLP of arch=nn
 // (model.py:218-224: linear 2*filters, linear filters, linear onum) -- plain [B,K] x [K,N] products of any size.  Those are
 // tiny (<= 1024 x 1024 x batch) and far from any roofline that matters for the step; this is a plain 64x64x16 shared-memory
-// tiled SIMT kernel, fp32 FMA in the reference's arithmetic type, with split-K (atomics) when M*N alone cannot fill the chip.
+// tiled SIMT kernel, fp32 FMA in the reference's arithmetic type, with split-K (atomics) when M*N alone cannot fill the chip
+// (not in deterministic mode, dfl_set_deterministic: one CTA per output tile walks all of K in order).
 //   C[M,N] = op(A)[M,K] * op(B)[K,N] (+ bias[N]) (+ C if accumulate)
 //   A: row-major [M,K], or [K,M] when transA;  B: row-major [K,N], or [N,K] when transB.
 #include "dfl_common.cuh"
@@ -62,7 +63,9 @@ int gemm_f32(const float* A, const float* B, const float* bias, float* C, int M,
   const long long sam = transA ? 1 : K, sak = transA ? M : 1, sbk = transB ? 1 : N, sbn = transB ? K : 1;
   const int gx = (N + GT - 1) / GT, gy = (M + GT - 1) / GT;
   int nsplit = 1;
-  if (gx * gy < num_sms() && K >= 4096) nsplit = std::min((K + 2047) / 2048, std::max(1, 2 * num_sms() / (gx * gy)));
+  size_t det_bytes = 0;
+  const bool det = deterministic_workspace(&det_bytes) != nullptr;     // dfl_set_deterministic: no atomics -> no split-K
+  if (!det && gx * gy < num_sms() && K >= 4096) nsplit = std::min((K + 2047) / 2048, std::max(1, 2 * num_sms() / (gx * gy)));
   int kchunk = ((K + nsplit - 1) / nsplit + GK - 1) / GK * GK;
   nsplit = (K + kchunk - 1) / kchunk;
   if (nsplit > 1 && !accumulate) DFL_CUDA_OK(cudaMemsetAsync(C, 0, static_cast<size_t>(M) * N * sizeof(float), st));

@@ -224,3 +224,24 @@ def test_autoencoder_training_runs_are_bit_reproducible(monkeypatch, is_3d):
         assert torch.equal(finals[0], finals[1])
     finally:
         K.set_deterministic(False)
+
+
+def test_gemm_f32_split_k_is_off_in_deterministic_mode():
+    """dfl_gemm_f32 splits K over atomics when M x N cannot fill the chip (the ops-level encoder FC: [B, 36 864+] x [.., 16]); under
+    dfl_set_deterministic one CTA per output tile walks K in order: repeated launches are bit-identical and equal to the split
+    result to fp32 summation accuracy"""
+    from deepfluids_b200 import kernels as K
+    g = torch.Generator().manual_seed(5)
+    a = torch.randn(8, 36864, generator=g).to(dev())
+    b = (torch.randn(36864, 16, generator=g) * 0.01).to(dev())
+    bias = torch.randn(16, generator=g).to(dev())
+    ref = (a.double() @ b.double() + bias.double()).float()
+    split = K.gemm(a, b, bias)
+    K.set_deterministic(True, dev())
+    try:
+        outs = [K.gemm(a, b, bias).clone() for _ in range(3)]
+    finally:
+        K.set_deterministic(False)
+    assert torch.equal(outs[0], outs[1]) and torch.equal(outs[0], outs[2])
+    assert float((outs[0] - ref).abs().max()) <= 1e-4 * float(ref.abs().max())
+    assert float((split - ref).abs().max()) <= 1e-4 * float(ref.abs().max())
