@@ -30,12 +30,18 @@
 
 namespace dfl {
 
-// Measured and NOT adopted (4 x 128^3, same box, tools/fused_ab.sh; baseline 2.05-2.13 ms): mask loads with L1::no_allocate
+// Measured and NOT adopted (4 x 128^3, same box, tools/fused_ab.sh; baseline 2.05-2.13 ms, all BEFORE the stencil warps'
+// spill-free loop and the L2 prefetch of the mask lines went in): mask loads with L1::no_allocate
 // 2.34 ms; the builder warps' mask pieces staged by cp.async two rounds ahead 2.08 ms; two register sets of mask pieces per
 // store thread 2.40-2.49 ms (ptxas tracks every mask LDG of the loop on ONE scoreboard, so waiting for the older set also
 // waits for the newer); TMEM base re-read from shared memory instead of its spill reload 2.05 ms; both image reads of a
 // store pass before its first store 2.08 ms.  The long-scoreboard samples ncu shows on the store warps' mask loads are slack,
-// not the critical path.  Adopted: the stencil warps' spill-free state (below), 2.00-2.02 ms.
+// not the critical path while the stencil warps are.  Adopted: the stencil warps' spill-free state (below), 2.00-2.02 ms, then
+// the L2 prefetch of the next tile's mask lines (fb_prefetch_mask), 1.70 ms.
+
+#ifndef FB_MASK_L2PF
+#define FB_MASK_L2PF 1         // store warps: prefetch.global.L2 of the NEXT tile's mask lines (0 = A/B build without it)
+#endif
 
 constexpr int FB_THREADS = 512;
 constexpr int FB_ST_WARP0 = 10;
@@ -346,8 +352,21 @@ __device__ __forceinline__ void fb_load_mask(const FusedBwdParams& p, const FBSt
       m[q] = __ldg(reinterpret_cast<const uint4*>(p.mask_src + (t0 + static_cast<size_t>(ly) * p.W + lx) * 128 + hh * 32 + L.piece * 8));
   }
 }
-// (Measured and dropped: a prefetch.global.L2 of the next tile's operand lines a whole tile ahead -- 2.05 vs 2.05 ms at
-// 4 x 128^3; the long-scoreboard stalls ncu shows on these warps are not what bounds the kernel.)
+// L2 prefetch of the 128-byte mask line that this lane's pieces of rounds hh and hh + 1 live in, one tile (= one plane of the
+// tile column) ahead: the register-landed mask loads of the next tile then hit L2 (~800 clocks) instead of DRAM under load
+// (~2 600 clocks, longer than a round, which the one-round-ahead request cannot hide).  1.99-2.00 -> 1.70 ms at 4 x 128^3
+// (0.67 -> 0.79 of the measured HBM peak), 1.02 -> 0.89 ms at 16 x 64^3 (profiles/r02b_fused_ab.txt, batch ab4).  Order matters:
+// the same prefetch was measured BEFORE the stencil warps' spill reloads were removed and did nothing (2.05 vs 2.05 ms) --
+// at that time the stencil warps were the critical path and the store warps' mask wait was slack.
+__device__ __forceinline__ void fb_prefetch_mask(const FusedBwdParams& p, const FBStoreLane L, size_t t0, int tx0, int y0, int hh,
+                                                 int it0) {
+#pragma unroll
+  for (int q = 0; q < 2; ++q) {
+    const int rr_ = (it0 + q) * 32 + L.prow, ly = rr_ >> 4, lx = rr_ & 15;
+    if (p.ds_masked && L.piece == 0 && tx0 + lx < p.W && y0 + ly < p.H)
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(p.mask_src + (t0 + static_cast<size_t>(ly) * p.W + lx) * 128 + hh * 32));
+  }
+}
 __device__ __forceinline__ void fb_store_passes(const FusedBwdParams& p, const FBStoreLane L, uint32_t sTa, size_t tile0, int tx0,
                                                 int y0, int h, int it0, const uint4 (&mv)[2]) {
 #pragma unroll
@@ -530,6 +549,9 @@ lastconv_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmS, const __grid_
         for (int h = 0; h < 4; ++h) {
           uint4 mv[2];
           mv[0] = mvn[0]; mv[1] = mvn[1];
+#if FB_MASK_L2PF
+          if (!(h & 1) && z + 1 < sg.ze) fb_prefetch_mask(p, L, tile0 + plane_vox, tx0, y0, h, 0);
+#endif
           if (h < 3) fb_load_mask(p, L, tile0, tx0, y0, h + 1, 0, mvn);
           else if (z + 1 < sg.ze) fb_load_mask(p, L, tile0 + plane_vox, tx0, y0, 0, 0, mvn);
           const uint32_t sTa = sT0 + (h & 1) * (128 * 64);     // alternating images
@@ -670,6 +692,9 @@ lastconv_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmS, const __grid_
         for (int h = 0; h < 4; ++h) {
           uint4 mv[2];
           mv[0] = mvn[0]; mv[1] = mvn[1];
+#if FB_MASK_L2PF
+          if (!(h & 1) && z + 1 < sg.ze) fb_prefetch_mask(p, L, tile0 + plane_vox, tx0, y0, h, 2);
+#endif
           if (h < 3) fb_load_mask(p, L, tile0, tx0, y0, h + 1, 2, mvn);
           else if (z + 1 < sg.ze) fb_load_mask(p, L, tile0 + plane_vox, tx0, y0, 0, 2, mvn);
           fb_bar_sync(FB_BAR_READY + (h & 1), 128 + FB_BUILD);

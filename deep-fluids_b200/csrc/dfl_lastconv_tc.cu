@@ -207,6 +207,25 @@ lastconv_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmS, LastBwdParams p)
       const int b = r / p.D;
       const size_t pos0 = ((static_cast<size_t>(b) * p.D + z) * p.H + y0) * p.W + x;    // row (ly = 0, lx = px) of the tile
       const uint32_t s = i & 1, ph = (i >> 1) & 1;
+      // L2 prefetch of the NEXT tile's mask lines (256 lines of 128 bytes; the lanes with piece 0 issue them): the mask pieces
+      // below are requested only a transposition ahead of their use, which hides an L2 hit but not a DRAM round trip under
+      // load (same finding as in the fused 3D kernel, dfl_lastconv_bwd_fused.cu: fb_prefetch_mask)
+      if (p.ds_masked && piece == 0 && tile + static_cast<int>(gridDim.x) < p.ntiles) {
+        int rn = tile + static_cast<int>(gridDim.x);
+        const int xn = (rn % p.tx) * 16 + px; rn /= p.tx;
+        const int yn = (rn % p.ty) * 8; rn /= p.ty;
+        const int zn = rn % p.D;
+        const int bn = rn / p.D;
+        if (xn < p.W) {
+          const __nv_bfloat16* m0 = p.mask_src + (((static_cast<size_t>(bn) * p.D + zn) * p.H + yn) * p.W + xn) * 128;
+#pragma unroll
+          for (int it = 0; it < 8; ++it)
+            if (yn + it < p.H) {
+              asm volatile("prefetch.global.L2 [%0];" ::"l"(m0 + static_cast<size_t>(it) * p.W * 128));
+              asm volatile("prefetch.global.L2 [%0];" ::"l"(m0 + static_cast<size_t>(it) * p.W * 128 + 64));
+            }
+        }
+      }
       mbar_wait(&d1_full[s], ph);
       tc_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + s * 128;
