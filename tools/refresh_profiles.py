@@ -91,9 +91,8 @@ def main():
                   m.get("sm__inst_executed.avg.per_cycle_elapsed"), m.get("smsp__issue_active.avg.pct_of_peak_sustained_active")),
               "warp stall reasons (warps stalled per issue-active cycle):"]
     lines += ["   %-28s %.2f" % (n, v) for v, n in stalls[:8]]
-    lines += ["", "reading: neither DRAM nor the tensor pipe nor the issue slots are saturated; one epilogue warp per scheduler walks a "
-              "dependent", "TMEM-load -> pack -> st.shared -> hand-over -> ld.shared -> select -> st.global chain (DESIGN.md 4d).  "
-              "CUDA-event time of the same", "launch outside the profiler: %s_final_lastconv_bwd_bench.json." % rnd]
+    lines += ["", "reading: DESIGN.md 4d (per-role accounting of the source page: profiles/r02b_ncu_fused_roles.txt; A/B of the variants:",
+              "profiles/r02b_fused_ab.txt).  CUDA-event time of the same launch outside the profiler: %s_final_lastconv_bwd_bench.json." % rnd]
     open(os.path.join(dst, "%s_ncu_lastconv_bwd_fused.txt" % rnd), "w").write("\n".join(lines) + "\n")
     for f in sorted(os.listdir(src)):
         if f.startswith("bench_") and f.endswith(".json"):
