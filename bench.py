@@ -419,6 +419,43 @@ def run_gpu_arm(args):
             "bound": "hbm", "achieved": fb_b / fb_t / 1e9, "unit": "GB/s", "frac": fb_b / fb_t / 1e9 / peaks["hbm_gbs"],
             "algorithmic_bytes_per_voxel": 1048 if cfg.is_3d else 1036, "avg_launch_ms": fb_t / fb_n * 1e3,
             "share_of_step": fb_t / 2 * accum / (ms_per_step * 1e-3)}
+        if cfg.is_3d:
+            # The same kernel timed ALONE on the step's own tensors (outside the timed region, L2 flushed between launches): inside
+            # the power-capped step the SM clock is ~1.5 GHz and this kernel's time scales with it, so the in-step figure above and
+            # this one bracket it (tools/lastconv_bwd_bench.py measures the same thing on synthetic tensors).
+            try:
+                fa = tr._fused_args(bm._pool[0][0])
+                top, nc = eng_.rep - 1, eng_.num_conv
+                P_ = eng_.params
+                flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+                torch.cuda.synchronize()
+                time.sleep(1.5)                  # leave the power-capped state of the step: "alone" means at the boost clock
+                K.PROF.events = []
+                sa_mhz = []
+                for _ in range(6):
+                    flush.zero_()
+                    K.lastconv_curl_loss_bwd(eng_.s, eng_.pot, fa["x"], P_.p(eng_.last_name + "/weights"), eng_.y[top][nc - 1],
+                                             eng_._gview(0, top), eng_._gview(1, top), P_.g(eng_.last_name + "/weights"),
+                                             P_.g(eng_.last_name + "/biases"), fa["loss3"], fa["workspace"], fa["w1"], fa["w2"], 1.0)
+                    torch.cuda.synchronize()
+                    try:
+                        sa_mhz.append(int(torch.cuda.clock_rate(dev)))
+                    except Exception:
+                        pass
+                    time.sleep(0.05)
+                ev = [(s_.elapsed_time(e_) * 1e-3, w_) for n_, s_, e_, w_, _ in K.PROF.events if n_ == "lastconv_bwd_fused"][1:]
+                K.PROF.events = None
+                del flush
+                sa_t, sa_b = sum(t for t, _ in ev), sum(w_ for _, w_ in ev)
+                roofline["others"]["lastconv_bwd_fused_kernel"]["standalone"] = {
+                    "measured": "the same kernel on the step's own tensors, timed alone after the timed region (1.5 s idle first, "
+                                "one launch at a time, L2 flushed between launches): SM clock not held down by the step's power cap",
+                    "sm_mhz_after_launch": sa_mhz[1:],
+                    "avg_launch_ms": sa_t / len(ev) * 1e3, "achieved": sa_b / sa_t / 1e9, "unit": "GB/s",
+                    "frac": sa_b / sa_t / 1e9 / peaks["hbm_gbs"]}
+            except Exception as ex:      # a diagnostic extra must never cost the bench line
+                K.PROF.events = None
+                roofline["others"]["lastconv_bwd_fused_kernel"]["standalone"] = {"error": repr(ex)[:200]}
     roofline["kernel_ms"] = kernel_ms
     fl = FLOPS_PER_FIELD[args.workload]
     if fl:
