@@ -201,8 +201,8 @@ int dfl_phase_wgrad_fold(const float* t_scratch, float* dw, int ndim, int cin, i
  * to dw / db in slab order: two runs on the same inputs then give bit-identical gradients.  The launches that use the
  * workspace must not overlap each other (one stream).  dfl_set_deterministic(NULL, 0) restores the atomic reduction.
  * The 128 -> 1..3 output conv's dW / db (dfl_lastconv_bwd, dfl_lastconv_curl_loss_bwd) follow the same switch (per-CTA
- * slots, added in CTA order), so a whole generator train step is reproducible.  Still order-dependent: the split-K fp32
- * atomics of dfl_enc_fc_fwd (auto-encoder) and of dfl_gemm_f32. */
+ * slots, added in CTA order), and so do dfl_enc_fc_fwd (per-block partial sums, added in block order by a second launch) and
+ * dfl_gemm_f32 (no split-K in this mode): whole generator and auto-encoder train steps are reproducible bit for bit. */
 size_t dfl_deterministic_workspace_bytes(void);
 int dfl_set_deterministic(void* workspace, size_t bytes);
 /* coarse[b,(z,)y,x,:] = fine[b,(2z,)2y,2x,:] (bf16, 128 channels): the coarse source s of an up-sampled tensor upscale(s) */
