@@ -277,3 +277,34 @@ def test_fused_engine_scopes_raise_on_reuse_before_creation():
         M.EncoderBE3(torch.zeros(2, 16, 16, 16, 3), 128, 16, reuse=True)
     with pytest.raises(ValueError):
         M.AE(torch.zeros(2, 32, 48, 2), 128, 16, reuse=True)
+
+
+def test_scope_engine_reuse_rules_on_fake_engines():
+    """host logic of model._scope_engine (no CUDA): reuse=False replaces the scope's variables and drops their siblings;
+    reuse=True at the scope's batch size returns the scope's engine, at another batch size ONE sibling built over the same
+    parameter object; every reuse call re-packs the operands"""
+    from deepfluids_b200 import model as M
+    M.reset()
+    built = []
+
+    class Fake(object):
+        def __init__(self, B, params):
+            self.B, self.params, self.repacks = B, params if params is not None else object(), 0
+            built.append(self)
+
+        def repack(self):
+            self.repacks += 1
+
+    key = ("G", 2)
+    e4 = M._scope_engine(key, False, 4, lambda shared: Fake(4, shared))
+    assert M._scope_engine(key, True, 4, lambda shared: Fake(4, shared)) is e4 and e4.repacks == 1 and len(built) == 1
+    e2 = M._scope_engine(key, True, 2, lambda shared: Fake(2, shared))
+    assert e2 is not e4 and e2.params is e4.params and e2.repacks == 1
+    assert M._scope_engine(key, True, 2, lambda shared: Fake(2, shared)) is e2 and len(built) == 2 and e2.repacks == 2
+    # an encoder scope of the same name is a different scope, not a sibling
+    enc = M._scope_engine(("G", 2, "enc"), False, 4, lambda shared: Fake(4, shared))
+    assert M._ENGINES[("G", 2, ("batch", 2))] is e2
+    # re-creating the scope drops the siblings of the old variables, keeps the other scope
+    n4 = M._scope_engine(key, False, 4, lambda shared: Fake(4, shared))
+    assert n4 is not e4 and ("G", 2, ("batch", 2)) not in M._ENGINES and M._ENGINES[("G", 2, "enc")] is enc
+    M.reset()
